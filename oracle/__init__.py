@@ -1,0 +1,269 @@
+"""TEST INFRASTRUCTURE ONLY -- the CPU oracle for the neurec_b200 hot path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package.  The product (``neurec_b200``) never
+does; it raises when its CUDA library is missing instead of falling back to anything here.
+
+Three things live here:
+
+* ``neurec_oracle.c``  -- plain-C restatement of the reference's compiled path
+  (evaluator, metrics, libstdc++ partial_sort_copy tie order, libc-rand sampler).
+* ``tf_math.py``       -- numpy fp32 restatement of the TF-1.12 graphs (MF/BPR, pointwise,
+  MLP/NeuMF, LightGCN, NGCF propagation) and of the TF optimizers.
+* ``_ref/``            -- the REAL reference: its C++ headers and .pyx files compiled from
+  where they lie under /root/reference by ``oracle/Makefile`` (``make ref``).  Used to pin
+  the restatements and, in bench.py, as the ``"kind": "reference"`` CPU baseline.
+
+Parity status: pinned (see the header of neurec_oracle.c and tests/test_oracle.py).
+"""
+from __future__ import annotations
+
+import ctypes
+import importlib.abc
+import importlib.util
+import os
+import subprocess
+import sys
+import sysconfig
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_ROOT = os.environ.get("NRC_REFERENCE_ROOT", "/root/reference")
+_EXT = sysconfig.get_config_var("EXT_SUFFIX")
+
+_c_f32p = ctypes.POINTER(ctypes.c_float)
+_c_i32p = ctypes.POINTER(ctypes.c_int32)
+_c_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+def build(ref: bool = True) -> None:
+    """Compile the C restatement and (when /root/reference exists) oracle/_ref."""
+    targets = ["oracle"] + (["ref"] if ref else [])
+    subprocess.run(["make", "-s", "-C", HERE, f"REF={REF_ROOT}"] + targets, check=True)
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(_c_f32p)
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(_c_i32p)
+
+
+def _i64(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, a.ctypes.data_as(_c_i64p)
+
+
+_LIB = None
+
+
+def lib() -> ctypes.CDLL:
+    """ctypes handle of the C restatement (builds it on first use when missing)."""
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(HERE, "_build", "libneurec_oracle.so")
+        if not os.path.isfile(path):
+            build(ref=False)
+        L = ctypes.CDLL(path)
+        L.orc_llrand.restype = ctypes.c_ulonglong
+        _LIB = L
+    return _LIB
+
+
+_REF = False
+
+
+def ref_lib():
+    """ctypes handle of the compiled reference headers, or None when not built."""
+    global _REF
+    if _REF is False:
+        path = os.path.join(HERE, "_ref", "libneurec_ref.so")
+        _REF = ctypes.CDLL(path) if os.path.isfile(path) else None
+    return _REF
+
+
+# ----------------------------------------------------------------------------------------
+# numpy-facing wrappers
+# ----------------------------------------------------------------------------------------
+METRIC_IDS = {"Precision": 1, "Recall": 2, "MAP": 3, "NDCG": 4, "MRR": 5}
+
+
+def dict_to_csr(d, num_rows):
+    """{row: [sorted ints]} -> (indptr int64[num_rows+1], indices int32)."""
+    indptr = np.zeros(num_rows + 1, dtype=np.int64)
+    for u, items in d.items():
+        indptr[u + 1] = len(items)
+    indptr = np.cumsum(indptr)
+    indices = np.empty(int(indptr[-1]), dtype=np.int32)
+    for u, items in d.items():
+        indices[indptr[u]:indptr[u + 1]] = np.sort(np.asarray(list(items), dtype=np.int32))
+    return indptr, indices
+
+
+def lists_to_csr(rows):
+    """[iterable of ints per row] -> CSR with sorted, duplicate-free rows."""
+    rows = [np.unique(np.asarray(list(r), dtype=np.int32)) for r in rows]
+    indptr = np.zeros(len(rows) + 1, dtype=np.int64)
+    indptr[1:] = np.cumsum([len(r) for r in rows])
+    indices = np.concatenate(rows).astype(np.int32) if rows else np.zeros(0, np.int32)
+    return indptr, indices
+
+
+def evaluate_matrix(scores, test_indptr, test_indices, metric, top_k, thread_num=1,
+                    return_ranks=False, impl="oracle"):
+    """eval_score_matrix (cpp_evaluator.pyx:28-42) on the C restatement (impl="oracle") or
+    on the real reference headers (impl="reference")."""
+    scores, sp = _f32(scores)
+    B, N = scores.shape
+    test_indptr, ip = _i64(test_indptr)
+    test_indices, xp = _i32(test_indices)
+    metric, mp = _i32(metric)
+    out = np.zeros((B, len(metric) * top_k), dtype=np.float32)
+    if impl == "reference":
+        R = ref_lib()
+        if R is None:
+            raise RuntimeError("oracle/_ref is not built")
+        R.ref_cpp_evaluate_matrix(sp, ctypes.c_int(N), ctypes.c_int(B), ip, xp, mp,
+                                  ctypes.c_int(len(metric)), ctypes.c_int(top_k),
+                                  ctypes.c_int(thread_num), out.ctypes.data_as(_c_f32p))
+        return out
+    ranks = np.zeros((B, top_k), dtype=np.int32)
+    rc = lib().orc_evaluate_matrix(sp, ctypes.c_int(N), ctypes.c_int(B), ip, xp, mp,
+                                   ctypes.c_int(len(metric)), ctypes.c_int(top_k),
+                                   ctypes.c_int(thread_num), out.ctypes.data_as(_c_f32p),
+                                   ranks.ctypes.data_as(_c_i32p))
+    if rc:
+        raise ValueError("unknown metric id")
+    return (out, ranks) if return_ranks else out
+
+
+def arg_topk(scores, top_k, thread_num=1, impl="oracle"):
+    """arg_topk (arg_topk.pyx:16-35)."""
+    scores, sp = _f32(scores)
+    U, N = scores.shape
+    out = np.zeros((U, top_k), dtype=np.int32)
+    if impl == "reference":
+        ref_lib().ref_arg_top_k_2d(sp, ctypes.c_int(N), ctypes.c_int(U), ctypes.c_int(top_k),
+                                   ctypes.c_int(thread_num), out.ctypes.data_as(_c_i32p))
+    else:
+        lib().orc_arg_topk_2d(sp, ctypes.c_int(N), ctypes.c_int(U), ctypes.c_int(top_k),
+                              ctypes.c_int(thread_num), out.ctypes.data_as(_c_i32p))
+    return out
+
+
+def mf_scores(U, V, users, thread_num=1):
+    """fp32 FMA-chain scores [len(users), num_items] (the oracle's definition of predict)."""
+    U, up = _f32(U)
+    V, vp = _f32(V)
+    users, usp = _i32(users)
+    out = np.empty((len(users), V.shape[0]), dtype=np.float32)
+    lib().orc_mf_scores(up, vp, usp, ctypes.c_int(len(users)), ctypes.c_int(V.shape[0]),
+                        ctypes.c_int(V.shape[1]), ctypes.c_int(thread_num),
+                        out.ctypes.data_as(_c_f32p))
+    return out
+
+
+def mask_train(scores, users, train_indptr, train_indices):
+    """In place: scores[b, train(users[b])] = -inf (uni_evaluator.py:140-143)."""
+    assert scores.dtype == np.float32 and scores.flags.c_contiguous
+    users, usp = _i32(users)
+    train_indptr, ip = _i64(train_indptr)
+    train_indices, xp = _i32(train_indices)
+    lib().orc_mask_train(scores.ctypes.data_as(_c_f32p), usp, ctypes.c_int(len(users)),
+                         ctypes.c_int(scores.shape[1]), ip, xp)
+    return scores
+
+
+def eval_mf(U, V, users, train_indptr, train_indices, test_indptr_b, test_indices_b, metric,
+            top_k, thread_num=1, return_ranks=False):
+    """predict -> mask -> eval for one batch of users; test CSR is per batch row."""
+    s = mf_scores(U, V, users, thread_num)
+    mask_train(s, users, train_indptr, train_indices)
+    return evaluate_matrix(s, test_indptr_b, test_indices_b, metric, top_k, thread_num,
+                           return_ranks=return_ranks)
+
+
+def batch_randint_choice(high, sizes, replace=True, exclusion_csr=None):
+    """batch_randint_choice (random_choice.pyx:64-89) on glibc rand(); flat int32 result."""
+    sizes, sp = _i32(sizes)
+    out = np.empty(int(sizes.sum()), dtype=np.int32)
+    if exclusion_csr is not None:
+        ei, eip = _i64(exclusion_csr[0])
+        ex, exp_ = _i32(exclusion_csr[1])
+    else:
+        eip, exp_ = None, None
+    rc = lib().orc_batch_randint_choice(ctypes.c_int(high), sp, ctypes.c_int(len(sizes)),
+                                        ctypes.c_int(1 if replace else 0), eip, exp_,
+                                        out.ctypes.data_as(_c_i32p))
+    if rc:
+        raise ValueError({-1: "'size' must be a positive integer.",
+                          -2: "The number of 'exclusion' is greater than 'high'.",
+                          -3: "There is not enough integers to be sampled."}[rc])
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# Importing the REAL Python reference (build container only; never on the GPU box)
+# ----------------------------------------------------------------------------------------
+_REF_EXT = {
+    "util.cython.random_choice": "random_choice",
+    "util.cython.tools": "tools",
+    "util.cython.arg_topk": "arg_topk",
+    "evaluator.backend.cpp.cpp_evaluator": "cpp_evaluator",
+}
+
+
+class _RefExtFinder(importlib.abc.MetaPathFinder):
+    """Resolves the reference's four Cython extension modules to oracle/_ref/*.so."""
+
+    def find_spec(self, fullname, path, target=None):
+        stem = _REF_EXT.get(fullname)
+        if stem is None:
+            return None
+        so = os.path.join(HERE, "_ref", stem + _EXT)
+        if not os.path.isfile(so):
+            return None
+        return importlib.util.spec_from_file_location(fullname, so)
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "main.py")) and \
+        os.path.isfile(os.path.join(HERE, "_ref", "cpp_evaluator" + _EXT))
+
+
+def import_reference(scratch="/tmp/nrc_ref_cwd"):
+    """Make ``import util / data / evaluator`` resolve to the unmodified reference.
+
+    Two shims: a stub ``tensorflow`` module (TF 1.12 is not
+    installable here; only TF-free pieces are used) and ``collections.Iterable``.
+    A scratch working directory holds symlinks to NeuRec.properties, conf/ and the dataset
+    files so the reference can write its split cache and logs without touching
+    /root/reference.  Returns the scratch directory (the caller should chdir into it).
+    """
+    if not reference_available():
+        raise RuntimeError("reference or oracle/_ref not available")
+    import collections
+    import collections.abc
+    if not hasattr(collections, "Iterable"):
+        collections.Iterable = collections.abc.Iterable
+    if "tensorflow" not in sys.modules:
+        sys.modules["tensorflow"] = types.ModuleType("tensorflow")
+    if not any(isinstance(f, _RefExtFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefExtFinder())
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    os.makedirs(os.path.join(scratch, "dataset"), exist_ok=True)
+    for name in ("NeuRec.properties", "conf"):
+        dst = os.path.join(scratch, name)
+        if not os.path.lexists(dst):
+            os.symlink(os.path.join(REF_ROOT, name), dst)
+    for name in os.listdir(os.path.join(REF_ROOT, "dataset")):
+        dst = os.path.join(scratch, "dataset", name)
+        if not os.path.lexists(dst):
+            os.symlink(os.path.join(REF_ROOT, "dataset", name), dst)
+    return scratch

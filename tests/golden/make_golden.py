@@ -1,0 +1,192 @@
+"""Generates tests/golden/*.npz|json by running the UNMODIFIED reference in this container.
+
+Run from the repo root:  ``python tests/golden/make_golden.py``  (needs /root/reference and
+``make -C oracle ref``).  The fixtures are committed; the GPU box never runs this script and
+never reads /root/reference.
+
+What is captured (all from the real reference code, imported through oracle.import_reference):
+  kat_sampler.json    randint_choice / batch_randint_choice first outputs in a FRESH process
+                      (glibc rand(), seed 1) + the first negatives of a PairwiseSampler epoch.
+  kat_evaluator.npz   eval_score_matrix and arg_topk on random and tie-heavy score matrices.
+  ml100k_split.npz    the ratio-0.8 split of ml-100k made by data.Dataset under
+                      np.random.seed(2018) (train/test CSR, int16 item ids).
+  kat_ml100k_eval.json  ProxyEvaluator.evaluate() strings on that split for random tables
+                      (predict = np.matmul, exactly MF.py:120-122), topk=[10,20] and topk=5,
+                      plus a user-subset (group) run.
+  kat_surface.json    Configurator / DataIterator / sampler / metrics_info surface behaviour.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def fresh(code: str) -> str:
+    """Run `code` in a fresh interpreter with the reference importable; return stdout."""
+    pre = ("import sys, os, json; sys.path.insert(0, %r); import oracle; "
+           "cwd = oracle.import_reference(); os.chdir(cwd); sys.argv=['main.py']\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", pre + code], capture_output=True, text=True,
+                       check=True)
+    return r.stdout
+
+
+def kat_sampler():
+    out = {}
+    out["a"] = json.loads(fresh(
+        "from util.cython.random_choice import randint_choice, batch_randint_choice\n"
+        "a = randint_choice(100, size=5, exclusion=[1,2,3])\n"
+        "b = randint_choice(40981, size=4)\n"
+        "print(json.dumps({'a': list(a), 'b': list(b)}))").strip().splitlines()[-1])
+    out["b"] = json.loads(fresh(
+        "from util.cython.random_choice import randint_choice, batch_randint_choice\n"
+        "a = randint_choice(100, size=5, exclusion=[1,2,3])\n"
+        "c = batch_randint_choice(1682, [3,2], replace=True, exclusion=[[0,1],[5]])\n"
+        "d = randint_choice(50, size=1, exclusion=list(range(40)))\n"
+        "e = randint_choice(30, size=10, replace=False, exclusion=[0,1,2])\n"
+        "print(json.dumps({'a': list(a), 'c': [list(x) for x in c], 'd': int(d), 'e': list(e)}))"
+    ).strip().splitlines()[-1])
+    # first negatives of a real PairwiseSampler epoch on the ml-100k split (fresh process)
+    out["pairwise"] = json.loads(fresh(
+        "import numpy as np, random\n"
+        "np.random.seed(2018); random.seed(2018)\n"
+        "from util import Configurator\n"
+        "from data.dataset import Dataset\n"
+        "from data import PairwiseSampler, PointwiseSampler\n"
+        "conf = Configurator('NeuRec.properties', default_section='hyperparameters')\n"
+        "ds = Dataset(conf)\n"
+        "s = PairwiseSampler(ds, neg_num=1, batch_size=512, shuffle=False)\n"
+        "it = iter(s); u, p, n = next(it)\n"
+        "s2 = PointwiseSampler(ds, neg_num=2, batch_size=7, shuffle=False, drop_last=True)\n"
+        "print(json.dumps({'len': len(s), 'users': u[:64], 'pos': [int(x) for x in p[:64]],"
+        " 'neg': [int(x) for x in n[:64]], 'len_pointwise': len(s2)}))"
+    ).strip().splitlines()[-1])
+    with open(os.path.join(OUT, "kat_sampler.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+def main():
+    import oracle
+    oracle.build()
+    cwd = oracle.import_reference()
+    os.chdir(cwd)
+    sys.argv = ["main.py"]
+
+    kat_sampler()
+
+    from util.cython.arg_topk import arg_topk
+    from evaluator.backend.cpp.cpp_evaluator import CPPEvaluator
+
+    # ---- evaluator KATs -------------------------------------------------------------
+    ev = CPPEvaluator()
+    kat = {}
+    S = np.random.RandomState(0).randn(4, 50).astype(np.float32)
+    truth = [[0, 24, 43], [47], [5, 13] + list(range(30, 40)), [2]]
+    kat["kat2_scores"] = S
+    kat["kat2_truth_indptr"] = np.cumsum([0] + [len(t) for t in truth]).astype(np.int64)
+    kat["kat2_truth_indices"] = np.concatenate([np.sort(t) for t in truth]).astype(np.int32)
+    kat["kat2_out"] = ev.eval_score_matrix(S, truth, [1, 2, 3, 4, 5], 5, 1)
+    kat["kat2_top5"] = arg_topk(S, 5, 1)
+    # metric subsets / order as configured in NeuRec.properties:34 (P, R, NDCG, MAP, MRR)
+    kat["kat2_out_41325"] = ev.eval_score_matrix(S, truth, [4, 1, 3, 2, 5], 5, 2)
+    # ties (KAT-3 and more): integer-valued and -inf heavy rows
+    z = np.zeros((1, 40), np.float32)
+    kat["tie_zeros_top5"] = arg_topk(z, 5, 1)
+    m3 = np.zeros((1, 40), np.float32); m3[0, ::3] = 1.0
+    kat["tie_mult3_top8"] = arg_topk(m3, 8, 1)
+    inf = np.full((1, 40), -np.inf, np.float32); inf[0, 7] = 1; inf[0, 3] = 2
+    kat["tie_inf_top5"] = arg_topk(inf, 5, 1)
+    rs = np.random.RandomState(7)
+    T = rs.randint(0, 5, size=(64, 333)).astype(np.float32)
+    T[rs.rand(64, 333) < 0.25] = -np.inf
+    ttruth = [sorted(rs.choice(333, rs.randint(1, 25), replace=False).tolist()) for _ in range(64)]
+    kat["tie_scores"] = T
+    kat["tie_truth_indptr"] = np.cumsum([0] + [len(t) for t in ttruth]).astype(np.int64)
+    kat["tie_truth_indices"] = np.concatenate(ttruth).astype(np.int32)
+    kat["tie_out_k20"] = ev.eval_score_matrix(T.copy(), ttruth, [1, 2, 3, 4, 5], 20, 4)
+    kat["tie_top20"] = arg_topk(T.copy(), 20, 4)
+    kat["tie_top40"] = arg_topk(T.copy(), 40, 4)
+    np.savez_compressed(os.path.join(OUT, "kat_evaluator.npz"), **kat)
+
+    # ---- ml-100k split + full evaluator ---------------------------------------------
+    np.random.seed(2018)
+    import random
+    random.seed(2018)
+    from util import Configurator
+    from data.dataset import Dataset
+    from evaluator import ProxyEvaluator
+    conf = Configurator("NeuRec.properties", default_section="hyperparameters")
+    ds = Dataset(conf)
+    tr, te = ds.train_matrix.tocsr(), ds.test_matrix.tocsr()
+    tr.sort_indices(); te.sort_indices()
+    np.savez_compressed(os.path.join(OUT, "ml100k_split.npz"),
+                        num_users=ds.num_users, num_items=ds.num_items,
+                        train_indptr=tr.indptr.astype(np.int32), train_indices=tr.indices.astype(np.int16),
+                        test_indptr=te.indptr.astype(np.int32), test_indices=te.indices.astype(np.int16))
+
+    class _Model:
+        def __init__(self, U, V):
+            self.U, self.V = U, V
+
+        def predict(self, user_ids, candidate_items=None):  # MF.py:120-124
+            ratings = np.matmul(self.U[user_ids], self.V.T)
+            if candidate_items is not None:
+                ratings = [r[i] for r, i in zip(ratings, candidate_items)]
+            return ratings
+
+    rng = np.random.RandomState(1)
+    U = (rng.randn(ds.num_users, 64) * .01).astype(np.float32)
+    V = (rng.randn(ds.num_items, 64) * .01).astype(np.float32)
+    model = _Model(U, V)
+    res = {}
+    train_d, test_d = ds.get_user_train_dict(), ds.get_user_test_dict()
+    e1 = ProxyEvaluator(train_d, test_d, None, metric=conf["metric"], group_view=None,
+                        top_k=conf["topk"], batch_size=conf["test_batch_size"], num_thread=8)
+    res["info_topk_10_20"] = e1.metrics_info()
+    res["eval_topk_10_20"] = e1.evaluate(model)
+    e2 = ProxyEvaluator(train_d, test_d, None, metric=["NDCG", "Recall"], top_k=5, batch_size=100)
+    res["info_topk_5"] = e2.metrics_info()
+    res["eval_topk_5"] = e2.evaluate(model)
+    # NOTE: GroupedEvaluator (grouped_evaluator.py:70-77) does not run under pandas 3.x
+    # (groupby(by=[...]) yields tuple keys -> TypeError at :76), so no grouped golden exists;
+    # its UniEvaluator-per-user-subset semantics (grouped_evaluator.py:108-110) is pinned by
+    # evaluating explicit user subsets instead.
+    sub = [u for u in test_d if 20 < len(train_d[u]) <= 50]
+    res["subset_users"] = [int(u) for u in sub]
+    res["eval_subset_20_50"] = e1.evaluator.evaluate(model, sub)
+    # trained-looking tables (larger scale, correlated) for a second data point
+    rng = np.random.RandomState(5)
+    U2 = (rng.randn(ds.num_users, 32)).astype(np.float32)
+    V2 = (rng.randn(ds.num_items, 32) + 0.3 * rng.randn(1, 32)).astype(np.float32)
+    res["eval_topk_10_20_d32"] = e1.evaluate(_Model(U2, V2))
+    res["dataset_str"] = str(ds)
+    res["n_train"] = int(tr.nnz); res["n_test"] = int(te.nnz)
+    with open(os.path.join(OUT, "kat_ml100k_eval.json"), "w") as f:
+        json.dump(res, f, indent=1)
+
+    # ---- surface behaviour ----------------------------------------------------------
+    from util import DataIterator
+    surf = {}
+    surf["conf_recommender"] = conf["recommender"]
+    surf["conf_topk"] = conf["topk"]
+    surf["conf_sep"] = conf["data.convert.separator"]
+    surf["conf_lr"] = conf["learning_rate"]
+    surf["conf_params_str"] = conf.params_str()
+    surf["conf_str"] = str(conf)
+    di = DataIterator(list(range(10)), list(range(10, 20)), batch_size=4, shuffle=False)
+    surf["dataiter"] = [b for b in di]
+    surf["dataiter_len_drop"] = len(DataIterator(list(range(10)), batch_size=4, drop_last=True))
+    np.random.seed(3)
+    surf["dataiter_shuffle"] = [b for b in DataIterator(list(range(10)), batch_size=4, shuffle=True)]
+    with open(os.path.join(OUT, "kat_surface.json"), "w") as f:
+        json.dump(surf, f, indent=1)
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
