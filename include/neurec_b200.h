@@ -1,0 +1,193 @@
+/*
+ * neurec_b200 -- C ABI of the B200-native (sm_100a) hot path of NeuRec.
+ *
+ * This header is the drop-in boundary: every entry point replaces one interface of the
+ * reference (cited as path:line relative to the reference root).  Signatures use plain
+ * pointers and sizes only; no torch / numpy / C++ types.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the function name ends in `_host`
+ *     (then every buffer is a host buffer and the call does its own staged H2D/D2H).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device
+ *     entry points are asynchronous on that stream and never free caller memory.
+ *   - ids are int32, CSR row pointers are int64, CSR rows are ascending and duplicate-free
+ *     (what util/tool.py:56-65 csr_to_user_dict produces).
+ *   - Return value: 0 on success, negative NRC_E_* otherwise; nrc_last_error() returns a
+ *     thread-local message.  Error codes mirror the Python exceptions the reference raises
+ *     at the same place (the Python wrapper re-raises them with the reference's message).
+ */
+#ifndef NEUREC_B200_H
+#define NEUREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRC_OK 0
+#define NRC_E_VALUE (-1)    /* reference raises ValueError */
+#define NRC_E_TYPE (-2)     /* reference raises TypeError */
+#define NRC_E_NOTIMPL (-3)  /* reference raises NotImplementedError */
+#define NRC_E_CUDA (-4)     /* CUDA runtime failure */
+#define NRC_E_LIMIT (-5)    /* argument outside this build's supported range */
+
+/* metric ids, evaluator/backend/cpp/include/metric.h:111-117 (metric_dict) */
+#define NRC_METRIC_PRECISION 1
+#define NRC_METRIC_RECALL 2
+#define NRC_METRIC_MAP 3
+#define NRC_METRIC_NDCG 4
+#define NRC_METRIC_MRR 5
+
+/* pairwise losses, util/learner.py:18-29; pointwise losses, util/learner.py:31-41 */
+#define NRC_LOSS_BPR 0
+#define NRC_LOSS_HINGE 1
+#define NRC_LOSS_SQUARE 2
+#define NRC_LOSS_CROSS_ENTROPY 3
+
+/* optimizers, util/learner.py:2-15 (TensorFlow 1.12 semantics) */
+#define NRC_OPT_GD 0
+#define NRC_OPT_ADAM 1
+#define NRC_OPT_ADAGRAD 2
+#define NRC_OPT_RMSPROP 3
+#define NRC_OPT_MOMENTUM 4
+
+int nrc_version(void);
+const char* nrc_last_error(void);
+
+/* ======================================================================================
+ * Evaluator
+ * ==================================================================================== */
+
+/* cpp_evaluate_matrix, evaluator/backend/cpp/include/evaluate.h:53-72, as bound by
+ * CPPEvaluator.eval_score_matrix, evaluator/backend/cpp/cpp_evaluator.pyx:28-42.
+ *   scores      f32 [num_users, rating_len] row-major (train items already -inf)
+ *   test_indptr i64 [num_users+1], test_indices i32: truth set of batch row b
+ *   metric      i32 [metric_num] HOST array of ids in 1..5 (it is a std::vector by value
+ *               in the reference); results f32 [num_users, metric_num*top_k], metric-major.
+ *   ranks       optional i32 [num_users, top_k]: the ranking the metrics were computed on.
+ * Selection reproduces std::partial_sort_copy over min(2*top_k, rating_len) slots
+ * (evaluate.h:38-42) including its tie order.  `thread_num` of the reference has no
+ * meaning on the GPU and is not part of this ABI. */
+int nrc_eval_score_matrix(const float* scores, int32_t rating_len, int32_t num_users,
+                          const int64_t* test_indptr, const int32_t* test_indices,
+                          const int32_t* metric_host, int32_t metric_num, int32_t top_k,
+                          float* results, int32_t* ranks, void* stream);
+
+/* Same, every buffer on the HOST (pageable or pinned); rows are streamed to the device in
+ * double-buffered chunks.  This is the call a `cdef extern` in cpp_evaluator.pyx binds. */
+int nrc_eval_score_matrix_host(const float* scores, int32_t rating_len, int32_t num_users,
+                               const int64_t* test_indptr, const int32_t* test_indices,
+                               const int32_t* metric_host, int32_t metric_num, int32_t top_k,
+                               float* results, int32_t* ranks);
+
+/* arg_top_k_2d, util/cython/include/arg_topk.h:27-45 (arg_topk.pyx:16-35): exactly top_k
+ * heap slots (no 2x margin), same tie order. */
+int nrc_arg_topk(const float* scores, int32_t rating_len, int32_t rows_num, int32_t top_k,
+                 int32_t* results, void* stream);
+int nrc_arg_topk_host(const float* scores, int32_t rating_len, int32_t rows_num, int32_t top_k,
+                      int32_t* results);
+
+/* Fused UniEvaluator batch body, evaluator/backend/cpp/uni_evaluator.py:132-146 with
+ * model.predict = U[users] . V^T (MF.py:120-122, LightGCN.py:187-189): score all items with
+ * an fp32 FMA chain over k, mask the user's train items to -inf, select, compute metrics.
+ * The [B, num_items] score matrix is never materialised.
+ *   user_table f32 [*, dim], item_table f32 [num_items, dim]
+ *   users i32 [num_eval_users]; train/test CSR are indexed by USER ID.
+ *   results f32 [num_eval_users, metric_num*top_k]; ranks optional. */
+int nrc_eval_mf(const float* user_table, const float* item_table, int32_t dim,
+                int32_t num_items, const int32_t* users, int32_t num_eval_users,
+                const int64_t* train_indptr, const int32_t* train_indices,
+                const int64_t* test_indptr, const int32_t* test_indices,
+                const int32_t* metric_host, int32_t metric_num, int32_t top_k,
+                float* results, int32_t* ranks, void* stream);
+
+/* np.mean(all_user_result, axis=0) in fp32, evaluator/backend/cpp/uni_evaluator.py:150:
+ * out[c] = (sequential fp32 sum over rows of results[:, c]) / num_rows, bit-identical to
+ * numpy's axis-0 reduction order. */
+int nrc_mean_rows(const float* results, int64_t num_rows, int32_t num_cols, float* out,
+                  void* stream);
+
+/* ======================================================================================
+ * Negative sampler
+ * ==================================================================================== */
+
+/* _sampling_negative_items, data/sampler.py:71-90 + batch_randint_choice,
+ * util/cython/random_choice.pyx:64-89 with replace=True: for positive p (owned by user
+ * users[p]) draw neg_num items uniformly from [0, num_items) \ train(users[p]).
+ * Counter-based Philox4x32-10: draw (p, s, attempt) depends only on (seed, stream_id) so any
+ * partition over GPUs yields the same negatives.  out i32 [n, neg_num].
+ * NRC_E_VALUE when neg_num <= 0 (sampler.py:72-73) or a user excludes every item
+ * (random_choice.pyx:32-33). */
+int nrc_sample_negatives(const int64_t* train_indptr, const int32_t* train_indices,
+                         const int32_t* users, int64_t n, int32_t neg_num, int32_t num_items,
+                         uint64_t seed, uint64_t stream_id, int64_t first_index,
+                         int32_t* out, void* stream);
+
+/* batch_randint_choice(high, size, replace, p=None, exclusion), random_choice.pyx:64-89.
+ * `size` is given as out_indptr i64 [n_rows+1] (prefix sums of the per-row sizes, device) and
+ * total_out = out_indptr[n_rows]; exclusion CSR may be NULL.  replace=0 draws without
+ * replacement inside a row.  A row whose exclusion covers [0, high) gets -1 entries (the
+ * reference raises ValueError, random_choice.pyx:32-33; the Python wrapper checks up front). */
+int nrc_batch_randint_choice(int32_t high, const int64_t* out_indptr, int32_t n_rows,
+                             int64_t total_out, int32_t replace, const int64_t* excl_indptr,
+                             const int32_t* excl_indices, uint64_t seed, uint64_t stream_id,
+                             int32_t* out, void* stream);
+
+/* ======================================================================================
+ * MF-family training step (BPRMF / pointwise "GMF")
+ * ==================================================================================== */
+
+/* Gradient phase of MF._create_loss, model/general_recommender/MF.py:54-69, with
+ * learner.pairwise_loss (util/learner.py:18-29) and tool.l2_loss (util/tool.py:216-217):
+ *   x = <U[u],V[i]> - <U[u],V[j]>;  loss = sum_b l(x_b) + reg/2 (|U[u]|^2+|V[i]|^2+|V[j]|^2)
+ * Reads the tables, adds the row gradients of every triplet into the dense accumulators
+ * grad_user/grad_item (duplicate ids sum, as TF's IndexedSlices dedup does), stamps touched
+ * rows with `stamp` (> 0, strictly increasing per step; the touched arrays start zeroed and
+ * are never cleared), adds the batch loss into *loss.  Tables are NOT modified. */
+int nrc_mf_pairwise_grad(const float* user_table, const float* item_table, int32_t dim,
+                         const int32_t* users, const int32_t* pos_items,
+                         const int32_t* neg_items, int64_t batch, int32_t loss_kind, float reg,
+                         float* grad_user, float* grad_item, int32_t* touched_user,
+                         int32_t* touched_item, int32_t stamp, float* loss, void* stream);
+
+/* Pointwise branch, MF.py:70-72 with learner.pointwise_loss (util/learner.py:31-41):
+ * cross_entropy = MEAN over the batch of max(x,0) - x*z + log1p(exp(-|x|)); square = SUM. */
+int nrc_mf_pointwise_grad(const float* user_table, const float* item_table, int32_t dim,
+                          const int32_t* users, const int32_t* items, const float* labels,
+                          int64_t batch, int32_t loss_kind, float reg, float* grad_user,
+                          float* grad_item, int32_t* touched_user, int32_t* touched_item,
+                          int32_t stamp, float* loss, void* stream);
+
+/* learner.optimizer, util/learner.py:2-15: apply TensorFlow-1.12 update rules to a table
+ * whose gradient arrived as IndexedSlices (embedding rows).
+ *   var, grad f32 [rows, dim]; slot0/slot1 optimizer state (adam: m, v; adagrad: accum;
+ *   rmsprop: ms, mom; momentum: accum; gd: unused); touched i32 [rows] from the grad phase.
+ *   hyper[0..3]: adam {lr_t, beta1, beta2, eps} with lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed
+ *   by the caller in fp32 as TF does; adagrad {lr}; rmsprop {lr, decay, momentum, eps};
+ *   momentum {lr, momentum}; gd {lr}.
+ * adam moves EVERY row (TF-1.12 _apply_sparse_shared decays m, v densely); the others only
+ * rows whose touched stamp equals `stamp`.  Zeroes grad afterwards (ready for the next step). */
+int nrc_opt_apply_rows(int32_t opt_kind, float* var, float* grad, float* slot0, float* slot1,
+                       const int32_t* touched, int32_t stamp, int64_t rows, int32_t dim,
+                       const float* hyper_host, void* stream);
+
+/* One epoch of MF.train_model, MF.py:92-108, on device-resident, already shuffled id arrays
+ * (n samples, steps = ceil(n / batch_size), last batch smaller, sampler.py:208-213).
+ *   third: neg items (pairwise, i32) or labels (pointwise, f32 bits) -- selected by
+ *   `pairwise`.  lr_t_host f32 [steps] per-step adam lr_t (ignored for other optimizers
+ *   except element 0 = lr).  step_loss f32 [steps] receives each step's loss.  Stamps
+ *   first_stamp .. first_stamp+steps-1 are consumed. */
+int nrc_mf_train_epoch(float* user_table, float* item_table, int32_t num_users,
+                       int32_t num_items, int32_t dim, const int32_t* users,
+                       const int32_t* items, const void* third, int64_t n, int32_t batch_size,
+                       int32_t pairwise, int32_t loss_kind, float reg, int32_t opt_kind,
+                       const float* lr_t_host, const float* hyper_host, float* grad_user,
+                       float* grad_item, int32_t* touched_user, int32_t* touched_item,
+                       float* slot0_user, float* slot1_user, float* slot0_item,
+                       float* slot1_item, int32_t first_stamp, float* step_loss, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUREC_B200_H */

@@ -1,0 +1,678 @@
+// Evaluator kernels: top-K selection with libstdc++-identical tie order + ranking metrics.
+//
+// Replaces (reference paths):
+//   evaluator/backend/cpp/include/evaluate.h:23-72   eval_one_user / cpp_evaluate_matrix
+//   evaluator/backend/cpp/include/metric.h:17-117    precision / recall / ap / ndcg / mrr
+//   util/cython/include/arg_topk.h:15-45             arg_top_k_1d / arg_top_k_2d
+//   evaluator/backend/cpp/uni_evaluator.py:132-146   predict -> mask -> eval (fused path)
+//
+// Selection semantics.  The reference ranks with std::partial_sort_copy(index, ..., L slots,
+// comp = ratings[a] > ratings[b]).  libstdc++ implements it as: copy the first L indices,
+// make_heap (root = smallest rating), then for every later index i: if ratings[i] >
+// ratings[root] replace the root (__adjust_heap), finally sort_heap.  Which of several equal
+// ratings survives and in what order is an artefact of those heap operations, so to be
+// bit-exact we run EXACTLY those heap operations -- but only on the few elements that beat the
+// current root.  The root value never decreases, so a warp can test 32 elements at a time
+// against a (possibly stale, hence lower) threshold with one ballot, and hand the rare
+// survivors, in ascending index order, to lane 0 which replays the sequential heap update.
+// Expected survivors per row: ~L*ln(N/L), e.g. ~280 of 40 981 items for L = 40.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace nrc {
+
+constexpr int kMaxTopK = 512;       // top_k limit of this build (L = 2*top_k <= 1024)
+constexpr int kMaxMetrics = 8;
+
+// Position-only tables, computed on the host with the host libm so that they carry the same
+// bits as the reference's `1.0/log2(i+2)` (metric.h:77-82) evaluated on the host.
+__constant__ double c_inv_log2[kMaxTopK];   // 1.0 / log2(i + 2)
+__constant__ float c_idcg[kMaxTopK];        // float running sum of the above (iDCG after i+1 terms)
+__constant__ int c_metric[kMaxMetrics];
+
+static bool g_tables_ready = false;
+
+static int upload_tables() {
+    if (g_tables_ready) return NRC_OK;
+    static double inv[kMaxTopK];
+    static float idcg[kMaxTopK];
+    float acc = 0.0f;
+    for (int i = 0; i < kMaxTopK; ++i) {
+        inv[i] = 1.0 / log2((double)(i + 2));
+        acc = (float)((double)acc + inv[i]);  // metric.h:82  iDCG += 1.0/log2(i+2)
+        idcg[i] = acc;
+    }
+    NRC_CUDA_CHECK(cudaMemcpyToSymbol(c_inv_log2, inv, sizeof(inv)));
+    NRC_CUDA_CHECK(cudaMemcpyToSymbol(c_idcg, idcg, sizeof(idcg)));
+    g_tables_ready = true;
+    return NRC_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// libstdc++ heap primitives (bits/stl_heap.h) on parallel (index, value) arrays.
+// comp(a, b) := value[a] > value[b].  Executed by ONE lane.
+// ----------------------------------------------------------------------------------------
+struct Heap {
+    int* idx;
+    float* val;
+};
+
+__device__ __forceinline__ void heap_push(Heap h, int hole, int top, int vi, float vv) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && h.val[parent] > vv) {
+        h.idx[hole] = h.idx[parent];
+        h.val[hole] = h.val[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    h.idx[hole] = vi;
+    h.val[hole] = vv;
+}
+
+__device__ __forceinline__ void heap_adjust(Heap h, int hole, int len, int vi, float vv) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (h.val[child] > h.val[child - 1]) child--;
+        h.idx[hole] = h.idx[child];
+        h.val[hole] = h.val[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        h.idx[hole] = h.idx[child - 1];
+        h.val[hole] = h.val[child - 1];
+        hole = child - 1;
+    }
+    heap_push(h, hole, top, vi, vv);
+}
+
+__device__ __forceinline__ void heap_make(Heap h, int len) {
+    if (len < 2) return;
+    int parent = (len - 2) / 2;
+    for (;;) {
+        heap_adjust(h, parent, len, h.idx[parent], h.val[parent]);
+        if (parent == 0) return;
+        parent--;
+    }
+}
+
+__device__ __forceinline__ void heap_sort(Heap h, int len) {
+    while (len > 1) {
+        --len;
+        int vi = h.idx[len];
+        float vv = h.val[len];
+        h.idx[len] = h.idx[0];
+        h.val[len] = h.val[0];
+        heap_adjust(h, 0, len, vi, vv);
+    }
+}
+
+// Offer the warp's 32 candidates (v, idx) -- idx ascending with the lane id -- to the heap.
+// Returns the current root value (the new threshold) in every lane.
+__device__ __forceinline__ float offer_candidates(Heap h, int L, float v, int idx, bool valid,
+                                                  float thr, int lane) {
+    unsigned m = __ballot_sync(kFull, valid && v > thr);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const float cv = __shfl_sync(kFull, v, src);
+        const int ci = __shfl_sync(kFull, idx, src);
+        if (lane == 0 && cv > h.val[0]) heap_adjust(h, 0, L, ci, cv);  // evaluate.h:40-41
+        __syncwarp();
+        thr = h.val[0];
+    }
+    return thr;
+}
+
+// ----------------------------------------------------------------------------------------
+// metric.h:17-109 for one user, executed by one warp.
+//   rank: smem, top_k ranked item ids; truth: sorted global row; scratch: 3*K words of smem.
+// Float/double expression shapes follow metric.h literally (see oracle/neurec_oracle.c).
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void metrics_for_user(const int* rank, int K, const int32_t* truth,
+                                                 int T, int* s_cnt, float* s_sum_pre,
+                                                 float* s_dcg, int M, float* out_row, int lane) {
+    // hit flags -> stash as 0/1 in s_cnt, prefix-summed serially below
+    for (int i = lane; i < K; i += kWarp) s_cnt[i] = sorted_contains(truth, T, rank[i]) ? 1 : 0;
+    __syncwarp();
+    int first_hit = K;
+    if (lane == 0) {
+        int hits = 0;
+        float sum_pre = 0.0f, dcg = 0.0f;
+        int fh = K;
+        for (int i = 0; i < K; ++i) {
+            if (s_cnt[i]) {
+                if (hits == 0) fh = i;
+                hits += 1;
+                const float pre = (float)__ddiv_rn((double)hits, (double)(i + 1));  // metric.h:59
+                sum_pre = __fadd_rn(sum_pre, pre);                                  // metric.h:60
+                dcg = (float)__dadd_rn((double)dcg, c_inv_log2[i]);                 // metric.h:78
+            }
+            s_cnt[i] = hits;
+            s_sum_pre[i] = sum_pre;
+            s_dcg[i] = dcg;
+        }
+        first_hit = fh;
+    }
+    first_hit = __shfl_sync(kFull, first_hit, 0);
+    __syncwarp();
+    const float Tf = (float)T;
+    for (int i = lane; i < K; i += kWarp) {
+        const int hits = s_cnt[i];
+        for (int m = 0; m < M; ++m) {
+            float r;
+            switch (c_metric[m]) {
+                case NRC_METRIC_PRECISION:  // metric.h:26
+                    r = (float)__ddiv_rn((double)hits, (double)(i + 1));
+                    break;
+                case NRC_METRIC_RECALL:  // metric.h:41
+                    r = (float)__ddiv_rn((double)hits, (double)T);
+                    break;
+                case NRC_METRIC_MAP: {  // metric.h:62-63
+                    const float den = (Tf < (float)(i + 1)) ? Tf : (float)(i + 1);
+                    r = (hits == 0) ? 0.0f : __fdiv_rn(s_sum_pre[i], den);
+                    break;
+                }
+                case NRC_METRIC_NDCG: {  // metric.h:80-84
+                    const float idcg = (T == 0) ? 0.0f : c_idcg[(i < T ? i : T - 1)];
+                    r = __fdiv_rn(s_dcg[i], idcg);
+                    break;
+                }
+                default:  // NRC_METRIC_MRR, metric.h:92-106
+                    r = (i >= first_hit) ? (float)__ddiv_rn(1.0, (double)(first_hit + 1)) : 0.0f;
+                    break;
+            }
+            out_row[m * K + i] = r;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Kernel A: score matrix given.  One warp per row; coalesced streaming read of the row.
+// ----------------------------------------------------------------------------------------
+constexpr int kRowUnroll = 8;
+
+template <bool kMetrics>
+__global__ void __launch_bounds__(256)
+eval_rows_kernel(const float* __restrict__ scores, int N, int rows, int K, int L,
+                 const int64_t* __restrict__ tptr, const int32_t* __restrict__ tidx, int M,
+                 float* __restrict__ results, int32_t* __restrict__ ranks) {
+    extern __shared__ int smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= rows) return;
+    const int stride = 2 * L + 3 * K;
+    Heap h;
+    h.idx = smem + warp * stride;
+    h.val = reinterpret_cast<float*>(h.idx + L);
+    int* s_cnt = h.idx + 2 * L;
+    float* s_sum_pre = reinterpret_cast<float*>(s_cnt + K);
+    float* s_dcg = s_sum_pre + K;
+
+    const float* __restrict__ r = scores + (size_t)row * N;
+    for (int i = lane; i < L; i += kWarp) {  // evaluate.h:40: first L indices seed the heap
+        h.idx[i] = i;
+        h.val[i] = r[i];
+    }
+    __syncwarp();
+    if (lane == 0) heap_make(h, L);
+    __syncwarp();
+    float thr = h.val[0];
+
+    for (int base = L; base < N; base += kWarp * kRowUnroll) {
+        float v[kRowUnroll];
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+            const int i = base + u * kWarp + lane;
+            v[u] = (i < N) ? __ldcs(r + i) : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < kRowUnroll; ++u) {
+            const int i = base + u * kWarp + lane;
+            thr = offer_candidates(h, L, v[u], i, i < N, thr, lane);
+        }
+    }
+    if (lane == 0) heap_sort(h, L);
+    __syncwarp();
+    if (ranks)
+        for (int i = lane; i < K; i += kWarp) ranks[(size_t)row * K + i] = h.idx[i];
+    if (kMetrics) {
+        const int64_t t0 = tptr[row];
+        const int T = (int)(tptr[row + 1] - t0);
+        metrics_for_user(h.idx, K, tidx + t0, T, s_cnt, s_sum_pre, s_dcg, M,
+                         results + (size_t)row * M * K, lane);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Kernel B: fused predict (U.V^T, fp32 FMA chain over k) -> train mask -> select -> metrics.
+//
+// CTA = kWarps warps; each warp owns TM users and, per item tile, each lane owns TN items
+// (item = tile_base + n*32 + lane).  The V tile sits in shared memory as [item][dim+4] floats
+// (row stride = odd multiple of 16 B => conflict-free LDS.128 by item), the CTA's user rows
+// as [user][dim] (LDS.128 broadcast).  Per 4 consecutive k: TN + TM LDS.128 feed 4*TM*TN FFMA.
+// Every (user, item) accumulator sees acc = fma(u[k], v[k], acc) for k = 0..dim-1 in order,
+// the oracle's definition of the score, so scores are bit-identical to the oracle's.
+//
+// Train masking: a masked score is -inf and -inf never beats the heap root, so masked items
+// only need explicit treatment (a) among the first L items that seed the heap and (b) so
+// that they do not pass the threshold test: the warp walks each user's sorted train row in
+// step with the item tiles and builds a TN*32-bit mask per tile.
+// ----------------------------------------------------------------------------------------
+template <int TM, int TN, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32)
+eval_mf_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, int D, int N,
+               const int32_t* __restrict__ users, int num_eval,
+               const int64_t* __restrict__ train_ptr, const int32_t* __restrict__ train_idx,
+               const int64_t* __restrict__ test_ptr, const int32_t* __restrict__ test_idx,
+               int K, int L, int M, float* __restrict__ results, int32_t* __restrict__ ranks) {
+    constexpr int TILE = TN * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int D4 = (D + 3) & ~3;       // padded dim (zero fill: fma(0,0,acc) == acc)
+    const int VS = D4 + 4;             // V tile row stride in floats
+    float* sU = reinterpret_cast<float*>(smem_raw);                 // [kWarps*TM][D4]
+    float* sV = sU + kWarps * TM * D4;                              // [TILE][VS]
+    int* sHeap = reinterpret_cast<int*>(sV + TILE * VS);            // per user 2L+3K words
+    const int hstride = 2 * L + 3 * K;
+
+    const int user_slot0 = blockIdx.x * (kWarps * TM) + warp * TM;  // first batch row of warp
+
+    // ---- stage this CTA's user rows ------------------------------------------------
+    for (int idx = threadIdx.x; idx < kWarps * TM * D4; idx += blockDim.x) {
+        const int us = idx / D4, k = idx - us * D4;
+        const int b = blockIdx.x * (kWarps * TM) + us;
+        float val = 0.0f;
+        if (b < num_eval && k < D) val = Utab[(size_t)users[b] * D + k];
+        sU[idx] = val;
+    }
+    __syncthreads();
+
+    // ---- per-user state (warp-uniform) ---------------------------------------------
+    int64_t tr_beg[TM];
+    int tr_len[TM], tr_pos[TM];
+    float thr[TM];
+    bool live[TM];
+#pragma unroll
+    for (int m = 0; m < TM; ++m) {
+        const int b = user_slot0 + m;
+        live[m] = b < num_eval;
+        const int u = live[m] ? users[b] : 0;
+        tr_beg[m] = live[m] ? train_ptr[u] : 0;
+        tr_len[m] = live[m] ? (int)(train_ptr[u + 1] - tr_beg[m]) : 0;
+        tr_pos[m] = 0;
+        thr[m] = INFINITY;
+    }
+
+    // ---- seed the heaps with items [0, L) (evaluate.h:40), masked exactly -----------
+#pragma unroll
+    for (int m = 0; m < TM; ++m) {
+        if (!live[m]) continue;
+        Heap h;
+        h.idx = sHeap + (warp * TM + m) * hstride;
+        h.val = reinterpret_cast<float*>(h.idx + L);
+        const float* su = sU + (warp * TM + m) * D4;
+        for (int i = lane; i < L; i += kWarp) {
+            const float* vr = Vtab + (size_t)i * D;
+            float acc = 0.0f;
+            for (int k = 0; k < D; ++k) acc = __fmaf_rn(su[k], __ldg(vr + k), acc);
+            if (sorted_contains(train_idx + tr_beg[m], tr_len[m], i)) acc = -INFINITY;
+            h.idx[i] = i;
+            h.val[i] = acc;
+        }
+        // first train position >= L
+        int cnt = 0;
+        for (int p = lane; p < tr_len[m]; p += kWarp) cnt += (__ldg(train_idx + tr_beg[m] + p) < L);
+        cnt = __reduce_add_sync(kFull, cnt);
+        tr_pos[m] = cnt;
+        __syncwarp();
+        if (lane == 0) heap_make(h, L);
+        __syncwarp();
+        thr[m] = h.val[0];
+    }
+
+    // ---- main loop over item tiles ---------------------------------------------------
+    for (int base = L; base < N; base += TILE) {
+        __syncthreads();  // previous tile fully consumed
+        // load V tile (coalesced float4 when dim % 4 == 0, scalar otherwise)
+        if ((D & 3) == 0) {
+            const int q_per_row = D >> 2;
+            for (int idx = threadIdx.x; idx < TILE * q_per_row; idx += blockDim.x) {
+                const int it = idx / q_per_row, q = idx - it * q_per_row;
+                const int item = base + it;
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (item < N) val = __ldg(reinterpret_cast<const float4*>(Vtab + (size_t)item * D) + q);
+                *reinterpret_cast<float4*>(sV + it * VS + q * 4) = val;
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < TILE * D4; idx += blockDim.x) {
+                const int it = idx / D4, k = idx - it * D4;
+                const int item = base + it;
+                sV[it * VS + k] = (item < N && k < D) ? __ldg(Vtab + (size_t)item * D + k) : 0.0f;
+            }
+        }
+        __syncthreads();
+
+        float acc[TM][TN];
+#pragma unroll
+        for (int m = 0; m < TM; ++m)
+#pragma unroll
+            for (int n = 0; n < TN; ++n) acc[m][n] = 0.0f;
+
+        const float* su = sU + warp * TM * D4;
+        for (int k = 0; k < D4; k += 4) {
+            float4 vv[TN], uu[TM];
+#pragma unroll
+            for (int n = 0; n < TN; ++n)
+                vv[n] = *reinterpret_cast<const float4*>(sV + (n * 32 + lane) * VS + k);
+#pragma unroll
+            for (int m = 0; m < TM; ++m) uu[m] = *reinterpret_cast<const float4*>(su + m * D4 + k);
+#pragma unroll
+            for (int m = 0; m < TM; ++m)
+#pragma unroll
+                for (int n = 0; n < TN; ++n) {
+                    float a = acc[m][n];
+                    a = __fmaf_rn(uu[m].x, vv[n].x, a);
+                    a = __fmaf_rn(uu[m].y, vv[n].y, a);
+                    a = __fmaf_rn(uu[m].z, vv[n].z, a);
+                    a = __fmaf_rn(uu[m].w, vv[n].w, a);
+                    acc[m][n] = a;
+                }
+        }
+
+        // train mask for this tile + candidate offers, user by user
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+            if (!live[m]) continue;
+            unsigned maskbits[TN];
+#pragma unroll
+            for (int n = 0; n < TN; ++n) maskbits[n] = 0u;
+            for (;;) {
+                const int p = tr_pos[m] + lane;
+                const int t = (p < tr_len[m]) ? __ldg(train_idx + tr_beg[m] + p) : INT32_MAX;
+                const bool in_tile = t < base + TILE;
+                const int off = t - base;  // >= 0 by construction when in_tile
+#pragma unroll
+                for (int n = 0; n < TN; ++n) {
+                    const unsigned bit = (in_tile && (off >> 5) == n) ? (1u << (off & 31)) : 0u;
+                    maskbits[n] |= __reduce_or_sync(kFull, bit);
+                }
+                const int c = __popc(__ballot_sync(kFull, in_tile));
+                tr_pos[m] += c;
+                if (c < kWarp) break;
+            }
+            Heap h;
+            h.idx = sHeap + (warp * TM + m) * hstride;
+            h.val = reinterpret_cast<float*>(h.idx + L);
+#pragma unroll
+            for (int n = 0; n < TN; ++n) {
+                const int item = base + n * 32 + lane;
+                const bool ok = item < N && !((maskbits[n] >> lane) & 1u);
+                thr[m] = offer_candidates(h, L, acc[m][n], item, ok, thr[m], lane);
+            }
+        }
+    }
+
+    // ---- finalise: sort_heap, ranks, metrics ------------------------------------------
+#pragma unroll
+    for (int m = 0; m < TM; ++m) {
+        if (!live[m]) continue;
+        const int b = user_slot0 + m;
+        Heap h;
+        h.idx = sHeap + (warp * TM + m) * hstride;
+        h.val = reinterpret_cast<float*>(h.idx + L);
+        if (lane == 0) heap_sort(h, L);
+        __syncwarp();
+        if (ranks)
+            for (int i = lane; i < K; i += kWarp) ranks[(size_t)b * K + i] = h.idx[i];
+        if (results) {
+            const int u = users[b];
+            const int64_t t0 = test_ptr[u];
+            const int T = (int)(test_ptr[u + 1] - t0);
+            int* s_cnt = h.idx + 2 * L;
+            float* s_sum_pre = reinterpret_cast<float*>(s_cnt + K);
+            float* s_dcg = s_sum_pre + K;
+            metrics_for_user(h.idx, K, test_idx + t0, T, s_cnt, s_sum_pre, s_dcg, M,
+                             results + (size_t)b * M * K, lane);
+        }
+        __syncwarp();
+    }
+}
+
+// np.mean(axis=0) of a C-contiguous [rows, cols] fp32 matrix: numpy adds row after row into
+// the fp32 output (no pairwise blocking along a non-contiguous reduction axis), then divides
+// by the row count in fp32.  One thread per column, rows in order.
+__global__ void mean_rows_kernel(const float* __restrict__ a, int64_t rows, int cols,
+                                 float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float acc = 0.0f;
+    if (rows > 0) {
+        acc = a[c];
+        for (int64_t r = 1; r < rows; ++r) acc = __fadd_rn(acc, a[r * cols + c]);
+    }
+    out[c] = __fdiv_rn(acc, (float)rows);
+}
+
+static int check_metrics(const int32_t* metric_host, int metric_num) {
+    NRC_REQUIRE(metric_num >= 0 && metric_num <= kMaxMetrics, NRC_E_LIMIT,
+                "metric_num %d outside [0, %d]", metric_num, kMaxMetrics);
+    int ids[kMaxMetrics] = {0};
+    for (int i = 0; i < metric_num; ++i) {
+        // cpp/uni_evaluator.py:71-73 raises ValueError for an unknown metric
+        NRC_REQUIRE(metric_host[i] >= 1 && metric_host[i] <= 5, NRC_E_VALUE,
+                    "There is not the metric id '%d'!", metric_host[i]);
+        ids[i] = metric_host[i];
+    }
+    static int cached[kMaxMetrics] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    if (memcmp(cached, ids, sizeof(ids)) != 0) {
+        // a previous launch may still be reading the old ids on another stream
+        NRC_CUDA_CHECK(cudaDeviceSynchronize());
+        NRC_CUDA_CHECK(cudaMemcpyToSymbol(c_metric, ids, sizeof(ids)));
+        memcpy(cached, ids, sizeof(ids));
+    }
+    return upload_tables();
+}
+
+static int launch_rows(const float* scores, int N, int rows, int K, int L, const int64_t* tptr,
+                       const int32_t* tidx, int M, float* results, int32_t* ranks, bool metrics,
+                       cudaStream_t st) {
+    if (rows == 0) return NRC_OK;
+    const int stride_bytes = (2 * L + 3 * K) * 4;
+    int warps = 8;
+    while (warps > 1 && warps * stride_bytes > 96 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * stride_bytes;
+    const int grid = (rows + warps - 1) / warps;
+    if (metrics) {
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(eval_rows_kernel<true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        eval_rows_kernel<true><<<grid, warps * 32, smem, st>>>(scores, N, rows, K, L, tptr, tidx, M,
+                                                              results, ranks);
+    } else {
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(eval_rows_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        eval_rows_kernel<false><<<grid, warps * 32, smem, st>>>(scores, N, rows, K, L, tptr, tidx,
+                                                               M, results, ranks);
+    }
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+}  // namespace nrc
+
+using namespace nrc;
+
+extern "C" int nrc_eval_score_matrix(const float* scores, int32_t rating_len, int32_t num_users,
+                                     const int64_t* test_indptr, const int32_t* test_indices,
+                                     const int32_t* metric_host, int32_t metric_num,
+                                     int32_t top_k, float* results, int32_t* ranks,
+                                     void* stream) {
+    NRC_REQUIRE(top_k > 0 && top_k <= kMaxTopK, NRC_E_LIMIT, "top_k %d outside [1, %d]", top_k,
+                kMaxTopK);
+    NRC_REQUIRE(rating_len >= top_k, NRC_E_VALUE,
+                "rating_len (%d) must be >= top_k (%d)", rating_len, top_k);
+    NRC_REQUIRE(num_users >= 0, NRC_E_VALUE, "num_users must be >= 0");
+    int rc = check_metrics(metric_host, metric_num);
+    if (rc) return rc;
+    const int L = (2 * top_k < rating_len) ? 2 * top_k : rating_len;  // evaluate.h:38
+    return launch_rows(scores, rating_len, num_users, top_k, L, test_indptr, test_indices,
+                       metric_num, results, ranks, true, as_stream(stream));
+}
+
+extern "C" int nrc_arg_topk(const float* scores, int32_t rating_len, int32_t rows_num,
+                            int32_t top_k, int32_t* results, void* stream) {
+    NRC_REQUIRE(top_k > 0 && top_k <= 2 * kMaxTopK, NRC_E_LIMIT, "top_k %d outside [1, %d]", top_k,
+                2 * kMaxTopK);
+    NRC_REQUIRE(rating_len >= top_k, NRC_E_VALUE, "rating_len (%d) must be >= top_k (%d)",
+                rating_len, top_k);
+    // arg_topk.h:22: exactly top_k slots.  (K = L = top_k; no metric scratch is touched.)
+    return launch_rows(scores, rating_len, rows_num, top_k, top_k, nullptr, nullptr, 0, nullptr,
+                       results, false, as_stream(stream));
+}
+
+// Host-buffer variants: stream row chunks through two device staging buffers.
+static int rows_host(const float* scores, int N, int rows, const int64_t* tptr_h,
+                     const int32_t* tidx_h, const int32_t* metric_host, int M, int K, int L,
+                     float* results_h, int32_t* ranks_h, bool metrics) {
+    if (rows == 0) return NRC_OK;
+    const size_t row_bytes = (size_t)N * sizeof(float);
+    size_t chunk_rows = (64u << 20) / (row_bytes ? row_bytes : 1);
+    if (chunk_rows < 1) chunk_rows = 1;
+    if (chunk_rows > (size_t)rows) chunk_rows = rows;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    float* d_scores[2] = {nullptr, nullptr};
+    float* d_res[2] = {nullptr, nullptr};
+    int32_t* d_rank[2] = {nullptr, nullptr};
+    int64_t* d_tptr = nullptr;
+    int32_t* d_tidx = nullptr;
+    int rc = NRC_OK;
+    auto cleanup = [&]() {
+        for (int i = 0; i < 2; ++i) {
+            if (d_scores[i]) cudaFree(d_scores[i]);
+            if (d_res[i]) cudaFree(d_res[i]);
+            if (d_rank[i]) cudaFree(d_rank[i]);
+        }
+        if (d_tptr) cudaFree(d_tptr);
+        if (d_tidx) cudaFree(d_tidx);
+        if (st[0]) cudaStreamDestroy(st[0]);
+        if (st[1]) cudaStreamDestroy(st[1]);
+    };
+    NRC_CUDA_CHECK(cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking));
+    NRC_CUDA_CHECK(cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking));
+#define NRC_TRY(expr)                                                                    \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                   \
+            cleanup();                                                                   \
+            return NRC_E_CUDA;                                                           \
+        }                                                                                \
+    } while (0)
+    for (int i = 0; i < 2; ++i) {
+        NRC_TRY(cudaMalloc(&d_scores[i], chunk_rows * row_bytes));
+        if (metrics) NRC_TRY(cudaMalloc(&d_res[i], chunk_rows * (size_t)M * K * sizeof(float)));
+        if (ranks_h || !metrics) NRC_TRY(cudaMalloc(&d_rank[i], chunk_rows * (size_t)K * sizeof(int32_t)));
+    }
+    if (metrics) {
+        const int64_t nnz = tptr_h[rows];
+        NRC_TRY(cudaMalloc(&d_tptr, (size_t)(rows + 1) * sizeof(int64_t)));
+        NRC_TRY(cudaMalloc(&d_tidx, (size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t)));
+        NRC_TRY(cudaMemcpy(d_tptr, tptr_h, (size_t)(rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+        NRC_TRY(cudaMemcpy(d_tidx, tidx_h, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    int buf = 0;
+    for (size_t r0 = 0; r0 < (size_t)rows; r0 += chunk_rows, buf ^= 1) {
+        const size_t nr = ((size_t)rows - r0 < chunk_rows) ? (size_t)rows - r0 : chunk_rows;
+        NRC_TRY(cudaMemcpyAsync(d_scores[buf], scores + r0 * N, nr * row_bytes, cudaMemcpyHostToDevice, st[buf]));
+        rc = launch_rows(d_scores[buf], N, (int)nr, K, L, metrics ? d_tptr + r0 : nullptr, d_tidx, M,
+                         d_res[buf], d_rank[buf], metrics, st[buf]);
+        if (rc) { cleanup(); return rc; }
+        if (metrics)
+            NRC_TRY(cudaMemcpyAsync(results_h + r0 * (size_t)M * K, d_res[buf], nr * (size_t)M * K * sizeof(float),
+                                    cudaMemcpyDeviceToHost, st[buf]));
+        if (ranks_h)
+            NRC_TRY(cudaMemcpyAsync(ranks_h + r0 * (size_t)K, d_rank[buf], nr * (size_t)K * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, st[buf]));
+    }
+    NRC_TRY(cudaStreamSynchronize(st[0]));
+    NRC_TRY(cudaStreamSynchronize(st[1]));
+#undef NRC_TRY
+    cleanup();
+    return NRC_OK;
+}
+
+extern "C" int nrc_eval_score_matrix_host(const float* scores, int32_t rating_len,
+                                          int32_t num_users, const int64_t* test_indptr,
+                                          const int32_t* test_indices, const int32_t* metric_host,
+                                          int32_t metric_num, int32_t top_k, float* results,
+                                          int32_t* ranks) {
+    NRC_REQUIRE(top_k > 0 && top_k <= kMaxTopK, NRC_E_LIMIT, "top_k %d outside [1, %d]", top_k,
+                kMaxTopK);
+    NRC_REQUIRE(rating_len >= top_k, NRC_E_VALUE, "rating_len (%d) must be >= top_k (%d)",
+                rating_len, top_k);
+    int rc = check_metrics(metric_host, metric_num);
+    if (rc) return rc;
+    const int L = (2 * top_k < rating_len) ? 2 * top_k : rating_len;
+    return rows_host(scores, rating_len, num_users, test_indptr, test_indices, metric_host,
+                     metric_num, top_k, L, results, ranks, true);
+}
+
+extern "C" int nrc_arg_topk_host(const float* scores, int32_t rating_len, int32_t rows_num,
+                                 int32_t top_k, int32_t* results) {
+    NRC_REQUIRE(top_k > 0 && top_k <= 2 * kMaxTopK, NRC_E_LIMIT, "top_k %d outside [1, %d]", top_k,
+                2 * kMaxTopK);
+    NRC_REQUIRE(rating_len >= top_k, NRC_E_VALUE, "rating_len (%d) must be >= top_k (%d)",
+                rating_len, top_k);
+    return rows_host(scores, rating_len, rows_num, nullptr, nullptr, nullptr, 0, top_k, top_k,
+                     nullptr, results, false);
+}
+
+extern "C" int nrc_eval_mf(const float* user_table, const float* item_table, int32_t dim,
+                           int32_t num_items, const int32_t* users, int32_t num_eval_users,
+                           const int64_t* train_indptr, const int32_t* train_indices,
+                           const int64_t* test_indptr, const int32_t* test_indices,
+                           const int32_t* metric_host, int32_t metric_num, int32_t top_k,
+                           float* results, int32_t* ranks, void* stream) {
+    NRC_REQUIRE(top_k > 0 && top_k <= kMaxTopK, NRC_E_LIMIT, "top_k %d outside [1, %d]", top_k,
+                kMaxTopK);
+    NRC_REQUIRE(num_items >= top_k, NRC_E_VALUE, "num_items (%d) must be >= top_k (%d)", num_items,
+                top_k);
+    NRC_REQUIRE(dim > 0 && dim <= 512, NRC_E_LIMIT, "dim %d outside [1, 512]", dim);
+    int rc = check_metrics(metric_host, metric_num);
+    if (rc) return rc;
+    if (num_eval_users <= 0) return NRC_OK;
+    const int K = top_k;
+    const int L = (2 * K < num_items) ? 2 * K : num_items;
+    const int D4 = (dim + 3) & ~3;
+    constexpr int TM = 8, TN = 2, W = 8;
+    const size_t smem = ((size_t)W * TM * D4 + (size_t)TN * 32 * (D4 + 4)) * 4 +
+                        (size_t)W * TM * (2 * L + 3 * K) * 4;
+    NRC_REQUIRE(smem <= 227 * 1024, NRC_E_LIMIT,
+                "dim %d / top_k %d need %zu B of shared memory (> 227 KB)", dim, top_k, smem);
+    auto kern = eval_mf_kernel<TM, TN, W>;
+    NRC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        227 * 1024));
+    const int grid = (num_eval_users + W * TM - 1) / (W * TM);
+    kern<<<grid, W * 32, smem, as_stream(stream)>>>(user_table, item_table, dim, num_items, users,
+                                                    num_eval_users, train_indptr, train_indices,
+                                                    test_indptr, test_indices, K, L, metric_num,
+                                                    results, ranks);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+extern "C" int nrc_mean_rows(const float* results, int64_t num_rows, int32_t num_cols,
+                             float* out, void* stream) {
+    NRC_REQUIRE(num_cols >= 0 && num_rows >= 0, NRC_E_VALUE, "negative shape");
+    if (num_cols == 0) return NRC_OK;
+    mean_rows_kernel<<<(num_cols + 127) / 128, 128, 0, as_stream(stream)>>>(results, num_rows,
+                                                                           num_cols, out);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}

@@ -1,0 +1,137 @@
+// TensorFlow-1.12 optimizer update rules (util/learner.py:2-15 selects them).
+//
+// Third-party arithmetic (tensorflow==1.12.3, python/training/*.py + core/kernels/training_ops.cc;
+// not vendored in the reference, restated from its published algorithm -- see DESIGN.md):
+//
+//  IndexedSlices gradients (embedding rows; `dense_var == 0`), g = de-duplicated row gradient
+//    gd        var -= g * lr                                     (touched rows; g = 0 elsewhere)
+//    adam      m = m*b1 + g*(1-b1); v = v*b2 + (g*g)*(1-b2);     EVERY row: _apply_sparse_shared
+//              var -= (lr_t * m) / (sqrt(v) + eps)               assigns m*b1, v*b2 densely
+//    adagrad   a += g*g; var -= (lr * g) * (1/sqrt(a))           touched rows only
+//    rmsprop   ms += (g*g - ms)*(1-rho); mom = mom*mu + (lr*g)*(1/sqrt(ms+eps)); var -= mom
+//    momentum  a = a*mu + g; var -= a*lr                         touched rows only
+//  Dense gradients (`dense_var == 1`): the Apply* functors
+//    adam      m += (g - m)*(1-b1); v += (g*g - v)*(1-b2); var -= (m*lr_t) / (sqrt(v) + eps)
+//    others    same formulas as above applied to every element.
+//
+// Every fp32 operation is written with a non-contracting intrinsic so the result is the
+// same sequence of IEEE roundings numpy produces in oracle/tf_math.py (bit-exact given the
+// same gradient).
+#include "optim.cuh"
+
+namespace nrc {
+
+struct OptParams {
+    OptSeg seg[kMaxOptSegs];
+    int nseg;
+    int kind;
+    float h0, h1, h2, h3;
+    int32_t stamp;
+    int64_t total;
+};
+
+__device__ __forceinline__ void opt_update(int kind, int dense_var, bool touched, float h0,
+                                           float h1, float h2, float h3, float& var, float g,
+                                           float& s0, float& s1) {
+    switch (kind) {
+        case NRC_OPT_GD:
+            var = __fsub_rn(var, __fmul_rn(g, h0));
+            break;
+        case NRC_OPT_ADAM: {
+            const float omb1 = __fsub_rn(1.0f, h1), omb2 = __fsub_rn(1.0f, h2);
+            if (dense_var) {
+                s0 = __fadd_rn(s0, __fmul_rn(__fsub_rn(g, s0), omb1));
+                s1 = __fadd_rn(s1, __fmul_rn(__fsub_rn(__fmul_rn(g, g), s1), omb2));
+                var = __fsub_rn(var, __fdiv_rn(__fmul_rn(s0, h0), __fadd_rn(__fsqrt_rn(s1), h3)));
+            } else {
+                s0 = __fadd_rn(__fmul_rn(s0, h1), __fmul_rn(g, omb1));
+                s1 = __fadd_rn(__fmul_rn(s1, h2), __fmul_rn(__fmul_rn(g, g), omb2));
+                var = __fsub_rn(var, __fdiv_rn(__fmul_rn(h0, s0), __fadd_rn(__fsqrt_rn(s1), h3)));
+            }
+            break;
+        }
+        case NRC_OPT_ADAGRAD:
+            if (touched) {
+                s0 = __fadd_rn(s0, __fmul_rn(g, g));
+                var = __fsub_rn(var, __fmul_rn(__fmul_rn(h0, g), __fdiv_rn(1.0f, __fsqrt_rn(s0))));
+            }
+            break;
+        case NRC_OPT_RMSPROP:
+            if (touched) {  // h = {lr, rho, momentum, eps}
+                s0 = __fadd_rn(s0, __fmul_rn(__fsub_rn(__fmul_rn(g, g), s0), __fsub_rn(1.0f, h1)));
+                s1 = __fadd_rn(__fmul_rn(s1, h2),
+                               __fmul_rn(__fmul_rn(h0, g), __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(s0, h3)))));
+                var = __fsub_rn(var, s1);
+            }
+            break;
+        default:  // NRC_OPT_MOMENTUM  h = {lr, momentum}
+            if (touched) {
+                s0 = __fadd_rn(__fmul_rn(s0, h1), g);
+                var = __fsub_rn(var, __fmul_rn(s0, h0));
+            }
+            break;
+    }
+}
+
+__global__ void __launch_bounds__(256) opt_apply_kernel(const OptParams P) {
+    const bool has0 = P.kind != NRC_OPT_GD;
+    const bool has1 = P.kind == NRC_OPT_ADAM || P.kind == NRC_OPT_RMSPROP;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < P.total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        int s = 0;
+#pragma unroll 1
+        while (s + 1 < P.nseg && e >= P.seg[s + 1].begin) ++s;
+        const OptSeg& sg = P.seg[s];
+        const int64_t i = e - sg.begin;
+        const float g = sg.grad[i];
+        bool touched = true;
+        if (!sg.dense_var && sg.touched) touched = (sg.touched[i / sg.dim] == P.stamp);
+        float var = sg.var[i];
+        float s0 = has0 ? sg.s0[i] : 0.0f;
+        float s1 = has1 ? sg.s1[i] : 0.0f;
+        opt_update(P.kind, sg.dense_var, touched, P.h0, P.h1, P.h2, P.h3, var, g, s0, s1);
+        sg.var[i] = var;
+        if (has0) sg.s0[i] = s0;
+        if (has1) sg.s1[i] = s1;
+        sg.grad[i] = 0.0f;
+    }
+}
+
+int opt_launch_init(OptLaunch& L, int opt_kind, const float* hyper_host) {
+    // learner.py:14-15 raises ValueError("please select a suitable optimizer")
+    NRC_REQUIRE(opt_kind >= NRC_OPT_GD && opt_kind <= NRC_OPT_MOMENTUM, NRC_E_VALUE,
+                "please select a suitable optimizer");
+    L.nseg = 0;
+    L.kind = opt_kind;
+    L.total = 0;
+    for (int i = 0; i < 4; ++i) L.h[i] = hyper_host ? hyper_host[i] : 0.0f;
+    return NRC_OK;
+}
+
+int opt_launch_add(OptLaunch& L, float* var, float* grad, float* s0, float* s1,
+                   const int32_t* touched, int64_t rows, int dim, int dense_var) {
+    NRC_REQUIRE(L.nseg < kMaxOptSegs, NRC_E_LIMIT, "too many optimizer segments");
+    NRC_REQUIRE(rows >= 0 && dim > 0, NRC_E_VALUE, "bad table shape");
+    OptSeg& s = L.seg[L.nseg++];
+    s.var = var; s.grad = grad; s.s0 = s0; s.s1 = s1; s.touched = touched;
+    s.elems = rows * dim; s.begin = L.total; s.dim = dim; s.dense_var = dense_var;
+    L.total += s.elems;
+    return NRC_OK;
+}
+
+int opt_launch_run(const OptLaunch& L, int32_t stamp, cudaStream_t st) {
+    if (L.total == 0) return NRC_OK;
+    OptParams P;
+    for (int i = 0; i < L.nseg; ++i) P.seg[i] = L.seg[i];
+    P.nseg = L.nseg; P.kind = L.kind;
+    P.h0 = L.h[0]; P.h1 = L.h[1]; P.h2 = L.h[2]; P.h3 = L.h[3];
+    P.stamp = stamp; P.total = L.total;
+    int64_t blocks = (L.total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    opt_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(P);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+}  // namespace nrc

@@ -1,0 +1,250 @@
+// MF-family training step: fused triplet gather -> score -> loss -> gradient accumulation,
+// TensorFlow-1.12-faithful optimizer apply, and the per-epoch driver.
+//
+// Replaces (reference paths):
+//   model/general_recommender/MF.py:54-76    _create_inference / _create_loss / _create_optimizer
+//   util/learner.py:2-41                     optimizer / pairwise_loss / pointwise_loss
+//   util/tool.py:216-217                     l2_loss
+//   model/general_recommender/MF.py:92-108   the per-batch sess.run loop of train_model
+// and the third-party arithmetic behind them (tensorflow==1.12.3, not vendored):
+// embedding_lookup gradients as IndexedSlices, duplicate indices summed before the update
+// (optimizer.py::_deduplicate_indexed_slices), Adam applied densely to the whole variable
+// (adam.py::_apply_sparse_shared), other optimizers only to the touched rows.
+//
+// Two phases per step, as TF does (all reads of the pre-step tables happen before any write):
+//   phase 1  one warp per triplet/sample: coalesced row gathers, shuffle-reduced dots,
+//            row gradients added with RED.ADD into dense accumulators (duplicates sum)
+//   phase 2  element-wise optimizer over every table of the model in ONE launch; zeroes the
+//            accumulators for the next step.
+#include "common.cuh"
+#include "optim.cuh"
+
+namespace nrc {
+
+// softplus(-x) = -log_sigmoid(x)  (learner.py:22, tool.py:224)
+__device__ __forceinline__ float neg_log_sigmoid(float x) {
+    return (x >= 0.0f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
+}
+
+// d/dx of the pairwise loss l(x)
+__device__ __forceinline__ void pairwise_loss_grad(int kind, float x, float& l, float& g) {
+    if (kind == NRC_LOSS_BPR) {           // learner.py:21-22  -sum(log_sigmoid(y))
+        l = neg_log_sigmoid(x);
+        g = -1.0f / (1.0f + expf(x));     // -sigmoid(-x)
+    } else if (kind == NRC_LOSS_HINGE) {  // learner.py:23-24  sum(max(y + margin, 0)) [sic]
+        const float t = x + 1.0f;
+        l = fmaxf(t, 0.0f);
+        g = (t > 0.0f) ? 1.0f : 0.0f;
+    } else {                              // learner.py:25-26  sum((1 - y)^2)
+        const float t = 1.0f - x;
+        l = t * t;
+        g = -2.0f * t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mf_pairwise_grad_kernel(const float* __restrict__ U, const float* __restrict__ V, int D,
+                        const int32_t* __restrict__ users, const int32_t* __restrict__ pos,
+                        const int32_t* __restrict__ neg, int64_t batch, int loss_kind, float reg,
+                        float* __restrict__ gU, float* __restrict__ gV,
+                        int32_t* __restrict__ tU, int32_t* __restrict__ tV, int32_t stamp,
+                        float* __restrict__ loss) {
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    float loss_acc = 0.0f;
+    for (int64_t b = (int64_t)blockIdx.x * wpb + wib; b < batch; b += (int64_t)gridDim.x * wpb) {
+        const int u = users[b], i = pos[b], j = neg[b];
+        const float* __restrict__ pu = U + (size_t)u * D;
+        const float* __restrict__ qi = V + (size_t)i * D;
+        const float* __restrict__ qj = V + (size_t)j * D;
+        float di = 0.0f, dj = 0.0f, sq = 0.0f;
+        for (int k = lane; k < D; k += kWarp) {
+            const float a = pu[k], bi = qi[k], bj = qj[k];
+            di = fmaf(a, bi, di);
+            dj = fmaf(a, bj, dj);
+            sq += a * a + bi * bi + bj * bj;
+        }
+        di = warp_sum(di);
+        dj = warp_sum(dj);
+        const float x = di - dj;  // MF.py:66  result = output - output_neg
+        float l, g;
+        pairwise_loss_grad(loss_kind, x, l, g);
+        if (reg != 0.0f) l += reg * 0.5f * warp_sum(sq);  // MF.py:67 reg * l2_loss(p1, q2, q1)
+        loss_acc += l;
+        float* gu = gU + (size_t)u * D;
+        float* gi = gV + (size_t)i * D;
+        float* gj = gV + (size_t)j * D;
+        for (int k = lane; k < D; k += kWarp) {
+            const float a = pu[k], bi = qi[k], bj = qj[k];
+            atomicAdd(gu + k, g * (bi - bj) + reg * a);
+            atomicAdd(gi + k, g * a + reg * bi);
+            atomicAdd(gj + k, -g * a + reg * bj);
+        }
+        if (lane == 0) {
+            tU[u] = stamp;
+            tV[i] = stamp;
+            tV[j] = stamp;
+        }
+    }
+    if (lane == 0 && loss) atomicAdd(loss, loss_acc);
+}
+
+__global__ void __launch_bounds__(256)
+mf_pointwise_grad_kernel(const float* __restrict__ U, const float* __restrict__ V, int D,
+                         const int32_t* __restrict__ users, const int32_t* __restrict__ items,
+                         const float* __restrict__ labels, int64_t batch, int loss_kind, float reg,
+                         float* __restrict__ gU, float* __restrict__ gV,
+                         int32_t* __restrict__ tU, int32_t* __restrict__ tV, int32_t stamp,
+                         float* __restrict__ loss) {
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const float inv_b = 1.0f / (float)batch;
+    float loss_acc = 0.0f;
+    for (int64_t b = (int64_t)blockIdx.x * wpb + wib; b < batch; b += (int64_t)gridDim.x * wpb) {
+        const int u = users[b], i = items[b];
+        const float z = labels[b];
+        const float* __restrict__ pu = U + (size_t)u * D;
+        const float* __restrict__ qi = V + (size_t)i * D;
+        float x = 0.0f, sq = 0.0f;
+        for (int k = lane; k < D; k += kWarp) {
+            const float a = pu[k], bi = qi[k];
+            x = fmaf(a, bi, x);
+            sq += a * a + bi * bi;
+        }
+        x = warp_sum(x);
+        float l, g;
+        if (loss_kind == NRC_LOSS_CROSS_ENTROPY) {
+            // learner.py:33-34 tf.losses.sigmoid_cross_entropy: mean_b of
+            // max(x,0) - x*z + log1p(exp(-|x|))
+            const float e = expf(-fabsf(x));
+            l = (fmaxf(x, 0.0f) - x * z + log1pf(e)) * inv_b;
+            const float s = (x >= 0.0f) ? 1.0f / (1.0f + e) : e / (1.0f + e);
+            g = (s - z) * inv_b;
+        } else {  // learner.py:37-38 sum((y_rea - y_pre)^2)
+            const float t = z - x;
+            l = t * t;
+            g = -2.0f * t;
+        }
+        if (reg != 0.0f) l += reg * 0.5f * warp_sum(sq);  // MF.py:72 reg * l2_loss(p1, q1)
+        loss_acc += l;
+        float* gu = gU + (size_t)u * D;
+        float* gi = gV + (size_t)i * D;
+        for (int k = lane; k < D; k += kWarp) {
+            const float a = pu[k], bi = qi[k];
+            atomicAdd(gu + k, g * bi + reg * a);
+            atomicAdd(gi + k, g * a + reg * bi);
+        }
+        if (lane == 0) {
+            tU[u] = stamp;
+            tV[i] = stamp;
+        }
+    }
+    if (lane == 0 && loss) atomicAdd(loss, loss_acc);
+}
+
+static int grad_grid(int64_t batch) {
+    const int wpb = 8;
+    int64_t blocks = (batch + wpb - 1) / wpb;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace nrc
+
+using namespace nrc;
+
+extern "C" int nrc_mf_pairwise_grad(const float* user_table, const float* item_table, int32_t dim,
+                                    const int32_t* users, const int32_t* pos_items,
+                                    const int32_t* neg_items, int64_t batch, int32_t loss_kind,
+                                    float reg, float* grad_user, float* grad_item,
+                                    int32_t* touched_user, int32_t* touched_item, int32_t stamp,
+                                    float* loss, void* stream) {
+    // learner.py:27-28 raises for an unknown loss
+    NRC_REQUIRE(loss_kind == NRC_LOSS_BPR || loss_kind == NRC_LOSS_HINGE ||
+                    loss_kind == NRC_LOSS_SQUARE,
+                NRC_E_VALUE, "please choose a suitable loss function");
+    NRC_REQUIRE(dim > 0 && batch >= 0, NRC_E_VALUE, "dim must be positive, batch >= 0");
+    if (batch == 0) return NRC_OK;
+    mf_pairwise_grad_kernel<<<grad_grid(batch), 256, 0, as_stream(stream)>>>(
+        user_table, item_table, dim, users, pos_items, neg_items, batch, loss_kind, reg, grad_user,
+        grad_item, touched_user, touched_item, stamp, loss);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+extern "C" int nrc_mf_pointwise_grad(const float* user_table, const float* item_table, int32_t dim,
+                                     const int32_t* users, const int32_t* items,
+                                     const float* labels, int64_t batch, int32_t loss_kind,
+                                     float reg, float* grad_user, float* grad_item,
+                                     int32_t* touched_user, int32_t* touched_item, int32_t stamp,
+                                     float* loss, void* stream) {
+    // learner.py:39-40
+    NRC_REQUIRE(loss_kind == NRC_LOSS_CROSS_ENTROPY || loss_kind == NRC_LOSS_SQUARE, NRC_E_VALUE,
+                "please choose a suitable loss function");
+    NRC_REQUIRE(dim > 0 && batch >= 0, NRC_E_VALUE, "dim must be positive, batch >= 0");
+    if (batch == 0) return NRC_OK;
+    mf_pointwise_grad_kernel<<<grad_grid(batch), 256, 0, as_stream(stream)>>>(
+        user_table, item_table, dim, users, items, labels, batch, loss_kind, reg, grad_user,
+        grad_item, touched_user, touched_item, stamp, loss);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+extern "C" int nrc_opt_apply_rows(int32_t opt_kind, float* var, float* grad, float* slot0,
+                                  float* slot1, const int32_t* touched, int32_t stamp, int64_t rows,
+                                  int32_t dim, const float* hyper_host, void* stream) {
+    OptLaunch L;
+    int rc = opt_launch_init(L, opt_kind, hyper_host);
+    if (rc) return rc;
+    rc = opt_launch_add(L, var, grad, slot0, slot1, touched, rows, dim, /*dense_var=*/0);
+    if (rc) return rc;
+    return opt_launch_run(L, stamp, as_stream(stream));
+}
+
+extern "C" int nrc_mf_train_epoch(float* user_table, float* item_table, int32_t num_users,
+                                  int32_t num_items, int32_t dim, const int32_t* users,
+                                  const int32_t* items, const void* third, int64_t n,
+                                  int32_t batch_size, int32_t pairwise, int32_t loss_kind, float reg,
+                                  int32_t opt_kind, const float* lr_t_host, const float* hyper_host,
+                                  float* grad_user, float* grad_item, int32_t* touched_user,
+                                  int32_t* touched_item, float* slot0_user, float* slot1_user,
+                                  float* slot0_item, float* slot1_item, int32_t first_stamp,
+                                  float* step_loss, void* stream) {
+    NRC_REQUIRE(batch_size > 0, NRC_E_VALUE, "batch_size should be a positive integeral value");
+    NRC_REQUIRE(n >= 0 && dim > 0, NRC_E_VALUE, "n >= 0 and dim > 0 required");
+    cudaStream_t st = as_stream(stream);
+    const int64_t steps = (n + batch_size - 1) / batch_size;  // sampler.py:208-213
+    if (steps == 0) return NRC_OK;
+    NRC_CUDA_CHECK(cudaMemsetAsync(step_loss, 0, (size_t)steps * sizeof(float), st));
+    float hyper[4] = {hyper_host[0], hyper_host[1], hyper_host[2], hyper_host[3]};
+    for (int64_t s = 0; s < steps; ++s) {
+        const int64_t off = s * batch_size;
+        const int64_t bs = (n - off < batch_size) ? (n - off) : batch_size;
+        const int32_t stamp = first_stamp + (int32_t)s;
+        int rc;
+        if (pairwise)
+            rc = nrc_mf_pairwise_grad(user_table, item_table, dim, users + off, items + off,
+                                      reinterpret_cast<const int32_t*>(third) + off, bs, loss_kind,
+                                      reg, grad_user, grad_item, touched_user, touched_item, stamp,
+                                      step_loss + s, stream);
+        else
+            rc = nrc_mf_pointwise_grad(user_table, item_table, dim, users + off, items + off,
+                                       reinterpret_cast<const float*>(third) + off, bs, loss_kind,
+                                       reg, grad_user, grad_item, touched_user, touched_item, stamp,
+                                       step_loss + s, stream);
+        if (rc) return rc;
+        if (opt_kind == NRC_OPT_ADAM) hyper[0] = lr_t_host[s];
+        OptLaunch L;
+        rc = opt_launch_init(L, opt_kind, hyper);
+        if (rc) return rc;
+        opt_launch_add(L, user_table, grad_user, slot0_user, slot1_user, touched_user, num_users, dim, 0);
+        opt_launch_add(L, item_table, grad_item, slot0_item, slot1_item, touched_item, num_items, dim, 0);
+        rc = opt_launch_run(L, stamp, st);
+        if (rc) return rc;
+    }
+    return NRC_OK;
+}

@@ -1,0 +1,203 @@
+"""Tensor-facing wrappers of the C ABI (torch.Tensor is only the device buffer).
+
+Every function launches hand-written sm_100a kernels from ``libneurec_b200.so`` on the
+current torch CUDA stream.  Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LOSS_IDS, METRIC_IDS, OPT_IDS, check
+
+launch_count = 0  # kernels launched through this module (bench.py reports it)
+
+
+def _p(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise TypeError("'%s' must be a contiguous CUDA tensor of dtype %s" % (name, dtype))
+    return t
+
+
+def _metric_arr(metric):
+    ids = [METRIC_IDS[m] if isinstance(m, str) else int(m) for m in metric]
+    return np.asarray(ids, dtype=np.int32)
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+# ------------------------------------------------------------------------------- evaluator
+def eval_score_matrix(scores, test_indptr, test_indices, metric, top_k, return_ranks=False):
+    """Device drop-in of CPPEvaluator.eval_score_matrix (cpp_evaluator.pyx:28-42)."""
+    _req(scores, torch.float32, "scores")
+    _req(test_indptr, torch.int64, "test_indptr")
+    _req(test_indices, torch.int32, "test_indices")
+    B, N = scores.shape
+    m = _metric_arr(metric)
+    res = torch.empty((B, len(m) * top_k), dtype=torch.float32, device=scores.device)
+    ranks = torch.empty((B, top_k), dtype=torch.int32, device=scores.device) if return_ranks else None
+    check(_lib.load().nrc_eval_score_matrix(_p(scores), N, B, _p(test_indptr), _p(test_indices),
+                                            m.ctypes.data, len(m), top_k, _p(res), _p(ranks),
+                                            _stream()))
+    _count()
+    return (res, ranks) if return_ranks else res
+
+
+def eval_score_matrix_host(scores, test_indptr, test_indices, metric, top_k, return_ranks=False):
+    """Host-buffer drop-in (numpy in, numpy out); H2D/D2H happen inside the call."""
+    scores = np.ascontiguousarray(scores, dtype=np.float32)
+    test_indptr = np.ascontiguousarray(test_indptr, dtype=np.int64)
+    test_indices = np.ascontiguousarray(test_indices, dtype=np.int32)
+    B, N = scores.shape
+    m = _metric_arr(metric)
+    res = np.empty((B, len(m) * top_k), dtype=np.float32)
+    ranks = np.empty((B, top_k), dtype=np.int32) if return_ranks else None
+    check(_lib.load().nrc_eval_score_matrix_host(
+        scores.ctypes.data, N, B, test_indptr.ctypes.data, test_indices.ctypes.data,
+        m.ctypes.data, len(m), top_k, res.ctypes.data,
+        ranks.ctypes.data if ranks is not None else None))
+    _count()
+    return (res, ranks) if return_ranks else res
+
+
+def arg_topk(scores, top_k):
+    """Device drop-in of util.cython.arg_topk.arg_topk (arg_topk.pyx:16-35)."""
+    _req(scores, torch.float32, "scores")
+    U, N = scores.shape
+    out = torch.empty((U, top_k), dtype=torch.int32, device=scores.device)
+    check(_lib.load().nrc_arg_topk(_p(scores), N, U, top_k, _p(out), _stream()))
+    _count()
+    return out
+
+
+def arg_topk_host(scores, top_k):
+    scores = np.ascontiguousarray(scores, dtype=np.float32)
+    U, N = scores.shape
+    out = np.empty((U, top_k), dtype=np.int32)
+    check(_lib.load().nrc_arg_topk_host(scores.ctypes.data, N, U, top_k, out.ctypes.data))
+    _count()
+    return out
+
+
+def eval_mf(user_table, item_table, users, train_indptr, train_indices, test_indptr,
+            test_indices, metric, top_k, return_ranks=False, want_results=True):
+    """Fused predict -> mask -> top-K -> metrics (uni_evaluator.py:132-146, MF.py:120-122)."""
+    _req(user_table, torch.float32, "user_table")
+    _req(item_table, torch.float32, "item_table")
+    _req(users, torch.int32, "users")
+    _req(train_indptr, torch.int64, "train_indptr")
+    _req(train_indices, torch.int32, "train_indices")
+    _req(test_indptr, torch.int64, "test_indptr")
+    _req(test_indices, torch.int32, "test_indices")
+    N, D = item_table.shape
+    B = users.numel()
+    m = _metric_arr(metric)
+    dev = users.device
+    res = torch.empty((B, len(m) * top_k), dtype=torch.float32, device=dev) if want_results else None
+    ranks = torch.empty((B, top_k), dtype=torch.int32, device=dev) if return_ranks else None
+    check(_lib.load().nrc_eval_mf(_p(user_table), _p(item_table), D, N, _p(users), B,
+                                  _p(train_indptr), _p(train_indices), _p(test_indptr),
+                                  _p(test_indices), m.ctypes.data, len(m), top_k, _p(res),
+                                  _p(ranks), _stream()))
+    _count()
+    return (res, ranks) if return_ranks else res
+
+
+def mean_rows(results):
+    """np.mean(results, axis=0) with numpy's fp32 summation order (uni_evaluator.py:150)."""
+    _req(results, torch.float32, "results")
+    rows, cols = results.shape
+    out = torch.empty((cols,), dtype=torch.float32, device=results.device)
+    check(_lib.load().nrc_mean_rows(_p(results), rows, cols, _p(out), _stream()))
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------------- sampler
+def sample_negatives(train_indptr, train_indices, users, neg_num, num_items, seed, stream_id,
+                     first_index=0):
+    """_sampling_negative_items (sampler.py:71-90): [n, neg_num] negatives, on device."""
+    _req(train_indptr, torch.int64, "train_indptr")
+    _req(train_indices, torch.int32, "train_indices")
+    _req(users, torch.int32, "users")
+    n = users.numel()
+    out = torch.empty((n, max(int(neg_num), 0)), dtype=torch.int32, device=users.device)
+    check(_lib.load().nrc_sample_negatives(_p(train_indptr), _p(train_indices), _p(users), n,
+                                           int(neg_num), int(num_items), int(seed),
+                                           int(stream_id), int(first_index), _p(out), _stream()))
+    _count()
+    return out
+
+
+def batch_randint_choice(high, out_indptr, total_out, replace=True, excl_indptr=None,
+                         excl_indices=None, seed=0, stream_id=0):
+    """batch_randint_choice (random_choice.pyx:64-89) on device CSR inputs; flat output."""
+    _req(out_indptr, torch.int64, "out_indptr")
+    n_rows = out_indptr.numel() - 1
+    out = torch.empty((int(total_out),), dtype=torch.int32, device=out_indptr.device)
+    check(_lib.load().nrc_batch_randint_choice(int(high), _p(out_indptr), n_rows, int(total_out),
+                                               1 if replace else 0, _p(excl_indptr),
+                                               _p(excl_indices), int(seed), int(stream_id),
+                                               _p(out), _stream()))
+    _count()
+    return out
+
+
+# -------------------------------------------------------------------------------- training
+def mf_pairwise_grad(U, V, users, pos, neg, loss, reg, gU, gV, tU, tV, stamp, loss_out):
+    check(_lib.load().nrc_mf_pairwise_grad(_p(U), _p(V), U.shape[1], _p(users), _p(pos), _p(neg),
+                                           users.numel(), LOSS_IDS[loss], float(reg), _p(gU),
+                                           _p(gV), _p(tU), _p(tV), int(stamp), _p(loss_out),
+                                           _stream()))
+    _count()
+
+
+def mf_pointwise_grad(U, V, users, items, labels, loss, reg, gU, gV, tU, tV, stamp, loss_out):
+    check(_lib.load().nrc_mf_pointwise_grad(_p(U), _p(V), U.shape[1], _p(users), _p(items),
+                                            _p(labels), users.numel(), LOSS_IDS[loss], float(reg),
+                                            _p(gU), _p(gV), _p(tU), _p(tV), int(stamp),
+                                            _p(loss_out), _stream()))
+    _count()
+
+
+def opt_apply_rows(opt, var, grad, slot0, slot1, touched, stamp, hyper):
+    h = np.zeros(4, dtype=np.float32)
+    h[:len(hyper)] = hyper
+    rows, dim = var.shape
+    check(_lib.load().nrc_opt_apply_rows(OPT_IDS[opt], _p(var), _p(grad), _p(slot0), _p(slot1),
+                                         _p(touched), int(stamp), rows, dim, h.ctypes.data,
+                                         _stream()))
+    _count()
+
+
+def mf_train_epoch(U, V, users, items, third, batch_size, pairwise, loss, reg, opt, lr_t, hyper,
+                   gU, gV, tU, tV, s0U, s1U, s0V, s1V, first_stamp, step_loss):
+    n = users.numel()
+    steps = (n + batch_size - 1) // batch_size
+    lr_t = np.ascontiguousarray(lr_t, dtype=np.float32)
+    assert lr_t.size >= max(steps, 1)
+    h = np.zeros(4, dtype=np.float32)
+    h[:len(hyper)] = hyper
+    check(_lib.load().nrc_mf_train_epoch(
+        _p(U), _p(V), U.shape[0], V.shape[0], U.shape[1], _p(users), _p(items), _p(third), n,
+        int(batch_size), 1 if pairwise else 0, LOSS_IDS[loss], float(reg), OPT_IDS[opt],
+        lr_t.ctypes.data, h.ctypes.data, _p(gU), _p(gV), _p(tU), _p(tV), _p(s0U), _p(s1U),
+        _p(s0V), _p(s1V), int(first_stamp), _p(step_loss), _stream()))
+    _count(2 * steps)
+    return steps

@@ -207,6 +207,35 @@ def batch_randint_choice(high, sizes, replace=True, exclusion_csr=None):
     return out
 
 
+def philox_sample_negatives(train_indptr, train_indices, users, neg_num, num_items, seed,
+                            stream_id, first_index=0):
+    """CPU restatement of the product's Philox sampler (bit-exact target for the kernel)."""
+    tp, tpp = _i64(train_indptr)
+    ti, tip = _i32(train_indices)
+    us, usp = _i32(users)
+    out = np.empty((len(us), neg_num), dtype=np.int32)
+    lib().orc_philox_sample_negatives(tpp, tip, usp, ctypes.c_int64(len(us)), ctypes.c_int(neg_num),
+                                      ctypes.c_int(num_items), ctypes.c_uint64(seed),
+                                      ctypes.c_uint64(stream_id), ctypes.c_int64(first_index),
+                                      out.ctypes.data_as(_c_i32p))
+    return out
+
+
+def philox_batch_choice(high, out_indptr, replace=True, exclusion_csr=None, seed=0, stream_id=0):
+    op, opp = _i64(out_indptr)
+    out = np.empty(int(op[-1]), dtype=np.int32)
+    if exclusion_csr is not None:
+        ei, eip = _i64(exclusion_csr[0])
+        ex, exp_ = _i32(exclusion_csr[1])
+    else:
+        eip, exp_ = None, None
+    lib().orc_philox_batch_choice(ctypes.c_int(high), opp, ctypes.c_int(len(op) - 1),
+                                  ctypes.c_int(1 if replace else 0), eip, exp_,
+                                  ctypes.c_uint64(seed), ctypes.c_uint64(stream_id),
+                                  out.ctypes.data_as(_c_i32p))
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # Importing the REAL Python reference (build container only; never on the GPU box)
 # ----------------------------------------------------------------------------------------

@@ -1,0 +1,208 @@
+"""GPU parity tests of the negative sampler and of the MF-family training step.
+
+Sampler: bit-exact against the CPU restatement of the product's Philox stream + the
+reference's contract (data/sampler.py:71-90): never a train item of the user, uniform over the
+rest, aligned with the positives, fresh per epoch.
+Training: fp32 with atomics => tolerance (stated per test) against oracle/tf_math.py fed the
+SAME triplets; the optimizer arithmetic alone is bit-exact given an identical gradient."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import tf_math
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------ sampler
+def test_sampler_bit_exact_vs_cpu_restatement(ml100k):
+    from neurec_b200 import ops
+    d = ml100k
+    users = np.repeat(np.arange(d["num_users"], dtype=np.int32), np.diff(d["train_indptr"]))
+    for neg_num, seed, sid, first in [(1, 2018, 0, 0), (4, 7, 3, 0), (2, 2 ** 40 + 5, 2 ** 33 + 1, 1000)]:
+        got = ops.sample_negatives(dev(d["train_indptr"]), dev(d["train_indices"]), dev(users), neg_num,
+                                   d["num_items"], seed, sid, first).cpu().numpy()
+        want = oracle.philox_sample_negatives(d["train_indptr"], d["train_indices"], users, neg_num,
+                                              d["num_items"], seed, sid, first)
+        assert np.array_equal(got, want)
+
+
+def test_sampler_contract(ml100k):
+    from neurec_b200 import ops
+    d = ml100k
+    ip, ix = d["train_indptr"], d["train_indices"]
+    users = np.repeat(np.arange(d["num_users"], dtype=np.int32), np.diff(ip))
+    a = ops.sample_negatives(dev(ip), dev(ix), dev(users), 1, d["num_items"], 1, 0).cpu().numpy()[:, 0]
+    b = ops.sample_negatives(dev(ip), dev(ix), dev(users), 1, d["num_items"], 1, 1).cpu().numpy()[:, 0]
+    assert a.min() >= 0 and a.max() < d["num_items"]
+    assert (a != b).mean() > 0.99                      # new negatives every epoch (stream_id)
+    train_sets = [set(ix[ip[u]:ip[u + 1]].tolist()) for u in range(d["num_users"])]
+    assert not any(int(n) in train_sets[u] for u, n in zip(users, a))
+    # shard invariance: sampling the second half alone gives the same numbers
+    h = len(users) // 2
+    c = ops.sample_negatives(dev(ip), dev(ix), dev(users[h:]), 1, d["num_items"], 1, 0, first_index=h)
+    assert np.array_equal(c.cpu().numpy()[:, 0], a[h:])
+    # uniformity over the allowed items of the heaviest user (chi-square, 5 sigma)
+    u = int(np.argmax(np.diff(ip)))
+    reps = 200000
+    s = ops.sample_negatives(dev(ip), dev(ix), dev(np.full(reps, u, np.int32)), 1, d["num_items"], 3, 9)
+    s = s.cpu().numpy()[:, 0]
+    allowed = np.setdiff1d(np.arange(d["num_items"]), ix[ip[u]:ip[u + 1]])
+    cnt = np.bincount(s, minlength=d["num_items"])[allowed]
+    exp = reps / len(allowed)
+    chi2 = ((cnt - exp) ** 2 / exp).sum()
+    dof = len(allowed) - 1
+    assert abs(chi2 - dof) < 5 * np.sqrt(2 * dof)
+
+
+def test_batch_randint_choice_modes():
+    from neurec_b200 import ops
+    rs = np.random.RandomState(0)
+    high = 300
+    sizes = rs.randint(1, 40, 57)
+    optr = np.zeros(58, np.int64); optr[1:] = np.cumsum(sizes)
+    ep, ei = oracle.lists_to_csr([rs.choice(high, rs.randint(0, 200), replace=False) for _ in range(57)])
+    for replace in (True, False):
+        got = ops.batch_randint_choice(high, dev(optr), int(optr[-1]), replace, dev(ep), dev(ei), 11, 2)
+        got = got.cpu().numpy()
+        want = oracle.philox_batch_choice(high, optr, replace, (ep, ei), 11, 2)
+        assert np.array_equal(got, want)
+        for r in range(57):
+            row = got[optr[r]:optr[r + 1]]
+            assert not np.isin(row, ei[ep[r]:ep[r + 1]]).any()
+            if not replace:
+                assert len(set(row.tolist())) == len(row)
+    got = ops.batch_randint_choice(high, dev(optr), int(optr[-1]), True, None, None, 1, 0).cpu().numpy()
+    assert got.min() >= 0 and got.max() < high
+    with pytest.raises(ValueError):
+        ops.sample_negatives(dev(ep), dev(ei), dev(np.zeros(3, np.int32)), 0, high, 1, 0)
+
+
+# ----------------------------------------------------------------------------- training
+def _tables(nu, ni, dim, seed=0, scale=0.1):
+    rs = np.random.RandomState(seed)
+    return (rs.randn(nu, dim) * scale).astype(np.float32), (rs.randn(ni, dim) * scale).astype(np.float32)
+
+
+@pytest.mark.parametrize("loss", ["bpr", "hinge", "square"])
+@pytest.mark.parametrize("dim", [64, 20])
+def test_pairwise_grad_vs_oracle(loss, dim):
+    from neurec_b200 import ops
+    nu, ni, bs = 50, 80, 512            # heavy duplication of users and items inside the batch
+    U, V = _tables(nu, ni, dim, 1)
+    rs = np.random.RandomState(2)
+    users = rs.randint(0, nu, bs).astype(np.int32)
+    pos = rs.randint(0, ni, bs).astype(np.int32)
+    neg = rs.randint(0, ni, bs).astype(np.int32)
+    l, gU, gV, tU, tV = tf_math.mf_pairwise_grad(U, V, users, pos, neg, loss, reg=0.01)
+    dgU = torch.zeros(nu, dim, device="cuda"); dgV = torch.zeros(ni, dim, device="cuda")
+    dtU = torch.zeros(nu, dtype=torch.int32, device="cuda"); dtV = torch.zeros(ni, dtype=torch.int32, device="cuda")
+    dl = torch.zeros(1, device="cuda")
+    ops.mf_pairwise_grad(dev(U), dev(V), dev(users), dev(pos), dev(neg), loss, 0.01, dgU, dgV, dtU, dtV, 5, dl)
+    # tolerance: fp32 sums of <= ~30 duplicate contributions in arbitrary (atomic) order
+    assert np.allclose(dgU.cpu().numpy(), gU, rtol=1e-4, atol=1e-6)
+    assert np.allclose(dgV.cpu().numpy(), gV, rtol=1e-4, atol=1e-6)
+    assert np.isclose(dl.item(), l, rtol=1e-5)
+    assert np.array_equal(dtU.cpu().numpy() == 5, tU) and np.array_equal(dtV.cpu().numpy() == 5, tV)
+
+
+@pytest.mark.parametrize("loss", ["cross_entropy", "square"])
+def test_pointwise_grad_vs_oracle(loss):
+    from neurec_b200 import ops
+    nu, ni, bs, dim = 40, 60, 256, 32
+    U, V = _tables(nu, ni, dim, 3, scale=0.5)
+    rs = np.random.RandomState(4)
+    users = rs.randint(0, nu, bs).astype(np.int32)
+    items = rs.randint(0, ni, bs).astype(np.int32)
+    labels = (rs.rand(bs) < 0.2).astype(np.float32)
+    l, gU, gV, tU, tV = tf_math.mf_pointwise_grad(U, V, users, items, labels, loss, reg=0.001)
+    dgU = torch.zeros(nu, dim, device="cuda"); dgV = torch.zeros(ni, dim, device="cuda")
+    dtU = torch.zeros(nu, dtype=torch.int32, device="cuda"); dtV = torch.zeros(ni, dtype=torch.int32, device="cuda")
+    dl = torch.zeros(1, device="cuda")
+    ops.mf_pointwise_grad(dev(U), dev(V), dev(users), dev(items), dev(labels), loss, 0.001, dgU, dgV, dtU, dtV, 1, dl)
+    assert np.allclose(dgU.cpu().numpy(), gU, rtol=1e-4, atol=1e-6)
+    assert np.allclose(dgV.cpu().numpy(), gV, rtol=1e-4, atol=1e-6)
+    assert np.isclose(dl.item(), l, rtol=1e-5)
+
+
+@pytest.mark.parametrize("opt", ["gd", "adam", "adagrad", "rmsprop", "momentum"])
+def test_optimizer_apply_bit_exact(opt):
+    """Given the same gradient the TF-1.12 update rules are bit-identical to the numpy oracle."""
+    from neurec_b200 import ops
+    rs = np.random.RandomState(5)
+    rows, dim = 37, 24
+    var = rs.randn(rows, dim).astype(np.float32)
+    i0, i1 = tf_math.SLOT_INIT[opt]
+    s0 = None if i0 is None else (np.abs(rs.randn(rows, dim)) * 0.1 + i0).astype(np.float32)
+    s1 = None if i1 is None else (np.abs(rs.randn(rows, dim)) * 0.1 + i1).astype(np.float32)
+    touched = rs.rand(rows) < 0.4
+    g = np.zeros((rows, dim), np.float32)
+    g[touched] = rs.randn(int(touched.sum()), dim).astype(np.float32)
+    hyper = tf_math.DEFAULT_HYPER[opt](0.05)
+    if opt == "adam":
+        hyper[0] = float(tf_math.adam_lr_t(0.05, 3)[2])
+    dvar, dg = dev(var), dev(g)
+    ds0 = dev(s0) if s0 is not None else None
+    ds1 = dev(s1) if s1 is not None else None
+    stamps = dev(np.where(touched, 9, 3).astype(np.int32))
+    ops.opt_apply_rows(opt, dvar, dg, ds0, ds1, stamps, 9, hyper)
+    tf_math.opt_apply(opt, var, g, s0, s1, touched, hyper)
+    assert np.array_equal(dvar.cpu().numpy(), var)
+    if s0 is not None:
+        assert np.array_equal(ds0.cpu().numpy(), s0)
+    if s1 is not None:
+        assert np.array_equal(ds1.cpu().numpy(), s1)
+    assert float(dg.abs().max()) == 0.0  # gradient buffer zeroed for the next step
+
+
+@pytest.mark.parametrize("opt,pairwise,loss", [("adam", True, "bpr"), ("gd", True, "bpr"),
+                                               ("adagrad", False, "cross_entropy"),
+                                               ("rmsprop", True, "hinge"), ("momentum", False, "square")])
+def test_train_epoch_vs_oracle(ml100k, opt, pairwise, loss):
+    """A real ml-100k epoch prefix (conf/MF.properties: bs 512, d 64): same triplet stream into
+    the kernel and the oracle.  Tolerance: tables within 2e-5 abs after 20 steps (fp32
+    re-association through atomics; Adam's division by sqrt(v)+1e-8 amplifies gradient ulps
+    at the first steps), per-step loss within 1e-4 relative."""
+    from neurec_b200 import ops
+    d = ml100k
+    nu, ni, dim, bs, steps = d["num_users"], d["num_items"], 64, 512, 20
+    rs = np.random.RandomState(11)
+    U0 = (rs.randn(nu, dim) * 0.01).astype(np.float32)
+    V0 = (rs.randn(ni, dim) * 0.01).astype(np.float32)
+    all_users = np.repeat(np.arange(nu, dtype=np.int32), np.diff(d["train_indptr"]))
+    perm = rs.permutation(len(all_users))[:bs * steps - 100]     # last batch is short
+    users = all_users[perm]; items = d["train_indices"][perm]
+    lr = 0.05 if opt in ("gd", "momentum") else 1e-3
+    if opt == "adagrad":
+        lr = 0.01
+    if pairwise:
+        neg = oracle.philox_sample_negatives(d["train_indptr"], d["train_indices"], users, 1, ni, 5, 0)[:, 0]
+        third = neg
+    else:
+        third = (rs.rand(len(users)) < 0.5).astype(np.float32)
+    tr = tf_math.MFTrainer(U0, V0, opt, lr, loss, reg=0.001, pairwise=pairwise)
+    want_loss = tr.epoch(users, items, third, bs)
+
+    dU, dV = dev(U0), dev(V0)
+    z = lambda a: torch.zeros_like(a)
+    i0, i1 = tf_math.SLOT_INIT[opt]
+    mk = lambda a, v: None if v is None else torch.full_like(a, v)
+    s0U, s1U, s0V, s1V = mk(dU, i0), mk(dU, i1), mk(dV, i0), mk(dV, i1)
+    gU, gV = z(dU), z(dV)
+    tU = torch.zeros(nu, dtype=torch.int32, device="cuda"); tV = torch.zeros(ni, dtype=torch.int32, device="cuda")
+    step_loss = torch.zeros(steps, device="cuda")
+    hyper = tf_math.DEFAULT_HYPER[opt](lr)
+    lr_t = tf_math.adam_lr_t(lr, steps) if opt == "adam" else np.full(steps, lr, np.float32)
+    n = ops.mf_train_epoch(dU, dV, dev(users), dev(items), dev(third), bs, pairwise, loss, 0.001, opt,
+                           lr_t, hyper, gU, gV, tU, tV, s0U, s1U, s0V, s1V, 1, step_loss)
+    assert n == steps
+    assert np.allclose(step_loss.cpu().numpy(), want_loss, rtol=1e-4)
+    assert np.abs(dU.cpu().numpy() - tr.U).max() < 2e-5
+    assert np.abs(dV.cpu().numpy() - tr.V).max() < 2e-5
+    # the tables really moved
+    assert np.abs(tr.U - U0).max() > 1e-4

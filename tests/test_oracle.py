@@ -1,0 +1,222 @@
+"""CPU tests: the oracle against the golden vectors captured from the REAL reference
+(tests/golden/make_golden.py) and, when oracle/_ref is built, live against the reference's own
+compiled headers.  No GPU needed."""
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import tf_math
+from conftest import ROOT, parse_result_string
+
+ALL = [1, 2, 3, 4, 5]
+
+
+def test_kat2_evaluator_golden(golden_eval):
+    g = golden_eval
+    out, ranks = oracle.evaluate_matrix(g["kat2_scores"], g["kat2_truth_indptr"],
+                                        g["kat2_truth_indices"], ALL, 5, return_ranks=True)
+    assert np.array_equal(out, g["kat2_out"])
+    assert np.array_equal(ranks, g["kat2_top5"])
+    out2 = oracle.evaluate_matrix(g["kat2_scores"], g["kat2_truth_indptr"],
+                                  g["kat2_truth_indices"], [4, 1, 3, 2, 5], 5, thread_num=2)
+    assert np.array_equal(out2, g["kat2_out_41325"])
+
+
+def test_kat3_tie_order_golden(golden_eval):
+    g = golden_eval
+    assert np.array_equal(oracle.arg_topk(np.zeros((1, 40), np.float32), 5), g["tie_zeros_top5"])
+    assert g["tie_zeros_top5"].tolist() == [[3, 4, 1, 0, 2]]
+    m3 = np.zeros((1, 40), np.float32); m3[0, ::3] = 1
+    assert np.array_equal(oracle.arg_topk(m3, 8), g["tie_mult3_top8"])
+    inf = np.full((1, 40), -np.inf, np.float32); inf[0, 7] = 1; inf[0, 3] = 2
+    assert np.array_equal(oracle.arg_topk(inf, 5), g["tie_inf_top5"])
+    assert np.array_equal(oracle.arg_topk(g["tie_scores"], 20), g["tie_top20"])
+    assert np.array_equal(oracle.arg_topk(g["tie_scores"], 40, thread_num=3), g["tie_top40"])
+    out = oracle.evaluate_matrix(g["tie_scores"], g["tie_truth_indptr"], g["tie_truth_indices"],
+                                 ALL, 20)
+    assert np.array_equal(out, g["tie_out_k20"])
+
+
+@pytest.mark.skipif(oracle.ref_lib() is None, reason="oracle/_ref not built")
+def test_restatement_vs_live_reference_headers():
+    for trial in range(120):
+        rs = np.random.RandomState(trial)
+        n = int(rs.randint(5, 400)); k = int(rs.randint(1, min(n // 2, 50) + 1))
+        if trial % 2:
+            S = rs.randint(0, 4, size=(9, n)).astype(np.float32)
+        else:
+            S = rs.randn(9, n).astype(np.float32)
+        if trial % 3 == 0:
+            S[rs.rand(9, n) < 0.3] = -np.inf
+        assert np.array_equal(oracle.arg_topk(S, k), oracle.arg_topk(S, k, impl="reference"))
+        ip, ix = oracle.lists_to_csr([rs.choice(n, rs.randint(1, 30), replace=True) for _ in range(9)])
+        a = oracle.evaluate_matrix(S, ip, ix, ALL, k)
+        b = oracle.evaluate_matrix(S, ip, ix, ALL, k, thread_num=4, impl="reference")
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+def _fresh(code):
+    r = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r)\n" % ROOT + code],
+                       capture_output=True, text=True, check=True)
+    return r.stdout.strip().splitlines()[-1]
+
+
+def test_kat1_libc_sampler_golden(golden_sampler):
+    """glibc rand() stream (seed 1) in a fresh process reproduces the reference's draws."""
+    g = golden_sampler
+    got = _fresh(
+        "import oracle, json, numpy as np\n"
+        "a = oracle.batch_randint_choice(100, [5], True, oracle.lists_to_csr([[1,2,3]]))\n"
+        "b = oracle.batch_randint_choice(40981, [4], True, None)\n"
+        "print(json.dumps({'a': a.tolist(), 'b': b.tolist()}))")
+    import json
+    got = json.loads(got)
+    assert got["a"] == g["a"]["a"] == [93, 69, 35, 0, 34]
+    assert got["b"] == g["a"]["b"]
+    got = json.loads(_fresh(
+        "import oracle, json, numpy as np\n"
+        "a = oracle.batch_randint_choice(100, [5], True, oracle.lists_to_csr([[1,2,3]]))\n"
+        "c = oracle.batch_randint_choice(1682, [3,2], True, oracle.lists_to_csr([[0,1],[5]]))\n"
+        "d = oracle.batch_randint_choice(50, [1], True, oracle.lists_to_csr([list(range(40))]))\n"
+        "e = oracle.batch_randint_choice(30, [10], False, oracle.lists_to_csr([[0,1,2]]))\n"
+        "print(json.dumps({'c': c.tolist(), 'd': d.tolist(), 'e': e.tolist()}))"))
+    assert got["c"] == g["b"]["c"][0] + g["b"]["c"][1]
+    assert got["d"] == [g["b"]["d"]]
+    assert got["e"] == g["b"]["e"]
+
+
+def test_pairwise_sampler_epoch_golden(golden_sampler, ml100k):
+    """First negatives of the reference's PairwiseSampler epoch on ml-100k == the C
+    restatement fed the same (user, n_pos, exclusion) rows in a fresh process."""
+    g = golden_sampler["pairwise"]
+    import json
+    got = json.loads(_fresh(
+        "import oracle, json, numpy as np\n"
+        "z = np.load(%r)\n"
+        "ip = z['train_indptr'].astype(np.int64); ix = z['train_indices'].astype(np.int32)\n"
+        "sizes = np.diff(ip)[:3].astype(np.int32)\n"
+        "neg = oracle.batch_randint_choice(int(z['num_items']), sizes, True, (ip[:4], ix[:ip[3]]))\n"
+        "print(json.dumps(neg[:64].tolist()))" % (ROOT + "/tests/golden/ml100k_split.npz")))
+    assert got == g["neg"]
+    # positives are flattened in ascending-user order (sampler.py:24-39)
+    users = np.repeat(np.arange(ml100k["num_users"]), np.diff(ml100k["train_indptr"]))
+    assert users[:64].tolist() == g["users"]
+    assert ml100k["train_indices"][:64].tolist() == g["pos"]
+    assert g["len"] == (len(ml100k["train_indices"]) + 511) // 512 == 157
+
+
+def test_kat5_ml100k_full_evaluator(ml100k, golden_ml100k_eval):
+    """Whole UniEvaluator pass on the ml-100k split: oracle (fp32 FMA-chain predict) vs the
+    reference run (np.matmul predict).  Scores differ in the last ulp, so a near-tie may flip:
+    the north-star tolerance is 1e-5 on the averaged metrics."""
+    d = ml100k
+    rng = np.random.RandomState(1)
+    U = (rng.randn(d["num_users"], 64) * .01).astype(np.float32)
+    V = (rng.randn(d["num_items"], 64) * .01).astype(np.float32)
+    users = np.arange(d["num_users"], dtype=np.int32)
+    res = oracle.eval_mf(U, V, users, d["train_indptr"], d["train_indices"], d["test_indptr"],
+                         d["test_indices"], [1, 2, 4, 3, 5], 20, thread_num=4)
+    mean = res.mean(axis=0).reshape(5, 20)[:, [9, 19]].reshape(-1)
+    want = parse_result_string(golden_ml100k_eval["eval_topk_10_20"])
+    assert np.abs(mean - want).max() < 1e-5
+    # exact-predict variant: same scores as the reference (np.matmul) => identical string
+    S = np.matmul(U, V.T)
+    oracle.mask_train(S, users, d["train_indptr"], d["train_indices"])
+    res2 = oracle.evaluate_matrix(S, d["test_indptr"], d["test_indices"], [1, 2, 4, 3, 5], 20)
+    # the reference evaluates in batches of 128 and np.mean's the concatenation (fp32)
+    final = np.mean(res2, axis=0).reshape(5, 20)[:, [9, 19]].reshape(-1)
+    buf = '\t'.join([("%.8f" % x).ljust(12) for x in final])
+    assert buf == golden_ml100k_eval["eval_topk_10_20"]
+
+
+def test_mf_scores_are_fma_chain():
+    rs = np.random.RandomState(3)
+    U = rs.randn(5, 24).astype(np.float32); V = rs.randn(11, 24).astype(np.float32)
+    S = oracle.mf_scores(U, V, np.arange(5, dtype=np.int32))
+    import math
+    for b in range(5):
+        for i in range(11):
+            acc = np.float32(0)
+            for k in range(24):  # fma = exact product + add, one rounding
+                acc = np.float32(math.fma(float(U[b, k]), float(V[i, k]), float(acc))) \
+                    if hasattr(math, "fma") else acc
+            if hasattr(math, "fma"):
+                # double fma then a float rounding can double-round; allow 1 ulp
+                assert abs(float(S[b, i]) - float(acc)) <= abs(float(acc)) * 2e-7 + 1e-12
+    assert np.allclose(S, U @ V.T, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------- tf_math pins
+def _num_grad(f, x, eps=1e-3):
+    g = np.zeros_like(x, dtype=np.float64)
+    it = np.nditer(x, flags=["multi_index"])
+    for _ in it:
+        i = it.multi_index
+        old = x[i]
+        x[i] = old + eps; fp = f()
+        x[i] = old - eps; fm = f()
+        x[i] = old
+        g[i] = (fp - fm) / (2 * eps)
+    return g
+
+
+@pytest.mark.parametrize("loss", ["bpr", "hinge", "square"])
+def test_pairwise_grad_matches_finite_differences(loss):
+    rs = np.random.RandomState(0)
+    U = rs.randn(6, 5); V = rs.randn(7, 5)
+    users = np.array([0, 1, 1, 5, 0]); pos = np.array([2, 2, 3, 6, 2]); neg = np.array([4, 0, 2, 1, 5])
+    _, gU, gV, _, _ = tf_math.mf_pairwise_grad(U, V, users, pos, neg, loss, reg=0.05)
+
+    def f64loss(Ux, Vx):
+        x = (Ux[users] * Vx[pos]).sum(1) - (Ux[users] * Vx[neg]).sum(1)
+        l = {"bpr": np.log1p(np.exp(-x)), "hinge": np.maximum(x + 1, 0), "square": (1 - x) ** 2}[loss]
+        return l.sum() + 0.05 * 0.5 * ((Ux[users] ** 2).sum() + (Vx[pos] ** 2).sum() + (Vx[neg] ** 2).sum())
+
+    U64, V64 = U.copy(), V.copy()
+    nU = _num_grad(lambda: f64loss(U64, V64), U64, 1e-5)
+    nV = _num_grad(lambda: f64loss(U64, V64), V64, 1e-5)
+    assert np.allclose(gU, nU, rtol=2e-3, atol=2e-4)
+    assert np.allclose(gV, nV, rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("loss", ["cross_entropy", "square"])
+def test_pointwise_grad_matches_finite_differences(loss):
+    rs = np.random.RandomState(1)
+    U = rs.randn(6, 4); V = rs.randn(7, 4)
+    users = np.array([0, 1, 1, 5]); items = np.array([2, 2, 3, 6]); z = np.array([1., 0., 1., 0.])
+    _, gU, gV, _, _ = tf_math.mf_pointwise_grad(U, V, users, items, z, loss, reg=0.1)
+
+    def f64loss(Ux, Vx):
+        x = (Ux[users] * Vx[items]).sum(1)
+        if loss == "cross_entropy":
+            l = (np.maximum(x, 0) - x * z + np.log1p(np.exp(-np.abs(x)))).mean()
+        else:
+            l = ((z - x) ** 2).sum()
+        return l + 0.1 * 0.5 * ((Ux[users] ** 2).sum() + (Vx[items] ** 2).sum())
+
+    U64, V64 = U.copy(), V.copy()
+    assert np.allclose(gU, _num_grad(lambda: f64loss(U64, V64), U64, 1e-5), rtol=2e-3, atol=2e-4)
+    assert np.allclose(gV, _num_grad(lambda: f64loss(U64, V64), V64, 1e-5), rtol=2e-3, atol=2e-4)
+
+
+def test_adam_sparse_is_dense_over_whole_table():
+    """TF-1.12 Adam on IndexedSlices moves rows whose gradient is zero (m, v decay)."""
+    var = np.ones((4, 3), np.float32); m = np.full((4, 3), 0.5, np.float32); v = np.full((4, 3), 0.25, np.float32)
+    g = np.zeros((4, 3), np.float32); g[1] = 1.0
+    tf_math.opt_apply("adam", var, g, m, v, None, [0.1, 0.9, 0.999, 1e-8])
+    assert np.all(var[0] < 1.0) and np.allclose(m[0], 0.45) and np.allclose(v[0], 0.25 * 0.999)
+    lr_t = tf_math.adam_lr_t(1e-3, 3)
+    assert np.allclose(lr_t, [1e-3 * np.sqrt(1 - .999 ** t) / (1 - .9 ** t) for t in (1, 2, 3)], rtol=1e-5)
+
+
+def test_numpy_axis0_mean_is_sequential_fp32():
+    """nrc_mean_rows restates np.mean(axis=0): sequential fp32 row adds, then / n."""
+    rs = np.random.RandomState(0)
+    a = rs.rand(5000, 7).astype(np.float32)
+    acc = a[0].copy()
+    for r in range(1, len(a)):
+        acc = (acc + a[r]).astype(np.float32)
+    assert np.array_equal(np.mean(a, axis=0), acc / np.float32(len(a)))
