@@ -172,6 +172,15 @@ int nrc_opt_apply_rows(int32_t opt_kind, float* var, float* grad, float* slot0, 
                        const int32_t* touched, int32_t stamp, int64_t rows, int32_t dim,
                        const float* hyper_host, void* stream);
 
+/* Same rules for every variable of a model in ONE launch (what `optimizer.minimize(loss)`
+ * applies per step).  All arrays are HOST arrays of length n_vars holding device pointers /
+ * shapes; dense_var[i] = 1 marks a variable whose gradient is a dense tensor (tf.layers.dense
+ * kernel / bias: Apply* functor formulas, every element), 0 an IndexedSlices variable. */
+int nrc_opt_apply_multi(int32_t opt_kind, int32_t n_vars, float* const* var, float* const* grad,
+                        float* const* slot0, float* const* slot1, const int32_t* const* touched,
+                        const int64_t* rows, const int32_t* dims, const int32_t* dense_var,
+                        int32_t stamp, const float* hyper_host, void* stream);
+
 /* One epoch of MF.train_model, MF.py:92-108, on device-resident, already shuffled id arrays
  * (n samples, steps = ceil(n / batch_size), last batch smaller, sampler.py:208-213).
  *   third: neg items (pairwise, i32) or labels (pointwise, f32 bits) -- selected by
@@ -186,6 +195,21 @@ int nrc_mf_train_epoch(float* user_table, float* item_table, int32_t num_users,
                        float* grad_item, int32_t* touched_user, int32_t* touched_item,
                        float* slot0_user, float* slot1_user, float* slot0_item,
                        float* slot1_item, int32_t first_stamp, float* step_loss, void* stream);
+
+/* One `sess.run((loss, optimizer), feed_dict)` of MF.train_model (MF.py:97-108): the id /
+ * label arrays of ONE batch are HOST buffers (the python lists the reference feeds; pinned
+ * memory makes the copies asynchronous), tables and optimizer state stay on the device like TF
+ * variables.  Copies the batch H2D into `staging` (device scratch, >= 12*batch+16 bytes), runs
+ * both phases, copies the loss back and synchronises the stream: *loss_host is valid on
+ * return.  hyper_host[0] must already hold this step's lr_t for adam. */
+int nrc_mf_train_step_host(float* user_table, float* item_table, int32_t num_users,
+                           int32_t num_items, int32_t dim, const int32_t* users_host,
+                           const int32_t* items_host, const void* third_host, int64_t batch,
+                           int32_t pairwise, int32_t loss_kind, float reg, int32_t opt_kind,
+                           const float* hyper_host, float* grad_user, float* grad_item,
+                           int32_t* touched_user, int32_t* touched_item, float* slot0_user,
+                           float* slot1_user, float* slot0_item, float* slot1_item,
+                           int32_t stamp, void* staging, float* loss_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -205,6 +205,23 @@ extern "C" int nrc_opt_apply_rows(int32_t opt_kind, float* var, float* grad, flo
     return opt_launch_run(L, stamp, as_stream(stream));
 }
 
+extern "C" int nrc_opt_apply_multi(int32_t opt_kind, int32_t n_vars, float* const* var,
+                                   float* const* grad, float* const* slot0, float* const* slot1,
+                                   const int32_t* const* touched, const int64_t* rows,
+                                   const int32_t* dims, const int32_t* dense_var, int32_t stamp,
+                                   const float* hyper_host, void* stream) {
+    OptLaunch L;
+    int rc = opt_launch_init(L, opt_kind, hyper_host);
+    if (rc) return rc;
+    for (int i = 0; i < n_vars; ++i) {
+        rc = opt_launch_add(L, var[i], grad[i], slot0 ? slot0[i] : nullptr,
+                            slot1 ? slot1[i] : nullptr, touched ? touched[i] : nullptr, rows[i],
+                            dims[i], dense_var ? dense_var[i] : 0);
+        if (rc) return rc;
+    }
+    return opt_launch_run(L, stamp, as_stream(stream));
+}
+
 extern "C" int nrc_mf_train_epoch(float* user_table, float* item_table, int32_t num_users,
                                   int32_t num_items, int32_t dim, const int32_t* users,
                                   const int32_t* items, const void* third, int64_t n,
@@ -246,5 +263,48 @@ extern "C" int nrc_mf_train_epoch(float* user_table, float* item_table, int32_t 
         rc = opt_launch_run(L, stamp, st);
         if (rc) return rc;
     }
+    return NRC_OK;
+}
+
+extern "C" int nrc_mf_train_step_host(float* user_table, float* item_table, int32_t num_users,
+                                      int32_t num_items, int32_t dim, const int32_t* users_host,
+                                      const int32_t* items_host, const void* third_host,
+                                      int64_t batch, int32_t pairwise, int32_t loss_kind, float reg,
+                                      int32_t opt_kind, const float* hyper_host, float* grad_user,
+                                      float* grad_item, int32_t* touched_user,
+                                      int32_t* touched_item, float* slot0_user, float* slot1_user,
+                                      float* slot0_item, float* slot1_item, int32_t stamp,
+                                      void* staging, float* loss_host, void* stream) {
+    NRC_REQUIRE(batch > 0 && dim > 0, NRC_E_VALUE, "batch and dim must be positive");
+    cudaStream_t st = as_stream(stream);
+    int32_t* d_users = reinterpret_cast<int32_t*>(staging);
+    int32_t* d_items = d_users + batch;
+    int32_t* d_third = d_items + batch;
+    float* d_loss = reinterpret_cast<float*>(d_third + batch);
+    const size_t nb = (size_t)batch * sizeof(int32_t);
+    NRC_CUDA_CHECK(cudaMemcpyAsync(d_users, users_host, nb, cudaMemcpyHostToDevice, st));
+    NRC_CUDA_CHECK(cudaMemcpyAsync(d_items, items_host, nb, cudaMemcpyHostToDevice, st));
+    NRC_CUDA_CHECK(cudaMemcpyAsync(d_third, third_host, nb, cudaMemcpyHostToDevice, st));
+    NRC_CUDA_CHECK(cudaMemsetAsync(d_loss, 0, sizeof(float), st));
+    int rc;
+    if (pairwise)
+        rc = nrc_mf_pairwise_grad(user_table, item_table, dim, d_users, d_items, d_third, batch,
+                                  loss_kind, reg, grad_user, grad_item, touched_user, touched_item,
+                                  stamp, d_loss, stream);
+    else
+        rc = nrc_mf_pointwise_grad(user_table, item_table, dim, d_users, d_items,
+                                   reinterpret_cast<const float*>(d_third), batch, loss_kind, reg,
+                                   grad_user, grad_item, touched_user, touched_item, stamp, d_loss,
+                                   stream);
+    if (rc) return rc;
+    OptLaunch L;
+    rc = opt_launch_init(L, opt_kind, hyper_host);
+    if (rc) return rc;
+    opt_launch_add(L, user_table, grad_user, slot0_user, slot1_user, touched_user, num_users, dim, 0);
+    opt_launch_add(L, item_table, grad_item, slot0_item, slot1_item, touched_item, num_items, dim, 0);
+    rc = opt_launch_run(L, stamp, st);
+    if (rc) return rc;
+    NRC_CUDA_CHECK(cudaMemcpyAsync(loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+    NRC_CUDA_CHECK(cudaStreamSynchronize(st));
     return NRC_OK;
 }

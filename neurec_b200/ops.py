@@ -186,6 +186,31 @@ def opt_apply_rows(opt, var, grad, slot0, slot1, touched, stamp, hyper):
     _count()
 
 
+def opt_apply_multi(opt, variables, stamp, hyper):
+    """variables: list of (var, grad, slot0|None, slot1|None, touched|None, dense_var:bool);
+    every variable of the model is updated by ONE kernel launch."""
+    n = len(variables)
+    PA = ctypes.c_void_p * n
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    var = PA(*[ptr(v[0]) for v in variables])
+    grad = PA(*[ptr(v[1]) for v in variables])
+    s0 = PA(*[ptr(v[2]) for v in variables])
+    s1 = PA(*[ptr(v[3]) for v in variables])
+    tch = PA(*[ptr(v[4]) for v in variables])
+    shp = [(v[0].shape[0], v[0].numel() // v[0].shape[0]) if v[0].dim() > 1 else (1, v[0].numel())
+           for v in variables]
+    rows = (ctypes.c_int64 * n)(*[s[0] for s in shp])
+    dims = (ctypes.c_int32 * n)(*[s[1] for s in shp])
+    dense = (ctypes.c_int32 * n)(*[1 if v[5] else 0 for v in variables])
+    h = np.zeros(4, dtype=np.float32)
+    h[:len(hyper)] = hyper
+    cast = lambda a: ctypes.cast(a, ctypes.c_void_p)
+    check(_lib.load().nrc_opt_apply_multi(OPT_IDS[opt], n, cast(var), cast(grad), cast(s0), cast(s1),
+                                          cast(tch), cast(rows), cast(dims), cast(dense), int(stamp),
+                                          h.ctypes.data, _stream()))
+    _count()
+
+
 def mf_train_epoch(U, V, users, items, third, batch_size, pairwise, loss, reg, opt, lr_t, hyper,
                    gU, gV, tU, tV, s0U, s1U, s0V, s1V, first_stamp, step_loss):
     n = users.numel()
