@@ -211,6 +211,105 @@ int nrc_mf_train_step_host(float* user_table, float* item_table, int32_t num_use
                            float* slot1_user, float* slot0_item, float* slot1_item,
                            int32_t stamp, void* staging, float* loss_host, void* stream);
 
+/* ======================================================================================
+ * NCF family: MLP (model/general_recommender/MLP.py) and NeuMF = GMF + MLP (NeuMF.py)
+ * ==================================================================================== */
+
+/* Model shape.  mf_dim = embedding_size (0 for MLP.py); mlp_dim = layers[0]/2, the width of
+ * each MLP embedding (NeuMF.py:58-61, MLP.py:48-51); layers = units of the tf.layers.dense
+ * stack -- the first layer maps layers[0] -> layers[0] (NeuMF.py:81-82); n_towers = 2 only for
+ * pairwise NeuMF, whose negative tower re-instantiates tf.layers.dense (NeuMF.py:90-92).
+ * Dense parameters are one packed f32 buffer: for tower t, layer l: kernel [in, out] row-major
+ * then bias [out]; towers back to back (nrc_ncf_dense_size floats in total). */
+typedef struct nrc_ncf_shape {
+    int32_t num_users, num_items;
+    int32_t mf_dim, mlp_dim;
+    int32_t n_layers;
+    int32_t layers[4];
+    int32_t n_towers;
+} nrc_ncf_shape;
+
+int nrc_ncf_dense_size(const nrc_ncf_shape* shape);
+
+/* Gradient phase of NeuMF._create_loss (NeuMF.py:87-100) / MLP._create_loss (MLP.py:72-82):
+ * prediction = sum(mf_user*mf_item) + sum(relu-MLP(concat(mlp_user, mlp_item))) (NeuMF.py:85);
+ * pairwise (third = neg items i32) or pointwise (third = labels f32) loss as in util/learner.py;
+ * + reg_mf*l2_loss(p1,q2,q1) + reg_mlp*l2_loss(m1,n2,n1).  Adds the gradients of the four
+ * tables and of the packed dense parameters into the g_* accumulators (never applies them). */
+int nrc_ncf_grad(const nrc_ncf_shape* shape, const float* mf_user, const float* mf_item,
+                 const float* mlp_user, const float* mlp_item, const float* dense,
+                 const int32_t* users, const int32_t* items, const void* third, int64_t batch,
+                 int32_t pairwise, int32_t loss_kind, float reg_mf, float reg_mlp,
+                 float* g_mf_user, float* g_mf_item, float* g_mlp_user, float* g_mlp_item,
+                 float* g_dense, int32_t* touched_user, int32_t* touched_item, int32_t stamp,
+                 float* loss, void* stream);
+
+/* NeuMF.predict / MLP.predict with candidate_items=None (NeuMF.py:163-168): the tower-0 forward
+ * of every (users[b], item) pair -> scores f32 [n_users, num_items] (device). */
+int nrc_ncf_scores(const nrc_ncf_shape* shape, const float* mf_user, const float* mf_item,
+                   const float* mlp_user, const float* mlp_item, const float* dense,
+                   const int32_t* users, int32_t n_users, int32_t num_items, float* scores,
+                   void* stream);
+
+/* One epoch of NeuMF.train_model (NeuMF.py:126-151) on device-resident shuffled arrays.
+ * grads / slot0 / slot1 are HOST arrays of 5 device pointers in the order
+ * {mf_user, mf_item, mlp_user, mlp_item, dense}; the four tables get IndexedSlices optimizer
+ * semantics, the packed dense parameters dense-gradient semantics (see nrc_opt_apply_multi). */
+int nrc_ncf_train_epoch(const nrc_ncf_shape* shape, float* mf_user, float* mf_item,
+                        float* mlp_user, float* mlp_item, float* dense, const int32_t* users,
+                        const int32_t* items, const void* third, int64_t n, int32_t batch_size,
+                        int32_t pairwise, int32_t loss_kind, float reg_mf, float reg_mlp,
+                        int32_t opt_kind, const float* lr_t_host, const float* hyper_host,
+                        float* const* grads, float* const* slot0, float* const* slot1,
+                        int32_t* touched_user, int32_t* touched_item, int32_t first_stamp,
+                        float* step_loss, void* stream);
+
+/* ======================================================================================
+ * Graph propagation: CSR SpMM and the LightGCN step
+ * ==================================================================================== */
+
+/* tf.sparse_tensor_dense_matmul(adj_mat, ego_embeddings), LightGCN.py:140 / NGCF.py:176:
+ *   y[r, :] = sum over the nnz of row r, in CSR order, of values[p] * x[indices[p], :]
+ * with separately rounded multiply and add (sequential, TF/scipy CPU order => bit-exact), then
+ * the optional epilogue  y = bias[r,:] + y;  Y[r,:] = y;  sum[r,:] = (sum[r,:] + y) [/ div].
+ * row_order (optional i32 [n_rows]) is the order rows are dealt to warps (degree-descending
+ * for load balance); bias / y / sum may be NULL; div = 0 disables the division. */
+int nrc_spmm_csr(const int64_t* indptr, const int32_t* indices, const float* values,
+                 const int32_t* row_order, int32_t n_rows, const float* x, int32_t dim,
+                 const float* bias, float* y, float* sum, float div, void* stream);
+
+/* _create_lightgcn_embed, LightGCN.py:132-149: e_final = mean(E_0, A E_0, ..., A^L E_0) with
+ * E_0 = concat(user_embedding, item_embedding).  work_a / work_b: [n_nodes, dim] scratch. */
+int nrc_lightgcn_propagate(const int64_t* indptr, const int32_t* indices, const float* values,
+                           const int32_t* row_order, int32_t n_nodes, int32_t dim,
+                           int32_t n_layers, const float* e0, float* e_final, float* work_a,
+                           float* work_b, void* stream);
+
+/* create_bpr_loss, LightGCN.py:156-166 on the propagated table e_final (users first, then
+ * items) with the regulariser on the layer-0 rows e0.  Adds scale * dLoss/dE_final into
+ * grad_final and reg * e0[row] into grad_reg (both dense [n_nodes, dim]); loss2 += {mf_loss,
+ * emb_loss}.  scale = 1/(n_layers+1) is the reduce_mean factor of LightGCN.py:147. */
+int nrc_lightgcn_bpr_grad(const float* e_final, const float* e0, int32_t num_users, int32_t dim,
+                          const int32_t* users, const int32_t* pos_items, const int32_t* neg_items,
+                          int64_t batch, float reg, float scale, float* grad_final,
+                          float* grad_reg, float* loss2, void* stream);
+
+/* One epoch of LightGCN.train_model, LightGCN.py:168-180: per batch the forward propagation
+ * (n_layers SpMM), the BPR gradient, the backward propagation (n_layers SpMM with the
+ * transposed CSR t_*; pass NULL when A_hat is symmetric, adj_type 'pre') and a dense Adam step
+ * over E_0 (TF ApplyAdam formulas; lr_t_host f32 [steps]).  grad_final and grad_e0 must be
+ * zero on entry and are zero on return.  step_loss2 f32 [steps, 2] = {mf_loss, emb_loss}. */
+int nrc_lightgcn_train_epoch(const int64_t* indptr, const int32_t* indices, const float* values,
+                             const int64_t* t_indptr, const int32_t* t_indices,
+                             const float* t_values, const int32_t* row_order, int32_t num_users,
+                             int32_t num_items, int32_t dim, int32_t n_layers, float* e0,
+                             float* adam_m, float* adam_v, const int32_t* users,
+                             const int32_t* pos_items, const int32_t* neg_items, int64_t n,
+                             int32_t batch_size, float reg, const float* lr_t_host,
+                             const float* hyper_host, float* e_final, float* grad_final,
+                             float* grad_e0, float* work_a, float* work_b, float* step_loss2,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

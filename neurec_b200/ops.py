@@ -211,6 +211,128 @@ def opt_apply_multi(opt, variables, stamp, hyper):
     _count()
 
 
+def spmm_csr(indptr, indices, values, x, row_order=None, bias=None, y=None, sum_=None, div=0.0,
+             want_y=True):
+    """y = A.x in CSR order (LightGCN.py:140); optional fused epilogue, see nrc_spmm_csr."""
+    _req(indptr, torch.int64, "indptr"); _req(indices, torch.int32, "indices")
+    _req(values, torch.float32, "values"); _req(x, torch.float32, "x")
+    n_rows = indptr.numel() - 1
+    dim = x.shape[1]
+    if y is None and want_y:
+        y = torch.empty((n_rows, dim), dtype=torch.float32, device=x.device)
+    check(_lib.load().nrc_spmm_csr(_p(indptr), _p(indices), _p(values), _p(row_order), n_rows, _p(x),
+                                   dim, _p(bias), _p(y), _p(sum_), float(div), _stream()))
+    _count()
+    return y
+
+
+def lightgcn_propagate(indptr, indices, values, row_order, e0, n_layers, e_final=None, work=None):
+    """mean(E_0, A E_0, ..., A^L E_0) (LightGCN.py:132-149)."""
+    n, dim = e0.shape
+    if e_final is None:
+        e_final = torch.empty_like(e0)
+    if work is None:
+        work = (torch.empty_like(e0), torch.empty_like(e0))
+    check(_lib.load().nrc_lightgcn_propagate(_p(indptr), _p(indices), _p(values), _p(row_order), n, dim,
+                                             int(n_layers), _p(e0), _p(e_final), _p(work[0]),
+                                             _p(work[1]), _stream()))
+    _count(n_layers)
+    return e_final
+
+
+def lightgcn_bpr_grad(e_final, e0, num_users, users, pos, neg, reg, scale, grad_final, grad_reg, loss2):
+    check(_lib.load().nrc_lightgcn_bpr_grad(_p(e_final), _p(e0), int(num_users), e0.shape[1], _p(users),
+                                            _p(pos), _p(neg), users.numel(), float(reg), float(scale),
+                                            _p(grad_final), _p(grad_reg), _p(loss2), _stream()))
+    _count()
+
+
+def lightgcn_train_epoch(csr, t_csr, row_order, num_users, num_items, n_layers, e0, m, v, users, pos,
+                         neg, batch_size, reg, lr_t, hyper, e_final, grad_final, grad_e0, work,
+                         step_loss2):
+    n = users.numel()
+    steps = (n + batch_size - 1) // batch_size
+    lr_t = np.ascontiguousarray(lr_t, dtype=np.float32)
+    h = np.zeros(4, dtype=np.float32)
+    h[:len(hyper)] = hyper
+    t = t_csr if t_csr is not None else (None, None, None)
+    check(_lib.load().nrc_lightgcn_train_epoch(
+        _p(csr[0]), _p(csr[1]), _p(csr[2]), _p(t[0]), _p(t[1]), _p(t[2]), _p(row_order), int(num_users),
+        int(num_items), e0.shape[1], int(n_layers), _p(e0), _p(m), _p(v), _p(users), _p(pos), _p(neg), n,
+        int(batch_size), float(reg), lr_t.ctypes.data, h.ctypes.data, _p(e_final), _p(grad_final),
+        _p(grad_e0), _p(work[0]), _p(work[1]), _p(step_loss2), _stream()))
+    _count(steps * (2 * n_layers + 3))
+    return steps
+
+
+class NcfShape(ctypes.Structure):
+    """ctypes mirror of nrc_ncf_shape (include/neurec_b200.h)."""
+    _fields_ = [("num_users", ctypes.c_int32), ("num_items", ctypes.c_int32),
+                ("mf_dim", ctypes.c_int32), ("mlp_dim", ctypes.c_int32),
+                ("n_layers", ctypes.c_int32), ("layers", ctypes.c_int32 * 4),
+                ("n_towers", ctypes.c_int32)]
+
+    @classmethod
+    def make(cls, num_users, num_items, mf_dim, layers, n_towers=1):
+        layers = list(layers or [])
+        if len(layers) > 4:
+            raise ValueError("at most 4 dense layers are supported")
+        s = cls()
+        s.num_users, s.num_items, s.mf_dim = int(num_users), int(num_items), int(mf_dim)
+        s.mlp_dim = int(layers[0] / 2) if layers else 0   # NeuMF.py:58 int(self.layers[0]/2)
+        s.n_layers = len(layers)
+        for i, v in enumerate(layers):
+            s.layers[i] = int(v)
+        s.n_towers = int(n_towers)
+        return s
+
+    def dense_size(self):
+        n = _lib.load().nrc_ncf_dense_size(ctypes.byref(self))
+        check(n if n < 0 else 0)
+        return n
+
+
+def ncf_grad(shape, P, users, items, third, pairwise, loss, reg_mf, reg_mlp, G, tU, tI, stamp,
+             loss_out):
+    """P / G: dicts with keys mf_user, mf_item, mlp_user, mlp_item, dense (tensors or None)."""
+    k = ("mf_user", "mf_item", "mlp_user", "mlp_item", "dense")
+    check(_lib.load().nrc_ncf_grad(ctypes.byref(shape), *[_p(P[n]) for n in k], _p(users), _p(items),
+                                   _p(third), users.numel(), 1 if pairwise else 0, LOSS_IDS[loss],
+                                   float(reg_mf), float(reg_mlp), *[_p(G[n]) for n in k], _p(tU),
+                                   _p(tI), int(stamp), _p(loss_out), _stream()))
+    _count()
+
+
+def ncf_scores(shape, P, users):
+    """NeuMF.predict(users, None): [len(users), num_items] scores on device (NeuMF.py:163-168)."""
+    k = ("mf_user", "mf_item", "mlp_user", "mlp_item", "dense")
+    out = torch.empty((users.numel(), shape.num_items), dtype=torch.float32, device=users.device)
+    check(_lib.load().nrc_ncf_scores(ctypes.byref(shape), *[_p(P[n]) for n in k], _p(users),
+                                     users.numel(), shape.num_items, _p(out), _stream()))
+    _count()
+    return out
+
+
+def ncf_train_epoch(shape, P, users, items, third, batch_size, pairwise, loss, reg_mf, reg_mlp, opt,
+                    lr_t, hyper, G, S0, S1, tU, tI, first_stamp, step_loss):
+    k = ("mf_user", "mf_item", "mlp_user", "mlp_item", "dense")
+    n = users.numel()
+    steps = (n + batch_size - 1) // batch_size
+    lr_t = np.ascontiguousarray(lr_t, dtype=np.float32)
+    h = np.zeros(4, dtype=np.float32)
+    h[:len(hyper)] = hyper
+    PA = ctypes.c_void_p * 5
+    arr = lambda D: ctypes.cast(PA(*[(D[x].data_ptr() if D.get(x) is not None else None) for x in k]),
+                                ctypes.c_void_p)
+    check(_lib.load().nrc_ncf_train_epoch(
+        ctypes.byref(shape), *[_p(P[x]) for x in k], _p(users), _p(items), _p(third), n, int(batch_size),
+        1 if pairwise else 0, LOSS_IDS[loss], float(reg_mf), float(reg_mlp), OPT_IDS[opt],
+        lr_t.ctypes.data, h.ctypes.data, arr(G), arr(S0), arr(S1), _p(tU), _p(tI), int(first_stamp),
+        _p(step_loss), _stream()))
+    _count(2 * steps)
+    return steps
+
+
 def mf_train_epoch(U, V, users, items, third, batch_size, pairwise, loss, reg, opt, lr_t, hyper,
                    gU, gV, tU, tV, s0U, s1U, s0V, s1V, first_stamp, step_loss):
     n = users.numel()

@@ -208,3 +208,260 @@ class MFTrainer:
             sl = slice(off, min(n, off + batch_size))
             losses.append(self.step(users[sl], items[sl], third[sl]))
         return np.asarray(losses, dtype=f32)
+
+
+# ----------------------------------------------------------------------------------------
+# LightGCN: LightGCN.py:35-78 (adjacency), 132-149 (propagation), 156-166 (loss)
+# ----------------------------------------------------------------------------------------
+def lightgcn_adj(train_indptr, train_indices, num_users, num_items, adj_type="pre"):
+    """create_adj_mat (LightGCN.py:35-78) with the reference's own scipy calls -> fp32 CSR."""
+    import scipy.sparse as sp
+    n = num_users + num_items
+    users = np.repeat(np.arange(num_users), np.diff(train_indptr)).astype(np.int32)
+    items = np.asarray(train_indices, dtype=np.int32)
+    tmp = sp.csr_matrix((np.ones(len(users), np.float32), (users, items + num_users)), shape=(n, n))
+    adj = tmp + tmp.T
+
+    def single(a):
+        rowsum = np.array(a.sum(1))
+        with np.errstate(divide="ignore"):
+            d_inv = np.power(rowsum, -1).flatten()
+        d_inv[np.isinf(d_inv)] = 0.
+        return sp.diags(d_inv).dot(a).tocoo()
+
+    if adj_type == "plain":
+        m = adj
+    elif adj_type == "norm":
+        m = single(adj + sp.eye(n))
+    elif adj_type == "gcmc":
+        m = single(adj)
+    elif adj_type == "pre":
+        rowsum = np.array(adj.sum(1))
+        with np.errstate(divide="ignore"):
+            d_inv = np.power(rowsum, -0.5).flatten()
+        d_inv[np.isinf(d_inv)] = 0.
+        d = sp.diags(d_inv)
+        m = d.dot(adj).dot(d)
+    else:
+        m = single(adj) + sp.eye(n)
+    m = m.tocoo().astype(np.float32).tocsr()   # _convert_sp_mat_to_sp_tensor (LightGCN.py:151-154)
+    m.sort_indices()
+    return m
+
+
+def lightgcn_propagate(A, e0, n_layers):
+    """mean over [E_0, A E_0, ...] (LightGCN.py:132-149); scipy's csr @ dense accumulates each
+    output row sequentially over its nnz with separate multiply and add, like TF's CPU kernel."""
+    e0 = np.asarray(e0, f32)
+    layers = [e0]
+    x = e0
+    for _ in range(n_layers):
+        x = (A @ x).astype(f32)
+        layers.append(x)
+    s = layers[0].copy()
+    for y in layers[1:]:
+        s = (s + y).astype(f32)
+    return (s / f32(n_layers + 1)).astype(f32), layers
+
+
+def lightgcn_grad(A, AT, e0, num_users, users, pos, neg, reg, n_layers):
+    """-> (mf_loss, emb_loss, dE0, e_final): manual backprop of LightGCN.py:99-130."""
+    e, _ = lightgcn_propagate(A, e0, n_layers)
+    ru, ri, rj = users, num_users + pos, num_users + neg
+    x = (e[ru] * e[ri]).sum(1, dtype=f32) - (e[ru] * e[rj]).sum(1, dtype=f32)
+    l, g = pairwise_loss_and_grad("bpr", x)
+    reg = f32(reg)
+    emb = reg * f32(0.5) * ((e0[ru] ** 2).sum(dtype=f32) + (e0[ri] ** 2).sum(dtype=f32) + (e0[rj] ** 2).sum(dtype=f32))
+    scale = f32(1.0) / f32(n_layers + 1)
+    G = np.zeros_like(e0)
+    gs = (g * scale)[:, None].astype(f32)
+    np.add.at(G, ru, gs * (e[ri] - e[rj]))
+    np.add.at(G, ri, gs * e[ru])
+    np.add.at(G, rj, -gs * e[ru])
+    R = np.zeros_like(e0)
+    for r in (ru, ri, rj):
+        np.add.at(R, r, reg * e0[r])
+    t = G
+    for _ in range(n_layers):
+        t = (G + (AT @ t).astype(f32)).astype(f32)
+    return l.sum(dtype=f32), f32(emb), (R + t).astype(f32), e
+
+
+class LightGCNTrainer:
+    def __init__(self, A, e0, num_users, n_layers, lr=0.01, reg=1e-3):
+        self.A, self.AT = A, A.T.tocsr()
+        self.AT.sort_indices()
+        self.e0 = np.array(e0, f32)
+        self.m, self.v = np.zeros_like(self.e0), np.zeros_like(self.e0)
+        self.num_users, self.n_layers, self.lr, self.reg, self.t = num_users, n_layers, lr, reg, 0
+
+    def step(self, users, pos, neg):
+        mf, emb, g, _ = lightgcn_grad(self.A, self.AT, self.e0, self.num_users, users, pos, neg, self.reg,
+                                      self.n_layers)
+        hyper = [adam_lr_t(self.lr, 1, start_step=self.t)[0], 0.9, 0.999, 1e-8]
+        opt_apply("adam", self.e0, g, self.m, self.v, None, hyper, dense_var=True)
+        self.t += 1
+        return mf, emb
+
+    def epoch(self, users, pos, neg, batch_size):
+        out = []
+        for off in range(0, len(users), batch_size):
+            sl = slice(off, min(len(users), off + batch_size))
+            out.append(self.step(users[sl], pos[sl], neg[sl]))
+        return np.asarray(out, f32)
+
+
+# ----------------------------------------------------------------------------------------
+# NCF family: NeuMF.py:69-104, MLP.py:45-87
+# ----------------------------------------------------------------------------------------
+def ncf_dense_layout(mlp_dim, layers, n_towers):
+    """Packed layout used by the product: per tower, per layer kernel [in,out] then bias."""
+    lay, off, inn = [], 0, 2 * mlp_dim
+    for out in layers:
+        lay.append((off, inn, out, off + inn * out))
+        off += inn * out + out
+        inn = out
+    return lay, off, off * n_towers
+
+
+def ncf_init_dense(mlp_dim, layers, n_towers, rs):
+    """tf.layers.dense defaults: glorot_uniform kernel, zero bias."""
+    lay, tower, total = ncf_dense_layout(mlp_dim, layers, n_towers)
+    buf = np.zeros(total, f32)
+    for t in range(n_towers):
+        for (wo, inn, out, bo) in lay:
+            lim = np.sqrt(6.0 / (inn + out))
+            buf[t * tower + wo:t * tower + wo + inn * out] = rs.uniform(-lim, lim, inn * out).astype(f32)
+    return buf
+
+
+def _ncf_tower(dense, lay, tower_off, h):
+    acts = [h]
+    for (wo, inn, out, bo) in lay:
+        W = dense[tower_off + wo:tower_off + wo + inn * out].reshape(inn, out)
+        b = dense[tower_off + bo:tower_off + bo + out]
+        h = np.maximum(h @ W + b, 0).astype(h.dtype)
+        acts.append(h)
+    return acts
+
+
+def ncf_predict(P, users, items, mlp_dim, layers, tower=0):
+    """prediction = reduce_sum(concat(mf_vector, mlp_vector), 1)  (NeuMF.py:85)."""
+    lay, tsz, _ = ncf_dense_layout(mlp_dim, layers, 1)
+    dt = P["dense"].dtype if layers else P["mf_user"].dtype
+    y = np.zeros(len(users), dt)
+    if P["mf_user"] is not None and P["mf_user"].shape[1] > 0:
+        y = y + (P["mf_user"][users] * P["mf_item"][items]).sum(1)
+    if layers:
+        h = np.concatenate([P["mlp_user"][users], P["mlp_item"][items]], axis=1)
+        acts = _ncf_tower(P["dense"], lay, tower * tsz, h)
+        y = y + acts[-1].sum(1)
+    return y.astype(dt)
+
+
+def ncf_grad(P, users, items, third, pairwise, loss, reg_mf, reg_mlp, mlp_dim, layers, n_towers):
+    """-> (loss, grads dict with the same keys as P, touched_user, touched_item).
+    Manual backprop of the TF graph; dtype follows P (fp32 in parity tests)."""
+    lay, tsz, total = ncf_dense_layout(mlp_dim, layers, n_towers)
+    has_mf = P["mf_user"] is not None and P["mf_user"].shape[1] > 0
+    dt = (P["dense"] if layers else P["mf_user"]).dtype
+    G = {k: (np.zeros_like(v) if v is not None else None) for k, v in P.items()}
+    reg_mf, reg_mlp = dt.type(reg_mf), dt.type(reg_mlp)
+    passes = [(items, 0)] + ([(third, 1 if n_towers == 2 else 0)] if pairwise else [])
+    cache, yh = [], []
+    for it, tw in passes:
+        y = np.zeros(len(users), dt)
+        acts = None
+        if has_mf:
+            y = y + (P["mf_user"][users] * P["mf_item"][it]).sum(1)
+        if layers:
+            h = np.concatenate([P["mlp_user"][users], P["mlp_item"][it]], axis=1)
+            acts = _ncf_tower(P["dense"], lay, tw * tsz, h)
+            y = y + acts[-1].sum(1)
+        cache.append(acts); yh.append(y.astype(dt))
+    if dt == np.float32:
+        if pairwise:
+            l, g = pairwise_loss_and_grad(loss, yh[0] - yh[1])
+        else:
+            l, g = pointwise_loss_and_grad(loss, third, yh[0])
+    else:  # float64 path for finite-difference pins
+        x = yh[0] - yh[1] if pairwise else yh[0]
+        if pairwise:
+            l = {"bpr": np.log1p(np.exp(-x)), "hinge": np.maximum(x + 1, 0), "square": (1 - x) ** 2}[loss]
+            g = {"bpr": -1 / (1 + np.exp(x)), "hinge": (x + 1 > 0) * 1.0, "square": -2 * (1 - x)}[loss]
+        elif loss == "cross_entropy":
+            l = (np.maximum(x, 0) - x * third + np.log1p(np.exp(-np.abs(x)))) / len(x)
+            g = (1 / (1 + np.exp(-x)) - third) / len(x)
+        else:
+            l = (third - x) ** 2; g = -2 * (third - x)
+    gs = [g, -g] if pairwise else [g]
+    total_loss = l.sum()
+    for p, (it, tw) in enumerate(passes):
+        gp = gs[p][:, None].astype(dt)
+        if has_mf:
+            pu, qi = P["mf_user"][users], P["mf_item"][it]
+            np.add.at(G["mf_user"], users, (gp * qi + (reg_mf * pu if p == 0 else 0)).astype(dt))
+            np.add.at(G["mf_item"], it, (gp * pu + reg_mf * qi).astype(dt))
+            total_loss += reg_mf * dt.type(0.5) * ((qi * qi).sum() + ((pu * pu).sum() if p == 0 else 0))
+        if layers:
+            acts = cache[p]
+            delta = (gp * (acts[-1] > 0)).astype(dt)
+            for li in range(len(lay) - 1, -1, -1):
+                wo, inn, out, bo = lay[li]
+                W = P["dense"][tw * tsz + wo:tw * tsz + wo + inn * out].reshape(inn, out)
+                G["dense"][tw * tsz + wo:tw * tsz + wo + inn * out] += (acts[li].T @ delta).reshape(-1).astype(dt)
+                G["dense"][tw * tsz + bo:tw * tsz + bo + out] += delta.sum(0)
+                delta = (delta @ W.T).astype(dt)
+                if li > 0:
+                    delta = (delta * (acts[li] > 0)).astype(dt)
+            mu, mi = P["mlp_user"][users], P["mlp_item"][it]
+            np.add.at(G["mlp_user"], users, (delta[:, :mlp_dim] + (reg_mlp * mu if p == 0 else 0)).astype(dt))
+            np.add.at(G["mlp_item"], it, (delta[:, mlp_dim:] + reg_mlp * mi).astype(dt))
+            total_loss += reg_mlp * dt.type(0.5) * ((mi * mi).sum() + ((mu * mu).sum() if p == 0 else 0))
+    nu = (P["mlp_user"] if layers else P["mf_user"]).shape[0]
+    ni = (P["mlp_item"] if layers else P["mf_item"]).shape[0]
+    tU = np.zeros(nu, bool); tU[users] = True
+    tI = np.zeros(ni, bool)
+    for it, _ in passes:
+        tI[it] = True
+    return dt.type(total_loss), G, tU, tI
+
+
+class NCFTrainer:
+    """CPU stand-in for NeuMF/MLP build_graph + train loop (NeuMF.py:106-151)."""
+    TABLES = ("mf_user", "mf_item", "mlp_user", "mlp_item")
+
+    def __init__(self, P, mlp_dim, layers, n_towers, learner="adam", lr=1e-3, loss="cross_entropy",
+                 reg_mf=0.0, reg_mlp=0.0, pairwise=False):
+        self.P = {k: (np.array(v, dtype=f32) if v is not None else None) for k, v in P.items()}
+        self.mlp_dim, self.layers, self.n_towers = mlp_dim, list(layers), n_towers
+        self.learner, self.lr, self.loss, self.pairwise = learner, lr, loss, pairwise
+        self.reg_mf, self.reg_mlp = reg_mf, reg_mlp
+        i0, i1 = SLOT_INIT[learner]
+        mk = lambda a, v: None if (v is None or a is None) else np.full_like(a, v)
+        self.s0 = {k: mk(v, i0) for k, v in self.P.items()}
+        self.s1 = {k: mk(v, i1) for k, v in self.P.items()}
+        self.t = 0
+
+    def step(self, users, items, third):
+        l, G, tU, tI = ncf_grad(self.P, users, items, third, self.pairwise, self.loss, self.reg_mf,
+                                self.reg_mlp, self.mlp_dim, self.layers, self.n_towers)
+        hyper = DEFAULT_HYPER[self.learner](self.lr)
+        if self.learner == "adam":
+            hyper[0] = adam_lr_t(self.lr, 1, start_step=self.t)[0]
+        for k in self.TABLES:
+            if self.P[k] is None or self.P[k].shape[1] == 0:
+                continue
+            opt_apply(self.learner, self.P[k], G[k], self.s0[k], self.s1[k], tU if "user" in k else tI, hyper)
+        if self.layers:
+            opt_apply(self.learner, self.P["dense"], G["dense"], self.s0["dense"], self.s1["dense"],
+                      None, hyper, dense_var=True)
+        self.t += 1
+        return l
+
+    def epoch(self, users, items, third, batch_size):
+        out = []
+        for off in range(0, len(users), batch_size):
+            sl = slice(off, min(len(users), off + batch_size))
+            out.append(self.step(users[sl], items[sl], third[sl]))
+        return np.asarray(out, f32)
