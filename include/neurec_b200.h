@@ -102,6 +102,19 @@ int nrc_eval_mf(const float* user_table, const float* item_table, int32_t dim,
                 const int32_t* metric_host, int32_t metric_num, int32_t top_k,
                 float* results, int32_t* ranks, void* stream);
 
+/* MF.predict(user_ids, None), model/general_recommender/MF.py:120-122 (np.matmul(U[users], V.T))
+ * and LightGCN.predict, LightGCN.py:187-189, materialised: scores f32 [num_rows, num_items]
+ * with the same fp32 FMA chain over k the fused evaluator uses. */
+int nrc_mf_scores(const float* user_table, const float* item_table, int32_t dim,
+                  int32_t num_items, const int32_t* users, int32_t num_rows, float* scores,
+                  void* stream);
+
+/* The train mask of UniEvaluator.evaluate, evaluator/backend/cpp/uni_evaluator.py:140-143:
+ * scores[b, train_items(users[b])] = -inf for a materialised [num_rows, rating_len] matrix
+ * (train CSR indexed by user id). */
+int nrc_mask_rows(float* scores, int32_t rating_len, int32_t num_rows, const int32_t* users,
+                  const int64_t* train_indptr, const int32_t* train_indices, void* stream);
+
 /* np.mean(all_user_result, axis=0) in fp32, evaluator/backend/cpp/uni_evaluator.py:150:
  * out[c] = (sequential fp32 sum over rows of results[:, c]) / num_rows, bit-identical to
  * numpy's axis-0 reduction order. */

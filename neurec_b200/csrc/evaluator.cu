@@ -667,6 +667,72 @@ extern "C" int nrc_eval_mf(const float* user_table, const float* item_table, int
     return NRC_OK;
 }
 
+namespace nrc {
+// uni_evaluator.py:140-143: ranking_score[idx][train_items] = -inf, one warp per batch row.
+__global__ void mask_rows_kernel(float* __restrict__ scores, int N, int rows,
+                                 const int32_t* __restrict__ users,
+                                 const int64_t* __restrict__ tptr,
+                                 const int32_t* __restrict__ tidx) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const int u = users[row];
+    const int64_t beg = tptr[u], end = tptr[u + 1];
+    for (int64_t p = beg + lane; p < end; p += kWarp) {
+        const int it = tidx[p];
+        if (it >= 0 && it < N) scores[(size_t)row * N + it] = -INFINITY;
+    }
+}
+}  // namespace nrc
+
+namespace nrc {
+// MF.predict / LightGCN.predict (MF.py:120-122, LightGCN.py:187-189) materialised: the same
+// fp32 FMA chain over k as the fused evaluator, so predict() returns exactly the scores the
+// fused path ranks.  One thread per (row, item); a warp covers 32 consecutive items.
+__global__ void mf_scores_kernel(const float* __restrict__ U, const float* __restrict__ V, int D,
+                                 int N, const int32_t* __restrict__ users, int rows,
+                                 float* __restrict__ out) {
+    const int64_t total = (int64_t)rows * N;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / N), i = (int)(e - (int64_t)b * N);
+        const float* u = U + (size_t)users[b] * D;
+        const float* v = V + (size_t)i * D;
+        float acc = 0.0f;
+        for (int k = 0; k < D; ++k) acc = __fmaf_rn(__ldg(u + k), __ldg(v + k), acc);
+        out[e] = acc;
+    }
+}
+}  // namespace nrc
+
+extern "C" int nrc_mf_scores(const float* user_table, const float* item_table, int32_t dim,
+                             int32_t num_items, const int32_t* users, int32_t num_rows,
+                             float* scores, void* stream) {
+    NRC_REQUIRE(dim > 0 && num_items > 0 && num_rows >= 0, NRC_E_VALUE, "bad shape");
+    if (num_rows == 0) return NRC_OK;
+    const int64_t total = (int64_t)num_rows * num_items;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    mf_scores_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(user_table, item_table, dim,
+                                                                      num_items, users, num_rows, scores);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+extern "C" int nrc_mask_rows(float* scores, int32_t rating_len, int32_t num_rows,
+                             const int32_t* users, const int64_t* train_indptr,
+                             const int32_t* train_indices, void* stream) {
+    NRC_REQUIRE(rating_len > 0 && num_rows >= 0, NRC_E_VALUE, "bad shape");
+    if (num_rows == 0) return NRC_OK;
+    const int threads = 256;
+    const int blocks = (int)(((int64_t)num_rows * 32 + threads - 1) / threads);
+    mask_rows_kernel<<<blocks, threads, 0, as_stream(stream)>>>(scores, rating_len, num_rows, users,
+                                                                train_indptr, train_indices);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
 extern "C" int nrc_mean_rows(const float* results, int64_t num_rows, int32_t num_cols,
                              float* out, void* stream) {
     NRC_REQUIRE(num_cols >= 0 && num_rows >= 0, NRC_E_VALUE, "negative shape");

@@ -119,6 +119,29 @@ def eval_mf(user_table, item_table, users, train_indptr, train_indices, test_ind
     return (res, ranks) if return_ranks else res
 
 
+def mf_scores(user_table, item_table, users):
+    """MF.predict(users, None) on device: [len(users), num_items] fp32 (MF.py:120-122)."""
+    _req(user_table, torch.float32, "user_table"); _req(item_table, torch.float32, "item_table")
+    _req(users, torch.int32, "users")
+    N, D = item_table.shape
+    out = torch.empty((users.numel(), N), dtype=torch.float32, device=users.device)
+    check(_lib.load().nrc_mf_scores(_p(user_table), _p(item_table), D, N, _p(users), users.numel(),
+                                    _p(out), _stream()))
+    _count()
+    return out
+
+
+def mask_rows(scores, users, train_indptr, train_indices):
+    """In place scores[b, train(users[b])] = -inf (uni_evaluator.py:140-143)."""
+    _req(scores, torch.float32, "scores")
+    _req(users, torch.int32, "users")
+    B, N = scores.shape
+    check(_lib.load().nrc_mask_rows(_p(scores), N, B, _p(users), _p(train_indptr), _p(train_indices),
+                                    _stream()))
+    _count()
+    return scores
+
+
 def mean_rows(results):
     """np.mean(results, axis=0) with numpy's fp32 summation order (uni_evaluator.py:150)."""
     _req(results, torch.float32, "results")
