@@ -1,30 +1,36 @@
 #!/usr/bin/env python
 """bench.py -- the driver's measurement contract for the neurec_b200 hot path.
 
-    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference] [--only]
 
 A "step" is one training batch (one `sess.run((loss, optimizer), feed_dict)` of the reference's
-train_model) through the fused sm_100a kernels.  One JSON line is printed by rank 0:
+train_model) through the fused sm_100a kernels.  Rank 0 prints ONE JSON line:
 
-  value     whole-job triplets/s with the epoch's (user, item, neg|label) arrays already
-            resident in HBM when the timed region starts (device sampler ran before it)
-  e2e       the same metric through the reference-facing per-step C-ABI call with HOST
-            buffers: per step H2D of the batch ids from pinned memory, both kernels, D2H of
-            the loss and a stream sync (the analogue of sess.run returning the loss)
+  value     whole-job samples/s ("triplets/s"; a pointwise sample counts as one triplet,
+            SURVEY.md 8d) with the epoch's id arrays already resident in HBM when the timed
+            region starts (the device sampler ran before it)
+  e2e       the same metric through the reference-facing per-step calls with HOST buffers: per
+            step H2D of the batch ids/labels from pinned memory, the step's kernels, D2H of the
+            loss and a stream sync (the analogue of sess.run returning the loss)
   eval      users/s of the full-catalogue evaluator (predict + mask + top-K + 5 metrics)
-  roofline  dominant kernel's algorithmic bytes / its CUDA-event launch time vs the measured
-            HBM copy peak (MEASURED_PEAKS.json)
-  cpu_baseline  the reference's CPU path (oracle/ref_port.py: real compiled reference pieces
-            from oracle/_ref where they exist + the numpy restatement of the TF-1.12 step)
-            timed on this box's host cores on a bounded sample
+  roofline  dominant kernel: algorithmic bytes per launch / its CUDA-event launch time (graph
+            replay of that kernel alone) vs the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's CPU path (oracle/ref_port.py: the real compiled reference
+            pieces from oracle/_ref where they exist + the numpy restatement of the TF-1.12
+            step) timed on this box's host cores on a bounded sample
+  others    (N=1, unless --only) the same measurements for the other single-GPU configs
 
-Multi-GPU: the training path of these table sizes does not shard (a 2 MB model with ~5 us
-steps; see DESIGN.md "replicas only"), so --gpus N runs N independent replicas (weak scaling);
-the evaluator shards users across ranks with one all-reduce of the metric sums.
+Workloads (BASELINE.json configs): neumf-ml100k (configs[1], default), bprmf-ml100k
+(configs[0]), lightgcn-gowalla (configs[2], synthetic gowalla-shaped graph).
+
+Multi-GPU: training of these table sizes does not shard (2-20 MB models with microsecond
+steps; DESIGN.md "replicas only"), so --gpus N runs N independent replicas (weak scaling); the
+evaluator shards users across ranks and all-gathers the per-user rows.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -36,8 +42,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = ("bprmf-ml100k", "neumf-ml100k", "lightgcn-gowalla")
-DEFAULT_WORKLOAD = "bprmf-ml100k"
+WORKLOADS = ("neumf-ml100k", "bprmf-ml100k", "lightgcn-gowalla")
+DEFAULT_WORKLOAD = "neumf-ml100k"
+METRICS = ["Precision", "Recall", "NDCG", "MAP", "MRR"]
 
 
 # ----------------------------------------------------------------------------------------
@@ -45,46 +52,76 @@ DEFAULT_WORKLOAD = "bprmf-ml100k"
 # ----------------------------------------------------------------------------------------
 def load_ml100k():
     z = np.load(os.path.join(ROOT, "tests", "golden", "ml100k_split.npz"))
-    return {"num_users": int(z["num_users"]), "num_items": int(z["num_items"]),
+    return {"name": "ml-100k", "num_users": int(z["num_users"]), "num_items": int(z["num_items"]),
             "train_indptr": z["train_indptr"].astype(np.int64),
             "train_indices": z["train_indices"].astype(np.int32),
             "test_indptr": z["test_indptr"].astype(np.int64),
             "test_indices": z["test_indices"].astype(np.int32)}
 
 
+def synth_gowalla(seed=7):
+    """Synthetic graph with gowalla's shape (U=29 858, I=40 981, ~810 k train and
+    ~217 k test interactions, power-law item popularity, user degrees 8..~800)."""
+    rs = np.random.RandomState(seed)
+    nu, ni = 29858, 40981
+    deg = np.clip((8 + rs.pareto(1.35, nu) * 9).astype(np.int64), 8, 811)
+    deg = (deg * (810128 / deg.sum())).astype(np.int64).clip(6, 811)
+    pop = 1.0 / np.power(np.arange(1, ni + 1), 0.75)
+    pop = pop[rs.permutation(ni)]
+    pop /= pop.sum()
+    tot = int((deg * 1.45).sum())
+    draws = rs.choice(ni, size=tot, p=pop).astype(np.int32)
+    off = np.concatenate([[0], np.cumsum((deg * 1.45).astype(np.int64))])
+    tr_rows, te_rows = [], []
+    for u in range(nu):
+        it = np.unique(draws[off[u]:off[u + 1]])
+        rs.shuffle(it)
+        k = max(1, int(round(len(it) * 0.79)))
+        tr_rows.append(np.sort(it[:k])); te_rows.append(np.sort(it[k:]) if len(it) > k else np.sort(it[:1]))
+
+    def csr(rows):
+        ptr = np.zeros(nu + 1, np.int64)
+        ptr[1:] = np.cumsum([len(r) for r in rows])
+        return ptr, np.concatenate(rows).astype(np.int32)
+    tp, ti = csr(tr_rows)
+    sp_, si = csr(te_rows)
+    return {"name": "gowalla-shaped synthetic", "num_users": nu, "num_items": ni, "train_indptr": tp,
+            "train_indices": ti, "test_indptr": sp_, "test_indices": si}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
-        d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
 class ClockSampler:
     """Samples SM clock / throttle reasons through NVML while the benchmark runs."""
 
-    def __init__(self, index=0, period=0.01):
-        self.samples, self.period, self.index = [], period, index
+    def __init__(self, index=0, period=0.005):
+        self.samples, self.period = [], period
         self._stop = threading.Event()
-        self.ok = False
+        self.ok, self.max = False, None
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
             self.ok = True
         except Exception:
-            self.max = None
+            pass
 
     def _run(self):
         nv = self.nv
         while not self._stop.is_set():
             try:
-                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
-                self.samples.append((time.perf_counter(), clk, rs, util))
+                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetCurrentClocksEventReasons(self.h),
+                                     nv.nvmlDeviceGetUtilizationRates(self.h).gpu))
             except Exception:
                 pass
             time.sleep(self.period)
@@ -99,14 +136,14 @@ class ClockSampler:
             self._stop.set()
             self.t.join()
 
-    def summary(self, t0=None, t1=None):
+    def summary(self, windows):
         if not self.ok or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max, "reasons": ["nvml unavailable"]}
         nv = self.nv
-        sel = [s for s in self.samples if (t0 is None or s[0] >= t0) and (t1 is None or s[0] <= t1)]
-        where = "timed region"
+        sel = [s for s in self.samples if any(a <= s[0] <= b for a, b in windows)]
+        where = "timed regions"
         if len(sel) < 3:
-            sel, where = self.samples, "whole run (timed region shorter than the sampling period)"
+            sel, where = self.samples, "whole run (timed regions shorter than the sampling period)"
         names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
                  "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
                  "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
@@ -114,13 +151,12 @@ class ClockSampler:
         bits = 0
         for s in sel:
             bits |= s[2]
-        reasons = [k for k, v in names.items() if bits & v]
         busy = [s[1] for s in sel if s[3] > 0] or [s[1] for s in sel]
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": self.max, "reasons": reasons,
-                "samples": len(sel), "window": where}
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": self.max,
+                "reasons": [k for k, v in names.items() if bits & v], "samples": len(sel), "window": where}
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -162,122 +198,206 @@ def flush_l2():
     _FLUSH.fill_(1)
 
 
-# ----------------------------------------------------------------------------------------
-# workload: BPRMF on ml-100k (BASELINE.json configs[0]; conf/MF.properties)
-# ----------------------------------------------------------------------------------------
-class BprmfMl100k:
-    name = "bprmf-ml100k"
-    describe = "BPRMF on ml-100k, dim=64, conf/MF.properties (bs 512, adam 1e-3, bpr, reg 0)"
-    dim, batch, lr, reg, loss, opt, pairwise, neg_num = 64, 512, 1e-3, 0.0, "bpr", "adam", True, 1
-    hyper = [1e-3, 0.9, 0.999, 1e-8]
+def graph_time(fn, reps=40, rounds=5):
+    """Average device time of one `fn()` launch group: `reps` calls captured in a CUDA graph and
+    replayed (no host launch overhead), CUDA events on the replay stream, best of `rounds`."""
+    import torch
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(rounds):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            g.replay()
+            b.record(s)
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+    torch.cuda.current_stream().wait_stream(s)
+    return best * 1e-3 / reps
 
-    def __init__(self, rank=0):
-        self.d = load_ml100k()
-        self.rank = rank
-        d = self.d
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ----------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------
+class Workload:
+    """Common plumbing: data, device sampler/shuffle, e2e staging, evaluator, CPU reference."""
+    pairwise = True
+    neg_num = 1
+    eval_k = 20
+
+    def __init__(self, data, rank):
+        self.d, self.rank = data, rank
+        d = data
         self.users_of_pos = np.repeat(np.arange(d["num_users"], dtype=np.int32), np.diff(d["train_indptr"]))
         self.n_pos = len(self.users_of_pos)
-        self.steps_per_epoch = (self.n_pos + self.batch - 1) // self.batch
-        rs = np.random.RandomState(2017 + rank)
-        self.U0 = (rs.randn(d["num_users"], self.dim) * 0.01).astype(np.float32)   # normal(0, .01)
-        self.V0 = (rs.randn(d["num_items"], self.dim) * 0.01).astype(np.float32)
+        self.n_samples = self.n_pos * (1 if self.pairwise else self.neg_num + 1)
+        self.steps_per_epoch = (self.n_samples + self.batch - 1) // self.batch
 
-    # ---------------------------------------------------------------- device state
-    def setup_device(self):
+    def setup_common(self):
         import torch
-        from oracle import tf_math  # only for the fp32 lr_t schedule helper (host arithmetic)
-        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
         d = self.d
         self.tp, self.ti = dev(d["train_indptr"]), dev(d["train_indices"])
         self.sp, self.si = dev(d["test_indptr"]), dev(d["test_indices"])
+        self.d_users_of_pos = dev(self.users_of_pos)
+        self.staging = torch.empty(3 * self.batch + 4, dtype=torch.int32, device="cuda")
+        self.loss_pin = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.lr_sched = self._lr_schedule(1 << 17)
+        self.t = 0
+        self.stamp = 1
+
+    def _lr_schedule(self, n):
+        out = np.empty(n, np.float32)
+        p1, p2, one, lr = np.float32(0.9), np.float32(0.999), np.float32(1), np.float32(self.lr)
+        for s in range(n):
+            out[s] = lr * np.sqrt(one - p2) / (one - p1)
+            p1 = np.float32(p1 * np.float32(0.9)); p2 = np.float32(p2 * np.float32(0.999))
+        return out
+
+    def epoch_arrays(self, n_steps, epoch=0):
+        """Device sampler + shuffle for n_steps batches (wraps over epochs if needed)."""
+        import torch
+        from neurec_b200 import ops
+        need = n_steps * self.batch
+        us, its, th = [], [], []
+        e = 0
+        while need > 0:
+            neg = ops.sample_negatives(self.tp, self.ti, self.d_users_of_pos, self.neg_num,
+                                       self.d["num_items"], 2018, epoch + e)
+            if self.pairwise:
+                u, i, t = self.d_users_of_pos, self.ti, neg[:, 0]
+            else:
+                u = self.d_users_of_pos.repeat(self.neg_num + 1)
+                i = torch.cat([self.ti, neg.t().reshape(-1)])
+                t = torch.cat([torch.ones(self.n_pos, device="cuda"),
+                               torch.zeros(self.n_pos * self.neg_num, device="cuda")])
+            perm = torch.randperm(u.numel(), device="cuda")[:min(need, u.numel())]
+            us.append(u[perm]); its.append(i[perm]); th.append(t[perm])
+            need -= perm.numel(); e += 1
+        cat = lambda xs: torch.cat(xs).contiguous()
+        return cat(us), cat(its), cat(th)
+
+    def stage(self, h_arrays, off):
+        """H2D of one batch of (users, items, third) from pinned host memory."""
+        from neurec_b200 import _lib
+        import torch
+        lib = _lib.load()
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = [ctypes.c_void_p(h.data_ptr() + 4 * off) for h in h_arrays]
+        _lib.check(lib.nrc_stage_batch_host(p[0], p[1], p[2], self.batch, ctypes.c_void_p(self.staging.data_ptr()), st))
+        b = self.batch
+        import torch as T
+        third = self.staging[2 * b:3 * b]
+        if not self.pairwise:
+            third = third.view(T.float32)
+        return self.staging[:b], self.staging[b:2 * b], third
+
+    def fetch(self, dev_tensor, count):
+        from neurec_b200 import _lib
+        import torch
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.load().nrc_fetch_host(ctypes.c_void_p(dev_tensor.data_ptr()),
+                                              ctypes.c_void_p(self.loss_pin.data_ptr()), count, st))
+        return float(self.loss_pin[0])
+
+    def run_steps_e2e(self, h_arrays, n_steps):
+        total = 0.0
+        for s in range(n_steps):
+            u, i, t = self.stage(h_arrays, s * self.batch)
+            loss = self.step_on_staged(u, i, t)
+            total += self.fetch(loss, self.loss_count)
+        return total, 3 * 4 * self.batch, 4 * self.loss_count
+
+    def cpu_eval(self, threads, U, V, max_users=None):
+        from oracle import ref_port
+        d = self.d
+        train_dict = ref_port.user_dict(d["train_indptr"], d["train_indices"])
+        test_dict = ref_port.user_dict(d["test_indptr"], d["test_indices"])
+        if max_users is not None and len(test_dict) > max_users:
+            keys = list(test_dict.keys())[:max_users]
+            test_dict = {k: test_dict[k] for k in keys}
+        best = None
+        for th in sorted({8, min(threads, 32)}):     # reference default num_thread=8 vs more threads
+            t0 = time.perf_counter()
+            _, parts, impl = ref_port.evaluate(U, V, train_dict, test_dict, [1, 2, 4, 3, 5], self.eval_k, 128, th)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, th, parts, impl)
+        return best[0], len(test_dict), best[3], best[1]
+
+
+class BprmfMl100k(Workload):
+    name = "bprmf-ml100k"
+    describe = "BPRMF on ml-100k, dim=64, conf/MF.properties (bs 512, adam 1e-3, bpr, reg 0)"
+    dim, batch, lr, reg, loss, opt = 64, 512, 1e-3, 0.0, "bpr", "adam"
+    hyper = [1e-3, 0.9, 0.999, 1e-8]
+    loss_count = 1
+    launches_per_step = 2
+
+    def __init__(self, rank=0):
+        super().__init__(load_ml100k(), rank)
+        rs = np.random.RandomState(2017 + rank)
+        self.U0 = (rs.randn(self.d["num_users"], self.dim) * 0.01).astype(np.float32)
+        self.V0 = (rs.randn(self.d["num_items"], self.dim) * 0.01).astype(np.float32)
+
+    def setup_device(self):
+        import torch
+        self.setup_common()
         self.dU, self.dV = dev(self.U0), dev(self.V0)
         z = torch.zeros_like
         self.gU, self.gV = z(self.dU), z(self.dV)
         self.mU, self.vU, self.mV, self.vV = z(self.dU), z(self.dU), z(self.dV), z(self.dV)
-        self.tU = torch.zeros(d["num_users"], dtype=torch.int32, device="cuda")
-        self.tV = torch.zeros(d["num_items"], dtype=torch.int32, device="cuda")
-        self.d_users_of_pos = dev(self.users_of_pos)
-        self.stamp = 1
-        self.lr_t = tf_math.adam_lr_t(self.lr, 1 << 16)
-        self.t = 0
+        self.tU = torch.zeros(self.d["num_users"], dtype=torch.int32, device="cuda")
+        self.tV = torch.zeros(self.d["num_items"], dtype=torch.int32, device="cuda")
+        self.step_loss = torch.zeros(1 << 16, device="cuda")
 
-    def device_epoch_arrays(self, n_steps, epoch):
-        """Device sampler + shuffle for n_steps batches (several epochs if needed)."""
-        import torch
+    def run_steps_device(self, arrays, n_steps):
         from neurec_b200 import ops
-        need = n_steps * self.batch
-        us, ps, ns = [], [], []
-        e = 0
-        while need > 0:
-            neg = ops.sample_negatives(self.tp, self.ti, self.d_users_of_pos, 1, self.d["num_items"],
-                                       2018, epoch + e)[:, 0]
-            perm = torch.randperm(self.n_pos, device="cuda")
-            take = min(need, self.n_pos)
-            perm = perm[:take]
-            us.append(self.d_users_of_pos[perm]); ps.append(self.ti[perm]); ns.append(neg[perm])
-            need -= take; e += 1
-        cat = lambda xs: torch.cat(xs).contiguous()
-        return cat(us), cat(ps), cat(ns)
-
-    def run_steps_device(self, users, pos, neg, n_steps):
-        import torch
-        from neurec_b200 import ops
-        n = min(users.numel(), n_steps * self.batch)
-        step_loss = torch.empty(n_steps, device="cuda")
-        ops.mf_train_epoch(self.dU, self.dV, users[:n], pos[:n], neg[:n], self.batch, True, self.loss,
-                           self.reg, self.opt, self.lr_t[self.t:self.t + n_steps], self.hyper, self.gU,
-                           self.gV, self.tU, self.tV, self.mU, self.vU, self.mV, self.vV, self.stamp,
-                           step_loss)
+        u, i, t = arrays
+        n = min(u.numel(), n_steps * self.batch)
+        ops.mf_train_epoch(self.dU, self.dV, u[:n], i[:n], t[:n], self.batch, True, self.loss, self.reg,
+                           self.opt, self.lr_sched[self.t:self.t + n_steps], self.hyper, self.gU, self.gV,
+                           self.tU, self.tV, self.mU, self.vU, self.mV, self.vV, self.stamp, self.step_loss)
         self.stamp += n_steps; self.t += n_steps
-        return step_loss, 2 * n_steps
+        return self.launches_per_step * n_steps
 
-    # ---------------------------------------------------------------- e2e (host buffers)
-    def run_steps_e2e(self, h_users, h_pos, h_neg, n_steps):
-        """Per step: pinned host ids -> H2D -> grad kernel -> optimizer kernel -> loss D2H."""
-        import ctypes
-        import torch
-        from neurec_b200 import _lib
-        lib = _lib.load()
-        staging = torch.empty(3 * self.batch + 4, dtype=torch.int32, device="cuda")
-        loss_h = torch.zeros(1, dtype=torch.float32).pin_memory()
-        hyper = np.array(self.hyper, dtype=np.float32)
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        p = lambda t: ctypes.c_void_p(t.data_ptr())
-        total = 0.0
-        bs = self.batch
-        for s in range(n_steps):
-            hyper[0] = self.lr_t[self.t]
-            o = s * bs
-            rc = lib.nrc_mf_train_step_host(
-                p(self.dU), p(self.dV), self.d["num_users"], self.d["num_items"], self.dim,
-                ctypes.c_void_p(h_users.data_ptr() + 4 * o), ctypes.c_void_p(h_pos.data_ptr() + 4 * o),
-                ctypes.c_void_p(h_neg.data_ptr() + 4 * o), bs, 1, _lib.LOSS_IDS[self.loss], self.reg,
-                _lib.OPT_IDS[self.opt], hyper.ctypes.data, p(self.gU), p(self.gV), p(self.tU), p(self.tV),
-                p(self.mU), p(self.vU), p(self.mV), p(self.vV), self.stamp, p(staging), p(loss_h), st)
-            _lib.check(rc)
-            total += float(loss_h[0])
-            self.stamp += 1; self.t += 1
-        return total, 3 * 4 * bs, 4
+    def step_on_staged(self, u, i, t):
+        self.run_steps_device((u, i, t), 1)
+        return self.step_loss
 
-    # ---------------------------------------------------------------- evaluator
-    def run_eval(self, users):
+    def eval_tables(self):
+        return self.dU, self.dV
+
+    def kernels(self, arrays):
         from neurec_b200 import ops
-        res = ops.eval_mf(self.dU, self.dV, users, self.tp, self.ti, self.sp, self.si,
-                          ["Precision", "Recall", "NDCG", "MAP", "MRR"], 20)
-        return ops.mean_rows(res)
-
-    # ---------------------------------------------------------------- roofline inputs
-    def algorithmic_bytes(self):
-        """per triplet gather 3 rows + ids = 12d+12 B; TF-faithful Adam moves
-        (U+I)*d*4 B * 3 arrays * (read+write) per step."""
+        import torch
+        u, i, t = (a[:self.batch] for a in arrays)
+        loss = torch.zeros(1, device="cuda")
+        hyper = list(self.hyper)
+        grad = lambda: ops.mf_pairwise_grad(self.dU, self.dV, u, i, t, self.loss, self.reg, self.gU, self.gV,
+                                            self.tU, self.tV, 7, loss)
+        opt = lambda: ops.opt_apply_multi(self.opt, [(self.dU, self.gU, self.mU, self.vU, self.tU, False),
+                                                     (self.dV, self.gV, self.mV, self.vV, self.tV, False)], 7, hyper)
         rows = self.d["num_users"] + self.d["num_items"]
-        grad = self.batch * (12 * self.dim + 12)
-        adam = rows * self.dim * 4 * 3 * 2
-        return {"mf_pairwise_grad_kernel": grad, "opt_apply_kernel": adam}
+        return {"mf_pairwise_grad_kernel": (grad, self.batch * (12 * self.dim + 12),
+                                            "512 triplets x (3 rows of 64 f32 + 3 ids)"),
+                "opt_apply_kernel": (opt, rows * self.dim * 4 * 3 * 2,
+                                     "TF-faithful Adam: (U+I)*d*4 B x {var,m,v} x read+write")}
 
-    # ---------------------------------------------------------------- CPU reference path
-    def cpu_reference(self, n_steps, threads):
-        """The reference's CPU path for n_steps batches: real sampler pieces + numpy TF step."""
+    def cpu_reference(self, n_steps):
         from oracle import ref_port, tf_math
         d = self.d
         train_dict = ref_port.user_dict(d["train_indptr"], d["train_indices"])
@@ -291,203 +411,411 @@ class BprmfMl100k:
                 done += 1
                 if done >= n_steps:
                     break
-        dt = time.perf_counter() - t0
-        return dt, ref_port.sampler_kind()
+        return time.perf_counter() - t0, ref_port.sampler_kind()
 
-    def cpu_eval(self, threads):
-        from oracle import ref_port
+    def cpu_tables(self):
+        return self.U0, self.V0
+
+
+class NeumfMl100k(Workload):
+    name = "neumf-ml100k"
+    describe = ("NeuMF (GMF+MLP) on ml-100k, embedding_size=32, layers [64,32,16], conf/NeuMF.properties "
+                "(pointwise cross_entropy, num_neg 4, bs 256, adam 1e-3)")
+    pairwise, neg_num = False, 4
+    mf_dim, layers, batch, lr, loss, opt = 32, [64, 32, 16], 256, 1e-3, "cross_entropy", "adam"
+    hyper = [1e-3, 0.9, 0.999, 1e-8]
+    loss_count = 1
+    launches_per_step = 2
+    KEYS = ("mf_user", "mf_item", "mlp_user", "mlp_item", "dense")
+
+    def __init__(self, rank=0):
+        super().__init__(load_ml100k(), rank)
+        rs = np.random.RandomState(2017 + rank)
+        nu, ni = self.d["num_users"], self.d["num_items"]
+        n = lambda r, c: (rs.randn(r, c) * 0.01).astype(np.float32)
+        self.P0 = {"mf_user": n(nu, 32), "mf_item": n(ni, 32), "mlp_user": n(nu, 32), "mlp_item": n(ni, 32)}
+        dense, inn = [], 64
+        for out in self.layers:                      # glorot-uniform kernels, zero biases
+            lim = np.sqrt(6.0 / (inn + out))
+            dense += [rs.uniform(-lim, lim, inn * out).astype(np.float32), np.zeros(out, np.float32)]
+            inn = out
+        self.P0["dense"] = np.concatenate(dense)
+
+    def setup_device(self):
+        import torch
+        from neurec_b200 import ops
+        self.setup_common()
+        nu, ni = self.d["num_users"], self.d["num_items"]
+        self.shape = ops.NcfShape.make(nu, ni, self.mf_dim, self.layers, 1)
+        self.P = {k: dev(v) for k, v in self.P0.items()}
+        z = lambda D: {k: torch.zeros_like(v) for k, v in D.items()}
+        self.G, self.S0, self.S1 = z(self.P), z(self.P), z(self.P)
+        self.tU = torch.zeros(nu, dtype=torch.int32, device="cuda")
+        self.tI = torch.zeros(ni, dtype=torch.int32, device="cuda")
+        self.step_loss = torch.zeros(1 << 16, device="cuda")
+
+    def run_steps_device(self, arrays, n_steps):
+        from neurec_b200 import ops
+        u, i, t = arrays
+        n = min(u.numel(), n_steps * self.batch)
+        ops.ncf_train_epoch(self.shape, self.P, u[:n], i[:n], t[:n], self.batch, False, self.loss, 0.0, 0.0,
+                            self.opt, self.lr_sched[self.t:self.t + n_steps], self.hyper, self.G, self.S0,
+                            self.S1, self.tU, self.tI, self.stamp, self.step_loss)
+        self.stamp += n_steps; self.t += n_steps
+        return self.launches_per_step * n_steps
+
+    def step_on_staged(self, u, i, t):
+        self.run_steps_device((u, i, t), 1)
+        return self.step_loss
+
+    def eval_tables(self):
+        return None
+
+    def run_eval(self, users):
+        """users must be a contiguous id range (what bench.py's sharding hands out)."""
+        from neurec_b200 import ops
+        a, b = int(users[0].item()), int(users[-1].item()) + 1
+        scores = ops.ncf_scores(self.shape, self.P, users)          # NeuMF.predict over all items
+        ops.mask_rows(scores, users, self.tp, self.ti)
+        ptr = (self.sp[a:b + 1] - self.sp[a]).contiguous()
+        idx = self.si[int(self.sp[a].item()):int(self.sp[b].item())].contiguous()
+        return ops.eval_score_matrix(scores, ptr, idx, METRICS, self.eval_k)
+
+    def kernels(self, arrays):
+        from neurec_b200 import ops
+        import torch
+        u, i, t = (a[:self.batch] for a in arrays)
+        loss = torch.zeros(1, device="cuda")
+        grad = lambda: ops.ncf_grad(self.shape, self.P, u, i, t, False, self.loss, 0.0, 0.0, self.G, self.tU,
+                                    self.tI, 7, loss)
+        variables = [(self.P[k], self.G[k], self.S0[k], self.S1[k], (self.tU if "user" in k else self.tI), False)
+                     for k in self.KEYS[:4]] + [(self.P["dense"], self.G["dense"], self.S0["dense"],
+                                                 self.S1["dense"], None, True)]
+        opt = lambda: ops.opt_apply_multi(self.opt, variables, 7, list(self.hyper))
+        n_par = sum(v.numel() for v in self.P.values())
+        return {"ncf_grad_kernel": (grad, self.batch * (4 * 32 * 4 * 2 + 12) + self.P["dense"].numel() * 4 * 2,
+                                    "256 samples x (4 rows of 32 f32 gathered + their gradients + ids) + "
+                                    "dense weights read + their gradient written"),
+                "opt_apply_kernel": (opt, n_par * 4 * 3 * 2,
+                                     "TF-faithful Adam over 4 tables + dense: params*4 B x {var,m,v} x R+W")}
+
+    def cpu_reference(self, n_steps):
+        from oracle import ref_port, tf_math
+        d = self.d
+        train_dict = ref_port.user_dict(d["train_indptr"], d["train_indices"])
+        np.random.seed(2018)
+        sampler = ref_port.PointwiseSamplerPort(train_dict, d["num_items"], self.neg_num, self.batch, True)
+        tr = tf_math.NCFTrainer(self.P0, 32, self.layers, 1, self.opt, self.lr, self.loss, 0.0, 0.0, False)
+        done, t0 = 0, time.perf_counter()
+        while done < n_steps:
+            for bu, bi, bl in sampler:
+                tr.step(np.asarray(bu, np.int32), np.asarray(bi, np.int32), np.asarray(bl, np.float32))
+                done += 1
+                if done >= n_steps:
+                    break
+        return time.perf_counter() - t0, ref_port.sampler_kind()
+
+    def cpu_eval(self, threads, U=None, V=None, max_users=None):
+        """NeuMF.predict on the CPU = one forward over all items per user (NeuMF.py:163-168)."""
+        from oracle import ref_port, tf_math
         d = self.d
         train_dict = ref_port.user_dict(d["train_indptr"], d["train_indices"])
         test_dict = ref_port.user_dict(d["test_indptr"], d["test_indices"])
+        keys = list(test_dict.keys())[:256]
+        test_dict = {k: test_dict[k] for k in keys}
+        items = np.arange(d["num_items"])
+        pred = lambda bu: np.stack([tf_math.ncf_predict(self.P0, np.full(len(items), u), items, 32, self.layers)
+                                    for u in bu])
         t0 = time.perf_counter()
-        _, parts, impl = ref_port.evaluate(self.U0, self.V0, train_dict, test_dict, [1, 2, 4, 3, 5], 20,
-                                           128, threads)
-        return time.perf_counter() - t0, len(test_dict), impl
+        _, parts, impl = ref_port.evaluate(None, None, train_dict, test_dict, [1, 2, 4, 3, 5], self.eval_k, 128, 8,
+                                           predict=pred)
+        return time.perf_counter() - t0, len(test_dict), impl, 8
+
+
+class LightgcnGowalla(Workload):
+    name = "lightgcn-gowalla"
+    describe = ("LightGCN on a gowalla-shaped graph (29 858 users, 40 981 items), 3 layers dim=64, "
+                "conf/LightGCN.properties (bs 1024, adam 0.01, reg 1e-3, adj_type pre)")
+    dim, n_layers, batch, lr, reg = 64, 3, 1024, 0.01, 1e-3
+    hyper = [0.01, 0.9, 0.999, 1e-8]
+    loss_count = 2
+
+    def __init__(self, rank=0):
+        super().__init__(synth_gowalla(), rank)
+        self.launches_per_step = 2 * self.n_layers + 3
+        from oracle import tf_math      # host-side adjacency construction only (scipy, like the reference)
+        d = self.d
+        self.A = tf_math.lightgcn_adj(d["train_indptr"], d["train_indices"], d["num_users"], d["num_items"], "pre")
+        rs = np.random.RandomState(2017 + rank)
+        n = d["num_users"] + d["num_items"]
+        lim = np.sqrt(6.0 / (d["num_users"] + self.dim))
+        self.E0 = rs.uniform(-lim, lim, (n, self.dim)).astype(np.float32)
+
+    def setup_device(self):
+        import torch
+        self.setup_common()
+        A = self.A
+        self.csr = (dev(A.indptr.astype(np.int64)), dev(A.indices.astype(np.int32)), dev(A.data.astype(np.float32)))
+        self.order = dev(np.argsort(-np.diff(A.indptr), kind="stable").astype(np.int32))
+        self.e0 = dev(self.E0)
+        z = lambda: torch.zeros_like(self.e0)
+        self.m, self.v, self.ef, self.gf, self.ge = z(), z(), z(), z(), z()
+        self.work = (z(), z())
+        self.step_loss = torch.zeros((1 << 14, 2), device="cuda")
+
+    def run_steps_device(self, arrays, n_steps):
+        from neurec_b200 import ops
+        u, i, t = arrays
+        n = min(u.numel(), n_steps * self.batch)
+        d = self.d
+        ops.lightgcn_train_epoch(self.csr, None, self.order, d["num_users"], d["num_items"], self.n_layers,
+                                 self.e0, self.m, self.v, u[:n], i[:n], t[:n], self.batch, self.reg,
+                                 self.lr_sched[self.t:self.t + n_steps], self.hyper, self.ef, self.gf, self.ge,
+                                 self.work, self.step_loss)
+        self.t += n_steps
+        return self.launches_per_step * n_steps
+
+    def step_on_staged(self, u, i, t):
+        self.run_steps_device((u, i, t), 1)
+        return self.step_loss
+
+    def eval_tables(self):
+        from neurec_b200 import ops
+        ops.lightgcn_propagate(self.csr[0], self.csr[1], self.csr[2], self.order, self.e0, self.n_layers,
+                               self.ef, self.work)
+        nu = self.d["num_users"]
+        return self.ef[:nu].contiguous(), self.ef[nu:].contiguous()
+
+    def kernels(self, arrays):
+        from neurec_b200 import ops
+        n, nnz = self.A.shape[0], self.A.nnz
+        spmm = lambda: ops.spmm_csr(self.csr[0], self.csr[1], self.csr[2], self.e0, row_order=self.order,
+                                    y=self.work[0])
+        opt = lambda: ops.opt_apply_multi("adam", [(self.e0, self.ge, self.m, self.v, None, True)], 0,
+                                          list(self.hyper))
+        return {"spmm_csr_kernel": (spmm, nnz * 8 + (n + 1) * 8 + 2 * n * self.dim * 4,
+                                    "SURVEY.md 8(d): nnz*(4 B col + 4 B val) + indptr + N*d*4 B read + written"),
+                "opt_apply_kernel": (opt, n * self.dim * 4 * 4 * 2, "dense Adam: N*d*4 B x {var,m,v,grad} x R+W")}
+
+    def cpu_reference(self, n_steps):
+        from oracle import ref_port, tf_math
+        d = self.d
+        train_dict = ref_port.user_dict(d["train_indptr"], d["train_indices"])
+        np.random.seed(2018)
+        t0 = time.perf_counter()
+        sampler = ref_port.PairwiseSamplerPort(train_dict, d["num_items"], 1, self.batch, True)
+        it = iter(sampler)
+        first = next(it)                      # pays the epoch's negative sampling
+        t_sample = time.perf_counter() - t0
+        tr = tf_math.LightGCNTrainer(self.A, self.E0, d["num_users"], self.n_layers, self.lr, self.reg)
+        t1 = time.perf_counter()
+        done, batch = 0, first
+        while done < n_steps:
+            tr.step(np.asarray(batch[0], np.int32), np.asarray(batch[1], np.int32), np.asarray(batch[2], np.int32))
+            done += 1
+            batch = next(it)
+        t_steps = time.perf_counter() - t1
+        # charge the sampler its per-step share of a whole epoch
+        return t_steps + t_sample * n_steps / self.steps_per_epoch, ref_port.sampler_kind()
+
+    def cpu_tables(self):
+        nu = self.d["num_users"]
+        return self.E0[:nu], self.E0[nu:]
 
 
 def make_workload(name, rank):
-    if name == "bprmf-ml100k":
-        return BprmfMl100k(rank)
-    raise SystemExit("workload %s is not available in this build" % name)
+    return {"bprmf-ml100k": BprmfMl100k, "neumf-ml100k": NeumfMl100k, "lightgcn-gowalla": LightgcnGowalla}[name](rank)
 
 
 # ----------------------------------------------------------------------------------------
-# arms
+# measurement
 # ----------------------------------------------------------------------------------------
-def time_dominant_kernels(w, users, pos, neg, n_steps):
-    """Per-kernel CUDA-event timing (each launch bracketed by events on the launching stream)."""
-    import torch
+def eval_once(w, users):
     from neurec_b200 import ops
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    tg, to = [], []
-    loss = torch.zeros(1, device="cuda")
-    bs = w.batch
-    for s in range(n_steps):
-        sl = slice(s * bs, (s + 1) * bs)
-        a, b, c = ev(), ev(), ev()
-        a.record()
-        ops.mf_pairwise_grad(w.dU, w.dV, users[sl], pos[sl], neg[sl], w.loss, w.reg, w.gU, w.gV, w.tU, w.tV,
-                             w.stamp, loss)
-        b.record()
-        hyper = np.array(w.hyper, dtype=np.float32); hyper[0] = w.lr_t[w.t]
-        # both tables in one launch, exactly as the epoch driver does
-        ops.opt_apply_multi(w.opt, [(w.dU, w.gU, w.mU, w.vU, w.tU, False),
-                                    (w.dV, w.gV, w.mV, w.vV, w.tV, False)], w.stamp, hyper)
-        c.record()
-        w.stamp += 1; w.t += 1
-        tg.append((a, b)); to.append((b, c))
+    tabs = w.eval_tables()
+    if tabs is None:
+        return ops.mean_rows(w.run_eval(users))
+    res = ops.eval_mf(tabs[0], tabs[1], users, w.tp, w.ti, w.sp, w.si, METRICS, w.eval_k)
+    return ops.mean_rows(res)
+
+
+def measure(w, K, W, world, rank, windows, with_cpu=True):
+    """All numbers for one workload.  Returns the dict rank 0 prints (None on other ranks)."""
+    import torch
+    w.setup_device()
+    arrays = w.epoch_arrays(K + W, epoch=0)
+    cut = lambda n0: tuple(a[n0 * w.batch:] for a in arrays)
+
+    # ---- value: device-resident steps
+    w.run_steps_device(arrays, W)
+    barrier(world); flush_l2(); barrier(world)
+    wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launches = w.run_steps_device(cut(W), K)
+    e1.record()
+    barrier(world)
+    windows.append((wall0, time.perf_counter()))
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    value = world * K * w.batch / (ms * 1e-3)
+
+    # ---- e2e: per-step host buffers (pinned), loss read back every step
+    h_arrays = tuple(a.cpu().pin_memory() for a in arrays)
+    w.run_steps_e2e(h_arrays, W)
+    barrier(world); flush_l2(); barrier(world)
+    wall0 = time.perf_counter()
+    _, h2d, d2h = w.run_steps_e2e(tuple(h[W * w.batch:] for h in h_arrays), K)
     torch.cuda.synchronize()
-    g = float(np.mean([x.elapsed_time(y) for x, y in tg])) * 1e-3
-    o = float(np.mean([x.elapsed_time(y) for x, y in to])) * 1e-3
-    return {"mf_pairwise_grad_kernel": g, "opt_apply_kernel": o}
+    e2e_s = max_over_ranks(time.perf_counter() - wall0, world)
+    windows.append((wall0, time.perf_counter()))
+    barrier(world)
+    e2e_value = world * K * w.batch / e2e_s
+
+    # ---- evaluator: users sharded over ranks
+    nu = w.d["num_users"]
+    n_eval = nu if w.eval_tables() is not None else min(nu, 943)
+    from neurec_b200.evaluator import sharded
+    a_, b_ = sharded.local_slice(n_eval, rank, world)
+    mine = torch.arange(a_, b_, dtype=torch.int32, device="cuda")
+    eval_once(w, mine)
+    barrier(world); flush_l2(); barrier(world)
+    reps = 3
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    a.record()
+    for _ in range(reps):
+        eval_once(w, mine)
+    b.record()
+    barrier(world)
+    windows.append((wall0, time.perf_counter()))
+    eval_ms = max_over_ranks(a.elapsed_time(b), world) / reps
+
+    if rank != 0:
+        return None
+    # ---- roofline: each kernel alone, graph-replayed, CUDA events
+    kt, kb, kn = {}, {}, {}
+    for name, (fn, nbytes, note) in w.kernels(arrays).items():
+        kt[name] = graph_time(fn)
+        kb[name], kn[name] = nbytes, note
+    dom = max(kt, key=lambda k: kt[k])
+    peak, peak_src = measured_peaks()
+    achieved = kb[dom] / kt[dom] / 1e9
+    out = {
+        "metric": "triplets/sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32",
+        "data": "%s (%s), random-init tables, device Philox negatives" % (
+            w.d["name"], "the reference's ratio-0.8 split, tests/golden/ml100k_split.npz"
+            if w.d["name"] == "ml-100k" else "synthetic, seed 7"),
+        "config": {"workload": w.describe, "global_batch": w.batch * world,
+                   "optimizer": "adam (TensorFlow-1.12 semantics: dense over every table each step)",
+                   "parallelism": "replicas x%d (training does not shard at this size); evaluator: users "
+                                  "sharded over ranks" % world,
+                   "l2": "flushed (256 MiB write) before each timed region; the K dependent steps then run "
+                         "back-to-back as in training (model + optimizer state are L2-sized)"},
+        "e2e": {"value": e2e_value, "unit": "triplets/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3 / K},
+        "gpu_launches": launches,
+        "eval": {"metric": "eval users/sec", "value": n_eval / (eval_ms * 1e-3), "unit": "users/s",
+                 "users": n_eval,
+                 "items": w.d["num_items"], "top_k": w.eval_k, "metrics": 5, "ms": eval_ms,
+                 "sharding": "users over %d rank(s)" % world},
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": kb[dom], "bytes_note": kn[dom], "launch_us": kt[dom] * 1e6,
+                     "all_kernels": {k: {"us": kt[k] * 1e6, "bytes": kb[k], "GBps": kb[k] / kt[k] / 1e9}
+                                     for k in kt},
+                     "timing": "each kernel alone: 40 launches in a CUDA graph, CUDA events on the replay "
+                               "stream, best of 5"},
+    }
+    if with_cpu:
+        threads = os.cpu_count() or 1
+        n_cpu = min(w.steps_per_epoch, 40 if w.name == "lightgcn-gowalla" else 2000)
+        dt, skind = w.cpu_reference(n_cpu)
+        out["cpu_baseline"] = {"value": n_cpu * w.batch / dt, "unit": "triplets/s", "cores": threads,
+                               "kind": "port",
+                               "sample": "%d steps of %d: reference sampler/batching (%s random_choice) + numpy/"
+                                         "scipy restatement of the TF-1.12 step (TensorFlow is not installable "
+                                         "offline); numpy elementwise work is single-threaded" % (n_cpu, w.batch, skind)}
+        tabs = w.cpu_tables() if hasattr(w, "cpu_tables") else (None, None)
+        dte, n_users_cpu, eimpl, eth = w.cpu_eval(threads, tabs[0], tabs[1],
+                                                  max_users=3000 if w.name == "lightgcn-gowalla" else None)
+        out["eval"]["cpu"] = {"value": n_users_cpu / dte, "unit": "users/s",
+                              "kind": "reference" if eimpl == "reference" else "port", "threads": eth,
+                              "sample": "%d users: predict + python mask loop + evaluate.h top-K/metrics, "
+                                        "test_batch_size 128" % n_users_cpu}
+    return out
 
 
 def run_ours(args):
     import torch
-    rank, world, local = dist_setup(args.gpus)
-    w = make_workload(args.workload, rank)
-    w.setup_device()
+    rank, world, local = dist_setup()
     K, W = args.steps, max(args.warmup, 3)
     clocks = ClockSampler(local)
     clocks.start()
-
-    users, pos, neg = w.device_epoch_arrays(K + W, epoch=0)
-    # ---- value: device-resident steps -------------------------------------------------
-    w.run_steps_device(users, pos, neg, W)
-    barrier(world)
-    flush_l2()
-    barrier(world)
-    t_wall0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    o = W * w.batch
-    e0.record()
-    _, launches = w.run_steps_device(users[o:], pos[o:], neg[o:], K)
-    e1.record()
-    barrier(world)
-    t_wall1 = time.perf_counter()
-    ms = max_over_ranks(e0.elapsed_time(e1), world)
-    value = world * K * w.batch / (ms * 1e-3)
-
-    # ---- e2e: per-step host buffers ---------------------------------------------------
-    h_users, h_pos, h_neg = (t.cpu().pin_memory() for t in (users, pos, neg))
-    w.run_steps_e2e(h_users, h_pos, h_neg, W)
-    barrier(world)
-    flush_l2()
-    barrier(world)
-    t0 = time.perf_counter()
-    _, h2d, d2h = w.run_steps_e2e(h_users[o:], h_pos[o:], h_neg[o:], K)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
-    barrier(world)
-    e2e_value = world * K * w.batch / e2e_s
-
-    # ---- evaluator: users sharded over ranks -------------------------------------------
-    nu = w.d["num_users"]
-    mine = torch.arange(rank, nu, world, dtype=torch.int32, device="cuda")
-    w.run_eval(mine)
-    barrier(world)
-    flush_l2()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    a.record()
-    for _ in range(reps):
-        w.run_eval(mine)
-    b.record()
-    barrier(world)
-    eval_ms = max_over_ranks(a.elapsed_time(b), world) / reps
+    windows = []
+    out = measure(make_workload(args.workload, rank), K, W, world, rank, windows)
+    if world == 1 and not args.only:
+        others = {}
+        for name in WORKLOADS:
+            if name == args.workload:
+                continue
+            k = min(K, 200) if name == "lightgcn-gowalla" else K
+            try:
+                o = measure(make_workload(name, rank), k, W, world, rank, windows)
+                others[name] = {x: o[x] for x in ("value", "unit", "steps", "ms_per_step", "e2e", "eval",
+                                                  "roofline", "cpu_baseline", "config", "gpu_launches")}
+            except Exception as ex:  # keep the headline line even if a secondary workload fails
+                others[name] = {"error": repr(ex)}
+        out["others"] = others
     clocks.stop()
-
-    out = None
     if rank == 0:
-        kt = time_dominant_kernels(w, users, pos, neg, min(K, 64))
-        ab = w.algorithmic_bytes()
-        dom = max(kt, key=lambda k: kt[k])
-        peak, peak_src = measured_peaks()
-        achieved = ab[dom] / kt[dom] / 1e9
-        # CPU baseline on a bounded sample
-        threads = os.cpu_count() or 1
-        n_cpu = min(w.steps_per_epoch, 157)
-        dt, skind = w.cpu_reference(n_cpu, threads)
-        cpu_value = n_cpu * w.batch / dt
-        dte, n_eval_users, eimpl = w.cpu_eval(threads)
-        out = {
-            "metric": "triplets/sec", "value": value, "unit": "triplets/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "ml-100k ratio-0.8 split of the reference (tests/golden/ml100k_split.npz), "
-                    "normal(0,0.01) random-init tables, device Philox negatives",
-            "config": {"workload": w.describe, "global_batch": w.batch * world, "dim": w.dim,
-                       "optimizer": "adam (TF-1.12 dense-over-table semantics)",
-                       "parallelism": "replicas x%d (training does not shard at this size)" % world,
-                       "l2": "flushed (256 MiB write) before the timed region; the K dependent "
-                             "steps then run back-to-back as in training (working set 2.7 MB)"},
-            "e2e": {"value": e2e_value, "unit": "triplets/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3 / K},
-            "gpu_launches": launches,
-            "eval": {"metric": "eval users/sec", "value": nu / (eval_ms * 1e-3), "unit": "users/s",
-                     "users": nu, "items": w.d["num_items"], "top_k": 20, "metrics": 5,
-                     "ms": eval_ms, "sharding": "users over %d rank(s)" % world,
-                     "cpu": {"value": n_eval_users / dte, "unit": "users/s", "kind":
-                             "reference" if eimpl == "reference" else "port",
-                             "what": "np.matmul predict + python mask loop + evaluate.h top-K/metrics, "
-                                     "test_batch_size 128, %d threads" % threads}},
-            "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "bytes_per_launch": ab[dom],
-                         "launch_us": kt[dom] * 1e6,
-                         "all_kernels_us": {k: v * 1e6 for k, v in kt.items()},
-                         "note": "tables (2.7 MB with Adam state) are L2-resident: the honest bound "
-                                 "here is launch latency, not HBM"},
-            "cpu_baseline": {"value": cpu_value, "unit": "triplets/s", "cores": threads,
-                             "kind": "port", "sample": "%d steps of %d (one ml-100k epoch): reference "
-                             "sampler (%s random_choice) + numpy restatement of the TF-1.12 BPR/Adam "
-                             "step" % (n_cpu, w.batch, skind)},
-            "clocks": clocks.summary(t_wall0, t_wall1),
-        }
+        out["clocks"] = clocks.summary(windows)
     barrier(world)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
-    if out is not None:
+    if rank == 0:
         print(json.dumps(out))
 
 
 def run_reference(args):
     """The reference's own CPU path on this box's host cores (rank 0 only)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     w = make_workload(args.workload, 0)
     threads = os.cpu_count() or 1
-    K, W = args.steps, args.warmup
-    # bounded sample made of WHOLE epochs (the reference draws an epoch's negatives up front,
-    # so a partial epoch would overcharge it): 1..3 epochs of steps_per_epoch batches
+    # bounded sample made of whole epochs where an epoch is short (the reference draws an epoch's
+    # negatives up front, so a partial epoch would overcharge it)
     spe = w.steps_per_epoch
-    n = spe * min(max(K // spe, 1), 3)
-    w.cpu_reference(min(W, 20), threads)
-    dt, skind = w.cpu_reference(n, threads)
+    if w.name == "lightgcn-gowalla":
+        n = min(max(args.steps, 10), 60)
+    else:
+        n = spe * min(max(args.steps // spe, 1), 2)
+    w.cpu_reference(min(max(args.warmup, 1), 20))
+    dt, skind = w.cpu_reference(n)
     value = n * w.batch / dt
     out = {"impl": "reference", "metric": "triplets/sec", "value": value, "unit": "triplets/s",
-           "n_gpus": args.gpus, "steps": n, "warmup": W, "ms_per_step": dt * 1e3 / n,
+           "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": dt * 1e3 / n,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "ml-100k ratio-0.8 split of the reference, same init tables",
+           "data": "%s, same init tables as the GPU arm" % w.d["name"],
            "config": {"workload": w.describe, "global_batch": w.batch},
            "cpu_baseline": {"value": value, "unit": "triplets/s", "cores": threads, "kind": "port",
-                            "sample": "%d steps: reference sampler (%s random_choice) + numpy "
-                                      "restatement of the TF-1.12 step (TensorFlow 1.12 is not "
-                                      "installable offline)" % (n, skind)},
-           "e2e": {"value": value, "unit": "triplets/s", "h2d_bytes_per_step": 0,
-                   "d2h_bytes_per_step": 0}}
+                            "sample": "%d steps: reference sampler/batching (%s random_choice) + numpy/scipy "
+                                      "restatement of the TF-1.12 step (TensorFlow 1.12 is not installable "
+                                      "offline)" % (n, skind)},
+           "e2e": {"value": value, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=157)
+    ap.add_argument("--steps", type=int, default=1570)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=WORKLOADS)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--only", action="store_true", help="measure only --workload (used under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

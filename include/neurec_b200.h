@@ -55,6 +55,15 @@ extern "C" {
 int nrc_version(void);
 const char* nrc_last_error(void);
 
+/* Host <-> device staging of ONE training batch, the analogue of feed_dict / fetches around a
+ * sess.run (MF.py:97-101): copy the three host id / label arrays (batch elements of 4 bytes
+ * each; pinned memory recommended) to staging[0:batch], [batch:2*batch], [2*batch:3*batch]
+ * asynchronously on `stream`; nrc_fetch_host copies `count` floats back and synchronises the
+ * stream so the values are valid on return. */
+int nrc_stage_batch_host(const void* a_host, const void* b_host, const void* c_host,
+                         int64_t batch, void* staging, void* stream);
+int nrc_fetch_host(const float* src_dev, float* dst_host, int64_t count, void* stream);
+
 /* ======================================================================================
  * Evaluator
  * ==================================================================================== */

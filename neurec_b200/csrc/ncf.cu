@@ -356,12 +356,16 @@ static int ncf_launch_grad(const nrc_ncf_shape* shape, const NcfPtrs& P, const i
     int64_t groups = (batch + kNcfWarps - 1) / kNcfWarps;
     int64_t cap = (int64_t)sm_count() * 2;
     const int grid = (int)(groups < cap ? groups : cap);
-    if (S.n_towers == 2 && pairwise) {
+    static bool attr_done = false;  // not inside a stream capture: set once, on first use
+    if (!attr_done) {
         NRC_CUDA_CHECK(cudaFuncSetAttribute(ncf_grad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(ncf_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    if (S.n_towers == 2 && pairwise) {
         ncf_grad_kernel<2><<<grid, kNcfWarps * 32, smem, st>>>(S, P, users, items, third, batch, pairwise,
                                                               loss_kind, reg_mf, reg_mlp, stamp, loss);
     } else {
-        NRC_CUDA_CHECK(cudaFuncSetAttribute(ncf_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         ncf_grad_kernel<1><<<grid, kNcfWarps * 32, smem, st>>>(S, P, users, items, third, batch, pairwise,
                                                               loss_kind, reg_mf, reg_mlp, stamp, loss);
     }
