@@ -66,7 +66,7 @@ def synth_gowalla(seed=7):
     nu, ni = 29858, 40981
     deg = np.clip((8 + rs.pareto(1.35, nu) * 9).astype(np.int64), 8, 811)
     deg = (deg * (810128 / deg.sum())).astype(np.int64).clip(6, 811)
-    pop = 1.0 / np.power(np.arange(1, ni + 1), 0.75)
+    pop = 1.0 / np.power(np.arange(1, ni + 1) + 50.0, 0.75)   # head capped like gowalla (max item degree ~1.4 k)
     pop = pop[rs.permutation(ni)]
     pop /= pop.sum()
     tot = int((deg * 1.45).sum())

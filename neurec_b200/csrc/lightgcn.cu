@@ -78,16 +78,32 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs A) {
             const int cnt = (int)((end - p < 32) ? (end - p) : 32);
             const int my_c = (lane < cnt) ? __ldg(A.indices + p + lane) : 0;
             const float my_v = (lane < cnt) ? __ldg(A.values + p + lane) : 0.0f;
-#pragma unroll 4
-            for (int q = 0; q < cnt; ++q) {
-                const int c = __shfl_sync(kFull, my_c, q);
-                const float v = __shfl_sync(kFull, my_v, q);
-                if constexpr (V != 0) {
-                    float x[V];
-                    vload(x, A.X + (size_t)c * A.dim + lane * V);
+            if constexpr (V != 0) {
+                // kDepth gathered rows in flight per warp, then the sequential (order-preserving)
+                // accumulation; padding lanes carry c = 0 (a valid row) and are skipped in the sum
+                constexpr int kDepth = (V == 4) ? 8 : 16;
+#pragma unroll 1
+                for (int q0 = 0; q0 < cnt; q0 += kDepth) {
+                    float x[kDepth][V];
 #pragma unroll
-                    for (int j = 0; j < V; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(v, x[j]));
-                } else {
+                    for (int j = 0; j < kDepth; ++j) {
+                        const int c = __shfl_sync(kFull, my_c, (q0 + j) & 31);
+                        vload(x[j], A.X + (size_t)c * A.dim + lane * V);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kDepth; ++j) {
+                        const float v = __shfl_sync(kFull, my_v, (q0 + j) & 31);
+                        if (q0 + j < cnt) {
+#pragma unroll
+                            for (int t = 0; t < V; ++t) acc[t] = __fadd_rn(acc[t], __fmul_rn(v, x[j][t]));
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 4
+                for (int q = 0; q < cnt; ++q) {
+                    const int c = __shfl_sync(kFull, my_c, q);
+                    const float v = __shfl_sync(kFull, my_v, q);
 #pragma unroll
                     for (int j = 0; j < VV; ++j) {
                         const int col = lane + 32 * j;

@@ -88,11 +88,38 @@ __device__ __forceinline__ float ncf_tower_forward(const NcfDev& S, const float*
         const float* B = sW + S.sb_off[l];
         const float* a = act + S.a_off[l];
         float* o = act + S.a_off[l + 1];
-        for (int j = lane; j < out; j += kWarp) {
-            float acc = B[j];
-            for (int k = 0; k < in; ++k) acc = fmaf(a[k], W[k * (out + 1) + j], acc);
-            o[j] = fmaxf(acc, 0.0f);  // tf.nn.relu
+        // lane owns outputs lane, lane+32, ... (<= 8): one broadcast read of a[k] feeds up to 8
+        // independent FMA chains
+        float acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = (lane + 32 * r < out) ? B[lane + 32 * r] : 0.0f;
+        const int nr = (out + 31) >> 5;
+        if (nr == 1) {
+            const bool ok = lane < out;
+            const float* w = W + (ok ? lane : 0);
+#pragma unroll 8
+            for (int k = 0; k < in; ++k) acc[0] = fmaf(a[k], w[k * (out + 1)], acc[0]);
+        } else if (nr == 2) {
+            const bool ok1 = lane + 32 < out;
+            const float* w0 = W + lane;
+            const float* w1 = W + (ok1 ? lane + 32 : lane);
+#pragma unroll 8
+            for (int k = 0; k < in; ++k) {
+                const float ak = a[k];
+                acc[0] = fmaf(ak, w0[k * (out + 1)], acc[0]);
+                acc[1] = fmaf(ak, w1[k * (out + 1)], acc[1]);
+            }
+        } else {
+            for (int k = 0; k < in; ++k) {
+                const float ak = a[k];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (lane + 32 * r < out) acc[r] = fmaf(ak, W[k * (out + 1) + lane + 32 * r], acc[r]);
+            }
         }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (lane + 32 * r < out) o[lane + 32 * r] = fmaxf(acc[r], 0.0f);  // tf.nn.relu
         __syncwarp();
     }
     float s = 0.0f;
@@ -121,10 +148,27 @@ __device__ __forceinline__ void ncf_tower_backward(const NcfDev& S, const float*
         const float* d = del + S.a_off[l + 1];
         const float* a = act + S.a_off[l];
         float* dp = del + S.a_off[l];
-        for (int k = lane; k < in; k += kWarp) {
-            float s = 0.0f;
-            for (int j = 0; j < out; ++j) s = fmaf(W[k * (out + 1) + j], d[j], s);
-            dp[k] = (l > 0) ? ((a[k] > 0.0f) ? s : 0.0f) : s;
+        // lane owns input rows lane, lane+32, ... : one broadcast read of d[j] feeds them all
+        const int nr = (in + 31) >> 5;
+        if (nr <= 2) {
+            const bool ok1 = lane + 32 < in;
+            const float* w0 = W + (size_t)((lane < in) ? lane : 0) * (out + 1);
+            const float* w1 = W + (size_t)(ok1 ? lane + 32 : 0) * (out + 1);
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll 8
+            for (int j = 0; j < out; ++j) {
+                const float dj = d[j];
+                s0 = fmaf(w0[j], dj, s0);
+                s1 = fmaf(w1[j], dj, s1);
+            }
+            if (lane < in) dp[lane] = (l > 0) ? ((a[lane] > 0.0f) ? s0 : 0.0f) : s0;
+            if (ok1) dp[lane + 32] = (l > 0) ? ((a[lane + 32] > 0.0f) ? s1 : 0.0f) : s1;
+        } else {
+            for (int k = lane; k < in; k += kWarp) {
+                float s = 0.0f;
+                for (int j = 0; j < out; ++j) s = fmaf(W[k * (out + 1) + j], d[j], s);
+                dp[k] = (l > 0) ? ((a[k] > 0.0f) ? s : 0.0f) : s;
+            }
         }
         __syncwarp();
     }
@@ -150,10 +194,10 @@ ncf_grad_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ use
             const int in = S.in_dim[l], out = S.out_dim[l];
             const float* gW = P.dense + (size_t)t * S.tower_size + S.w_off[l];
             float* dW = sW + t * S.s_tower_size + S.sw_off[l];
-            for (int e = tid; e < in * out; e += blockDim.x) {
-                const int k = e / out, j = e - k * out;
-                dW[k * (out + 1) + j] = gW[e];
-            }
+            // warp w copies rows w, w+8, ...: coalesced, no integer division, loads pipeline
+#pragma unroll 4
+            for (int k = warp; k < in; k += kNcfWarps)
+                for (int j = lane; j < out; j += kWarp) dW[k * (out + 1) + j] = __ldg(gW + k * out + j);
             const float* gB = P.dense + (size_t)t * S.tower_size + S.b_off[l];
             float* dB = sW + t * S.s_tower_size + S.sb_off[l];
             for (int e = tid; e < out; e += blockDim.x) dB[e] = gB[e];
@@ -309,10 +353,10 @@ ncf_scores_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ u
     float* sAct = sW + S.s_tower_size;
     for (int l = 0; l < S.n_layers; ++l) {
         const int in = S.in_dim[l], out = S.out_dim[l];
-        for (int e = tid; e < in * out; e += blockDim.x) {
-            const int k = e / out, j = e - k * out;
-            sW[S.sw_off[l] + k * (out + 1) + j] = P.dense[S.w_off[l] + e];
-        }
+#pragma unroll 4
+        for (int k = warp; k < in; k += kNcfWarps)
+            for (int j = lane; j < out; j += kWarp)
+                sW[S.sw_off[l] + k * (out + 1) + j] = __ldg(P.dense + S.w_off[l] + k * out + j);
         for (int e = tid; e < out; e += blockDim.x) sW[S.sb_off[l] + e] = P.dense[S.b_off[l] + e];
     }
     __syncthreads();
