@@ -313,13 +313,56 @@ class Workload:
                                               ctypes.c_void_p(self.loss_pin.data_ptr()), count, st))
         return float(self.loss_pin[0])
 
+    def build_step_graph(self):
+        """Capture ONE training step (H2D of the pinned batch block, the step's kernels, D2H of the
+        loss) into a CUDA graph: the per-batch host cost becomes one cudaGraphLaunch + one sync."""
+        import torch
+        from neurec_b200 import _lib
+        lib = _lib.load()
+        b = self.batch
+        self.e2e_stream = torch.cuda.Stream()
+        self.pin = torch.zeros(3 * b + 4, dtype=torch.int32).pin_memory()
+        self.graph = ctypes.c_void_p()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(self.e2e_stream):
+            st = ctypes.c_void_p(self.e2e_stream.cuda_stream)
+            vp = ctypes.c_void_p
+            _lib.check(lib.nrc_graph_capture_begin(st))
+            _lib.check(lib.nrc_graph_stage_async(vp(self.pin.data_ptr()), vp(self.staging.data_ptr()),
+                                                 (3 * b + 1) * 4, st))
+            _lib.check(lib.nrc_opt_set_lr_source(vp(self.staging.data_ptr() + 12 * b)))
+            third = self.staging[2 * b:3 * b]
+            if not self.pairwise:
+                third = third.view(torch.float32)
+            t_keep = self.t
+            self.step_on_staged(self.staging[:b], self.staging[b:2 * b], third)
+            self.t = t_keep
+            _lib.check(lib.nrc_opt_set_lr_source(None))
+            _lib.check(lib.nrc_graph_fetch_async(vp(self.step_loss.data_ptr()), vp(self.loss_pin.data_ptr()),
+                                                 self.loss_count, st))
+            _lib.check(lib.nrc_graph_capture_end(st, ctypes.byref(self.graph)))
+        torch.cuda.synchronize()
+
     def run_steps_e2e(self, h_arrays, n_steps):
-        total = 0.0
+        """Per batch: host arrays -> pinned block -> graph launch (H2D, kernels, loss D2H) -> sync."""
+        from neurec_b200 import _lib
+        lib = _lib.load()
+        if not hasattr(self, "graph"):
+            self.build_step_graph()
+        st = ctypes.c_void_p(self.e2e_stream.cuda_stream)
+        pin = ctypes.c_void_p(self.pin.data_ptr())
+        ptrs = [h.data_ptr() for h in h_arrays]
+        loss_np = self.loss_pin.numpy()
+        total, b = 0.0, self.batch
         for s in range(n_steps):
-            u, i, t = self.stage(h_arrays, s * self.batch)
-            loss = self.step_on_staged(u, i, t)
-            total += self.fetch(loss, self.loss_count)
-        return total, 3 * 4 * self.batch, 4 * self.loss_count
+            o = 4 * s * b
+            rc = lib.nrc_graph_step(self.graph, ctypes.c_void_p(ptrs[0] + o), ctypes.c_void_p(ptrs[1] + o),
+                                    ctypes.c_void_p(ptrs[2] + o), b, float(self.lr_sched[self.t]), pin, st)
+            if rc:
+                _lib.check(rc)
+            self.t += 1
+            total += float(loss_np[0])
+        return total, 3 * 4 * self.batch + 4, 4 * self.loss_count
 
     def cpu_eval(self, threads, U, V, max_users=None):
         from oracle import ref_port
@@ -425,7 +468,7 @@ class NeumfMl100k(Workload):
     mf_dim, layers, batch, lr, loss, opt = 32, [64, 32, 16], 256, 1e-3, "cross_entropy", "adam"
     hyper = [1e-3, 0.9, 0.999, 1e-8]
     loss_count = 1
-    launches_per_step = 2
+    launches_per_step = 3
     KEYS = ("mf_user", "mf_item", "mlp_user", "mlp_item", "dense")
 
     def __init__(self, rank=0):
@@ -493,7 +536,7 @@ class NeumfMl100k(Workload):
                                                  self.S1["dense"], None, True)]
         opt = lambda: ops.opt_apply_multi(self.opt, variables, 7, list(self.hyper))
         n_par = sum(v.numel() for v in self.P.values())
-        return {"ncf_grad_kernel": (grad, self.batch * (4 * 32 * 4 * 2 + 12) + self.P["dense"].numel() * 4 * 2,
+        return {"ncf_sample_kernel+ncf_wgrad_kernel": (grad, self.batch * (4 * 32 * 4 * 2 + 12) + self.P["dense"].numel() * 4 * 2,
                                     "256 samples x (4 rows of 32 f32 gathered + their gradients + ids) + "
                                     "dense weights read + their gradient written"),
                 "opt_apply_kernel": (opt, n_par * 4 * 3 * 2,

@@ -64,6 +64,26 @@ int nrc_stage_batch_host(const void* a_host, const void* b_host, const void* c_h
                          int64_t batch, void* staging, void* stream);
 int nrc_fetch_host(const float* src_dev, float* dst_host, int64_t count, void* stream);
 
+/* Captured training steps.  The reference pays one `sess.run` per batch; the lowest-overhead
+ * analogue here is ONE cudaGraphLaunch per batch.  Between nrc_graph_capture_begin and
+ * nrc_graph_capture_end every nrc_* device call issued on `stream` is recorded instead of run:
+ *   nrc_graph_stage_async   H2D of the pinned staging block (3*batch ids/labels + 1 float lr_t)
+ *   nrc_opt_set_lr_source   make the optimizer read lr / Adam's lr_t from that device float
+ *   nrc_*_train_epoch       with n = batch (one step)            [adam and gd only: the touched
+ *                            stamps are frozen in a graph; TF's adam/gd do not depend on them]
+ *   nrc_graph_fetch_async   D2H of the step's loss into pinned memory
+ * nrc_graph_step then copies one batch of HOST arrays into the pinned block, stores lr_t after
+ * them, launches the graph and synchronises the stream (loss valid on return). */
+typedef struct nrc_step_graph nrc_step_graph;
+int nrc_graph_capture_begin(void* stream);
+int nrc_graph_capture_end(void* stream, nrc_step_graph** out);
+int nrc_graph_stage_async(const void* pinned_host, void* staging_dev, int64_t nbytes, void* stream);
+int nrc_graph_fetch_async(const float* src_dev, float* pinned_host, int64_t count, void* stream);
+int nrc_graph_step(nrc_step_graph* g, const void* a_host, const void* b_host, const void* c_host,
+                   int64_t batch, float lr_t, void* pinned_stage, void* stream);
+int nrc_graph_destroy(nrc_step_graph* g);
+int nrc_opt_set_lr_source(const float* lr_dev);
+
 /* ======================================================================================
  * Evaluator
  * ==================================================================================== */

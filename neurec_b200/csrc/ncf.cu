@@ -13,27 +13,31 @@
 // so the two towers have DIFFERENT weights (NeuMF.py:81-82, 90-92; n_towers = 2); MLP.py shares
 // its Dense objects (n_towers = 1).
 //
-// Kernel shape.  CTA = 8 warps; one warp runs one sample's towers forward and backward with the
-// dense weights in shared memory (row stride out+1: conflict-free both by output column for the
-// forward pass and by input row for the backward pass).  Per-sample weight gradients are NOT
-// accumulated with atomics: every group of 8 samples leaves its activations and deltas in
-// shared memory and the 256 threads each own a fixed set of (k, j) weight-gradient entries in
-// REGISTERS, adding a_l[s][k] * delta_l[s][j] over the group; one RED.ADD per entry per CTA at
-// the end.  Embedding-row gradients go straight to the dense accumulators (duplicates sum).
+// Two kernels per step (the batch is tiny -- 256 samples x 6.7 k MACs -- so the design goal is
+// latency, i.e. as many SMs as possible and no serial tail):
+//   ncf_sample_kernel  one CTA (4 warps) per sample: gathers the embedding rows, runs the
+//                      tower(s) forward and backward with the dense weights read through L1
+//                      (27 KB, shared by every CTA on the SM), adds the embedding-row gradients
+//                      to the dense accumulators (duplicates sum) and leaves activations and
+//                      deltas of every layer in a scratch buffer;
+//   ncf_wgrad_kernel   dW_l = A_l^T . Delta_l and db_l = colsum(Delta_l) over the batch: one
+//                      thread per weight entry and batch slice, coalesced over the output
+//                      column, one RED.ADD per entry and slice.
 #include "common.cuh"
 #include "optim.cuh"
 
 namespace nrc {
 
 constexpr int kNcfMaxLayers = 4;
-constexpr int kNcfEntries = 16;   // weight-gradient entries per thread and layer
-constexpr int kNcfWarps = 8;
+constexpr int kNcfThreads = 128;   // threads per sample CTA
+constexpr int kNcfWarps = 8;       // warps per CTA of the score kernel
+constexpr int kWgradSlices = 4;    // batch slices of the weight-gradient kernel
 
 struct NcfDev {
     int mf_dim, mlp_dim, n_layers, n_towers;
     int in_dim[kNcfMaxLayers], out_dim[kNcfMaxLayers];
     int w_off[kNcfMaxLayers], b_off[kNcfMaxLayers];      // offsets in the packed dense buffer
-    int sw_off[kNcfMaxLayers], sb_off[kNcfMaxLayers];    // offsets in the padded smem copy
+    int sw_off[kNcfMaxLayers], sb_off[kNcfMaxLayers];    // offsets in the padded smem copy (scores)
     int a_off[kNcfMaxLayers + 1];                        // activation offsets (a_0 = input)
     int tower_size, s_tower_size, act_size;
 };
@@ -53,17 +57,20 @@ static int ncf_make(NcfDev& S, const nrc_ncf_shape* sh) {
     NRC_REQUIRE(sh->mf_dim >= 0 && sh->mlp_dim >= 0 && (sh->mf_dim > 0 || sh->n_layers > 0),
                 NRC_E_VALUE, "model has neither an MF nor an MLP part");
     NRC_REQUIRE(sh->n_layers == 0 || sh->mlp_dim > 0, NRC_E_VALUE, "mlp_dim must be > 0");
+    NRC_REQUIRE(sh->mlp_dim <= 256 && sh->mf_dim <= 1024, NRC_E_LIMIT, "embedding width too large");
     S.mf_dim = sh->mf_dim; S.mlp_dim = sh->n_layers ? sh->mlp_dim : 0;
     S.n_layers = sh->n_layers; S.n_towers = sh->n_towers;
     int in = 2 * S.mlp_dim, off = 0, soff = 0, aoff = 0;
     S.a_off[0] = 0; aoff = in;
     for (int l = 0; l < kNcfMaxLayers; ++l) {
-        if (l >= S.n_layers) { S.in_dim[l] = S.out_dim[l] = 0; S.w_off[l] = S.b_off[l] = S.sw_off[l] = S.sb_off[l] = 0; S.a_off[l + 1] = aoff; continue; }
+        if (l >= S.n_layers) {
+            S.in_dim[l] = S.out_dim[l] = 0;
+            S.w_off[l] = S.b_off[l] = S.sw_off[l] = S.sb_off[l] = 0;
+            S.a_off[l + 1] = aoff;
+            continue;
+        }
         const int out = sh->layers[l];
-        NRC_REQUIRE(out > 0 && out <= 256, NRC_E_LIMIT, "layer width %d outside [1, 256]", out);
-        const int stride = 256 / out;
-        NRC_REQUIRE((in + stride - 1) / stride <= kNcfEntries, NRC_E_LIMIT,
-                    "dense layer %d (%d -> %d) is too large for this build (in*out <= ~4096)", l, in, out);
+        NRC_REQUIRE(out > 0 && out <= 512, NRC_E_LIMIT, "layer width %d outside [1, 512]", out);
         S.in_dim[l] = in; S.out_dim[l] = out;
         S.w_off[l] = off; off += in * out; S.b_off[l] = off; off += out;
         S.sw_off[l] = soff; soff += in * (out + 1); S.sb_off[l] = soff; soff += out;
@@ -74,281 +81,181 @@ static int ncf_make(NcfDev& S, const nrc_ncf_shape* sh) {
     return NRC_OK;
 }
 
-static size_t ncf_smem_bytes(const NcfDev& S, int passes) {
-    // weights (all towers) + per-warp, per-pass activations and deltas
-    return ((size_t)S.n_towers * S.s_tower_size + (size_t)kNcfWarps * passes * 2 * S.act_size) * 4;
+__device__ __forceinline__ float block_sum_128(float v, float* red, int tid) {
+    v = warp_sum(v);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    const float r = red[0] + red[1] + red[2] + red[3];
+    __syncthreads();
+    return r;
 }
 
-// One tower forward for the warp's sample.  act: this pass' activation buffer (a_0 filled).
-__device__ __forceinline__ float ncf_tower_forward(const NcfDev& S, const float* sW, float* act,
-                                                   int lane) {
-    for (int l = 0; l < S.n_layers; ++l) {
-        const int in = S.in_dim[l], out = S.out_dim[l];
-        const float* W = sW + S.sw_off[l];
-        const float* B = sW + S.sb_off[l];
-        const float* a = act + S.a_off[l];
-        float* o = act + S.a_off[l + 1];
-        // lane owns outputs lane, lane+32, ... (<= 8): one broadcast read of a[k] feeds up to 8
-        // independent FMA chains
-        float acc[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = (lane + 32 * r < out) ? B[lane + 32 * r] : 0.0f;
-        const int nr = (out + 31) >> 5;
-        if (nr == 1) {
-            const bool ok = lane < out;
-            const float* w = W + (ok ? lane : 0);
-#pragma unroll 8
-            for (int k = 0; k < in; ++k) acc[0] = fmaf(a[k], w[k * (out + 1)], acc[0]);
-        } else if (nr == 2) {
-            const bool ok1 = lane + 32 < out;
-            const float* w0 = W + lane;
-            const float* w1 = W + (ok1 ? lane + 32 : lane);
-#pragma unroll 8
-            for (int k = 0; k < in; ++k) {
-                const float ak = a[k];
-                acc[0] = fmaf(ak, w0[k * (out + 1)], acc[0]);
-                acc[1] = fmaf(ak, w1[k * (out + 1)], acc[1]);
-            }
-        } else {
-            for (int k = 0; k < in; ++k) {
-                const float ak = a[k];
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if (lane + 32 * r < out) acc[r] = fmaf(ak, W[k * (out + 1) + lane + 32 * r], acc[r]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-            if (lane + 32 * r < out) o[lane + 32 * r] = fmaxf(acc[r], 0.0f);  // tf.nn.relu
-        __syncwarp();
-    }
-    float s = 0.0f;
-    if (S.n_layers > 0) {
-        const float* o = act + S.a_off[S.n_layers];
-        for (int j = lane; j < S.out_dim[S.n_layers - 1]; j += kWarp) s += o[j];
-    }
-    return warp_sum(s);
-}
-
-// Backward through one tower: fills delta buffers (same layout as act; delta of a_0 = gradient
-// w.r.t. the concatenated MLP embeddings).  g = dLoss/dPrediction of this pass.
-__device__ __forceinline__ void ncf_tower_backward(const NcfDev& S, const float* sW,
-                                                   const float* act, float* del, float g, int lane) {
-    if (S.n_layers == 0) return;
-    {
-        const int L = S.n_layers;
-        const float* o = act + S.a_off[L];
-        float* d = del + S.a_off[L];
-        for (int j = lane; j < S.out_dim[L - 1]; j += kWarp) d[j] = (o[j] > 0.0f) ? g : 0.0f;
-        __syncwarp();
-    }
-    for (int l = S.n_layers - 1; l >= 0; --l) {
-        const int in = S.in_dim[l], out = S.out_dim[l];
-        const float* W = sW + S.sw_off[l];
-        const float* d = del + S.a_off[l + 1];
-        const float* a = act + S.a_off[l];
-        float* dp = del + S.a_off[l];
-        // lane owns input rows lane, lane+32, ... : one broadcast read of d[j] feeds them all
-        const int nr = (in + 31) >> 5;
-        if (nr <= 2) {
-            const bool ok1 = lane + 32 < in;
-            const float* w0 = W + (size_t)((lane < in) ? lane : 0) * (out + 1);
-            const float* w1 = W + (size_t)(ok1 ? lane + 32 : 0) * (out + 1);
-            float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll 8
-            for (int j = 0; j < out; ++j) {
-                const float dj = d[j];
-                s0 = fmaf(w0[j], dj, s0);
-                s1 = fmaf(w1[j], dj, s1);
-            }
-            if (lane < in) dp[lane] = (l > 0) ? ((a[lane] > 0.0f) ? s0 : 0.0f) : s0;
-            if (ok1) dp[lane + 32] = (l > 0) ? ((a[lane + 32] > 0.0f) ? s1 : 0.0f) : s1;
-        } else {
-            for (int k = lane; k < in; k += kWarp) {
-                float s = 0.0f;
-                for (int j = 0; j < out; ++j) s = fmaf(W[k * (out + 1) + j], d[j], s);
-                dp[k] = (l > 0) ? ((a[k] > 0.0f) ? s : 0.0f) : s;
-            }
-        }
-        __syncwarp();
-    }
-}
-
-// kind: 0 = pointwise (labels), 1 = pairwise.
-template <int NT>
-__global__ void __launch_bounds__(kNcfWarps * 32)
-ncf_grad_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ users,
-                const int32_t* __restrict__ items, const void* __restrict__ third, int64_t batch,
-                int pairwise, int loss_kind, float reg_mf, float reg_mlp, int32_t stamp,
-                float* __restrict__ loss) {
+// ----------------------------------------------------------------------------------------
+// per-sample forward + backward.  scratch layout per sample: [pass][act_size] activations then
+// [pass][act_size] deltas (delta of a_{l+1} = gradient w.r.t. layer l's pre-activation).
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNcfThreads)
+ncf_sample_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ users,
+                  const int32_t* __restrict__ items, const void* __restrict__ third, int64_t batch,
+                  int pairwise, int loss_kind, float reg_mf, float reg_mlp, int32_t stamp,
+                  float* __restrict__ scratch, float* __restrict__ loss) {
     extern __shared__ __align__(16) float sm[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const int passes = pairwise ? 2 : 1;
-    float* sW = sm;                                           // [n_towers][s_tower_size]
-    float* sAct = sW + S.n_towers * S.s_tower_size;           // [warp][pass][act_size]
-    float* sDel = sAct + kNcfWarps * passes * S.act_size;     // [warp][pass][act_size]
+    float* sAct = sm;                                // [passes][act_size]
+    float* sDel = sAct + passes * S.act_size;        // [passes][act_size]
+    float* red = sDel + passes * S.act_size;         // [8]
+    const int64_t b = blockIdx.x;
+    const int u = users[b];
+    const int it[2] = {items[b], pairwise ? reinterpret_cast<const int32_t*>(third)[b] : 0};
 
-    // stage dense weights with the padded row stride
-    for (int t = 0; t < S.n_towers; ++t)
+    float yhat[2] = {0.0f, 0.0f};
+    for (int p = 0; p < passes; ++p) {
+        float* act = sAct + p * S.act_size;
+        float mf = 0.0f;
+        for (int k = tid; k < S.mf_dim; k += kNcfThreads)
+            mf = fmaf(P.mf_user[(size_t)u * S.mf_dim + k], P.mf_item[(size_t)it[p] * S.mf_dim + k], mf);
+        for (int k = tid; k < S.mlp_dim; k += kNcfThreads) {
+            act[k] = P.mlp_user[(size_t)u * S.mlp_dim + k];
+            act[S.mlp_dim + k] = P.mlp_item[(size_t)it[p] * S.mlp_dim + k];
+        }
+        __syncthreads();
+        const float* tw = P.dense + (size_t)((p == 1 && S.n_towers == 2) ? 1 : 0) * S.tower_size;
         for (int l = 0; l < S.n_layers; ++l) {
             const int in = S.in_dim[l], out = S.out_dim[l];
-            const float* gW = P.dense + (size_t)t * S.tower_size + S.w_off[l];
-            float* dW = sW + t * S.s_tower_size + S.sw_off[l];
-            // warp w copies rows w, w+8, ...: coalesced, no integer division, loads pipeline
-#pragma unroll 4
-            for (int k = warp; k < in; k += kNcfWarps)
-                for (int j = lane; j < out; j += kWarp) dW[k * (out + 1) + j] = __ldg(gW + k * out + j);
-            const float* gB = P.dense + (size_t)t * S.tower_size + S.b_off[l];
-            float* dB = sW + t * S.s_tower_size + S.sb_off[l];
-            for (int e = tid; e < out; e += blockDim.x) dB[e] = gB[e];
-        }
-    __syncthreads();
-
-    float accW[NT][kNcfMaxLayers][kNcfEntries];
-    float accB[NT][kNcfMaxLayers];
-#pragma unroll
-    for (int t = 0; t < NT; ++t)
-#pragma unroll
-        for (int l = 0; l < kNcfMaxLayers; ++l) {
-            accB[t][l] = 0.0f;
-#pragma unroll
-            for (int m = 0; m < kNcfEntries; ++m) accW[t][l][m] = 0.0f;
-        }
-
-    const float inv_b = 1.0f / (float)batch;
-    float loss_acc = 0.0f;
-    const int64_t n_groups = (batch + kNcfWarps - 1) / kNcfWarps;
-    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int64_t b = grp * kNcfWarps + warp;
-        const bool live = b < batch;
-        float* act0 = sAct + (warp * passes) * S.act_size;
-        float* del0 = sDel + (warp * passes) * S.act_size;
-        if (live) {
-            const int u = users[b];
-            const int it[2] = {items[b], pairwise ? reinterpret_cast<const int32_t*>(third)[b] : 0};
-            float yhat[2] = {0.0f, 0.0f};
-            for (int p = 0; p < passes; ++p) {
-                float* act = act0 + p * S.act_size;
-                float mf = 0.0f;
-                for (int k = lane; k < S.mf_dim; k += kWarp)
-                    mf = fmaf(P.mf_user[(size_t)u * S.mf_dim + k], P.mf_item[(size_t)it[p] * S.mf_dim + k], mf);
-                mf = warp_sum(mf);
-                for (int k = lane; k < S.mlp_dim; k += kWarp) {
-                    act[k] = P.mlp_user[(size_t)u * S.mlp_dim + k];
-                    act[S.mlp_dim + k] = P.mlp_item[(size_t)it[p] * S.mlp_dim + k];
-                }
-                __syncwarp();
-                const int tower = (p == 1 && S.n_towers == 2) ? 1 : 0;
-                yhat[p] = mf + ncf_tower_forward(S, sW + tower * S.s_tower_size, act, lane);
+            const float* __restrict__ W = tw + S.w_off[l];
+            const float* a = act + S.a_off[l];
+            float* o = act + S.a_off[l + 1];
+            for (int j = tid; j < out; j += kNcfThreads) {
+                float acc = __ldg(tw + S.b_off[l] + j);
+#pragma unroll 8
+                for (int k = 0; k < in; ++k) acc = fmaf(a[k], __ldg(W + k * out + j), acc);
+                o[j] = fmaxf(acc, 0.0f);  // tf.nn.relu
             }
-            float l, g;
-            if (pairwise) {
-                const float x = yhat[0] - yhat[1];  // NeuMF.py:92 result = output - output_neg
-                if (loss_kind == NRC_LOSS_BPR) { l = (x >= 0.f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x))); g = -1.0f / (1.0f + expf(x)); }
-                else if (loss_kind == NRC_LOSS_HINGE) { const float t = x + 1.0f; l = fmaxf(t, 0.f); g = (t > 0.f) ? 1.f : 0.f; }
-                else { const float t = 1.0f - x; l = t * t; g = -2.0f * t; }
-            } else {
-                const float x = yhat[0], z = reinterpret_cast<const float*>(third)[b];
-                if (loss_kind == NRC_LOSS_CROSS_ENTROPY) {
-                    const float e = expf(-fabsf(x));
-                    l = (fmaxf(x, 0.f) - x * z + log1pf(e)) * inv_b;
-                    const float s = (x >= 0.f) ? 1.f / (1.f + e) : e / (1.f + e);
-                    g = (s - z) * inv_b;
-                } else { const float t = z - x; l = t * t; g = -2.0f * t; }
-            }
-            // regularisers (NeuMF.py:94-100): reg_mf*l2(p1,q2,q1) + reg_mlp*l2(m1,n2,n1)
-            float sq_mf = 0.f, sq_mlp = 0.f;
-            for (int p = 0; p < passes; ++p) {
-                const float gp = (p == 0) ? g : -g;
-                const int tower = (p == 1 && S.n_towers == 2) ? 1 : 0;
-                float* act = act0 + p * S.act_size;
-                float* del = del0 + p * S.act_size;
-                ncf_tower_backward(S, sW + tower * S.s_tower_size, act, del, gp, lane);
-                for (int k = lane; k < S.mf_dim; k += kWarp) {
-                    const float pu = P.mf_user[(size_t)u * S.mf_dim + k];
-                    const float qi = P.mf_item[(size_t)it[p] * S.mf_dim + k];
-                    atomicAdd(P.g_mf_user + (size_t)u * S.mf_dim + k, gp * qi + (p == 0 ? reg_mf * pu : 0.f));
-                    atomicAdd(P.g_mf_item + (size_t)it[p] * S.mf_dim + k, gp * pu + reg_mf * qi);
-                    sq_mf += qi * qi + (p == 0 ? pu * pu : 0.f);
-                }
-                for (int k = lane; k < S.mlp_dim; k += kWarp) {
-                    const float mu = act[k], mi = act[S.mlp_dim + k];
-                    atomicAdd(P.g_mlp_user + (size_t)u * S.mlp_dim + k, del[k] + (p == 0 ? reg_mlp * mu : 0.f));
-                    atomicAdd(P.g_mlp_item + (size_t)it[p] * S.mlp_dim + k, del[S.mlp_dim + k] + reg_mlp * mi);
-                    sq_mlp += mi * mi + (p == 0 ? mu * mu : 0.f);
-                }
-                if (lane == 0) P.t_item[it[p]] = stamp;
-            }
-            if (lane == 0) P.t_user[u] = stamp;
-            if (reg_mf != 0.f) l += reg_mf * 0.5f * warp_sum(sq_mf);
-            if (reg_mlp != 0.f) l += reg_mlp * 0.5f * warp_sum(sq_mlp);
-            loss_acc += l;
-        } else {
-            // dead warp: zero its buffers so the group reduction below adds nothing
-            for (int e = lane; e < passes * S.act_size; e += kWarp) { del0[e] = 0.0f; act0[e] = 0.0f; }
+            __syncthreads();
         }
-        __syncthreads();
-        // weight / bias gradients of this group, accumulated in registers
-#pragma unroll
-        for (int l = 0; l < kNcfMaxLayers; ++l) {
-            if (l < S.n_layers) {
-                const int in = S.in_dim[l], out = S.out_dim[l];
-                const int stride = 256 / out;
-                const int j = tid % out, k0 = tid / out;
-                if (k0 < stride) {
-                    for (int w = 0; w < kNcfWarps; ++w)
-                        for (int p = 0; p < passes; ++p) {
-                            const int tower = (NT == 2 && p == 1) ? 1 : 0;
-                            const float* a = sAct + (w * passes + p) * S.act_size + S.a_off[l];
-                            const float dj = sDel[(w * passes + p) * S.act_size + S.a_off[l + 1] + j];
-#pragma unroll
-                            for (int m = 0; m < kNcfEntries; ++m) {
-                                const int k = k0 + m * stride;
-                                if (k < in) {
-                                    if (tower == 0) accW[0][l][m] = fmaf(a[k], dj, accW[0][l][m]);
-                                    else accW[NT - 1][l][m] = fmaf(a[k], dj, accW[NT - 1][l][m]);
-                                }
-                            }
-                            if (k0 == 0) {
-                                if (tower == 0) accB[0][l] += dj; else accB[NT - 1][l] += dj;
-                            }
-                        }
-                }
-            }
-        }
-        __syncthreads();
+        float s = 0.0f;
+        if (S.n_layers > 0)
+            for (int j = tid; j < S.out_dim[S.n_layers - 1]; j += kNcfThreads) s += act[S.a_off[S.n_layers] + j];
+        yhat[p] = block_sum_128(mf + s, red, tid);   // NeuMF.py:85 reduce_sum(concat(mf, mlp))
     }
-    // flush the register accumulators: one RED per owned entry
-#pragma unroll
-    for (int t = 0; t < NT; ++t)
-#pragma unroll
-        for (int l = 0; l < kNcfMaxLayers; ++l) {
-            if (l < S.n_layers) {
-                const int in = S.in_dim[l], out = S.out_dim[l];
-                const int stride = 256 / out;
-                const int j = tid % out, k0 = tid / out;
-                if (k0 < stride) {
-                    float* gW = P.g_dense + (size_t)t * S.tower_size + S.w_off[l];
-#pragma unroll
-                    for (int m = 0; m < kNcfEntries; ++m) {
-                        const int k = k0 + m * stride;
-                        if (k < in && accW[t][l][m] != 0.0f) atomicAdd(gW + k * out + j, accW[t][l][m]);
-                    }
-                    if (k0 == 0 && accB[t][l] != 0.0f)
-                        atomicAdd(P.g_dense + (size_t)t * S.tower_size + S.b_off[l] + j, accB[t][l]);
+
+    float l, g;
+    if (pairwise) {
+        const float x = yhat[0] - yhat[1];  // NeuMF.py:92 result = output - output_neg
+        if (loss_kind == NRC_LOSS_BPR) {
+            l = (x >= 0.f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
+            g = -1.0f / (1.0f + expf(x));
+        } else if (loss_kind == NRC_LOSS_HINGE) {
+            const float t = x + 1.0f; l = fmaxf(t, 0.f); g = (t > 0.f) ? 1.f : 0.f;
+        } else {
+            const float t = 1.0f - x; l = t * t; g = -2.0f * t;
+        }
+    } else {
+        const float x = yhat[0], z = reinterpret_cast<const float*>(third)[b];
+        if (loss_kind == NRC_LOSS_CROSS_ENTROPY) {
+            const float inv_b = 1.0f / (float)batch;
+            const float e = expf(-fabsf(x));
+            l = (fmaxf(x, 0.f) - x * z + log1pf(e)) * inv_b;
+            const float s = (x >= 0.f) ? 1.f / (1.f + e) : e / (1.f + e);
+            g = (s - z) * inv_b;
+        } else {
+            const float t = z - x; l = t * t; g = -2.0f * t;
+        }
+    }
+
+    float sq_mf = 0.f, sq_mlp = 0.f;
+    for (int p = 0; p < passes; ++p) {
+        const float gp = (p == 0) ? g : -g;
+        const float* tw = P.dense + (size_t)((p == 1 && S.n_towers == 2) ? 1 : 0) * S.tower_size;
+        float* act = sAct + p * S.act_size;
+        float* del = sDel + p * S.act_size;
+        if (S.n_layers > 0) {
+            const int L = S.n_layers;
+            for (int j = tid; j < S.out_dim[L - 1]; j += kNcfThreads)
+                del[S.a_off[L] + j] = (act[S.a_off[L] + j] > 0.0f) ? gp : 0.0f;
+            __syncthreads();
+            for (int l2 = L - 1; l2 >= 0; --l2) {
+                const int in = S.in_dim[l2], out = S.out_dim[l2];
+                const float* __restrict__ W = tw + S.w_off[l2];
+                const float* d = del + S.a_off[l2 + 1];
+                const float* a = act + S.a_off[l2];
+                float* dp = del + S.a_off[l2];
+                for (int k = tid; k < in; k += kNcfThreads) {
+                    const float* wr = W + (size_t)k * out;
+                    float s = 0.0f;
+#pragma unroll 8
+                    for (int j = 0; j < out; ++j) s = fmaf(__ldg(wr + j), d[j], s);
+                    dp[k] = (l2 > 0) ? ((a[k] > 0.0f) ? s : 0.0f) : s;
                 }
+                __syncthreads();
             }
         }
-    if (lane == 0 && loss && loss_acc != 0.0f) atomicAdd(loss, loss_acc);
+        // embedding-row gradients (IndexedSlices; duplicates sum) + regulariser terms
+        for (int k = tid; k < S.mf_dim; k += kNcfThreads) {
+            const float pu = P.mf_user[(size_t)u * S.mf_dim + k];
+            const float qi = P.mf_item[(size_t)it[p] * S.mf_dim + k];
+            atomicAdd(P.g_mf_user + (size_t)u * S.mf_dim + k, gp * qi + (p == 0 ? reg_mf * pu : 0.f));
+            atomicAdd(P.g_mf_item + (size_t)it[p] * S.mf_dim + k, gp * pu + reg_mf * qi);
+            sq_mf += qi * qi + (p == 0 ? pu * pu : 0.f);
+        }
+        for (int k = tid; k < S.mlp_dim; k += kNcfThreads) {
+            const float mu = act[k], mi = act[S.mlp_dim + k];
+            atomicAdd(P.g_mlp_user + (size_t)u * S.mlp_dim + k, del[k] + (p == 0 ? reg_mlp * mu : 0.f));
+            atomicAdd(P.g_mlp_item + (size_t)it[p] * S.mlp_dim + k, del[S.mlp_dim + k] + reg_mlp * mi);
+            sq_mlp += mi * mi + (p == 0 ? mu * mu : 0.f);
+        }
+        if (tid == 0) P.t_item[it[p]] = stamp;
+    }
+    if (tid == 0) P.t_user[u] = stamp;
+    if (reg_mf != 0.f || reg_mlp != 0.f) {   // NeuMF.py:94-100
+        const float r = block_sum_128(reg_mf * 0.5f * sq_mf + reg_mlp * 0.5f * sq_mlp, red, tid);
+        l += r;
+    }
+    if (tid == 0 && loss) atomicAdd(loss, l);
+    // activations and deltas for the weight-gradient kernel
+    float* out_s = scratch + (size_t)b * (2 * passes * S.act_size);
+    for (int e = tid; e < 2 * passes * S.act_size; e += kNcfThreads) out_s[e] = sm[e];
+}
+
+// dW[k][j] += sum_s a_l[s][k] * delta_l[s][j];  db[j] += sum_s delta_l[s][j]
+__global__ void __launch_bounds__(256)
+ncf_wgrad_kernel(const NcfDev S, float* __restrict__ g_dense, const float* __restrict__ scratch,
+                 int64_t batch, int passes, int n_entries_total) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;   // entry inside one tower
+    if (e >= S.tower_size) return;
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < kNcfMaxLayers; ++q)
+        if (q < S.n_layers && e >= S.w_off[q]) l = q;
+    const int out = S.out_dim[l];
+    const bool is_bias = e >= S.b_off[l];
+    const int r = is_bias ? (e - S.b_off[l]) : (e - S.w_off[l]);
+    const int k = is_bias ? 0 : r / out;
+    const int j = is_bias ? r : r - k * out;
+    const int64_t s0 = (batch * blockIdx.y) / gridDim.y, s1 = (batch * (blockIdx.y + 1)) / gridDim.y;
+    const int stride = 2 * passes * S.act_size;
+    for (int p = 0; p < passes; ++p) {
+        const int tower = (p == 1 && S.n_towers == 2) ? 1 : 0;
+        const float* a = scratch + p * S.act_size + S.a_off[l] + k;
+        const float* d = scratch + (passes + p) * S.act_size + S.a_off[l + 1] + j;
+        float acc = 0.0f;
+#pragma unroll 4
+        for (int64_t s = s0; s < s1; ++s) {
+            const float dj = __ldg(d + s * stride);
+            acc = is_bias ? acc + dj : fmaf(__ldg(a + s * stride), dj, acc);
+        }
+        if (acc != 0.0f) atomicAdd(g_dense + (size_t)tower * S.tower_size + e, acc);
+    }
 }
 
 // predict for ALL items (NeuMF.py:163-168 / MLP.py:136-140): scores[b, i] = tower-0 forward.
-// One warp per (user, item); CTA = 8 warps over 8 consecutive items of one user.
+// One warp per (user, item); weights staged in shared memory with row stride out+1.
 __global__ void __launch_bounds__(kNcfWarps * 32)
 ncf_scores_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ users, int n_users,
                   int num_items, float* __restrict__ scores) {
     extern __shared__ __align__(16) float sm[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* sW = sm;
     float* sAct = sW + S.s_tower_size;
     for (int l = 0; l < S.n_layers; ++l) {
@@ -357,7 +264,7 @@ ncf_scores_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ u
         for (int k = warp; k < in; k += kNcfWarps)
             for (int j = lane; j < out; j += kWarp)
                 sW[S.sw_off[l] + k * (out + 1) + j] = __ldg(P.dense + S.w_off[l] + k * out + j);
-        for (int e = tid; e < out; e += blockDim.x) sW[S.sb_off[l] + e] = P.dense[S.b_off[l] + e];
+        for (int e = threadIdx.x; e < out; e += blockDim.x) sW[S.sb_off[l] + e] = P.dense[S.b_off[l] + e];
     }
     __syncthreads();
     float* act = sAct + warp * S.act_size;
@@ -368,17 +275,37 @@ ncf_scores_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ u
         float mf = 0.0f;
         for (int k = lane; k < S.mf_dim; k += kWarp)
             mf = fmaf(P.mf_user[(size_t)u * S.mf_dim + k], P.mf_item[(size_t)i * S.mf_dim + k], mf);
-        mf = warp_sum(mf);
         for (int k = lane; k < S.mlp_dim; k += kWarp) {
             act[k] = P.mlp_user[(size_t)u * S.mlp_dim + k];
             act[S.mlp_dim + k] = P.mlp_item[(size_t)i * S.mlp_dim + k];
         }
         __syncwarp();
-        const float y = mf + ncf_tower_forward(S, sW, act, lane);
-        if (lane == 0) scores[e] = y;
+        for (int l = 0; l < S.n_layers; ++l) {
+            const int in = S.in_dim[l], out = S.out_dim[l];
+            const float* W = sW + S.sw_off[l];
+            const float* a = act + S.a_off[l];
+            float* o = act + S.a_off[l + 1];
+            for (int j = lane; j < out; j += kWarp) {
+                float acc = sW[S.sb_off[l] + j];
+#pragma unroll 8
+                for (int k = 0; k < in; ++k) acc = fmaf(a[k], W[k * (out + 1) + j], acc);
+                o[j] = fmaxf(acc, 0.0f);
+            }
+            __syncwarp();
+        }
+        float s = mf;
+        if (S.n_layers > 0)
+            for (int j = lane; j < S.out_dim[S.n_layers - 1]; j += kWarp) s += act[S.a_off[S.n_layers] + j];
+        s = warp_sum(s);
+        if (lane == 0) scores[e] = s;
         __syncwarp();
     }
 }
+
+// library-owned scratch for activations / deltas, grown on demand (never inside a capture:
+// callers warm up once before capturing a step graph)
+static float* g_scratch = nullptr;
+static size_t g_scratch_floats = 0;
 
 static int ncf_launch_grad(const nrc_ncf_shape* shape, const NcfPtrs& P, const int32_t* users,
                            const int32_t* items, const void* third, int64_t batch, int pairwise,
@@ -395,25 +322,27 @@ static int ncf_launch_grad(const nrc_ncf_shape* shape, const NcfPtrs& P, const i
                     "please choose a suitable loss function");
     if (batch <= 0) return NRC_OK;
     const int passes = pairwise ? 2 : 1;
-    const size_t smem = ncf_smem_bytes(S, passes);
-    NRC_REQUIRE(smem <= 200 * 1024, NRC_E_LIMIT, "NCF tower needs %zu B of shared memory", smem);
-    int64_t groups = (batch + kNcfWarps - 1) / kNcfWarps;
-    int64_t cap = (int64_t)sm_count() * 2;
-    const int grid = (int)(groups < cap ? groups : cap);
-    static bool attr_done = false;  // not inside a stream capture: set once, on first use
-    if (!attr_done) {
-        NRC_CUDA_CHECK(cudaFuncSetAttribute(ncf_grad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        NRC_CUDA_CHECK(cudaFuncSetAttribute(ncf_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
+    const size_t per_sample = (size_t)2 * passes * S.act_size;
+    const size_t need = per_sample * (size_t)batch;
+    if (need > g_scratch_floats) {
+        if (g_scratch) NRC_CUDA_CHECK(cudaFree(g_scratch));
+        g_scratch = nullptr; g_scratch_floats = 0;
+        const size_t cap = need + need / 2 + 1024;
+        NRC_CUDA_CHECK(cudaMalloc(&g_scratch, cap * sizeof(float)));
+        g_scratch_floats = cap;
     }
-    if (S.n_towers == 2 && pairwise) {
-        ncf_grad_kernel<2><<<grid, kNcfWarps * 32, smem, st>>>(S, P, users, items, third, batch, pairwise,
-                                                              loss_kind, reg_mf, reg_mlp, stamp, loss);
-    } else {
-        ncf_grad_kernel<1><<<grid, kNcfWarps * 32, smem, st>>>(S, P, users, items, third, batch, pairwise,
-                                                              loss_kind, reg_mf, reg_mlp, stamp, loss);
-    }
+    const size_t smem = (per_sample + 8) * sizeof(float);
+    NRC_REQUIRE(smem <= 48 * 1024, NRC_E_LIMIT, "NCF tower too wide: %zu B of shared memory", smem);
+    ncf_sample_kernel<<<(unsigned)batch, kNcfThreads, smem, st>>>(S, P, users, items, third, batch, pairwise,
+                                                                  loss_kind, reg_mf, reg_mlp, stamp,
+                                                                  g_scratch, loss);
     NRC_CUDA_CHECK(cudaGetLastError());
+    if (S.n_layers > 0) {
+        const int slices = (batch >= 64) ? kWgradSlices : 1;
+        dim3 grid((S.tower_size + 255) / 256, slices);
+        ncf_wgrad_kernel<<<grid, 256, 0, st>>>(S, P.g_dense, g_scratch, batch, passes, S.tower_size);
+        NRC_CUDA_CHECK(cudaGetLastError());
+    }
     return NRC_OK;
 }
 
@@ -453,7 +382,11 @@ extern "C" int nrc_ncf_scores(const nrc_ncf_shape* shape, const float* mf_user, 
               nullptr, nullptr, nullptr};
     const size_t smem = ((size_t)S.s_tower_size + (size_t)kNcfWarps * S.act_size) * 4;
     NRC_REQUIRE(smem <= 200 * 1024, NRC_E_LIMIT, "NCF tower needs %zu B of shared memory", smem);
-    NRC_CUDA_CHECK(cudaFuncSetAttribute(ncf_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    static bool attr_done = false;
+    if (!attr_done) {
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(ncf_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
     const int64_t total = (int64_t)n_users * num_items;
     int64_t blocks = (total + kNcfWarps - 1) / kNcfWarps;
     const int64_t cap = (int64_t)sm_count() * 4;

@@ -26,6 +26,7 @@ struct OptParams {
     int nseg;
     int kind;
     float h0, h1, h2, h3;
+    const float* h0_src;   // optional device-resident lr / lr_t (captured step graphs)
     int32_t stamp;
     int64_t total;
 };
@@ -76,6 +77,7 @@ __device__ __forceinline__ void opt_update(int kind, int dense_var, bool touched
 __global__ void __launch_bounds__(256) opt_apply_kernel(const OptParams P) {
     const bool has0 = P.kind != NRC_OPT_GD;
     const bool has1 = P.kind == NRC_OPT_ADAM || P.kind == NRC_OPT_RMSPROP;
+    const float h0 = P.h0_src ? __ldg(P.h0_src) : P.h0;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < P.total;
          e += (int64_t)gridDim.x * blockDim.x) {
         int s = 0;
@@ -89,13 +91,15 @@ __global__ void __launch_bounds__(256) opt_apply_kernel(const OptParams P) {
         float var = sg.var[i];
         float s0 = has0 ? sg.s0[i] : 0.0f;
         float s1 = has1 ? sg.s1[i] : 0.0f;
-        opt_update(P.kind, sg.dense_var, touched, P.h0, P.h1, P.h2, P.h3, var, g, s0, s1);
+        opt_update(P.kind, sg.dense_var, touched, h0, P.h1, P.h2, P.h3, var, g, s0, s1);
         sg.var[i] = var;
         if (has0) sg.s0[i] = s0;
         if (has1) sg.s1[i] = s1;
         sg.grad[i] = 0.0f;
     }
 }
+
+static thread_local const float* g_lr_src = nullptr;
 
 int opt_launch_init(OptLaunch& L, int opt_kind, const float* hyper_host) {
     // learner.py:14-15 raises ValueError("please select a suitable optimizer")
@@ -125,6 +129,7 @@ int opt_launch_run(const OptLaunch& L, int32_t stamp, cudaStream_t st) {
     for (int i = 0; i < L.nseg; ++i) P.seg[i] = L.seg[i];
     P.nseg = L.nseg; P.kind = L.kind;
     P.h0 = L.h[0]; P.h1 = L.h[1]; P.h2 = L.h[2]; P.h3 = L.h[3];
+    P.h0_src = g_lr_src;
     P.stamp = stamp; P.total = L.total;
     int64_t blocks = (L.total + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -135,3 +140,11 @@ int opt_launch_run(const OptLaunch& L, int32_t stamp, cudaStream_t st) {
 }
 
 }  // namespace nrc
+
+// While a non-NULL source is set, every optimizer launch of this thread reads hyper[0] (lr, or
+// Adam's lr_t) from that device float instead of the by-value argument -- what lets a captured
+// CUDA graph of a training step be replayed with a different lr_t each step.
+extern "C" int nrc_opt_set_lr_source(const float* lr_dev) {
+    nrc::g_lr_src = lr_dev;
+    return NRC_OK;
+}

@@ -352,7 +352,7 @@ def ncf_train_epoch(shape, P, users, items, third, batch_size, pairwise, loss, r
         1 if pairwise else 0, LOSS_IDS[loss], float(reg_mf), float(reg_mlp), OPT_IDS[opt],
         lr_t.ctypes.data, h.ctypes.data, arr(G), arr(S0), arr(S1), _p(tU), _p(tI), int(first_stamp),
         _p(step_loss), _stream()))
-    _count(2 * steps)
+    _count(3 * steps)
     return steps
 
 

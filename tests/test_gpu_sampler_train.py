@@ -83,6 +83,62 @@ def test_batch_randint_choice_modes():
         ops.sample_negatives(dev(ep), dev(ei), dev(np.zeros(3, np.int32)), 0, high, 1, 0)
 
 
+def test_captured_step_graph_matches_oracle(ml100k):
+    """The reference-facing per-batch path (host id arrays -> pinned block -> ONE graph launch ->
+    loss back) must train exactly like the eager path: 8 BPR/Adam steps vs the numpy oracle,
+    lr_t read from device memory inside the captured graph."""
+    import ctypes
+    from neurec_b200 import _lib, ops
+    d = ml100k
+    lib = _lib.load()
+    nu, ni, dim, bs, steps = d["num_users"], d["num_items"], 64, 512, 8
+    rs = np.random.RandomState(3)
+    U0 = (rs.randn(nu, dim) * 0.01).astype(np.float32); V0 = (rs.randn(ni, dim) * 0.01).astype(np.float32)
+    all_users = np.repeat(np.arange(nu, dtype=np.int32), np.diff(d["train_indptr"]))
+    perm = rs.permutation(len(all_users))[:bs * steps]
+    users, pos = all_users[perm].copy(), d["train_indices"][perm].copy()
+    neg = rs.randint(0, ni, len(users)).astype(np.int32)
+    tr = tf_math.MFTrainer(U0, V0, "adam", 1e-3, "bpr", 0.0, True)
+    want = tr.epoch(users, pos, neg, bs)
+
+    dU, dV = dev(U0), dev(V0)
+    z = torch.zeros_like
+    gU, gV, mU, vU, mV, vV = z(dU), z(dV), z(dU), z(dU), z(dV), z(dV)
+    tU = torch.zeros(nu, dtype=torch.int32, device="cuda"); tV = torch.zeros(ni, dtype=torch.int32, device="cuda")
+    staging = torch.zeros(3 * bs + 4, dtype=torch.int32, device="cuda")
+    pin = torch.zeros(3 * bs + 4, dtype=torch.int32).pin_memory()
+    loss_pin = torch.zeros(4).pin_memory()
+    step_loss = torch.zeros(4, device="cuda")
+    s = torch.cuda.Stream()
+    graph = ctypes.c_void_p()
+    vp = ctypes.c_void_p
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        st = vp(s.cuda_stream)
+        _lib.check(lib.nrc_graph_capture_begin(st))
+        _lib.check(lib.nrc_graph_stage_async(vp(pin.data_ptr()), vp(staging.data_ptr()), (3 * bs + 1) * 4, st))
+        _lib.check(lib.nrc_opt_set_lr_source(vp(staging.data_ptr() + 12 * bs)))
+        ops.mf_train_epoch(dU, dV, staging[:bs], staging[bs:2 * bs], staging[2 * bs:3 * bs], bs, True, "bpr", 0.0,
+                           "adam", np.zeros(1, np.float32), [0.0, 0.9, 0.999, 1e-8], gU, gV, tU, tV, mU, vU, mV,
+                           vV, 1, step_loss)
+        _lib.check(lib.nrc_opt_set_lr_source(None))
+        _lib.check(lib.nrc_graph_fetch_async(vp(step_loss.data_ptr()), vp(loss_pin.data_ptr()), 1, st))
+        _lib.check(lib.nrc_graph_capture_end(st, ctypes.byref(graph)))
+    torch.cuda.synchronize()
+    assert float(dU.cpu().numpy().std()) > 0 and np.array_equal(dU.cpu().numpy(), U0)   # capture ran nothing
+    lr_t = tf_math.adam_lr_t(1e-3, steps)
+    got = []
+    for k in range(steps):
+        o = k * bs
+        _lib.check(lib.nrc_graph_step(graph, vp(users[o:].ctypes.data), vp(pos[o:].ctypes.data),
+                                      vp(neg[o:].ctypes.data), bs, float(lr_t[k]), vp(pin.data_ptr()),
+                                      vp(s.cuda_stream)))
+        got.append(float(loss_pin[0]))
+    lib.nrc_graph_destroy(graph)
+    assert np.allclose(got, want, rtol=1e-4)
+    assert np.abs(dU.cpu().numpy() - tr.U).max() < 2e-5 and np.abs(dV.cpu().numpy() - tr.V).max() < 2e-5
+
+
 # ----------------------------------------------------------------------------- training
 def _tables(nu, ni, dim, seed=0, scale=0.1):
     rs = np.random.RandomState(seed)
