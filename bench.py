@@ -790,6 +790,107 @@ def measure(w, K, W, world, rank, windows, with_cpu=True):
     return out
 
 
+def measure_synth_sgd(K, W, world, rank, windows, with_cpu=True):
+    """BASELINE config 5 scaled to ONE GPU: BPRMF with plain SGD on synthetic tables far larger
+    than L2 (4 M users x 8 M items x d=128 = 6.1 GB), users uniform, positives Zipf(1.05),
+    batch 2^20 -- the HBM-bound single-pass kernel (nrc_mf_bpr_sgd_fused)."""
+    import torch
+    from neurec_b200 import ops
+    nu, ni, dim, bs, lr = 4_000_000, 8_000_000, 128, 1 << 20, 0.05
+    K = min(K, 24)
+    g = torch.Generator(device="cuda").manual_seed(3 + rank)
+    U = torch.randn(nu, dim, device="cuda", generator=g) * 0.01
+    V = torch.randn(ni, dim, device="cuda", generator=g) * 0.01
+
+    def ids(n):
+        u = torch.randint(0, nu, (n,), device="cuda", generator=g, dtype=torch.int32)
+        x = torch.rand(n, device="cuda", generator=g, dtype=torch.float64)
+        a = 1.05   # inverse CDF of the continuous Zipf(a) truncated to [1, ni]
+        r = (((ni ** (1 - a) - 1) * x + 1) ** (1 / (1 - a))).clamp(1, ni).long() - 1
+        p = ((r * 2654435761) % ni).to(torch.int32)          # scatter the hot ranks over the table
+        ng = torch.randint(0, ni, (n,), device="cuda", generator=g, dtype=torch.int32)
+        return u, p, ng
+    u, p, ng = ids((K + W) * bs)
+    loss = torch.zeros(1, device="cuda")
+    step = lambda s: ops.mf_bpr_sgd_fused(U, V, u[s * bs:(s + 1) * bs], p[s * bs:(s + 1) * bs],
+                                          ng[s * bs:(s + 1) * bs], lr, 0.0, loss)
+    for s in range(W):
+        step(s)
+    barrier(world); flush_l2(); barrier(world)
+    wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(W, W + K):
+        step(s)
+    e1.record()
+    barrier(world)
+    windows.append((wall0, time.perf_counter()))
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    # e2e: ids of every step come from pinned host memory, the loss goes back every step
+    hu, hp, hn = (t.cpu().pin_memory() for t in (u, p, ng))
+    du, dp, dn = (torch.empty(bs, dtype=torch.int32, device="cuda") for _ in range(3))
+    loss_pin = torch.zeros(1).pin_memory()
+
+    def e2e_step(s):
+        sl = slice(s * bs, (s + 1) * bs)
+        du.copy_(hu[sl], non_blocking=True); dp.copy_(hp[sl], non_blocking=True); dn.copy_(hn[sl], non_blocking=True)
+        loss.zero_()
+        ops.mf_bpr_sgd_fused(U, V, du, dp, dn, lr, 0.0, loss)
+        loss_pin.copy_(loss, non_blocking=True)
+        torch.cuda.synchronize()
+    for s in range(W):
+        e2e_step(s)
+    barrier(world)
+    wall0 = time.perf_counter()
+    for s in range(W, W + K):
+        e2e_step(s)
+    e2e_s = max_over_ranks(time.perf_counter() - wall0, world)
+    windows.append((wall0, time.perf_counter()))
+    barrier(world)
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peaks()
+    nbytes = bs * (24 * dim + 12)
+    kt = ms * 1e-3 / K
+    out = {"value": world * K * bs / (ms * 1e-3), "unit": "triplets/s", "steps": K, "ms_per_step": ms / K,
+           "e2e": {"value": world * K * bs / e2e_s, "unit": "triplets/s", "h2d_bytes_per_step": 12 * bs,
+                   "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / K},
+           "gpu_launches": K,
+           "config": {"workload": "BPRMF synthetic %d users x %d items, dim %d (%.1f GB of tables), learner=gd, "
+                                  "batch 2^20, users uniform, positives Zipf(1.05), negatives uniform; single-pass "
+                                  "fused step (BASELINE config 5 scaled to one GPU)" % (nu, ni, dim, (nu + ni) * dim * 4 / 1e9),
+                      "l2": "tables (6.1 GB) and the per-step id arrays are far larger than L2; every step uses "
+                            "fresh ids"},
+           "roofline": {"kernel": "mf_bpr_sgd_fused_kernel", "bound": "hbm", "achieved": nbytes / kt / 1e9,
+                        "peak": peak, "unit": "GB/s", "frac": nbytes / kt / 1e9 / peak, "traffic": None,
+                        "peak_source": peak_src, "bytes_per_launch": nbytes, "launch_us": kt * 1e6,
+                        "bytes_note": "SURVEY.md 8(d): (24*d + 12) B per triplet x 2^20 triplets",
+                        "timing": "CUDA events around the K timed launches (one kernel per step)"}}
+    if with_cpu:
+        from oracle import tf_math
+        cn_u, cn_i, cbs = 400_000, 800_000, 1 << 14
+        rs = np.random.RandomState(0)
+        Uc = (rs.randn(cn_u, dim) * 0.01).astype(np.float32); Vc = (rs.randn(cn_i, dim) * 0.01).astype(np.float32)
+        cu, cp, cn = rs.randint(0, cn_u, cbs), rs.randint(0, cn_i, cbs), rs.randint(0, cn_i, cbs)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):   # sparse gd step: gather, dot, g, scatter-sub (TF scatter_sub on IndexedSlices)
+            pu, qi, qj = Uc[cu], Vc[cp], Vc[cn]
+            x = (pu * qi).sum(1) - (pu * qj).sum(1)
+            _, gg = tf_math.pairwise_loss_and_grad("bpr", x)
+            gg = gg[:, None]
+            np.subtract.at(Uc, cu, np.float32(lr) * gg * (qi - qj))
+            np.subtract.at(Vc, cp, np.float32(lr) * gg * pu)
+            np.subtract.at(Vc, cn, np.float32(lr) * -gg * pu)
+        dt = (time.perf_counter() - t0) / reps
+        out["cpu_baseline"] = {"value": cbs / dt, "unit": "triplets/s", "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": "numpy restatement of the TF gd step on a host-RAM-sized slice (%d x %d "
+                                         "rows, d=%d, batch 2^14), per-triplet cost extrapolates linearly" % (cn_u, cn_i, dim)}
+    del U, V
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     rank, world, local = dist_setup()
@@ -810,6 +911,10 @@ def run_ours(args):
                                                   "roofline", "cpu_baseline", "config", "gpu_launches")}
             except Exception as ex:  # keep the headline line even if a secondary workload fails
                 others[name] = {"error": repr(ex)}
+        try:
+            others["bprmf-synth-sgd"] = measure_synth_sgd(24, W, world, rank, windows)
+        except Exception as ex:
+            others["bprmf-synth-sgd"] = {"error": repr(ex)}
         out["others"] = others
     clocks.stop()
     if rank == 0:

@@ -214,6 +214,16 @@ int nrc_opt_apply_rows(int32_t opt_kind, float* var, float* grad, float* slot0, 
                        const int32_t* touched, int32_t stamp, int64_t rows, int32_t dim,
                        const float* hyper_host, void* stream);
 
+/* Large-table BPR + plain SGD (learner=gd) in ONE HBM pass, for tables too big for a dense
+ * gradient accumulator (BASELINE config 5; dim 32 / 64 / 128): per triplet three coalesced row
+ * gathers, the two dots, g = -sigmoid(-x), and `row -= lr * grad` applied in place with vector
+ * RED.ADD so repeated rows still receive every contribution.  Equals MF.py:62-69 +
+ * GradientDescentOptimizer exactly when no row repeats inside the batch; with repeats a triplet
+ * may read a row already updated by another triplet of the same batch (documented deviation). */
+int nrc_mf_bpr_sgd_fused(float* user_table, float* item_table, int32_t dim, const int32_t* users,
+                         const int32_t* pos_items, const int32_t* neg_items, int64_t batch,
+                         float lr, float reg, float* loss, void* stream);
+
 /* Same rules for every variable of a model in ONE launch (what `optimizer.minimize(loss)`
  * applies per step).  All arrays are HOST arrays of length n_vars holding device pointers /
  * shapes; dense_var[i] = 1 marks a variable whose gradient is a dense tensor (tf.layers.dense

@@ -31,7 +31,7 @@ namespace nrc {
 constexpr int kNcfMaxLayers = 4;
 constexpr int kNcfThreads = 128;   // threads per sample CTA
 constexpr int kNcfWarps = 8;       // warps per CTA of the score kernel
-constexpr int kWgradSlices = 4;    // batch slices of the weight-gradient kernel
+constexpr int kWgradSlices = 16;   // batch slices of the weight-gradient kernel
 
 struct NcfDev {
     int mf_dim, mlp_dim, n_layers, n_towers;
@@ -181,12 +181,15 @@ ncf_sample_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ u
                 const float* d = del + S.a_off[l2 + 1];
                 const float* a = act + S.a_off[l2];
                 float* dp = del + S.a_off[l2];
-                for (int k = tid; k < in; k += kNcfThreads) {
+                // one warp per input row k: lanes stride over the (contiguous) row => coalesced
+                // weight reads, then a shuffle reduction
+                const int lane = tid & 31, wrp = tid >> 5;
+                for (int k = wrp; k < in; k += kNcfThreads / 32) {
                     const float* wr = W + (size_t)k * out;
                     float s = 0.0f;
-#pragma unroll 8
-                    for (int j = 0; j < out; ++j) s = fmaf(__ldg(wr + j), d[j], s);
-                    dp[k] = (l2 > 0) ? ((a[k] > 0.0f) ? s : 0.0f) : s;
+                    for (int j = lane; j < out; j += kWarp) s = fmaf(__ldg(wr + j), d[j], s);
+                    s = warp_sum(s);
+                    if (lane == 0) dp[k] = (l2 > 0) ? ((a[k] > 0.0f) ? s : 0.0f) : s;
                 }
                 __syncthreads();
             }
@@ -218,32 +221,171 @@ ncf_sample_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ u
     for (int e = tid; e < 2 * passes * S.act_size; e += kNcfThreads) out_s[e] = sm[e];
 }
 
-// dW[k][j] += sum_s a_l[s][k] * delta_l[s][j];  db[j] += sum_s delta_l[s][j]
+// ----------------------------------------------------------------------------------------
+// Fast path for the reference's default tower (conf/NeuMF.properties, conf/MLP.properties:
+// layers=[64,32,16], so IN0 = 64): every dimension is a compile-time constant, all 128 threads
+// work in every layer (the k-range of a layer is split over thread groups and the partial sums
+// are combined in a fixed order), weight rows are read fully coalesced in both directions.
+// ----------------------------------------------------------------------------------------
+template <int IN, int OUT>
+__device__ __forceinline__ void fast_dense_fwd(const float* __restrict__ W, const float* __restrict__ bias,
+                                               const float* a_in, float* a_out, float* part, int tid) {
+    constexpr int G = kNcfThreads / OUT, KPG = IN / G;
+    const int j = tid % OUT, g = tid / OUT;
+    float acc = 0.0f;
+#pragma unroll
+    for (int kk = 0; kk < KPG; ++kk) {
+        const int k = g * KPG + kk;
+        acc = fmaf(a_in[k], __ldg(W + k * OUT + j), acc);
+    }
+    part[tid] = acc;
+    __syncthreads();
+    if (tid < OUT) {
+        float s = __ldg(bias + tid);
+#pragma unroll
+        for (int q = 0; q < G; ++q) s += part[q * OUT + tid];
+        a_out[tid] = fmaxf(s, 0.0f);  // tf.nn.relu
+    }
+    __syncthreads();
+}
+
+template <int IN, int OUT, bool MASK>
+__device__ __forceinline__ void fast_dense_bwd(const float* __restrict__ W, const float* d_out,
+                                               const float* a_in, float* d_in, int tid) {
+    constexpr int TPR = kNcfThreads / IN, JPT = OUT / TPR;   // threads per input row
+    const int k = tid / TPR, jq = tid % TPR;
+    const float* wr = W + k * OUT + jq * JPT;
+    float s = 0.0f;
+#pragma unroll
+    for (int jj = 0; jj < JPT; ++jj) s = fmaf(__ldg(wr + jj), d_out[jq * JPT + jj], s);
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    if (jq == 0) d_in[k] = MASK ? ((a_in[k] > 0.0f) ? s : 0.0f) : s;
+    __syncthreads();
+}
+
+template <int IN0, int O0, int O1, int O2>
+__global__ void __launch_bounds__(kNcfThreads)
+ncf_sample_fast_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ users,
+                       const int32_t* __restrict__ items, const void* __restrict__ third,
+                       int64_t batch, int pairwise, int loss_kind, float reg_mf, float reg_mlp,
+                       int32_t stamp, float* __restrict__ scratch, float* __restrict__ loss) {
+    constexpr int ACT = IN0 + O0 + O1 + O2, A1 = IN0, A2 = IN0 + O0, A3 = IN0 + O0 + O1, MD = IN0 / 2;
+    constexpr int W0 = 0, B0 = IN0 * O0, W1 = B0 + O0, B1 = W1 + O0 * O1, W2 = B1 + O1, B2 = W2 + O1 * O2;
+    __shared__ __align__(16) float sm[4 * ACT + kNcfThreads + 8];
+    const int tid = threadIdx.x;
+    const int passes = pairwise ? 2 : 1;
+    float* sAct = sm;
+    float* sDel = sAct + passes * ACT;
+    float* part = sm + 4 * ACT;
+    float* red = part + kNcfThreads;
+    const int64_t b = blockIdx.x;
+    const int u = users[b];
+    const int it[2] = {items[b], pairwise ? reinterpret_cast<const int32_t*>(third)[b] : 0};
+
+    float yhat[2] = {0.0f, 0.0f};
+    for (int p = 0; p < passes; ++p) {
+        float* act = sAct + p * ACT;
+        float mf = 0.0f;
+        for (int k = tid; k < S.mf_dim; k += kNcfThreads)
+            mf = fmaf(P.mf_user[(size_t)u * S.mf_dim + k], P.mf_item[(size_t)it[p] * S.mf_dim + k], mf);
+        if (tid < MD) act[tid] = P.mlp_user[(size_t)u * MD + tid];
+        else if (tid < IN0) act[tid] = P.mlp_item[(size_t)it[p] * MD + (tid - MD)];
+        __syncthreads();
+        const float* tw = P.dense + (size_t)((p == 1 && S.n_towers == 2) ? 1 : 0) * S.tower_size;
+        fast_dense_fwd<IN0, O0>(tw + W0, tw + B0, act, act + A1, part, tid);
+        fast_dense_fwd<O0, O1>(tw + W1, tw + B1, act + A1, act + A2, part, tid);
+        fast_dense_fwd<O1, O2>(tw + W2, tw + B2, act + A2, act + A3, part, tid);
+        const float s = (tid < O2) ? act[A3 + tid] : 0.0f;
+        yhat[p] = block_sum_128(mf + s, red, tid);
+    }
+
+    float l, g;
+    if (pairwise) {
+        const float x = yhat[0] - yhat[1];
+        if (loss_kind == NRC_LOSS_BPR) {
+            l = (x >= 0.f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
+            g = -1.0f / (1.0f + expf(x));
+        } else if (loss_kind == NRC_LOSS_HINGE) {
+            const float t = x + 1.0f; l = fmaxf(t, 0.f); g = (t > 0.f) ? 1.f : 0.f;
+        } else {
+            const float t = 1.0f - x; l = t * t; g = -2.0f * t;
+        }
+    } else {
+        const float x = yhat[0], z = reinterpret_cast<const float*>(third)[b];
+        if (loss_kind == NRC_LOSS_CROSS_ENTROPY) {
+            const float inv_b = 1.0f / (float)batch;
+            const float e = expf(-fabsf(x));
+            l = (fmaxf(x, 0.f) - x * z + log1pf(e)) * inv_b;
+            const float s = (x >= 0.f) ? 1.f / (1.f + e) : e / (1.f + e);
+            g = (s - z) * inv_b;
+        } else {
+            const float t = z - x; l = t * t; g = -2.0f * t;
+        }
+    }
+
+    float sq_mf = 0.f, sq_mlp = 0.f;
+    for (int p = 0; p < passes; ++p) {
+        const float gp = (p == 0) ? g : -g;
+        const float* tw = P.dense + (size_t)((p == 1 && S.n_towers == 2) ? 1 : 0) * S.tower_size;
+        float* act = sAct + p * ACT;
+        float* del = sDel + p * ACT;
+        if (tid < O2) del[A3 + tid] = (act[A3 + tid] > 0.0f) ? gp : 0.0f;
+        __syncthreads();
+        fast_dense_bwd<O1, O2, true>(tw + W2, del + A3, act + A2, del + A2, tid);
+        fast_dense_bwd<O0, O1, true>(tw + W1, del + A2, act + A1, del + A1, tid);
+        fast_dense_bwd<IN0, O0, false>(tw + W0, del + A1, act, del, tid);
+        for (int k = tid; k < S.mf_dim; k += kNcfThreads) {
+            const float pu = P.mf_user[(size_t)u * S.mf_dim + k];
+            const float qi = P.mf_item[(size_t)it[p] * S.mf_dim + k];
+            atomicAdd(P.g_mf_user + (size_t)u * S.mf_dim + k, gp * qi + (p == 0 ? reg_mf * pu : 0.f));
+            atomicAdd(P.g_mf_item + (size_t)it[p] * S.mf_dim + k, gp * pu + reg_mf * qi);
+            sq_mf += qi * qi + (p == 0 ? pu * pu : 0.f);
+        }
+        if (tid < MD) {
+            const float mu = act[tid];
+            atomicAdd(P.g_mlp_user + (size_t)u * MD + tid, del[tid] + (p == 0 ? reg_mlp * mu : 0.f));
+            if (p == 0) sq_mlp += mu * mu;
+        } else if (tid < IN0) {
+            const float mi = act[tid];
+            atomicAdd(P.g_mlp_item + (size_t)it[p] * MD + (tid - MD), del[tid] + reg_mlp * mi);
+            sq_mlp += mi * mi;
+        }
+        if (tid == 0) P.t_item[it[p]] = stamp;
+    }
+    if (tid == 0) P.t_user[u] = stamp;
+    if (reg_mf != 0.f || reg_mlp != 0.f)
+        l += block_sum_128(reg_mf * 0.5f * sq_mf + reg_mlp * 0.5f * sq_mlp, red, tid);
+    if (tid == 0 && loss) atomicAdd(loss, l);
+    float* out_s = scratch + (size_t)b * (2 * passes * ACT);
+    for (int e = tid; e < 2 * passes * ACT; e += kNcfThreads) out_s[e] = sm[e];
+}
+
+// dW_l[k][j] += sum_s a_l[s][k] * delta_l[s][j];  db_l[j] += sum_s delta_l[s][j]
+// grid = (ceil(max_out/32), ceil((max_in+1)/8), n_layers * slices); block = (32, 8): thread
+// (tx, ty) owns entry (k = tile_y*8 + ty, j = tile_x*32 + tx) of layer z / slices, row k == in
+// being the bias; no integer division anywhere, delta reads coalesced over j.
 __global__ void __launch_bounds__(256)
 ncf_wgrad_kernel(const NcfDev S, float* __restrict__ g_dense, const float* __restrict__ scratch,
-                 int64_t batch, int passes, int n_entries_total) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;   // entry inside one tower
-    if (e >= S.tower_size) return;
-    int l = 0;
-#pragma unroll
-    for (int q = 1; q < kNcfMaxLayers; ++q)
-        if (q < S.n_layers && e >= S.w_off[q]) l = q;
-    const int out = S.out_dim[l];
-    const bool is_bias = e >= S.b_off[l];
-    const int r = is_bias ? (e - S.b_off[l]) : (e - S.w_off[l]);
-    const int k = is_bias ? 0 : r / out;
-    const int j = is_bias ? r : r - k * out;
-    const int64_t s0 = (batch * blockIdx.y) / gridDim.y, s1 = (batch * (blockIdx.y + 1)) / gridDim.y;
+                 int64_t batch, int passes, int slices) {
+    const int l = blockIdx.z / slices, slice = blockIdx.z - l * slices;
+    const int in = S.in_dim[l], out = S.out_dim[l];
+    const int j = blockIdx.x * 32 + threadIdx.x, k = blockIdx.y * 8 + threadIdx.y;
+    if (j >= out || k > in) return;
+    const bool is_bias = (k == in);
+    const int64_t s0 = (batch * slice) / slices, s1 = (batch * (slice + 1)) / slices;
     const int stride = 2 * passes * S.act_size;
+    const int e = is_bias ? (S.b_off[l] + j) : (S.w_off[l] + k * out + j);
     for (int p = 0; p < passes; ++p) {
         const int tower = (p == 1 && S.n_towers == 2) ? 1 : 0;
-        const float* a = scratch + p * S.act_size + S.a_off[l] + k;
+        const float* a = scratch + p * S.act_size + S.a_off[l] + (is_bias ? 0 : k);
         const float* d = scratch + (passes + p) * S.act_size + S.a_off[l + 1] + j;
         float acc = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
         for (int64_t s = s0; s < s1; ++s) {
             const float dj = __ldg(d + s * stride);
-            acc = is_bias ? acc + dj : fmaf(__ldg(a + s * stride), dj, acc);
+            const float av = is_bias ? 1.0f : __ldg(a + s * stride);
+            acc = fmaf(av, dj, acc);
         }
         if (acc != 0.0f) atomicAdd(g_dense + (size_t)tower * S.tower_size + e, acc);
     }
@@ -333,14 +475,25 @@ static int ncf_launch_grad(const nrc_ncf_shape* shape, const NcfPtrs& P, const i
     }
     const size_t smem = (per_sample + 8) * sizeof(float);
     NRC_REQUIRE(smem <= 48 * 1024, NRC_E_LIMIT, "NCF tower too wide: %zu B of shared memory", smem);
-    ncf_sample_kernel<<<(unsigned)batch, kNcfThreads, smem, st>>>(S, P, users, items, third, batch, pairwise,
-                                                                  loss_kind, reg_mf, reg_mlp, stamp,
-                                                                  g_scratch, loss);
+    const bool fast = S.n_layers == 3 && S.in_dim[0] == 64 && S.out_dim[0] == 64 &&
+                      S.out_dim[1] == 32 && S.out_dim[2] == 16;
+    if (fast)
+        ncf_sample_fast_kernel<64, 64, 32, 16><<<(unsigned)batch, kNcfThreads, 0, st>>>(
+            S, P, users, items, third, batch, pairwise, loss_kind, reg_mf, reg_mlp, stamp, g_scratch, loss);
+    else
+        ncf_sample_kernel<<<(unsigned)batch, kNcfThreads, smem, st>>>(S, P, users, items, third, batch,
+                                                                      pairwise, loss_kind, reg_mf, reg_mlp,
+                                                                      stamp, g_scratch, loss);
     NRC_CUDA_CHECK(cudaGetLastError());
     if (S.n_layers > 0) {
         const int slices = (batch >= 64) ? kWgradSlices : 1;
-        dim3 grid((S.tower_size + 255) / 256, slices);
-        ncf_wgrad_kernel<<<grid, 256, 0, st>>>(S, P.g_dense, g_scratch, batch, passes, S.tower_size);
+        int max_in = 0, max_out = 0;
+        for (int l = 0; l < S.n_layers; ++l) {
+            max_in = S.in_dim[l] > max_in ? S.in_dim[l] : max_in;
+            max_out = S.out_dim[l] > max_out ? S.out_dim[l] : max_out;
+        }
+        dim3 grid((max_out + 31) / 32, (max_in + 1 + 7) / 8, S.n_layers * slices);
+        ncf_wgrad_kernel<<<grid, dim3(32, 8), 0, st>>>(S, P.g_dense, g_scratch, batch, passes, slices);
         NRC_CUDA_CHECK(cudaGetLastError());
     }
     return NRC_OK;

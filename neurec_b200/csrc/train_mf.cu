@@ -144,6 +144,79 @@ mf_pointwise_grad_kernel(const float* __restrict__ U, const float* __restrict__ 
     if (lane == 0 && loss) atomicAdd(loss, loss_acc);
 }
 
+// ----------------------------------------------------------------------------------------
+// Large-table path (BASELINE config 5: tables that leave no room for a dense gradient
+// accumulator): BPR + plain SGD in ONE pass.  One warp per triplet, lane owns VEC consecutive
+// floats of the row (dim = 32*VEC): three coalesced row gathers, two shuffle-reduced dots,
+// g = -sigmoid(-x), then `var -= lr * grad` applied in place with vector RED.ADD (float4 /
+// float2 atomics, sm_90+), so duplicate rows still accumulate every contribution.  Algorithmic
+// traffic: 3 rows read + 3 rows read-modify-written = 24*dim + 12 B per triplet.
+// Deviation from TF, by construction: a triplet may read a row another triplet of the same
+// batch has already updated ("hogwild inside a batch"); identical to the two-phase step when
+// no row repeats inside the batch.
+// ----------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256)
+mf_bpr_sgd_fused_kernel(float* __restrict__ U, float* __restrict__ V, const int32_t* __restrict__ users,
+                        const int32_t* __restrict__ pos, const int32_t* __restrict__ neg, int64_t batch,
+                        float lr, float reg, float* __restrict__ loss) {
+    constexpr int D = 32 * VEC;
+    const int lane = threadIdx.x & 31;
+    const int64_t wpb = blockDim.x >> 5;
+    float loss_acc = 0.0f;
+    for (int64_t b = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); b < batch; b += (int64_t)gridDim.x * wpb) {
+        float* pu = U + (size_t)users[b] * D + lane * VEC;
+        float* qi = V + (size_t)pos[b] * D + lane * VEC;
+        float* qj = V + (size_t)neg[b] * D + lane * VEC;
+        float a[VEC], bi[VEC], bj[VEC];
+        if constexpr (VEC == 4) {
+            const float4 x = *reinterpret_cast<const float4*>(pu), y = *reinterpret_cast<const float4*>(qi),
+                         z = *reinterpret_cast<const float4*>(qj);
+            a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w;
+            bi[0] = y.x; bi[1] = y.y; bi[2] = y.z; bi[3] = y.w;
+            bj[0] = z.x; bj[1] = z.y; bj[2] = z.z; bj[3] = z.w;
+        } else if constexpr (VEC == 2) {
+            const float2 x = *reinterpret_cast<const float2*>(pu), y = *reinterpret_cast<const float2*>(qi),
+                         z = *reinterpret_cast<const float2*>(qj);
+            a[0] = x.x; a[1] = x.y; bi[0] = y.x; bi[1] = y.y; bj[0] = z.x; bj[1] = z.y;
+        } else {
+            a[0] = *pu; bi[0] = *qi; bj[0] = *qj;
+        }
+        float di = 0.f, dj = 0.f, sq = 0.f;
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) {
+            di = fmaf(a[t], bi[t], di);
+            dj = fmaf(a[t], bj[t], dj);
+            sq += a[t] * a[t] + bi[t] * bi[t] + bj[t] * bj[t];
+        }
+        di = warp_sum(di); dj = warp_sum(dj);
+        const float x = di - dj;
+        float l = (x >= 0.f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
+        if (reg != 0.0f) l += reg * 0.5f * warp_sum(sq);
+        loss_acc += l;
+        const float g = -1.0f / (1.0f + expf(x));
+        float du[VEC], dvi[VEC], dvj[VEC];
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) {
+            du[t] = -lr * (g * (bi[t] - bj[t]) + reg * a[t]);
+            dvi[t] = -lr * (g * a[t] + reg * bi[t]);
+            dvj[t] = -lr * (-g * a[t] + reg * bj[t]);
+        }
+        if constexpr (VEC == 4) {
+            atomicAdd(reinterpret_cast<float4*>(pu), make_float4(du[0], du[1], du[2], du[3]));
+            atomicAdd(reinterpret_cast<float4*>(qi), make_float4(dvi[0], dvi[1], dvi[2], dvi[3]));
+            atomicAdd(reinterpret_cast<float4*>(qj), make_float4(dvj[0], dvj[1], dvj[2], dvj[3]));
+        } else if constexpr (VEC == 2) {
+            atomicAdd(reinterpret_cast<float2*>(pu), make_float2(du[0], du[1]));
+            atomicAdd(reinterpret_cast<float2*>(qi), make_float2(dvi[0], dvi[1]));
+            atomicAdd(reinterpret_cast<float2*>(qj), make_float2(dvj[0], dvj[1]));
+        } else {
+            atomicAdd(pu, du[0]); atomicAdd(qi, dvi[0]); atomicAdd(qj, dvj[0]);
+        }
+    }
+    if (lane == 0 && loss) atomicAdd(loss, loss_acc);
+}
+
 static int grad_grid(int64_t batch) {
     const int wpb = 8;
     int64_t blocks = (batch + wpb - 1) / wpb;
@@ -190,6 +263,31 @@ extern "C" int nrc_mf_pointwise_grad(const float* user_table, const float* item_
     mf_pointwise_grad_kernel<<<grad_grid(batch), 256, 0, as_stream(stream)>>>(
         user_table, item_table, dim, users, items, labels, batch, loss_kind, reg, grad_user,
         grad_item, touched_user, touched_item, stamp, loss);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+extern "C" int nrc_mf_bpr_sgd_fused(float* user_table, float* item_table, int32_t dim,
+                                    const int32_t* users, const int32_t* pos_items,
+                                    const int32_t* neg_items, int64_t batch, float lr, float reg,
+                                    float* loss, void* stream) {
+    NRC_REQUIRE(dim == 32 || dim == 64 || dim == 128, NRC_E_LIMIT,
+                "the fused single-pass step supports dim 32, 64 or 128 (got %d)", dim);
+    NRC_REQUIRE(batch >= 0, NRC_E_VALUE, "batch must be >= 0");
+    if (batch == 0) return NRC_OK;
+    int64_t blocks = (batch + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;   // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = as_stream(stream);
+    if (dim == 128)
+        mf_bpr_sgd_fused_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(user_table, item_table, users, pos_items,
+                                                                    neg_items, batch, lr, reg, loss);
+    else if (dim == 64)
+        mf_bpr_sgd_fused_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(user_table, item_table, users, pos_items,
+                                                                    neg_items, batch, lr, reg, loss);
+    else
+        mf_bpr_sgd_fused_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(user_table, item_table, users, pos_items,
+                                                                    neg_items, batch, lr, reg, loss);
     NRC_CUDA_CHECK(cudaGetLastError());
     return NRC_OK;
 }

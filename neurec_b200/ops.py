@@ -199,6 +199,13 @@ def mf_pointwise_grad(U, V, users, items, labels, loss, reg, gU, gV, tU, tV, sta
     _count()
 
 
+def mf_bpr_sgd_fused(U, V, users, pos, neg, lr, reg, loss_out):
+    """Single-pass BPR + SGD for huge tables (see nrc_mf_bpr_sgd_fused)."""
+    check(_lib.load().nrc_mf_bpr_sgd_fused(_p(U), _p(V), U.shape[1], _p(users), _p(pos), _p(neg),
+                                           users.numel(), float(lr), float(reg), _p(loss_out), _stream()))
+    _count()
+
+
 def opt_apply_rows(opt, var, grad, slot0, slot1, touched, stamp, hyper):
     h = np.zeros(4, dtype=np.float32)
     h[:len(hyper)] = hyper

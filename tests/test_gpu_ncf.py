@@ -60,8 +60,10 @@ def test_ncf_grad_vs_oracle(mf_dim, layers, pairwise, loss, n_towers):
     for k in KEYS:
         if P[k] is None:
             continue
-        # sums of <= ~200 fp32 terms in a different order: 1e-4 relative, 2e-6 absolute
-        assert np.allclose(dG[k].cpu().numpy(), G[k], rtol=1e-4, atol=2e-6), k
+        # sums of <= ~400 fp32 terms of mixed sign in a different order: 1e-4 relative plus an
+        # absolute term scaled by the largest gradient entry (near-cancelling sums)
+        atol = 2e-6 * max(1.0, float(np.abs(G[k]).max()))
+        assert np.allclose(dG[k].cpu().numpy(), G[k], rtol=1e-4, atol=atol), k
     assert np.array_equal(dtU.cpu().numpy() == 3, tU) and np.array_equal(dtI.cpu().numpy() == 3, tI)
 
 

@@ -186,6 +186,40 @@ def test_pointwise_grad_vs_oracle(loss):
     assert np.isclose(dl.item(), l, rtol=1e-5)
 
 
+@pytest.mark.parametrize("dim", [128, 64, 32])
+def test_fused_single_pass_sgd_vs_oracle(dim):
+    """Large-table path: with no repeated row inside the batch the one-pass kernel equals the
+    TF gd step (1e-6 abs); with heavy repeats every contribution still lands (atomics), only
+    the read/update interleaving differs -> compare against sequential per-triplet SGD bounds."""
+    from neurec_b200 import ops
+    rs = np.random.RandomState(dim)
+    nu, ni, bs = 3000, 5000, 1024
+    U, V = _tables(nu, ni, dim, 9, scale=0.3)
+    users = rs.permutation(nu)[:bs].astype(np.int32)
+    items = rs.permutation(ni)[:2 * bs].astype(np.int32)        # all rows distinct
+    pos, neg = items[:bs], items[bs:]
+    tr = tf_math.MFTrainer(U, V, "gd", 0.05, "bpr", 0.01, True)
+    want_loss = tr.step(users, pos, neg)
+    dU, dV, dl = dev(U), dev(V), torch.zeros(1, device="cuda")
+    ops.mf_bpr_sgd_fused(dU, dV, dev(users), dev(pos), dev(neg), 0.05, 0.01, dl)
+    assert np.isclose(dl.item(), want_loss, rtol=1e-5)
+    assert np.abs(dU.cpu().numpy() - tr.U).max() < 1e-6 and np.abs(dV.cpu().numpy() - tr.V).max() < 1e-6
+    # repeats: one hot item in every triplet -> its row receives all 1024 contributions
+    pos2 = np.full(bs, 7, np.int32)
+    tr2 = tf_math.MFTrainer(U, V, "gd", 1e-4, "bpr", 0.0, True)
+    tr2.step(users, pos2, neg)
+    dU, dV = dev(U), dev(V)
+    ops.mf_bpr_sgd_fused(dU, dV, dev(users), dev(pos2), dev(neg), 1e-4, 0.0, dl)
+    # hogwild-inside-batch deviation is second order in lr: |delta| <= ~lr^2 * bs * |grad|^2
+    assert np.abs(dV.cpu().numpy()[7] - tr2.V[7]).max() < 5e-3 * np.abs(tr2.V[7] - V[7]).max() + 1e-6
+    assert np.abs(dU.cpu().numpy() - tr2.U).max() < 1e-5
+    with pytest.raises(_NrcLimit):
+        ops.mf_bpr_sgd_fused(dev(U[:, :48].copy()), dev(V[:, :48].copy()), dev(users), dev(pos), dev(neg), 0.1, 0.0, dl)
+
+
+from neurec_b200._lib import NrcError as _NrcLimit  # noqa: E402
+
+
 @pytest.mark.parametrize("opt", ["gd", "adam", "adagrad", "rmsprop", "momentum"])
 def test_optimizer_apply_bit_exact(opt):
     """Given the same gradient the TF-1.12 update rules are bit-identical to the numpy oracle."""
