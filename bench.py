@@ -898,7 +898,16 @@ def run_ours(args):
     clocks = ClockSampler(local)
     clocks.start()
     windows = []
-    out = measure(make_workload(args.workload, rank), K, W, world, rank, windows)
+    if args.workload == "bprmf-synth":
+        o = measure_synth_sgd(K, W, world, rank, windows)
+        out = None
+        if rank == 0:
+            out = {"metric": "triplets/sec", "n_gpus": world, "warmup": W, "higher_is_better": True,
+                   "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic, seed 3"}
+            out.update(o)
+        args.only = True
+    else:
+        out = measure(make_workload(args.workload, rank), K, W, world, rank, windows)
     if world == 1 and not args.only:
         others = {}
         for name in WORKLOADS:
@@ -961,7 +970,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1570)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=WORKLOADS)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=WORKLOADS + ("bprmf-synth",))
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--only", action="store_true", help="measure only --workload (used under ncu)")
     args = ap.parse_args()

