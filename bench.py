@@ -208,7 +208,9 @@ def graph_time(fn, reps=40, rounds=5):
         fn()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=s):
+        # thread-local capture mode: the NCCL watchdog thread of a multi-rank run must stay free to
+        # query its events while this thread captures
+        with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
             for _ in range(reps):
                 fn()
         g.replay()
@@ -928,12 +930,11 @@ def run_ours(args):
     clocks.stop()
     if rank == 0:
         out["clocks"] = clocks.summary(windows)
+        print(json.dumps(out), flush=True)
     barrier(world)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
-    if rank == 0:
-        print(json.dumps(out))
 
 
 def run_reference(args):

@@ -131,6 +131,12 @@ int nrc_eval_mf(const float* user_table, const float* item_table, int32_t dim,
                 const int32_t* metric_host, int32_t metric_num, int32_t top_k,
                 float* results, int32_t* ranks, void* stream);
 
+/* nrc_eval_mf normally runs a tie-free fast pass (valid whenever the K+1 largest scores of a
+ * user are pairwise distinct) and re-does the remaining users with the exact libstdc++ heap
+ * replay; both give the reference's ranking bit for bit.  on != 0 forces the heap replay for
+ * every user (test / debugging hook). */
+int nrc_eval_force_exact(int32_t on);
+
 /* MF.predict(user_ids, None), model/general_recommender/MF.py:120-122 (np.matmul(U[users], V.T))
  * and LightGCN.predict, LightGCN.py:187-189, materialised: scores f32 [num_rows, num_items]
  * with the same fp32 FMA chain over k the fused evaluator uses. */

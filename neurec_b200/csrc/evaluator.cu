@@ -267,12 +267,17 @@ eval_rows_kernel(const float* __restrict__ scores, int N, int rows, int K, int L
 template <int TM, int TN, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32)
 eval_mf_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, int D, int N,
-               const int32_t* __restrict__ users, int num_eval,
+               const int32_t* __restrict__ users, int num_eval_arg,
                const int64_t* __restrict__ train_ptr, const int32_t* __restrict__ train_idx,
                const int64_t* __restrict__ test_ptr, const int32_t* __restrict__ test_idx,
-               int K, int L, int M, float* __restrict__ results, int32_t* __restrict__ ranks) {
+               int K, int L, int M, float* __restrict__ results, int32_t* __restrict__ ranks,
+               const int32_t* __restrict__ row_map, const int32_t* __restrict__ count_ptr) {
+    // row_map / count_ptr (optional): evaluate only the batch rows listed in row_map[0, *count_ptr)
+    // -- the users the tie-free fast kernel could not decide.
     constexpr int TILE = TN * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int num_eval = count_ptr ? *count_ptr : num_eval_arg;
+    if ((int)(blockIdx.x * (kWarps * TM)) >= num_eval) return;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int D4 = (D + 3) & ~3;       // padded dim (zero fill: fma(0,0,acc) == acc)
@@ -289,7 +294,7 @@ eval_mf_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, i
         const int us = idx / D4, k = idx - us * D4;
         const int b = blockIdx.x * (kWarps * TM) + us;
         float val = 0.0f;
-        if (b < num_eval && k < D) val = Utab[(size_t)users[b] * D + k];
+        if (b < num_eval && k < D) val = Utab[(size_t)users[row_map ? row_map[b] : b] * D + k];
         sU[idx] = val;
     }
     __syncthreads();
@@ -303,7 +308,7 @@ eval_mf_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, i
     for (int m = 0; m < TM; ++m) {
         const int b = user_slot0 + m;
         live[m] = b < num_eval;
-        const int u = live[m] ? users[b] : 0;
+        const int u = live[m] ? users[row_map ? row_map[b] : b] : 0;
         tr_beg[m] = live[m] ? train_ptr[u] : 0;
         tr_len[m] = live[m] ? (int)(train_ptr[u + 1] - tr_beg[m]) : 0;
         tr_pos[m] = 0;
@@ -423,7 +428,7 @@ eval_mf_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, i
 #pragma unroll
     for (int m = 0; m < TM; ++m) {
         if (!live[m]) continue;
-        const int b = user_slot0 + m;
+        const int b = row_map ? row_map[user_slot0 + m] : (user_slot0 + m);
         Heap h;
         h.idx = sHeap + (warp * TM + m) * hstride;
         h.val = reinterpret_cast<float*>(h.idx + L);
@@ -439,6 +444,184 @@ eval_mf_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, i
             float* s_sum_pre = reinterpret_cast<float*>(s_cnt + K);
             float* s_dcg = s_sum_pre + K;
             metrics_for_user(h.idx, K, test_idx + t0, T, s_cnt, s_sum_pre, s_dcg, M,
+                             results + (size_t)b * M * K, lane);
+        }
+        __syncwarp();
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Kernel B-fast: the same fused scoring, but selection WITHOUT the heap replay.
+//
+// std::partial_sort_copy's output is ambiguous only where scores tie: if the K+1 largest scores
+// of a row are pairwise distinct, the first K entries of the reference's ranking are exactly
+// those K items in descending score order, whatever the heap did (the heap always holds the L
+// largest values; sort_heap orders distinct values uniquely; ties below rank K+1 cannot move
+// anything above them).  So each warp keeps, per user, the running top-(K+1) as a sorted list
+// spread over its lanes (lane r = rank r; K+1 <= 32): an insertion is one ballot + two
+// shuffles instead of ~150 single-lane heap instructions.  At the end the warp checks that the
+// K+1 values are strictly decreasing and finite; users that fail the check (exact ties in the
+// top K+1, or fewer than K+1 unmasked items) are appended to a list and re-done by the exact
+// heap-replay kernel above, so the result stays bit-identical to the reference for every input.
+// ----------------------------------------------------------------------------------------
+template <int TM, int TN, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32)
+eval_mf_fast_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, int D, int N,
+                    const int32_t* __restrict__ users, int num_eval,
+                    const int64_t* __restrict__ train_ptr, const int32_t* __restrict__ train_idx,
+                    const int64_t* __restrict__ test_ptr, const int32_t* __restrict__ test_idx,
+                    int K, int M, float* __restrict__ results, int32_t* __restrict__ ranks,
+                    int32_t* __restrict__ slow_count, int32_t* __restrict__ slow_rows) {
+    constexpr int TILE = TN * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int D4 = (D + 3) & ~3;
+    const int VS = D4 + 4;
+    float* sU = reinterpret_cast<float*>(smem_raw);                 // [kWarps*TM][D4]
+    float* sV = sU + kWarps * TM * D4;                              // [TILE][VS]
+    int* sMet = reinterpret_cast<int*>(sV + TILE * VS);             // per user 4K words
+    const int user_slot0 = blockIdx.x * (kWarps * TM) + warp * TM;
+
+    for (int idx = threadIdx.x; idx < kWarps * TM * D4; idx += blockDim.x) {
+        const int us = idx / D4, k = idx - us * D4;
+        const int b = blockIdx.x * (kWarps * TM) + us;
+        float val = 0.0f;
+        if (b < num_eval && k < D) val = Utab[(size_t)users[b] * D + k];
+        sU[idx] = val;
+    }
+    __syncthreads();
+
+    int64_t tr_beg[TM];
+    int tr_len[TM], tr_pos[TM];
+    float top_v[TM], thr[TM];   // lane r holds the rank-r entry of user m's running top-(K+1)
+    int top_i[TM];
+    bool live[TM];
+#pragma unroll
+    for (int m = 0; m < TM; ++m) {
+        const int b = user_slot0 + m;
+        live[m] = b < num_eval;
+        const int u = live[m] ? users[b] : 0;
+        tr_beg[m] = live[m] ? train_ptr[u] : 0;
+        tr_len[m] = live[m] ? (int)(train_ptr[u + 1] - tr_beg[m]) : 0;
+        tr_pos[m] = 0;
+        top_v[m] = -INFINITY;
+        top_i[m] = -1;
+        thr[m] = -INFINITY;
+    }
+
+    for (int base = 0; base < N; base += TILE) {
+        __syncthreads();
+        if ((D & 3) == 0) {
+            const int q_per_row = D >> 2;
+            for (int idx = threadIdx.x; idx < TILE * q_per_row; idx += blockDim.x) {
+                const int it = idx / q_per_row, q = idx - it * q_per_row;
+                const int item = base + it;
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (item < N) val = __ldg(reinterpret_cast<const float4*>(Vtab + (size_t)item * D) + q);
+                *reinterpret_cast<float4*>(sV + it * VS + q * 4) = val;
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < TILE * D4; idx += blockDim.x) {
+                const int it = idx / D4, k = idx - it * D4;
+                const int item = base + it;
+                sV[it * VS + k] = (item < N && k < D) ? __ldg(Vtab + (size_t)item * D + k) : 0.0f;
+            }
+        }
+        __syncthreads();
+
+        float acc[TM][TN];
+#pragma unroll
+        for (int m = 0; m < TM; ++m)
+#pragma unroll
+            for (int n = 0; n < TN; ++n) acc[m][n] = 0.0f;
+        const float* su = sU + warp * TM * D4;
+        for (int k = 0; k < D4; k += 4) {
+            float4 vv[TN], uu[TM];
+#pragma unroll
+            for (int n = 0; n < TN; ++n)
+                vv[n] = *reinterpret_cast<const float4*>(sV + (n * 32 + lane) * VS + k);
+#pragma unroll
+            for (int m = 0; m < TM; ++m) uu[m] = *reinterpret_cast<const float4*>(su + m * D4 + k);
+#pragma unroll
+            for (int m = 0; m < TM; ++m)
+#pragma unroll
+                for (int n = 0; n < TN; ++n) {
+                    float a = acc[m][n];
+                    a = __fmaf_rn(uu[m].x, vv[n].x, a);
+                    a = __fmaf_rn(uu[m].y, vv[n].y, a);
+                    a = __fmaf_rn(uu[m].z, vv[n].z, a);
+                    a = __fmaf_rn(uu[m].w, vv[n].w, a);
+                    acc[m][n] = a;
+                }
+        }
+
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+            if (!live[m]) continue;
+            unsigned maskbits[TN];
+#pragma unroll
+            for (int n = 0; n < TN; ++n) maskbits[n] = 0u;
+            for (;;) {
+                const int p = tr_pos[m] + lane;
+                const int t = (p < tr_len[m]) ? __ldg(train_idx + tr_beg[m] + p) : INT32_MAX;
+                const bool in_tile = t < base + TILE;
+                const int off = t - base;
+#pragma unroll
+                for (int n = 0; n < TN; ++n) {
+                    const unsigned bit = (in_tile && (off >> 5) == n) ? (1u << (off & 31)) : 0u;
+                    maskbits[n] |= __reduce_or_sync(kFull, bit);
+                }
+                const int c = __popc(__ballot_sync(kFull, in_tile));
+                tr_pos[m] += c;
+                if (c < kWarp) break;
+            }
+#pragma unroll
+            for (int n = 0; n < TN; ++n) {
+                const int item = base + n * 32 + lane;
+                const bool ok = item < N && !((maskbits[n] >> lane) & 1u);
+                unsigned cand = __ballot_sync(kFull, ok && acc[m][n] > thr[m]);
+                while (cand) {
+                    const int src = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const float cv = __shfl_sync(kFull, acc[m][n], src);
+                    if (!(cv > thr[m])) continue;            // threshold rose since the ballot
+                    const int ci = base + n * 32 + src;
+                    // insert after every entry >= cv (earlier index first among equals)
+                    const int pos = __popc(__ballot_sync(kFull, lane <= K && top_v[m] >= cv));
+                    const float up_v = __shfl_up_sync(kFull, top_v[m], 1);
+                    const int up_i = __shfl_up_sync(kFull, top_i[m], 1);
+                    if (lane > pos) { top_v[m] = up_v; top_i[m] = up_i; }
+                    if (lane == pos) { top_v[m] = cv; top_i[m] = ci; }
+                    thr[m] = __shfl_sync(kFull, top_v[m], K);
+                }
+            }
+        }
+    }
+
+#pragma unroll
+    for (int m = 0; m < TM; ++m) {
+        if (!live[m]) continue;
+        const int b = user_slot0 + m;
+        // decidable without the heap: K+1 finite, strictly decreasing values
+        const float nxt = __shfl_down_sync(kFull, top_v[m], 1);
+        const bool bad = (lane < K && !(top_v[m] > nxt)) || (lane == K && !(top_v[m] > -INFINITY));
+        if (__ballot_sync(kFull, bad)) {
+            if (lane == 0) slow_rows[atomicAdd(slow_count, 1)] = b;
+            continue;
+        }
+        int* rank = sMet + (warp * TM + m) * 4 * K;
+        if (lane < K) rank[lane] = top_i[m];
+        __syncwarp();
+        if (ranks && lane < K) ranks[(size_t)b * K + lane] = top_i[m];
+        if (results) {
+            const int u = users[b];
+            const int64_t t0 = test_ptr[u];
+            const int T = (int)(test_ptr[u + 1] - t0);
+            int* s_cnt = rank + K;
+            float* s_sum_pre = reinterpret_cast<float*>(s_cnt + K);
+            float* s_dcg = s_sum_pre + K;
+            metrics_for_user(rank, K, test_idx + t0, T, s_cnt, s_sum_pre, s_dcg, M,
                              results + (size_t)b * M * K, lane);
         }
         __syncwarp();
@@ -633,6 +816,17 @@ extern "C" int nrc_arg_topk_host(const float* scores, int32_t rating_len, int32_
                      nullptr, results, false);
 }
 
+// library-owned list of batch rows the fast kernel could not decide: [count, rows...]
+static int32_t* g_slow = nullptr;
+static size_t g_slow_cap = 0;
+static bool g_force_exact = false;
+
+// Test hook: 1 = always use the exact heap-replay kernel (no tie-free fast pass).
+extern "C" int nrc_eval_force_exact(int32_t on) {
+    g_force_exact = on != 0;
+    return NRC_OK;
+}
+
 extern "C" int nrc_eval_mf(const float* user_table, const float* item_table, int32_t dim,
                            int32_t num_items, const int32_t* users, int32_t num_eval_users,
                            const int64_t* train_indptr, const int32_t* train_indices,
@@ -655,14 +849,52 @@ extern "C" int nrc_eval_mf(const float* user_table, const float* item_table, int
                         (size_t)W * TM * (2 * L + 3 * K) * 4;
     NRC_REQUIRE(smem <= 227 * 1024, NRC_E_LIMIT,
                 "dim %d / top_k %d need %zu B of shared memory (> 227 KB)", dim, top_k, smem);
+    cudaStream_t st = as_stream(stream);
     auto kern = eval_mf_kernel<TM, TN, W>;
-    NRC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        227 * 1024));
+    static bool attr_done = false;
+    if (!attr_done) {
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(eval_mf_fast_kernel<8, 2, 8>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(eval_mf_fast_kernel<2, 2, 8>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
     const int grid = (num_eval_users + W * TM - 1) / (W * TM);
-    kern<<<grid, W * 32, smem, as_stream(stream)>>>(user_table, item_table, dim, num_items, users,
-                                                    num_eval_users, train_indptr, train_indices,
-                                                    test_indptr, test_indices, K, L, metric_num,
-                                                    results, ranks);
+    const bool fast = (K + 1 <= 32) && !g_force_exact;
+    if (!fast) {
+        kern<<<grid, W * 32, smem, st>>>(user_table, item_table, dim, num_items, users, num_eval_users,
+                                         train_indptr, train_indices, test_indptr, test_indices, K, L,
+                                         metric_num, results, ranks, nullptr, nullptr);
+        NRC_CUDA_CHECK(cudaGetLastError());
+        return NRC_OK;
+    }
+    // tie-free fast pass, then the exact heap replay for the users it could not decide
+    if ((size_t)num_eval_users + 1 > g_slow_cap) {
+        if (g_slow) NRC_CUDA_CHECK(cudaFree(g_slow));
+        g_slow = nullptr; g_slow_cap = 0;
+        const size_t cap = (size_t)num_eval_users * 2 + 1024;
+        NRC_CUDA_CHECK(cudaMalloc(&g_slow, cap * sizeof(int32_t)));
+        g_slow_cap = cap;
+    }
+    NRC_CUDA_CHECK(cudaMemsetAsync(g_slow, 0, sizeof(int32_t), st));
+    if (num_eval_users <= 148 * 16) {   // few users: 2 per warp => 4x the CTAs
+        constexpr int TMs = 2;
+        const size_t fsmem = ((size_t)W * TMs * D4 + (size_t)TN * 32 * (D4 + 4)) * 4 + (size_t)W * TMs * 4 * K * 4;
+        const int fgrid = (num_eval_users + W * TMs - 1) / (W * TMs);
+        eval_mf_fast_kernel<TMs, TN, W><<<fgrid, W * 32, fsmem, st>>>(
+            user_table, item_table, dim, num_items, users, num_eval_users, train_indptr, train_indices,
+            test_indptr, test_indices, K, metric_num, results, ranks, g_slow, g_slow + 1);
+    } else {
+        const size_t fsmem = ((size_t)W * TM * D4 + (size_t)TN * 32 * (D4 + 4)) * 4 + (size_t)W * TM * 4 * K * 4;
+        eval_mf_fast_kernel<TM, TN, W><<<grid, W * 32, fsmem, st>>>(
+            user_table, item_table, dim, num_items, users, num_eval_users, train_indptr, train_indices,
+            test_indptr, test_indices, K, metric_num, results, ranks, g_slow, g_slow + 1);
+    }
+    NRC_CUDA_CHECK(cudaGetLastError());
+    kern<<<grid, W * 32, smem, st>>>(user_table, item_table, dim, num_items, users, num_eval_users,
+                                     train_indptr, train_indices, test_indptr, test_indices, K, L,
+                                     metric_num, results, ranks, g_slow + 1, g_slow);
     NRC_CUDA_CHECK(cudaGetLastError());
     return NRC_OK;
 }

@@ -92,8 +92,18 @@ def test_empty_batch_and_errors():
         ops.eval_score_matrix(S.double(), ip, ix, ALL, 5)
 
 
-@pytest.mark.parametrize("dim,K", [(64, 20), (32, 10), (16, 5), (10, 20), (128, 50), (7, 3)])
-def test_fused_mf_eval_vs_oracle_ml100k(ml100k, dim, K):
+@pytest.fixture(params=["fast+exact", "exact-only"])
+def eval_mode(request):
+    """nrc_eval_mf's two code paths: tie-free fast pass + heap replay for undecidable users
+    (default) vs heap replay for everybody.  Both must be bit-identical to the oracle."""
+    from neurec_b200 import _lib
+    _lib.load().nrc_eval_force_exact(1 if request.param == "exact-only" else 0)
+    yield request.param
+    _lib.load().nrc_eval_force_exact(0)
+
+
+@pytest.mark.parametrize("dim,K", [(64, 20), (32, 10), (16, 5), (10, 20), (128, 50), (7, 3), (64, 31)])
+def test_fused_mf_eval_vs_oracle_ml100k(ml100k, dim, K, eval_mode):
     """Fused predict+mask+topK+metrics on the real ml-100k split: bit-exact ranks and rows."""
     from neurec_b200 import ops
     d = ml100k
@@ -115,7 +125,7 @@ def test_fused_mf_eval_vs_oracle_ml100k(ml100k, dim, K):
     assert np.array_equal(got.cpu().numpy(), want)
 
 
-def test_fused_mf_eval_ties_and_heavy_masks():
+def test_fused_mf_eval_ties_and_heavy_masks(eval_mode):
     """Integer-valued tables (massive score ties, Pop-like) + users whose train set covers
     most of the catalogue (fewer than 2K unmasked items)."""
     from neurec_b200 import ops
