@@ -33,6 +33,7 @@ __constant__ float c_idcg[kMaxTopK];        // float running sum of the above (i
 __constant__ int c_metric[kMaxMetrics];
 
 static bool g_tables_ready = false;
+static bool g_force_exact = false;   // nrc_eval_force_exact: skip the tie-free fast passes
 
 static int upload_tables() {
     if (g_tables_ready) return NRC_OK;
@@ -200,7 +201,7 @@ template <bool kMetrics>
 __global__ void __launch_bounds__(256)
 eval_rows_kernel(const float* __restrict__ scores, int N, int rows, int K, int L,
                  const int64_t* __restrict__ tptr, const int32_t* __restrict__ tidx, int M,
-                 float* __restrict__ results, int32_t* __restrict__ ranks) {
+                 float* __restrict__ results, int32_t* __restrict__ ranks, int fast) {
     extern __shared__ int smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -215,6 +216,52 @@ eval_rows_kernel(const float* __restrict__ scores, int N, int rows, int K, int L
     float* s_dcg = s_sum_pre + K;
 
     const float* __restrict__ r = scores + (size_t)row * N;
+    if (fast) {
+        // tie-free fast pass (see eval_mf_fast_kernel): running top-(K+1) as a sorted list over
+        // the lanes; if its values end up strictly decreasing and finite the reference's first K
+        // ranks are exactly this list, otherwise fall through to the exact heap replay below.
+        float tv = -INFINITY, fthr = -INFINITY;
+        int ti = -1;
+        for (int base = 0; base < N; base += kWarp * kRowUnroll) {
+            float v[kRowUnroll];
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u) {
+                const int i = base + u * kWarp + lane;
+                v[u] = (i < N) ? __ldcs(r + i) : -INFINITY;
+            }
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u) {
+                unsigned cand = __ballot_sync(kFull, v[u] > fthr);
+                while (cand) {
+                    const int src = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const float cv = __shfl_sync(kFull, v[u], src);
+                    if (!(cv > fthr)) continue;
+                    const int ci = base + u * kWarp + src;
+                    const int pos = __popc(__ballot_sync(kFull, lane <= K && tv >= cv));
+                    const float up_v = __shfl_up_sync(kFull, tv, 1);
+                    const int up_i = __shfl_up_sync(kFull, ti, 1);
+                    if (lane > pos) { tv = up_v; ti = up_i; }
+                    if (lane == pos) { tv = cv; ti = ci; }
+                    fthr = __shfl_sync(kFull, tv, K);
+                }
+            }
+        }
+        const float nxt = __shfl_down_sync(kFull, tv, 1);
+        const bool bad = (lane < K && !(tv > nxt)) || (lane == K && !(tv > -INFINITY));
+        if (!__ballot_sync(kFull, bad)) {
+            if (lane < K) h.idx[lane] = ti;
+            __syncwarp();
+            if (ranks && lane < K) ranks[(size_t)row * K + lane] = ti;
+            if (kMetrics) {
+                const int64_t t0 = tptr[row];
+                const int T = (int)(tptr[row + 1] - t0);
+                metrics_for_user(h.idx, K, tidx + t0, T, s_cnt, s_sum_pre, s_dcg, M,
+                                 results + (size_t)row * M * K, lane);
+            }
+            return;
+        }
+    }
     for (int i = lane; i < L; i += kWarp) {  // evaluate.h:40: first L indices seed the heap
         h.idx[i] = i;
         h.val[i] = r[i];
@@ -672,16 +719,17 @@ static int launch_rows(const float* scores, int N, int rows, int K, int L, const
     while (warps > 1 && warps * stride_bytes > 96 * 1024) warps >>= 1;
     const size_t smem = (size_t)warps * stride_bytes;
     const int grid = (rows + warps - 1) / warps;
+    const int fast = (K + 1 <= 32 && K < N && !g_force_exact) ? 1 : 0;
     if (metrics) {
         NRC_CUDA_CHECK(cudaFuncSetAttribute(eval_rows_kernel<true>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         eval_rows_kernel<true><<<grid, warps * 32, smem, st>>>(scores, N, rows, K, L, tptr, tidx, M,
-                                                              results, ranks);
+                                                              results, ranks, fast);
     } else {
         NRC_CUDA_CHECK(cudaFuncSetAttribute(eval_rows_kernel<false>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         eval_rows_kernel<false><<<grid, warps * 32, smem, st>>>(scores, N, rows, K, L, tptr, tidx,
-                                                               M, results, ranks);
+                                                               M, results, ranks, fast);
     }
     NRC_CUDA_CHECK(cudaGetLastError());
     return NRC_OK;
@@ -819,7 +867,6 @@ extern "C" int nrc_arg_topk_host(const float* scores, int32_t rating_len, int32_
 // library-owned list of batch rows the fast kernel could not decide: [count, rows...]
 static int32_t* g_slow = nullptr;
 static size_t g_slow_cap = 0;
-static bool g_force_exact = false;
 
 // Test hook: 1 = always use the exact heap-replay kernel (no tie-free fast pass).
 extern "C" int nrc_eval_force_exact(int32_t on) {

@@ -19,7 +19,17 @@ def dev(a, dtype=None):
     return t.cuda()
 
 
-def test_kat2_golden_device_and_host(golden_eval):
+@pytest.fixture(params=["fast+exact", "exact-only"])
+def eval_mode(request):
+    """nrc_eval_mf's two code paths: tie-free fast pass + heap replay for undecidable users
+    (default) vs heap replay for everybody.  Both must be bit-identical to the oracle."""
+    from neurec_b200 import _lib
+    _lib.load().nrc_eval_force_exact(1 if request.param == "exact-only" else 0)
+    yield request.param
+    _lib.load().nrc_eval_force_exact(0)
+
+
+def test_kat2_golden_device_and_host(golden_eval, eval_mode):
     from neurec_b200 import ops
     g = golden_eval
     res, ranks = ops.eval_score_matrix(dev(g["kat2_scores"]), dev(g["kat2_truth_indptr"]),
@@ -34,7 +44,7 @@ def test_kat2_golden_device_and_host(golden_eval):
     assert np.array_equal(res_h, g["kat2_out"]) and np.array_equal(ranks_h, g["kat2_top5"])
 
 
-def test_tie_order_golden(golden_eval):
+def test_tie_order_golden(golden_eval, eval_mode):
     from neurec_b200 import ops
     g = golden_eval
     assert np.array_equal(ops.arg_topk(torch.zeros(1, 40, device="cuda"), 5).cpu().numpy(),
@@ -52,7 +62,7 @@ def test_tie_order_golden(golden_eval):
 
 
 @pytest.mark.parametrize("trial", range(12))
-def test_score_matrix_random_vs_oracle(trial):
+def test_score_matrix_random_vs_oracle(trial, eval_mode):
     """Ragged shapes, ties, -inf rows, N < 2K, N == K, N % 32 != 0, K > 32."""
     from neurec_b200 import ops
     rs = np.random.RandomState(100 + trial)
@@ -90,16 +100,6 @@ def test_empty_batch_and_errors():
         ops.eval_score_matrix(S, ip, ix, ALL, 60)          # top_k > rating_len
     with pytest.raises(TypeError):
         ops.eval_score_matrix(S.double(), ip, ix, ALL, 5)
-
-
-@pytest.fixture(params=["fast+exact", "exact-only"])
-def eval_mode(request):
-    """nrc_eval_mf's two code paths: tie-free fast pass + heap replay for undecidable users
-    (default) vs heap replay for everybody.  Both must be bit-identical to the oracle."""
-    from neurec_b200 import _lib
-    _lib.load().nrc_eval_force_exact(1 if request.param == "exact-only" else 0)
-    yield request.param
-    _lib.load().nrc_eval_force_exact(0)
 
 
 @pytest.mark.parametrize("dim,K", [(64, 20), (32, 10), (16, 5), (10, 20), (128, 50), (7, 3), (64, 31)])

@@ -214,7 +214,8 @@ def test_fused_single_pass_sgd_vs_oracle(dim):
     assert np.abs(dV.cpu().numpy()[7] - tr2.V[7]).max() < 3e-2 * np.abs(tr2.V[7] - V[7]).max() + 1e-6
     assert np.abs(dU.cpu().numpy() - tr2.U).max() < 1e-5
     with pytest.raises(_NrcLimit):
-        ops.mf_bpr_sgd_fused(dev(U[:, :48].copy()), dev(V[:, :48].copy()), dev(users), dev(pos), dev(neg), 0.1, 0.0, dl)
+        U48, V48 = _tables(nu, ni, 48, 1)
+        ops.mf_bpr_sgd_fused(dev(U48), dev(V48), dev(users), dev(pos), dev(neg), 0.1, 0.0, dl)
 
 
 from neurec_b200._lib import NrcError as _NrcLimit  # noqa: E402
