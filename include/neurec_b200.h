@@ -136,6 +136,8 @@ int nrc_eval_mf(const float* user_table, const float* item_table, int32_t dim,
  * replay; both give the reference's ranking bit for bit.  on != 0 forces the heap replay for
  * every user (test / debugging hook). */
 int nrc_eval_force_exact(int32_t on);
+/* How many users of the last nrc_eval_mf call needed the heap replay (host int32 out). */
+int nrc_eval_last_undecided(int32_t* count_host);
 
 /* MF.predict(user_ids, None), model/general_recommender/MF.py:120-122 (np.matmul(U[users], V.T))
  * and LightGCN.predict, LightGCN.py:187-189, materialised: scores f32 [num_rows, num_items]

@@ -678,16 +678,50 @@ eval_mf_fast_kernel(const float* __restrict__ Utab, const float* __restrict__ Vt
 // np.mean(axis=0) of a C-contiguous [rows, cols] fp32 matrix: numpy adds row after row into
 // the fp32 output (no pairwise blocking along a non-contiguous reduction axis), then divides
 // by the row count in fp32.  One thread per column, rows in order.
-__global__ void mean_rows_kernel(const float* __restrict__ a, int64_t rows, int cols,
-                                 float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// Block = 256 threads owning 32 columns: tiles of 256 rows x 32 columns are staged through
+// shared memory by all threads (many loads in flight), then lanes 0..31 add their column's 256
+// values strictly in row order -- the same sequence of fp32 additions as numpy.
+constexpr int kMeanTileRows = 128;
+__global__ void __launch_bounds__(256)
+mean_rows_kernel(const float* __restrict__ a, int64_t rows, int cols, float* __restrict__ out) {
+    __shared__ float tile[2][kMeanTileRows][33];
+    const int c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // ty: 8 row groups
+    const int c = c0 + tx;
     float acc = 0.0f;
-    if (rows > 0) {
-        acc = a[c];
-        for (int64_t r = 1; r < rows; ++r) acc = __fadd_rn(acc, a[r * cols + c]);
+    bool first = true;
+    const int64_t n_tiles = (rows + kMeanTileRows - 1) / kMeanTileRows;
+    auto load = [&](int buf, int64_t t) {
+        const int64_t r0 = t * kMeanTileRows;
+#pragma unroll 8
+        for (int rr = ty; rr < kMeanTileRows; rr += 8) {
+            const int64_t r = r0 + rr;
+            tile[buf][rr][tx] = (r < rows && c < cols) ? __ldg(a + r * cols + c) : 0.0f;
+        }
+    };
+    if (n_tiles > 0) load(0, 0);
+    __syncthreads();
+    for (int64_t t = 0; t < n_tiles; ++t) {
+        const int buf = (int)(t & 1);
+        if (t + 1 < n_tiles && ty != 0) load(buf ^ 1, t + 1);     // warps 1..7 prefetch
+        if (ty == 0) {
+            const int64_t r0 = t * kMeanTileRows;
+            const int n = (int)((rows - r0 < kMeanTileRows) ? (rows - r0) : kMeanTileRows);
+            int rr = 0;
+            if (first) { acc = tile[buf][0][tx]; rr = 1; first = false; }
+            for (; rr < n; ++rr) acc = __fadd_rn(acc, tile[buf][rr][tx]);
+            if (t + 1 < n_tiles) {                                 // warp 0's share of the prefetch
+                const int64_t r1 = (t + 1) * kMeanTileRows;
+#pragma unroll 8
+                for (int q = 0; q < kMeanTileRows; q += 8) {
+                    const int64_t r = r1 + q;
+                    tile[buf ^ 1][q][tx] = (r < rows && c < cols) ? __ldg(a + r * cols + c) : 0.0f;
+                }
+            }
+        }
+        __syncthreads();
     }
-    out[c] = __fdiv_rn(acc, (float)rows);
+    if (ty == 0 && c < cols) out[c] = __fdiv_rn(acc, (float)rows);
 }
 
 static int check_metrics(const int32_t* metric_host, int metric_num) {
@@ -874,6 +908,16 @@ extern "C" int nrc_eval_force_exact(int32_t on) {
     return NRC_OK;
 }
 
+// Number of users of the last nrc_eval_mf call that the tie-free pass could not decide (ties
+// among the K+1 best scores, or fewer than K+1 unmasked items) and that were re-ranked by the
+// heap replay.  Synchronises the device.
+extern "C" int nrc_eval_last_undecided(int32_t* count_host) {
+    NRC_REQUIRE(count_host != nullptr, NRC_E_VALUE, "count_host is NULL");
+    *count_host = 0;
+    if (g_slow) NRC_CUDA_CHECK(cudaMemcpy(count_host, g_slow, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return NRC_OK;
+}
+
 extern "C" int nrc_eval_mf(const float* user_table, const float* item_table, int32_t dim,
                            int32_t num_items, const int32_t* users, int32_t num_eval_users,
                            const int64_t* train_indptr, const int32_t* train_indices,
@@ -904,6 +948,8 @@ extern "C" int nrc_eval_mf(const float* user_table, const float* item_table, int
         NRC_CUDA_CHECK(cudaFuncSetAttribute(eval_mf_fast_kernel<8, 2, 8>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         NRC_CUDA_CHECK(cudaFuncSetAttribute(eval_mf_fast_kernel<2, 2, 8>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(eval_mf_kernel<1, 2, 8>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
@@ -939,9 +985,15 @@ extern "C" int nrc_eval_mf(const float* user_table, const float* item_table, int
             test_indptr, test_indices, K, metric_num, results, ranks, g_slow, g_slow + 1);
     }
     NRC_CUDA_CHECK(cudaGetLastError());
-    kern<<<grid, W * 32, smem, st>>>(user_table, item_table, dim, num_items, users, num_eval_users,
-                                     train_indptr, train_indices, test_indptr, test_indices, K, L,
-                                     metric_num, results, ranks, g_slow + 1, g_slow);
+    {   // undecided users are rare: one user per warp so that the replay spreads over many SMs
+        constexpr int TMx = 1;
+        const size_t xsmem = ((size_t)W * TMx * D4 + (size_t)TN * 32 * (D4 + 4)) * 4 +
+                             (size_t)W * TMx * (2 * L + 3 * K) * 4;
+        const int xgrid = (num_eval_users + W * TMx - 1) / (W * TMx);
+        eval_mf_kernel<TMx, TN, W><<<xgrid, W * 32, xsmem, st>>>(
+            user_table, item_table, dim, num_items, users, num_eval_users, train_indptr, train_indices,
+            test_indptr, test_indices, K, L, metric_num, results, ranks, g_slow + 1, g_slow);
+    }
     NRC_CUDA_CHECK(cudaGetLastError());
     return NRC_OK;
 }
@@ -1016,8 +1068,7 @@ extern "C" int nrc_mean_rows(const float* results, int64_t num_rows, int32_t num
                              float* out, void* stream) {
     NRC_REQUIRE(num_cols >= 0 && num_rows >= 0, NRC_E_VALUE, "negative shape");
     if (num_cols == 0) return NRC_OK;
-    mean_rows_kernel<<<(num_cols + 127) / 128, 128, 0, as_stream(stream)>>>(results, num_rows,
-                                                                           num_cols, out);
+    mean_rows_kernel<<<(num_cols + 31) / 32, 256, 0, as_stream(stream)>>>(results, num_rows, num_cols, out);
     NRC_CUDA_CHECK(cudaGetLastError());
     return NRC_OK;
 }
