@@ -89,6 +89,14 @@ def synth_gowalla(seed=7):
             "train_indices": ti, "test_indptr": sp_, "test_indices": si}
 
 
+def profiled_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, or None."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.isfile(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -766,7 +774,7 @@ def measure(w, K, W, world, rank, windows, with_cpu=True):
                  "items": w.d["num_items"], "top_k": w.eval_k, "metrics": 5, "ms": eval_ms,
                  "sharding": "users over %d rank(s)" % world},
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": profiled_traffic(dom), "peak_source": peak_src,
                      "bytes_per_launch": kb[dom], "bytes_note": kn[dom], "launch_us": kt[dom] * 1e6,
                      "all_kernels": {k: {"us": kt[k] * 1e6, "bytes": kb[k], "GBps": kb[k] / kt[k] / 1e9}
                                      for k in kt},
@@ -864,7 +872,8 @@ def measure_synth_sgd(K, W, world, rank, windows, with_cpu=True):
                       "l2": "tables (6.1 GB) and the per-step id arrays are far larger than L2; every step uses "
                             "fresh ids"},
            "roofline": {"kernel": "mf_bpr_sgd_fused_kernel", "bound": "hbm", "achieved": nbytes / kt / 1e9,
-                        "peak": peak, "unit": "GB/s", "frac": nbytes / kt / 1e9 / peak, "traffic": None,
+                        "peak": peak, "unit": "GB/s", "frac": nbytes / kt / 1e9 / peak,
+                        "traffic": profiled_traffic("mf_bpr_sgd_fused_kernel"),
                         "peak_source": peak_src, "bytes_per_launch": nbytes, "launch_us": kt * 1e6,
                         "bytes_note": "SURVEY.md 8(d): (24*d + 12) B per triplet x 2^20 triplets",
                         "timing": "CUDA events around the K timed launches (one kernel per step)"}}

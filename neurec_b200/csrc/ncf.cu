@@ -227,42 +227,56 @@ ncf_sample_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ u
 // work in every layer (the k-range of a layer is split over thread groups and the partial sums
 // are combined in a fixed order), weight rows are read fully coalesced in both directions.
 // ----------------------------------------------------------------------------------------
+// Weights are pre-loaded into registers (one batch of independent loads at the start of a pass),
+// so the dependent chain layer -> layer never waits on global memory.
 template <int IN, int OUT>
-__device__ __forceinline__ void fast_dense_fwd(const float* __restrict__ W, const float* __restrict__ bias,
-                                               const float* a_in, float* a_out, float* part, int tid) {
-    constexpr int G = kNcfThreads / OUT, KPG = IN / G;
-    const int j = tid % OUT, g = tid / OUT;
-    float acc = 0.0f;
+struct FwdW {
+    static constexpr int G = kNcfThreads / OUT, KPG = IN / G;
+    float w[KPG];
+    float bias;
+    __device__ __forceinline__ void load(const float* __restrict__ W, const float* __restrict__ B, int tid) {
+        const int j = tid % OUT, g = tid / OUT;
 #pragma unroll
-    for (int kk = 0; kk < KPG; ++kk) {
-        const int k = g * KPG + kk;
-        acc = fmaf(a_in[k], __ldg(W + k * OUT + j), acc);
+        for (int kk = 0; kk < KPG; ++kk) w[kk] = __ldg(W + (g * KPG + kk) * OUT + j);
+        bias = (tid < OUT) ? __ldg(B + tid) : 0.0f;
     }
-    part[tid] = acc;
-    __syncthreads();
-    if (tid < OUT) {
-        float s = __ldg(bias + tid);
+    __device__ __forceinline__ void run(const float* a_in, float* a_out, float* part, int tid) const {
+        const int g = tid / OUT;
+        float acc = 0.0f;
 #pragma unroll
-        for (int q = 0; q < G; ++q) s += part[q * OUT + tid];
-        a_out[tid] = fmaxf(s, 0.0f);  // tf.nn.relu
+        for (int kk = 0; kk < KPG; ++kk) acc = fmaf(a_in[g * KPG + kk], w[kk], acc);
+        part[tid] = acc;
+        __syncthreads();
+        if (tid < OUT) {
+            float s = bias;
+#pragma unroll
+            for (int q = 0; q < G; ++q) s += part[q * OUT + tid];
+            a_out[tid] = fmaxf(s, 0.0f);  // tf.nn.relu
+        }
+        __syncthreads();
     }
-    __syncthreads();
-}
+};
 
 template <int IN, int OUT, bool MASK>
-__device__ __forceinline__ void fast_dense_bwd(const float* __restrict__ W, const float* d_out,
-                                               const float* a_in, float* d_in, int tid) {
-    constexpr int TPR = kNcfThreads / IN, JPT = OUT / TPR;   // threads per input row
-    const int k = tid / TPR, jq = tid % TPR;
-    const float* wr = W + k * OUT + jq * JPT;
-    float s = 0.0f;
+struct BwdW {
+    static constexpr int TPR = kNcfThreads / IN, JPT = OUT / TPR;   // threads per input row
+    float w[JPT];
+    __device__ __forceinline__ void load(const float* __restrict__ W, int tid) {
+        const int k = tid / TPR, jq = tid % TPR;
 #pragma unroll
-    for (int jj = 0; jj < JPT; ++jj) s = fmaf(__ldg(wr + jj), d_out[jq * JPT + jj], s);
+        for (int jj = 0; jj < JPT; ++jj) w[jj] = __ldg(W + k * OUT + jq * JPT + jj);
+    }
+    __device__ __forceinline__ void run(const float* d_out, const float* a_in, float* d_in, int tid) const {
+        const int k = tid / TPR, jq = tid % TPR;
+        float s = 0.0f;
 #pragma unroll
-    for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
-    if (jq == 0) d_in[k] = MASK ? ((a_in[k] > 0.0f) ? s : 0.0f) : s;
-    __syncthreads();
-}
+        for (int jj = 0; jj < JPT; ++jj) s = fmaf(w[jj], d_out[jq * JPT + jj], s);
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+        if (jq == 0) d_in[k] = MASK ? ((a_in[k] > 0.0f) ? s : 0.0f) : s;
+        __syncthreads();
+    }
+};
 
 template <int IN0, int O0, int O1, int O2>
 __global__ void __launch_bounds__(kNcfThreads)
@@ -283,6 +297,8 @@ ncf_sample_fast_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restric
     const int u = users[b];
     const int it[2] = {items[b], pairwise ? reinterpret_cast<const int32_t*>(third)[b] : 0};
 
+    FwdW<IN0, O0> f0; FwdW<O0, O1> f1; FwdW<O1, O2> f2;
+    BwdW<O1, O2, true> g2, h2; BwdW<O0, O1, true> g1, h1; BwdW<IN0, O0, false> g0, h0;   // pass 0 / pass 1
     float yhat[2] = {0.0f, 0.0f};
     for (int p = 0; p < passes; ++p) {
         float* act = sAct + p * ACT;
@@ -292,10 +308,15 @@ ncf_sample_fast_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restric
         if (tid < MD) act[tid] = P.mlp_user[(size_t)u * MD + tid];
         else if (tid < IN0) act[tid] = P.mlp_item[(size_t)it[p] * MD + (tid - MD)];
         __syncthreads();
-        const float* tw = P.dense + (size_t)((p == 1 && S.n_towers == 2) ? 1 : 0) * S.tower_size;
-        fast_dense_fwd<IN0, O0>(tw + W0, tw + B0, act, act + A1, part, tid);
-        fast_dense_fwd<O0, O1>(tw + W1, tw + B1, act + A1, act + A2, part, tid);
-        fast_dense_fwd<O1, O2>(tw + W2, tw + B2, act + A2, act + A3, part, tid);
+        if (p == 0 || S.n_towers == 2) {   // (re)load this pass' tower into registers
+            const float* tw = P.dense + (size_t)((p == 1) ? 1 : 0) * S.tower_size;
+            f0.load(tw + W0, tw + B0, tid); f1.load(tw + W1, tw + B1, tid); f2.load(tw + W2, tw + B2, tid);
+            if (p == 0) { g2.load(tw + W2, tid); g1.load(tw + W1, tid); g0.load(tw + W0, tid); }
+            else { h2.load(tw + W2, tid); h1.load(tw + W1, tid); h0.load(tw + W0, tid); }
+        }
+        f0.run(act, act + A1, part, tid);
+        f1.run(act + A1, act + A2, part, tid);
+        f2.run(act + A2, act + A3, part, tid);
         const float s = (tid < O2) ? act[A3 + tid] : 0.0f;
         yhat[p] = block_sum_128(mf + s, red, tid);
     }
@@ -327,14 +348,19 @@ ncf_sample_fast_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restric
     float sq_mf = 0.f, sq_mlp = 0.f;
     for (int p = 0; p < passes; ++p) {
         const float gp = (p == 0) ? g : -g;
-        const float* tw = P.dense + (size_t)((p == 1 && S.n_towers == 2) ? 1 : 0) * S.tower_size;
         float* act = sAct + p * ACT;
         float* del = sDel + p * ACT;
         if (tid < O2) del[A3 + tid] = (act[A3 + tid] > 0.0f) ? gp : 0.0f;
         __syncthreads();
-        fast_dense_bwd<O1, O2, true>(tw + W2, del + A3, act + A2, del + A2, tid);
-        fast_dense_bwd<O0, O1, true>(tw + W1, del + A2, act + A1, del + A1, tid);
-        fast_dense_bwd<IN0, O0, false>(tw + W0, del + A1, act, del, tid);
+        if (p == 0 || S.n_towers == 1) {
+            g2.run(del + A3, act + A2, del + A2, tid);
+            g1.run(del + A2, act + A1, del + A1, tid);
+            g0.run(del + A1, act, del, tid);
+        } else {
+            h2.run(del + A3, act + A2, del + A2, tid);
+            h1.run(del + A2, act + A1, del + A1, tid);
+            h0.run(del + A1, act, del, tid);
+        }
         for (int k = tid; k < S.mf_dim; k += kNcfThreads) {
             const float pu = P.mf_user[(size_t)u * S.mf_dim + k];
             const float qi = P.mf_item[(size_t)it[p] * S.mf_dim + k];
