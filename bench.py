@@ -975,7 +975,20 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def lift_cpu_thread_limits():
+    """torchrun exports OMP_NUM_THREADS=1 to its children; the CPU reference legs must be free to
+    use every host core (BLAS/OpenMP pools are resized at run time through threadpoolctl)."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+    except Exception:
+        pass
+
+
 def main():
+    lift_cpu_thread_limits()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1570)
