@@ -139,6 +139,26 @@ int nrc_eval_force_exact(int32_t on);
 /* How many users of the last nrc_eval_mf call needed the heap replay (host int32 out). */
 int nrc_eval_last_undecided(int32_t* count_host);
 
+/* nrc_eval_mf for large catalogues (BASELINE config 4) with the score step on the 5th-gen
+ * tensor cores: bf16 copies of the tables, tcgen05.mma (128 users x 256 items x k16) with fp32
+ * accumulators in Tensor Memory, a per-user running threshold with a rigorous error margin to
+ * keep every item that can still belong to the exact top K+1, then exact fp32 re-scoring of the
+ * candidates and the same tie-aware selection as nrc_eval_mf -- results are bit-identical to
+ * nrc_eval_mf.  dim in {64,128,192,256}, top_k <= 31; cand_cap = candidate slots per user
+ * (0 = 1024; users that overflow fall back to the exact heap-replay kernel). */
+int nrc_eval_mf_tc(const float* user_table, const float* item_table, int32_t dim,
+                   int32_t num_items, const int32_t* users, int32_t num_eval_users,
+                   const int64_t* train_indptr, const int32_t* train_indices,
+                   const int64_t* test_indptr, const int32_t* test_indices,
+                   const int32_t* metric_host, int32_t metric_num, int32_t top_k, int32_t cand_cap,
+                   float* results, int32_t* ranks, void* stream);
+
+/* Self-test of the tcgen05 / TMEM building block used by the tensor-core candidate pass:
+ * out f32 [128, 256] = a bf16 [128, k] . b bf16 [256, k]^T (k multiple of 16, <= 256);
+ * swizzle = 0: no-swizzle K-major operand layout, 1: SWIZZLE_128B (k % 64 == 0). */
+int nrc_tc_gemm_debug(const void* a_bf16, const void* b_bf16, int32_t k, int32_t swizzle, float* out,
+                      void* stream);
+
 /* MF.predict(user_ids, None), model/general_recommender/MF.py:120-122 (np.matmul(U[users], V.T))
  * and LightGCN.predict, LightGCN.py:187-189, materialised: scores f32 [num_rows, num_items]
  * with the same fp32 FMA chain over k the fused evaluator uses. */

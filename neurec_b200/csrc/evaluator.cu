@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_eval.cuh"
 
 namespace nrc {
 
@@ -1074,6 +1075,135 @@ extern "C" int nrc_mask_rows(float* scores, int32_t rating_len, int32_t num_rows
     mask_rows_kernel<<<blocks, threads, 0, as_stream(stream)>>>(scores, rating_len, num_rows, users,
                                                                 train_indptr, train_indices);
     NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+namespace nrc {
+// Finalisation of the tensor-core candidate pass: one warp per evaluated user re-scores the
+// user's candidates (ascending item order) with the oracle's fp32 FMA chain and runs the same
+// tie-aware fast selection as eval_mf_fast_kernel; undecidable users and users whose candidate
+// buffer overflowed go to the heap-replay list.
+__global__ void __launch_bounds__(256)
+eval_tc_finalize_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, int D,
+                        const int32_t* __restrict__ users, int num_eval,
+                        const int64_t* __restrict__ test_ptr, const int32_t* __restrict__ test_idx,
+                        const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int cap,
+                        int K, int M, float* __restrict__ results, int32_t* __restrict__ ranks,
+                        int32_t* __restrict__ slow_count, int32_t* __restrict__ slow_rows) {
+    extern __shared__ int smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= num_eval) return;
+    float* su = reinterpret_cast<float*>(smem) + warp * (D + 4 * K);
+    int* rank = reinterpret_cast<int*>(su + D);
+    const int cnt = cand_cnt[row];
+    if (cnt > cap) {
+        if (lane == 0) slow_rows[atomicAdd(slow_count, 1)] = row;
+        return;
+    }
+    const int u = users[row];
+    for (int k = lane; k < D; k += kWarp) su[k] = Utab[(size_t)u * D + k];
+    __syncwarp();
+    float tv = -INFINITY, thr = -INFINITY;
+    int ti = -1;
+    for (int base = 0; base < cnt; base += kWarp) {
+        const int idx = base + lane;
+        const int item = (idx < cnt) ? cand[(size_t)row * cap + idx] : -1;
+        float s = -INFINITY;
+        if (item >= 0) {
+            const float* v = Vtab + (size_t)item * D;
+            float acc = 0.0f;
+            for (int k = 0; k < D; ++k) acc = __fmaf_rn(su[k], __ldg(v + k), acc);
+            s = acc;
+        }
+        unsigned c = __ballot_sync(kFull, item >= 0 && s > thr);
+        while (c) {
+            const int src = __ffs(c) - 1;
+            c &= c - 1;
+            const float cv = __shfl_sync(kFull, s, src);
+            const int ci = __shfl_sync(kFull, item, src);
+            if (!(cv > thr)) continue;
+            const int pos = __popc(__ballot_sync(kFull, lane <= K && tv >= cv));
+            const float up_v = __shfl_up_sync(kFull, tv, 1);
+            const int up_i = __shfl_up_sync(kFull, ti, 1);
+            if (lane > pos) { tv = up_v; ti = up_i; }
+            if (lane == pos) { tv = cv; ti = ci; }
+            thr = __shfl_sync(kFull, tv, K);
+        }
+    }
+    const float nxt = __shfl_down_sync(kFull, tv, 1);
+    const bool bad = (lane < K && !(tv > nxt)) || (lane == K && !(tv > -INFINITY));
+    if (__ballot_sync(kFull, bad)) {
+        if (lane == 0) slow_rows[atomicAdd(slow_count, 1)] = row;
+        return;
+    }
+    if (lane < K) rank[lane] = ti;
+    __syncwarp();
+    if (ranks && lane < K) ranks[(size_t)row * K + lane] = ti;
+    if (results) {
+        const int64_t t0 = test_ptr[u];
+        const int T = (int)(test_ptr[u + 1] - t0);
+        int* s_cnt = rank + K;
+        float* s_sum_pre = reinterpret_cast<float*>(s_cnt + K);
+        float* s_dcg = s_sum_pre + K;
+        metrics_for_user(rank, K, test_idx + t0, T, s_cnt, s_sum_pre, s_dcg, M, results + (size_t)row * M * K, lane);
+    }
+}
+}  // namespace nrc
+
+// nrc_eval_mf with the score step on the tensor cores (tcgen05 / TMEM), for large catalogues:
+// bf16 candidate pass -> exact fp32 re-scoring -> tie-aware selection -> metrics.  Same results
+// as nrc_eval_mf, bit for bit.  cand_cap: candidate slots per user (0 = default 1024).
+extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, int32_t dim,
+                              int32_t num_items, const int32_t* users, int32_t num_eval_users,
+                              const int64_t* train_indptr, const int32_t* train_indices,
+                              const int64_t* test_indptr, const int32_t* test_indices,
+                              const int32_t* metric_host, int32_t metric_num, int32_t top_k,
+                              int32_t cand_cap, float* results, int32_t* ranks, void* stream) {
+    NRC_REQUIRE(top_k > 0 && top_k + 1 <= 32, NRC_E_LIMIT, "the tensor-core path needs top_k in [1, 31]");
+    NRC_REQUIRE(num_items > top_k, NRC_E_VALUE, "num_items (%d) must be > top_k (%d)", num_items, top_k);
+    int rc = check_metrics(metric_host, metric_num);
+    if (rc) return rc;
+    if (num_eval_users <= 0) return NRC_OK;
+    const int K = top_k, cap = cand_cap > 0 ? cand_cap : 1024;
+    cudaStream_t st = as_stream(stream);
+    const int32_t *cand = nullptr, *cnt = nullptr;
+    rc = tc::run_candidates(user_table, item_table, dim, num_items, users, num_eval_users, train_indptr,
+                            train_indices, K, cap, &cand, &cnt, st);
+    if (rc) return rc;
+    if ((size_t)num_eval_users + 1 > g_slow_cap) {
+        if (g_slow) NRC_CUDA_CHECK(cudaFree(g_slow));
+        g_slow = nullptr; g_slow_cap = 0;
+        const size_t c2 = (size_t)num_eval_users * 2 + 1024;
+        NRC_CUDA_CHECK(cudaMalloc(&g_slow, c2 * sizeof(int32_t)));
+        g_slow_cap = c2;
+    }
+    NRC_CUDA_CHECK(cudaMemsetAsync(g_slow, 0, sizeof(int32_t), st));
+    {
+        const int warps = 8;
+        const size_t smem = (size_t)warps * (dim + 4 * K) * 4;
+        eval_tc_finalize_kernel<<<(num_eval_users + warps - 1) / warps, warps * 32, smem, st>>>(
+            user_table, item_table, dim, users, num_eval_users, test_indptr, test_indices, cand, cnt, cap, K,
+            metric_num, results, ranks, g_slow, g_slow + 1);
+        NRC_CUDA_CHECK(cudaGetLastError());
+    }
+    {   // heap replay for undecided / overflowed users (rare)
+        constexpr int TMx = 1, TN = 2, W = 8;
+        const int L = (2 * K < num_items) ? 2 * K : num_items;
+        const int D4 = (dim + 3) & ~3;
+        const size_t xsmem = ((size_t)W * TMx * D4 + (size_t)TN * 32 * (D4 + 4)) * 4 + (size_t)W * TMx * (2 * L + 3 * K) * 4;
+        static bool attr_done = false;
+        if (!attr_done) {
+            NRC_CUDA_CHECK(cudaFuncSetAttribute(eval_mf_kernel<1, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                227 * 1024));
+            attr_done = true;
+        }
+        const int xgrid = (num_eval_users + W * TMx - 1) / (W * TMx);
+        eval_mf_kernel<TMx, TN, W><<<xgrid, W * 32, xsmem, st>>>(
+            user_table, item_table, dim, num_items, users, num_eval_users, train_indptr, train_indices,
+            test_indptr, test_indices, K, L, metric_num, results, ranks, g_slow + 1, g_slow);
+        NRC_CUDA_CHECK(cudaGetLastError());
+    }
     return NRC_OK;
 }
 

@@ -1,0 +1,478 @@
+// Tensor-core (tcgen05 / TMEM) candidate pass of the evaluator for large catalogues
+// (BASELINE config 4: 1 M users x 10 M items x d=128, SURVEY.md 7.1 "tensor-core path").
+//
+// Replaces the score step of evaluator/backend/cpp/uni_evaluator.py:134 (model.predict = U.V^T,
+// MF.py:120-122) for catalogues where an fp32 SIMT contraction is 30x off the machine's
+// throughput.  The ranking still has to be the reference's, bit for bit, so the tensor cores
+// only SELECT: scores are computed from bf16 copies of the tables (exact products, fp32
+// accumulation in TMEM), every item whose approximate score can still belong to the exact top
+// K+1 (a rigorous margin, see below) becomes a candidate, and the candidates are re-scored with
+// the oracle's fp32 FMA chain and ranked by the tie-aware selection of evaluator.cu.
+//
+// Blackwell specifics used here (sm_100a only):
+//   * tcgen05.mma.cta_group::1.kind::f16, M=128 (users) x N=256 (items) x K=16 per instruction,
+//     issued by ONE thread; operands in shared memory described by UMMA descriptors (K-major,
+//     no swizzle: 8x16-byte core matrices, LBO = distance between the two K-chunks of a k-step,
+//     SBO = distance between 8-row groups);
+//   * the fp32 accumulator tile lives in Tensor Memory (tcgen05.alloc, 256 columns per buffer,
+//     two buffers so that the epilogue of tile t overlaps the MMAs of tile t+1);
+//   * tcgen05.commit -> mbarrier hands the accumulator to the epilogue warps, which read it with
+//     tcgen05.ld.32x32b (warp w owns TMEM lanes 32w..32w+31 = 32 users, one user per thread).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace nrc {
+namespace tc {
+
+constexpr int kM = 128;        // users per CTA tile (UMMA M)
+constexpr int kN = 256;        // items per tile (UMMA N)
+constexpr int kUmmaK = 16;     // bf16 elements per tcgen05.mma k-step
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// shared-memory writes made with ordinary stores must be fenced before the tensor core (async
+// proxy) reads them
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute/arch/mma_sm100_desc.hpp bit layout):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout type = 0.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 0) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(layout_type & 7u) << 61;
+    return d;
+}
+
+// SWIZZLE_128B K-major layout (layout type 2): the tile is cut along K into blocks of 64 bf16
+// (128 B); inside a block row r occupies 128 contiguous bytes at r*128 and its 16-byte chunk c
+// sits at position c ^ (r & 7); 8-row groups are 1024 B apart (SBO), LBO is unused (1).  A warp
+// copying 4 rows x 8 chunks reads 4 x 128 contiguous global bytes and stores conflict-free.
+__device__ __forceinline__ void load_tile_sw128(uint8_t* smem, const __nv_bfloat16* __restrict__ g, int rows,
+                                                int valid_rows, int K, int tid, int nthreads) {
+    const int chunks = K >> 3;
+    for (int idx = tid; idx < rows * chunks; idx += nthreads) {
+        const int row = idx / chunks, cg = idx - row * chunks;
+        const int blk = cg >> 3, c = cg & 7;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (row < valid_rows) v = __ldg(reinterpret_cast<const uint4*>(g + (size_t)row * K) + cg);
+        *reinterpret_cast<uint4*>(smem + (size_t)blk * rows * 128 + (size_t)row * 128 + ((c ^ (row & 7)) << 4)) = v;
+    }
+}
+
+// descriptors of k-step s (16 bf16) for a SWIZZLE_128B tile of `rows` rows
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t tile_base, int rows, int s) {
+    return make_smem_desc(tile_base + (uint32_t)(s >> 2) * rows * 128 + (uint32_t)(s & 3) * 32, 16, 1024, 2);
+}
+
+// Instruction descriptor for kind::f16: D = f32 (c_format 1 @ bit 4), A = B = bf16 (format 1 @ bits
+// 7 and 10), both K-major (bits 15, 16 = 0), N >> 3 @ bit 17, M >> 4 @ bit 24.
+__host__ __device__ constexpr uint32_t make_instr_desc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread (lane) gets its row's columns [c, c+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Copy a [rows, K] row-major bf16 tile from global memory into the canonical no-swizzle K-major
+// layout: 16-byte chunk (row, kc) -> smem[(kc * rows + row) * 16 B].  Rows >= valid_rows are zero.
+__device__ __forceinline__ void load_tile_kmajor(uint8_t* smem, const __nv_bfloat16* __restrict__ g, int rows,
+                                                 int valid_rows, int K, int tid, int nthreads) {
+    const int chunks = K >> 3;   // 8 bf16 per 16-byte chunk
+    for (int idx = tid; idx < rows * chunks; idx += nthreads) {
+        const int row = idx % rows, kc = idx / rows;   // consecutive threads -> consecutive rows: conflict-free smem
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (row < valid_rows) v = __ldg(reinterpret_cast<const uint4*>(g + (size_t)row * K) + kc);
+        *reinterpret_cast<uint4*>(smem + ((size_t)kc * rows + row) * 16) = v;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Stage-1 self-test kernel: out[128, 256] = A[128, K] . B[256, K]^T through tcgen05/TMEM.
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192)
+tc_gemm_debug_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, int K,
+                     float* __restrict__ out, int swizzle) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;                          // [K/8][128] x 16 B
+    uint8_t* sB = sA + (size_t)kM * K * 2;       // [K/8][256] x 16 B
+    __shared__ uint64_t bar_full;
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (swizzle) {
+        load_tile_sw128(sA, A, kM, kM, K, tid, blockDim.x);
+        load_tile_sw128(sB, B, kN, kN, K, tid, blockDim.x);
+    } else {
+        load_tile_kmajor(sA, A, kM, kM, K, tid, blockDim.x);
+        load_tile_kmajor(sB, B, kN, kN, K, tid, blockDim.x);
+    }
+    fence_async_smem();
+    if (tid == 0) {
+        mbar_init(&bar_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {   // one warp allocates (and later frees) the accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"((uint32_t)kN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+
+    if (warp == 4 && lane == 0) {
+        const uint32_t idesc = make_instr_desc(kM, kN);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        for (int s = 0; s < K / kUmmaK; ++s) {
+            const uint64_t ad = swizzle ? sw128_desc(a0, kM, s) : make_smem_desc(a0 + s * 2 * kM * 16, kM * 16, 128);
+            const uint64_t bd = swizzle ? sw128_desc(b0, kN, s) : make_smem_desc(b0 + s * 2 * kN * 16, kN * 16, 128);
+            umma_bf16(tmem_d, ad, bd, idesc, s > 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_full);
+    }
+    if (warp < 4) {
+        mbar_wait(&bar_full, 0);
+        tc_fence_after();
+        const int row = warp * 32 + lane;
+        for (int c = 0; c < kN; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) out[(size_t)row * kN + c + i] = v[i];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)kN));
+}
+
+}  // namespace tc
+}  // namespace nrc
+
+using namespace nrc;
+
+// Test hook: out f32 [128, 256] = A bf16 [128, K] . B bf16 [256, K]^T  (K multiple of 16, <= 256).
+extern "C" int nrc_tc_gemm_debug(const void* a_bf16, const void* b_bf16, int32_t k, int32_t swizzle, float* out,
+                                 void* stream) {
+    NRC_REQUIRE(k >= 16 && k <= 256 && (k % 16) == 0, NRC_E_LIMIT, "k must be a multiple of 16 in [16, 256]");
+    NRC_REQUIRE(!swizzle || (k % 64) == 0, NRC_E_LIMIT, "the SWIZZLE_128B layout needs k % 64 == 0");
+    const size_t smem = (size_t)(tc::kM + tc::kN) * k * 2;
+    NRC_CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    tc::tc_gemm_debug_kernel<<<1, 192, smem, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a_bf16), reinterpret_cast<const __nv_bfloat16*>(b_bf16), k, out,
+        swizzle);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+// =========================================================================================
+// Candidate pass + finalisation
+// =========================================================================================
+namespace nrc {
+namespace tc {
+
+constexpr int kThreads = 288;          // warps 0-3 epilogue, warp 4 MMA issuer, warps 5-8 producers
+constexpr int kProducerThreads = 128;
+constexpr int kMaxList = 32;           // K + 1 <= 32
+
+struct CandArgs {
+    const __nv_bfloat16* Ub;   // [num_eval, D] bf16 rows of the users being evaluated (gathered)
+    const __nv_bfloat16* Vb;   // [N, D] bf16 item table
+    const float* margin;       // [num_eval] 2 * eps_u (see tc_prepare_users_kernel)
+    const int32_t* users;      // [num_eval] user ids (train CSR is indexed by user id)
+    const int64_t* train_ptr; const int32_t* train_idx;
+    int num_eval, N, D, K, cap;
+    int32_t* cand;             // [num_eval, cap] candidate item ids, ascending
+    int32_t* cand_cnt;         // [num_eval] number of candidates seen (> cap => overflow)
+};
+
+__global__ void __launch_bounds__(kThreads, 1) tc_candidate_kernel(const CandArgs P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int D = P.D;
+    uint8_t* sA = smem;                                   // 128 x D bf16, SWIZZLE_128B blocks
+    uint8_t* sB0 = sA + (size_t)kM * D * 2;               // 2 stages of 256 x D bf16
+    uint8_t* sB1 = sB0 + (size_t)kN * D * 2;
+    float* sList = reinterpret_cast<float*>(sB1 + (size_t)kN * D * 2);   // [128][K+1]
+    __shared__ uint64_t full_b[2], empty_b[2], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = blockIdx.x * kM;
+    const int valid_rows = min(kM, P.num_eval - row0);
+    const int T = (P.N + kN - 1) / kN;
+    const int K1 = P.K + 1;
+
+    load_tile_sw128(sA, P.Ub + (size_t)row0 * D, kM, valid_rows, D, tid, kThreads);
+    for (int i = tid; i < kM * K1; i += kThreads) sList[i] = -INFINITY;
+    fence_async_smem();
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full_b[i], kProducerThreads);
+            mbar_init(&empty_b[i], 1);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp >= 5) {
+        // ---------------- producers: item tiles -> shared memory ----------------
+        const int ptid = tid - 5 * 32;
+        for (int t = 0; t < T; ++t) {
+            const int s = t & 1, ph = (t >> 1) & 1;
+            mbar_wait(&empty_b[s], ph ^ 1);
+            load_tile_sw128(s ? sB1 : sB0, P.Vb + (size_t)t * kN * D, kN, min(kN, P.N - t * kN), D, ptid,
+                            kProducerThreads);
+            fence_async_smem();
+            mbar_arrive(&full_b[s]);
+        }
+    } else if (warp == 4) {
+        // ---------------- MMA issuer (one thread) ----------------
+        if (lane == 0) {
+            const uint32_t idesc = make_instr_desc(kM, kN);
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB0), b1 = smem_u32(sB1);
+            for (int t = 0; t < T; ++t) {
+                const int s = t & 1, ph = (t >> 1) & 1;
+                mbar_wait(&full_b[s], ph);
+                mbar_wait(&acc_empty[s], ph ^ 1);
+                tc_fence_after();
+                const uint32_t td = tmem_base + (uint32_t)s * kN;
+                for (int ks = 0; ks < D / kUmmaK; ++ks)
+                    umma_bf16(td, sw128_desc(a0, kM, ks), sw128_desc(s ? b1 : b0, kN, ks), idesc, ks > 0 ? 1u : 0u);
+                umma_commit(&empty_b[s]);
+                umma_commit(&acc_full[s]);
+            }
+        }
+    } else {
+        // ---------------- epilogue: one user per thread ----------------
+        const int r = warp * 32 + lane;              // row inside the tile == TMEM lane
+        const int row = row0 + r;
+        const bool live = row < P.num_eval;
+        float* lst = sList + r * K1;
+        const float margin = live ? P.margin[row] : 0.0f;
+        const int u = live ? P.users[row] : 0;
+        const int64_t tb = live ? P.train_ptr[u] : 0;
+        const int tl = live ? (int)(P.train_ptr[u + 1] - tb) : 0;
+        int32_t* my_cand = P.cand + (size_t)row * P.cap;
+        float thr = -INFINITY, thr_m = -INFINITY;
+        int cnt = 0;
+        for (int t = 0; t < T; ++t) {
+            const int s = t & 1, ph = (t >> 1) & 1;
+            mbar_wait(&acc_full[s], ph);
+            tc_fence_after();
+            for (int c = 0; c < kN; c += 32) {
+                float v[32];
+                __syncwarp();   // the candidate branch below diverges; tcgen05.ld needs the whole warp
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * kN + c), v);
+                if (live) {
+                    const int item0 = t * kN + c;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (v[i] > thr_m && item0 + i < P.N) {
+                            const int item = item0 + i;
+                            if (!sorted_contains(P.train_idx + tb, tl, item)) {
+                                if (cnt < P.cap) my_cand[cnt] = item;
+                                ++cnt;
+                                if (v[i] > thr) {   // keep the running (K+1)-th best approximate score
+                                    int j = P.K;
+                                    while (j > 0 && lst[j - 1] < v[i]) { lst[j] = lst[j - 1]; --j; }
+                                    lst[j] = v[i];
+                                    thr = lst[P.K];
+                                    thr_m = thr - margin;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[s]);
+        }
+        if (live) P.cand_cnt[row] = cnt;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+// bf16 copy of the item table + largest row norm (positive floats order like their bit patterns)
+__global__ void tc_prepare_items_kernel(const float* __restrict__ V, int64_t N, int D, __nv_bfloat16* __restrict__ Vb,
+                                        unsigned int* __restrict__ vmax_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float best = 0.0f;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += warps) {
+        float sq = 0.0f;
+        for (int k = lane; k < D; k += 32) {
+            const float x = V[i * D + k];
+            Vb[i * D + k] = __float2bfloat16_rn(x);
+            sq = fmaf(x, x, sq);
+        }
+        sq = warp_sum(sq);
+        best = fmaxf(best, sqrtf(sq));
+    }
+    if (lane == 0) atomicMax(vmax_bits, __float_as_uint(best));
+}
+
+// bf16 rows of the evaluated users + their candidate margin
+//   |s_bf16 - s_exact| <= (2^-8 + 2^-12) |u| |v|   (bf16 rounding of both factors, fp32 accumulation)
+//   margin = 2 * eps, eps = (2^-8 + 2^-11) * |u| * max_i |v_i| * (1 + 2^-10)
+__global__ void tc_prepare_users_kernel(const float* __restrict__ U, const int32_t* __restrict__ users, int num_eval,
+                                        int D, const unsigned int* __restrict__ vmax_bits,
+                                        __nv_bfloat16* __restrict__ Ub, float* __restrict__ margin) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= num_eval) return;
+    const float* u = U + (size_t)users[row] * D;
+    float sq = 0.0f;
+    for (int k = lane; k < D; k += 32) {
+        const float x = u[k];
+        Ub[(size_t)row * D + k] = __float2bfloat16_rn(x);
+        sq = fmaf(x, x, sq);
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) {
+        const float vmax = __uint_as_float(*vmax_bits);
+        margin[row] = 2.0f * (0.00390625f + 0.00048828125f) * sqrtf(sq) * vmax * 1.001f;
+    }
+}
+
+}  // namespace tc
+}  // namespace nrc
+
+#include "tc_eval.cuh"
+
+namespace nrc {
+namespace tc {
+
+// library-owned workspace, grown on demand (never inside a stream capture)
+static void* g_ws = nullptr;
+static size_t g_ws_bytes = 0;
+
+int run_candidates(const float* U, const float* V, int D, int N, const int32_t* users, int num_eval,
+                   const int64_t* train_ptr, const int32_t* train_idx, int K, int cap,
+                   const int32_t** cand, const int32_t** cand_cnt, cudaStream_t st) {
+    NRC_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, NRC_E_LIMIT,
+                "the tensor-core pass needs dim in {64, 128, 192, 256} (got %d)", D);
+    NRC_REQUIRE(K + 1 <= kMaxList, NRC_E_LIMIT, "the tensor-core pass needs top_k <= %d", kMaxList - 1);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t rows_pad = (size_t)((num_eval + kM - 1) / kM) * kM;
+    const size_t o_vb = 0;
+    const size_t o_ub = o_vb + up((size_t)N * D * 2);
+    const size_t o_margin = o_ub + up(rows_pad * D * 2);
+    const size_t o_vmax = o_margin + up(rows_pad * 4);
+    const size_t o_cnt = o_vmax + 256;
+    const size_t o_cand = o_cnt + up(rows_pad * 4);
+    const size_t total = o_cand + up(rows_pad * (size_t)cap * 4);
+    if (total > g_ws_bytes) {
+        if (g_ws) NRC_CUDA_CHECK(cudaFree(g_ws));
+        g_ws = nullptr; g_ws_bytes = 0;
+        NRC_CUDA_CHECK(cudaMalloc(&g_ws, total));
+        g_ws_bytes = total;
+    }
+    uint8_t* ws = reinterpret_cast<uint8_t*>(g_ws);
+    __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(ws + o_vb);
+    __nv_bfloat16* Ub = reinterpret_cast<__nv_bfloat16*>(ws + o_ub);
+    float* margin = reinterpret_cast<float*>(ws + o_margin);
+    unsigned int* vmax = reinterpret_cast<unsigned int*>(ws + o_vmax);
+    int32_t* cnt = reinterpret_cast<int32_t*>(ws + o_cnt);
+    int32_t* cd = reinterpret_cast<int32_t*>(ws + o_cand);
+
+    NRC_CUDA_CHECK(cudaMemsetAsync(vmax, 0, 4, st));
+    tc_prepare_items_kernel<<<sm_count() * 8, 256, 0, st>>>(V, N, D, Vb, vmax);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    tc_prepare_users_kernel<<<(num_eval * 32 + 255) / 256, 256, 0, st>>>(U, users, num_eval, D, vmax, Ub, margin);
+    NRC_CUDA_CHECK(cudaGetLastError());
+
+    CandArgs P{Ub, Vb, margin, users, train_ptr, train_idx, num_eval, N, D, K, cap, cd, cnt};
+    size_t smem = (size_t)(kM + 2 * kN) * D * 2 + (size_t)kM * (K + 1) * 4;
+    if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
+    NRC_REQUIRE(smem <= 220 * 1024, NRC_E_LIMIT, "tensor-core pass needs %zu B of shared memory", smem);
+    static bool attr_done = false;
+    if (!attr_done) {
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            220 * 1024));
+        attr_done = true;
+    }
+    tc_candidate_kernel<<<(num_eval + kM - 1) / kM, kThreads, smem, st>>>(P);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    *cand = cd;
+    *cand_cnt = cnt;
+    return NRC_OK;
+}
+
+}  // namespace tc
+}  // namespace nrc

@@ -119,6 +119,22 @@ def eval_mf(user_table, item_table, users, train_indptr, train_indices, test_ind
     return (res, ranks) if return_ranks else res
 
 
+def eval_mf_tc(user_table, item_table, users, train_indptr, train_indices, test_indptr, test_indices,
+               metric, top_k, return_ranks=False, cand_cap=0):
+    """eval_mf with the score step on the tensor cores (tcgen05 candidate pass + exact re-score);
+    bit-identical results, meant for catalogues of millions of items."""
+    N, D = item_table.shape
+    B = users.numel()
+    m = _metric_arr(metric)
+    res = torch.empty((B, len(m) * top_k), dtype=torch.float32, device=users.device)
+    ranks = torch.empty((B, top_k), dtype=torch.int32, device=users.device) if return_ranks else None
+    check(_lib.load().nrc_eval_mf_tc(_p(user_table), _p(item_table), D, N, _p(users), B, _p(train_indptr),
+                                     _p(train_indices), _p(test_indptr), _p(test_indices), m.ctypes.data,
+                                     len(m), top_k, int(cand_cap), _p(res), _p(ranks), _stream()))
+    _count(5)
+    return (res, ranks) if return_ranks else res
+
+
 def mf_scores(user_table, item_table, users):
     """MF.predict(users, None) on device: [len(users), num_items] fp32 (MF.py:120-122)."""
     _req(user_table, torch.float32, "user_table"); _req(item_table, torch.float32, "item_table")

@@ -1,0 +1,99 @@
+"""GPU parity tests of the tensor-core (tcgen05 / TMEM) evaluator path: bit-identical ranks and
+metric rows to the oracle (and therefore to nrc_eval_mf), including masks, ties and candidate
+overflow (which must fall back to the exact heap replay)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import random_csr
+
+pytestmark = pytest.mark.gpu
+ALL = [1, 2, 3, 4, 5]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("K,sw", [(64, 0), (128, 0), (64, 1), (128, 1), (256, 1)])
+def test_tcgen05_gemm_building_block(K, sw):
+    from neurec_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(K + sw)
+    A = torch.randn(128, K, device="cuda", generator=g).bfloat16()
+    B = torch.randn(256, K, device="cuda", generator=g).bfloat16()
+    out = torch.zeros(128, 256, device="cuda")
+    _lib.check(lib.nrc_tc_gemm_debug(ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()), K, sw,
+                                     ctypes.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().T          # bf16 products are exact; only the fp32 accumulation differs
+    assert (out.double() - ref).abs().max().item() < 2e-4
+
+
+def _problem(nu, ni, dim, seed, scale=0.1, int_tables=False):
+    rs = np.random.RandomState(seed)
+    if int_tables:
+        U = rs.randint(-2, 3, size=(nu, dim)).astype(np.float32)
+        V = rs.randint(-2, 3, size=(ni, dim)).astype(np.float32)
+    else:
+        U = (rs.randn(nu, dim) * scale).astype(np.float32)
+        V = (rs.randn(ni, dim) * scale).astype(np.float32)
+    tp, ti = random_csr(rs, nu, ni, rs.randint(1, 80, nu))
+    sp, si = random_csr(rs, nu, ni, rs.randint(1, 12, nu))
+    return U, V, tp, ti, sp, si
+
+
+@pytest.mark.parametrize("nu,ni,dim,K", [(300, 5000, 64, 20), (129, 2049, 128, 10), (500, 12345, 128, 31),
+                                         (77, 300, 64, 5)])
+def test_tc_eval_bit_exact_vs_oracle(nu, ni, dim, K):
+    from neurec_b200 import ops
+    U, V, tp, ti, sp, si = _problem(nu, ni, dim, nu + ni)
+    users = np.random.RandomState(1).permutation(nu).astype(np.int32)
+    tip = np.zeros(nu + 1, np.int64); tip[1:] = np.cumsum(sp[users + 1] - sp[users])
+    tix = np.concatenate([si[sp[u]:sp[u + 1]] for u in users])
+    want, wranks = oracle.eval_mf(U, V, users, tp, ti, tip, tix, ALL, K, thread_num=4, return_ranks=True)
+    args = (dev(U), dev(V), dev(users), dev(tp), dev(ti), dev(sp), dev(si), ALL, K)
+    got, ranks = ops.eval_mf_tc(*args, return_ranks=True)
+    assert np.array_equal(ranks.cpu().numpy(), wranks)
+    assert np.array_equal(got.cpu().numpy(), want)
+    got2, ranks2 = ops.eval_mf(*args, return_ranks=True)               # and identical to the SIMT path
+    assert torch.equal(ranks, ranks2) and torch.equal(got, got2)
+
+
+def test_tc_eval_ties_and_overflow_fall_back_to_heap_replay():
+    from neurec_b200 import ops
+    # integer tables: massive exact ties -> undecidable users -> heap replay must reproduce libstdc++ order
+    U, V, tp, ti, sp, si = _problem(140, 900, 64, 5, int_tables=True)
+    users = np.arange(140, dtype=np.int32)
+    want, wranks = oracle.eval_mf(U, V, users, tp, ti, sp, si, ALL, 20, return_ranks=True)
+    args = (dev(U), dev(V), dev(users), dev(tp), dev(ti), dev(sp), dev(si), ALL, 20)
+    got, ranks = ops.eval_mf_tc(*args, return_ranks=True)
+    assert np.array_equal(ranks.cpu().numpy(), wranks) and np.array_equal(got.cpu().numpy(), want)
+    # tiny candidate buffer: (almost) every user overflows and is re-done exactly
+    U, V, tp, ti, sp, si = _problem(150, 4000, 128, 6)
+    users = np.arange(150, dtype=np.int32)
+    want, wranks = oracle.eval_mf(U, V, users, tp, ti, sp, si, ALL, 20, return_ranks=True)
+    got, ranks = ops.eval_mf_tc(dev(U), dev(V), dev(users), dev(tp), dev(ti), dev(sp), dev(si), ALL, 20,
+                                return_ranks=True, cand_cap=24)
+    assert np.array_equal(ranks.cpu().numpy(), wranks) and np.array_equal(got.cpu().numpy(), want)
+
+
+def test_tc_eval_large_scale_matches_simt_path():
+    """200 k items x 2 000 users, d=128: the tensor-core path must agree bit for bit with the SIMT
+    fused evaluator (itself pinned on the oracle) -- checks the error-margin argument at scale,
+    with score magnitudes that make bf16 rounding errors comparable to the top-K gaps."""
+    from neurec_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    nu, ni, dim, K = 2000, 200_000, 128, 20
+    U = torch.randn(nu, dim, device="cuda", generator=g) * 0.1
+    V = torch.randn(ni, dim, device="cuda", generator=g) * 0.1
+    rs = np.random.RandomState(3)
+    tp, ti = random_csr(rs, nu, ni, np.full(nu, 50))
+    sp, si = random_csr(rs, nu, ni, np.full(nu, 10))
+    users = torch.arange(nu, dtype=torch.int32, device="cuda")
+    a = ops.eval_mf_tc(U, V, users, dev(tp), dev(ti), dev(sp), dev(si), ALL, K, return_ranks=True)
+    b = ops.eval_mf(U, V, users, dev(tp), dev(ti), dev(sp), dev(si), ALL, K, return_ranks=True)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
