@@ -136,16 +136,18 @@ int nrc_eval_mf(const float* user_table, const float* item_table, int32_t dim,
  * replay; both give the reference's ranking bit for bit.  on != 0 forces the heap replay for
  * every user (test / debugging hook). */
 int nrc_eval_force_exact(int32_t on);
-/* How many users of the last nrc_eval_mf call needed the heap replay (host int32 out). */
+/* How many users of the last nrc_eval_mf / nrc_eval_mf_tc call needed a heap replay (host int32 out). */
 int nrc_eval_last_undecided(int32_t* count_host);
 
 /* nrc_eval_mf for large catalogues (BASELINE config 4) with the score step on the 5th-gen
  * tensor cores: bf16 copies of the tables, tcgen05.mma (128 users x 256 items x k16) with fp32
- * accumulators in Tensor Memory, a per-user running threshold with a rigorous error margin to
- * keep every item that can still belong to the exact top K+1, then exact fp32 re-scoring of the
- * candidates and the same tie-aware selection as nrc_eval_mf -- results are bit-identical to
- * nrc_eval_mf.  dim in {64,128,192,256}, top_k <= 31; cand_cap = candidate slots per user
- * (0 = 1024; users that overflow fall back to the exact heap-replay kernel). */
+ * accumulators in Tensor Memory, a per-user running threshold (the 2*top_k-th best score so far,
+ * the reference's heap root, evaluate.h:38-41) with a rigorous error margin to keep every item
+ * that can enter the reference's heap, then exact fp32 re-scoring of the candidates, the same
+ * tie-aware selection as nrc_eval_mf and -- for users with ties -- the libstdc++ heap replayed
+ * over the first 2*top_k items + the candidates.  Results are bit-identical to nrc_eval_mf.
+ * dim in {64,128,192,256}, top_k <= 31; cand_cap = candidate slots per user (0 = 2048; users
+ * that overflow fall back to the full-catalogue heap-replay kernel). */
 int nrc_eval_mf_tc(const float* user_table, const float* item_table, int32_t dim,
                    int32_t num_items, const int32_t* users, int32_t num_eval_users,
                    const int64_t* train_indptr, const int32_t* train_indices,

@@ -903,6 +903,8 @@ extern "C" int nrc_arg_topk_host(const float* scores, int32_t rating_len, int32_
 // library-owned list of batch rows the fast kernel could not decide: [count, rows...]
 static int32_t* g_slow = nullptr;
 static size_t g_slow_cap = 0;
+static int32_t* g_replay = nullptr;   // tensor-core path: users decided by the candidate-list heap replay
+static bool g_last_was_tc = false;
 
 // Test hook: 1 = always use the exact heap-replay kernel (no tie-free fast pass).
 extern "C" int nrc_eval_force_exact(int32_t on) {
@@ -917,6 +919,11 @@ extern "C" int nrc_eval_last_undecided(int32_t* count_host) {
     NRC_REQUIRE(count_host != nullptr, NRC_E_VALUE, "count_host is NULL");
     *count_host = 0;
     if (g_slow) NRC_CUDA_CHECK(cudaMemcpy(count_host, g_slow, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (g_last_was_tc && g_replay) {
+        int32_t r = 0;
+        NRC_CUDA_CHECK(cudaMemcpy(&r, g_replay, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        *count_host += r;
+    }
     return NRC_OK;
 }
 
@@ -934,6 +941,7 @@ extern "C" int nrc_eval_mf(const float* user_table, const float* item_table, int
     int rc = check_metrics(metric_host, metric_num);
     if (rc) return rc;
     if (num_eval_users <= 0) return NRC_OK;
+    g_last_was_tc = false;
     const int K = top_k;
     const int L = (2 * K < num_items) ? 2 * K : num_items;
     const int D4 = (dim + 3) & ~3;
@@ -1086,60 +1094,103 @@ namespace nrc {
 __global__ void __launch_bounds__(256)
 eval_tc_finalize_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, int D,
                         const int32_t* __restrict__ users, int num_eval,
+                        const int64_t* __restrict__ train_ptr, const int32_t* __restrict__ train_idx,
                         const int64_t* __restrict__ test_ptr, const int32_t* __restrict__ test_idx,
                         const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int cap,
-                        int K, int M, float* __restrict__ results, int32_t* __restrict__ ranks,
-                        int32_t* __restrict__ slow_count, int32_t* __restrict__ slow_rows) {
+                        int K, int L, int M, int force_exact, float* __restrict__ results,
+                        int32_t* __restrict__ ranks, int32_t* __restrict__ slow_count,
+                        int32_t* __restrict__ slow_rows, int32_t* __restrict__ replay_count) {
     extern __shared__ int smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= num_eval) return;
-    float* su = reinterpret_cast<float*>(smem) + warp * (D + 4 * K);
+    float* su = reinterpret_cast<float*>(smem) + warp * ((D + 4 * K + 2 * L + 3) & ~3);   // float4 reads
     int* rank = reinterpret_cast<int*>(su + D);
     const int cnt = cand_cnt[row];
-    if (cnt > cap) {
+    if (cnt > cap) {   // candidate buffer overflowed: full-catalogue heap replay (eval_mf_kernel)
         if (lane == 0) slow_rows[atomicAdd(slow_count, 1)] = row;
         return;
     }
     const int u = users[row];
     for (int k = lane; k < D; k += kWarp) su[k] = Utab[(size_t)u * D + k];
     __syncwarp();
-    float tv = -INFINITY, thr = -INFINITY;
-    int ti = -1;
-    for (int base = 0; base < cnt; base += kWarp) {
-        const int idx = base + lane;
-        const int item = (idx < cnt) ? cand[(size_t)row * cap + idx] : -1;
-        float s = -INFINITY;
-        if (item >= 0) {
-            const float* v = Vtab + (size_t)item * D;
-            float acc = 0.0f;
-            for (int k = 0; k < D; ++k) acc = __fmaf_rn(su[k], __ldg(v + k), acc);
-            s = acc;
+    const float4* su4 = reinterpret_cast<const float4*>(su);
+    const int D4 = D >> 2;   // the tensor-core path requires D % 64 == 0
+    auto exact_score = [&](int item) {   // the oracle's fp32 FMA chain, k ascending
+        const float4* v = reinterpret_cast<const float4*>(Vtab + (size_t)item * D);
+        float acc = 0.0f;
+#pragma unroll 4
+        for (int q = 0; q < D4; ++q) {
+            const float4 b = __ldg(v + q);
+            const float4 a = su4[q];
+            acc = __fmaf_rn(a.x, b.x, acc);
+            acc = __fmaf_rn(a.y, b.y, acc);
+            acc = __fmaf_rn(a.z, b.z, acc);
+            acc = __fmaf_rn(a.w, b.w, acc);
         }
-        unsigned c = __ballot_sync(kFull, item >= 0 && s > thr);
-        while (c) {
-            const int src = __ffs(c) - 1;
-            c &= c - 1;
-            const float cv = __shfl_sync(kFull, s, src);
-            const int ci = __shfl_sync(kFull, item, src);
-            if (!(cv > thr)) continue;
-            const int pos = __popc(__ballot_sync(kFull, lane <= K && tv >= cv));
-            const float up_v = __shfl_up_sync(kFull, tv, 1);
-            const int up_i = __shfl_up_sync(kFull, ti, 1);
-            if (lane > pos) { tv = up_v; ti = up_i; }
-            if (lane == pos) { tv = cv; ti = ci; }
-            thr = __shfl_sync(kFull, tv, K);
+        return acc;
+    };
+    const int32_t* crow = cand + (size_t)row * cap;
+    bool undecided = force_exact != 0;
+    if (!undecided) {
+        float tv = -INFINITY, thr = -INFINITY;
+        int ti = -1;
+        for (int base = 0; base < cnt; base += kWarp) {
+            const int idx = base + lane;
+            const int item = (idx < cnt) ? crow[idx] : -1;
+            const float s = (item >= 0) ? exact_score(item) : -INFINITY;
+            unsigned c = __ballot_sync(kFull, item >= 0 && s > thr);
+            while (c) {
+                const int src = __ffs(c) - 1;
+                c &= c - 1;
+                const float cv = __shfl_sync(kFull, s, src);
+                const int ci = __shfl_sync(kFull, item, src);
+                if (!(cv > thr)) continue;
+                const int pos = __popc(__ballot_sync(kFull, lane <= K && tv >= cv));
+                const float up_v = __shfl_up_sync(kFull, tv, 1);
+                const int up_i = __shfl_up_sync(kFull, ti, 1);
+                if (lane > pos) { tv = up_v; ti = up_i; }
+                if (lane == pos) { tv = cv; ti = ci; }
+                thr = __shfl_sync(kFull, tv, K);
+            }
         }
+        const float nxt = __shfl_down_sync(kFull, tv, 1);
+        const bool bad = (lane < K && !(tv > nxt)) || (lane == K && !(tv > -INFINITY));
+        undecided = __ballot_sync(kFull, bad) != 0u;
+        if (!undecided && lane < K) rank[lane] = ti;
     }
-    const float nxt = __shfl_down_sync(kFull, tv, 1);
-    const bool bad = (lane < K && !(tv > nxt)) || (lane == K && !(tv > -INFINITY));
-    if (__ballot_sync(kFull, bad)) {
-        if (lane == 0) slow_rows[atomicAdd(slow_count, 1)] = row;
-        return;
+    if (undecided) {
+        // Ties (or fewer than K+1 finite scores): replay the reference's heap (evaluate.h:33-47)
+        // over the only elements that can change it -- the first L items, which seed it, and the
+        // candidates, a superset of every later element that beats the heap root when offered.
+        Heap h;
+        h.idx = rank + 4 * K;
+        h.val = reinterpret_cast<float*>(h.idx + L);
+        const int64_t tr0 = train_ptr[u];
+        const int64_t trn = train_ptr[u + 1] - tr0;
+        for (int i = lane; i < L; i += kWarp) {
+            float s = exact_score(i);
+            if (sorted_contains(train_idx + tr0, trn, i)) s = -INFINITY;
+            h.idx[i] = i;
+            h.val[i] = s;
+        }
+        __syncwarp();
+        if (lane == 0) heap_make(h, L);
+        __syncwarp();
+        float thr = h.val[0];
+        for (int base = 0; base < cnt; base += kWarp) {
+            const int idx = base + lane;
+            const int item = (idx < cnt) ? crow[idx] : -1;
+            const bool ok = item >= L;
+            const float s = ok ? exact_score(item) : -INFINITY;
+            thr = offer_candidates(h, L, s, item, ok, thr, lane);
+        }
+        if (lane == 0) { heap_sort(h, L); atomicAdd(replay_count, 1); }
+        __syncwarp();
+        if (lane < K) rank[lane] = h.idx[lane];
     }
-    if (lane < K) rank[lane] = ti;
     __syncwarp();
-    if (ranks && lane < K) ranks[(size_t)row * K + lane] = ti;
+    if (ranks && lane < K) ranks[(size_t)row * K + lane] = rank[lane];
     if (results) {
         const int64_t t0 = test_ptr[u];
         const int T = (int)(test_ptr[u + 1] - t0);
@@ -1165,11 +1216,13 @@ extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, 
     int rc = check_metrics(metric_host, metric_num);
     if (rc) return rc;
     if (num_eval_users <= 0) return NRC_OK;
-    const int K = top_k, cap = cand_cap > 0 ? cand_cap : 1024;
+    g_last_was_tc = true;
+    const int K = top_k, cap = cand_cap > 0 ? cand_cap : 2048;
+    const int L = (2 * K < num_items) ? 2 * K : num_items;   // evaluate.h:38 heap size
     cudaStream_t st = as_stream(stream);
     const int32_t *cand = nullptr, *cnt = nullptr;
     rc = tc::run_candidates(user_table, item_table, dim, num_items, users, num_eval_users, train_indptr,
-                            train_indices, K, cap, &cand, &cnt, st);
+                            train_indices, L, cap, &cand, &cnt, st);
     if (rc) return rc;
     if ((size_t)num_eval_users + 1 > g_slow_cap) {
         if (g_slow) NRC_CUDA_CHECK(cudaFree(g_slow));
@@ -1179,17 +1232,19 @@ extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, 
         g_slow_cap = c2;
     }
     NRC_CUDA_CHECK(cudaMemsetAsync(g_slow, 0, sizeof(int32_t), st));
+    if (!g_replay) NRC_CUDA_CHECK(cudaMalloc(&g_replay, sizeof(int32_t)));
+    NRC_CUDA_CHECK(cudaMemsetAsync(g_replay, 0, sizeof(int32_t), st));
     {
         const int warps = 8;
-        const size_t smem = (size_t)warps * (dim + 4 * K) * 4;
+        const size_t smem = (size_t)warps * ((dim + 4 * K + 2 * L + 3) & ~3) * 4;
         eval_tc_finalize_kernel<<<(num_eval_users + warps - 1) / warps, warps * 32, smem, st>>>(
-            user_table, item_table, dim, users, num_eval_users, test_indptr, test_indices, cand, cnt, cap, K,
-            metric_num, results, ranks, g_slow, g_slow + 1);
+            user_table, item_table, dim, users, num_eval_users, train_indptr, train_indices, test_indptr,
+            test_indices, cand, cnt, cap, K, L, metric_num, g_force_exact ? 1 : 0, results, ranks, g_slow,
+            g_slow + 1, g_replay);
         NRC_CUDA_CHECK(cudaGetLastError());
     }
-    {   // heap replay for undecided / overflowed users (rare)
+    {   // full-catalogue heap replay for users whose candidate buffer overflowed (rare)
         constexpr int TMx = 1, TN = 2, W = 8;
-        const int L = (2 * K < num_items) ? 2 * K : num_items;
         const int D4 = (dim + 3) & ~3;
         const size_t xsmem = ((size_t)W * TMx * D4 + (size_t)TN * 32 * (D4 + 4)) * 4 + (size_t)W * TMx * (2 * L + 3 * K) * 4;
         static bool attr_done = false;

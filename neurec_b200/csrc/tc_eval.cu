@@ -90,6 +90,24 @@ __device__ __forceinline__ void load_tile_sw128(uint8_t* smem, const __nv_bfloat
     }
 }
 
+// Same layout, filled with cp.async (LDGSTS): no register staging, so a producer thread puts its
+// whole share of the tile in flight before waiting (rows >= valid_rows are zero-filled through
+// the src-size operand).  Caller: cp_async_wait_all(); fence_async_smem(); arrive.
+__device__ __forceinline__ void load_tile_sw128_async(uint8_t* smem, const __nv_bfloat16* __restrict__ g, int rows,
+                                                      int valid_rows, int K, int tid, int nthreads) {
+    const int chunks = K >> 3;
+    const uint32_t sbase = smem_u32(smem);
+    for (int idx = tid; idx < rows * chunks; idx += nthreads) {
+        const int row = idx / chunks, cg = idx - row * chunks;
+        const int blk = cg >> 3, c = cg & 7;
+        const uint32_t dst = sbase + (uint32_t)blk * rows * 128 + (uint32_t)row * 128 + ((c ^ (row & 7)) << 4);
+        const bool ok = row < valid_rows;
+        const void* src = ok ? (const void*)(reinterpret_cast<const uint4*>(g + (size_t)row * K) + cg) : (const void*)g;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // descriptors of k-step s (16 bf16) for a SWIZZLE_128B tile of `rows` rows
 __device__ __forceinline__ uint64_t sw128_desc(uint32_t tile_base, int rows, int s) {
     return make_smem_desc(tile_base + (uint32_t)(s >> 2) * rows * 128 + (uint32_t)(s & 3) * 32, 16, 1024, 2);
@@ -238,7 +256,8 @@ namespace tc {
 
 constexpr int kThreads = 288;          // warps 0-3 epilogue, warp 4 MMA issuer, warps 5-8 producers
 constexpr int kProducerThreads = 128;
-constexpr int kMaxList = 32;           // K + 1 <= 32
+constexpr int kListStride = 65;        // per-user list stride in shared memory (words, odd)
+constexpr int kMaxList = 64;           // threshold rank (2*top_k, the reference's heap size) <= 64
 
 struct CandArgs {
     const __nv_bfloat16* Ub;   // [num_eval, D] bf16 rows of the users being evaluated (gathered)
@@ -246,7 +265,7 @@ struct CandArgs {
     const float* margin;       // [num_eval] 2 * eps_u (see tc_prepare_users_kernel)
     const int32_t* users;      // [num_eval] user ids (train CSR is indexed by user id)
     const int64_t* train_ptr; const int32_t* train_idx;
-    int num_eval, N, D, K, cap;
+    int num_eval, N, D, LQ, cap;   // LQ: rank of the running threshold (= min(2*top_k, N), evaluate.h:38)
     int32_t* cand;             // [num_eval, cap] candidate item ids, ascending
     int32_t* cand_cnt;         // [num_eval] number of candidates seen (> cap => overflow)
 };
@@ -264,10 +283,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_candidate_kernel(const CandArg
     const int row0 = blockIdx.x * kM;
     const int valid_rows = min(kM, P.num_eval - row0);
     const int T = (P.N + kN - 1) / kN;
-    const int K1 = P.K + 1;
 
     load_tile_sw128(sA, P.Ub + (size_t)row0 * D, kM, valid_rows, D, tid, kThreads);
-    for (int i = tid; i < kM * K1; i += kThreads) sList[i] = -INFINITY;
+    for (int i = tid; i < kM * kListStride; i += kThreads) sList[i] = -INFINITY;
     fence_async_smem();
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -294,8 +312,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_candidate_kernel(const CandArg
         for (int t = 0; t < T; ++t) {
             const int s = t & 1, ph = (t >> 1) & 1;
             mbar_wait(&empty_b[s], ph ^ 1);
-            load_tile_sw128(s ? sB1 : sB0, P.Vb + (size_t)t * kN * D, kN, min(kN, P.N - t * kN), D, ptid,
-                            kProducerThreads);
+            load_tile_sw128_async(s ? sB1 : sB0, P.Vb + (size_t)t * kN * D, kN, min(kN, P.N - t * kN), D, ptid,
+                                  kProducerThreads);
+            cp_async_wait_all();
             fence_async_smem();
             mbar_arrive(&full_b[s]);
         }
@@ -321,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_candidate_kernel(const CandArg
         const int r = warp * 32 + lane;              // row inside the tile == TMEM lane
         const int row = row0 + r;
         const bool live = row < P.num_eval;
-        float* lst = sList + r * K1;
+        float* lst = sList + r * kListStride;   // odd stride: conflict-free whatever slot each lane touches
         const float margin = live ? P.margin[row] : 0.0f;
         const int u = live ? P.users[row] : 0;
         const int64_t tb = live ? P.train_ptr[u] : 0;
@@ -329,6 +348,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_candidate_kernel(const CandArg
         int32_t* my_cand = P.cand + (size_t)row * P.cap;
         float thr = -INFINITY, thr_m = -INFINITY;
         int cnt = 0;
+        // merge-walk over the user's sorted train row: items arrive in ascending order, so the
+        // mask test of a candidate is "advance the cursor to >= item, compare" (amortised O(deg))
+        int tpos = 0;
+        int tnext = (tl > 0) ? __ldg(P.train_idx + tb) : INT32_MAX;
+        int tahead = (tl > 1) ? __ldg(P.train_idx + tb + 1) : INT32_MAX;   // prefetched: advancing never waits on memory
         for (int t = 0; t < T; ++t) {
             const int s = t & 1, ph = (t >> 1) & 1;
             mbar_wait(&acc_full[s], ph);
@@ -337,24 +361,51 @@ __global__ void __launch_bounds__(kThreads, 1) tc_candidate_kernel(const CandArg
                 float v[32];
                 __syncwarp();   // the candidate branch below diverges; tcgen05.ld needs the whole warp
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * kN + c), v);
-                if (live) {
-                    const int item0 = t * kN + c;
+                // cheap common case: the chunk maximum does not reach the threshold
+                float mx = v[0];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (v[i] > thr_m && item0 + i < P.N) {
-                            const int item = item0 + i;
-                            if (!sorted_contains(P.train_idx + tb, tl, item)) {
-                                if (cnt < P.cap) my_cand[cnt] = item;
-                                ++cnt;
-                                if (v[i] > thr) {   // keep the running (K+1)-th best approximate score
-                                    int j = P.K;
-                                    while (j > 0 && lst[j - 1] < v[i]) { lst[j] = lst[j - 1]; --j; }
-                                    lst[j] = v[i];
-                                    thr = lst[P.K];
-                                    thr_m = thr - margin;
-                                }
+                for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
+                unsigned m = 0u;
+                if (mx > thr_m) {   // bit i set when column i can still matter for this user
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m |= (v[i] > thr_m ? 1u : 0u) << i;
+                }
+                const int item0 = t * kN + c;
+                if (item0 + 32 > P.N) m &= (item0 >= P.N) ? 0u : ((1u << (P.N - item0)) - 1u);
+                if (!live) m = 0u;
+                while (m) {                       // rare: ~(K+1) ln(N/(K+1)) times per user in total
+                    const int i = __ffs(m) - 1;
+                    m &= m - 1;
+                    float x = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) x = (j == i) ? v[j] : x;   // register select, no local memory
+                    if (!(x > thr_m)) continue;   // the threshold may have risen inside this chunk
+                    const int item = item0 + i;
+                    while (tnext < item) {
+                        ++tpos;
+                        tnext = tahead;
+                        tahead = (tpos + 1 < tl) ? __ldg(P.train_idx + tb + tpos + 1) : INT32_MAX;
+                    }
+                    if (tnext == item) continue;  // train item: masked to -inf by the reference
+                    if (cnt < P.cap) my_cand[cnt] = item;
+                    ++cnt;
+                    if (x > thr) {                // keep the LQ best approximate scores in a min-heap
+                        int hpos = 0;             // replace the root (the LQ-th best) and sift down
+                        for (;;) {
+                            int ch = 2 * hpos + 1;
+                            if (ch >= P.LQ) break;
+                            float cv = lst[ch];
+                            if (ch + 1 < P.LQ) {
+                                const float cv2 = lst[ch + 1];
+                                if (cv2 < cv) { cv = cv2; ++ch; }
                             }
+                            if (!(cv < x)) break;
+                            lst[hpos] = cv;
+                            hpos = ch;
                         }
+                        lst[hpos] = x;
+                        thr = lst[0];
+                        thr_m = thr - margin;
                     }
                 }
             }
@@ -423,11 +474,11 @@ static void* g_ws = nullptr;
 static size_t g_ws_bytes = 0;
 
 int run_candidates(const float* U, const float* V, int D, int N, const int32_t* users, int num_eval,
-                   const int64_t* train_ptr, const int32_t* train_idx, int K, int cap,
+                   const int64_t* train_ptr, const int32_t* train_idx, int LQ, int cap,
                    const int32_t** cand, const int32_t** cand_cnt, cudaStream_t st) {
     NRC_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, NRC_E_LIMIT,
                 "the tensor-core pass needs dim in {64, 128, 192, 256} (got %d)", D);
-    NRC_REQUIRE(K + 1 <= kMaxList, NRC_E_LIMIT, "the tensor-core pass needs top_k <= %d", kMaxList - 1);
+    NRC_REQUIRE(LQ >= 1 && LQ <= kMaxList, NRC_E_LIMIT, "the tensor-core pass needs 2*top_k <= %d", kMaxList);
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t rows_pad = (size_t)((num_eval + kM - 1) / kM) * kM;
     const size_t o_vb = 0;
@@ -457,8 +508,8 @@ int run_candidates(const float* U, const float* V, int D, int N, const int32_t* 
     tc_prepare_users_kernel<<<(num_eval * 32 + 255) / 256, 256, 0, st>>>(U, users, num_eval, D, vmax, Ub, margin);
     NRC_CUDA_CHECK(cudaGetLastError());
 
-    CandArgs P{Ub, Vb, margin, users, train_ptr, train_idx, num_eval, N, D, K, cap, cd, cnt};
-    size_t smem = (size_t)(kM + 2 * kN) * D * 2 + (size_t)kM * (K + 1) * 4;
+    CandArgs P{Ub, Vb, margin, users, train_ptr, train_idx, num_eval, N, D, LQ, cap, cd, cnt};
+    size_t smem = (size_t)(kM + 2 * kN) * D * 2 + (size_t)kM * kListStride * 4;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
     NRC_REQUIRE(smem <= 220 * 1024, NRC_E_LIMIT, "tensor-core pass needs %zu B of shared memory", smem);
     static bool attr_done = false;

@@ -81,6 +81,34 @@ def test_tc_eval_ties_and_overflow_fall_back_to_heap_replay():
     assert np.array_equal(ranks.cpu().numpy(), wranks) and np.array_equal(got.cpu().numpy(), want)
 
 
+def test_tc_eval_candidate_list_heap_replay_matches_reference_heap():
+    """Force every user through the candidate-list heap replay (the tie path): the first 2K items seed
+    the heap, the candidates are a superset of everything that later enters it, so ranks and metrics
+    must still be bit-identical -- also with integer tables where most of the catalogue ties."""
+    from neurec_b200 import ops, _lib
+    lib = _lib.load()
+    try:
+        lib.nrc_eval_force_exact(1)
+        for (nu, ni, dim, K, ints) in ((200, 6000, 64, 20, False), (130, 3000, 128, 7, False),
+                                       (140, 5000, 64, 20, True), (64, 45, 64, 31, False)):
+            U, V, tp, ti, sp, si = _problem(nu, ni, dim, 17 + ni, int_tables=ints)
+            if ni < 100:
+                rs = np.random.RandomState(4)
+                tp, ti = random_csr(rs, nu, ni, rs.randint(0, 20, nu))
+                sp, si = random_csr(rs, nu, ni, rs.randint(1, 6, nu))
+            users = np.arange(nu, dtype=np.int32)
+            want, wranks = oracle.eval_mf(U, V, users, tp, ti, sp, si, ALL, K, return_ranks=True)
+            got, ranks = ops.eval_mf_tc(dev(U), dev(V), dev(users), dev(tp), dev(ti), dev(sp), dev(si), ALL, K,
+                                        return_ranks=True)
+            assert np.array_equal(ranks.cpu().numpy(), wranks), (nu, ni, dim, K, ints)
+            assert np.array_equal(got.cpu().numpy(), want)
+            n = ctypes.c_int32(0)
+            lib.nrc_eval_last_undecided(ctypes.byref(n))
+            assert n.value == nu          # every user went through a heap replay
+    finally:
+        lib.nrc_eval_force_exact(0)
+
+
 def test_tc_eval_large_scale_matches_simt_path():
     """200 k items x 2 000 users, d=128: the tensor-core path must agree bit for bit with the SIMT
     fused evaluator (itself pinned on the oracle) -- checks the error-margin argument at scale,
