@@ -18,6 +18,8 @@
 //     two buffers so that the epilogue of tile t overlaps the MMAs of tile t+1);
 //   * tcgen05.commit -> mbarrier hands the accumulator to the epilogue warps, which read it with
 //     tcgen05.ld.32x32b (warp w owns TMEM lanes 32w..32w+31 = 32 users, one user per thread).
+#include <cuda.h>            // CUtensorMap (types only; the encoder is fetched from the driver at run time)
+#include <cudaTypedefs.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -48,6 +50,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n\t"
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// TMA: one [box_rows x 64] bf16 box of a row-major [rows, K] tensor -> shared memory, laid out
+// by the copy engine in the SWIZZLE_128B pattern the UMMA descriptors below expect; rows past
+// the end of the tensor arrive as zeros.  Completion is signalled on `bar` (complete_tx).
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c_k, int c_row, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c_k), "r"(c_row), "r"(smem_u32(bar))
         : "memory");
 }
 
@@ -153,6 +169,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load without the wait, so that the next chunk can be in flight while this one is used.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+// tcgen05.wait::ld; the registers are in/out operands so that no use of them is scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
 // Copy a [rows, K] row-major bf16 tile from global memory into the canonical no-swizzle K-major
 // layout: 16-byte chunk (row, kc) -> smem[(kc * rows + row) * 16 B].  Rows >= valid_rows are zero.
 __device__ __forceinline__ void load_tile_kmajor(uint8_t* smem, const __nv_bfloat16* __restrict__ g, int rows,
@@ -254,8 +294,7 @@ extern "C" int nrc_tc_gemm_debug(const void* a_bf16, const void* b_bf16, int32_t
 namespace nrc {
 namespace tc {
 
-constexpr int kThreads = 288;          // warps 0-3 epilogue, warp 4 MMA issuer, warps 5-8 producers
-constexpr int kProducerThreads = 128;
+constexpr int kThreads = 192;          // warps 0-3 epilogue, warp 4 MMA issuer, warp 5 TMA producer
 constexpr int kListStride = 65;        // per-user list stride in shared memory (words, odd)
 constexpr int kMaxList = 64;           // threshold rank (2*top_k, the reference's heap size) <= 64
 
@@ -270,7 +309,8 @@ struct CandArgs {
     int32_t* cand_cnt;         // [num_eval] number of candidates seen (> cap => overflow)
 };
 
-__global__ void __launch_bounds__(kThreads, 1) tc_candidate_kernel(const CandArgs P) {
+__global__ void __launch_bounds__(kThreads, 1)
+tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int D = P.D;
     uint8_t* sA = smem;                                   // 128 x D bf16, SWIZZLE_128B blocks
@@ -289,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_candidate_kernel(const CandArg
     fence_async_smem();
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&full_b[i], kProducerThreads);
+            mbar_init(&full_b[i], 1);   // the producer's arrive.expect_tx; the copy engine completes the bytes
             mbar_init(&empty_b[i], 1);
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], 128);
@@ -306,17 +346,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_candidate_kernel(const CandArg
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp >= 5) {
-        // ---------------- producers: item tiles -> shared memory ----------------
-        const int ptid = tid - 5 * 32;
-        for (int t = 0; t < T; ++t) {
-            const int s = t & 1, ph = (t >> 1) & 1;
-            mbar_wait(&empty_b[s], ph ^ 1);
-            load_tile_sw128_async(s ? sB1 : sB0, P.Vb + (size_t)t * kN * D, kN, min(kN, P.N - t * kN), D, ptid,
-                                  kProducerThreads);
-            cp_async_wait_all();
-            fence_async_smem();
-            mbar_arrive(&full_b[s]);
+    if (warp == 5) {
+        // ---------------- producer (one thread): item tiles -> shared memory by TMA ----------------
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapV)) : "memory");
+            const uint32_t b0 = smem_u32(sB0), b1 = smem_u32(sB1);
+            const uint32_t stage_bytes = (uint32_t)kN * D * 2;
+            for (int t = 0; t < T; ++t) {
+                const int s = t & 1, ph = (t >> 1) & 1;
+                mbar_wait(&empty_b[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full_b[s], stage_bytes);
+                for (int kb = 0; kb < D / 64; ++kb)   // one 256 x 64 box per 128-byte K block
+                    tma_load_2d((s ? b1 : b0) + (uint32_t)kb * kN * 128, &tmapV, kb * 64, t * kN, &full_b[s]);
+            }
         }
     } else if (warp == 4) {
         // ---------------- MMA issuer (one thread) ----------------
@@ -357,10 +399,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_candidate_kernel(const CandArg
             const int s = t & 1, ph = (t >> 1) & 1;
             mbar_wait(&acc_full[s], ph);
             tc_fence_after();
-            for (int c = 0; c < kN; c += 32) {
+            // filter one chunk of 32 columns (items t*kN + c ..) held in registers
+            auto filter_chunk = [&](const uint32_t (&raw)[32], const int c) {
                 float v[32];
-                __syncwarp();   // the candidate branch below diverges; tcgen05.ld needs the whole warp
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * kN + c), v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
                 // cheap common case: the chunk maximum does not reach the threshold
                 float mx = v[0];
 #pragma unroll
@@ -408,6 +451,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_candidate_kernel(const CandArg
                         thr_m = thr - margin;
                     }
                 }
+            };
+            // two chunks in flight: tcgen05.ld of chunk c+1 overlaps the filtering of chunk c
+            const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * kN);
+            uint32_t ra[32], rb[32];
+            __syncwarp();   // the candidate branch diverges; tcgen05.ld needs the whole warp
+            tmem_ld32_issue(tbase, ra);
+#pragma unroll 1
+            for (int c = 0; c < kN; c += 64) {
+                tmem_ld_wait(ra);
+                tmem_ld32_issue(tbase + (uint32_t)(c + 32), rb);
+                filter_chunk(ra, c);
+                __syncwarp();
+                tmem_ld_wait(rb);
+                if (c + 64 < kN) tmem_ld32_issue(tbase + (uint32_t)(c + 64), ra);
+                filter_chunk(rb, c + 32);
+                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[s]);
@@ -509,6 +568,26 @@ int run_candidates(const float* U, const float* V, int D, int N, const int32_t* 
     NRC_CUDA_CHECK(cudaGetLastError());
 
     CandArgs P{Ub, Vb, margin, users, train_ptr, train_idx, num_eval, N, D, LQ, cap, cd, cnt};
+    CUtensorMap tmapV;
+    {   // bf16 item table [N, D] row-major; box = 256 items x 64 k (one 128-byte swizzle span)
+        static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            NRC_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+            NRC_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, NRC_E_CUDA,
+                        "the driver does not export cuTensorMapEncodeTiled");
+            encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+        }
+        const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)N};
+        const cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
+        const cuuint32_t box[2] = {64u, (cuuint32_t)kN};
+        const cuuint32_t estr[2] = {1u, 1u};
+        const CUresult cr = encode(&tmapV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)Vb, gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        NRC_REQUIRE(cr == CUDA_SUCCESS, NRC_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    }
     size_t smem = (size_t)(kM + 2 * kN) * D * 2 + (size_t)kM * kListStride * 4;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
     NRC_REQUIRE(smem <= 220 * 1024, NRC_E_LIMIT, "tensor-core pass needs %zu B of shared memory", smem);
@@ -518,7 +597,7 @@ int run_candidates(const float* U, const float* V, int D, int N, const int32_t* 
                                             220 * 1024));
         attr_done = true;
     }
-    tc_candidate_kernel<<<(num_eval + kM - 1) / kM, kThreads, smem, st>>>(P);
+    tc_candidate_kernel<<<(num_eval + kM - 1) / kM, kThreads, smem, st>>>(P, tmapV);
     NRC_CUDA_CHECK(cudaGetLastError());
     *cand = cd;
     *cand_cnt = cnt;
