@@ -902,6 +902,125 @@ def measure_synth_sgd(K, W, world, rank, windows, with_cpu=True):
     return out
 
 
+def measure_synth_eval(K, W, world, rank, windows, with_cpu=True):
+    """BASELINE config 4 on ONE GPU per rank: the full-catalogue evaluator over 10 M items x d=128
+    with the score step on the tensor cores (nrc_eval_mf_tc: bf16 tcgen05 candidate pass, exact fp32
+    re-score, top-20 in the reference's order, Precision/Recall/MAP/NDCG/MRR).  A step = one batch of
+    37 888 users (2 waves of 148 CTAs x 128 users); users are sharded over ranks, the item table is
+    replicated, no collective in the data path."""
+    import torch
+    from neurec_b200 import ops
+    nu, ni, dim, topk, ub = 1_000_000, 10_000_000, 128, 20, 37_888
+    K = max(1, min(K, 8))
+    W = 3
+    g = torch.Generator(device="cuda").manual_seed(5)
+    V = torch.randn(ni, dim, device="cuda", generator=g) * 0.1
+    U = torch.randn(nu, dim, device="cuda", generator=g) * 0.1
+
+    def csr(deg, seed):
+        gg = torch.Generator(device="cuda").manual_seed(seed)
+        idx = torch.randint(0, ni - deg, (nu, deg), device="cuda", generator=gg, dtype=torch.int32).sort(1).values
+        idx += torch.arange(deg, device="cuda", dtype=torch.int32)      # strictly increasing rows: no duplicates
+        return (torch.arange(nu + 1, device="cuda", dtype=torch.int64) * deg), idx.reshape(-1).contiguous()
+    tp, ti = csr(50, 6)
+    sp, si = csr(10, 7)
+    batch = lambda s: (torch.arange(ub, device="cuda", dtype=torch.int64)
+                       + (rank * (K + W) + s) * ub).remainder(nu).to(torch.int32)
+    step = lambda users: ops.eval_mf_tc(U, V, users, tp, ti, sp, si, METRICS, topk)
+    for s in range(W):
+        step(batch(s))
+    torch.cuda.synchronize()
+    barrier(world)
+    wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, kernel_flops, replays = 0.0, 0.0, 0
+    batches = [batch(s) for s in range(W, W + K)]
+    e0.record()
+    for users in batches:
+        res = step(users)
+        km, fl = ops.eval_tc_last_launch()     # waits for the candidate kernel only (events on its stream)
+        kernel_ms += km; kernel_flops += fl
+    e1.record()
+    barrier(world)
+    windows.append((wall0, time.perf_counter()))
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    replays = ops.eval_last_undecided()
+    # e2e: user ids from pinned host memory, metric rows back to pinned host memory, every step
+    h_users = [b.cpu().pin_memory() for b in batches]
+    d_users = torch.empty(ub, dtype=torch.int32, device="cuda")
+    h_res = torch.empty((ub, len(METRICS) * topk), dtype=torch.float32).pin_memory()
+
+    def e2e_step(h):
+        d_users.copy_(h, non_blocking=True)
+        r = step(d_users)
+        h_res.copy_(r, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_step(h_users[0])
+    barrier(world)
+    wall0 = time.perf_counter()
+    for h in h_users:
+        e2e_step(h)
+    e2e_s = max_over_ranks(time.perf_counter() - wall0, world)
+    windows.append((wall0, time.perf_counter()))
+    barrier(world)
+    mean_ndcg = float(res.view(ub, len(METRICS), topk)[:, METRICS.index("NDCG"), topk - 1].mean())
+    if rank != 0:
+        return None
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tpeak = pk.get("bf16_tflops_sustained") or pk.get("bf16_tflops") or 2250.0
+    tsrc = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if pk.get("bf16_tflops_sustained")
+            else "nominal dense bf16 (B200_PROFILING.md fallback)")
+    ach = kernel_flops / (kernel_ms * 1e-3) / 1e12
+    out = {"value": world * K * ub / (ms * 1e-3), "unit": "users/s", "steps": K, "ms_per_step": ms / K,
+           "e2e": {"value": world * K * ub / e2e_s, "unit": "users/s", "h2d_bytes_per_step": 4 * ub,
+                   "d2h_bytes_per_step": 4 * ub * len(METRICS) * topk, "ms_per_step": e2e_s * 1e3 / K},
+           "gpu_launches": 5 * K,
+           "config": {"workload": "full-catalogue evaluator, synthetic %d users x %d items, dim %d, top-%d, 5 metrics, "
+                                  "train rows of 50 / test rows of 10 items; %d users per step (BASELINE config 4, "
+                                  "item table replicated per GPU, users sharded)" % (nu, ni, dim, topk, ub),
+                      "l2": "the bf16 item table (2.56 GB) streamed by every step is far larger than L2",
+                      "heap_replays_last_step": replays, "ndcg_at_20_last_step": mean_ndcg},
+           "roofline": {"kernel": "tc_candidate_kernel", "bound": "tensor", "achieved": ach, "peak": tpeak,
+                        "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": profiled_traffic("tc_candidate_kernel"),
+                        "peak_source": tsrc, "flops_per_launch": kernel_flops / K, "launch_us": kernel_ms * 1e3 / K,
+                        "flops_note": "SURVEY.md 8(d): 2*d flop per (user, item) pair x 37 888 users x 10 M items",
+                        "kernel_share_of_step": kernel_ms / ms,
+                        "timing": "CUDA events on the launching stream around every timed tc_candidate_kernel "
+                                  "launch (nrc_eval_tc_last_launch)"}}
+    if with_cpu:
+        import oracle
+        threads = os.cpu_count() or 1
+        n_cpu = 32
+        Vh = V.cpu().numpy()
+        cu = batches[-1][:256].cpu().numpy().astype(np.int64)
+        tph, tih, sph, sih = (x.cpu().numpy() for x in (tp, ti, sp, si))
+
+        def run_cpu(n):
+            us = cu[:n]
+            Uh = U[torch.from_numpy(us).cuda()].cpu().numpy()
+            rows = lambda ptr, idx: oracle.lists_to_csr([idx[ptr[u]:ptr[u + 1]] for u in us])
+            trp, tri = rows(tph, tih)
+            tep, tei = rows(sph, sih)
+            t0 = time.perf_counter()
+            want = oracle.eval_mf(Uh, Vh, np.arange(n, dtype=np.int32), trp, tri, tep, tei,
+                                  [int(x) for x in ops._metric_arr(METRICS)], topk,
+                                  thread_num=threads)
+            return time.perf_counter() - t0, want
+        dt, want = run_cpu(n_cpu)
+        if dt < 4.0:
+            n_cpu = int(min(256, max(n_cpu, n_cpu * 10.0 / max(dt, 1e-3)) // 8 * 8))
+            dt, want = run_cpu(n_cpu)
+        got = res[:n_cpu].cpu().numpy()
+        out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "users/s", "cores": threads, "kind": "port",
+                               "sample": "%d users of the last step against the full 10 M-item catalogue: C "
+                                         "restatement of MF.predict + the reference's C++ evaluator (OpenMP/AVX2, %d "
+                                         "threads)" % (n_cpu, threads),
+                               "bit_identical_to_gpu": bool(np.array_equal(got, want))}
+    del U, V
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     rank, world, local = dist_setup()
@@ -915,6 +1034,15 @@ def run_ours(args):
         if rank == 0:
             out = {"metric": "triplets/sec", "n_gpus": world, "warmup": W, "higher_is_better": True,
                    "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic, seed 3"}
+            out.update(o)
+        args.only = True
+    elif args.workload == "eval-synth":
+        o = measure_synth_eval(K, W, world, rank, windows)
+        out = None
+        if rank == 0:
+            out = {"metric": "eval users/sec", "n_gpus": world, "warmup": 3, "higher_is_better": True,
+                   "scaling": "weak", "vs_baseline": None, "dtype": "bf16 candidates + f32 exact re-score",
+                   "data": "synthetic, seed 5"}
             out.update(o)
         args.only = True
     else:
@@ -935,6 +1063,10 @@ def run_ours(args):
             others["bprmf-synth-sgd"] = measure_synth_sgd(24, W, world, rank, windows)
         except Exception as ex:
             others["bprmf-synth-sgd"] = {"error": repr(ex)}
+        try:
+            others["eval-synth"] = measure_synth_eval(4, W, world, rank, windows)
+        except Exception as ex:
+            others["eval-synth"] = {"error": repr(ex)}
         out["others"] = others
     clocks.stop()
     if rank == 0:
@@ -993,7 +1125,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1570)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=WORKLOADS + ("bprmf-synth",))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=WORKLOADS + ("bprmf-synth", "eval-synth"))
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--only", action="store_true", help="measure only --workload (used under ncu)")
     args = ap.parse_args()

@@ -154,6 +154,10 @@ int nrc_eval_mf_tc(const float* user_table, const float* item_table, int32_t dim
                    const int64_t* test_indptr, const int32_t* test_indices,
                    const int32_t* metric_host, int32_t metric_num, int32_t top_k, int32_t cand_cap,
                    float* results, int32_t* ranks, void* stream);
+/* Measurement hook: CUDA-event duration (ms, on the launching stream) and algorithmic flops
+ * (2 * users * items * dim) of the last tcgen05 candidate-kernel launch made by nrc_eval_mf_tc;
+ * waits for that launch.  bench.py derives the tensor-pipe roofline fraction from it. */
+int nrc_eval_tc_last_launch(float* kernel_ms, double* flops);
 
 /* Self-test of the tcgen05 / TMEM building block used by the tensor-core candidate pass:
  * out f32 [128, 256] = a bf16 [128, k] . b bf16 [256, k]^T (k multiple of 16, <= 256);

@@ -304,6 +304,7 @@ struct CandArgs {
     const float* margin;       // [num_eval] 2 * eps_u (see tc_prepare_users_kernel)
     const int32_t* users;      // [num_eval] user ids (train CSR is indexed by user id)
     const int64_t* train_ptr; const int32_t* train_idx;
+    int dbg;                   // NRC_TC_DBG experiment bits (0 in normal use): 1 skip epilogue, 2 skip TMA, 4 skip MMA, 8 TMEM read-out only
     int num_eval, N, D, LQ, cap;   // LQ: rank of the running threshold (= min(2*top_k, N), evaluate.h:38)
     int32_t* cand;             // [num_eval, cap] candidate item ids, ascending
     int32_t* cand_cnt;         // [num_eval] number of candidates seen (> cap => overflow)
@@ -355,6 +356,7 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
             for (int t = 0; t < T; ++t) {
                 const int s = t & 1, ph = (t >> 1) & 1;
                 mbar_wait(&empty_b[s], ph ^ 1);
+                if (P.dbg & 2) { mbar_arrive(&full_b[s]); continue; }
                 mbar_arrive_expect_tx(&full_b[s], stage_bytes);
                 for (int kb = 0; kb < D / 64; ++kb)   // one 256 x 64 box per 128-byte K block
                     tma_load_2d((s ? b1 : b0) + (uint32_t)kb * kN * 128, &tmapV, kb * 64, t * kN, &full_b[s]);
@@ -371,6 +373,7 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
                 mbar_wait(&acc_empty[s], ph ^ 1);
                 tc_fence_after();
                 const uint32_t td = tmem_base + (uint32_t)s * kN;
+                if (!(P.dbg & 4))
                 for (int ks = 0; ks < D / kUmmaK; ++ks)
                     umma_bf16(td, sw128_desc(a0, kM, ks), sw128_desc(s ? b1 : b0, kN, ks), idesc, ks > 0 ? 1u : 0u);
                 umma_commit(&empty_b[s]);
@@ -401,17 +404,25 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
             tc_fence_after();
             // filter one chunk of 32 columns (items t*kN + c ..) held in registers
             auto filter_chunk = [&](const uint32_t (&raw)[32], const int c) {
+                if (P.dbg & 8) return;   // experiment: Tensor Memory read-out only
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
                 // cheap common case: the chunk maximum does not reach the threshold
-                float mx = v[0];
+                float t16[16];   // max tree: one epilogue warp per scheduler, so dependent chains are exposed
 #pragma unroll
-                for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
+                for (int i = 0; i < 16; ++i) t16[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t16[i] = fmaxf(t16[2 * i], t16[2 * i + 1]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) t16[i] = fmaxf(t16[2 * i], t16[2 * i + 1]);
+                const float mx = fmaxf(fmaxf(t16[0], t16[1]), fmaxf(t16[2], t16[3]));
                 unsigned m = 0u;
                 if (mx > thr_m) {   // bit i set when column i can still matter for this user
+                    unsigned m4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) m |= (v[i] > thr_m ? 1u : 0u) << i;
+                    for (int i = 0; i < 32; ++i) m4[i & 3] |= (v[i] > thr_m ? 1u : 0u) << i;
+                    m = (m4[0] | m4[1]) | (m4[2] | m4[3]);
                 }
                 const int item0 = t * kN + c;
                 if (item0 + 32 > P.N) m &= (item0 >= P.N) ? 0u : ((1u << (P.N - item0)) - 1u);
@@ -455,6 +466,7 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
             // two chunks in flight: tcgen05.ld of chunk c+1 overlaps the filtering of chunk c
             const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * kN);
             uint32_t ra[32], rb[32];
+            if (P.dbg & 1) { tc_fence_before(); mbar_arrive(&acc_empty[s]); continue; }
             __syncwarp();   // the candidate branch diverges; tcgen05.ld needs the whole warp
             tmem_ld32_issue(tbase, ra);
 #pragma unroll 1
@@ -531,6 +543,8 @@ namespace tc {
 // library-owned workspace, grown on demand (never inside a stream capture)
 static void* g_ws = nullptr;
 static size_t g_ws_bytes = 0;
+static cudaEvent_t g_ev[2] = {nullptr, nullptr};   // around the last tc_candidate_kernel launch
+static double g_last_flops = 0.0;
 
 int run_candidates(const float* U, const float* V, int D, int N, const int32_t* users, int num_eval,
                    const int64_t* train_ptr, const int32_t* train_idx, int LQ, int cap,
@@ -567,7 +581,8 @@ int run_candidates(const float* U, const float* V, int D, int N, const int32_t* 
     tc_prepare_users_kernel<<<(num_eval * 32 + 255) / 256, 256, 0, st>>>(U, users, num_eval, D, vmax, Ub, margin);
     NRC_CUDA_CHECK(cudaGetLastError());
 
-    CandArgs P{Ub, Vb, margin, users, train_ptr, train_idx, num_eval, N, D, LQ, cap, cd, cnt};
+    const char* dbg_env = getenv("NRC_TC_DBG");
+    CandArgs P{Ub, Vb, margin, users, train_ptr, train_idx, dbg_env ? atoi(dbg_env) : 0, num_eval, N, D, LQ, cap, cd, cnt};
     CUtensorMap tmapV;
     {   // bf16 item table [N, D] row-major; box = 256 items x 64 k (one 128-byte swizzle span)
         static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -597,8 +612,15 @@ int run_candidates(const float* U, const float* V, int D, int N, const int32_t* 
                                             220 * 1024));
         attr_done = true;
     }
+    if (!g_ev[0]) {
+        NRC_CUDA_CHECK(cudaEventCreate(&g_ev[0]));
+        NRC_CUDA_CHECK(cudaEventCreate(&g_ev[1]));
+    }
+    NRC_CUDA_CHECK(cudaEventRecord(g_ev[0], st));
     tc_candidate_kernel<<<(num_eval + kM - 1) / kM, kThreads, smem, st>>>(P, tmapV);
     NRC_CUDA_CHECK(cudaGetLastError());
+    NRC_CUDA_CHECK(cudaEventRecord(g_ev[1], st));
+    g_last_flops = 2.0 * (double)num_eval * (double)N * (double)D;
     *cand = cd;
     *cand_cnt = cnt;
     return NRC_OK;
@@ -606,3 +628,14 @@ int run_candidates(const float* U, const float* V, int D, int N, const int32_t* 
 
 }  // namespace tc
 }  // namespace nrc
+
+// Duration (CUDA events on the launching stream) and algorithmic flops (2 * users * items * dim)
+// of the last tcgen05 candidate-kernel launch; waits for that launch to finish.
+extern "C" int nrc_eval_tc_last_launch(float* kernel_ms, double* flops) {
+    NRC_REQUIRE(kernel_ms != nullptr && flops != nullptr, NRC_E_VALUE, "NULL output");
+    NRC_REQUIRE(nrc::tc::g_ev[0] != nullptr, NRC_E_VALUE, "nrc_eval_mf_tc has not run yet");
+    NRC_CUDA_CHECK(cudaEventSynchronize(nrc::tc::g_ev[1]));
+    NRC_CUDA_CHECK(cudaEventElapsedTime(kernel_ms, nrc::tc::g_ev[0], nrc::tc::g_ev[1]));
+    *flops = nrc::tc::g_last_flops;
+    return NRC_OK;
+}

@@ -135,6 +135,22 @@ def eval_mf_tc(user_table, item_table, users, train_indptr, train_indices, test_
     return (res, ranks) if return_ranks else res
 
 
+def eval_tc_last_launch():
+    """(kernel_ms, flops) of the last tcgen05 candidate-kernel launch made by eval_mf_tc."""
+    import ctypes
+    ms, fl = ctypes.c_float(0.0), ctypes.c_double(0.0)
+    check(_lib.load().nrc_eval_tc_last_launch(ctypes.byref(ms), ctypes.byref(fl)))
+    return ms.value, fl.value
+
+
+def eval_last_undecided():
+    """Users of the last eval_mf / eval_mf_tc call that needed a heap replay (ties, overflow)."""
+    import ctypes
+    n = ctypes.c_int32(0)
+    check(_lib.load().nrc_eval_last_undecided(ctypes.byref(n)))
+    return n.value
+
+
 def mf_scores(user_table, item_table, users):
     """MF.predict(users, None) on device: [len(users), num_items] fp32 (MF.py:120-122)."""
     _req(user_table, torch.float32, "user_table"); _req(item_table, torch.float32, "item_table")
