@@ -903,7 +903,9 @@ extern "C" int nrc_arg_topk_host(const float* scores, int32_t rating_len, int32_
 // library-owned list of batch rows the fast kernel could not decide: [count, rows...]
 static int32_t* g_slow = nullptr;
 static size_t g_slow_cap = 0;
-static int32_t* g_replay = nullptr;   // tensor-core path: users decided by the candidate-list heap replay
+static int32_t* g_und = nullptr;      // tensor-core path: users with ties (second, heap-replay pass)
+static size_t g_und_cap = 0;
+static int32_t g_last_replays = 0;
 static bool g_last_was_tc = false;
 
 // Test hook: 1 = always use the exact heap-replay kernel (no tie-free fast pass).
@@ -919,11 +921,7 @@ extern "C" int nrc_eval_last_undecided(int32_t* count_host) {
     NRC_REQUIRE(count_host != nullptr, NRC_E_VALUE, "count_host is NULL");
     *count_host = 0;
     if (g_slow) NRC_CUDA_CHECK(cudaMemcpy(count_host, g_slow, sizeof(int32_t), cudaMemcpyDeviceToHost));
-    if (g_last_was_tc && g_replay) {
-        int32_t r = 0;
-        NRC_CUDA_CHECK(cudaMemcpy(&r, g_replay, sizeof(int32_t), cudaMemcpyDeviceToHost));
-        *count_host += r;
-    }
+    if (g_last_was_tc) *count_host += g_last_replays;
     return NRC_OK;
 }
 
@@ -1087,58 +1085,69 @@ extern "C" int nrc_mask_rows(float* scores, int32_t rating_len, int32_t num_rows
 }
 
 namespace nrc {
-// Finalisation of the tensor-core candidate pass: one warp per evaluated user re-scores the
-// user's candidates (ascending item order) with the oracle's fp32 FMA chain and runs the same
-// tie-aware fast selection as eval_mf_fast_kernel; undecidable users and users whose candidate
-// buffer overflowed go to the heap-replay list.
+// ----------------------------------------------------------------------------------------
+// Finalisation of the tensor-core candidate passes (tc_eval.cu).  One warp per user.
+// ----------------------------------------------------------------------------------------
+
+// The oracle's score: fp32 FMA chain over k ascending (D % 4 == 0 on this path).
+__device__ __forceinline__ float tc_exact_score(const float4* __restrict__ su4, const float* __restrict__ Vtab,
+                                                int item, int D) {
+    const float4* v = reinterpret_cast<const float4*>(Vtab + (size_t)item * D);
+    float acc = 0.0f;
+#pragma unroll 4
+    for (int q = 0; q < (D >> 2); ++q) {
+        const float4 b = __ldg(v + q);
+        const float4 a = su4[q];
+        acc = __fmaf_rn(a.x, b.x, acc);
+        acc = __fmaf_rn(a.y, b.y, acc);
+        acc = __fmaf_rn(a.z, b.z, acc);
+        acc = __fmaf_rn(a.w, b.w, acc);
+    }
+    return acc;
+}
+
+// Main pass: exact re-scoring of the user's candidate lists (any order) and the same tie-aware
+// selection as eval_mf_fast_kernel.  Users with ties inside the top K+1 go to `und_rows` (second,
+// heap-replay pass); users with an overflowed list go to `slow_rows` (full-catalogue heap replay).
 __global__ void __launch_bounds__(256)
 eval_tc_finalize_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, int D,
                         const int32_t* __restrict__ users, int num_eval,
-                        const int64_t* __restrict__ train_ptr, const int32_t* __restrict__ train_idx,
                         const int64_t* __restrict__ test_ptr, const int32_t* __restrict__ test_idx,
-                        const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int cap,
-                        int K, int L, int M, int force_exact, float* __restrict__ results,
+                        const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int nslots, int cap,
+                        int K, int M, int force_exact, float* __restrict__ results,
                         int32_t* __restrict__ ranks, int32_t* __restrict__ slow_count,
-                        int32_t* __restrict__ slow_rows, int32_t* __restrict__ replay_count) {
+                        int32_t* __restrict__ slow_rows, int32_t* __restrict__ und_count,
+                        int32_t* __restrict__ und_rows) {
     extern __shared__ int smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= num_eval) return;
-    float* su = reinterpret_cast<float*>(smem) + warp * ((D + 4 * K + 2 * L + 3) & ~3);   // float4 reads
+    float* su = reinterpret_cast<float*>(smem) + warp * ((D + 4 * K + 3) & ~3);   // float4 reads
     int* rank = reinterpret_cast<int*>(su + D);
-    const int cnt = cand_cnt[row];
-    if (cnt > cap) {   // candidate buffer overflowed: full-catalogue heap replay (eval_mf_kernel)
+    const int32_t* ccnt = cand_cnt + (size_t)row * nslots;
+    bool overflow = false;
+    for (int sl = lane; sl < nslots; sl += kWarp) overflow |= ccnt[sl] > cap;
+    if (__any_sync(kFull, overflow)) {
         if (lane == 0) slow_rows[atomicAdd(slow_count, 1)] = row;
+        return;
+    }
+    if (force_exact) {
+        if (lane == 0) und_rows[atomicAdd(und_count, 1)] = row;
         return;
     }
     const int u = users[row];
     for (int k = lane; k < D; k += kWarp) su[k] = Utab[(size_t)u * D + k];
     __syncwarp();
     const float4* su4 = reinterpret_cast<const float4*>(su);
-    const int D4 = D >> 2;   // the tensor-core path requires D % 64 == 0
-    auto exact_score = [&](int item) {   // the oracle's fp32 FMA chain, k ascending
-        const float4* v = reinterpret_cast<const float4*>(Vtab + (size_t)item * D);
-        float acc = 0.0f;
-#pragma unroll 4
-        for (int q = 0; q < D4; ++q) {
-            const float4 b = __ldg(v + q);
-            const float4 a = su4[q];
-            acc = __fmaf_rn(a.x, b.x, acc);
-            acc = __fmaf_rn(a.y, b.y, acc);
-            acc = __fmaf_rn(a.z, b.z, acc);
-            acc = __fmaf_rn(a.w, b.w, acc);
-        }
-        return acc;
-    };
-    const int32_t* crow = cand + (size_t)row * cap;
-    bool undecided = force_exact != 0;
-    if (!undecided) {
-        float tv = -INFINITY, thr = -INFINITY;
-        int ti = -1;
+    float tv = -INFINITY, thr = -INFINITY;
+    int ti = -1;
+    for (int sl = 0; sl < nslots; ++sl) {
+        const int cnt = ccnt[sl];
+        const int32_t* crow = cand + ((size_t)row * nslots + sl) * cap;
         for (int base = 0; base < cnt; base += kWarp) {
             const int idx = base + lane;
             const int item = (idx < cnt) ? crow[idx] : -1;
-            const float s = (item >= 0) ? exact_score(item) : -INFINITY;
+            const float s = (item >= 0) ? tc_exact_score(su4, Vtab, item, D) : -INFINITY;
             unsigned c = __ballot_sync(kFull, item >= 0 && s > thr);
             while (c) {
                 const int src = __ffs(c) - 1;
@@ -1154,41 +1163,91 @@ eval_tc_finalize_kernel(const float* __restrict__ Utab, const float* __restrict_
                 thr = __shfl_sync(kFull, tv, K);
             }
         }
-        const float nxt = __shfl_down_sync(kFull, tv, 1);
-        const bool bad = (lane < K && !(tv > nxt)) || (lane == K && !(tv > -INFINITY));
-        undecided = __ballot_sync(kFull, bad) != 0u;
-        if (!undecided && lane < K) rank[lane] = ti;
     }
-    if (undecided) {
-        // Ties (or fewer than K+1 finite scores): replay the reference's heap (evaluate.h:33-47)
-        // over the only elements that can change it -- the first L items, which seed it, and the
-        // candidates, a superset of every later element that beats the heap root when offered.
-        Heap h;
-        h.idx = rank + 4 * K;
-        h.val = reinterpret_cast<float*>(h.idx + L);
-        const int64_t tr0 = train_ptr[u];
-        const int64_t trn = train_ptr[u + 1] - tr0;
-        for (int i = lane; i < L; i += kWarp) {
-            float s = exact_score(i);
-            if (sorted_contains(train_idx + tr0, trn, i)) s = -INFINITY;
-            h.idx[i] = i;
-            h.val[i] = s;
-        }
-        __syncwarp();
-        if (lane == 0) heap_make(h, L);
-        __syncwarp();
-        float thr = h.val[0];
+    const float nxt = __shfl_down_sync(kFull, tv, 1);
+    const bool bad = (lane < K && !(tv > nxt)) || (lane == K && !(tv > -INFINITY));
+    if (__ballot_sync(kFull, bad)) {
+        if (lane == 0) und_rows[atomicAdd(und_count, 1)] = row;
+        return;
+    }
+    if (lane < K) rank[lane] = ti;
+    __syncwarp();
+    if (ranks && lane < K) ranks[(size_t)row * K + lane] = ti;
+    if (results) {
+        const int64_t t0 = test_ptr[u];
+        const int T = (int)(test_ptr[u + 1] - t0);
+        int* s_cnt = rank + K;
+        float* s_sum_pre = reinterpret_cast<float*>(s_cnt + K);
+        float* s_dcg = s_sum_pre + K;
+        metrics_for_user(rank, K, test_idx + t0, T, s_cnt, s_sum_pre, s_dcg, M, results + (size_t)row * M * K, lane);
+    }
+}
+
+__global__ void tc_gather_users_kernel(const int32_t* __restrict__ users, const int32_t* __restrict__ rows, int n,
+                                       int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = users[rows[i]];
+}
+
+// Replay pass, for the users with ties: the reference's heap (evaluate.h:33-47) replayed over the
+// only elements that can change it -- the first L items, which seed it, and the replay pass's
+// candidates in ascending item order (lists in slot order), a superset of every later element
+// that beats the heap root when offered.  `urow[i]` is the row of the original call.
+__global__ void __launch_bounds__(256)
+eval_tc_replay_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, int D,
+                      const int32_t* __restrict__ users2, const int32_t* __restrict__ urow, int n_und,
+                      const int64_t* __restrict__ train_ptr, const int32_t* __restrict__ train_idx,
+                      const int64_t* __restrict__ test_ptr, const int32_t* __restrict__ test_idx,
+                      const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int nslots, int cap,
+                      int K, int L, int M, float* __restrict__ results, int32_t* __restrict__ ranks,
+                      int32_t* __restrict__ slow_count, int32_t* __restrict__ slow_rows) {
+    extern __shared__ int smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (i >= n_und) return;
+    const int row = urow[i];
+    float* su = reinterpret_cast<float*>(smem) + warp * ((D + 4 * K + 2 * L + 3) & ~3);
+    int* rank = reinterpret_cast<int*>(su + D);
+    const int32_t* ccnt = cand_cnt + (size_t)i * nslots;
+    bool overflow = false;
+    for (int sl = lane; sl < nslots; sl += kWarp) overflow |= ccnt[sl] > cap;
+    if (__any_sync(kFull, overflow)) {
+        if (lane == 0) slow_rows[atomicAdd(slow_count, 1)] = row;
+        return;
+    }
+    const int u = users2[i];
+    for (int k = lane; k < D; k += kWarp) su[k] = Utab[(size_t)u * D + k];
+    __syncwarp();
+    const float4* su4 = reinterpret_cast<const float4*>(su);
+    Heap h;
+    h.idx = rank + 4 * K;
+    h.val = reinterpret_cast<float*>(h.idx + L);
+    const int64_t tr0 = train_ptr[u];
+    const int64_t trn = train_ptr[u + 1] - tr0;
+    for (int j = lane; j < L; j += kWarp) {
+        float s = tc_exact_score(su4, Vtab, j, D);
+        if (sorted_contains(train_idx + tr0, trn, j)) s = -INFINITY;
+        h.idx[j] = j;
+        h.val[j] = s;
+    }
+    __syncwarp();
+    if (lane == 0) heap_make(h, L);
+    __syncwarp();
+    float thr = h.val[0];
+    for (int sl = 0; sl < nslots; ++sl) {
+        const int cnt = ccnt[sl];
+        const int32_t* crow = cand + ((size_t)i * nslots + sl) * cap;
         for (int base = 0; base < cnt; base += kWarp) {
             const int idx = base + lane;
             const int item = (idx < cnt) ? crow[idx] : -1;
             const bool ok = item >= L;
-            const float s = ok ? exact_score(item) : -INFINITY;
+            const float s = ok ? tc_exact_score(su4, Vtab, item, D) : -INFINITY;
             thr = offer_candidates(h, L, s, item, ok, thr, lane);
         }
-        if (lane == 0) { heap_sort(h, L); atomicAdd(replay_count, 1); }
-        __syncwarp();
-        if (lane < K) rank[lane] = h.idx[lane];
     }
+    if (lane == 0) heap_sort(h, L);
+    __syncwarp();
+    if (lane < K) rank[lane] = h.idx[lane];
     __syncwarp();
     if (ranks && lane < K) ranks[(size_t)row * K + lane] = rank[lane];
     if (results) {
@@ -1202,9 +1261,14 @@ eval_tc_finalize_kernel(const float* __restrict__ Utab, const float* __restrict_
 }
 }  // namespace nrc
 
-// nrc_eval_mf with the score step on the tensor cores (tcgen05 / TMEM), for large catalogues:
-// bf16 candidate pass -> exact fp32 re-scoring -> tie-aware selection -> metrics.  Same results
-// as nrc_eval_mf, bit for bit.  cand_cap: candidate slots per user (0 = default 1024).
+// nrc_eval_mf with the score step on the tensor cores (tcgen05 / TMEM), for large catalogues.
+//   pass 0: bf16 candidate pass with the (K+1)-th best score as running threshold -> exact fp32
+//           re-scoring -> tie-aware selection -> metrics (users without ties: almost all);
+//   pass 1: users with ties only: candidate pass with the reference's heap root (2K-th best) as
+//           threshold -> libstdc++ heap replayed over the first 2K items + those candidates;
+//   users whose candidate list overflowed: full-catalogue heap replay (eval_mf_kernel).
+// Same results as nrc_eval_mf, bit for bit.  Synchronises `stream` once (to size pass 1), so it
+// cannot be captured into a CUDA graph.  cand_cap: entries per candidate list (0 = 1024).
 extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, int32_t dim,
                               int32_t num_items, const int32_t* users, int32_t num_eval_users,
                               const int64_t* train_indptr, const int32_t* train_indices,
@@ -1217,13 +1281,15 @@ extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, 
     if (rc) return rc;
     if (num_eval_users <= 0) return NRC_OK;
     g_last_was_tc = true;
-    const int K = top_k, cap = cand_cap > 0 ? cand_cap : 2048;
+    const int K = top_k, cap = cand_cap > 0 ? cand_cap : 1024;
     const int L = (2 * K < num_items) ? 2 * K : num_items;   // evaluate.h:38 heap size
     cudaStream_t st = as_stream(stream);
-    const int32_t *cand = nullptr, *cnt = nullptr;
-    rc = tc::run_candidates(user_table, item_table, dim, num_items, users, num_eval_users, train_indptr,
-                            train_indices, L, cap, &cand, &cnt, st);
+    rc = tc::prepare_items(item_table, dim, num_items, st);
     if (rc) return rc;
+    tc::CandLists c0;
+    rc = tc::run_pass(0, user_table, users, num_eval_users, train_indptr, train_indices, K + 1, 2, cap, &c0, st);
+    if (rc) return rc;
+    // g_slow: [count, rows...] full-catalogue replays; g_und: [count, rows..., gathered user ids...]
     if ((size_t)num_eval_users + 1 > g_slow_cap) {
         if (g_slow) NRC_CUDA_CHECK(cudaFree(g_slow));
         g_slow = nullptr; g_slow_cap = 0;
@@ -1231,19 +1297,44 @@ extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, 
         NRC_CUDA_CHECK(cudaMalloc(&g_slow, c2 * sizeof(int32_t)));
         g_slow_cap = c2;
     }
+    if ((size_t)2 * num_eval_users + 1 > g_und_cap) {
+        if (g_und) NRC_CUDA_CHECK(cudaFree(g_und));
+        g_und = nullptr; g_und_cap = 0;
+        const size_t c2 = (size_t)num_eval_users * 3 + 1024;
+        NRC_CUDA_CHECK(cudaMalloc(&g_und, c2 * sizeof(int32_t)));
+        g_und_cap = c2;
+    }
     NRC_CUDA_CHECK(cudaMemsetAsync(g_slow, 0, sizeof(int32_t), st));
-    if (!g_replay) NRC_CUDA_CHECK(cudaMalloc(&g_replay, sizeof(int32_t)));
-    NRC_CUDA_CHECK(cudaMemsetAsync(g_replay, 0, sizeof(int32_t), st));
+    NRC_CUDA_CHECK(cudaMemsetAsync(g_und, 0, sizeof(int32_t), st));
+    const int warps = 8;
     {
-        const int warps = 8;
-        const size_t smem = (size_t)warps * ((dim + 4 * K + 2 * L + 3) & ~3) * 4;
+        const size_t smem = (size_t)warps * ((dim + 4 * K + 3) & ~3) * 4;
         eval_tc_finalize_kernel<<<(num_eval_users + warps - 1) / warps, warps * 32, smem, st>>>(
-            user_table, item_table, dim, users, num_eval_users, train_indptr, train_indices, test_indptr,
-            test_indices, cand, cnt, cap, K, L, metric_num, g_force_exact ? 1 : 0, results, ranks, g_slow,
-            g_slow + 1, g_replay);
+            user_table, item_table, dim, users, num_eval_users, test_indptr, test_indices, c0.cand, c0.cnt,
+            c0.nslots, c0.cap, K, metric_num, g_force_exact ? 1 : 0, results, ranks, g_slow, g_slow + 1, g_und,
+            g_und + 1);
         NRC_CUDA_CHECK(cudaGetLastError());
     }
-    {   // full-catalogue heap replay for users whose candidate buffer overflowed (rare)
+    int32_t n_und = 0;
+    NRC_CUDA_CHECK(cudaMemcpyAsync(&n_und, g_und, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    NRC_CUDA_CHECK(cudaStreamSynchronize(st));
+    g_last_replays = n_und;
+    if (n_und > 0) {
+        int32_t* und_rows = g_und + 1;
+        int32_t* users2 = g_und + 1 + num_eval_users;
+        tc_gather_users_kernel<<<(n_und + 255) / 256, 256, 0, st>>>(users, und_rows, n_und, users2);
+        NRC_CUDA_CHECK(cudaGetLastError());
+        tc::CandLists c1;
+        rc = tc::run_pass(1, user_table, users2, n_und, train_indptr, train_indices, L, 1, cap > 2048 ? cap : 2048,
+                          &c1, st);
+        if (rc) return rc;
+        const size_t smem = (size_t)warps * ((dim + 4 * K + 2 * L + 3) & ~3) * 4;
+        eval_tc_replay_kernel<<<(n_und + warps - 1) / warps, warps * 32, smem, st>>>(
+            user_table, item_table, dim, users2, und_rows, n_und, train_indptr, train_indices, test_indptr,
+            test_indices, c1.cand, c1.cnt, c1.nslots, c1.cap, K, L, metric_num, results, ranks, g_slow, g_slow + 1);
+        NRC_CUDA_CHECK(cudaGetLastError());
+    }
+    {   // full-catalogue heap replay for users whose candidate list overflowed (rare)
         constexpr int TMx = 1, TN = 2, W = 8;
         const int D4 = (dim + 3) & ~3;
         const size_t xsmem = ((size_t)W * TMx * D4 + (size_t)TN * 32 * (D4 + 4)) * 4 + (size_t)W * TMx * (2 * L + 3 * K) * 4;

@@ -294,9 +294,12 @@ extern "C" int nrc_tc_gemm_debug(const void* a_bf16, const void* b_bf16, int32_t
 namespace nrc {
 namespace tc {
 
-constexpr int kThreads = 192;          // warps 0-3 epilogue, warp 4 MMA issuer, warp 5 TMA producer
-constexpr int kListStride = 65;        // per-user list stride in shared memory (words, odd)
-constexpr int kMaxList = 64;           // threshold rank (2*top_k, the reference's heap size) <= 64
+// Warp roles, for STREAMS = 1 or 2 epilogue warp sets: warps [0, 4*STREAMS) epilogue (set q =
+// warp / 4 filters the tiles t == q (mod STREAMS) of this CTA, i.e. TMEM stage q when STREAMS == 2),
+// warp 4*STREAMS the MMA issuer, warp 4*STREAMS + 1 the TMA producer.
+constexpr int kMaxList = 64;           // threshold rank <= 64 (2*top_k for the tie-replay pass)
+constexpr int kNT = 128;               // items per candidate-kernel tile (UMMA N)
+constexpr int kStages = 4;             // shared-memory item-tile stages == TMEM accumulator stages (4 x 128 columns)
 
 struct CandArgs {
     const __nv_bfloat16* Ub;   // [num_eval, D] bf16 rows of the users being evaluated (gathered)
@@ -305,39 +308,46 @@ struct CandArgs {
     const int32_t* users;      // [num_eval] user ids (train CSR is indexed by user id)
     const int64_t* train_ptr; const int32_t* train_idx;
     int dbg;                   // NRC_TC_DBG experiment bits (0 in normal use): 1 skip epilogue, 2 skip TMA, 4 skip MMA, 8 TMEM read-out only
-    int num_eval, N, D, LQ, cap;   // LQ: rank of the running threshold (= min(2*top_k, N), evaluate.h:38)
-    int32_t* cand;             // [num_eval, cap] candidate item ids, ascending
-    int32_t* cand_cnt;         // [num_eval] number of candidates seen (> cap => overflow)
+    int num_eval, N, D;
+    int LQ;                    // rank of the running threshold kept per (user, slot)
+    int lstride;               // shared-memory words per list (odd: conflict-free whatever entry a lane touches)
+    int seg_tiles;             // item tiles per grid.y segment
+    int nslots;                // candidate lists per user = gridDim.y * STREAMS
+    int cap;                   // entries per list
+    int32_t* cand;             // [num_eval, nslots, cap] candidate item ids, ascending inside a list
+    int32_t* cand_cnt;         // [num_eval, nslots] candidates seen (> cap => overflow)
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int STREAMS>
+__global__ void __launch_bounds__((4 * STREAMS + 2) * 32, 1)
 tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV) {
+    constexpr int kMmaWarp = 4 * STREAMS, kTmaWarp = 4 * STREAMS + 1, kThreads = (4 * STREAMS + 2) * 32;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int D = P.D;
     uint8_t* sA = smem;                                   // 128 x D bf16, SWIZZLE_128B blocks
-    uint8_t* sB0 = sA + (size_t)kM * D * 2;               // 2 stages of 256 x D bf16
-    uint8_t* sB1 = sB0 + (size_t)kN * D * 2;
-    float* sList = reinterpret_cast<float*>(sB1 + (size_t)kN * D * 2);   // [128][K+1]
-    __shared__ uint64_t full_b[2], empty_b[2], acc_full[2], acc_empty[2];
+    uint8_t* sB = sA + (size_t)kM * D * 2;                // kStages stages of 128 x D bf16
+    const uint32_t stage_bytes = (uint32_t)kNT * D * 2;
+    float* sList = reinterpret_cast<float*>(sB + (size_t)kStages * stage_bytes);   // [STREAMS][128][lstride]
+    __shared__ uint64_t full_b[kStages], acc_full[kStages], acc_empty[kStages];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * kM;
     const int valid_rows = min(kM, P.num_eval - row0);
-    const int T = (P.N + kN - 1) / kN;
+    const int t_begin = blockIdx.y * P.seg_tiles;                       // first item tile of this CTA
+    const int T = min(P.seg_tiles, (P.N + kNT - 1) / kNT - t_begin);       // its tile count (>= 1)
 
     load_tile_sw128(sA, P.Ub + (size_t)row0 * D, kM, valid_rows, D, tid, kThreads);
-    for (int i = tid; i < kM * kListStride; i += kThreads) sList[i] = -INFINITY;
+    for (int i = tid; i < STREAMS * kM * P.lstride; i += kThreads) sList[i] = -INFINITY;
     fence_async_smem();
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_b[i], 1);   // the producer's arrive.expect_tx; the copy engine completes the bytes
-            mbar_init(&empty_b[i], 1);
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                      "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -347,62 +357,83 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp == 5) {
+    if (warp == kTmaWarp) {
         // ---------------- producer (one thread): item tiles -> shared memory by TMA ----------------
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapV)) : "memory");
-            const uint32_t b0 = smem_u32(sB0), b1 = smem_u32(sB1);
-            const uint32_t stage_bytes = (uint32_t)kN * D * 2;
+            const uint32_t b0 = smem_u32(sB);
             for (int t = 0; t < T; ++t) {
-                const int s = t & 1, ph = (t >> 1) & 1;
-                mbar_wait(&empty_b[s], ph ^ 1);
+                const int s = t & (kStages - 1), ph = (t / kStages) & 1;
+                mbar_wait(&acc_full[s], ph ^ 1);   // MMA of tile t - kStages has read this stage
                 if (P.dbg & 2) { mbar_arrive(&full_b[s]); continue; }
                 mbar_arrive_expect_tx(&full_b[s], stage_bytes);
-                for (int kb = 0; kb < D / 64; ++kb)   // one 256 x 64 box per 128-byte K block
-                    tma_load_2d((s ? b1 : b0) + (uint32_t)kb * kN * 128, &tmapV, kb * 64, t * kN, &full_b[s]);
+                for (int kb = 0; kb < D / 64; ++kb)   // one 128 x 64 box per 128-byte K block
+                    tma_load_2d(b0 + (uint32_t)s * stage_bytes + (uint32_t)kb * kNT * 128, &tmapV, kb * 64, (t_begin + t) * kNT, &full_b[s]);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == kMmaWarp) {
         // ---------------- MMA issuer (one thread) ----------------
         if (lane == 0) {
-            const uint32_t idesc = make_instr_desc(kM, kN);
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB0), b1 = smem_u32(sB1);
+            const uint32_t idesc = make_instr_desc(kM, kNT);
+            // Descriptors differ only in the 14-bit start-address field (16-byte units; shared
+            // memory is < 256 KB, so adding offsets never carries out of the field): build the two
+            // bases once and add per stage / k-step -- the issue loop must stay well under the
+            // 512 cycles the tensor pipe needs per 128 x 128 x D tile.
+            const uint64_t a_base = sw128_desc(smem_u32(sA), kM, 0);
+            const uint64_t b_base = sw128_desc(smem_u32(sB), kNT, 0);
+            const int nks = D / kUmmaK;
             for (int t = 0; t < T; ++t) {
-                const int s = t & 1, ph = (t >> 1) & 1;
+                const int s = t & (kStages - 1), ph = (t / kStages) & 1;
                 mbar_wait(&full_b[s], ph);
                 mbar_wait(&acc_empty[s], ph ^ 1);
                 tc_fence_after();
-                const uint32_t td = tmem_base + (uint32_t)s * kN;
-                if (!(P.dbg & 4))
-                for (int ks = 0; ks < D / kUmmaK; ++ks)
-                    umma_bf16(td, sw128_desc(a0, kM, ks), sw128_desc(s ? b1 : b0, kN, ks), idesc, ks > 0 ? 1u : 0u);
-                umma_commit(&empty_b[s]);
-                umma_commit(&acc_full[s]);
+                const uint32_t td = tmem_base + (uint32_t)s * kNT;
+                const uint64_t bb = b_base + (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
+                if (!(P.dbg & 4)) {
+#pragma unroll 4
+                    for (int ks = 0; ks < nks; ++ks) {
+                        // k-step ks: 64-element K block (ks >> 2) of 128 rows x 128 B, 32 B per step inside it
+                        const uint64_t koff = (uint64_t)((((uint32_t)ks >> 2) * kM * 128u + ((uint32_t)ks & 3u) * 32u) >> 4);
+                        umma_bf16(td, a_base + koff, bb + koff, idesc, ks > 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(&acc_full[s]);   // "MMA of tile t done": frees the smem stage AND publishes the accumulator
             }
         }
     } else {
         // ---------------- epilogue: one user per thread ----------------
-        const int r = warp * 32 + lane;              // row inside the tile == TMEM lane
+        const int q = warp >> 2, wq = warp & 3;      // warp set (stream) and TMEM lane quarter
+        const int r = wq * 32 + lane;                // row inside the tile == TMEM lane
         const int row = row0 + r;
         const bool live = row < P.num_eval;
-        float* lst = sList + r * kListStride;   // odd stride: conflict-free whatever slot each lane touches
+        float* lst = sList + (q * kM + r) * P.lstride;
+        const int slot = blockIdx.y * STREAMS + q;
         const float margin = live ? P.margin[row] : 0.0f;
         const int u = live ? P.users[row] : 0;
         const int64_t tb = live ? P.train_ptr[u] : 0;
         const int tl = live ? (int)(P.train_ptr[u + 1] - tb) : 0;
-        int32_t* my_cand = P.cand + (size_t)row * P.cap;
+        int32_t* my_cand = P.cand + ((size_t)row * P.nslots + slot) * P.cap;
         float thr = -INFINITY, thr_m = -INFINITY;
         int cnt = 0;
         // merge-walk over the user's sorted train row: items arrive in ascending order, so the
         // mask test of a candidate is "advance the cursor to >= item, compare" (amortised O(deg))
         int tpos = 0;
-        int tnext = (tl > 0) ? __ldg(P.train_idx + tb) : INT32_MAX;
-        int tahead = (tl > 1) ? __ldg(P.train_idx + tb + 1) : INT32_MAX;   // prefetched: advancing never waits on memory
-        for (int t = 0; t < T; ++t) {
-            const int s = t & 1, ph = (t >> 1) & 1;
+        if (t_begin > 0) {   // first train item at or after this segment's first item
+            int lo = 0, hi = tl;
+            const int first = t_begin * kNT;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(P.train_idx + tb + mid) < first) lo = mid + 1; else hi = mid;
+            }
+            tpos = lo;
+        }
+        int tnext = (tpos < tl) ? __ldg(P.train_idx + tb + tpos) : INT32_MAX;
+        int tahead = (tpos + 1 < tl) ? __ldg(P.train_idx + tb + tpos + 1) : INT32_MAX;   // prefetched: advancing never waits on memory
+        for (int t = q; t < T; t += STREAMS) {
+            const int s = t & (kStages - 1), ph = (t / kStages) & 1;
             mbar_wait(&acc_full[s], ph);
             tc_fence_after();
-            // filter one chunk of 32 columns (items t*kN + c ..) held in registers
+            // filter one chunk of 32 columns (items t*kNT + c ..) held in registers
             auto filter_chunk = [&](const uint32_t (&raw)[32], const int c) {
                 if (P.dbg & 8) return;   // experiment: Tensor Memory read-out only
                 float v[32];
@@ -424,7 +455,7 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
                     for (int i = 0; i < 32; ++i) m4[i & 3] |= (v[i] > thr_m ? 1u : 0u) << i;
                     m = (m4[0] | m4[1]) | (m4[2] | m4[3]);
                 }
-                const int item0 = t * kN + c;
+                const int item0 = (t_begin + t) * kNT + c;
                 if (item0 + 32 > P.N) m &= (item0 >= P.N) ? 0u : ((1u << (P.N - item0)) - 1u);
                 if (!live) m = 0u;
                 while (m) {                       // rare: ~(K+1) ln(N/(K+1)) times per user in total
@@ -464,30 +495,30 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
                 }
             };
             // two chunks in flight: tcgen05.ld of chunk c+1 overlaps the filtering of chunk c
-            const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * kN);
+            const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(s * kNT);
             uint32_t ra[32], rb[32];
             if (P.dbg & 1) { tc_fence_before(); mbar_arrive(&acc_empty[s]); continue; }
             __syncwarp();   // the candidate branch diverges; tcgen05.ld needs the whole warp
             tmem_ld32_issue(tbase, ra);
 #pragma unroll 1
-            for (int c = 0; c < kN; c += 64) {
+            for (int c = 0; c < kNT; c += 64) {
                 tmem_ld_wait(ra);
                 tmem_ld32_issue(tbase + (uint32_t)(c + 32), rb);
                 filter_chunk(ra, c);
                 __syncwarp();
                 tmem_ld_wait(rb);
-                if (c + 64 < kN) tmem_ld32_issue(tbase + (uint32_t)(c + 64), ra);
+                if (c + 64 < kNT) tmem_ld32_issue(tbase + (uint32_t)(c + 64), ra);
                 filter_chunk(rb, c + 32);
                 __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[s]);
         }
-        if (live) P.cand_cnt[row] = cnt;
+        if (live) P.cand_cnt[(size_t)row * P.nslots + slot] = cnt;
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
 // bf16 copy of the item table + largest row norm (positive floats order like their bit patterns)
@@ -540,49 +571,106 @@ __global__ void tc_prepare_users_kernel(const float* __restrict__ U, const int32
 namespace nrc {
 namespace tc {
 
-// library-owned workspace, grown on demand (never inside a stream capture)
-static void* g_ws = nullptr;
-static size_t g_ws_bytes = 0;
-static cudaEvent_t g_ev[2] = {nullptr, nullptr};   // around the last tc_candidate_kernel launch
+// library-owned workspaces, grown on demand (never inside a stream capture)
+struct Arena {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t need) {
+        if (need <= bytes) return NRC_OK;
+        if (p) NRC_CUDA_CHECK(cudaFree(p));
+        p = nullptr; bytes = 0;
+        NRC_CUDA_CHECK(cudaMalloc(&p, need));
+        bytes = need;
+        return NRC_OK;
+    }
+};
+static Arena g_items;          // bf16 item table + max row norm
+static Arena g_pass[2];        // per pass: bf16 user rows, margins, candidate lists and counts
+static const __nv_bfloat16* g_vb = nullptr;
+static unsigned int* g_vmax = nullptr;
+static int g_items_n = 0, g_items_d = 0;
+static cudaEvent_t g_ev[2] = {nullptr, nullptr};   // around the last main-pass tc_candidate_kernel launch
 static double g_last_flops = 0.0;
 
-int run_candidates(const float* U, const float* V, int D, int N, const int32_t* users, int num_eval,
-                   const int64_t* train_ptr, const int32_t* train_idx, int LQ, int cap,
-                   const int32_t** cand, const int32_t** cand_cnt, cudaStream_t st) {
+static size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int prepare_items(const float* V, int D, int N, cudaStream_t st) {
     NRC_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, NRC_E_LIMIT,
                 "the tensor-core pass needs dim in {64, 128, 192, 256} (got %d)", D);
-    NRC_REQUIRE(LQ >= 1 && LQ <= kMaxList, NRC_E_LIMIT, "the tensor-core pass needs 2*top_k <= %d", kMaxList);
-    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t rows_pad = (size_t)((num_eval + kM - 1) / kM) * kM;
-    const size_t o_vb = 0;
-    const size_t o_ub = o_vb + up((size_t)N * D * 2);
-    const size_t o_margin = o_ub + up(rows_pad * D * 2);
-    const size_t o_vmax = o_margin + up(rows_pad * 4);
-    const size_t o_cnt = o_vmax + 256;
-    const size_t o_cand = o_cnt + up(rows_pad * 4);
-    const size_t total = o_cand + up(rows_pad * (size_t)cap * 4);
-    if (total > g_ws_bytes) {
-        if (g_ws) NRC_CUDA_CHECK(cudaFree(g_ws));
-        g_ws = nullptr; g_ws_bytes = 0;
-        NRC_CUDA_CHECK(cudaMalloc(&g_ws, total));
-        g_ws_bytes = total;
+    const size_t o_vmax = up256((size_t)N * D * 2);
+    int rc = g_items.reserve(o_vmax + 256);
+    if (rc) return rc;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(g_items.p);
+    __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(ws);
+    g_vmax = reinterpret_cast<unsigned int*>(ws + o_vmax);
+    NRC_CUDA_CHECK(cudaMemsetAsync(g_vmax, 0, 4, st));
+    tc_prepare_items_kernel<<<sm_count() * 8, 256, 0, st>>>(V, N, D, Vb, g_vmax);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    g_vb = Vb; g_items_n = N; g_items_d = D;
+    return NRC_OK;
+}
+
+template <int STREAMS>
+static int launch_candidates(const CandArgs& P, const CUtensorMap& tmapV, dim3 grid, size_t smem, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel<STREAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            220 * 1024));
+        attr_done = true;
     }
-    uint8_t* ws = reinterpret_cast<uint8_t*>(g_ws);
-    __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(ws + o_vb);
+    tc_candidate_kernel<STREAMS><<<grid, (4 * STREAMS + 2) * 32, smem, st>>>(P, tmapV);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const int64_t* train_ptr,
+             const int32_t* train_idx, int LQ, int streams, int cap, CandLists* out, cudaStream_t st) {
+    NRC_REQUIRE(pass == 0 || pass == 1, NRC_E_VALUE, "pass must be 0 or 1");
+    NRC_REQUIRE(g_vb != nullptr, NRC_E_VALUE, "prepare_items has not run");
+    NRC_REQUIRE(streams == 1 || streams == 2, NRC_E_VALUE, "streams must be 1 or 2");
+    NRC_REQUIRE(LQ >= 1 && LQ <= kMaxList && (streams == 1 || LQ <= 32), NRC_E_LIMIT,
+                "threshold rank %d outside this build's range", LQ);
+    const int D = g_items_d, N = g_items_n;
+    const int row_tiles = (num_rows + kM - 1) / kM;
+    const int T = (N + kNT - 1) / kNT;
+    // Item segments (grid.y): with few user tiles, split the catalogue so that every SM has a CTA.
+    // Each segment restarts its threshold (still a lower bound of the true one), which costs a few
+    // more candidates; pick the split with the fewest waves per unit of work, at most 8 unless a
+    // single wave needs more (16 at most), and never segments shorter than 32 tiles.
+    int G = 1;
+    {
+        const int sms = sm_count();
+        const int gmax = (row_tiles * 8 < sms) ? ((sms / row_tiles < 16) ? sms / row_tiles : 16) : 8;
+        double best = 1e30;
+        for (int g = 1; g <= gmax && g * 32 <= (T > 32 ? T : 32); ++g) {
+            const int ctas = row_tiles * g;
+            const double cost = (double)((ctas + sms - 1) / sms) / g * (1.0 + 0.02 * (g - 1));
+            if (cost < best - 1e-9) { best = cost; G = g; }
+        }
+    }
+    const int seg_tiles = (T + G - 1) / G;
+    G = (T + seg_tiles - 1) / seg_tiles;           // no empty segment
+    const int nslots = G * streams;
+    const int lstride = (LQ <= 32) ? 33 : 65;
+    const size_t rows_pad = (size_t)row_tiles * kM;
+    const size_t o_ub = 0;
+    const size_t o_margin = o_ub + up256(rows_pad * D * 2);
+    const size_t o_cnt = o_margin + up256(rows_pad * 4);
+    const size_t o_cand = o_cnt + up256(rows_pad * nslots * 4);
+    const size_t total = o_cand + up256(rows_pad * (size_t)nslots * cap * 4);
+    int rc = g_pass[pass].reserve(total);
+    if (rc) return rc;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(g_pass[pass].p);
     __nv_bfloat16* Ub = reinterpret_cast<__nv_bfloat16*>(ws + o_ub);
     float* margin = reinterpret_cast<float*>(ws + o_margin);
-    unsigned int* vmax = reinterpret_cast<unsigned int*>(ws + o_vmax);
     int32_t* cnt = reinterpret_cast<int32_t*>(ws + o_cnt);
     int32_t* cd = reinterpret_cast<int32_t*>(ws + o_cand);
-
-    NRC_CUDA_CHECK(cudaMemsetAsync(vmax, 0, 4, st));
-    tc_prepare_items_kernel<<<sm_count() * 8, 256, 0, st>>>(V, N, D, Vb, vmax);
-    NRC_CUDA_CHECK(cudaGetLastError());
-    tc_prepare_users_kernel<<<(num_eval * 32 + 255) / 256, 256, 0, st>>>(U, users, num_eval, D, vmax, Ub, margin);
+    tc_prepare_users_kernel<<<(num_rows * 32 + 255) / 256, 256, 0, st>>>(U, users, num_rows, D, g_vmax, Ub, margin);
     NRC_CUDA_CHECK(cudaGetLastError());
 
     const char* dbg_env = getenv("NRC_TC_DBG");
-    CandArgs P{Ub, Vb, margin, users, train_ptr, train_idx, dbg_env ? atoi(dbg_env) : 0, num_eval, N, D, LQ, cap, cd, cnt};
+    CandArgs P{Ub, g_vb, margin, users, train_ptr, train_idx, dbg_env ? atoi(dbg_env) : 0, num_rows, N, D,
+               LQ, lstride, seg_tiles, nslots, cap, cd, cnt};
     CUtensorMap tmapV;
     {   // bf16 item table [N, D] row-major; box = 256 items x 64 k (one 128-byte swizzle span)
         static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -596,33 +684,34 @@ int run_candidates(const float* U, const float* V, int D, int N, const int32_t* 
         }
         const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)N};
         const cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
-        const cuuint32_t box[2] = {64u, (cuuint32_t)kN};
+        const cuuint32_t box[2] = {64u, (cuuint32_t)kNT};
         const cuuint32_t estr[2] = {1u, 1u};
-        const CUresult cr = encode(&tmapV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)Vb, gdim, gstride, box, estr,
+        const CUresult cr = encode(&tmapV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)g_vb, gdim, gstride, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         NRC_REQUIRE(cr == CUDA_SUCCESS, NRC_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
     }
-    size_t smem = (size_t)(kM + 2 * kN) * D * 2 + (size_t)kM * kListStride * 4;
+    size_t smem = (size_t)(kM + kStages * kNT) * D * 2 + (size_t)streams * kM * lstride * 4;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
     NRC_REQUIRE(smem <= 220 * 1024, NRC_E_LIMIT, "tensor-core pass needs %zu B of shared memory", smem);
-    static bool attr_done = false;
-    if (!attr_done) {
-        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            220 * 1024));
-        attr_done = true;
+    const dim3 grid(row_tiles, G);
+    if (pass == 0) {
+        if (!g_ev[0]) {
+            NRC_CUDA_CHECK(cudaEventCreate(&g_ev[0]));
+            NRC_CUDA_CHECK(cudaEventCreate(&g_ev[1]));
+        }
+        NRC_CUDA_CHECK(cudaEventRecord(g_ev[0], st));
     }
-    if (!g_ev[0]) {
-        NRC_CUDA_CHECK(cudaEventCreate(&g_ev[0]));
-        NRC_CUDA_CHECK(cudaEventCreate(&g_ev[1]));
+    rc = (streams == 2) ? launch_candidates<2>(P, tmapV, grid, smem, st) : launch_candidates<1>(P, tmapV, grid, smem, st);
+    if (rc) return rc;
+    if (pass == 0) {
+        NRC_CUDA_CHECK(cudaEventRecord(g_ev[1], st));
+        g_last_flops = 2.0 * (double)num_rows * (double)N * (double)D;
     }
-    NRC_CUDA_CHECK(cudaEventRecord(g_ev[0], st));
-    tc_candidate_kernel<<<(num_eval + kM - 1) / kM, kThreads, smem, st>>>(P, tmapV);
-    NRC_CUDA_CHECK(cudaGetLastError());
-    NRC_CUDA_CHECK(cudaEventRecord(g_ev[1], st));
-    g_last_flops = 2.0 * (double)num_eval * (double)N * (double)D;
-    *cand = cd;
-    *cand_cnt = cnt;
+    out->cand = cd;
+    out->cnt = cnt;
+    out->nslots = nslots;
+    out->cap = cap;
     return NRC_OK;
 }
 

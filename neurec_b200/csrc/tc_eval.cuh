@@ -5,14 +5,29 @@
 namespace nrc {
 namespace tc {
 
-// Runs bf16 conversion + the tcgen05 candidate kernel on `st`.  LQ = rank of the running
-// threshold: every unmasked item whose score may exceed the LQ-th best score of the items before
-// it is reported (LQ = min(2*top_k, N) covers every element that can enter the reference's heap).  On return (asynchronously)
-// *cand points at [num_eval, cap] ascending candidate item ids and *cand_cnt at [num_eval]
-// counts (count > cap = overflow).  Buffers are library-owned and reused between calls.
-int run_candidates(const float* U, const float* V, int D, int N, const int32_t* users, int num_eval,
-                   const int64_t* train_ptr, const int32_t* train_idx, int LQ, int cap,
-                   const int32_t** cand, const int32_t** cand_cnt, cudaStream_t st);
+// Candidate lists produced by one pass: `nslots` lists per row (one per item segment and epilogue
+// stream), each ascending, `cap` entries long; cnt > cap marks an overflowed list.
+struct CandLists {
+    const int32_t* cand;   // [rows, nslots, cap]
+    const int32_t* cnt;    // [rows, nslots]
+    int nslots, cap;
+};
+
+// bf16 copy of the item table + its largest row norm, kept in a library-owned buffer until the
+// next call.  dim in {64, 128, 192, 256}.
+int prepare_items(const float* V, int D, int N, cudaStream_t st);
+
+// One tcgen05 candidate pass over the prepared item table for the rows `users` (device ids).
+// LQ = rank of the running threshold: every unmasked item whose score may exceed the LQ-th best
+// score of the items before it IN ITS LIST'S ITEM SUBSET is reported, so each list is a superset
+// of what a threshold over the whole prefix would keep:
+//   pass 0 (main):   LQ = top_k + 1, streams = 2 (two epilogue warp sets, even / odd tiles) --
+//                    every item of the exact top (K+1) is in some list;
+//   pass 1 (replay): LQ = min(2*top_k, N), streams = 1 -- lists in slot order are ascending and
+//                    hold every element that can enter the reference's heap (evaluate.h:38-41).
+// Buffers are library-owned (one arena per pass) and reused between calls.
+int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const int64_t* train_ptr,
+             const int32_t* train_idx, int LQ, int streams, int cap, CandLists* out, cudaStream_t st);
 
 }  // namespace tc
 }  // namespace nrc
