@@ -1192,33 +1192,45 @@ __global__ void tc_gather_users_kernel(const int32_t* __restrict__ users, const 
 // Replay pass, for the users with ties: the reference's heap (evaluate.h:33-47) replayed over the
 // only elements that can change it -- the first L items, which seed it, and the replay pass's
 // candidates in ascending item order (lists in slot order), a superset of every later element
-// that beats the heap root when offered.  `urow[i]` is the row of the original call.
+// that beats the heap root when offered.  One CTA per user: all warps re-score the candidates
+// exactly (scores parked in `scratch`), then warp 0 replays the heap.  `urow[i]` is the row of
+// the original call.
 __global__ void __launch_bounds__(256)
 eval_tc_replay_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, int D,
                       const int32_t* __restrict__ users2, const int32_t* __restrict__ urow, int n_und,
                       const int64_t* __restrict__ train_ptr, const int32_t* __restrict__ train_idx,
                       const int64_t* __restrict__ test_ptr, const int32_t* __restrict__ test_idx,
-                      const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int nslots, int cap,
+                      const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+                      float* __restrict__ scratch, int nslots, int cap,
                       int K, int L, int M, float* __restrict__ results, int32_t* __restrict__ ranks,
                       int32_t* __restrict__ slow_count, int32_t* __restrict__ slow_rows) {
     extern __shared__ int smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (i >= n_und) return;
+    const int i = blockIdx.x;
     const int row = urow[i];
-    float* su = reinterpret_cast<float*>(smem) + warp * ((D + 4 * K + 2 * L + 3) & ~3);
-    int* rank = reinterpret_cast<int*>(su + D);
+    float* su = reinterpret_cast<float*>(smem);
+    int* rank = reinterpret_cast<int*>(su + ((D + 3) & ~3));
     const int32_t* ccnt = cand_cnt + (size_t)i * nslots;
     bool overflow = false;
-    for (int sl = lane; sl < nslots; sl += kWarp) overflow |= ccnt[sl] > cap;
-    if (__any_sync(kFull, overflow)) {
-        if (lane == 0) slow_rows[atomicAdd(slow_count, 1)] = row;
+    for (int sl = threadIdx.x; sl < nslots; sl += blockDim.x) overflow |= ccnt[sl] > cap;
+    if (__syncthreads_or(overflow ? 1 : 0)) {
+        if (threadIdx.x == 0) slow_rows[atomicAdd(slow_count, 1)] = row;
         return;
     }
     const int u = users2[i];
-    for (int k = lane; k < D; k += kWarp) su[k] = Utab[(size_t)u * D + k];
-    __syncwarp();
+    for (int k = threadIdx.x; k < D; k += blockDim.x) su[k] = Utab[(size_t)u * D + k];
+    __syncthreads();
     const float4* su4 = reinterpret_cast<const float4*>(su);
+    for (int sl = 0; sl < nslots; ++sl) {   // exact scores of every candidate, one per thread
+        const int cnt = ccnt[sl];
+        const size_t base = ((size_t)i * nslots + sl) * cap;
+        for (int idx = threadIdx.x; idx < cnt; idx += blockDim.x) {
+            const int item = cand[base + idx];
+            scratch[base + idx] = (item >= L) ? tc_exact_score(su4, Vtab, item, D) : -INFINITY;
+        }
+    }
+    __syncthreads();
+    if (warp != 0) return;
     Heap h;
     h.idx = rank + 4 * K;
     h.val = reinterpret_cast<float*>(h.idx + L);
@@ -1236,12 +1248,12 @@ eval_tc_replay_kernel(const float* __restrict__ Utab, const float* __restrict__ 
     float thr = h.val[0];
     for (int sl = 0; sl < nslots; ++sl) {
         const int cnt = ccnt[sl];
-        const int32_t* crow = cand + ((size_t)i * nslots + sl) * cap;
-        for (int base = 0; base < cnt; base += kWarp) {
-            const int idx = base + lane;
-            const int item = (idx < cnt) ? crow[idx] : -1;
+        const size_t base = ((size_t)i * nslots + sl) * cap;
+        for (int b0 = 0; b0 < cnt; b0 += kWarp) {
+            const int idx = b0 + lane;
+            const int item = (idx < cnt) ? cand[base + idx] : -1;
             const bool ok = item >= L;
-            const float s = ok ? tc_exact_score(su4, Vtab, item, D) : -INFINITY;
+            const float s = ok ? scratch[base + idx] : -INFINITY;
             thr = offer_candidates(h, L, s, item, ok, thr, lane);
         }
     }
@@ -1287,7 +1299,7 @@ extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, 
     rc = tc::prepare_items(item_table, dim, num_items, st);
     if (rc) return rc;
     tc::CandLists c0;
-    rc = tc::run_pass(0, user_table, users, num_eval_users, train_indptr, train_indices, K + 1, 2, cap, &c0, st);
+    rc = tc::run_pass(0, user_table, users, num_eval_users, train_indptr, train_indices, K + 1, cap, &c0, st);
     if (rc) return rc;
     // g_slow: [count, rows...] full-catalogue replays; g_und: [count, rows..., gathered user ids...]
     if ((size_t)num_eval_users + 1 > g_slow_cap) {
@@ -1325,13 +1337,14 @@ extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, 
         tc_gather_users_kernel<<<(n_und + 255) / 256, 256, 0, st>>>(users, und_rows, n_und, users2);
         NRC_CUDA_CHECK(cudaGetLastError());
         tc::CandLists c1;
-        rc = tc::run_pass(1, user_table, users2, n_und, train_indptr, train_indices, L, 1, cap > 2048 ? cap : 2048,
+        rc = tc::run_pass(1, user_table, users2, n_und, train_indptr, train_indices, L, cap > 2048 ? cap : 2048,
                           &c1, st);
         if (rc) return rc;
-        const size_t smem = (size_t)warps * ((dim + 4 * K + 2 * L + 3) & ~3) * 4;
-        eval_tc_replay_kernel<<<(n_und + warps - 1) / warps, warps * 32, smem, st>>>(
+        const size_t smem = (size_t)(((dim + 3) & ~3) + 4 * K + 2 * L) * 4;
+        eval_tc_replay_kernel<<<n_und, 256, smem, st>>>(
             user_table, item_table, dim, users2, und_rows, n_und, train_indptr, train_indices, test_indptr,
-            test_indices, c1.cand, c1.cnt, c1.nslots, c1.cap, K, L, metric_num, results, ranks, g_slow, g_slow + 1);
+            test_indices, c1.cand, c1.cnt, c1.scratch, c1.nslots, c1.cap, K, L, metric_num, results, ranks, g_slow,
+            g_slow + 1);
         NRC_CUDA_CHECK(cudaGetLastError());
     }
     {   // full-catalogue heap replay for users whose candidate list overflowed (rare)

@@ -294,12 +294,21 @@ extern "C" int nrc_tc_gemm_debug(const void* a_bf16, const void* b_bf16, int32_t
 namespace nrc {
 namespace tc {
 
-// Warp roles, for STREAMS = 1 or 2 epilogue warp sets: warps [0, 4*STREAMS) epilogue (set q =
-// warp / 4 filters the tiles t == q (mod STREAMS) of this CTA, i.e. TMEM stage q when STREAMS == 2),
-// warp 4*STREAMS the MMA issuer, warp 4*STREAMS + 1 the TMA producer.
+// Candidate kernel.  One CTA owns 256 users (two UMMA M=128 halves, both multiplied with every
+// item tile, so the bf16 item table is read from L2 once per 256 users -- with 128 users per CTA
+// the kernel sat on the L2->SM bandwidth cap) and one contiguous range of item tiles.
+//   warps 0-7  epilogue: warp w serves user half h = w / 4 through TMEM lanes 32*(w%4) .. +31;
+//              one thread = one user: running threshold, min-heap of the LQ best approximate
+//              scores, merge-walk over the user's train row, candidate list
+//   warp 8     MMA issuer (one thread): 2 x D/16 tcgen05.mma (M128 N128 K16) per item tile
+//   warp 9     TMA producer (one thread): item tile -> shared memory (SWIZZLE_128B boxes)
+// Pipelines: `nst` shared-memory item stages (full_b / empty_b) and 2 TMEM stages of 2 x 128 fp32
+// columns (acc_full / acc_empty), so the MMAs of tile t+1 overlap the filtering of tile t.
 constexpr int kMaxList = 64;           // threshold rank <= 64 (2*top_k for the tie-replay pass)
-constexpr int kNT = 128;               // items per candidate-kernel tile (UMMA N)
-constexpr int kStages = 4;             // shared-memory item-tile stages == TMEM accumulator stages (4 x 128 columns)
+constexpr int kMU = 256;               // users per CTA
+constexpr int kNT = 128;               // items per tile (UMMA N)
+constexpr int kMaxStages = 3;
+constexpr int kCandThreads = 320;
 
 struct CandArgs {
     const __nv_bfloat16* Ub;   // [num_eval, D] bf16 rows of the users being evaluated (gathered)
@@ -309,41 +318,46 @@ struct CandArgs {
     const int64_t* train_ptr; const int32_t* train_idx;
     int dbg;                   // NRC_TC_DBG experiment bits (0 in normal use): 1 skip epilogue, 2 skip TMA, 4 skip MMA, 8 TMEM read-out only
     int num_eval, N, D;
-    int LQ;                    // rank of the running threshold kept per (user, slot)
+    int LQ;                    // rank of the running threshold kept per (user, list)
     int lstride;               // shared-memory words per list (odd: conflict-free whatever entry a lane touches)
+    int nst;                   // shared-memory item stages (2 or 3)
     int seg_tiles;             // item tiles per grid.y segment
-    int nslots;                // candidate lists per user = gridDim.y * STREAMS
+    int nslots;                // candidate lists per user = gridDim.y
     int cap;                   // entries per list
     int32_t* cand;             // [num_eval, nslots, cap] candidate item ids, ascending inside a list
     int32_t* cand_cnt;         // [num_eval, nslots] candidates seen (> cap => overflow)
 };
 
-template <int STREAMS>
-__global__ void __launch_bounds__((4 * STREAMS + 2) * 32, 1)
+__global__ void __launch_bounds__(kCandThreads, 1)
 tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV) {
-    constexpr int kMmaWarp = 4 * STREAMS, kTmaWarp = 4 * STREAMS + 1, kThreads = (4 * STREAMS + 2) * 32;
+    constexpr int kMmaWarp = 8, kTmaWarp = 9;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int D = P.D;
-    uint8_t* sA = smem;                                   // 128 x D bf16, SWIZZLE_128B blocks
-    uint8_t* sB = sA + (size_t)kM * D * 2;                // kStages stages of 128 x D bf16
-    const uint32_t stage_bytes = (uint32_t)kNT * D * 2;
-    float* sList = reinterpret_cast<float*>(sB + (size_t)kStages * stage_bytes);   // [STREAMS][128][lstride]
-    __shared__ uint64_t full_b[kStages], acc_full[kStages], acc_empty[kStages];
+    const uint32_t half_bytes = (uint32_t)kM * D * 2;     // one 128-user operand tile
+    const uint32_t stage_bytes = (uint32_t)kNT * D * 2;   // one 128-item operand tile
+    uint8_t* sA = smem;                                   // 2 x [128 x D] bf16, SWIZZLE_128B blocks
+    uint8_t* sB = sA + 2 * (size_t)half_bytes;            // nst x [128 x D] bf16
+    float* sList = reinterpret_cast<float*>(sB + (size_t)P.nst * stage_bytes);   // [256][lstride]
+    __shared__ uint64_t full_b[kMaxStages], empty_b[kMaxStages], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = blockIdx.x * kM;
-    const int valid_rows = min(kM, P.num_eval - row0);
-    const int t_begin = blockIdx.y * P.seg_tiles;                       // first item tile of this CTA
-    const int T = min(P.seg_tiles, (P.N + kNT - 1) / kNT - t_begin);       // its tile count (>= 1)
+    const int row0 = blockIdx.x * kMU;
+    const int t_begin = blockIdx.y * P.seg_tiles;                         // first item tile of this CTA
+    const int T = min(P.seg_tiles, (P.N + kNT - 1) / kNT - t_begin);      // its tile count (>= 1)
 
-    load_tile_sw128(sA, P.Ub + (size_t)row0 * D, kM, valid_rows, D, tid, kThreads);
-    for (int i = tid; i < STREAMS * kM * P.lstride; i += kThreads) sList[i] = -INFINITY;
+    for (int h = 0; h < 2; ++h)
+        load_tile_sw128(sA + (size_t)h * half_bytes, P.Ub + (size_t)(row0 + h * kM) * D, kM,
+                        max(0, min(kM, P.num_eval - row0 - h * kM)), D, tid, kCandThreads);
+    for (int i = tid; i < kMU * P.lstride; i += kCandThreads) sList[i] = -INFINITY;
     fence_async_smem();
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) {
-            mbar_init(&full_b[i], 1);   // the producer's arrive.expect_tx; the copy engine completes the bytes
+        for (int i = 0; i < kMaxStages; ++i) {
+            mbar_init(&full_b[i], 1);    // the producer's arrive.expect_tx; the copy engine completes the bytes
+            mbar_init(&empty_b[i], 1);   // tcgen05.commit of the tile that read the stage
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 128);
+            mbar_init(&acc_empty[i], 256);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -362,13 +376,18 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapV)) : "memory");
             const uint32_t b0 = smem_u32(sB);
+            int s = 0, ph = 0;
             for (int t = 0; t < T; ++t) {
-                const int s = t & (kStages - 1), ph = (t / kStages) & 1;
-                mbar_wait(&acc_full[s], ph ^ 1);   // MMA of tile t - kStages has read this stage
-                if (P.dbg & 2) { mbar_arrive(&full_b[s]); continue; }
-                mbar_arrive_expect_tx(&full_b[s], stage_bytes);
-                for (int kb = 0; kb < D / 64; ++kb)   // one 128 x 64 box per 128-byte K block
-                    tma_load_2d(b0 + (uint32_t)s * stage_bytes + (uint32_t)kb * kNT * 128, &tmapV, kb * 64, (t_begin + t) * kNT, &full_b[s]);
+                mbar_wait(&empty_b[s], ph ^ 1);
+                if (P.dbg & 2) {
+                    mbar_arrive(&full_b[s]);
+                } else {
+                    mbar_arrive_expect_tx(&full_b[s], stage_bytes);
+                    for (int kb = 0; kb < D / 64; ++kb)   // one 128 x 64 box per 128-byte K block
+                        tma_load_2d(b0 + (uint32_t)s * stage_bytes + (uint32_t)kb * kNT * 128, &tmapV, kb * 64,
+                                    (t_begin + t) * kNT, &full_b[s]);
+                }
+                if (++s == P.nst) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == kMmaWarp) {
@@ -376,38 +395,43 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
         if (lane == 0) {
             const uint32_t idesc = make_instr_desc(kM, kNT);
             // Descriptors differ only in the 14-bit start-address field (16-byte units; shared
-            // memory is < 256 KB, so adding offsets never carries out of the field): build the two
-            // bases once and add per stage / k-step -- the issue loop must stay well under the
-            // 512 cycles the tensor pipe needs per 128 x 128 x D tile.
+            // memory is < 256 KB, so adding offsets never carries out of the field).
             const uint64_t a_base = sw128_desc(smem_u32(sA), kM, 0);
             const uint64_t b_base = sw128_desc(smem_u32(sB), kNT, 0);
             const int nks = D / kUmmaK;
+            int s = 0, ph = 0;
             for (int t = 0; t < T; ++t) {
-                const int s = t & (kStages - 1), ph = (t / kStages) & 1;
+                const int a = t & 1, pa = (t >> 1) & 1;
                 mbar_wait(&full_b[s], ph);
-                mbar_wait(&acc_empty[s], ph ^ 1);
+                mbar_wait(&acc_empty[a], pa ^ 1);
                 tc_fence_after();
-                const uint32_t td = tmem_base + (uint32_t)s * kNT;
                 const uint64_t bb = b_base + (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
                 if (!(P.dbg & 4)) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t td = tmem_base + (uint32_t)(a * 256 + h * kNT);
+                        const uint64_t ah = a_base + (uint64_t)(((uint32_t)h * half_bytes) >> 4);
 #pragma unroll 4
-                    for (int ks = 0; ks < nks; ++ks) {
-                        // k-step ks: 64-element K block (ks >> 2) of 128 rows x 128 B, 32 B per step inside it
-                        const uint64_t koff = (uint64_t)((((uint32_t)ks >> 2) * kM * 128u + ((uint32_t)ks & 3u) * 32u) >> 4);
-                        umma_bf16(td, a_base + koff, bb + koff, idesc, ks > 0 ? 1u : 0u);
+                        for (int ks = 0; ks < nks; ++ks) {
+                            // k-step ks: 64-element K block (ks >> 2) of 128 rows x 128 B, 32 B per step inside it
+                            const uint64_t koff = (uint64_t)((((uint32_t)ks >> 2) * kM * 128u + ((uint32_t)ks & 3u) * 32u) >> 4);
+                            umma_bf16(td, ah + koff, bb + koff, idesc, ks > 0 ? 1u : 0u);
+                        }
                     }
                 }
-                umma_commit(&acc_full[s]);   // "MMA of tile t done": frees the smem stage AND publishes the accumulator
+                umma_commit(&empty_b[s]);    // the shared-memory stage may be refilled
+                umma_commit(&acc_full[a]);   // both 128 x 128 accumulators of tile t are complete
+                if (++s == P.nst) { s = 0; ph ^= 1; }
             }
         }
     } else {
         // ---------------- epilogue: one user per thread ----------------
-        const int q = warp >> 2, wq = warp & 3;      // warp set (stream) and TMEM lane quarter
-        const int r = wq * 32 + lane;                // row inside the tile == TMEM lane
+        const int h = warp >> 2, wq = warp & 3;      // user half and TMEM lane quarter
+        const int r = h * kM + wq * 32 + lane;       // user row inside the CTA
         const int row = row0 + r;
         const bool live = row < P.num_eval;
-        float* lst = sList + (q * kM + r) * P.lstride;
-        const int slot = blockIdx.y * STREAMS + q;
+        float* lst = sList + r * P.lstride;
+        const int slot = blockIdx.y;
         const float margin = live ? P.margin[row] : 0.0f;
         const int u = live ? P.users[row] : 0;
         const int64_t tb = live ? P.train_ptr[u] : 0;
@@ -429,18 +453,18 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
         }
         int tnext = (tpos < tl) ? __ldg(P.train_idx + tb + tpos) : INT32_MAX;
         int tahead = (tpos + 1 < tl) ? __ldg(P.train_idx + tb + tpos + 1) : INT32_MAX;   // prefetched: advancing never waits on memory
-        for (int t = q; t < T; t += STREAMS) {
-            const int s = t & (kStages - 1), ph = (t / kStages) & 1;
-            mbar_wait(&acc_full[s], ph);
+        for (int t = 0; t < T; ++t) {
+            const int a = t & 1, pa = (t >> 1) & 1;
+            mbar_wait(&acc_full[a], pa);
             tc_fence_after();
-            // filter one chunk of 32 columns (items t*kNT + c ..) held in registers
+            // filter one chunk of 32 columns (items (t_begin + t)*kNT + c ..) held in registers
             auto filter_chunk = [&](const uint32_t (&raw)[32], const int c) {
                 if (P.dbg & 8) return;   // experiment: Tensor Memory read-out only
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
                 // cheap common case: the chunk maximum does not reach the threshold
-                float t16[16];   // max tree: one epilogue warp per scheduler, so dependent chains are exposed
+                float t16[16];   // max tree: few warps per scheduler, so dependent chains are exposed
 #pragma unroll
                 for (int i = 0; i < 16; ++i) t16[i] = fmaxf(v[2 * i], v[2 * i + 1]);
 #pragma unroll
@@ -458,7 +482,7 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
                 const int item0 = (t_begin + t) * kNT + c;
                 if (item0 + 32 > P.N) m &= (item0 >= P.N) ? 0u : ((1u << (P.N - item0)) - 1u);
                 if (!live) m = 0u;
-                while (m) {                       // rare: ~(K+1) ln(N/(K+1)) times per user in total
+                while (m) {                       // rare: ~LQ ln(N/LQ) times per user in total
                     const int i = __ffs(m) - 1;
                     m &= m - 1;
                     float x = v[0];
@@ -494,10 +518,10 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
                     }
                 }
             };
+            if (P.dbg & 1) { tc_fence_before(); mbar_arrive(&acc_empty[a]); continue; }
             // two chunks in flight: tcgen05.ld of chunk c+1 overlaps the filtering of chunk c
-            const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(s * kNT);
+            const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * 256 + h * kNT);
             uint32_t ra[32], rb[32];
-            if (P.dbg & 1) { tc_fence_before(); mbar_arrive(&acc_empty[s]); continue; }
             __syncwarp();   // the candidate branch diverges; tcgen05.ld needs the whole warp
             tmem_ld32_issue(tbase, ra);
 #pragma unroll 1
@@ -512,7 +536,7 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
                 __syncwarp();
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[s]);
+            mbar_arrive(&acc_empty[a]);
         }
         if (live) P.cand_cnt[(size_t)row * P.nslots + slot] = cnt;
     }
@@ -610,37 +634,24 @@ int prepare_items(const float* V, int D, int N, cudaStream_t st) {
     return NRC_OK;
 }
 
-template <int STREAMS>
-static int launch_candidates(const CandArgs& P, const CUtensorMap& tmapV, dim3 grid, size_t smem, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel<STREAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            220 * 1024));
-        attr_done = true;
-    }
-    tc_candidate_kernel<STREAMS><<<grid, (4 * STREAMS + 2) * 32, smem, st>>>(P, tmapV);
-    NRC_CUDA_CHECK(cudaGetLastError());
-    return NRC_OK;
-}
-
 int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const int64_t* train_ptr,
-             const int32_t* train_idx, int LQ, int streams, int cap, CandLists* out, cudaStream_t st) {
+             const int32_t* train_idx, int LQ, int cap, CandLists* out, cudaStream_t st) {
     NRC_REQUIRE(pass == 0 || pass == 1, NRC_E_VALUE, "pass must be 0 or 1");
     NRC_REQUIRE(g_vb != nullptr, NRC_E_VALUE, "prepare_items has not run");
-    NRC_REQUIRE(streams == 1 || streams == 2, NRC_E_VALUE, "streams must be 1 or 2");
-    NRC_REQUIRE(LQ >= 1 && LQ <= kMaxList && (streams == 1 || LQ <= 32), NRC_E_LIMIT,
-                "threshold rank %d outside this build's range", LQ);
+    NRC_REQUIRE(LQ >= 1 && LQ <= kMaxList, NRC_E_LIMIT, "threshold rank %d outside [1, %d]", LQ, kMaxList);
     const int D = g_items_d, N = g_items_n;
-    const int row_tiles = (num_rows + kM - 1) / kM;
+    const int row_tiles = (num_rows + kMU - 1) / kMU;
     const int T = (N + kNT - 1) / kNT;
     // Item segments (grid.y): with few user tiles, split the catalogue so that every SM has a CTA.
     // Each segment restarts its threshold (still a lower bound of the true one), which costs a few
     // more candidates; pick the split with the fewest waves per unit of work, at most 8 unless a
-    // single wave needs more (16 at most), and never segments shorter than 32 tiles.
+    // single wave needs more (16 at most; 48 in the replay pass), and never segments shorter
+    // than 32 tiles.
     int G = 1;
     {
         const int sms = sm_count();
-        const int gmax = (row_tiles * 8 < sms) ? ((sms / row_tiles < 16) ? sms / row_tiles : 16) : 8;
+        const int few = (pass == 1) ? 48 : 16;   // the replay pass re-scores its lists with a whole CTA per user
+        const int gmax = (row_tiles * 8 < sms) ? ((sms / row_tiles < few) ? sms / row_tiles : few) : 8;
         double best = 1e30;
         for (int g = 1; g <= gmax && g * 32 <= (T > 32 ? T : 32); ++g) {
             const int ctas = row_tiles * g;
@@ -650,14 +661,20 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
     }
     const int seg_tiles = (T + G - 1) / G;
     G = (T + seg_tiles - 1) / seg_tiles;           // no empty segment
-    const int nslots = G * streams;
+    const int nslots = G;
     const int lstride = (LQ <= 32) ? 33 : 65;
-    const size_t rows_pad = (size_t)row_tiles * kM;
+    const size_t list_bytes = (size_t)kMU * lstride * 4;
+    const size_t fixed = (size_t)2 * kM * D * 2 + list_bytes + 2048;
+    int nst = (int)((227 * 1024 - fixed) / ((size_t)kNT * D * 2));
+    if (nst > kMaxStages) nst = kMaxStages;
+    NRC_REQUIRE(nst >= 2, NRC_E_LIMIT, "dim %d with threshold rank %d does not fit the tensor-core pass", D, LQ);
+    const size_t rows_pad = (size_t)row_tiles * kMU;
     const size_t o_ub = 0;
     const size_t o_margin = o_ub + up256(rows_pad * D * 2);
     const size_t o_cnt = o_margin + up256(rows_pad * 4);
     const size_t o_cand = o_cnt + up256(rows_pad * nslots * 4);
-    const size_t total = o_cand + up256(rows_pad * (size_t)nslots * cap * 4);
+    const size_t o_scr = o_cand + up256(rows_pad * (size_t)nslots * cap * 4);
+    const size_t total = o_scr + (pass == 1 ? up256(rows_pad * (size_t)nslots * cap * 4) : 0);
     int rc = g_pass[pass].reserve(total);
     if (rc) return rc;
     uint8_t* ws = reinterpret_cast<uint8_t*>(g_pass[pass].p);
@@ -670,9 +687,9 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
 
     const char* dbg_env = getenv("NRC_TC_DBG");
     CandArgs P{Ub, g_vb, margin, users, train_ptr, train_idx, dbg_env ? atoi(dbg_env) : 0, num_rows, N, D,
-               LQ, lstride, seg_tiles, nslots, cap, cd, cnt};
+               LQ, lstride, nst, seg_tiles, nslots, cap, cd, cnt};
     CUtensorMap tmapV;
-    {   // bf16 item table [N, D] row-major; box = 256 items x 64 k (one 128-byte swizzle span)
+    {   // bf16 item table [N, D] row-major; box = 128 items x 64 k (one 128-byte swizzle span)
         static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
         if (!encode) {
             void* fn = nullptr;
@@ -691,9 +708,14 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         NRC_REQUIRE(cr == CUDA_SUCCESS, NRC_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
     }
-    size_t smem = (size_t)(kM + kStages * kNT) * D * 2 + (size_t)streams * kM * lstride * 4;
+    size_t smem = (size_t)2 * kM * D * 2 + (size_t)nst * kNT * D * 2 + list_bytes;
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
-    NRC_REQUIRE(smem <= 220 * 1024, NRC_E_LIMIT, "tensor-core pass needs %zu B of shared memory", smem);
+    static bool attr_done = false;
+    if (!attr_done) {
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            226 * 1024));
+        attr_done = true;
+    }
     const dim3 grid(row_tiles, G);
     if (pass == 0) {
         if (!g_ev[0]) {
@@ -702,13 +724,14 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
         }
         NRC_CUDA_CHECK(cudaEventRecord(g_ev[0], st));
     }
-    rc = (streams == 2) ? launch_candidates<2>(P, tmapV, grid, smem, st) : launch_candidates<1>(P, tmapV, grid, smem, st);
-    if (rc) return rc;
+    tc_candidate_kernel<<<grid, kCandThreads, smem, st>>>(P, tmapV);
+    NRC_CUDA_CHECK(cudaGetLastError());
     if (pass == 0) {
         NRC_CUDA_CHECK(cudaEventRecord(g_ev[1], st));
         g_last_flops = 2.0 * (double)num_rows * (double)N * (double)D;
     }
     out->cand = cd;
+    out->scratch = (pass == 1) ? reinterpret_cast<float*>(ws + o_scr) : nullptr;
     out->cnt = cnt;
     out->nslots = nslots;
     out->cap = cap;
