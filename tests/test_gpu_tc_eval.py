@@ -125,3 +125,26 @@ def test_tc_eval_large_scale_matches_simt_path():
     a = ops.eval_mf_tc(U, V, users, dev(tp), dev(ti), dev(sp), dev(si), ALL, K, return_ranks=True)
     b = ops.eval_mf(U, V, users, dev(tp), dev(ti), dev(sp), dev(si), ALL, K, return_ranks=True)
     assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0])
+
+
+def test_uni_evaluator_routes_large_catalogues_to_the_tensor_core_path(monkeypatch):
+    """UniEvaluator picks nrc_eval_mf_tc above TC_MIN_ITEMS; the printed metric string (the thing
+    main.py logs, uni_evaluator.py:150-156) must not change by a character."""
+    from neurec_b200.evaluator.uni_evaluator import UniEvaluator
+    from neurec_b200 import ops
+    nu, ni, dim = 300, 3000, 64
+    U, V, tp, ti, sp, si = _problem(nu, ni, dim, 77)
+    train = {u: ti[tp[u]:tp[u + 1]].tolist() for u in range(nu)}
+    test = {u: si[sp[u]:sp[u + 1]].tolist() for u in range(nu)}
+
+    class Model:
+        def get_eval_tables(self):
+            return dev(U), dev(V)
+    ev = UniEvaluator(train, test, metric=["Precision", "Recall", "MAP", "NDCG", "MRR"], top_k=[5, 10, 20])
+    plain = ev.evaluate(Model())
+    calls = []
+    real = ops.eval_mf_tc
+    monkeypatch.setattr(ops, "eval_mf_tc", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    monkeypatch.setattr(UniEvaluator, "TC_MIN_ITEMS", 1000)
+    assert ev.evaluate(Model()) == plain
+    assert calls == [1]
