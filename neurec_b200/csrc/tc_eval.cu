@@ -300,13 +300,16 @@ namespace tc {
 //   warps 0-7  epilogue: warp w serves user half h = w / 4 through TMEM lanes 32*(w%4) .. +31;
 //              one thread = one user: running threshold, min-heap of the LQ best approximate
 //              scores, merge-walk over the user's train row, candidate list
-//   warp 8     MMA issuer (one thread): 2 x D/16 tcgen05.mma (M128 N128 K16) per item tile
+//   warp 8     MMA issuer (one thread): 2 x D/16 tcgen05.mma (M128 N{256|128} K16) per item tile
 //   warp 9     TMA producer (one thread): item tile -> shared memory (SWIZZLE_128B boxes)
-// Pipelines: `nst` shared-memory item stages (full_b / empty_b) and 2 TMEM stages of 2 x 128 fp32
-// columns (acc_full / acc_empty), so the MMAs of tile t+1 overlap the filtering of tile t.
+// Pipelines: `nst` shared-memory item stages (full_b / empty_b) and, per user half, 256/NT TMEM
+// accumulators of NT fp32 columns (acc_full / acc_empty per half): the MMAs of one half overlap
+// the filtering of the other, and with NT = 128 also the filtering of the same half's previous tile.
+// An SS-mode M128 N128 K16 MMA reads 8 KB of shared memory per 64 clk, exactly the 128 B/clk
+// shared-memory limit (N256 needs 96 B/clk), but the kernel as a whole is paced by the epilogue's
+// Tensor Memory read-out, so both tile widths measure the same; see DESIGN.md 3a.
 constexpr int kMaxList = 64;           // threshold rank <= 64 (2*top_k for the tie-replay pass)
 constexpr int kMU = 256;               // users per CTA
-constexpr int kNT = 128;               // items per tile (UMMA N)
 constexpr int kMaxStages = 3;
 constexpr int kCandThreads = 320;
 
@@ -328,22 +331,24 @@ struct CandArgs {
     int32_t* cand_cnt;         // [num_eval, nslots] candidates seen (> cap => overflow)
 };
 
+template <int NT>   // items per tile (UMMA N): 128 (default) or 256
 __global__ void __launch_bounds__(kCandThreads, 1)
 tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV) {
     constexpr int kMmaWarp = 8, kTmaWarp = 9;
+    constexpr int kAccStages = 256 / NT;   // TMEM stages per user half: 512 columns = 2 halves x kAccStages x NT
     extern __shared__ __align__(1024) uint8_t smem[];
     const int D = P.D;
     const uint32_t half_bytes = (uint32_t)kM * D * 2;     // one 128-user operand tile
-    const uint32_t stage_bytes = (uint32_t)kNT * D * 2;   // one 128-item operand tile
+    const uint32_t stage_bytes = (uint32_t)NT * D * 2;   // one 128-item operand tile
     uint8_t* sA = smem;                                   // 2 x [128 x D] bf16, SWIZZLE_128B blocks
     uint8_t* sB = sA + 2 * (size_t)half_bytes;            // nst x [128 x D] bf16
     float* sList = reinterpret_cast<float*>(sB + (size_t)P.nst * stage_bytes);   // [256][lstride]
-    __shared__ uint64_t full_b[kMaxStages], empty_b[kMaxStages], acc_full[2], acc_empty[2];
+    __shared__ uint64_t full_b[kMaxStages], empty_b[kMaxStages], acc_full[4], acc_empty[4];   // [stage * 2 + half]
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row0 = blockIdx.x * kMU;
     const int t_begin = blockIdx.y * P.seg_tiles;                         // first item tile of this CTA
-    const int T = min(P.seg_tiles, (P.N + kNT - 1) / kNT - t_begin);      // its tile count (>= 1)
+    const int T = min(P.seg_tiles, (P.N + NT - 1) / NT - t_begin);      // its tile count (>= 1)
 
     for (int h = 0; h < 2; ++h)
         load_tile_sw128(sA + (size_t)h * half_bytes, P.Ub + (size_t)(row0 + h * kM) * D, kM,
@@ -355,9 +360,9 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
             mbar_init(&full_b[i], 1);    // the producer's arrive.expect_tx; the copy engine completes the bytes
             mbar_init(&empty_b[i], 1);   // tcgen05.commit of the tile that read the stage
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 256);
+            mbar_init(&acc_empty[i], 128);   // the four epilogue warps of one user half
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -384,8 +389,8 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
                 } else {
                     mbar_arrive_expect_tx(&full_b[s], stage_bytes);
                     for (int kb = 0; kb < D / 64; ++kb)   // one 128 x 64 box per 128-byte K block
-                        tma_load_2d(b0 + (uint32_t)s * stage_bytes + (uint32_t)kb * kNT * 128, &tmapV, kb * 64,
-                                    (t_begin + t) * kNT, &full_b[s]);
+                        tma_load_2d(b0 + (uint32_t)s * stage_bytes + (uint32_t)kb * NT * 128, &tmapV, kb * 64,
+                                    (t_begin + t) * NT, &full_b[s]);
                 }
                 if (++s == P.nst) { s = 0; ph ^= 1; }
             }
@@ -393,34 +398,36 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
     } else if (warp == kMmaWarp) {
         // ---------------- MMA issuer (one thread) ----------------
         if (lane == 0) {
-            const uint32_t idesc = make_instr_desc(kM, kNT);
+            const uint32_t idesc = make_instr_desc(kM, NT);
             // Descriptors differ only in the 14-bit start-address field (16-byte units; shared
             // memory is < 256 KB, so adding offsets never carries out of the field).
             const uint64_t a_base = sw128_desc(smem_u32(sA), kM, 0);
-            const uint64_t b_base = sw128_desc(smem_u32(sB), kNT, 0);
+            const uint64_t b_base = sw128_desc(smem_u32(sB), NT, 0);
             const int nks = D / kUmmaK;
             int s = 0, ph = 0;
             for (int t = 0; t < T; ++t) {
-                const int a = t & 1, pa = (t >> 1) & 1;
+                const int a = t % kAccStages, pa = (t / kAccStages) & 1;
                 mbar_wait(&full_b[s], ph);
-                mbar_wait(&acc_empty[a], pa ^ 1);
-                tc_fence_after();
                 const uint64_t bb = b_base + (uint64_t)(((uint32_t)s * stage_bytes) >> 4);
-                if (!(P.dbg & 4)) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t td = tmem_base + (uint32_t)(a * 256 + h * kNT);
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(&acc_empty[a * 2 + h], pa ^ 1);
+                    tc_fence_after();
+                    if (!(P.dbg & 4)) {
+                        const uint32_t td = tmem_base + (uint32_t)((a * 2 + h) * NT);
                         const uint64_t ah = a_base + (uint64_t)(((uint32_t)h * half_bytes) >> 4);
 #pragma unroll 4
                         for (int ks = 0; ks < nks; ++ks) {
-                            // k-step ks: 64-element K block (ks >> 2) of 128 rows x 128 B, 32 B per step inside it
-                            const uint64_t koff = (uint64_t)((((uint32_t)ks >> 2) * kM * 128u + ((uint32_t)ks & 3u) * 32u) >> 4);
-                            umma_bf16(td, ah + koff, bb + koff, idesc, ks > 0 ? 1u : 0u);
+                            // k-step ks: 64-element K block (ks >> 2), 32 B per step inside it; the block
+                            // pitch is rows x 128 B, which differs between the user and the item tile
+                            const uint32_t kblk = (uint32_t)ks >> 2, kin = ((uint32_t)ks & 3u) * 32u;
+                            umma_bf16(td, ah + (uint64_t)((kblk * kM * 128u + kin) >> 4),
+                                      bb + (uint64_t)((kblk * NT * 128u + kin) >> 4), idesc, ks > 0 ? 1u : 0u);
                         }
                     }
+                    umma_commit(&acc_full[a * 2 + h]);   // this half's 128 x NT accumulator is complete
                 }
                 umma_commit(&empty_b[s]);    // the shared-memory stage may be refilled
-                umma_commit(&acc_full[a]);   // both 128 x 128 accumulators of tile t are complete
                 if (++s == P.nst) { s = 0; ph ^= 1; }
             }
         }
@@ -437,14 +444,14 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
         const int64_t tb = live ? P.train_ptr[u] : 0;
         const int tl = live ? (int)(P.train_ptr[u + 1] - tb) : 0;
         int32_t* my_cand = P.cand + ((size_t)row * P.nslots + slot) * P.cap;
-        float thr = -INFINITY, thr_m = -INFINITY;
+        float thr = -INFINITY, thr_m = live ? -INFINITY : INFINITY;   // padding rows never produce candidates
         int cnt = 0;
         // merge-walk over the user's sorted train row: items arrive in ascending order, so the
         // mask test of a candidate is "advance the cursor to >= item, compare" (amortised O(deg))
         int tpos = 0;
         if (t_begin > 0) {   // first train item at or after this segment's first item
             int lo = 0, hi = tl;
-            const int first = t_begin * kNT;
+            const int first = t_begin * NT;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
                 if (__ldg(P.train_idx + tb + mid) < first) lo = mid + 1; else hi = mid;
@@ -454,10 +461,11 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
         int tnext = (tpos < tl) ? __ldg(P.train_idx + tb + tpos) : INT32_MAX;
         int tahead = (tpos + 1 < tl) ? __ldg(P.train_idx + tb + tpos + 1) : INT32_MAX;   // prefetched: advancing never waits on memory
         for (int t = 0; t < T; ++t) {
-            const int a = t & 1, pa = (t >> 1) & 1;
-            mbar_wait(&acc_full[a], pa);
+            const int a = t % kAccStages, pa = (t / kAccStages) & 1;
+            const bool tail = (t_begin + t + 1) * NT > P.N;   // only the catalogue's last tile has columns past N
+            mbar_wait(&acc_full[a * 2 + h], pa);
             tc_fence_after();
-            // filter one chunk of 32 columns (items (t_begin + t)*kNT + c ..) held in registers
+            // filter one chunk of 32 columns (items (t_begin + t)*NT + c ..) held in registers
             auto filter_chunk = [&](const uint32_t (&raw)[32], const int c) {
                 if (P.dbg & 8) return;   // experiment: Tensor Memory read-out only
                 float v[32];
@@ -479,9 +487,8 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
                     for (int i = 0; i < 32; ++i) m4[i & 3] |= (v[i] > thr_m ? 1u : 0u) << i;
                     m = (m4[0] | m4[1]) | (m4[2] | m4[3]);
                 }
-                const int item0 = (t_begin + t) * kNT + c;
-                if (item0 + 32 > P.N) m &= (item0 >= P.N) ? 0u : ((1u << (P.N - item0)) - 1u);
-                if (!live) m = 0u;
+                const int item0 = (t_begin + t) * NT + c;
+                if (tail && item0 + 32 > P.N) m &= (item0 >= P.N) ? 0u : ((1u << (P.N - item0)) - 1u);
                 while (m) {                       // rare: ~LQ ln(N/LQ) times per user in total
                     const int i = __ffs(m) - 1;
                     m &= m - 1;
@@ -518,25 +525,25 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
                     }
                 }
             };
-            if (P.dbg & 1) { tc_fence_before(); mbar_arrive(&acc_empty[a]); continue; }
+            if (P.dbg & 1) { tc_fence_before(); mbar_arrive(&acc_empty[a * 2 + h]); continue; }
             // two chunks in flight: tcgen05.ld of chunk c+1 overlaps the filtering of chunk c
-            const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * 256 + h * kNT);
+            const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((a * 2 + h) * NT);
             uint32_t ra[32], rb[32];
             __syncwarp();   // the candidate branch diverges; tcgen05.ld needs the whole warp
             tmem_ld32_issue(tbase, ra);
 #pragma unroll 1
-            for (int c = 0; c < kNT; c += 64) {
+            for (int c = 0; c < NT; c += 64) {
                 tmem_ld_wait(ra);
                 tmem_ld32_issue(tbase + (uint32_t)(c + 32), rb);
                 filter_chunk(ra, c);
                 __syncwarp();
                 tmem_ld_wait(rb);
-                if (c + 64 < kNT) tmem_ld32_issue(tbase + (uint32_t)(c + 64), ra);
+                if (c + 64 < NT) tmem_ld32_issue(tbase + (uint32_t)(c + 64), ra);
                 filter_chunk(rb, c + 32);
                 __syncwarp();
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[a]);
+            mbar_arrive(&acc_empty[a * 2 + h]);
         }
         if (live) P.cand_cnt[(size_t)row * P.nslots + slot] = cnt;
     }
@@ -641,19 +648,32 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
     NRC_REQUIRE(LQ >= 1 && LQ <= kMaxList, NRC_E_LIMIT, "threshold rank %d outside [1, %d]", LQ, kMaxList);
     const int D = g_items_d, N = g_items_n;
     const int row_tiles = (num_rows + kMU - 1) / kMU;
+    // Tile width.  Both instantiations end up paced by the Tensor Memory read-out of the epilogue
+    // (every fp32 accumulator is read once: 128 KB per 128 x 256 block at ~64 B/clk/SM), so the
+    // default is the 128-item tile, whose double-buffered accumulators tolerate bursts of
+    // candidates better; NRC_TC_NT=256 selects the 256-item tile (fewer shared-memory reads per
+    // MMA, single-buffered accumulators) when two such stages fit.
+    const int lstride = (LQ <= 32) ? 33 : 65;
+    const size_t list_bytes = (size_t)kMU * lstride * 4;
+    const size_t fixed = (size_t)2 * kM * D * 2 + list_bytes + 2048;
+    const size_t budget = 227 * 1024 - fixed;
+    const char* nt_env = getenv("NRC_TC_NT");
+    int kNT = 128;
+    if (nt_env && atoi(nt_env) == 256 && budget / ((size_t)256 * D * 2) >= 2) kNT = 256;
     const int T = (N + kNT - 1) / kNT;
     // Item segments (grid.y): with few user tiles, split the catalogue so that every SM has a CTA.
     // Each segment restarts its threshold (still a lower bound of the true one), which costs a few
     // more candidates; pick the split with the fewest waves per unit of work, at most 8 unless a
     // single wave needs more (16 at most; 48 in the replay pass), and never segments shorter
-    // than 32 tiles.
+    // than 4096 items.
     int G = 1;
     {
         const int sms = sm_count();
         const int few = (pass == 1) ? 48 : 16;   // the replay pass re-scores its lists with a whole CTA per user
         const int gmax = (row_tiles * 8 < sms) ? ((sms / row_tiles < few) ? sms / row_tiles : few) : 8;
         double best = 1e30;
-        for (int g = 1; g <= gmax && g * 32 <= (T > 32 ? T : 32); ++g) {
+        const int min_tiles = 4096 / kNT;
+        for (int g = 1; g <= gmax && g * min_tiles <= (T > min_tiles ? T : min_tiles); ++g) {
             const int ctas = row_tiles * g;
             const double cost = (double)((ctas + sms - 1) / sms) / g * (1.0 + 0.02 * (g - 1));
             if (cost < best - 1e-9) { best = cost; G = g; }
@@ -662,10 +682,7 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
     const int seg_tiles = (T + G - 1) / G;
     G = (T + seg_tiles - 1) / seg_tiles;           // no empty segment
     const int nslots = G;
-    const int lstride = (LQ <= 32) ? 33 : 65;
-    const size_t list_bytes = (size_t)kMU * lstride * 4;
-    const size_t fixed = (size_t)2 * kM * D * 2 + list_bytes + 2048;
-    int nst = (int)((227 * 1024 - fixed) / ((size_t)kNT * D * 2));
+    int nst = (int)(budget / ((size_t)kNT * D * 2));
     if (nst > kMaxStages) nst = kMaxStages;
     NRC_REQUIRE(nst >= 2, NRC_E_LIMIT, "dim %d with threshold rank %d does not fit the tensor-core pass", D, LQ);
     const size_t rows_pad = (size_t)row_tiles * kMU;
@@ -712,7 +729,9 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
     static bool attr_done = false;
     if (!attr_done) {
-        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            226 * 1024));
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             226 * 1024));
         attr_done = true;
     }
@@ -724,7 +743,8 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
         }
         NRC_CUDA_CHECK(cudaEventRecord(g_ev[0], st));
     }
-    tc_candidate_kernel<<<grid, kCandThreads, smem, st>>>(P, tmapV);
+    if (kNT == 256) tc_candidate_kernel<256><<<grid, kCandThreads, smem, st>>>(P, tmapV);
+    else tc_candidate_kernel<128><<<grid, kCandThreads, smem, st>>>(P, tmapV);
     NRC_CUDA_CHECK(cudaGetLastError());
     if (pass == 0) {
         NRC_CUDA_CHECK(cudaEventRecord(g_ev[1], st));
