@@ -1071,7 +1071,7 @@ def run_ours(args):
     clocks.stop()
     if rank == 0:
         out["clocks"] = clocks.summary(windows)
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     barrier(world)
     if world > 1:
         import torch.distributed as dist
@@ -1104,7 +1104,7 @@ def run_reference(args):
                                       "restatement of the TF-1.12 step (TensorFlow 1.12 is not installable "
                                       "offline)" % (n, skind)},
            "e2e": {"value": value, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(json.dumps(out))
 
 
 def lift_cpu_thread_limits():
@@ -1119,7 +1119,24 @@ def lift_cpu_thread_limits():
         pass
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything libraries print (NCCL's version banner,
+    warnings) was diverted to stderr by main()."""
+    data = (line + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line + "\n"); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # stray prints of native libraries -> stderr
     lift_cpu_thread_limits()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
