@@ -323,41 +323,102 @@ class Workload:
                                               ctypes.c_void_p(self.loss_pin.data_ptr()), count, st))
         return float(self.loss_pin[0])
 
+    RING = 16
+
+    def _capture_step(self, lib, r, copy_in, main, copy_out):
+        """Issue step r of the ring into the current capture: H2D on `copy_in`, kernels on `main`,
+        loss D2H on `copy_out` (the three may be the same stream)."""
+        import torch
+        from neurec_b200 import _lib
+        vp = ctypes.c_void_p
+        b = self.batch
+        stag = self.stag_ring[r]
+        _lib.check(lib.nrc_graph_stage_async(vp(self.pins[r].data_ptr()), vp(stag.data_ptr()), (3 * b + 1) * 4,
+                                             vp(copy_in.cuda_stream)))
+        if copy_in is not main:
+            _lib.check(lib.nrc_graph_depend(vp(copy_in.cuda_stream), vp(main.cuda_stream)))
+        _lib.check(lib.nrc_opt_set_lr_source(vp(stag.data_ptr() + 12 * b)))
+        third = stag[2 * b:3 * b]
+        if not self.pairwise:
+            third = third.view(torch.float32)
+        t_keep, loss_keep = self.t, self.step_loss
+        self.step_loss = self.loss_ring[r]
+        with torch.cuda.stream(main):
+            self.step_on_staged(stag[:b], stag[b:2 * b], third)
+        self.t, self.step_loss = t_keep, loss_keep
+        _lib.check(lib.nrc_opt_set_lr_source(None))
+        if copy_out is not main:
+            _lib.check(lib.nrc_graph_depend(vp(main.cuda_stream), vp(copy_out.cuda_stream)))
+        _lib.check(lib.nrc_graph_fetch_async(vp(self.loss_ring[r].data_ptr()), vp(self.loss_pins[r].data_ptr()),
+                                             self.loss_count, vp(copy_out.cuda_stream)))
+
     def build_step_graph(self):
-        """Capture ONE training step (H2D of the pinned batch block, the step's kernels, D2H of the
-        loss) into a CUDA graph: the per-batch host cost becomes one cudaGraphLaunch + one sync."""
+        """Captured training steps for the host-facing path.  Per ring slot r: a pinned block, a device
+        staging block, a device + pinned loss slot and a single-step graph (H2D, the step's kernels,
+        loss D2H).  Plus ONE burst graph of RING consecutive steps whose H2D chain and loss-D2H chain
+        are captured on two side streams: inside a burst the copy of step s+1 overlaps the kernels of
+        step s (nrc_graph_run_steps)."""
         import torch
         from neurec_b200 import _lib
         lib = _lib.load()
-        b = self.batch
+        b, R = self.batch, self.RING
         self.e2e_stream = torch.cuda.Stream()
-        self.pin = torch.zeros(3 * b + 4, dtype=torch.int32).pin_memory()
-        self.graph = ctypes.c_void_p()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        self.pins = [torch.zeros(3 * b + 4, dtype=torch.int32).pin_memory() for _ in range(R)]
+        self.loss_pins = [torch.zeros(max(self.loss_count, 1)).pin_memory() for _ in range(R)]
+        self.stag_ring = torch.zeros((R, 3 * b + 4), dtype=torch.int32, device="cuda")
+        self.loss_ring = torch.zeros((R, 16), device="cuda")
+        self.graphs = []
         torch.cuda.synchronize()
-        with torch.cuda.stream(self.e2e_stream):
-            st = ctypes.c_void_p(self.e2e_stream.cuda_stream)
-            vp = ctypes.c_void_p
+        vp = ctypes.c_void_p
+        main = self.e2e_stream
+        st = vp(main.cuda_stream)
+        for r in range(R):
+            g = ctypes.c_void_p()
             _lib.check(lib.nrc_graph_capture_begin(st))
-            _lib.check(lib.nrc_graph_stage_async(vp(self.pin.data_ptr()), vp(self.staging.data_ptr()),
-                                                 (3 * b + 1) * 4, st))
-            _lib.check(lib.nrc_opt_set_lr_source(vp(self.staging.data_ptr() + 12 * b)))
-            third = self.staging[2 * b:3 * b]
-            if not self.pairwise:
-                third = third.view(torch.float32)
-            t_keep = self.t
-            self.step_on_staged(self.staging[:b], self.staging[b:2 * b], third)
-            self.t = t_keep
-            _lib.check(lib.nrc_opt_set_lr_source(None))
-            _lib.check(lib.nrc_graph_fetch_async(vp(self.step_loss.data_ptr()), vp(self.loss_pin.data_ptr()),
-                                                 self.loss_count, st))
-            _lib.check(lib.nrc_graph_capture_end(st, ctypes.byref(self.graph)))
+            self._capture_step(lib, r, main, main, main)
+            _lib.check(lib.nrc_graph_capture_end(st, ctypes.byref(g)))
+            self.graphs.append(g)
+        self.burst = ctypes.c_void_p()
+        _lib.check(lib.nrc_graph_capture_begin(st))
+        _lib.check(lib.nrc_graph_depend(st, vp(s_in.cuda_stream)))        # fork: both side streams join the capture
+        _lib.check(lib.nrc_graph_depend(st, vp(s_out.cuda_stream)))
+        for r in range(R):
+            self._capture_step(lib, r, s_in, main, s_out)
+        _lib.check(lib.nrc_graph_depend(vp(s_in.cuda_stream), st))        # join
+        _lib.check(lib.nrc_graph_depend(vp(s_out.cuda_stream), st))
+        _lib.check(lib.nrc_graph_capture_end(st, ctypes.byref(self.burst)))
+        self.graph, self.pin, self.loss_pin = self.graphs[0], self.pins[0], self.loss_pins[0]
+        self.c_graphs = (ctypes.c_void_p * R)(*[g.value for g in self.graphs])
+        self.c_pins = (ctypes.c_void_p * R)(*[p.data_ptr() for p in self.pins])
+        self.c_loss = (ctypes.c_void_p * R)(*[p.data_ptr() for p in self.loss_pins])
         torch.cuda.synchronize()
 
     def run_steps_e2e(self, h_arrays, n_steps):
-        """Per batch: host arrays -> pinned block -> graph launch (H2D, kernels, loss D2H) -> sync."""
+        """Steps from HOST arrays: the host stages RING batches into the pinned ring and launches the
+        burst graph (per step: H2D node, the step's kernels, loss D2H node; copies of step s+1 overlap
+        the kernels of step s), waits, reads the RING losses; leftover steps use the single-step graphs."""
         from neurec_b200 import _lib
         lib = _lib.load()
-        if not hasattr(self, "graph"):
+        if not hasattr(self, "graphs"):
+            self.build_step_graph()
+        st = ctypes.c_void_p(self.e2e_stream.cuda_stream)
+        lr = np.ascontiguousarray(self.lr_sched[self.t:self.t + n_steps], dtype=np.float32)
+        total = ctypes.c_double(0.0)
+        vp = ctypes.c_void_p
+        _lib.check(lib.nrc_graph_run_steps(self.burst, self.c_graphs, self.RING, vp(h_arrays[0].data_ptr()),
+                                           vp(h_arrays[1].data_ptr()), vp(h_arrays[2].data_ptr()), self.batch,
+                                           lr.ctypes.data_as(ctypes.c_void_p), n_steps, self.c_pins, self.c_loss,
+                                           self.loss_count, ctypes.byref(total), st))
+        self.t += n_steps
+        return total.value, 3 * 4 * self.batch + 4, 4 * self.loss_count
+
+    def run_steps_e2e_sync(self, h_arrays, n_steps):
+        """The strictly synchronous variant (what `sess.run` per batch does): stage, launch, wait for
+        the loss, every step."""
+        from neurec_b200 import _lib
+        lib = _lib.load()
+        if not hasattr(self, "graphs"):
             self.build_step_graph()
         st = ctypes.c_void_p(self.e2e_stream.cuda_stream)
         pin = ctypes.c_void_p(self.pin.data_ptr())
@@ -723,6 +784,15 @@ def measure(w, K, W, world, rank, windows, with_cpu=True):
     windows.append((wall0, time.perf_counter()))
     barrier(world)
     e2e_value = world * K * w.batch / e2e_s
+    # the same with a host wait after EVERY step (the reference's `sess.run` per batch behaviour)
+    ks = min(K, 400)
+    barrier(world)
+    wall0 = time.perf_counter()
+    w.run_steps_e2e_sync(tuple(h[W * w.batch:] for h in h_arrays), ks)
+    torch.cuda.synchronize()
+    e2e_sync_s = max_over_ranks(time.perf_counter() - wall0, world)
+    windows.append((wall0, time.perf_counter()))
+    barrier(world)
 
     # ---- evaluator: users sharded over ranks
     nu = w.d["num_users"]
@@ -767,7 +837,13 @@ def measure(w, K, W, world, rank, windows, with_cpu=True):
                    "l2": "flushed (256 MiB write) before each timed region; the K dependent steps then run "
                          "back-to-back as in training (model + optimizer state are L2-sized)"},
         "e2e": {"value": e2e_value, "unit": "triplets/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3 / K},
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3 / K,
+                "how": "nrc_graph_run_steps: the host stages %d batches from the host arrays into a pinned ring and "
+                       "launches one captured burst graph; every step has its own H2D node, kernels and loss "
+                       "D2H node, the copies of step s+1 overlap the kernels of step s; the host waits and reads "
+                       "the losses once per burst" % w.RING,
+                "sync_every_step": {"value": world * ks * w.batch / e2e_sync_s, "unit": "triplets/s",
+                                    "ms_per_step": e2e_sync_s * 1e3 / ks, "steps": ks}},
         "gpu_launches": launches,
         "eval": {"metric": "eval users/sec", "value": n_eval / (eval_ms * 1e-3), "unit": "users/s",
                  "users": n_eval,

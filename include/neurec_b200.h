@@ -81,6 +81,22 @@ int nrc_graph_stage_async(const void* pinned_host, void* staging_dev, int64_t nb
 int nrc_graph_fetch_async(const float* src_dev, float* pinned_host, int64_t count, void* stream);
 int nrc_graph_step(nrc_step_graph* g, const void* a_host, const void* b_host, const void* c_host,
                    int64_t batch, float lr_t, void* pinned_stage, void* stream);
+/* to_stream waits for everything issued so far on from_stream.  During a capture this forks /
+ * joins the graph: the second stream joins the capture. */
+int nrc_graph_depend(void* from_stream, void* to_stream);
+/* A run of n_steps steps over consecutive batches of the host arrays with a RING of `ring` pinned
+ * blocks (pinned_stage[r], loss slot loss_pinned[r]).  `burst` (may be NULL) is ONE captured graph
+ * holding `ring` consecutive steps, captured with nrc_graph_depend so that the H2D of step s+1
+ * overlaps the kernels of step s: the host stages `ring` batches, launches it, waits, reads the
+ * `ring` losses.  Steps that do not fill a burst (all of them when burst is NULL) use the per-slot
+ * single-step graphs `graphs[r]`, launched back to back with one wait per ring wrap.  Every step
+ * performs its own H2D and its own loss D2H.  lr_t[s] = learning rate (Adam's lr_t) of step s.
+ * *loss_sum = sum of every fetched loss value. */
+int nrc_graph_run_steps(nrc_step_graph* burst, nrc_step_graph* const* graphs, int32_t ring,
+                        const void* a_host, const void* b_host, const void* c_host, int64_t batch,
+                        const float* lr_t, int64_t n_steps, void* const* pinned_stage,
+                        const float* const* loss_pinned, int32_t loss_count, double* loss_sum,
+                        void* stream);
 int nrc_graph_destroy(nrc_step_graph* g);
 int nrc_opt_set_lr_source(const float* lr_dev);
 

@@ -89,6 +89,20 @@ extern "C" int nrc_graph_fetch_async(const float* src_dev, float* pinned_host, i
     return NRC_OK;
 }
 
+// `to_stream` will not run past this point before everything issued so far on `from_stream` has
+// completed.  Inside a stream capture this forks / joins the captured graph (the second stream
+// joins the capture), which is how a burst graph overlaps the H2D of step s+1 with step s.
+extern "C" int nrc_graph_depend(void* from_stream, void* to_stream) {
+    static cudaEvent_t pool[512];
+    static int next = 0;
+    cudaEvent_t& ev = pool[next];
+    next = (next + 1) % 512;
+    if (!ev) NRC_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    NRC_CUDA_CHECK(cudaEventRecord(ev, nrc::as_stream(from_stream)));
+    NRC_CUDA_CHECK(cudaStreamWaitEvent(nrc::as_stream(to_stream), ev, 0));
+    return NRC_OK;
+}
+
 extern "C" int nrc_graph_step(nrc_step_graph* g, const void* a_host, const void* b_host,
                               const void* c_host, int64_t batch, float lr_t, void* pinned_stage,
                               void* stream) {
@@ -102,6 +116,69 @@ extern "C" int nrc_graph_step(nrc_step_graph* g, const void* a_host, const void*
     cudaStream_t st = nrc::as_stream(stream);
     NRC_CUDA_CHECK(cudaGraphLaunch(g->exec, st));
     NRC_CUDA_CHECK(cudaStreamSynchronize(st));
+    return NRC_OK;
+}
+
+// A run of steps over consecutive batches of host arrays with a ring of `ring` pinned blocks.
+// `burst` (optional) is ONE captured graph holding `ring` consecutive steps whose H2D / loss-D2H
+// nodes sit on a second captured stream, so inside a burst the copy of step s+1 overlaps the
+// kernels of step s; the host stages `ring` batches, launches it and waits.  Steps that do not fill
+// a burst (and every step when burst == NULL) go through the per-slot single-step graphs, launched
+// back to back with one wait per ring wrap.  Every step does its own H2D and its own loss D2H.
+extern "C" int nrc_graph_run_steps(nrc_step_graph* burst, nrc_step_graph* const* graphs, int32_t ring,
+                                   const void* a_host, const void* b_host, const void* c_host, int64_t batch,
+                                   const float* lr_t, int64_t n_steps, void* const* pinned_stage,
+                                   const float* const* loss_pinned, int32_t loss_count, double* loss_sum,
+                                   void* stream) {
+    NRC_REQUIRE(pinned_stage != nullptr && ring > 0, NRC_E_VALUE, "pinned ring is empty");
+    NRC_REQUIRE(burst != nullptr || graphs != nullptr, NRC_E_VALUE, "no graph given");
+    NRC_REQUIRE(lr_t != nullptr && n_steps >= 0 && batch > 0, NRC_E_VALUE, "bad step arguments");
+    cudaStream_t st = nrc::as_stream(stream);
+    const size_t nb = (size_t)batch * 4;
+    double acc = 0.0;
+    auto drain = [&](int64_t upto) {   // losses of the steps launched since the last wait
+        for (int64_t r = 0; r < upto; ++r)
+            if (loss_pinned && loss_pinned[r])
+                for (int32_t k = 0; k < loss_count; ++k) acc += (double)loss_pinned[r][k];
+    };
+    auto stage = [&](int64_t s, int64_t r) {
+        char* dst = reinterpret_cast<char*>(pinned_stage[r]);
+        const size_t off = (size_t)s * nb;
+        if (a_host) memcpy(dst, reinterpret_cast<const char*>(a_host) + off, nb);
+        if (b_host) memcpy(dst + nb, reinterpret_cast<const char*>(b_host) + off, nb);
+        if (c_host) memcpy(dst + 2 * nb, reinterpret_cast<const char*>(c_host) + off, nb);
+        memcpy(dst + 3 * nb, lr_t + s, sizeof(float));
+    };
+    for (int64_t r = 0; r < ring; ++r)
+        NRC_REQUIRE(pinned_stage[r] != nullptr, NRC_E_VALUE, "pinned ring slot %lld is NULL", (long long)r);
+    int64_t s = 0;
+    if (burst) {
+        for (; s + ring <= n_steps; s += ring) {
+            for (int64_t r = 0; r < ring; ++r) stage(s + r, r);
+            NRC_CUDA_CHECK(cudaGraphLaunch(burst->exec, st));
+            NRC_CUDA_CHECK(cudaStreamSynchronize(st));
+            drain(ring);
+        }
+    }
+    if (s < n_steps) {
+        NRC_REQUIRE(graphs != nullptr, NRC_E_VALUE, "%lld steps do not fill a burst and no single-step graphs were given",
+                    (long long)(n_steps - s));
+        int64_t in_flight = 0;
+        for (; s < n_steps; ++s) {
+            const int64_t r = in_flight;
+            NRC_REQUIRE(graphs[r] != nullptr, NRC_E_VALUE, "graph ring slot %lld is NULL", (long long)r);
+            stage(s, r);
+            NRC_CUDA_CHECK(cudaGraphLaunch(graphs[r]->exec, st));
+            if (++in_flight == ring) {
+                NRC_CUDA_CHECK(cudaStreamSynchronize(st));
+                drain(in_flight);
+                in_flight = 0;
+            }
+        }
+        NRC_CUDA_CHECK(cudaStreamSynchronize(st));
+        drain(in_flight);
+    }
+    if (loss_sum) *loss_sum = acc;
     return NRC_OK;
 }
 

@@ -139,6 +139,87 @@ def test_captured_step_graph_matches_oracle(ml100k):
     assert np.abs(dU.cpu().numpy() - tr.U).max() < 2e-5 and np.abs(dV.cpu().numpy() - tr.V).max() < 2e-5
 
 
+def test_graph_ring_burst_matches_oracle(ml100k):
+    """nrc_graph_run_steps: 11 BPR/Adam steps from host arrays through a ring of 4 pinned blocks --
+    two bursts of the 4-step burst graph (H2D chain and loss-D2H chain captured on side streams with
+    nrc_graph_depend, so copies overlap the previous step's kernels) and 3 leftover steps through the
+    single-step graphs.  Every step stages its own batch and returns its own loss.  Same result as
+    the numpy oracle stepping through the same batches."""
+    import ctypes
+    from neurec_b200 import _lib, ops
+    d = ml100k
+    lib = _lib.load()
+    nu, ni, dim, bs, steps, ring = d["num_users"], d["num_items"], 64, 512, 11, 4
+    rs = np.random.RandomState(5)
+    U0 = (rs.randn(nu, dim) * 0.01).astype(np.float32); V0 = (rs.randn(ni, dim) * 0.01).astype(np.float32)
+    all_users = np.repeat(np.arange(nu, dtype=np.int32), np.diff(d["train_indptr"]))
+    perm = rs.permutation(len(all_users))[:bs * steps]
+    users, pos = all_users[perm].copy(), d["train_indices"][perm].copy()
+    neg = rs.randint(0, ni, len(users)).astype(np.int32)
+    tr = tf_math.MFTrainer(U0, V0, "adam", 1e-3, "bpr", 0.0, True)
+    want = tr.epoch(users, pos, neg, bs)
+
+    dU, dV = dev(U0), dev(V0)
+    z = torch.zeros_like
+    gU, gV, mU, vU, mV, vV = z(dU), z(dV), z(dU), z(dU), z(dV), z(dV)
+    tU = torch.zeros(nu, dtype=torch.int32, device="cuda"); tV = torch.zeros(ni, dtype=torch.int32, device="cuda")
+    stag = torch.zeros((ring, 3 * bs + 4), dtype=torch.int32, device="cuda")
+    loss_dev = torch.zeros((ring, 4), device="cuda")
+    pins = [torch.zeros(3 * bs + 4, dtype=torch.int32).pin_memory() for _ in range(ring)]
+    loss_pins = [torch.zeros(4).pin_memory() for _ in range(ring)]
+    main, s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    vp = ctypes.c_void_p
+    sp = lambda x: vp(x.cuda_stream)
+
+    def capture_step(r, cin, cout):
+        _lib.check(lib.nrc_graph_stage_async(vp(pins[r].data_ptr()), vp(stag[r].data_ptr()), (3 * bs + 1) * 4, sp(cin)))
+        if cin is not main:
+            _lib.check(lib.nrc_graph_depend(sp(cin), sp(main)))
+        _lib.check(lib.nrc_opt_set_lr_source(vp(stag[r].data_ptr() + 12 * bs)))
+        with torch.cuda.stream(main):
+            ops.mf_train_epoch(dU, dV, stag[r, :bs], stag[r, bs:2 * bs], stag[r, 2 * bs:3 * bs], bs, True, "bpr",
+                               0.0, "adam", np.zeros(1, np.float32), [0.0, 0.9, 0.999, 1e-8], gU, gV, tU, tV, mU,
+                               vU, mV, vV, 1, loss_dev[r])
+        _lib.check(lib.nrc_opt_set_lr_source(None))
+        if cout is not main:
+            _lib.check(lib.nrc_graph_depend(sp(main), sp(cout)))
+        _lib.check(lib.nrc_graph_fetch_async(vp(loss_dev[r].data_ptr()), vp(loss_pins[r].data_ptr()), 1, sp(cout)))
+
+    graphs = []
+    torch.cuda.synchronize()
+    for r in range(ring):
+        g = ctypes.c_void_p()
+        _lib.check(lib.nrc_graph_capture_begin(sp(main)))
+        capture_step(r, main, main)
+        _lib.check(lib.nrc_graph_capture_end(sp(main), ctypes.byref(g)))
+        graphs.append(g)
+    burst = ctypes.c_void_p()
+    _lib.check(lib.nrc_graph_capture_begin(sp(main)))
+    _lib.check(lib.nrc_graph_depend(sp(main), sp(s_in)))
+    _lib.check(lib.nrc_graph_depend(sp(main), sp(s_out)))
+    for r in range(ring):
+        capture_step(r, s_in, s_out)
+    _lib.check(lib.nrc_graph_depend(sp(s_in), sp(main)))
+    _lib.check(lib.nrc_graph_depend(sp(s_out), sp(main)))
+    _lib.check(lib.nrc_graph_capture_end(sp(main), ctypes.byref(burst)))
+    torch.cuda.synchronize()
+    assert np.array_equal(dU.cpu().numpy(), U0)                      # capturing ran nothing
+
+    lr_t = np.ascontiguousarray(tf_math.adam_lr_t(1e-3, steps), dtype=np.float32)
+    total = ctypes.c_double(0.0)
+    c_graphs = (ctypes.c_void_p * ring)(*[g.value for g in graphs])
+    c_pins = (ctypes.c_void_p * ring)(*[p.data_ptr() for p in pins])
+    c_loss = (ctypes.c_void_p * ring)(*[p.data_ptr() for p in loss_pins])
+    _lib.check(lib.nrc_graph_run_steps(burst, c_graphs, ring, vp(users.ctypes.data), vp(pos.ctypes.data),
+                                       vp(neg.ctypes.data), bs, vp(lr_t.ctypes.data), steps, c_pins, c_loss, 1,
+                                       ctypes.byref(total), sp(main)))
+    for g in graphs + [burst]:
+        lib.nrc_graph_destroy(g)
+    assert np.isclose(total.value, float(np.sum(want, dtype=np.float64)), rtol=1e-4)
+    assert np.isclose(float(loss_pins[(steps - 1) % ring][0]), want[-1], rtol=1e-4)   # last step's own loss
+    assert np.abs(dU.cpu().numpy() - tr.U).max() < 2e-5 and np.abs(dV.cpu().numpy() - tr.V).max() < 2e-5
+
+
 # ----------------------------------------------------------------------------- training
 def _tables(nu, ni, dim, seed=0, scale=0.1):
     rs = np.random.RandomState(seed)
