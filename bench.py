@@ -749,7 +749,7 @@ def eval_once(w, users):
     tabs = w.eval_tables()
     if tabs is None:
         return ops.mean_rows(w.run_eval(users))
-    res = ops.eval_mf(tabs[0], tabs[1], users, w.tp, w.ti, w.sp, w.si, METRICS, w.eval_k)
+    res = ops.eval_mf_auto(tabs[0], tabs[1], users, w.tp, w.ti, w.sp, w.si, METRICS, w.eval_k)   # what UniEvaluator calls
     return ops.mean_rows(res)
 
 

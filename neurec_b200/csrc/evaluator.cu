@@ -1113,7 +1113,8 @@ __global__ void __launch_bounds__(256)
 eval_tc_finalize_kernel(const float* __restrict__ Utab, const float* __restrict__ Vtab, int D,
                         const int32_t* __restrict__ users, int num_eval,
                         const int64_t* __restrict__ test_ptr, const int32_t* __restrict__ test_idx,
-                        const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt, int nslots, int cap,
+                        const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+                        const float* __restrict__ cand_val, const float* __restrict__ margin, int nslots, int cap,
                         int K, int M, int force_exact, float* __restrict__ results,
                         int32_t* __restrict__ ranks, int32_t* __restrict__ slow_count,
                         int32_t* __restrict__ slow_rows, int32_t* __restrict__ und_count,
@@ -1139,29 +1140,56 @@ eval_tc_finalize_kernel(const float* __restrict__ Utab, const float* __restrict_
     for (int k = lane; k < D; k += kWarp) su[k] = Utab[(size_t)u * D + k];
     __syncwarp();
     const float4* su4 = reinterpret_cast<const float4*>(su);
+    // warp-wide sorted insertion of (value, index) into the top K+1 held one per lane
+    auto insert_all = [&](float s, int item, bool ok, float& tv, int& ti, float& thr) {
+        unsigned c = __ballot_sync(kFull, ok && s > thr);
+        while (c) {
+            const int src = __ffs(c) - 1;
+            c &= c - 1;
+            const float cv = __shfl_sync(kFull, s, src);
+            const int ci = __shfl_sync(kFull, item, src);
+            if (!(cv > thr)) continue;
+            const int pos = __popc(__ballot_sync(kFull, lane <= K && tv >= cv));
+            const float up_v = __shfl_up_sync(kFull, tv, 1);
+            const int up_i = __shfl_up_sync(kFull, ti, 1);
+            if (lane > pos) { tv = up_v; ti = up_i; }
+            if (lane == pos) { tv = cv; ti = ci; }
+            thr = __shfl_sync(kFull, tv, K);
+        }
+    };
+    // Phase 1 (no gathers): the (K+1)-th best APPROXIMATE score over all candidates.  Every item of
+    // the exact top K+1 has an approximate score >= that value - margin (both the item's score and
+    // the order statistic move by at most margin/2 between exact and approximate), so only those
+    // candidates -- ~1.4 (K+1) of the ~15 (K+1) in the lists -- need an exact re-score.
+    float a_cut = -INFINITY;
+    {
+        float av = -INFINITY, athr = -INFINITY;
+        int ai = -1;
+        for (int sl = 0; sl < nslots; ++sl) {
+            const int cnt = ccnt[sl];
+            const float* arow = cand_val + ((size_t)row * nslots + sl) * cap;
+            for (int base = 0; base < cnt; base += kWarp) {
+                const int idx = base + lane;
+                const float s = (idx < cnt) ? arow[idx] : -INFINITY;
+                insert_all(s, idx, idx < cnt, av, ai, athr);
+            }
+        }
+        a_cut = athr - margin[row];     // -inf while fewer than K+1 candidates exist
+    }
+    // Phase 2: exact fp32 re-score (the oracle's FMA chain) of the survivors, tie-aware selection
     float tv = -INFINITY, thr = -INFINITY;
     int ti = -1;
     for (int sl = 0; sl < nslots; ++sl) {
         const int cnt = ccnt[sl];
         const int32_t* crow = cand + ((size_t)row * nslots + sl) * cap;
+        const float* arow = cand_val + ((size_t)row * nslots + sl) * cap;
         for (int base = 0; base < cnt; base += kWarp) {
             const int idx = base + lane;
-            const int item = (idx < cnt) ? crow[idx] : -1;
-            const float s = (item >= 0) ? tc_exact_score(su4, Vtab, item, D) : -INFINITY;
-            unsigned c = __ballot_sync(kFull, item >= 0 && s > thr);
-            while (c) {
-                const int src = __ffs(c) - 1;
-                c &= c - 1;
-                const float cv = __shfl_sync(kFull, s, src);
-                const int ci = __shfl_sync(kFull, item, src);
-                if (!(cv > thr)) continue;
-                const int pos = __popc(__ballot_sync(kFull, lane <= K && tv >= cv));
-                const float up_v = __shfl_up_sync(kFull, tv, 1);
-                const int up_i = __shfl_up_sync(kFull, ti, 1);
-                if (lane > pos) { tv = up_v; ti = up_i; }
-                if (lane == pos) { tv = cv; ti = ci; }
-                thr = __shfl_sync(kFull, tv, K);
-            }
+            const bool keep = idx < cnt && !(arow[idx] < a_cut);
+            if (!__any_sync(kFull, keep)) continue;
+            const int item = keep ? crow[idx] : -1;
+            const float s = keep ? tc_exact_score(su4, Vtab, item, D) : -INFINITY;
+            insert_all(s, item, keep, tv, ti, thr);
         }
     }
     const float nxt = __shfl_down_sync(kFull, tv, 1);
@@ -1323,7 +1351,7 @@ extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, 
         const size_t smem = (size_t)warps * ((dim + 4 * K + 3) & ~3) * 4;
         eval_tc_finalize_kernel<<<(num_eval_users + warps - 1) / warps, warps * 32, smem, st>>>(
             user_table, item_table, dim, users, num_eval_users, test_indptr, test_indices, c0.cand, c0.cnt,
-            c0.nslots, c0.cap, K, metric_num, g_force_exact ? 1 : 0, results, ranks, g_slow, g_slow + 1, g_und,
+            c0.scratch, c0.margin, c0.nslots, c0.cap, K, metric_num, g_force_exact ? 1 : 0, results, ranks, g_slow, g_slow + 1, g_und,
             g_und + 1);
         NRC_CUDA_CHECK(cudaGetLastError());
     }

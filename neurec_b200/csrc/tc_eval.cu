@@ -328,6 +328,7 @@ struct CandArgs {
     int nslots;                // candidate lists per user = gridDim.y
     int cap;                   // entries per list
     int32_t* cand;             // [num_eval, nslots, cap] candidate item ids, ascending inside a list
+    float* cand_val;           // same shape: the approximate (bf16 tensor-core) score of each candidate
     int32_t* cand_cnt;         // [num_eval, nslots] candidates seen (> cap => overflow)
 };
 
@@ -444,6 +445,7 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
         const int64_t tb = live ? P.train_ptr[u] : 0;
         const int tl = live ? (int)(P.train_ptr[u + 1] - tb) : 0;
         int32_t* my_cand = P.cand + ((size_t)row * P.nslots + slot) * P.cap;
+        float* my_val = P.cand_val + ((size_t)row * P.nslots + slot) * P.cap;
         float thr = -INFINITY, thr_m = live ? -INFINITY : INFINITY;   // padding rows never produce candidates
         int cnt = 0;
         // merge-walk over the user's sorted train row: items arrive in ascending order, so the
@@ -503,7 +505,7 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
                         tahead = (tpos + 1 < tl) ? __ldg(P.train_idx + tb + tpos + 1) : INT32_MAX;
                     }
                     if (tnext == item) continue;  // train item: masked to -inf by the reference
-                    if (cnt < P.cap) my_cand[cnt] = item;
+                    if (cnt < P.cap) { my_cand[cnt] = item; my_val[cnt] = x; }
                     ++cnt;
                     if (x > thr) {                // keep the LQ best approximate scores in a min-heap
                         int hpos = 0;             // replace the root (the LQ-th best) and sift down
@@ -691,7 +693,7 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
     const size_t o_cnt = o_margin + up256(rows_pad * 4);
     const size_t o_cand = o_cnt + up256(rows_pad * nslots * 4);
     const size_t o_scr = o_cand + up256(rows_pad * (size_t)nslots * cap * 4);
-    const size_t total = o_scr + (pass == 1 ? up256(rows_pad * (size_t)nslots * cap * 4) : 0);
+    const size_t total = o_scr + up256(rows_pad * (size_t)nslots * cap * 4);
     int rc = g_pass[pass].reserve(total);
     if (rc) return rc;
     uint8_t* ws = reinterpret_cast<uint8_t*>(g_pass[pass].p);
@@ -704,7 +706,7 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
 
     const char* dbg_env = getenv("NRC_TC_DBG");
     CandArgs P{Ub, g_vb, margin, users, train_ptr, train_idx, dbg_env ? atoi(dbg_env) : 0, num_rows, N, D,
-               LQ, lstride, nst, seg_tiles, nslots, cap, cd, cnt};
+               LQ, lstride, nst, seg_tiles, nslots, cap, cd, reinterpret_cast<float*>(ws + o_scr), cnt};
     CUtensorMap tmapV;
     {   // bf16 item table [N, D] row-major; box = 128 items x 64 k (one 128-byte swizzle span)
         static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -751,7 +753,8 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
         g_last_flops = 2.0 * (double)num_rows * (double)N * (double)D;
     }
     out->cand = cd;
-    out->scratch = (pass == 1) ? reinterpret_cast<float*>(ws + o_scr) : nullptr;
+    out->scratch = reinterpret_cast<float*>(ws + o_scr);
+    out->margin = margin;
     out->cnt = cnt;
     out->nslots = nslots;
     out->cap = cap;

@@ -9,7 +9,9 @@ namespace tc {
 struct CandLists {
     const int32_t* cand;   // [rows, nslots, cap]
     const int32_t* cnt;    // [rows, nslots]
-    float* scratch;        // pass 1 only: [rows, nslots, cap] floats for the exact scores of the candidates
+    float* scratch;        // [rows, nslots, cap]: the candidates' approximate scores (the replay kernel overwrites
+                           // them with exact ones)
+    const float* margin;   // [rows] the per-user error margin the candidate kernel used
     int nslots, cap;
 };
 

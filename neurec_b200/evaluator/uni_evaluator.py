@@ -5,7 +5,7 @@ names and ids, ``metrics_info()`` / ``evaluate()`` string formats, ``test_users`
 What changes is where the work happens:
   * models that expose ``get_eval_tables() -> (user_table, item_table)`` (MF, LightGCN: predict is
     U[users] . V^T) are evaluated by ONE fused launch of ``nrc_eval_mf`` over all test users --
-    scores never leave the SM -- or, for catalogues of >= 262 144 items, by ``nrc_eval_mf_tc``
+    scores never leave the SM -- or, for catalogues of >= 16 384 items, by ``nrc_eval_mf_tc``
     (tcgen05 candidate pass + exact re-score; same bits);
   * any other model keeps the reference flow per batch: ``model.predict(batch_users, None)`` ->
     [B, num_items] scores -> train items masked to -inf (``nrc_mask_rows``) ->
@@ -111,18 +111,12 @@ class UniEvaluator(AbstractEvaluator):
         final = np.reshape(final, [self.metrics_num, self.max_top])[:, self.top_show - 1].reshape(-1)
         return "\t".join([("%.8f" % x).ljust(12) for x in final])      # uni_evaluator.py:156
 
-    TC_MIN_ITEMS = 262144
-
     def _evaluate_fused(self, model, test_users):
         (trp, tri), (tep, tei) = self._device_csr()
         U, V = model.get_eval_tables()
         users = torch.as_tensor(np.asarray(test_users, dtype=np.int32)).cuda()
-        n_items, dim = V.shape
-        # Large catalogues: score step on the tensor cores (bit-identical results).
-        # Below ~256 k items the SIMT kernel's single pass is faster than candidate pass + re-score.
-        if n_items >= self.TC_MIN_ITEMS and dim in (64, 128, 192) and self.max_top <= 31:
-            return ops.eval_mf_tc(U, V, users, trp, tri, tep, tei, self.metrics, self.max_top)
-        return ops.eval_mf(U, V, users, trp, tri, tep, tei, self.metrics, self.max_top)
+        # Large catalogues go through the tensor-core path (bit-identical results).
+        return ops.eval_mf_auto(U, V, users, trp, tri, tep, tei, self.metrics, self.max_top)
 
     def _evaluate_generic(self, model, test_users):
         (trp, tri), _ = self._device_csr()

@@ -135,6 +135,21 @@ def eval_mf_tc(user_table, item_table, users, train_indptr, train_indices, test_
     return (res, ranks) if return_ranks else res
 
 
+TC_MIN_ITEMS = 16384     # measured crossover on B200: 8 192 users x 16 384 items, d=64 -> 1.8x; see profiles/dbg_tc_crossover.py
+
+
+def eval_mf_auto(user_table, item_table, users, train_indptr, train_indices, test_indptr, test_indices,
+                 metric, top_k, return_ranks=False):
+    """eval_mf, with the score step on the tensor cores when the catalogue is large enough for the
+    candidate pass to pay off (results are bit-identical either way)."""
+    n_items, dim = item_table.shape
+    if n_items >= TC_MIN_ITEMS and dim in (64, 128, 192) and top_k <= 31 and users.numel() >= 1024:
+        return eval_mf_tc(user_table, item_table, users, train_indptr, train_indices, test_indptr, test_indices,
+                          metric, top_k, return_ranks)
+    return eval_mf(user_table, item_table, users, train_indptr, train_indices, test_indptr, test_indices,
+                   metric, top_k, return_ranks)
+
+
 def eval_tc_last_launch():
     """(kernel_ms, flops) of the last tcgen05 candidate-kernel launch made by eval_mf_tc."""
     import ctypes

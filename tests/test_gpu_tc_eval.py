@@ -132,7 +132,7 @@ def test_uni_evaluator_routes_large_catalogues_to_the_tensor_core_path(monkeypat
     main.py logs, uni_evaluator.py:150-156) must not change by a character."""
     from neurec_b200.evaluator.uni_evaluator import UniEvaluator
     from neurec_b200 import ops
-    nu, ni, dim = 300, 3000, 64
+    nu, ni, dim = 1100, 3000, 64
     U, V, tp, ti, sp, si = _problem(nu, ni, dim, 77)
     train = {u: ti[tp[u]:tp[u + 1]].tolist() for u in range(nu)}
     test = {u: si[sp[u]:sp[u + 1]].tolist() for u in range(nu)}
@@ -145,6 +145,6 @@ def test_uni_evaluator_routes_large_catalogues_to_the_tensor_core_path(monkeypat
     calls = []
     real = ops.eval_mf_tc
     monkeypatch.setattr(ops, "eval_mf_tc", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
-    monkeypatch.setattr(UniEvaluator, "TC_MIN_ITEMS", 1000)
+    monkeypatch.setattr(ops, "TC_MIN_ITEMS", 1000)
     assert ev.evaluate(Model()) == plain
     assert calls == [1]
