@@ -274,6 +274,20 @@ int nrc_mf_bpr_sgd_fused(float* user_table, float* item_table, int32_t dim, cons
                          const int32_t* pos_items, const int32_t* neg_items, int64_t batch,
                          float lr, float reg, float* loss, void* stream);
 
+/* nrc_mf_bpr_sgd_fused on ROW-SHARDED tables (BASELINE config 5: tables larger than one GPU).
+ * Shard r of a table holds global rows [r*rows_per_shard, (r+1)*rows_per_shard); user_shards /
+ * item_shards are HOST arrays of `world` device pointers: the caller's own shard plus peer
+ * mappings of the other ranks' shards (CUDA IPC; nrc_enable_peer_access first).  Every rank calls
+ * it with its own triplets (global ids; the reference partitions by user, so `users` are normally
+ * local rows); remote rows are read and updated in place over NVLink by the same kernel -- no
+ * all-to-all of ids, rows or gradients.  world <= 8, global ids must fit int32. */
+int nrc_mf_bpr_sgd_sharded(float* const* user_shards, float* const* item_shards, int32_t world,
+                           int64_t users_per_shard, int64_t items_per_shard, int32_t dim,
+                           const int32_t* users, const int32_t* pos_items, const int32_t* neg_items,
+                           int64_t batch, float lr, float reg, float* loss, void* stream);
+/* Let kernels of the current device dereference memory of `peer_device` (idempotent). */
+int nrc_enable_peer_access(int32_t peer_device);
+
 /* Same rules for every variable of a model in ONE launch (what `optimizer.minimize(loss)`
  * applies per step).  All arrays are HOST arrays of length n_vars holding device pointers /
  * shapes; dense_var[i] = 1 marks a variable whose gradient is a dense tensor (tf.layers.dense

@@ -155,9 +155,22 @@ mf_pointwise_grad_kernel(const float* __restrict__ U, const float* __restrict__ 
 // batch has already updated ("hogwild inside a batch"); identical to the two-phase step when
 // no row repeats inside the batch.
 // ----------------------------------------------------------------------------------------
+// A table row-sharded over up to 8 GPUs of one NVLink domain: shard r holds rows
+// [r*rows_per_shard, (r+1)*rows_per_shard) at base[r]; base[own rank] is local memory, the others
+// are peer mappings (CUDA IPC), read with plain loads and updated with RED over NVLink.
+struct RowShards {
+    float* base[8];
+    int32_t rows_per_shard;   // 0: a single local table at base[0]
+    __device__ __forceinline__ float* row(int32_t id, int D) const {
+        if (rows_per_shard == 0) return base[0] + (size_t)id * D;
+        const int32_t owner = id / rows_per_shard;
+        return base[owner] + (size_t)(id - owner * rows_per_shard) * D;
+    }
+};
+
 template <int VEC>
 __global__ void __launch_bounds__(256)
-mf_bpr_sgd_fused_kernel(float* __restrict__ U, float* __restrict__ V, const int32_t* __restrict__ users,
+mf_bpr_sgd_fused_kernel(const RowShards U, const RowShards V, const int32_t* __restrict__ users,
                         const int32_t* __restrict__ pos, const int32_t* __restrict__ neg, int64_t batch,
                         float lr, float reg, float* __restrict__ loss) {
     constexpr int D = 32 * VEC;
@@ -165,9 +178,9 @@ mf_bpr_sgd_fused_kernel(float* __restrict__ U, float* __restrict__ V, const int3
     const int64_t wpb = blockDim.x >> 5;
     float loss_acc = 0.0f;
     for (int64_t b = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); b < batch; b += (int64_t)gridDim.x * wpb) {
-        float* pu = U + (size_t)users[b] * D + lane * VEC;
-        float* qi = V + (size_t)pos[b] * D + lane * VEC;
-        float* qj = V + (size_t)neg[b] * D + lane * VEC;
+        float* pu = U.row(users[b], D) + lane * VEC;
+        float* qi = V.row(pos[b], D) + lane * VEC;
+        float* qj = V.row(neg[b], D) + lane * VEC;
         float a[VEC], bi[VEC], bj[VEC];
         if constexpr (VEC == 4) {
             const float4 x = *reinterpret_cast<const float4*>(pu), y = *reinterpret_cast<const float4*>(qi),
@@ -215,6 +228,22 @@ mf_bpr_sgd_fused_kernel(float* __restrict__ U, float* __restrict__ V, const int3
         }
     }
     if (lane == 0 && loss) atomicAdd(loss, loss_acc);
+}
+
+static int launch_bpr_sgd(const RowShards& SU, const RowShards& SV, int dim, const int32_t* users,
+                          const int32_t* pos, const int32_t* neg, int64_t batch, float lr, float reg, float* loss,
+                          cudaStream_t st) {
+    int64_t blocks = (batch + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;   // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (dim == 128)
+        mf_bpr_sgd_fused_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(SU, SV, users, pos, neg, batch, lr, reg, loss);
+    else if (dim == 64)
+        mf_bpr_sgd_fused_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(SU, SV, users, pos, neg, batch, lr, reg, loss);
+    else
+        mf_bpr_sgd_fused_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(SU, SV, users, pos, neg, batch, lr, reg, loss);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
 }
 
 static int grad_grid(int64_t batch) {
@@ -275,20 +304,49 @@ extern "C" int nrc_mf_bpr_sgd_fused(float* user_table, float* item_table, int32_
                 "the fused single-pass step supports dim 32, 64 or 128 (got %d)", dim);
     NRC_REQUIRE(batch >= 0, NRC_E_VALUE, "batch must be >= 0");
     if (batch == 0) return NRC_OK;
-    int64_t blocks = (batch + 7) / 8;
-    const int64_t cap = (int64_t)sm_count() * 8;   // 8 resident CTAs of 256 threads per SM
-    if (blocks > cap) blocks = cap;
-    cudaStream_t st = as_stream(stream);
-    if (dim == 128)
-        mf_bpr_sgd_fused_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(user_table, item_table, users, pos_items,
-                                                                    neg_items, batch, lr, reg, loss);
-    else if (dim == 64)
-        mf_bpr_sgd_fused_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(user_table, item_table, users, pos_items,
-                                                                    neg_items, batch, lr, reg, loss);
-    else
-        mf_bpr_sgd_fused_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(user_table, item_table, users, pos_items,
-                                                                    neg_items, batch, lr, reg, loss);
-    NRC_CUDA_CHECK(cudaGetLastError());
+    RowShards SU{}, SV{};
+    SU.base[0] = user_table; SV.base[0] = item_table;
+    return launch_bpr_sgd(SU, SV, dim, users, pos_items, neg_items, batch, lr, reg, loss, as_stream(stream));
+}
+
+// The same single-pass step on ROW-SHARDED tables (BASELINE config 5): every rank runs it on its
+// own triplets (users it owns, items anywhere); rows of other ranks are read and updated in place
+// through peer memory over NVLink -- gather, score, loss, gradient and the exchange are ONE kernel,
+// there is no all-to-all of ids, rows or gradients.
+extern "C" int nrc_mf_bpr_sgd_sharded(float* const* user_shards, float* const* item_shards, int32_t world,
+                                      int64_t users_per_shard, int64_t items_per_shard, int32_t dim,
+                                      const int32_t* users, const int32_t* pos_items, const int32_t* neg_items,
+                                      int64_t batch, float lr, float reg, float* loss, void* stream) {
+    NRC_REQUIRE(world >= 1 && world <= 8, NRC_E_LIMIT, "world %d outside [1, 8]", world);
+    NRC_REQUIRE(user_shards != nullptr && item_shards != nullptr, NRC_E_VALUE, "shard pointer arrays are NULL");
+    NRC_REQUIRE(users_per_shard > 0 && items_per_shard > 0 && users_per_shard < (1ll << 31) &&
+                    items_per_shard < (1ll << 31) && users_per_shard * world < (1ll << 31) &&
+                    items_per_shard * world < (1ll << 31),
+                NRC_E_LIMIT, "global row ids must fit int32");
+    NRC_REQUIRE(dim == 32 || dim == 64 || dim == 128, NRC_E_LIMIT, "fused SGD supports dim 32, 64, 128 (got %d)", dim);
+    if (batch <= 0) return NRC_OK;
+    RowShards SU{}, SV{};
+    for (int r = 0; r < world; ++r) {
+        NRC_REQUIRE(user_shards[r] != nullptr && item_shards[r] != nullptr, NRC_E_VALUE, "shard %d is NULL", r);
+        SU.base[r] = user_shards[r];
+        SV.base[r] = item_shards[r];
+    }
+    SU.rows_per_shard = (int32_t)users_per_shard;
+    SV.rows_per_shard = (int32_t)items_per_shard;
+    return launch_bpr_sgd(SU, SV, dim, users, pos_items, neg_items, batch, lr, reg, loss, as_stream(stream));
+}
+
+// Peer mappings are only usable by kernels of this device after peer access is enabled.
+extern "C" int nrc_enable_peer_access(int32_t peer_device) {
+    int cur = 0;
+    NRC_CUDA_CHECK(cudaGetDevice(&cur));
+    if (cur == peer_device) return NRC_OK;
+    int can = 0;
+    NRC_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+    NRC_REQUIRE(can, NRC_E_CUDA, "device %d cannot access device %d", cur, peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return NRC_OK; }
+    NRC_CUDA_CHECK(e);
     return NRC_OK;
 }
 

@@ -52,3 +52,37 @@ def test_single_process_is_identity():
     assert sharded.gather_rows(x, 5) is x
     s, n = sharded.reduce_sums(x)
     assert n == 5 and np.allclose(s.numpy(), x.double().sum(0).numpy())
+
+
+def _route_worker(rank, ws, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    from neurec_b200.util import peer
+    per = peer.rows_per_shard(1001, ws)                       # 501 rows per shard
+    rs = np.random.RandomState(10 + rank)
+    n = 300 + 17 * rank
+    users = rs.randint(0, 1001, n).astype(np.int32)
+    pos = (users * 3 + rank).astype(np.int32)                 # payload tied to the user id and the source
+    neg = (users * 5 + 7).astype(np.int32)
+    u, p, q = peer.route_triplets_to_user_owner(users, pos, neg, per)
+    ok = bool(np.all(peer.owner_of(u, per) == rank))          # only my users arrive
+    ok &= bool(np.all(q == u * 5 + 7)) and bool(np.all((p - u * 3 >= 0) & (p - u * 3 < ws)))
+    counts = [None] * ws
+    dist.all_gather_object(counts, (n, len(u), int(np.sum(peer.owner_of(users, per) == rank))))
+    ok &= sum(c[0] for c in counts) == sum(c[1] for c in counts)       # nothing lost or duplicated
+    # triplets keep (source rank, original order): my own part is a subsequence of what I sent
+    mine_sent = users[peer.owner_of(users, per) == rank]
+    src = p - u * 3
+    ok &= bool(np.array_equal(u[src == rank], mine_sent))
+    out[rank] = int(ok)
+    dist.destroy_process_group()
+
+
+def test_route_triplets_to_user_owner_world_size_2_gloo():
+    """Host logic of the row-sharded training path (BASELINE config 5): triplets are exchanged so
+    that every rank trains the users whose rows it owns."""
+    ws = 2
+    out = mp.Manager().dict()
+    mp.spawn(_route_worker, args=(ws, _free_port(), out), nprocs=ws, join=True)
+    assert [out[r] for r in range(ws)] == [1, 1]
