@@ -1135,7 +1135,7 @@ def measure_sharded_sgd(K, W, world, rank, windows):
         return u, p, ng
     u, p, ng = ids((K + W) * bs)
     loss = torch.zeros(1, device="cuda")
-    step = lambda s: ops.mf_bpr_sgd_sharded(Us, Vs, u[s * bs:(s + 1) * bs], p[s * bs:(s + 1) * bs],
+    step = lambda s: ops.mf_bpr_sgd_sharded(Us, Vs, rank, u[s * bs:(s + 1) * bs], p[s * bs:(s + 1) * bs],
                                             ng[s * bs:(s + 1) * bs], lr, 0.0, loss)
     for s in range(W):
         step(s)
@@ -1158,7 +1158,7 @@ def measure_sharded_sgd(K, W, world, rank, windows):
         sl = slice(s * bs, (s + 1) * bs)
         du.copy_(hu[sl], non_blocking=True); dp.copy_(hp[sl], non_blocking=True); dn.copy_(hn[sl], non_blocking=True)
         loss.zero_()
-        ops.mf_bpr_sgd_sharded(Us, Vs, du, dp, dn, lr, 0.0, loss)
+        ops.mf_bpr_sgd_sharded(Us, Vs, rank, du, dp, dn, lr, 0.0, loss)
         loss_pin.copy_(loss, non_blocking=True)
         torch.cuda.synchronize()
     for s in range(W):
@@ -1217,6 +1217,15 @@ def run_ours(args):
             out.update(o)
         args.only = True
     elif args.workload == "bprmf-sharded":
+        if world > 1 and os.environ.get("NRC_EXPERIMENTAL_SHARDED") != "1":
+            # Round-1 status: the kernel, the ABI and the host logic exist and the local-row path is
+            # verified, but kernels faulted on the CUDA-IPC peer mappings on the 2-GPU box
+            # (tests/mgpu_sharded_check.py stage 1); see DESIGN.md section 5.  Refuse instead of crashing.
+            if rank == 0:
+                emit(json.dumps({"workload": "bprmf-sharded", "n_gpus": world,
+                                 "unavailable": "row-sharded peer-memory path not validated yet "
+                                                "(set NRC_EXPERIMENTAL_SHARDED=1 to run it anyway)"}))
+            return
         o = measure_sharded_sgd(K, W, world, rank, windows)
         out = None
         if rank == 0:

@@ -280,9 +280,10 @@ int nrc_mf_bpr_sgd_fused(float* user_table, float* item_table, int32_t dim, cons
  * mappings of the other ranks' shards (CUDA IPC; nrc_enable_peer_access first).  Every rank calls
  * it with its own triplets (global ids; the reference partitions by user, so `users` are normally
  * local rows); remote rows are read and updated in place over NVLink by the same kernel -- no
- * all-to-all of ids, rows or gradients.  world <= 8, global ids must fit int32. */
+ * all-to-all of ids, rows or gradients (local rows: one vector RED; peer rows: scalar REDs).
+ * self_rank = index of the caller's own shard.  world <= 8, global ids must fit int32. */
 int nrc_mf_bpr_sgd_sharded(float* const* user_shards, float* const* item_shards, int32_t world,
-                           int64_t users_per_shard, int64_t items_per_shard, int32_t dim,
+                           int32_t self_rank, int64_t users_per_shard, int64_t items_per_shard, int32_t dim,
                            const int32_t* users, const int32_t* pos_items, const int32_t* neg_items,
                            int64_t batch, float lr, float reg, float* loss, void* stream);
 /* Let kernels of the current device dereference memory of `peer_device` (idempotent). */

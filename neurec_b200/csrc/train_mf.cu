@@ -161,12 +161,28 @@ mf_pointwise_grad_kernel(const float* __restrict__ U, const float* __restrict__ 
 struct RowShards {
     float* base[8];
     int32_t rows_per_shard;   // 0: a single local table at base[0]
-    __device__ __forceinline__ float* row(int32_t id, int D) const {
-        if (rows_per_shard == 0) return base[0] + (size_t)id * D;
+    int32_t self;             // this rank's shard (rows of other shards live in peer memory)
+    __device__ __forceinline__ float* row(int32_t id, int D, bool& remote) const {
+        if (rows_per_shard == 0) { remote = false; return base[0] + (size_t)id * D; }
         const int32_t owner = id / rows_per_shard;
+        remote = owner != self;
         return base[owner] + (size_t)(id - owner * rows_per_shard) * D;
     }
 };
+
+// In-place row update.  Local rows take one vector RED; rows in peer memory take scalar REDs
+// (32-bit float atomics are the form every NVLink generation forwards to the owner's L2).
+template <int VEC>
+__device__ __forceinline__ void red_row(float* p, const float (&d)[VEC], bool remote) {
+    if (remote) {
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) atomicAdd(p + t, d[t]);
+        return;
+    }
+    if constexpr (VEC == 4) atomicAdd(reinterpret_cast<float4*>(p), make_float4(d[0], d[1], d[2], d[3]));
+    else if constexpr (VEC == 2) atomicAdd(reinterpret_cast<float2*>(p), make_float2(d[0], d[1]));
+    else atomicAdd(p, d[0]);
+}
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
@@ -178,9 +194,10 @@ mf_bpr_sgd_fused_kernel(const RowShards U, const RowShards V, const int32_t* __r
     const int64_t wpb = blockDim.x >> 5;
     float loss_acc = 0.0f;
     for (int64_t b = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); b < batch; b += (int64_t)gridDim.x * wpb) {
-        float* pu = U.row(users[b], D) + lane * VEC;
-        float* qi = V.row(pos[b], D) + lane * VEC;
-        float* qj = V.row(neg[b], D) + lane * VEC;
+        bool ru, ri, rj;
+        float* pu = U.row(users[b], D, ru) + lane * VEC;
+        float* qi = V.row(pos[b], D, ri) + lane * VEC;
+        float* qj = V.row(neg[b], D, rj) + lane * VEC;
         float a[VEC], bi[VEC], bj[VEC];
         if constexpr (VEC == 4) {
             const float4 x = *reinterpret_cast<const float4*>(pu), y = *reinterpret_cast<const float4*>(qi),
@@ -215,17 +232,9 @@ mf_bpr_sgd_fused_kernel(const RowShards U, const RowShards V, const int32_t* __r
             dvi[t] = -lr * (g * a[t] + reg * bi[t]);
             dvj[t] = -lr * (-g * a[t] + reg * bj[t]);
         }
-        if constexpr (VEC == 4) {
-            atomicAdd(reinterpret_cast<float4*>(pu), make_float4(du[0], du[1], du[2], du[3]));
-            atomicAdd(reinterpret_cast<float4*>(qi), make_float4(dvi[0], dvi[1], dvi[2], dvi[3]));
-            atomicAdd(reinterpret_cast<float4*>(qj), make_float4(dvj[0], dvj[1], dvj[2], dvj[3]));
-        } else if constexpr (VEC == 2) {
-            atomicAdd(reinterpret_cast<float2*>(pu), make_float2(du[0], du[1]));
-            atomicAdd(reinterpret_cast<float2*>(qi), make_float2(dvi[0], dvi[1]));
-            atomicAdd(reinterpret_cast<float2*>(qj), make_float2(dvj[0], dvj[1]));
-        } else {
-            atomicAdd(pu, du[0]); atomicAdd(qi, dvi[0]); atomicAdd(qj, dvj[0]);
-        }
+        red_row<VEC>(pu, du, ru);
+        red_row<VEC>(qi, dvi, ri);
+        red_row<VEC>(qj, dvj, rj);
     }
     if (lane == 0 && loss) atomicAdd(loss, loss_acc);
 }
@@ -314,10 +323,11 @@ extern "C" int nrc_mf_bpr_sgd_fused(float* user_table, float* item_table, int32_
 // through peer memory over NVLink -- gather, score, loss, gradient and the exchange are ONE kernel,
 // there is no all-to-all of ids, rows or gradients.
 extern "C" int nrc_mf_bpr_sgd_sharded(float* const* user_shards, float* const* item_shards, int32_t world,
-                                      int64_t users_per_shard, int64_t items_per_shard, int32_t dim,
+                                      int32_t self_rank, int64_t users_per_shard, int64_t items_per_shard, int32_t dim,
                                       const int32_t* users, const int32_t* pos_items, const int32_t* neg_items,
                                       int64_t batch, float lr, float reg, float* loss, void* stream) {
     NRC_REQUIRE(world >= 1 && world <= 8, NRC_E_LIMIT, "world %d outside [1, 8]", world);
+    NRC_REQUIRE(self_rank >= 0 && self_rank < world, NRC_E_VALUE, "self_rank %d outside [0, %d)", self_rank, world);
     NRC_REQUIRE(user_shards != nullptr && item_shards != nullptr, NRC_E_VALUE, "shard pointer arrays are NULL");
     NRC_REQUIRE(users_per_shard > 0 && items_per_shard > 0 && users_per_shard < (1ll << 31) &&
                     items_per_shard < (1ll << 31) && users_per_shard * world < (1ll << 31) &&
@@ -333,6 +343,7 @@ extern "C" int nrc_mf_bpr_sgd_sharded(float* const* user_shards, float* const* i
     }
     SU.rows_per_shard = (int32_t)users_per_shard;
     SV.rows_per_shard = (int32_t)items_per_shard;
+    SU.self = SV.self = self_rank;
     return launch_bpr_sgd(SU, SV, dim, users, pos_items, neg_items, batch, lr, reg, loss, as_stream(stream));
 }
 

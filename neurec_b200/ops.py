@@ -253,7 +253,7 @@ def mf_bpr_sgd_fused(U, V, users, pos, neg, lr, reg, loss_out):
     _count()
 
 
-def mf_bpr_sgd_sharded(user_shards, item_shards, users, pos, neg, lr, reg, loss_out):
+def mf_bpr_sgd_sharded(user_shards, item_shards, self_rank, users, pos, neg, lr, reg, loss_out):
     """The single-pass BPR + SGD step on row-sharded tables (nrc_mf_bpr_sgd_sharded): `user_shards`
     / `item_shards` are lists with one [rows_per_shard, dim] tensor per rank -- this rank's own
     shard and peer mappings of the others (neurec_b200.util.peer.open_peer_shards); ids are global."""
@@ -262,7 +262,7 @@ def mf_bpr_sgd_sharded(user_shards, item_shards, users, pos, neg, lr, reg, loss_
     assert w == len(item_shards) and w >= 1
     up = (ctypes.c_void_p * w)(*[t.data_ptr() for t in user_shards])
     ip = (ctypes.c_void_p * w)(*[t.data_ptr() for t in item_shards])
-    check(_lib.load().nrc_mf_bpr_sgd_sharded(up, ip, w, user_shards[0].shape[0], item_shards[0].shape[0],
+    check(_lib.load().nrc_mf_bpr_sgd_sharded(up, ip, w, int(self_rank), user_shards[0].shape[0], item_shards[0].shape[0],
                                              user_shards[0].shape[1], _p(users), _p(pos), _p(neg), users.numel(),
                                              float(lr), float(reg), _p(loss_out), _stream()))
     _count()
