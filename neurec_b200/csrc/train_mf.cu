@@ -162,11 +162,22 @@ struct RowShards {
     float* base[8];
     int32_t rows_per_shard;   // 0: a single local table at base[0]
     int32_t self;             // this rank's shard (rows of other shards live in peer memory)
+    // SHARDED is a compile-time switch and the shard base is picked with constant indices only, so
+    // the struct stays in the kernel-parameter constant bank (a dynamic index would spill it to
+    // local memory and cost the single-GPU kernel ~15 % of its bandwidth).
+    template <bool SHARDED>
     __device__ __forceinline__ float* row(int32_t id, int D, bool& remote) const {
-        if (rows_per_shard == 0) { remote = false; return base[0] + (size_t)id * D; }
-        const int32_t owner = id / rows_per_shard;
-        remote = owner != self;
-        return base[owner] + (size_t)(id - owner * rows_per_shard) * D;
+        if constexpr (!SHARDED) {
+            remote = false;
+            return base[0] + (size_t)id * D;
+        } else {
+            const int32_t owner = id / rows_per_shard;
+            remote = owner != self;
+            float* b = base[0];
+#pragma unroll
+            for (int r = 1; r < 8; ++r) b = (owner == r) ? base[r] : b;
+            return b + (size_t)(id - owner * rows_per_shard) * D;
+        }
     }
 };
 
@@ -184,7 +195,7 @@ __device__ __forceinline__ void red_row(float* p, const float (&d)[VEC], bool re
     else atomicAdd(p, d[0]);
 }
 
-template <int VEC>
+template <int VEC, bool SHARDED>
 __global__ void __launch_bounds__(256)
 mf_bpr_sgd_fused_kernel(const RowShards U, const RowShards V, const int32_t* __restrict__ users,
                         const int32_t* __restrict__ pos, const int32_t* __restrict__ neg, int64_t batch,
@@ -195,9 +206,9 @@ mf_bpr_sgd_fused_kernel(const RowShards U, const RowShards V, const int32_t* __r
     float loss_acc = 0.0f;
     for (int64_t b = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); b < batch; b += (int64_t)gridDim.x * wpb) {
         bool ru, ri, rj;
-        float* pu = U.row(users[b], D, ru) + lane * VEC;
-        float* qi = V.row(pos[b], D, ri) + lane * VEC;
-        float* qj = V.row(neg[b], D, rj) + lane * VEC;
+        float* pu = U.row<SHARDED>(users[b], D, ru) + lane * VEC;
+        float* qi = V.row<SHARDED>(pos[b], D, ri) + lane * VEC;
+        float* qj = V.row<SHARDED>(neg[b], D, rj) + lane * VEC;
         float a[VEC], bi[VEC], bj[VEC];
         if constexpr (VEC == 4) {
             const float4 x = *reinterpret_cast<const float4*>(pu), y = *reinterpret_cast<const float4*>(qi),
@@ -245,12 +256,14 @@ static int launch_bpr_sgd(const RowShards& SU, const RowShards& SV, int dim, con
     int64_t blocks = (batch + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 8;   // 8 resident CTAs of 256 threads per SM
     if (blocks > cap) blocks = cap;
-    if (dim == 128)
-        mf_bpr_sgd_fused_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(SU, SV, users, pos, neg, batch, lr, reg, loss);
-    else if (dim == 64)
-        mf_bpr_sgd_fused_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(SU, SV, users, pos, neg, batch, lr, reg, loss);
-    else
-        mf_bpr_sgd_fused_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(SU, SV, users, pos, neg, batch, lr, reg, loss);
+    const unsigned gb = (unsigned)blocks;
+#define NRC_LAUNCH_SGD(VEC, SH) \
+    mf_bpr_sgd_fused_kernel<VEC, SH><<<gb, 256, 0, st>>>(SU, SV, users, pos, neg, batch, lr, reg, loss)
+    const bool sharded = SU.rows_per_shard != 0;
+    if (dim == 128) { if (sharded) NRC_LAUNCH_SGD(4, true); else NRC_LAUNCH_SGD(4, false); }
+    else if (dim == 64) { if (sharded) NRC_LAUNCH_SGD(2, true); else NRC_LAUNCH_SGD(2, false); }
+    else { if (sharded) NRC_LAUNCH_SGD(1, true); else NRC_LAUNCH_SGD(1, false); }
+#undef NRC_LAUNCH_SGD
     NRC_CUDA_CHECK(cudaGetLastError());
     return NRC_OK;
 }
