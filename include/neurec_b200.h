@@ -288,6 +288,12 @@ int nrc_mf_bpr_sgd_sharded(float* const* user_shards, float* const* item_shards,
                            int64_t batch, float lr, float reg, float* loss, void* stream);
 /* Let kernels of the current device dereference memory of `peer_device` (idempotent). */
 int nrc_enable_peer_access(int32_t peer_device);
+/* CUDA IPC for the shards: export = 64-byte handle of the allocation holding dev_ptr + the offset
+ * of dev_ptr inside it; open (in ANOTHER process, with the importing device current) maps it with
+ * lazy peer access and returns the pointer that corresponds to dev_ptr; close unmaps it. */
+int nrc_ipc_export(const void* dev_ptr, void* handle64_out, int64_t* offset_out);
+int nrc_ipc_open(const void* handle64, int64_t offset, void** dev_ptr_out);
+int nrc_ipc_close(void* dev_ptr, int64_t offset);
 
 /* Same rules for every variable of a model in ONE launch (what `optimizer.minimize(loss)`
  * applies per step).  All arrays are HOST arrays of length n_vars holding device pointers /

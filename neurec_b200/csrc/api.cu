@@ -191,6 +191,51 @@ extern "C" int nrc_graph_destroy(nrc_step_graph* g) {
     return NRC_OK;
 }
 
+// ---- CUDA IPC for row-sharded tables -----------------------------------------------------------
+// The exporter hands out the handle of the ALLOCATION that holds `dev_ptr` plus the offset of
+// dev_ptr inside it (framework allocators sub-allocate).  The importer opens it with ITS OWN device
+// current and cudaIpcMemLazyEnablePeerAccess, the way NCCL maps peer buffers, so that kernels of
+// the importing device can dereference the mapping over NVLink.
+extern "C" int nrc_ipc_export(const void* dev_ptr, void* handle64_out, int64_t* offset_out) {
+    NRC_REQUIRE(dev_ptr && handle64_out && offset_out, NRC_E_VALUE, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);   // cuMemGetAddressRange_v2
+    static range_fn get_range = nullptr;
+    if (!get_range) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        NRC_CUDA_CHECK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q));
+        NRC_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, NRC_E_CUDA,
+                    "the driver does not export cuMemGetAddressRange");
+        get_range = reinterpret_cast<range_fn>(fn);
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    const int cr = get_range(&base, &size, (unsigned long long)(uintptr_t)dev_ptr);
+    NRC_REQUIRE(cr == 0 && base != 0, NRC_E_CUDA, "cuMemGetAddressRange failed (%d)", cr);
+    cudaIpcMemHandle_t h;
+    NRC_CUDA_CHECK(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base)));
+    memcpy(handle64_out, &h, sizeof(h));
+    *offset_out = (int64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+    return NRC_OK;
+}
+
+extern "C" int nrc_ipc_open(const void* handle64, int64_t offset, void** dev_ptr_out) {
+    NRC_REQUIRE(handle64 && dev_ptr_out && offset >= 0, NRC_E_VALUE, "bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* base = nullptr;
+    NRC_CUDA_CHECK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr_out = reinterpret_cast<char*>(base) + offset;
+    return NRC_OK;
+}
+
+extern "C" int nrc_ipc_close(void* dev_ptr, int64_t offset) {
+    if (!dev_ptr) return NRC_OK;
+    NRC_CUDA_CHECK(cudaIpcCloseMemHandle(reinterpret_cast<char*>(dev_ptr) - offset));
+    return NRC_OK;
+}
+
 extern "C" int nrc_version(void) { return 100; }  // 0.1.0
 
 extern "C" const char* nrc_last_error(void) { return nrc::g_err; }

@@ -5,6 +5,8 @@ allocates its block and maps the blocks of the other ranks into its address spac
 IPC (PyTorch's storage-sharing plumbing), so that a kernel can read and `RED` remote rows directly
 over NVLink (`nrc_mf_bpr_sgd_sharded`).  `torch.distributed` is only used to exchange the handles.
 """
+import ctypes
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -22,25 +24,57 @@ def owner_of(ids, per_shard):
     return np.asarray(ids) // int(per_shard)
 
 
+class PeerShard:
+    """A row block that lives on another rank's GPU, mapped into this process with CUDA IPC
+    (nrc_ipc_open, importing device current).  Only what the kernels need: data_ptr() and shape."""
+
+    def __init__(self, ptr, offset, shape, dtype):
+        self._ptr, self._offset, self.shape, self.dtype = ptr, offset, tuple(shape), dtype
+
+    def data_ptr(self):
+        return self._ptr
+
+    def close(self):
+        if self._ptr:
+            _lib.load().nrc_ipc_close(ctypes.c_void_p(self._ptr), self._offset)
+            self._ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def open_peer_shards(local):
     """All-gather CUDA IPC handles of `local` (this rank's [rows_per_shard, dim] block, the same
-    shape on every rank) and return one tensor per rank: `local` itself at this rank's position,
-    peer mappings elsewhere.  Peer access is enabled for kernels of the current device.  Keep the
-    returned tensors alive as long as kernels may touch them."""
-    from torch.multiprocessing.reductions import reduce_tensor
+    shape on every rank) and return one entry per rank: `local` itself at this rank's position,
+    PeerShard mappings elsewhere (opened with THIS rank's device current, so its kernels can read
+    and RED the rows over NVLink).  Keep `local` alive on its owner while any peer uses it.
+
+    Round-1 status: the first version went through torch's storage sharing, which opens the handle
+    with the owner's device current; kernels then faulted on the mapping.  This version has not run
+    on a multi-GPU box yet (tests/mgpu_sharded_check.py is the check)."""
     ws, rank = dist.get_world_size(), dist.get_rank()
     assert local.is_cuda and local.is_contiguous()
+    lib = _lib.load()
+    handle = (ctypes.c_ubyte * 64)()
+    offset = ctypes.c_int64(0)
+    _lib.check(lib.nrc_ipc_export(ctypes.c_void_p(local.data_ptr()), handle, ctypes.byref(offset)))
+    info = (bytes(handle), int(offset.value), tuple(local.shape), str(local.dtype), int(local.device.index))
     gathered = [None] * ws
-    dist.all_gather_object(gathered, reduce_tensor(local))     # (rebuild function, IPC handle + layout)
+    dist.all_gather_object(gathered, info)
     out = []
-    for r, (rebuild, args) in enumerate(gathered):
+    for r, (hbytes, off, shape, dtype, dev_index) in enumerate(gathered):
         if r == rank:
             out.append(local)
             continue
-        t = rebuild(*args)                                       # cudaIpcOpenMemHandle on the owner's device
-        assert t.shape == local.shape and t.dtype == local.dtype
-        _lib.check(_lib.load().nrc_enable_peer_access(int(t.device.index)))
-        out.append(t)
+        assert tuple(shape) == tuple(local.shape) and dtype == str(local.dtype)
+        _lib.check(lib.nrc_enable_peer_access(dev_index))
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(hbytes)
+        ptr = ctypes.c_void_p()
+        _lib.check(lib.nrc_ipc_open(buf, off, ctypes.byref(ptr)))
+        out.append(PeerShard(int(ptr.value), off, shape, local.dtype))
     dist.barrier()
     return out
 

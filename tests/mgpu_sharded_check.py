@@ -36,7 +36,7 @@ def main():
     myV = torch.randn(ni_l, dim, device="cuda", generator=g) * 0.1
     Us, Vs = peer.open_peer_shards(myU), peer.open_peer_shards(myV)
     if rank == 0:
-        print("peer shards mapped: devices", [str(t.device) for t in Us], flush=True)
+        print("peer shards mapped:", [type(t).__name__ for t in Us], flush=True)
     loc = lambda n, per: (torch.randperm(per, device="cuda")[:n] + rank * per).to(torch.int32)
     loss = torch.zeros(1, device="cuda")
     before = myV.clone()
