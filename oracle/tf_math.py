@@ -465,3 +465,107 @@ class NCFTrainer:
             sl = slice(off, min(len(users), off + batch_size))
             out.append(self.step(users[sl], items[sl], third[sl]))
         return np.asarray(out, f32)
+
+
+# ----------------------------------------------------------------------------------------
+# NGCF: restatement of NGCF.py:160-202 (propagation + dense part) and
+# NGCF.py:94-110 (loss), ahead of the CUDA kernels.  Same conventions as above: numpy, the
+# arrays' own dtype (fp32 in use, fp64 for the finite-difference checks), explicit dropout masks
+# so that a GPU run and this restatement can share them (tf.nn.dropout is ALWAYS on in the
+# reference, also at evaluation time, NGCF.py:193).  Parity unpinned at the TensorFlow boundary.
+# ----------------------------------------------------------------------------------------
+LEAKY_ALPHA = 0.2            # tf.nn.leaky_relu default
+L2NORM_EPS = 1e-12           # tf.nn.l2_normalize default epsilon
+
+
+def ngcf_adj(train_indptr, train_indices, num_users, num_items, adj_type="norm"):
+    """get_adj_mat (NGCF.py:299-322): 'norm' = D^-1 (A + I) (the conf default), 'plain', 'gcmc',
+    otherwise D^-1 A + I -- the same four matrices create_adj_mat of LightGCN builds."""
+    return lightgcn_adj(train_indptr, train_indices, num_users, num_items, adj_type)
+
+
+def ngcf_init_weights(rs, emb_dim, layer_size):
+    """[(W_gc, b_gc, W_bi, b_bi)] per layer with xavier-normal kernels (conf default) and the
+    reference's shapes: W [d_k, d_{k+1}], b [1, d_{k+1}] (NGCF.py:262-284)."""
+    dims = [emb_dim] + list(layer_size)
+    out = []
+    for k in range(len(layer_size)):
+        std = np.sqrt(2.0 / (dims[k] + dims[k + 1]))
+        mk = lambda r, c: (rs.randn(r, c) * std).astype(f32)
+        out.append((mk(dims[k], dims[k + 1]), mk(1, dims[k + 1]), mk(dims[k], dims[k + 1]), mk(1, dims[k + 1])))
+    return out
+
+
+def _leaky(x):
+    return np.where(x > 0, x, x * x.dtype.type(LEAKY_ALPHA))
+
+
+def ngcf_forward(A, e0, weights, masks=None, keep=1.0):
+    """_create_ngcf_embed (NGCF.py:160-202).  masks[k]: 0/1 array like layer k's output (None = no
+    dropout); tf.nn.dropout(x, keep) = x * mask / keep.  The n_fold row slabs (174-179) are a
+    memory work-around: concatenating slab products equals one product with the whole matrix.
+    -> (all_embeddings [N, d0 + sum(d_k)], cache for ngcf_backward)."""
+    dt = e0.dtype.type
+    ego = e0
+    outs, cache = [e0], []
+    for k, (Wgc, bgc, Wbi, bbi) in enumerate(weights):
+        side = np.asarray(A @ ego, dtype=e0.dtype)                    # sum messages of neighbours
+        z1 = side @ Wgc + bgc
+        bi = ego * side
+        z2 = bi @ Wbi + bbi
+        h = _leaky(z1) + _leaky(z2)
+        m = None if masks is None or masks[k] is None else masks[k].astype(e0.dtype)
+        hd = h if m is None else h * m / dt(keep)
+        sq = (hd * hd).sum(1, keepdims=True)
+        inv = 1.0 / np.sqrt(np.maximum(sq, dt(L2NORM_EPS)))
+        outs.append((hd * inv).astype(e0.dtype))
+        cache.append((ego, side, z1, z2, m, hd, sq, inv))
+        ego = hd
+    return np.concatenate(outs, axis=1), cache
+
+
+def ngcf_loss_and_grad(A, AT, e0, weights, num_users, users, pos, neg, reg, masks=None, keep=1.0):
+    """NGCF.py:94-110: sum softplus(-(pos - neg)) + reg * l2_loss(u, i, j) on the CONCATENATED
+    embeddings, back-propagated by hand through the normalise / dropout / leaky-relu / two GEMMs /
+    SpMM of every layer.  -> (mf_loss, emb_loss, dE0, [(dWgc, dbgc, dWbi, dbbi)], all_embeddings)."""
+    dt = e0.dtype.type
+    allE, cache = ngcf_forward(A, e0, weights, masks, keep)
+    ru, ri, rj = np.asarray(users), num_users + np.asarray(pos), num_users + np.asarray(neg)
+    eu, ei, ej = allE[ru], allE[ri], allE[rj]
+    x = (eu * ei).sum(1) - (eu * ej).sum(1)
+    l = np.where(x >= 0, np.log1p(np.exp(-x)), -x + np.log1p(np.exp(x)))      # softplus(-x)
+    g = (-1.0 / (1.0 + np.exp(x))).astype(e0.dtype)[:, None]
+    reg = dt(reg)
+    emb = reg * dt(0.5) * ((eu * eu).sum() + (ei * ei).sum() + (ej * ej).sum())
+    G = np.zeros_like(allE)
+    np.add.at(G, ru, g * (ei - ej) + reg * eu)
+    np.add.at(G, ri, g * eu + reg * ei)
+    np.add.at(G, rj, -g * eu + reg * ej)
+    # split the gradient of the concatenation back onto the layers
+    dims = [e0.shape[1]] + [w[0].shape[1] for w in weights]
+    offs = np.cumsum([0] + dims)
+    d_ego_next = np.zeros((e0.shape[0], dims[-1]), e0.dtype)      # gradient flowing into layer K's raw output
+    grads = [None] * len(weights)
+    for k in range(len(weights) - 1, -1, -1):
+        Wgc, bgc, Wbi, bbi = weights[k]
+        ego, side, z1, z2, m, hd, sq, inv = cache[k]
+        gn = G[:, offs[k + 1]:offs[k + 2]]                          # d loss / d normalised output of layer k
+        # y = hd * inv,  inv = max(sq, eps)^-1/2  (l2_normalize)
+        dot = (gn * hd).sum(1, keepdims=True)
+        live = (sq > dt(L2NORM_EPS)).astype(e0.dtype)
+        dhd = gn * inv - live * hd * dot * inv ** 3
+        dhd = dhd + d_ego_next                                       # the un-normalised hd also feeds layer k+1
+        dh = dhd if m is None else dhd * m / dt(keep)
+        dz1 = dh * np.where(z1 > 0, dt(1), dt(LEAKY_ALPHA))
+        dz2 = dh * np.where(z2 > 0, dt(1), dt(LEAKY_ALPHA))
+        dWgc, dbgc = side.T @ dz1, dz1.sum(0, keepdims=True)
+        bi = ego * side
+        dWbi, dbbi = bi.T @ dz2, dz2.sum(0, keepdims=True)
+        dside = dz1 @ Wgc.T
+        dbi = dz2 @ Wbi.T
+        dside = dside + dbi * ego
+        dego = dbi * side + np.asarray(AT @ dside, dtype=e0.dtype)
+        grads[k] = (dWgc.astype(e0.dtype), dbgc.astype(e0.dtype), dWbi.astype(e0.dtype), dbbi.astype(e0.dtype))
+        d_ego_next = dego
+    dE0 = (G[:, :dims[0]] + d_ego_next).astype(e0.dtype)
+    return l.sum(), emb, dE0, grads, allE

@@ -220,3 +220,68 @@ def test_numpy_axis0_mean_is_sequential_fp32():
     for r in range(1, len(a)):
         acc = (acc + a[r]).astype(np.float32)
     assert np.array_equal(np.mean(a, axis=0), acc / np.float32(len(a)))
+
+
+# ----------------------------------------------------------------------------- NGCF restatement
+def _ngcf_problem(dtype, seed=3, nu=23, ni=31, d=8, layers=(6, 5)):
+    from oracle import tf_math
+    rs = np.random.RandomState(seed)
+    rows = [np.unique(rs.randint(0, ni, rs.randint(1, 7))) for _ in range(nu)]
+    indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum([len(r) for r in rows])
+    A = tf_math.ngcf_adj(indptr, np.concatenate(rows).astype(np.int32), nu, ni, "norm").astype(dtype)
+    e0 = (rs.randn(nu + ni, d) * 0.3).astype(dtype)
+    W = [tuple(w.astype(dtype) for w in ws) for ws in tf_math.ngcf_init_weights(rs, d, list(layers))]
+    masks = [(rs.rand(nu + ni, k) < 0.9).astype(dtype) for k in layers]
+    users = rs.randint(0, nu, 40); pos = rs.randint(0, ni, 40); neg = rs.randint(0, ni, 40)
+    return A, e0, W, masks, nu, users, pos, neg
+
+
+def test_ngcf_adjacency_is_row_normalised_with_self_loops():
+    """NGCF.py:308-310: 'norm' = D^-1 (A + I): every row sums to 1, the diagonal is 1/(deg+1)."""
+    A, e0, *_ = _ngcf_problem(np.float64)
+    assert np.allclose(np.asarray(A.sum(1)).ravel(), 1.0)
+    deg = np.diff(A.indptr) - 1
+    assert np.allclose(A.diagonal(), 1.0 / (deg + 1))
+
+
+def test_ngcf_forward_shapes_and_normalisation():
+    from oracle import tf_math
+    A, e0, W, masks, nu, *_ = _ngcf_problem(np.float32)
+    allE, cache = tf_math.ngcf_forward(A, e0, W, masks, keep=0.9)
+    assert allE.dtype == np.float32 and allE.shape == (e0.shape[0], 8 + 6 + 5)
+    assert np.array_equal(allE[:, :8], e0)                                   # layer 0 is the raw table
+    n1 = np.linalg.norm(allE[:, 8:14], axis=1)
+    assert np.allclose(n1[n1 > 0], 1.0, atol=1e-5)                           # l2_normalize(axis=1)
+    # n_fold slabs are a no-op: concatenated slab products == one product
+    fold = (A.shape[0]) // 7
+    slabs = [A[i * fold:(A.shape[0] if i == 6 else (i + 1) * fold)] @ e0 for i in range(7)]
+    assert np.array_equal(np.concatenate(slabs, 0), A @ e0)
+
+
+def test_ngcf_gradients_match_finite_differences():
+    """Manual backprop of NGCF.py:160-202 + 94-110 (normalise, always-on dropout, leaky-relu, W_gc /
+    W_bi GEMMs, SpMM, concat) against central differences in fp64."""
+    from oracle import tf_math
+    A, e0, W, masks, nu, users, pos, neg = _ngcf_problem(np.float64)
+    AT = A.T.tocsr()
+    reg = 0.05
+
+    def total(e0_, W_):
+        mf, emb, *_ = tf_math.ngcf_loss_and_grad(A, AT, e0_, W_, nu, users, pos, neg, reg, masks, keep=0.9)
+        return mf + emb
+    mf, emb, dE0, grads, _ = tf_math.ngcf_loss_and_grad(A, AT, e0, W, nu, users, pos, neg, reg, masks, keep=0.9)
+    rs = np.random.RandomState(0)
+    h = 1e-6
+    for _ in range(12):                                                       # embedding table entries
+        r, c = rs.randint(e0.shape[0]), rs.randint(e0.shape[1])
+        p, m = e0.copy(), e0.copy(); p[r, c] += h; m[r, c] -= h
+        fd = (total(p, W) - total(m, W)) / (2 * h)
+        assert abs(fd - dE0[r, c]) < 1e-5 * max(1.0, abs(fd)), (r, c, fd, dE0[r, c])
+    for k in range(len(W)):                                                   # every weight tensor of every layer
+        for t in range(4):
+            r, c = rs.randint(W[k][t].shape[0]), rs.randint(W[k][t].shape[1])
+            Wp = [list(w) for w in W]; Wm = [list(w) for w in W]
+            Wp[k][t] = W[k][t].copy(); Wp[k][t][r, c] += h
+            Wm[k][t] = W[k][t].copy(); Wm[k][t][r, c] -= h
+            fd = (total(e0, [tuple(w) for w in Wp]) - total(e0, [tuple(w) for w in Wm])) / (2 * h)
+            assert abs(fd - grads[k][t][r, c]) < 1e-5 * max(1.0, abs(fd)), (k, t, fd, grads[k][t][r, c])
