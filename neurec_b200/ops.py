@@ -138,12 +138,19 @@ def eval_mf_tc(user_table, item_table, users, train_indptr, train_indices, test_
 TC_MIN_ITEMS = 16384     # measured crossover on B200: 8 192 users x 16 384 items, d=64 -> 1.8x; see profiles/dbg_tc_crossover.py
 
 
+def use_tensor_core_eval(n_items, dim, top_k, n_users):
+    """Routing rule of eval_mf_auto: the tcgen05 candidate pass needs dim in {64, 128, 192} (operand
+    tiles of 64-element K blocks that fit shared memory), top_k + 1 <= 32 (one lane per kept score)
+    and pays off from TC_MIN_ITEMS items / ~1 k users up."""
+    return n_items >= TC_MIN_ITEMS and dim in (64, 128, 192) and 1 <= top_k <= 31 and n_users >= 1024
+
+
 def eval_mf_auto(user_table, item_table, users, train_indptr, train_indices, test_indptr, test_indices,
                  metric, top_k, return_ranks=False):
     """eval_mf, with the score step on the tensor cores when the catalogue is large enough for the
     candidate pass to pay off (results are bit-identical either way)."""
     n_items, dim = item_table.shape
-    if n_items >= TC_MIN_ITEMS and dim in (64, 128, 192) and top_k <= 31 and users.numel() >= 1024:
+    if use_tensor_core_eval(n_items, dim, top_k, users.numel()):
         return eval_mf_tc(user_table, item_table, users, train_indptr, train_indices, test_indptr, test_indices,
                           metric, top_k, return_ranks)
     return eval_mf(user_table, item_table, users, train_indptr, train_indices, test_indptr, test_indices,

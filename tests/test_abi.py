@@ -56,3 +56,14 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.NrcError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_evaluator_routing_rule():
+    """Host logic only: which evaluations go to the tensor-core path (ops.eval_mf_auto)."""
+    from neurec_b200 import ops
+    assert ops.use_tensor_core_eval(40981, 64, 20, 29858)            # gowalla (LightGCN config)
+    assert ops.use_tensor_core_eval(10_000_000, 128, 20, 37888)      # BASELINE config 4
+    assert not ops.use_tensor_core_eval(1682, 64, 20, 943)           # ml-100k: SIMT kernel
+    assert not ops.use_tensor_core_eval(40981, 32, 20, 29858)        # dim not a multiple of 64
+    assert not ops.use_tensor_core_eval(40981, 64, 50, 29858)        # top_k > 31
+    assert not ops.use_tensor_core_eval(40981, 64, 20, 128)          # a handful of users
