@@ -162,8 +162,9 @@ int nrc_eval_last_undecided(int32_t* count_host);
  * that can enter the reference's heap, then exact fp32 re-scoring of the candidates, the same
  * tie-aware selection as nrc_eval_mf and -- for users with ties -- the libstdc++ heap replayed
  * over the first 2*top_k items + the candidates.  Results are bit-identical to nrc_eval_mf.
- * dim in {64,128,192,256}, top_k <= 31; cand_cap = candidate slots per user (0 = 2048; users
- * that overflow fall back to the full-catalogue heap-replay kernel). */
+ * dim 64 or 128 with top_k <= 31, or dim 192 with top_k <= 16; cand_cap = entries per candidate
+ * list (0 = 1024; users whose list overflows fall back to the full-catalogue heap-replay kernel).
+ * Synchronises `stream` once (to size the tie-replay pass): not capturable into a CUDA graph. */
 int nrc_eval_mf_tc(const float* user_table, const float* item_table, int32_t dim,
                    int32_t num_items, const int32_t* users, int32_t num_eval_users,
                    const int64_t* train_indptr, const int32_t* train_indices,

@@ -1317,6 +1317,11 @@ extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, 
                               int32_t cand_cap, float* results, int32_t* ranks, void* stream) {
     NRC_REQUIRE(top_k > 0 && top_k + 1 <= 32, NRC_E_LIMIT, "the tensor-core path needs top_k in [1, 31]");
     NRC_REQUIRE(num_items > top_k, NRC_E_VALUE, "num_items (%d) must be > top_k (%d)", num_items, top_k);
+    // shared memory: 2 user tiles + >= 2 item stages + per-user lists (33 words, 65 for the replay
+    // pass when 2*top_k > 32) must fit 227 KB -- dim 192 leaves room for the short lists only
+    NRC_REQUIRE(dim == 64 || dim == 128 || (dim == 192 && 2 * top_k <= 32), NRC_E_LIMIT,
+                "the tensor-core path supports dim 64, 128 (top_k <= 31) and 192 (top_k <= 16); got dim %d top_k %d",
+                dim, top_k);
     int rc = check_metrics(metric_host, metric_num);
     if (rc) return rc;
     if (num_eval_users <= 0) return NRC_OK;

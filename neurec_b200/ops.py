@@ -139,10 +139,11 @@ TC_MIN_ITEMS = 16384     # measured crossover on B200: 8 192 users x 16 384 item
 
 
 def use_tensor_core_eval(n_items, dim, top_k, n_users):
-    """Routing rule of eval_mf_auto: the tcgen05 candidate pass needs dim in {64, 128, 192} (operand
-    tiles of 64-element K blocks that fit shared memory), top_k + 1 <= 32 (one lane per kept score)
+    """Routing rule of eval_mf_auto: the tcgen05 candidate pass needs dim 64 or 128 with top_k <= 31 (one
+    lane per kept score) or dim 192 with top_k <= 16 (shared-memory budget of the tie-replay pass)
     and pays off from TC_MIN_ITEMS items / ~1 k users up."""
-    return n_items >= TC_MIN_ITEMS and dim in (64, 128, 192) and 1 <= top_k <= 31 and n_users >= 1024
+    fits = (dim in (64, 128) and 1 <= top_k <= 31) or (dim == 192 and 1 <= top_k <= 16)
+    return n_items >= TC_MIN_ITEMS and fits and n_users >= 1024
 
 
 def eval_mf_auto(user_table, item_table, users, train_indptr, train_indices, test_indptr, test_indices,
