@@ -6,18 +6,24 @@
 // throughput.  The ranking still has to be the reference's, bit for bit, so the tensor cores
 // only SELECT: scores are computed from bf16 copies of the tables (exact products, fp32
 // accumulation in TMEM), every item whose approximate score can still belong to the exact top
-// K+1 (a rigorous margin, see below) becomes a candidate, and the candidates are re-scored with
-// the oracle's fp32 FMA chain and ranked by the tie-aware selection of evaluator.cu.
+// K+1 (a rigorous margin, see tc_prepare_users_kernel) becomes a candidate, and the candidates are
+// re-scored with the oracle's fp32 FMA chain and ranked by the tie-aware selection of evaluator.cu
+// (users with ties: second pass with the reference's heap root as threshold + libstdc++ heap replay).
 //
 // Blackwell specifics used here (sm_100a only):
-//   * tcgen05.mma.cta_group::1.kind::f16, M=128 (users) x N=256 (items) x K=16 per instruction,
-//     issued by ONE thread; operands in shared memory described by UMMA descriptors (K-major,
-//     no swizzle: 8x16-byte core matrices, LBO = distance between the two K-chunks of a k-step,
-//     SBO = distance between 8-row groups);
-//   * the fp32 accumulator tile lives in Tensor Memory (tcgen05.alloc, 256 columns per buffer,
-//     two buffers so that the epilogue of tile t overlaps the MMAs of tile t+1);
-//   * tcgen05.commit -> mbarrier hands the accumulator to the epilogue warps, which read it with
-//     tcgen05.ld.32x32b (warp w owns TMEM lanes 32w..32w+31 = 32 users, one user per thread).
+//   * TMA: cp.async.bulk.tensor.2d through a CUtensorMap (SWIZZLE_128B, 128 x 64 bf16 boxes, rows
+//     past the end of the table zero-filled) brings the item tiles into a ring of shared-memory
+//     stages; completion is signalled with mbarrier complete_tx;
+//   * tcgen05.mma.cta_group::1.kind::f16, M=128 (users) x N=128|256 (items) x K=16 per instruction,
+//     issued by ONE thread; operands described by UMMA shared-memory descriptors (K-major,
+//     SWIZZLE_128B: 64-element K blocks, rows 128 B apart, 16-byte chunk c of row r at c ^ (r & 7));
+//   * the fp32 accumulators live in Tensor Memory (tcgen05.alloc of all 512 columns: two user
+//     halves x 256 columns); tcgen05.commit -> mbarrier hands an accumulator to its epilogue warps,
+//     which read it with tcgen05.ld.32x32b.x32 (warp w owns TMEM lanes 32(w%4).. = 32 users, one
+//     user per thread) and release it through another mbarrier.
+// The kernel, its pipelines and what bounds it are described above tc_candidate_kernel and in
+// DESIGN.md section 3a; nrc_tc_gemm_debug below is the stand-alone MMA building block the tests
+// use to pin the descriptor encodings (no-swizzle and SWIZZLE_128B) against a torch matmul.
 #include <cuda.h>            // CUtensorMap (types only; the encoder is fetched from the driver at run time)
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
@@ -105,24 +111,6 @@ __device__ __forceinline__ void load_tile_sw128(uint8_t* smem, const __nv_bfloat
         *reinterpret_cast<uint4*>(smem + (size_t)blk * rows * 128 + (size_t)row * 128 + ((c ^ (row & 7)) << 4)) = v;
     }
 }
-
-// Same layout, filled with cp.async (LDGSTS): no register staging, so a producer thread puts its
-// whole share of the tile in flight before waiting (rows >= valid_rows are zero-filled through
-// the src-size operand).  Caller: cp_async_wait_all(); fence_async_smem(); arrive.
-__device__ __forceinline__ void load_tile_sw128_async(uint8_t* smem, const __nv_bfloat16* __restrict__ g, int rows,
-                                                      int valid_rows, int K, int tid, int nthreads) {
-    const int chunks = K >> 3;
-    const uint32_t sbase = smem_u32(smem);
-    for (int idx = tid; idx < rows * chunks; idx += nthreads) {
-        const int row = idx / chunks, cg = idx - row * chunks;
-        const int blk = cg >> 3, c = cg & 7;
-        const uint32_t dst = sbase + (uint32_t)blk * rows * 128 + (uint32_t)row * 128 + ((c ^ (row & 7)) << 4);
-        const bool ok = row < valid_rows;
-        const void* src = ok ? (const void*)(reinterpret_cast<const uint4*>(g + (size_t)row * K) + cg) : (const void*)g;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
-    }
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // descriptors of k-step s (16 bf16) for a SWIZZLE_128B tile of `rows` rows
 __device__ __forceinline__ uint64_t sw128_desc(uint32_t tile_base, int rows, int s) {
