@@ -657,9 +657,12 @@ class LightgcnGowalla(Workload):
     def __init__(self, rank=0):
         super().__init__(synth_gowalla(), rank)
         self.launches_per_step = 2 * self.n_layers + 3
-        from oracle import tf_math      # host-side adjacency construction only (scipy, like the reference)
+        from neurec_b200.model.general_recommender.LightGCN import bipartite_adjacency   # the product's builder
         d = self.d
-        self.A = tf_math.lightgcn_adj(d["train_indptr"], d["train_indices"], d["num_users"], d["num_items"], "pre")
+        u = np.repeat(np.arange(d["num_users"], dtype=np.int32), np.diff(d["train_indptr"]))
+        A = bipartite_adjacency(u, d["train_indices"], d["num_users"], d["num_items"], "pre", verbose=False)
+        self.A = A.tocoo().astype(np.float32).tocsr()          # LightGCN.py:151-154
+        self.A.sort_indices()
         rs = np.random.RandomState(2017 + rank)
         n = d["num_users"] + d["num_items"]
         lim = np.sqrt(6.0 / (d["num_users"] + self.dim))

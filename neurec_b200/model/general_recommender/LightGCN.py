@@ -11,6 +11,49 @@ from ..AbstractRecommender import AbstractRecommender
 from .._engine import OptimizerState, get_initializer
 
 
+def bipartite_adjacency(users, items, n_users, n_items, adj_type, verbose=True):
+    """create_adj_mat of the reference (LightGCN.py:35-78; NGCF.py:299-322 builds the same four
+    matrices): [[0, R], [R^T, 0]] over users+items and its normalisations, fp64 scipy calls in the
+    reference's order.  'plain' A; 'norm' D^-1 (A + I); 'gcmc' D^-1 A; 'pre' D^-1/2 A D^-1/2;
+    anything else D^-1 A + I."""
+    say = print if verbose else (lambda *a: None)
+    u = np.asarray(users, dtype=np.int32)
+    i = np.asarray(items, dtype=np.int32)
+    n = n_users + n_items
+    half = sp.csr_matrix((np.ones_like(u, dtype=np.float32), (u, i + n_users)), shape=(n, n))
+    adj = half + half.T
+
+    def row_normalised(a):
+        deg = np.array(a.sum(1))
+        with np.errstate(divide="ignore"):
+            inv = np.power(deg, -1).flatten()
+        inv[np.isinf(inv)] = 0.
+        say("generate single-normalized adjacency matrix.")
+        return sp.diags(inv).dot(a).tocoo()
+
+    if adj_type == "plain":
+        out = adj
+        say("use the plain adjacency matrix")
+    elif adj_type == "norm":
+        out = row_normalised(adj + sp.eye(n))
+        say("use the normalized adjacency matrix")
+    elif adj_type == "gcmc":
+        out = row_normalised(adj)
+        say("use the gcmc adjacency matrix")
+    elif adj_type == "pre":
+        deg = np.array(adj.sum(1))
+        with np.errstate(divide="ignore"):
+            inv = np.power(deg, -0.5).flatten()
+        inv[np.isinf(inv)] = 0.
+        d = sp.diags(inv)
+        out = d.dot(adj).dot(d)
+        say("use the pre adjcency matrix")
+    else:
+        out = row_normalised(adj) + sp.eye(n)
+        say("use the mean adjacency matrix")
+    return out
+
+
 class LightGCN(AbstractRecommender):
     def __init__(self, sess, dataset, config):
         super(LightGCN, self).__init__(dataset, config)
@@ -32,41 +75,7 @@ class LightGCN(AbstractRecommender):
         """LightGCN.py:35-78: bipartite adjacency and its normalisations, fp64 scipy like the
         reference; cast to fp32 when uploaded (LightGCN.py:151-154)."""
         users, items = self.dataset.get_train_interactions()
-        u = np.asarray(users, dtype=np.int32)
-        i = np.asarray(items, dtype=np.int32)
-        n = self.n_users + self.n_items
-        half = sp.csr_matrix((np.ones_like(u, dtype=np.float32), (u, i + self.n_users)), shape=(n, n))
-        adj = half + half.T
-
-        def row_normalised(a):
-            deg = np.array(a.sum(1))
-            with np.errstate(divide="ignore"):
-                inv = np.power(deg, -1).flatten()
-            inv[np.isinf(inv)] = 0.
-            print("generate single-normalized adjacency matrix.")
-            return sp.diags(inv).dot(a).tocoo()
-
-        if adj_type == "plain":
-            out = adj
-            print("use the plain adjacency matrix")
-        elif adj_type == "norm":
-            out = row_normalised(adj + sp.eye(n))
-            print("use the normalized adjacency matrix")
-        elif adj_type == "gcmc":
-            out = row_normalised(adj)
-            print("use the gcmc adjacency matrix")
-        elif adj_type == "pre":
-            deg = np.array(adj.sum(1))
-            with np.errstate(divide="ignore"):
-                inv = np.power(deg, -0.5).flatten()
-            inv[np.isinf(inv)] = 0.
-            d = sp.diags(inv)
-            out = d.dot(adj).dot(d)
-            print("use the pre adjcency matrix")
-        else:
-            out = row_normalised(adj) + sp.eye(n)
-            print("use the mean adjacency matrix")
-        return out
+        return bipartite_adjacency(users, items, self.n_users, self.n_items, adj_type)
 
     def build_graph(self):
         gen = torch.Generator().manual_seed(2017)

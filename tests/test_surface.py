@@ -281,3 +281,19 @@ def test_main_end_to_end(tmp_path, args):
         assert vals[-1, 4] > vals[0, 4] * 1.2                               # NDCG@5 improves
     assert os.path.isdir(tmp_path / "log" / "toy")
     assert os.path.isfile(data / "_tmp_toy" / "toy_ratio_u0_i0.train")      # split cache
+
+
+def test_product_adjacency_builder_equals_the_oracle(ml100k):
+    """neurec_b200's own create_adj_mat restatement (used by the LightGCN plug-in and by bench.py)
+    against the oracle's, for every adj_type of LightGCN.py:35-78 -- CPU only, no kernels."""
+    from neurec_b200.model.general_recommender.LightGCN import bipartite_adjacency
+    from oracle import tf_math
+    d = ml100k
+    nu, ni = d["num_users"], d["num_items"]
+    users = np.repeat(np.arange(nu, dtype=np.int32), np.diff(d["train_indptr"]))
+    for adj_type in ("plain", "norm", "gcmc", "pre", "mean"):
+        got = bipartite_adjacency(users, d["train_indices"], nu, ni, adj_type, verbose=False)
+        got = got.tocoo().astype(np.float32).tocsr(); got.sort_indices()
+        want = tf_math.lightgcn_adj(d["train_indptr"], d["train_indices"], nu, ni, adj_type)
+        assert got.shape == want.shape and np.array_equal(got.indptr, want.indptr)
+        assert np.array_equal(got.indices, want.indices) and np.array_equal(got.data, want.data), adj_type
