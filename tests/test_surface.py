@@ -297,3 +297,35 @@ def test_product_adjacency_builder_equals_the_oracle(ml100k):
         want = tf_math.lightgcn_adj(d["train_indptr"], d["train_indices"], nu, ni, adj_type)
         assert got.shape == want.shape and np.array_equal(got.indptr, want.indptr)
         assert np.array_equal(got.indices, want.indices) and np.array_equal(got.data, want.data), adj_type
+
+
+def test_abstract_recommender_wires_evaluator_and_logger(ml100k, tmp_path, monkeypatch):
+    """AbstractRecommender.__init__ (AbstractRecommender.py:23-36): ProxyEvaluator built from the
+    dataset's three dicts and the evaluation options of NeuRec.properties, a log file under
+    log/<dataset>/<model>/, dataset + configuration logged.  CPU only (no kernel is launched)."""
+    import scipy.sparse as sp
+    from neurec_b200.data import Dataset
+    from neurec_b200.evaluator import ProxyEvaluator
+    from neurec_b200.model.AbstractRecommender import AbstractRecommender
+    from neurec_b200.util import Configurator
+    (tmp_path / "conf").mkdir()
+    (tmp_path / "conf" / "MF.properties").write_text(REF_MF_CONF)
+    (tmp_path / "NeuRec.properties").write_text(open(os.path.join(ROOT, "NeuRec.properties")).read())
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(sys, "argv", ["main.py"])
+    conf = Configurator("NeuRec.properties", default_section="hyperparameters")
+    d = ml100k
+    shape = (d["num_users"], d["num_items"])
+    mk = lambda p, i: sp.csr_matrix((np.ones(len(d[i]), np.float32), d[i], d[p]), shape=shape)
+    ds = Dataset.from_csr("ml-100k", mk("train_indptr", "train_indices"), mk("test_indptr", "test_indices"))
+    model = AbstractRecommender(ds, conf)
+    assert isinstance(model.evaluator, ProxyEvaluator)
+    assert model.evaluator.metrics_info().startswith("metrics:\t")
+    for k in conf["topk"]:
+        assert "NDCG@%d" % k in model.evaluator.metrics_info()
+    logs = list((tmp_path / "log" / "ml-100k" / "MF").glob("ml-100k_*.log"))
+    assert len(logs) == 1 and "recommender" in logs[0].read_text()
+    with pytest.raises(NotImplementedError):
+        model.build_graph()
+    with pytest.raises(NotImplementedError):
+        model.predict([0], None)
