@@ -64,7 +64,9 @@ int nrc_stage_batch_host(const void* a_host, const void* b_host, const void* c_h
                          int64_t batch, void* staging, void* stream);
 int nrc_fetch_host(const float* src_dev, float* dst_host, int64_t count, void* stream);
 
-/* Captured training steps.  The reference pays one `sess.run` per batch; the lowest-overhead
+/* Captured training steps (replace the per-batch `sess.run((loss, optimizer), feed_dict)` of
+ * MF.py:97-108, NeuMF.py:131-147, MLP.py:104-120, LightGCN.py:170-178).  The reference pays one
+ * `sess.run` per batch; the lowest-overhead
  * analogue here is ONE cudaGraphLaunch per batch.  Between nrc_graph_capture_begin and
  * nrc_graph_capture_end every nrc_* device call issued on `stream` is recorded instead of run:
  *   nrc_graph_stage_async   H2D of the pinned staging block (3*batch ids/labels + 1 float lr_t)
@@ -275,7 +277,9 @@ int nrc_mf_bpr_sgd_fused(float* user_table, float* item_table, int32_t dim, cons
                          const int32_t* pos_items, const int32_t* neg_items, int64_t batch,
                          float lr, float reg, float* loss, void* stream);
 
-/* nrc_mf_bpr_sgd_fused on ROW-SHARDED tables (BASELINE config 5: tables larger than one GPU).
+/* nrc_mf_bpr_sgd_fused on ROW-SHARDED tables (BASELINE config 5: tables larger than one GPU; the
+ * arithmetic is MF.py:54-76 + learner.py:8 `GradientDescentOptimizer`, the reference itself has no
+ * multi-device path).
  * Shard r of a table holds global rows [r*rows_per_shard, (r+1)*rows_per_shard); user_shards /
  * item_shards are HOST arrays of `world` device pointers: the caller's own shard plus peer
  * mappings of the other ranks' shards (CUDA IPC; nrc_enable_peer_access first).  Every rank calls
@@ -296,8 +300,8 @@ int nrc_ipc_export(const void* dev_ptr, void* handle64_out, int64_t* offset_out)
 int nrc_ipc_open(const void* handle64, int64_t offset, void** dev_ptr_out);
 int nrc_ipc_close(void* dev_ptr, int64_t offset);
 
-/* Same rules for every variable of a model in ONE launch (what `optimizer.minimize(loss)`
- * applies per step).  All arrays are HOST arrays of length n_vars holding device pointers /
+/* Same rules for every variable of a model in ONE launch (what `optimizer.minimize(loss)`,
+ * util/learner.py:2-16, applies per step).  All arrays are HOST arrays of length n_vars holding device pointers /
  * shapes; dense_var[i] = 1 marks a variable whose gradient is a dense tensor (tf.layers.dense
  * kernel / bias: Apply* functor formulas, every element), 0 an IndexedSlices variable. */
 int nrc_opt_apply_multi(int32_t opt_kind, int32_t n_vars, float* const* var, float* const* grad,
