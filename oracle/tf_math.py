@@ -569,3 +569,49 @@ def ngcf_loss_and_grad(A, AT, e0, weights, num_users, users, pos, neg, reg, mask
         d_ego_next = dego
     dE0 = (G[:, :dims[0]] + d_ego_next).astype(e0.dtype)
     return l.sum(), emb, dE0, grads, allE
+
+
+class NGCFTrainer:
+    """NGCF.train_model (NGCF.py:125-141) on the restatement above: BPR-softplus step with TF-1.12
+    Adam; every gradient is dense here (E_0 through concat + SpMM, the layer weights by
+    construction), so all variables take the dense ApplyAdam formulas, like LightGCN's table.
+    Message dropout is always on in the reference (NGCF.py:193); masks come from `rs` so that a
+    GPU run can be fed the same ones."""
+
+    def __init__(self, A, e0, weights, num_users, lr=1e-3, reg=0.0, keep=0.9, rs=None):
+        self.A, self.AT = A, A.T.tocsr()
+        self.AT.sort_indices()
+        self.e0 = np.array(e0, f32)
+        self.W = [tuple(np.array(w, f32) for w in ws) for ws in weights]
+        self.num_users, self.lr, self.reg, self.keep, self.t = num_users, lr, reg, keep, 0
+        self.rs = rs or np.random.RandomState(0)
+        z = np.zeros_like
+        self.m_e, self.v_e = z(self.e0), z(self.e0)
+        self.m_w = [tuple(z(w) for w in ws) for ws in self.W]
+        self.v_w = [tuple(z(w) for w in ws) for ws in self.W]
+
+    def draw_masks(self):
+        if self.keep >= 1.0:
+            return None
+        n = self.e0.shape[0]
+        return [(self.rs.rand(n, ws[0].shape[1]) < self.keep).astype(f32) for ws in self.W]
+
+    def step(self, users, pos, neg, masks="draw"):
+        masks = self.draw_masks() if isinstance(masks, str) else masks
+        mf, emb, dE0, grads, _ = ngcf_loss_and_grad(self.A, self.AT, self.e0, self.W, self.num_users, users, pos, neg,
+                                                    self.reg, masks, self.keep)
+        hyper = [adam_lr_t(self.lr, 1, start_step=self.t)[0], 0.9, 0.999, 1e-8]
+        opt_apply("adam", self.e0, dE0.astype(f32), self.m_e, self.v_e, None, hyper, dense_var=True)
+        for k in range(len(self.W)):
+            for j in range(4):
+                opt_apply("adam", self.W[k][j], grads[k][j].astype(f32), self.m_w[k][j], self.v_w[k][j], None, hyper,
+                          dense_var=True)
+        self.t += 1
+        return f32(mf), f32(emb)
+
+    def embeddings(self, masks="draw"):
+        """What `evaluate` reads (NGCF.py:144-146): the concatenated embeddings of one more forward
+        pass -- with dropout still applied, as in the reference."""
+        masks = self.draw_masks() if isinstance(masks, str) else masks
+        allE, _ = ngcf_forward(self.A, self.e0, self.W, masks, self.keep)
+        return allE[:self.num_users], allE[self.num_users:]

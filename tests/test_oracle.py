@@ -285,3 +285,23 @@ def test_ngcf_gradients_match_finite_differences():
             Wm[k][t] = W[k][t].copy(); Wm[k][t][r, c] -= h
             fd = (total(e0, [tuple(w) for w in Wp]) - total(e0, [tuple(w) for w in Wm])) / (2 * h)
             assert abs(fd - grads[k][t][r, c]) < 1e-5 * max(1.0, abs(fd)), (k, t, fd, grads[k][t][r, c])
+
+
+def test_ngcf_trainer_learns_the_training_pairs():
+    """NGCFTrainer (BPR softplus + TF Adam over E_0 and all layer weights, always-on dropout): the loss
+    of a fixed batch goes down and positives end up ranked above negatives."""
+    from oracle import tf_math
+    A, e0, W, masks, nu, users, pos, neg = _ngcf_problem(np.float32, seed=9, nu=40, ni=60, d=8, layers=(8, 8))
+    rs = np.random.RandomState(1)
+    pos = np.array([A[u].indices[A[u].indices >= nu][0] - nu for u in users])   # a train item of each user
+    neg = rs.randint(0, 60, len(users))
+    tr = tf_math.NGCFTrainer(A, e0 * 0.1, W, nu, lr=0.01, reg=1e-4, keep=0.9, rs=np.random.RandomState(2))
+    first = [float(tr.step(users, pos, neg)[0]) for _ in range(5)]
+    for _ in range(150):
+        tr.step(users, pos, neg)
+    last = [float(tr.step(users, pos, neg)[0]) for _ in range(5)]
+    assert np.mean(last) < 0.6 * np.mean(first)
+    Ue, Ie = tr.embeddings(masks=None)
+    assert Ue.shape == (nu, 8 + 8 + 8) and Ie.shape == (60, 24) and Ue.dtype == np.float32
+    x = (Ue[users] * Ie[pos]).sum(1) - (Ue[users] * Ie[neg]).sum(1)
+    assert (x > 0).mean() > 0.8
