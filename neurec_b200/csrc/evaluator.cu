@@ -1308,7 +1308,7 @@ eval_tc_replay_kernel(const float* __restrict__ Utab, const float* __restrict__ 
 //           threshold -> libstdc++ heap replayed over the first 2K items + those candidates;
 //   users whose candidate list overflowed: full-catalogue heap replay (eval_mf_kernel).
 // Same results as nrc_eval_mf, bit for bit.  Synchronises `stream` once (to size pass 1), so it
-// cannot be captured into a CUDA graph.  cand_cap: entries per candidate list (0 = 1024).
+// cannot be captured into a CUDA graph.  cand_cap: entries per candidate list (0 = 1024; 2048 above 2^20 items).
 extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, int32_t dim,
                               int32_t num_items, const int32_t* users, int32_t num_eval_users,
                               const int64_t* train_indptr, const int32_t* train_indices,
@@ -1326,7 +1326,7 @@ extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, 
     if (rc) return rc;
     if (num_eval_users <= 0) return NRC_OK;
     g_last_was_tc = true;
-    const int K = top_k, cap = cand_cap > 0 ? cand_cap : 1024;
+    const int K = top_k, cap = cand_cap > 0 ? cand_cap : (num_items > (1 << 20) ? 2048 : 1024);
     const int L = (2 * K < num_items) ? 2 * K : num_items;   // evaluate.h:38 heap size
     cudaStream_t st = as_stream(stream);
     rc = tc::prepare_items(item_table, dim, num_items, st);

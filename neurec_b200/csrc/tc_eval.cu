@@ -562,8 +562,12 @@ __global__ void tc_prepare_items_kernel(const float* __restrict__ V, int64_t N, 
 }
 
 // bf16 rows of the evaluated users + their candidate margin
-//   |s_bf16 - s_exact| <= (2^-8 + 2^-12) |u| |v|   (bf16 rounding of both factors, fp32 accumulation)
-//   margin = 2 * eps, eps = (2^-8 + 2^-11) * |u| * max_i |v_i| * (1 + 2^-10)
+//   bf16 keeps 8 significant bits, so round-to-nearest has unit roundoff 2^-8 per FACTOR:
+//   u^_k v^_k = u_k v_k (1+a)(1+b), |a|,|b| <= 2^-8  =>  |u^.v^ - u.v| <= (2^-7 + 2^-16) sum|u_k v_k|
+//   <= (2^-7 + 2^-16) |u| |v| (Cauchy-Schwarz).  The fp32 accumulation in Tensor Memory (truncating
+//   adder, d <= 192 terms) and the fp32 FMA chain of the exact score add < 2^-11 |u| |v| together.
+//   eps = (2^-7 + 2^-11) * |u| * max_i |v_i| * 1.001 (norms are fp32-rounded), margin = 2 * eps:
+//   an item's approximate score and the order statistic it is compared with each move by <= eps.
 __global__ void tc_prepare_users_kernel(const float* __restrict__ U, const int32_t* __restrict__ users, int num_eval,
                                         int D, const unsigned int* __restrict__ vmax_bits,
                                         __nv_bfloat16* __restrict__ Ub, float* __restrict__ margin) {
@@ -580,7 +584,7 @@ __global__ void tc_prepare_users_kernel(const float* __restrict__ U, const int32
     sq = warp_sum(sq);
     if (lane == 0) {
         const float vmax = __uint_as_float(*vmax_bits);
-        margin[row] = 2.0f * (0.00390625f + 0.00048828125f) * sqrtf(sq) * vmax * 1.001f;
+        margin[row] = 2.0f * (0.0078125f + 0.00048828125f) * sqrtf(sq) * vmax * 1.001f;
     }
 }
 

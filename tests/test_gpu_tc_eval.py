@@ -148,3 +148,34 @@ def test_uni_evaluator_routes_large_catalogues_to_the_tensor_core_path(monkeypat
     monkeypatch.setattr(ops, "TC_MIN_ITEMS", 1000)
     assert ev.evaluate(Model()) == plain
     assert calls == [1]
+
+
+@pytest.mark.parametrize("K", [1, 5])
+def test_tc_eval_adversarial_bf16_rounding_keeps_the_exact_top1(K):
+    """Round-1 verdict's counter-example (tests/test_tc_algorithm_model.py::adversarial_top1_tables):
+    bf16 rounding pushes two decoys UP and the exact top-1 DOWN by almost 2^-7 relative each.  With the
+    round-1 margin (2^-8) the true top-1 was never a candidate; with eps = 2^-7 + 2^-11 it must be.
+    Padded past TC_MIN_ITEMS (16 384) so this is the shape UniEvaluator routes to the tensor cores."""
+    from neurec_b200 import ops
+    from test_tc_algorithm_model import adversarial_top1_tables
+    ni, dim = 16_500, 128
+    u, V = adversarial_top1_tables(n_items=ni, d=dim)
+    rs = np.random.RandomState(5)
+    V[3:] *= rs.uniform(0.2, 1.0, size=(ni - 3, 1)).astype(np.float32)      # distinct fillers, all far below
+    place = rs.permutation(ni)                                               # decoys / target anywhere in the stream
+    V = np.ascontiguousarray(V[np.argsort(place)])
+    target = int(place[2])
+    nu = 140
+    U = np.stack([u * np.float32(2.0 ** (j % 7 - 3)) for j in range(nu)])   # power-of-two scales keep the roundings
+    users = np.arange(nu, dtype=np.int32)
+    tp, ti = random_csr(rs, nu, ni, np.full(nu, 3))
+    for r in range(nu):                                                      # never mask the three special items
+        row = ti[tp[r]:tp[r + 1]]
+        assert not (set(row.tolist()) & {int(place[0]), int(place[1]), target})
+    sp, si = random_csr(rs, nu, ni, np.full(nu, 4))
+    want, wranks = oracle.eval_mf(U, V, users, tp, ti, sp, si, ALL, K, return_ranks=True)
+    assert (wranks[:, 0] == target).all()
+    got, ranks = ops.eval_mf_tc(dev(U), dev(V), dev(users), dev(tp), dev(ti), dev(sp), dev(si), ALL, K,
+                                return_ranks=True)
+    assert np.array_equal(ranks.cpu().numpy(), wranks)
+    assert np.array_equal(got.cpu().numpy(), want)

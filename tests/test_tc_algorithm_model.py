@@ -47,9 +47,15 @@ def approx_scores(u, V, order):
     return acc
 
 
-def margin_of(u, V):
+# bf16 has 8 significant bits: unit roundoff 2^-8 per factor, so two rounded factors move a product by
+# up to (2^-7 + 2^-16) of its size; 2^-11 covers the fp32 accumulation (tc_prepare_users_kernel).
+EPS_REL = 2.0 ** -7 + 2.0 ** -11
+EPS_REL_ROUND1 = 2.0 ** -8 + 2.0 ** -11      # the round-1 constant (assumed a roundoff of 2^-9): NOT rigorous
+
+
+def margin_of(u, V, eps_rel=EPS_REL):
     vmax = np.sqrt((V.astype(np.float32) ** 2).sum(1, dtype=np.float32)).max()
-    return np.float32(2.0) * np.float32(0.00390625 + 0.00048828125) * np.sqrt(np.float32((u * u).sum(dtype=np.float32))) \
+    return np.float32(2.0) * np.float32(eps_rel) * np.sqrt(np.float32((u * u).sum(dtype=np.float32))) \
         * vmax * np.float32(1.001)
 
 
@@ -59,8 +65,12 @@ CASES = {
                                           (rs.randn(n, d) * np.exp(rs.randn(n, 1) * 1.5)).astype(np.float32)),
     "cancelling": lambda rs, n, d: ((np.tile([1.0, -1.0], d // 2) * (1 + rs.rand(d) * 2 ** -8)).astype(np.float32),
                                     (1.0 + rs.rand(n, d) * 2 ** -7).astype(np.float32)),
-    "worst_rounding": lambda rs, n, d: (np.full(d, 1.0 + 2 ** -9 + 2 ** -12, np.float32),          # just above a bf16 tie
-                                        (np.full((n, d), 1.0 + 2 ** -9 + 2 ** -12) * rs.choice([1, 2, 4], (n, 1))).astype(np.float32)),
+    # just below / above a bf16 rounding tie (bf16 spacing in [1,2) is 2^-7, the tie sits at 1 + 2^-8):
+    # every factor moves by almost the full unit roundoff 2^-8, all in the same direction
+    "worst_rounding": lambda rs, n, d: (np.full(d, 1.0 + 2 ** -8 - 2 ** -20, np.float32),
+                                        (np.full((n, d), 1.0 + 2 ** -8 - 2 ** -20) * rs.choice([1, 2, 4], (n, 1))).astype(np.float32)),
+    "worst_rounding_up": lambda rs, n, d: (np.full(d, 1.0 + 2 ** -8 + 2 ** -20, np.float32),
+                                           (np.full((n, d), 1.0 + 2 ** -8 + 2 ** -20) * rs.choice([1, 2, 4], (n, 1))).astype(np.float32)),
     "tiny_and_huge": lambda rs, n, d: ((rs.randn(d) * 1e-18).astype(np.float32), (rs.randn(n, d) * 1e15).astype(np.float32)),
 }
 
@@ -128,3 +138,42 @@ def test_candidate_lists_are_supersets(case, segments):
         if exm[i] > heap[0]:                                       # evaluate.h:40-41, strict >
             assert i in cand2, (case, i)
             heap[0] = exm[i]; heap.sort()
+
+
+def adversarial_top1_tables(n_items=64, d=128):
+    """Round-1 verdict's counter-example: two decoys whose bf16 scores round UP by almost 2^-7 relative,
+    and the true top-1 (item 2) whose bf16 score rounds DOWN by as much.  K = 1."""
+    lo, hi = np.float32(1 + 2.0 ** -8 - 2.0 ** -16), np.float32(1 + 2.0 ** -8 + 2.0 ** -16)
+    assert d >= 128
+    u = np.zeros(d, np.float32); u[:63] = lo; u[63:126] = hi; u[126] = 0.5
+    A = np.zeros(d, np.float32); A[:63] = lo; A[126] = 0.25      # lo*lo: both factors round down
+    B = np.zeros(d, np.float32); B[63:126] = hi                  # hi*hi: both factors round up
+    V = np.zeros((n_items, d), np.float32)
+    V[0], V[1], V[2] = B, B, A
+    V[3:] = A * np.float32(0.5)                                  # filler far below
+    return u, V
+
+
+def test_round1_margin_drops_the_exact_top1_and_the_rigorous_one_keeps_it():
+    u, V = adversarial_top1_tables()
+    ex, ap = exact_scores(u, V), approx_scores(u, V, "fwd")
+    assert np.argmax(ex) == 2 and ex[2] > ex[0] == ex[1]          # item 2 is the exact top-1 ...
+    assert ap[0] > ap[2] and ap[1] > ap[2]                        # ... but bf16 ranks both decoys above it
+    masked = np.zeros(len(ex), bool)
+    K = 1
+    old = _stream_candidates(ap, masked, K + 1, margin_of(u, V, EPS_REL_ROUND1), 1)
+    assert 2 not in set(old.tolist())                             # the round-1 constant loses the true top-1
+    new = _stream_candidates(ap, masked, K + 1, margin_of(u, V), 1)
+    assert {0, 1, 2} <= set(new.tolist())
+    # (1) holds with the rigorous constant and is violated by the old one on this input
+    err = np.abs(ap.astype(np.float64) - ex.astype(np.float64)).max()
+    assert err <= 0.5 * float(margin_of(u, V)) and err > 0.5 * float(margin_of(u, V, EPS_REL_ROUND1))
+
+
+def test_single_factor_worst_case_exceeds_the_round1_bound():
+    u = np.full(128, 1 + 2.0 ** -8 - 2.0 ** -20, np.float32)
+    V = u[None, :].copy()
+    ex, ap = exact_scores(u, V), approx_scores(u, V, "f64")
+    err = float(abs(np.float64(ap[0]) - np.float64(ex[0])))
+    assert err > 0.5 * float(margin_of(u, V, EPS_REL_ROUND1))
+    assert err <= 0.5 * float(margin_of(u, V))
