@@ -219,6 +219,57 @@ int nrc_sample_negatives(const int64_t* train_indptr, const int32_t* train_indic
                          uint64_t seed, uint64_t stream_id, int64_t first_index,
                          int32_t* out, void* stream);
 
+/* ======================================================================================
+ * The device-resident epoch: shuffle + sampling + batching
+ * ==================================================================================== */
+
+/* RandomSampler, util/data_iterator.py:45-63 (`np.random.permutation(n)` per epoch): out[p] =
+ * index of the sample that lands at shuffled position p.  The order is a keyed bijection of
+ * [0, n) (alternating Feistel network + cycle walking, round keys from Philox4x32-10 keyed by
+ * (seed, epoch)) evaluated per element: no host permutation, no sort.  shuffle = 0 gives the
+ * identity (SequentialSampler, data_iterator.py:33-42).  out i64 [n]. */
+int nrc_shuffle_perm(int64_t n, int32_t shuffle, uint64_t seed, uint64_t epoch, int64_t* out,
+                     void* stream);
+
+/* One epoch of PairwiseSampler.__iter__ (data/sampler.py:189-206) or PointwiseSampler.__iter__
+ * (data/sampler.py:121-147) as device arrays, WITHOUT the per-sample python gather of
+ * util/data_iterator.py:147-152: positions [first, first + n_out) of the shuffled epoch.
+ *   pos_users / pos_items  the flattened positives of _generate_positive_items (sampler.py:24-39)
+ *   pairwise = 1: out_third i32 [n_out, neg_num] negatives of the positive at that position
+ *   pairwise = 0: samples are the positives (label 1.0) followed by the k-th negatives of all
+ *                 positives, k-major (sampler.py:139-141); out_items holds the item, out_third
+ *                 f32 [n_out] the label
+ * Negatives are the draws nrc_sample_negatives(seed, stream_id = epoch) makes for the same
+ * positive, so the epoch does not depend on how it is cut into calls or GPUs. */
+int nrc_epoch_build(const int64_t* train_indptr, const int32_t* train_indices,
+                    const int32_t* pos_users, const int32_t* pos_items, int64_t n_pos,
+                    int32_t neg_num, int32_t num_items, int32_t pairwise, int32_t shuffle,
+                    uint64_t seed, uint64_t epoch, int64_t first, int64_t n_out,
+                    int32_t* out_users, int32_t* out_items, void* out_third, void* stream);
+
+/* Steps [first_step, first_step + num_steps) of one epoch of MF.train_model (MF.py:84-108:
+ * sampler construction aside, `for batch in data_iter: sess.run((loss, optimizer), feed_dict)`)
+ * in ONE persistent cooperative launch: the epoch arrays of nrc_epoch_build (built in the same
+ * launch when first_step == 0, into ws_users / ws_items / ws_third, i32 [n_samples] each), then
+ * per step the gradient pass and the TensorFlow-1.12 optimizer over both tables with grid-wide
+ * barriers in between -- same arithmetic as nrc_mf_train_epoch.
+ *   adam_pows   device f32 [2] = {beta1^t, beta2^t} of the next step (TF's beta-power variables,
+ *               initialise to {beta1, beta2}); read and advanced by the kernel (adam only)
+ *   step_loss   device f32 [steps of the epoch]; zeroed when first_step == 0
+ *   drop_last   trims the epoch to a multiple of batch_size (sampler.py:150-155, 208-213)
+ * hyper_host = {lr, beta1|rho|momentum, beta2|momentum, eps} as in nrc_opt_apply_rows. */
+int nrc_mf_epoch_fused(float* user_table, float* item_table, int32_t num_users, int32_t num_items,
+                       int32_t dim, const int64_t* train_indptr, const int32_t* train_indices,
+                       const int32_t* pos_users, const int32_t* pos_items, int64_t n_pos,
+                       int32_t neg_num, int32_t pairwise, int32_t shuffle, int32_t drop_last,
+                       uint64_t seed, uint64_t epoch, int32_t batch_size, int64_t first_step,
+                       int64_t num_steps, int32_t loss_kind, float reg, int32_t opt_kind,
+                       const float* hyper_host, float* adam_pows, float* grad_user,
+                       float* grad_item, int32_t* touched_user, int32_t* touched_item,
+                       float* slot0_user, float* slot1_user, float* slot0_item, float* slot1_item,
+                       int32_t first_stamp, int32_t* ws_users, int32_t* ws_items, void* ws_third,
+                       float* step_loss, void* stream);
+
 /* batch_randint_choice(high, size, replace, p=None, exclusion), random_choice.pyx:64-89.
  * `size` is given as out_indptr i64 [n_rows+1] (prefix sums of the per-row sizes, device) and
  * total_out = out_indptr[n_rows]; exclusion CSR may be NULL.  replace=0 draws without
@@ -291,6 +342,30 @@ int nrc_mf_bpr_sgd_sharded(float* const* user_shards, float* const* item_shards,
                            int32_t self_rank, int64_t users_per_shard, int64_t items_per_shard, int32_t dim,
                            const int32_t* users, const int32_t* pos_items, const int32_t* neg_items,
                            int64_t batch, float lr, float reg, float* loss, void* stream);
+/* BPR + SGD straight from the train CSR (BASELINE configs[4]; MF.py:54-76 with learner=gd, plus
+ * data/sampler.py:71-90,189-206 and util/data_iterator.py:59 fused in): positions
+ * [first, first + count) of shuffled epoch `epoch` are sampled (keyed bijection + Philox rejection
+ * draw), scored and applied in place by ONE kernel -- no id arrays, no sampler pass.  user_table is
+ * this rank's row block and pos_users are LOCAL row ids (the train CSR is partitioned by user
+ * owner); item ids are global, item_shards[r] (host array of `world` device pointers) is the row
+ * block of rank r: own memory for r == self_rank, peer mappings otherwise (nrc_shard_alloc /
+ * nrc_ipc_open), read and RED-updated over NVLink by the same kernel.  world = 1: item_shards[0]
+ * is the whole table.  *loss += sum of the triplets' losses. */
+int nrc_mf_bpr_sgd_epoch(float* user_table, float* const* item_shards, int32_t world,
+                         int32_t self_rank, int64_t items_per_shard, int32_t dim,
+                         const int64_t* train_indptr, const int32_t* train_indices,
+                         const int32_t* pos_users, const int32_t* pos_items, int64_t n_pos,
+                         int32_t num_items, int32_t shuffle, uint64_t seed, uint64_t epoch,
+                         int64_t first, int64_t count, float lr, float reg, float* loss,
+                         void* stream);
+
+/* A device allocation of its own (cudaMalloc, never a slice of a caching allocator's block) for a
+ * table shard that other ranks map: *dev_ptr_out and its 64-byte CUDA IPC handle.  Peers open the
+ * handle with nrc_ipc_open(handle, 0, &ptr) -- one handle per shard, so a mapping is never opened
+ * twice in a process -- and close it with nrc_ipc_close(ptr, 0) before the owner frees. */
+int nrc_shard_alloc(int64_t nbytes, void** dev_ptr_out, void* handle64_out);
+int nrc_shard_free(void* dev_ptr);
+
 /* Let kernels of the current device dereference memory of `peer_device` (idempotent). */
 int nrc_enable_peer_access(int32_t peer_device);
 /* CUDA IPC for the shards: export = 64-byte handle of the allocation holding dev_ptr + the offset

@@ -236,6 +236,27 @@ extern "C" int nrc_ipc_close(void* dev_ptr, int64_t offset) {
     return NRC_OK;
 }
 
+extern "C" int nrc_shard_alloc(int64_t nbytes, void** dev_ptr_out, void* handle64_out) {
+    NRC_REQUIRE(nbytes > 0 && dev_ptr_out && handle64_out, NRC_E_VALUE, "bad argument");
+    void* p = nullptr;
+    NRC_CUDA_CHECK(cudaMalloc(&p, (size_t)nbytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        nrc::set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return NRC_E_CUDA;
+    }
+    memcpy(handle64_out, &h, sizeof(h));
+    *dev_ptr_out = p;
+    return NRC_OK;
+}
+
+extern "C" int nrc_shard_free(void* dev_ptr) {
+    if (dev_ptr) NRC_CUDA_CHECK(cudaFree(dev_ptr));
+    return NRC_OK;
+}
+
 extern "C" int nrc_version(void) { return 100; }  // 0.1.0
 
 extern "C" const char* nrc_last_error(void) { return nrc::g_err; }

@@ -8,10 +8,11 @@
 //    adam      m = m*b1 + g*(1-b1); v = v*b2 + (g*g)*(1-b2);     EVERY row: _apply_sparse_shared
 //              var -= (lr_t * m) / (sqrt(v) + eps)               assigns m*b1, v*b2 densely
 //    adagrad   a += g*g; var -= (lr * g) * (1/sqrt(a))           touched rows only
-//    rmsprop   ms += (g*g - ms)*(1-rho); mom = mom*mu + (lr*g)*(1/sqrt(ms+eps)); var -= mom
+//    rmsprop   ms = ms*rho + (g*g)*(1-rho); mom = mom*mu + ((1/sqrt(ms+eps))*lr)*g; var -= mom   (SparseApplyRMSProp)
 //    momentum  a = a*mu + g; var -= a*lr                         touched rows only
 //  Dense gradients (`dense_var == 1`): the Apply* functors
 //    adam      m += (g - m)*(1-b1); v += (g*g - v)*(1-b2); var -= (m*lr_t) / (sqrt(v) + eps)
+//    rmsprop   ms += (g*g - ms)*(1-rho); mom = mom*mu + (lr*g)*(1/sqrt(ms+eps)); var -= mom     (ApplyRMSProp)
 //    others    same formulas as above applied to every element.
 //
 // Every fp32 operation is written with a non-contracting intrinsic so the result is the
@@ -30,49 +31,6 @@ struct OptParams {
     int32_t stamp;
     int64_t total;
 };
-
-__device__ __forceinline__ void opt_update(int kind, int dense_var, bool touched, float h0,
-                                           float h1, float h2, float h3, float& var, float g,
-                                           float& s0, float& s1) {
-    switch (kind) {
-        case NRC_OPT_GD:
-            var = __fsub_rn(var, __fmul_rn(g, h0));
-            break;
-        case NRC_OPT_ADAM: {
-            const float omb1 = __fsub_rn(1.0f, h1), omb2 = __fsub_rn(1.0f, h2);
-            if (dense_var) {
-                s0 = __fadd_rn(s0, __fmul_rn(__fsub_rn(g, s0), omb1));
-                s1 = __fadd_rn(s1, __fmul_rn(__fsub_rn(__fmul_rn(g, g), s1), omb2));
-                var = __fsub_rn(var, __fdiv_rn(__fmul_rn(s0, h0), __fadd_rn(__fsqrt_rn(s1), h3)));
-            } else {
-                s0 = __fadd_rn(__fmul_rn(s0, h1), __fmul_rn(g, omb1));
-                s1 = __fadd_rn(__fmul_rn(s1, h2), __fmul_rn(__fmul_rn(g, g), omb2));
-                var = __fsub_rn(var, __fdiv_rn(__fmul_rn(h0, s0), __fadd_rn(__fsqrt_rn(s1), h3)));
-            }
-            break;
-        }
-        case NRC_OPT_ADAGRAD:
-            if (touched) {
-                s0 = __fadd_rn(s0, __fmul_rn(g, g));
-                var = __fsub_rn(var, __fmul_rn(__fmul_rn(h0, g), __fdiv_rn(1.0f, __fsqrt_rn(s0))));
-            }
-            break;
-        case NRC_OPT_RMSPROP:
-            if (touched) {  // h = {lr, rho, momentum, eps}
-                s0 = __fadd_rn(s0, __fmul_rn(__fsub_rn(__fmul_rn(g, g), s0), __fsub_rn(1.0f, h1)));
-                s1 = __fadd_rn(__fmul_rn(s1, h2),
-                               __fmul_rn(__fmul_rn(h0, g), __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(s0, h3)))));
-                var = __fsub_rn(var, s1);
-            }
-            break;
-        default:  // NRC_OPT_MOMENTUM  h = {lr, momentum}
-            if (touched) {
-                s0 = __fadd_rn(__fmul_rn(s0, h1), g);
-                var = __fsub_rn(var, __fmul_rn(s0, h0));
-            }
-            break;
-    }
-}
 
 __global__ void __launch_bounds__(256) opt_apply_kernel(const OptParams P) {
     const bool has0 = P.kind != NRC_OPT_GD;

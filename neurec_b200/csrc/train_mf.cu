@@ -17,6 +17,7 @@
 //   phase 2  element-wise optimizer over every table of the model in ONE launch; zeroes the
 //            accumulators for the next step.
 #include "common.cuh"
+#include "epoch.cuh"
 #include "optim.cuh"
 
 namespace nrc {
@@ -268,6 +269,117 @@ static int launch_bpr_sgd(const RowShards& SU, const RowShards& SV, int dim, con
     return NRC_OK;
 }
 
+// ----------------------------------------------------------------------------------------
+// The same single-pass step fed straight from the train CSR: positions [first, first + count) of
+// the shuffled epoch (epoch.cuh) are sampled INSIDE the kernel -- no id arrays in HBM, no sampler
+// or shuffle pass in front (data/sampler.py:71-90,189-206 + util/data_iterator.py:59 fused in).
+// A CTA takes 256 consecutive positions at a time:
+//   phase a  one THREAD per triplet: bijection -> (user, positive) -> Philox rejection draw against
+//            the user's sorted row; ~10 dependent loads, 256 chains in flight per CTA;
+//   phase b  one WARP per triplet, two triplets in flight per warp: row gathers (float4 per lane),
+//            shuffle-reduced dots, in-place vector RED.ADD.
+// User rows are always local (the train CSR is sharded by user owner); item rows may
+// live on any rank (RowShards) and are then read / RED-updated over NVLink by the same kernel.
+// ----------------------------------------------------------------------------------------
+template <int VEC>
+__device__ __forceinline__ void ld_vec(const float* p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) {
+        const float4 x = *reinterpret_cast<const float4*>(p);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    } else if constexpr (VEC == 2) {
+        const float2 x = *reinterpret_cast<const float2*>(p);
+        v[0] = x.x; v[1] = x.y;
+    } else {
+        v[0] = *p;
+    }
+}
+
+template <int VEC, bool SHARDED>
+__global__ void __launch_bounds__(256)
+mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const EpochSpec E, int64_t first,
+                         int64_t count, float lr, float reg, float* __restrict__ loss) {
+    constexpr int D = 32 * VEC;
+    constexpr int CH = 256;
+    __shared__ int32_t s_u[CH], s_i[CH], s_j[CH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float loss_acc = 0.0f;
+    for (int64_t c0 = (int64_t)blockIdx.x * CH; c0 < count; c0 += (int64_t)gridDim.x * CH) {
+        const int n = (count - c0 < CH) ? (int)(count - c0) : CH;
+        if ((int)threadIdx.x < n) {
+            int32_t u, i, j;
+            epoch_sample(E, first + c0 + threadIdx.x, 0, u, i, j);
+            s_u[threadIdx.x] = u; s_i[threadIdx.x] = i; s_j[threadIdx.x] = j;
+        }
+        __syncthreads();
+        for (int t0 = warp * 2; t0 < n; t0 += 16) {
+            const bool two = t0 + 1 < n;
+            const int t1 = two ? t0 + 1 : t0;
+            bool ri0, rj0, ri1, rj1;
+            float* pu0 = U_local + (size_t)s_u[t0] * D + lane * VEC;
+            float* pu1 = U_local + (size_t)s_u[t1] * D + lane * VEC;
+            float* qi0 = V.row<SHARDED>(s_i[t0], D, ri0) + lane * VEC;
+            float* qj0 = V.row<SHARDED>(s_j[t0], D, rj0) + lane * VEC;
+            float* qi1 = V.row<SHARDED>(s_i[t1], D, ri1) + lane * VEC;
+            float* qj1 = V.row<SHARDED>(s_j[t1], D, rj1) + lane * VEC;
+            float a0[VEC], b0[VEC], c0v[VEC], a1[VEC], b1[VEC], c1v[VEC];
+            ld_vec<VEC>(pu0, a0); ld_vec<VEC>(qi0, b0); ld_vec<VEC>(qj0, c0v);
+            ld_vec<VEC>(pu1, a1); ld_vec<VEC>(qi1, b1); ld_vec<VEC>(qj1, c1v);
+            float di0 = 0.f, dj0 = 0.f, sq0 = 0.f, di1 = 0.f, dj1 = 0.f, sq1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < VEC; ++t) {
+                di0 = fmaf(a0[t], b0[t], di0); dj0 = fmaf(a0[t], c0v[t], dj0);
+                sq0 += a0[t] * a0[t] + b0[t] * b0[t] + c0v[t] * c0v[t];
+                di1 = fmaf(a1[t], b1[t], di1); dj1 = fmaf(a1[t], c1v[t], dj1);
+                sq1 += a1[t] * a1[t] + b1[t] * b1[t] + c1v[t] * c1v[t];
+            }
+            di0 = warp_sum(di0); dj0 = warp_sum(dj0); di1 = warp_sum(di1); dj1 = warp_sum(dj1);
+            const float x0 = di0 - dj0, x1 = di1 - dj1;
+            float l0 = (x0 >= 0.f) ? log1pf(expf(-x0)) : (-x0 + log1pf(expf(x0)));
+            float l1 = (x1 >= 0.f) ? log1pf(expf(-x1)) : (-x1 + log1pf(expf(x1)));
+            if (reg != 0.0f) { l0 += reg * 0.5f * warp_sum(sq0); l1 += reg * 0.5f * warp_sum(sq1); }
+            const float g0 = -1.0f / (1.0f + expf(x0)), g1 = -1.0f / (1.0f + expf(x1));
+            float du[VEC], dvi[VEC], dvj[VEC];
+#pragma unroll
+            for (int t = 0; t < VEC; ++t) {
+                du[t] = -lr * (g0 * (b0[t] - c0v[t]) + reg * a0[t]);
+                dvi[t] = -lr * (g0 * a0[t] + reg * b0[t]);
+                dvj[t] = -lr * (-g0 * a0[t] + reg * c0v[t]);
+            }
+            red_row<VEC>(pu0, du, false); red_row<VEC>(qi0, dvi, ri0); red_row<VEC>(qj0, dvj, rj0);
+            loss_acc += l0;
+            if (two) {
+#pragma unroll
+                for (int t = 0; t < VEC; ++t) {
+                    du[t] = -lr * (g1 * (b1[t] - c1v[t]) + reg * a1[t]);
+                    dvi[t] = -lr * (g1 * a1[t] + reg * b1[t]);
+                    dvj[t] = -lr * (-g1 * a1[t] + reg * c1v[t]);
+                }
+                red_row<VEC>(pu1, du, false); red_row<VEC>(qi1, dvi, ri1); red_row<VEC>(qj1, dvj, rj1);
+                loss_acc += l1;
+            }
+        }
+        __syncthreads();
+    }
+    if (lane == 0 && loss) atomicAdd(loss, loss_acc);
+}
+
+static int launch_bpr_sgd_stream(float* U_local, const RowShards& SV, int dim, const EpochSpec& E, int64_t first,
+                                 int64_t count, float lr, float reg, float* loss, cudaStream_t st) {
+    int64_t blocks = (count + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const unsigned gb = (unsigned)blocks;
+#define NRC_LAUNCH_STREAM(VEC, SH) \
+    mf_bpr_sgd_stream_kernel<VEC, SH><<<gb, 256, 0, st>>>(U_local, SV, E, first, count, lr, reg, loss)
+    const bool sharded = SV.rows_per_shard != 0;
+    if (dim == 128) { if (sharded) NRC_LAUNCH_STREAM(4, true); else NRC_LAUNCH_STREAM(4, false); }
+    else if (dim == 64) { if (sharded) NRC_LAUNCH_STREAM(2, true); else NRC_LAUNCH_STREAM(2, false); }
+    else { if (sharded) NRC_LAUNCH_STREAM(1, true); else NRC_LAUNCH_STREAM(1, false); }
+#undef NRC_LAUNCH_STREAM
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
 static int grad_grid(int64_t batch) {
     const int wpb = 8;
     int64_t blocks = (batch + wpb - 1) / wpb;
@@ -358,6 +470,42 @@ extern "C" int nrc_mf_bpr_sgd_sharded(float* const* user_shards, float* const* i
     SV.rows_per_shard = (int32_t)items_per_shard;
     SU.self = SV.self = self_rank;
     return launch_bpr_sgd(SU, SV, dim, users, pos_items, neg_items, batch, lr, reg, loss, as_stream(stream));
+}
+
+// Steps of a BPR + SGD epoch straight from the train CSR: positions [first, first + count) of the
+// shuffled epoch `epoch` are sampled, scored and applied by ONE kernel (nrc_epoch_build +
+// nrc_mf_bpr_sgd_fused / _sharded without the id arrays in between).  user_table is THIS rank's
+// row block (pos_users are local row ids: the train CSR is partitioned by user owner); items are
+// global ids, item_shards[r] the row block of rank r (world = 1: the whole table).
+extern "C" int nrc_mf_bpr_sgd_epoch(float* user_table, float* const* item_shards, int32_t world, int32_t self_rank,
+                                    int64_t items_per_shard, int32_t dim, const int64_t* train_indptr,
+                                    const int32_t* train_indices, const int32_t* pos_users, const int32_t* pos_items,
+                                    int64_t n_pos, int32_t num_items, int32_t shuffle, uint64_t seed, uint64_t epoch,
+                                    int64_t first, int64_t count, float lr, float reg, float* loss, void* stream) {
+    NRC_REQUIRE(world >= 1 && world <= 8, NRC_E_LIMIT, "world %d outside [1, 8]", world);
+    NRC_REQUIRE(self_rank >= 0 && self_rank < world, NRC_E_VALUE, "self_rank %d outside [0, %d)", self_rank, world);
+    NRC_REQUIRE(user_table != nullptr && item_shards != nullptr, NRC_E_VALUE, "table pointers are NULL");
+    NRC_REQUIRE(dim == 32 || dim == 64 || dim == 128, NRC_E_LIMIT, "fused SGD supports dim 32, 64, 128 (got %d)", dim);
+    NRC_REQUIRE(world == 1 || (items_per_shard > 0 && items_per_shard * world < (1ll << 31) &&
+                               items_per_shard * world >= num_items),
+                NRC_E_VALUE, "items_per_shard %lld x world %d must cover num_items %d and fit int32",
+                (long long)items_per_shard, world, num_items);
+    EpochSpec E;
+    int rc = epoch_spec_init(E, train_indptr, train_indices, pos_users, pos_items, n_pos, 1, num_items, 1, shuffle, seed,
+                             epoch);
+    if (rc) return rc;
+    NRC_REQUIRE(first >= 0 && count >= 0 && first + count <= n_pos, NRC_E_VALUE,
+                "[first, first + count) = [%lld, %lld) outside the epoch's %lld triplets", (long long)first,
+                (long long)(first + count), (long long)n_pos);
+    if (count == 0) return NRC_OK;
+    RowShards SV{};
+    for (int r = 0; r < world; ++r) {
+        NRC_REQUIRE(item_shards[r] != nullptr, NRC_E_VALUE, "item shard %d is NULL", r);
+        SV.base[r] = item_shards[r];
+    }
+    SV.rows_per_shard = world > 1 ? (int32_t)items_per_shard : 0;
+    SV.self = self_rank;
+    return launch_bpr_sgd_stream(user_table, SV, dim, E, first, count, lr, reg, loss, as_stream(stream));
 }
 
 // Peer mappings are only usable by kernels of this device after peer access is enabled.

@@ -1,22 +1,36 @@
 """PointwiseSampler / PairwiseSampler with the reference's interface (data/sampler.py:93-213)
-on the device sampler.
+on the device epoch (csrc/epoch.cu).
 
 Python-visible behaviour is the reference's: construct once, iterate once per epoch (new
-negatives every ``__iter__``), batches are python lists of length <= batch_size, ``len()`` is the
-number of batches, ``ValueError`` for ``neg_num <= 0``.  Differences, by design:
-  * negatives come from the counter-based Philox kernel (``nrc_sample_negatives``) instead of the
-    serial glibc ``rand()`` loop -- same distribution (uniform over items the user has not
-    interacted with, with replacement, aligned with the flattened positives), different stream;
+negatives and a new order every ``__iter__``), batches are python lists of length <= batch_size,
+``len()`` is the number of batches, ``ValueError`` for ``neg_num <= 0``.  Differences, by design:
+  * negatives come from the counter-based Philox kernel instead of the serial glibc ``rand()``
+    loop -- same distribution (uniform over items the user has not interacted with, with
+    replacement, aligned with the flattened positives), different stream;
+  * the epoch order is a keyed bijection evaluated on the device (``nrc_shuffle_perm`` /
+    ``nrc_epoch_build``) instead of ``np.random.permutation`` + per-sample python gathers
+    (util/data_iterator.py:59,147-152 -- ~70 % of a reference sampler epoch);
   * ``device_epoch()`` hands the whole shuffled epoch to the training kernels as int32 CUDA
-    tensors without ever building python lists (the reference spends ~70 % of a sampler epoch
-    in list gathering).
-Shuffling is ONE ``np.random.permutation(n)`` per epoch, exactly like the reference's
-RandomSampler (util/data_iterator.py:59), so the numpy seed still controls the order.
+    tensors; MF trains straight from ``epoch_args()`` (sampling + shuffling + every step in one
+    persistent launch, ``nrc_mf_epoch_fused``).
+Like the reference's global ``rand()`` / ``np.random`` state, the stream position is process-wide:
+every epoch drawn by ANY sampler takes the next epoch number, so a model that builds a new sampler
+per epoch (MLP.py:100) still sees fresh negatives.
 """
+import itertools
+
 import numpy as np
 import torch
 
 from .. import ops
+
+_EPOCH_COUNTER = itertools.count()      # process-wide stream position (the reference's global RNG state)
+
+
+def reseed(first_epoch=0):
+    """Restart the process-wide epoch numbering (tests; the analogue of re-seeding np.random)."""
+    global _EPOCH_COUNTER
+    _EPOCH_COUNTER = itertools.count(int(first_epoch))
 
 
 class Sampler(object):
@@ -54,7 +68,7 @@ class _NegativeSamplerBase(Sampler):
         self.user_pos_len, self._users_np, self._pos_np = _generate_positive_items(self.user_pos_dict)
         if int(self.user_pos_len[:, 1].max()) >= self.item_num:
             raise ValueError("The number of 'exclusion' is greater than 'high'.")  # pyx:32-33
-        self.seed, self.epoch = int(seed), 0
+        self.seed, self.epoch = int(seed), -1
         self._dev = None
 
     # device-resident train CSR (rows = sorted item lists) and flattened positives
@@ -72,19 +86,25 @@ class _NegativeSamplerBase(Sampler):
             self._dev = {"ptr": t(ptr), "idx": t(idx), "users": t(self._users_np), "pos": t(self._pos_np)}
         return self._dev
 
-    def _sample_negatives(self):
-        """[n_pos, neg_num] int32 CUDA tensor (data/sampler.py:71-90)."""
-        d = self._device_state()
-        neg = ops.sample_negatives(d["ptr"], d["idx"], d["users"], self.neg_num, self.item_num,
-                                   self.seed, self.epoch)
-        self.epoch += 1
-        return neg
+    def _next_epoch(self):
+        self.epoch = next(_EPOCH_COUNTER)
+        return self.epoch
 
-    def _order(self, n):
-        order = np.random.permutation(n) if self.shuffle else np.arange(n)
-        if self.drop_last:
-            order = order[:(n // self.batch_size) * self.batch_size]
-        return torch.from_numpy(order).cuda()
+    def _n_used(self):
+        n = self._n_samples()
+        return (n // self.batch_size) * self.batch_size if self.drop_last else n
+
+    def epoch_args(self):
+        """(train_indptr, train_indices, pos_users, pos_items) device tensors + the scalars
+        nrc_mf_epoch_fused / nrc_epoch_build take; draws the next epoch number."""
+        d = self._device_state()
+        return d, dict(neg_num=self.neg_num, num_items=self.item_num, shuffle=bool(self.shuffle),
+                       drop_last=bool(self.drop_last), seed=self.seed, epoch=self._next_epoch())
+
+    def _device_epoch(self, pairwise):
+        d, a = self.epoch_args()
+        return ops.epoch_build(d["ptr"], d["idx"], d["users"], d["pos"], a["neg_num"], a["num_items"], pairwise,
+                               a["shuffle"], a["seed"], a["epoch"], 0, self._n_used())
 
     def _n_samples(self):
         raise NotImplementedError
@@ -106,12 +126,8 @@ class PairwiseSampler(_NegativeSamplerBase):
 
     def device_epoch(self):
         """Shuffled epoch as CUDA tensors: users [n], pos [n], neg [n] (or [n, neg_num])."""
-        d = self._device_state()
-        neg = self._sample_negatives()
-        order = self._order(len(self._users_np))
-        neg = neg[order]
-        return d["users"][order].contiguous(), d["pos"][order].contiguous(), \
-            (neg[:, 0] if self.neg_num == 1 else neg).contiguous()
+        users, pos, neg = self._device_epoch(True)
+        return users, pos, (neg.view(-1) if self.neg_num == 1 else neg)
 
     def __iter__(self):
         users, pos, neg = (t.cpu().numpy() for t in self.device_epoch())
@@ -135,14 +151,8 @@ class PointwiseSampler(_NegativeSamplerBase):
         return len(self._users_np) * (self.neg_num + 1)
 
     def device_epoch(self):
-        d = self._device_state()
-        neg = self._sample_negatives()                       # [n_pos, neg_num]
-        items = torch.cat([d["pos"], neg.t().reshape(-1)])   # sampler.py:139-141 neg.T flattened
-        users = d["users"].repeat(self.neg_num + 1)
-        if "labels" not in d:
-            d["labels"] = torch.from_numpy(self.all_labels).cuda()
-        order = self._order(self._n_samples())
-        return users[order].contiguous(), items[order].contiguous(), d["labels"][order].contiguous()
+        """Shuffled epoch as CUDA tensors: users [n] i32, items [n] i32, labels [n] f32."""
+        return self._device_epoch(False)
 
     def __iter__(self):
         users, items, labels = (t.cpu().numpy() for t in self.device_epoch())

@@ -66,6 +66,7 @@ class OptimizerState(object):
         self._p1 = np.float32(0.9)
         self._p2 = np.float32(0.999)
         self.stamp = 1
+        self._pows_dev = None
 
     def lr_t(self, steps):
         """fp32 lr*sqrt(1-b2^t)/(1-b1^t) for the next `steps` steps (adam.py::_prepare/_finish)."""
@@ -77,6 +78,15 @@ class OptimizerState(object):
                 self._p1 = np.float32(self._p1 * np.float32(0.9))
                 self._p2 = np.float32(self._p2 * np.float32(0.999))
         return out
+
+    def device_pows(self):
+        """Device copy of TF's beta1_power / beta2_power variables (fp32 [2]); the persistent epoch
+        kernels read and advance it themselves, `lr_t(steps)` advances the host mirror."""
+        if self.kind != "adam":
+            return None
+        if self._pows_dev is None:
+            self._pows_dev = torch.tensor([float(self._p1), float(self._p2)], dtype=torch.float32, device="cuda")
+        return self._pows_dev
 
     def take_stamps(self, steps):
         first = self.stamp

@@ -3,7 +3,8 @@
 Plug-in mirror of the reference's model/general_recommender/MF.py:16-134 (same constructor,
 configuration keys, log lines, predict contract) with the TensorFlow graph replaced by the fused
 sm_100a step: ``build_graph`` allocates the tables / optimizer slots / gradient accumulators in
-HBM, ``train_model`` runs one ``nrc_mf_train_epoch`` per epoch on the sampler's device epoch.
+HBM, ``train_model`` runs ONE persistent launch per epoch (``nrc_mf_epoch_fused``: shuffle +
+negative sampling + every batch of the epoch), reading back only the per-step losses.
 """
 from time import time
 
@@ -55,19 +56,27 @@ class MF(AbstractRecommender):
         self._s0V, self._s1V = self.opt.slots_like(V)
         self._tU = torch.zeros(self.num_users, dtype=torch.int32, device="cuda")
         self._tV = torch.zeros(self.num_items, dtype=torch.int32, device="cuda")
+        self._ws = self._step_loss = None
 
     def _train_epoch(self, data_iter):
-        users, items, third = data_iter.device_epoch()
-        if self.is_pairwise is True and third.dim() != 1:
+        if self.is_pairwise is True and data_iter.neg_num != 1:
             raise ValueError("MF trains on one negative per positive (MF.py:88)")
         steps = len(data_iter)
-        step_loss = torch.empty(max(steps, 1), dtype=torch.float32, device="cuda")
-        ops.mf_train_epoch(self.user_embeddings, self.item_embeddings, users, items, third,
-                           self.batch_size, self.is_pairwise is True, self._loss, self.reg_mf,
-                           self.opt.kind, self.opt.lr_t(steps), self.opt.hyper, self._gU, self._gV,
-                           self._tU, self._tV, self._s0U, self._s1U, self._s0V, self._s1V,
-                           self.opt.take_stamps(steps), step_loss)
-        return float(step_loss[:steps].sum().item())
+        d, a = data_iter.epoch_args()
+        if self._ws is None or self._ws[0].numel() < data_iter._n_samples():
+            n = data_iter._n_samples()
+            mk = lambda: torch.empty(n, dtype=torch.int32, device="cuda")
+            self._ws = (mk(), mk(), mk())
+        if self._step_loss is None or self._step_loss.numel() < steps:
+            self._step_loss = torch.empty(max(steps, 1), dtype=torch.float32, device="cuda")
+        ops.mf_epoch_fused(self.user_embeddings, self.item_embeddings, d["ptr"], d["idx"], d["users"], d["pos"],
+                           a["neg_num"], self.is_pairwise is True, a["shuffle"], a["drop_last"], a["seed"],
+                           a["epoch"], self.batch_size, 0, steps, self._loss, self.reg_mf, self.opt.kind,
+                           self.opt.hyper, self.opt.device_pows(), self._gU, self._gV, self._tU, self._tV,
+                           self._s0U, self._s1U, self._s0V, self._s1V, self.opt.take_stamps(steps),
+                           self._ws[0], self._ws[1], self._ws[2], self._step_loss)
+        self.opt.lr_t(steps)              # keep the host mirror of the beta powers in step
+        return float(self._step_loss[:steps].sum().item())
 
     def train_model(self):
         self.logger.info(self.evaluator.metrics_info())

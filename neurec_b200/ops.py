@@ -237,6 +237,56 @@ def batch_randint_choice(high, out_indptr, total_out, replace=True, excl_indptr=
     return out
 
 
+# ----------------------------------------------------------------------------- device epoch
+def shuffle_perm(n, seed, epoch, shuffle=True, device="cuda"):
+    """RandomSampler's per-epoch order (data_iterator.py:45-63) as a keyed bijection: int64 [n]."""
+    out = torch.empty((int(n),), dtype=torch.int64, device=device)
+    check(_lib.load().nrc_shuffle_perm(int(n), 1 if shuffle else 0, int(seed), int(epoch), _p(out), _stream()))
+    _count()
+    return out
+
+
+def epoch_build(train_indptr, train_indices, pos_users, pos_items, neg_num, num_items, pairwise, shuffle,
+                seed, epoch, first=0, n_out=None):
+    """One epoch of Pairwise/PointwiseSampler as device arrays (nrc_epoch_build): users i32 [n],
+    items i32 [n], third = i32 [n, neg_num] negatives (pairwise) or f32 [n] labels (pointwise)."""
+    _req(train_indptr, torch.int64, "train_indptr"); _req(train_indices, torch.int32, "train_indices")
+    _req(pos_users, torch.int32, "pos_users"); _req(pos_items, torch.int32, "pos_items")
+    if int(neg_num) <= 0:
+        raise ValueError("'neg_num' must be a positive integer.")
+    n_pos = pos_users.numel()
+    n_samples = n_pos if pairwise else n_pos * (int(neg_num) + 1)
+    n_out = n_samples - first if n_out is None else int(n_out)
+    dev = pos_users.device
+    users = torch.empty((n_out,), dtype=torch.int32, device=dev)
+    items = torch.empty((n_out,), dtype=torch.int32, device=dev)
+    third = torch.empty((n_out, int(neg_num)), dtype=torch.int32, device=dev) if pairwise else \
+        torch.empty((n_out,), dtype=torch.float32, device=dev)
+    check(_lib.load().nrc_epoch_build(_p(train_indptr), _p(train_indices), _p(pos_users), _p(pos_items), n_pos,
+                                      int(neg_num), int(num_items), 1 if pairwise else 0, 1 if shuffle else 0,
+                                      int(seed), int(epoch), int(first), n_out, _p(users), _p(items), _p(third),
+                                      _stream()))
+    _count()
+    return users, items, third
+
+
+def mf_epoch_fused(U, V, train_indptr, train_indices, pos_users, pos_items, neg_num, pairwise, shuffle, drop_last,
+                   seed, epoch, batch_size, first_step, num_steps, loss, reg, opt, hyper, adam_pows, gU, gV, tU, tV,
+                   s0U, s1U, s0V, s1V, first_stamp, ws_users, ws_items, ws_third, step_loss):
+    """Steps [first_step, first_step + num_steps) of one MF epoch -- shuffle, negative sampling and
+    every step -- in one persistent cooperative launch (nrc_mf_epoch_fused)."""
+    h = np.zeros(4, dtype=np.float32)
+    h[:len(hyper)] = hyper
+    check(_lib.load().nrc_mf_epoch_fused(
+        _p(U), _p(V), U.shape[0], V.shape[0], U.shape[1], _p(train_indptr), _p(train_indices), _p(pos_users),
+        _p(pos_items), pos_users.numel(), int(neg_num), 1 if pairwise else 0, 1 if shuffle else 0,
+        1 if drop_last else 0, int(seed), int(epoch), int(batch_size), int(first_step), int(num_steps),
+        LOSS_IDS[loss], float(reg), OPT_IDS[opt], h.ctypes.data, _p(adam_pows), _p(gU), _p(gV), _p(tU), _p(tV),
+        _p(s0U), _p(s1U), _p(s0V), _p(s1V), int(first_stamp), _p(ws_users), _p(ws_items), _p(ws_third),
+        _p(step_loss), _stream()))
+    _count()
+
+
 # -------------------------------------------------------------------------------- training
 def mf_pairwise_grad(U, V, users, pos, neg, loss, reg, gU, gV, tU, tV, stamp, loss_out):
     check(_lib.load().nrc_mf_pairwise_grad(_p(U), _p(V), U.shape[1], _p(users), _p(pos), _p(neg),
@@ -263,16 +313,31 @@ def mf_bpr_sgd_fused(U, V, users, pos, neg, lr, reg, loss_out):
 
 def mf_bpr_sgd_sharded(user_shards, item_shards, self_rank, users, pos, neg, lr, reg, loss_out):
     """The single-pass BPR + SGD step on row-sharded tables (nrc_mf_bpr_sgd_sharded): `user_shards`
-    / `item_shards` are lists with one [rows_per_shard, dim] tensor per rank -- this rank's own
-    shard and peer mappings of the others (neurec_b200.util.peer.open_peer_shards); ids are global."""
-    import ctypes
-    w = len(user_shards)
-    assert w == len(item_shards) and w >= 1
-    up = (ctypes.c_void_p * w)(*[t.data_ptr() for t in user_shards])
-    ip = (ctypes.c_void_p * w)(*[t.data_ptr() for t in item_shards])
-    check(_lib.load().nrc_mf_bpr_sgd_sharded(up, ip, w, int(self_rank), user_shards[0].shape[0], item_shards[0].shape[0],
-                                             user_shards[0].shape[1], _p(users), _p(pos), _p(neg), users.numel(),
-                                             float(lr), float(reg), _p(loss_out), _stream()))
+    / `item_shards` are neurec_b200.util.peer.ShardSet objects (this rank's own block and peer
+    mappings of the others); ids are global."""
+    w = user_shards.world
+    assert w == item_shards.world and w >= 1
+    check(_lib.load().nrc_mf_bpr_sgd_sharded(user_shards.ptr_array(), item_shards.ptr_array(), w, int(self_rank),
+                                             user_shards.shape[0], item_shards.shape[0], user_shards.shape[1],
+                                             _p(users), _p(pos), _p(neg), users.numel(), float(lr), float(reg),
+                                             _p(loss_out), _stream()))
+    _count()
+
+
+def mf_bpr_sgd_epoch(user_table, item_shards, train_indptr, train_indices, pos_users, pos_items, num_items, shuffle,
+                     seed, epoch, first, count, lr, reg, loss_out):
+    """Triplets [first, first + count) of a shuffled BPR + SGD epoch straight from the train CSR
+    (nrc_mf_bpr_sgd_epoch): sampling, shuffling, scoring and the in-place update in ONE kernel.
+    `user_table` is this rank's row block (pos_users are local ids), `item_shards` a ShardSet."""
+    _req(user_table, torch.float32, "user_table")
+    _req(train_indptr, torch.int64, "train_indptr"); _req(train_indices, torch.int32, "train_indices")
+    _req(pos_users, torch.int32, "pos_users"); _req(pos_items, torch.int32, "pos_items")
+    check(_lib.load().nrc_mf_bpr_sgd_epoch(_p(user_table), item_shards.ptr_array(), item_shards.world,
+                                           item_shards.rank, item_shards.shape[0], user_table.shape[1],
+                                           _p(train_indptr), _p(train_indices), _p(pos_users), _p(pos_items),
+                                           pos_users.numel(), int(num_items), 1 if shuffle else 0, int(seed),
+                                           int(epoch), int(first), int(count), float(lr), float(reg), _p(loss_out),
+                                           _stream()))
     _count()
 
 

@@ -1,11 +1,19 @@
 """Row-sharded tables across the GPUs of one NVLink domain (BASELINE config 5).
 
 One process per GPU.  A table too large for one GPU is cut into equal row blocks; every rank
-allocates its block and maps the blocks of the other ranks into its address space through CUDA
-IPC (PyTorch's storage-sharing plumbing), so that a kernel can read and `RED` remote rows directly
-over NVLink (`nrc_mf_bpr_sgd_sharded`).  `torch.distributed` is only used to exchange the handles.
+allocates its block and maps the blocks of the other ranks into its own address space, so that a
+kernel can read and `RED` remote rows directly over NVLink (`nrc_mf_bpr_sgd_sharded`,
+`nrc_mf_bpr_sgd_epoch`, the item-sharded evaluator).  `torch.distributed` only exchanges handles.
+
+Two ways to get the mappings (``backend``):
+  "ipc"   every shard is its own cudaMalloc (`nrc_shard_alloc`, never a slice of torch's caching
+          allocator, so a handle is opened at most once per process) exported with CUDA IPC and
+          opened by the peers with their own device current (`nrc_ipc_open`);
+  "symm"  torch.distributed._symmetric_memory (CUDA VMM allocations exchanged as file descriptors),
+          the plumbing NCCL-free collectives in PyTorch use.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -24,59 +32,95 @@ def owner_of(ids, per_shard):
     return np.asarray(ids) // int(per_shard)
 
 
-class PeerShard:
-    """A row block that lives on another rank's GPU, mapped into this process with CUDA IPC
-    (nrc_ipc_open, importing device current).  Only what the kernels need: data_ptr() and shape."""
+class _RawCuda:
+    """Minimal __cuda_array_interface__ carrier so torch can view memory it did not allocate."""
 
-    def __init__(self, ptr, offset, shape, dtype):
-        self._ptr, self._offset, self.shape, self.dtype = ptr, offset, tuple(shape), dtype
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr,
+                                         "version": 2, "strides": None}
 
-    def data_ptr(self):
-        return self._ptr
+
+def _view(ptr, shape, device):
+    return torch.as_tensor(_RawCuda(ptr, shape), device=device)
+
+
+class ShardSet:
+    """One fp32 table cut into `world` row blocks.  `local` is this rank's block as a torch tensor
+    (a view of the shard allocation), `ptrs[r]` the device address of rank r's block in THIS
+    process (own memory for r == rank, a peer mapping otherwise)."""
+
+    def __init__(self, local, ptrs, rank, backend, keep):
+        self.local, self.ptrs, self.rank, self.backend, self._keep = local, list(ptrs), rank, backend, keep
+        self.shape = tuple(local.shape)
+
+    @property
+    def world(self):
+        return len(self.ptrs)
+
+    def peer_view(self, r):
+        """rank r's block as a tensor of this process (reads go over NVLink); debugging / tests."""
+        return self.local if r == self.rank else _view(self.ptrs[r], self.shape, self.local.device)
+
+    def ptr_array(self):
+        return (ctypes.c_void_p * self.world)(*self.ptrs)
 
     def close(self):
-        if self._ptr:
-            _lib.load().nrc_ipc_close(ctypes.c_void_p(self._ptr), self._offset)
-            self._ptr = 0
+        """Unmap the peers' blocks, then (after a barrier: nobody may still be writing) free ours."""
+        if self._keep is None:
+            return
+        keep, self._keep = self._keep, None
+        lib = _lib.load()
+        if self.backend == "ipc":
+            for r, p in enumerate(self.ptrs):
+                if r != self.rank:
+                    lib.nrc_ipc_close(ctypes.c_void_p(p), 0)
+            if dist.is_initialized():
+                dist.barrier()
+            self.local = None
+            lib.nrc_shard_free(ctypes.c_void_p(keep))
+        else:
+            self.local = None
 
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
 
-
-def open_peer_shards(local):
-    """All-gather CUDA IPC handles of `local` (this rank's [rows_per_shard, dim] block, the same
-    shape on every rank) and return one entry per rank: `local` itself at this rank's position,
-    PeerShard mappings elsewhere (opened with THIS rank's device current, so its kernels can read
-    and RED the rows over NVLink).  Keep `local` alive on its owner while any peer uses it.
-
-    Round-1 status: the first version went through torch's storage sharing, which opens the handle
-    with the owner's device current; kernels then faulted on the mapping.  This version has not run
-    on a multi-GPU box yet (tests/mgpu_sharded_check.py is the check)."""
+def alloc_sharded(rows, dim, backend=None):
+    """Allocate this rank's [rows, dim] fp32 block (same shape on every rank) and map everyone
+    else's.  Collective over the default process group."""
+    backend = backend or os.environ.get("NRC_PEER_BACKEND", "ipc")
     ws, rank = dist.get_world_size(), dist.get_rank()
-    assert local.is_cuda and local.is_contiguous()
+    device = torch.device("cuda", torch.cuda.current_device())
     lib = _lib.load()
-    handle = (ctypes.c_ubyte * 64)()
-    offset = ctypes.c_int64(0)
-    _lib.check(lib.nrc_ipc_export(ctypes.c_void_p(local.data_ptr()), handle, ctypes.byref(offset)))
-    info = (bytes(handle), int(offset.value), tuple(local.shape), str(local.dtype), int(local.device.index))
-    gathered = [None] * ws
-    dist.all_gather_object(gathered, info)
-    out = []
-    for r, (hbytes, off, shape, dtype, dev_index) in enumerate(gathered):
-        if r == rank:
-            out.append(local)
-            continue
-        assert tuple(shape) == tuple(local.shape) and dtype == str(local.dtype)
-        _lib.check(lib.nrc_enable_peer_access(dev_index))
-        buf = (ctypes.c_ubyte * 64).from_buffer_copy(hbytes)
+    if backend == "ipc":
+        handle = (ctypes.c_ubyte * 64)()
         ptr = ctypes.c_void_p()
-        _lib.check(lib.nrc_ipc_open(buf, off, ctypes.byref(ptr)))
-        out.append(PeerShard(int(ptr.value), off, shape, local.dtype))
-    dist.barrier()
-    return out
+        _lib.check(lib.nrc_shard_alloc(int(rows) * int(dim) * 4, ctypes.byref(ptr), handle))
+        gathered = [None] * ws
+        dist.all_gather_object(gathered, (bytes(handle), int(device.index)))
+        ptrs = []
+        for r, (hbytes, dev_index) in enumerate(gathered):
+            if r == rank:
+                ptrs.append(int(ptr.value))
+                continue
+            _lib.check(lib.nrc_enable_peer_access(dev_index))
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(hbytes)
+            p = ctypes.c_void_p()
+            _lib.check(lib.nrc_ipc_open(buf, 0, ctypes.byref(p)))
+            ptrs.append(int(p.value))
+        local = _view(ptr.value, (rows, dim), device)
+        dist.barrier()
+        return ShardSet(local, ptrs, rank, "ipc", int(ptr.value))
+    if backend == "symm":
+        import torch.distributed._symmetric_memory as symm_mem
+        local = symm_mem.empty((rows, dim), dtype=torch.float32, device=device)
+        hdl = symm_mem.rendezvous(local, dist.group.WORLD.group_name)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        dist.barrier()
+        return ShardSet(local, ptrs, rank, "symm", hdl)
+    raise ValueError("unknown peer backend %r" % backend)
+
+
+def single(local):
+    """world = 1: the ShardSet of an ordinary tensor (no mapping)."""
+    return ShardSet(local, [local.data_ptr()], 0, "local", None)
 
 
 def route_triplets_to_user_owner(users, pos, neg, users_per_shard):

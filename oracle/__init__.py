@@ -67,7 +67,8 @@ def lib() -> ctypes.CDLL:
     global _LIB
     if _LIB is None:
         path = os.path.join(HERE, "_build", "libneurec_oracle.so")
-        if not os.path.isfile(path):
+        src = os.path.join(HERE, "neurec_oracle.c")
+        if not os.path.isfile(path) or os.path.getmtime(src) > os.path.getmtime(path):
             build(ref=False)
         L = ctypes.CDLL(path)
         L.orc_llrand.restype = ctypes.c_ulonglong
@@ -219,6 +220,34 @@ def philox_sample_negatives(train_indptr, train_indices, users, neg_num, num_ite
                                       ctypes.c_uint64(stream_id), ctypes.c_int64(first_index),
                                       out.ctypes.data_as(_c_i32p))
     return out
+
+
+def shuffle_perm(n, seed, epoch, shuffle=True):
+    """CPU restatement of the product's epoch order (csrc/epoch.cuh): int64 [n] permutation of
+    range(n) -- the stand-in for RandomSampler's np.random.permutation (data_iterator.py:45-63)."""
+    out = np.empty(int(n), dtype=np.int64)
+    lib().orc_feistel_perm(ctypes.c_int64(int(n)), ctypes.c_int(1 if shuffle else 0), ctypes.c_uint64(seed),
+                           ctypes.c_uint64(epoch), out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+    return out
+
+
+def epoch_build(train_indptr, train_indices, pos_users, pos_items, neg_num, num_items, pairwise, shuffle,
+                seed, epoch):
+    """One epoch of Pairwise / PointwiseSampler (data/sampler.py:189-206 / 121-147) in the product's
+    order and with the product's negatives: (users, items, third); third = int32 [n, neg_num]
+    negatives (pairwise) or float32 [n] labels (pointwise, positives then k-major negatives)."""
+    pos_users = np.ascontiguousarray(pos_users, dtype=np.int32)
+    pos_items = np.ascontiguousarray(pos_items, dtype=np.int32)
+    n_pos = len(pos_users)
+    neg = philox_sample_negatives(train_indptr, train_indices, pos_users, neg_num, num_items, seed, epoch)
+    if pairwise:
+        perm = shuffle_perm(n_pos, seed, epoch, shuffle)
+        return pos_users[perm], pos_items[perm], neg[perm]
+    users = np.tile(pos_users, neg_num + 1)
+    items = np.concatenate([pos_items, neg.T.reshape(-1)])
+    labels = np.concatenate([np.ones(n_pos, np.float32), np.zeros(n_pos * neg_num, np.float32)])
+    perm = shuffle_perm(len(users), seed, epoch, shuffle)
+    return users[perm], items[perm], labels[perm]
 
 
 def philox_batch_choice(high, out_indptr, replace=True, exclusion_csr=None, seed=0, stream_id=0):

@@ -165,8 +165,12 @@ def opt_apply(kind, var, g, s0, s1, touched, hyper, dense_var=False):
             s0[rows] = s0[rows] + gg * gg
             var[rows] = var[rows] - (h[0] * gg) * (one / np.sqrt(s0[rows]))
         elif kind == "rmsprop":
-            s0[rows] = s0[rows] + (gg * gg - s0[rows]) * (one - h[1])
-            s1[rows] = s1[rows] * h[2] + (h[0] * gg) * (one / np.sqrt(s0[rows] + h[3]))
+            if dense_var:     # ApplyRMSProp functor (training_ops.cc)
+                s0[rows] = s0[rows] + (gg * gg - s0[rows]) * (one - h[1])
+                s1[rows] = s1[rows] * h[2] + (h[0] * gg) * (one / np.sqrt(s0[rows] + h[3]))
+            else:             # SparseApplyRMSProp: ms*rho + g*g*(1-rho); mom*mu + rsqrt(ms+eps)*lr*g
+                s0[rows] = s0[rows] * h[1] + (gg * gg) * (one - h[1])
+                s1[rows] = s1[rows] * h[2] + ((one / np.sqrt(s0[rows] + h[3])) * h[0]) * gg
             var[rows] = var[rows] - s1[rows]
         elif kind == "momentum":
             s0[rows] = s0[rows] * h[1] + gg

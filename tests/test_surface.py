@@ -117,11 +117,19 @@ def test_samplers_contract(ml100k, golden_sampler):
     assert all(isinstance(x, int) for x in n) and all(nn not in train[uu] for uu, nn in zip(u, n))
     n2 = list(s)[0][2]
     assert n2 != n                                        # fresh negatives every __iter__
-    np.random.seed(5)
-    a = list(PairwiseSampler(ds, batch_size=1000, shuffle=True))[0][0]
-    np.random.seed(5)
-    b = np.repeat(np.arange(ds.num_users), np.diff(ml100k["train_indptr"]))[np.random.permutation(80367)[:1000]]
-    assert a == b.tolist()                                # one np.random.permutation per epoch
+    import oracle
+    sh = PairwiseSampler(ds, batch_size=1000, shuffle=True)
+    a = list(sh)[0][0]
+    flat_users = np.repeat(np.arange(ds.num_users), np.diff(ml100k["train_indptr"]))
+    b = flat_users[oracle.shuffle_perm(80367, sh.seed, sh.epoch)[:1000]]
+    assert a == b.tolist()                                # one keyed permutation per epoch (csrc/epoch.cuh)
+    e0 = sh.epoch
+    a2 = list(sh)[0][0]
+    assert sh.epoch > e0 and a2 != a                      # a new order every __iter__
+    # a NEW sampler continues the process-wide stream (MLP.py:100 builds one per epoch): fresh negatives
+    n_a = list(PairwiseSampler(ds, batch_size=512, shuffle=False))[0][2]
+    n_b = list(PairwiseSampler(ds, batch_size=512, shuffle=False))[0][2]
+    assert n_a != n_b
     s3 = PairwiseSampler(ds, neg_num=3, batch_size=100, shuffle=False, drop_last=True)
     assert len(s3) == 803 and np.asarray(next(iter(s3))[2]).shape == (100, 3)
     pw = PointwiseSampler(ds, neg_num=2, batch_size=7, shuffle=False, drop_last=True)
