@@ -27,13 +27,15 @@ re_metric_dict = {v: k for k, v in metric_dict.items()}
 
 
 def _dict_to_device_csr(d, num_rows):
+    # the reference turns every list into a set (cpp_evaluator.pyx:33-36): duplicates collapse
+    rows = {u: np.unique(np.asarray(list(items), dtype=np.int32)) for u, items in d.items()}
     ptr = np.zeros(num_rows + 1, dtype=np.int64)
-    for u, items in d.items():
-        ptr[u + 1] = len(items)
+    for u, r in rows.items():
+        ptr[u + 1] = len(r)
     ptr = np.cumsum(ptr)
     idx = np.empty(int(ptr[-1]), dtype=np.int32)
-    for u, items in d.items():
-        idx[ptr[u]:ptr[u + 1]] = np.unique(np.asarray(list(items), dtype=np.int32))[:ptr[u + 1] - ptr[u]]
+    for u, r in rows.items():
+        idx[ptr[u]:ptr[u + 1]] = r
     if idx.size == 0:
         idx = np.zeros(1, np.int32)
     return torch.from_numpy(ptr).cuda(), torch.from_numpy(idx).cuda()

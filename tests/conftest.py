@@ -48,6 +48,35 @@ def ml100k():
 
 
 @pytest.fixture(scope="session")
+def gowalla():
+    """dataset/gowalla.{train,test} ('given' split) as loaded by the reference's data.Dataset
+    (tests/golden/make_golden.py gowalla) + what the reference computed on it."""
+    z = np.load(os.path.join(GOLDEN, "gowalla_split.npz"))
+    with open(os.path.join(GOLDEN, "kat_gowalla.json")) as f:
+        kat = json.load(f)
+    return {
+        "num_users": int(z["num_users"]), "num_items": int(z["num_items"]),
+        "train_indptr": z["train_indptr"].astype(np.int64),
+        "train_indices": z["train_indices"].astype(np.int32),
+        "test_indptr": z["test_indptr"].astype(np.int64),
+        "test_indices": z["test_indices"].astype(np.int32),
+        "kat": kat, "adj": dict(np.load(os.path.join(GOLDEN, "kat_gowalla_adj.npz"))),
+    }
+
+
+def gowalla_tables(g):
+    """The tables of make_golden.py::gowalla (RandomState(11); noise + mean of 3 held-out items)."""
+    rng = np.random.RandomState(11)
+    V = (rng.randn(g["num_items"], 64) * .1).astype(np.float32)
+    U = (rng.randn(g["num_users"], 64) * .1).astype(np.float32)
+    tp, ti = g["test_indptr"], g["test_indices"]
+    for u in range(g["num_users"]):
+        if tp[u + 1] > tp[u]:
+            U[u] += V[ti[tp[u]:tp[u + 1]][:3]].mean(0) * np.float32(1.5)
+    return U, V
+
+
+@pytest.fixture(scope="session")
 def golden_ml100k_eval():
     with open(os.path.join(GOLDEN, "kat_ml100k_eval.json")) as f:
         return json.load(f)

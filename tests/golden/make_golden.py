@@ -14,6 +14,11 @@ What is captured (all from the real reference code, imported through oracle.impo
                       (predict = np.matmul, exactly MF.py:120-122), topk=[10,20] and topk=5,
                       plus a user-subset (group) run.
   kat_surface.json    Configurator / DataIterator / sampler / metrics_info surface behaviour.
+  gowalla_split.npz   (``python tests/golden/make_golden.py gowalla``) the 'given' split of
+                      dataset/gowalla.{train,test} as loaded by data.Dataset (BASELINE config 3).
+  kat_gowalla.json / kat_gowalla_adj.npz   LightGCN.create_adj_mat('pre') (LightGCN.py:35-78) on that
+                      split: nnz, row sums, value checksums; ProxyEvaluator strings for random
+                      tables on all 29 858 test users and on a 512-user slice.
 """
 import json
 import os
@@ -188,5 +193,75 @@ def main():
     print("golden fixtures written to", OUT)
 
 
+def gowalla():
+    """BASELINE configs[2]: LightGCN on gowalla with the reference's own loader and adjacency."""
+    import importlib
+    import zlib
+    import oracle
+    cwd = oracle.import_reference()
+    os.chdir(cwd)
+    sys.argv = ["main.py", "--recommender=LightGCN", "--data.input.dataset=gowalla", "--splitter=given",
+                "--data.column.format=UI", "--data.convert.separator=','", "--n_layers=3"]
+    np.random.seed(2018)
+    from util import Configurator
+    from data.dataset import Dataset
+    from evaluator import ProxyEvaluator
+    conf = Configurator("NeuRec.properties", default_section="hyperparameters")
+    ds = Dataset(conf)
+    tr, te = ds.train_matrix.tocsr(), ds.test_matrix.tocsr()
+    tr.sort_indices(); te.sort_indices()
+    assert ds.num_items < 65536
+    np.savez_compressed(os.path.join(OUT, "gowalla_split.npz"), num_users=ds.num_users, num_items=ds.num_items,
+                        train_indptr=tr.indptr.astype(np.int32), train_indices=tr.indices.astype(np.uint16),
+                        test_indptr=te.indptr.astype(np.int32), test_indices=te.indices.astype(np.uint16))
+    m = importlib.import_module("model.general_recommender.LightGCN")
+
+    class _Self:
+        pass
+    f = _Self(); f.dataset = ds; f.n_users = ds.num_users; f.n_items = ds.num_items
+    A = m.LightGCN.create_adj_mat(f, "pre").tocsr()
+    A.sort_indices()
+    np.savez_compressed(os.path.join(OUT, "kat_gowalla_adj.npz"),
+                        rowsum=np.asarray(A.sum(1)).ravel().astype(np.float32),
+                        row_nnz=np.diff(A.indptr).astype(np.int32),
+                        data_head=A.data[:256].astype(np.float32), data_tail=A.data[-256:].astype(np.float32))
+    res = {"num_users": int(ds.num_users), "num_items": int(ds.num_items), "train_nnz": int(tr.nnz),
+           "test_nnz": int(te.nnz), "adj_shape": list(A.shape), "adj_nnz": int(A.nnz), "adj_dtype": str(A.dtype),
+           "adj_sum_f64": float(A.data.astype(np.float64).sum()),
+           "adj_indices_crc32": int(zlib.crc32(A.indices.astype(np.int32).tobytes())),
+           "adj_data_crc32": int(zlib.crc32(A.data.astype(np.float32).tobytes())),
+           "dataset_str": str(ds), "conf_n_layers": conf["n_layers"], "conf_batch_size": conf["batch_size"],
+           "conf_lr": conf["lr"], "conf_reg": conf["reg"], "conf_embed_size": conf["embed_size"],
+           "conf_adj_type": conf["adj_type"]}
+
+    class _Model:
+        def __init__(self, U, V):
+            self.U, self.V = U, V
+
+        def predict(self, user_ids, candidate_items=None):  # MF.py:120-124
+            return np.matmul(self.U[user_ids], self.V.T)
+    rng = np.random.RandomState(11)
+    V = (rng.randn(ds.num_items, 64) * .1).astype(np.float32)
+    train_d, test_d = ds.get_user_train_dict(), ds.get_user_test_dict()
+    # trained-looking user rows: noise + the mean of a few of the user's held-out items, so that the
+    # metric rows are non-trivial (hits at many ranks) -- same recipe in tests/test_gpu_gowalla.py
+    U = (rng.randn(ds.num_users, 64) * .1).astype(np.float32)
+    for u, items in test_d.items():
+        U[u] += V[np.asarray(items[:3])].mean(0) * np.float32(1.5)
+    ev = ProxyEvaluator(train_d, test_d, None, metric=conf["metric"], group_view=None, top_k=conf["topk"],
+                        batch_size=conf["test_batch_size"], num_thread=8)
+    res["info"] = ev.metrics_info()
+    res["eval_all_users"] = ev.evaluate(_Model(U, V))
+    sub = sorted(test_d.keys())[1000:1512]
+    res["subset_users"] = [int(u) for u in sub]
+    res["eval_subset_512"] = ev.evaluator.evaluate(_Model(U, V), sub)
+    with open(os.path.join(OUT, "kat_gowalla.json"), "w") as fo:
+        json.dump(res, fo, indent=1)
+    print("gowalla fixtures written to", OUT)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "gowalla":
+        gowalla()
+    else:
+        main()
