@@ -471,6 +471,13 @@ int nrc_ncf_train_epoch(const nrc_ncf_shape* shape, float* mf_user, float* mf_it
  * Graph propagation: CSR SpMM and the LightGCN step
  * ==================================================================================== */
 
+/* Accumulation order of every SpMM below.  0 (default): fast order -- several non-zeros per load
+ * instruction, FFMA into independent partial sums, long rows split over a CTA; deterministic, within
+ * fp32 re-association (<= 1e-6 relative) of the sequential product.  1: each output row is the
+ * SEQUENTIAL sum over its non-zeros with separately rounded multiply and add, bit-identical to
+ * scipy's csr_matvecs and to TF-1.12's sparse_tensor_dense_matmul CPU kernel (LightGCN.py:140). */
+int nrc_spmm_set_exact(int32_t on);
+
 /* tf.sparse_tensor_dense_matmul(adj_mat, ego_embeddings), LightGCN.py:140 / NGCF.py:176:
  *   y[r, :] = sum over the nnz of row r, in CSR order, of values[p] * x[indices[p], :]
  * with separately rounded multiply and add (sequential, TF/scipy CPU order => bit-exact), then

@@ -153,12 +153,136 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs A) {
     }
 }
 
+// ----------------------------------------------------------------------------------------
+// Default ("fast") SpMM: same product, accumulation order free (north_star's tolerance for this
+// path is NDCG within 1e-5, not a bit-exact SpMM; the sequential kernel above stays available
+// through nrc_spmm_set_exact for bit-level parity tests).
+//   * a gathered row is dim/4 float4 loads, so a warp fetches 32/(dim/4) non-zeros per load
+//     instruction (2 for dim 64, 4 for dim 32, 1 for dim 128) -- half the instructions per nnz;
+//   * FFMA into two independent accumulator sets (no serial FADD chain), groups reduced by shuffle;
+//   * 8 load instructions in flight per warp (16-32 gathered rows);
+//   * rows longer than kLongRow are not left to one warp: the CTA's 8 warps stride over the row's
+//     32-nnz segments and combine through shared memory in fixed order (deterministic).  A CTA
+//     works on units of 8 rows of the caller's (degree-descending) order, so long rows are met by
+//     whole units and the decision is one __syncthreads_or per unit.
+// ----------------------------------------------------------------------------------------
+constexpr int kLongRow = 192;
+
+template <int G>   // lanes per gathered row: dim == 4 * G, G in {8, 16, 32}
+__device__ __forceinline__ void spmm_accumulate(const SpmmArgs& A, int64_t beg, int64_t end, int64_t seg_stride,
+                                                int lane, float4& acc) {
+    constexpr int NPI = 32 / G;            // non-zeros per load instruction
+    constexpr int STEPS = 32 / NPI;        // load instructions per 32-nnz segment
+    constexpr int UN = (STEPS < 8) ? STEPS : 8;
+    const int grp = lane / G, sub = lane % G;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    for (int64_t p = beg; p < end; p += seg_stride) {
+        const int cnt = (int)((end - p < 32) ? (end - p) : 32);
+        const int my_c = (lane < cnt) ? __ldg(A.indices + p + lane) : 0;
+        const float my_v = (lane < cnt) ? __ldg(A.values + p + lane) : 0.0f;   // padding: 0 * row 0
+#pragma unroll 1
+        for (int j0 = 0; j0 * NPI < cnt; j0 += UN) {
+            float4 x[UN];
+            float v[UN];
+#pragma unroll
+            for (int j = 0; j < UN; ++j) {
+                const int src = (j0 + j) * NPI + grp;
+                const int c = __shfl_sync(kFull, my_c, src & 31);
+                v[j] = __shfl_sync(kFull, my_v, src & 31);
+                x[j] = __ldg(reinterpret_cast<const float4*>(A.X + (size_t)c * A.dim) + sub);
+            }
+#pragma unroll
+            for (int j = 0; j < UN; ++j) {
+                float4& a = (j & 1) ? a1 : a0;
+                a.x = fmaf(v[j], x[j].x, a.x); a.y = fmaf(v[j], x[j].y, a.y);
+                a.z = fmaf(v[j], x[j].z, a.z); a.w = fmaf(v[j], x[j].w, a.w);
+            }
+        }
+    }
+    acc.x = a0.x + a1.x; acc.y = a0.y + a1.y; acc.z = a0.z + a1.z; acc.w = a0.w + a1.w;
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) {     // sum the 32/G groups (fixed tree)
+        acc.x += __shfl_xor_sync(kFull, acc.x, o); acc.y += __shfl_xor_sync(kFull, acc.y, o);
+        acc.z += __shfl_xor_sync(kFull, acc.z, o); acc.w += __shfl_xor_sync(kFull, acc.w, o);
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void spmm_epilogue(const SpmmArgs& A, int r, int sub, float4 a) {
+    const size_t o = (size_t)r * A.dim + sub * 4;
+    if (A.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(A.bias + o));
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (A.Y) *reinterpret_cast<float4*>(A.Y + o) = a;
+    if (A.sum) {
+        float4 s = *reinterpret_cast<const float4*>(A.sum + o);
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        if (A.div != 0.0f) { s.x = __fdiv_rn(s.x, A.div); s.y = __fdiv_rn(s.y, A.div); s.z = __fdiv_rn(s.z, A.div); s.w = __fdiv_rn(s.w, A.div); }
+        *reinterpret_cast<float4*>(A.sum + o) = s;
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) spmm_csr_fast_kernel(const SpmmArgs A) {
+    __shared__ float4 s_part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int units = (A.n_rows + 7) >> 3;
+    for (int w = blockIdx.x; w < units; w += gridDim.x) {
+        const int rr = w * 8 + warp;
+        const bool live = rr < A.n_rows;
+        const int r = live ? (A.row_order ? __ldg(A.row_order + rr) : rr) : 0;
+        const int64_t beg = live ? __ldg(A.indptr + r) : 0, end = live ? __ldg(A.indptr + r + 1) : 0;
+        const bool any_long = __syncthreads_or(live && (end - beg) > kLongRow);
+        if (!any_long) {
+            if (live) {
+                float4 acc;
+                spmm_accumulate<G>(A, beg, end, 32, lane, acc);
+                if (lane < G) spmm_epilogue<G>(A, r, lane, acc);
+            }
+            continue;
+        }
+        // a unit with a long row: every row of the unit by the whole CTA, one after the other
+        for (int k = 0; k < 8; ++k) {
+            const int rk = w * 8 + k;
+            if (rk >= A.n_rows) break;
+            const int row = A.row_order ? __ldg(A.row_order + rk) : rk;
+            const int64_t b0 = __ldg(A.indptr + row), e0 = __ldg(A.indptr + row + 1);
+            float4 acc;
+            spmm_accumulate<G>(A, b0 + 32 * warp, e0, 32 * 8, lane, acc);
+            s_part[warp][lane] = acc;
+            __syncthreads();
+            if (warp == 0 && lane < G) {
+                float4 t = s_part[0][lane];
+#pragma unroll
+                for (int q = 1; q < 8; ++q) {
+                    const float4 u = s_part[q][lane];
+                    t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                }
+                spmm_epilogue<G>(A, row, lane, t);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+static bool g_spmm_exact = false;
+
 static int spmm_launch(const SpmmArgs& A, cudaStream_t st) {
     if (A.n_rows <= 0) return NRC_OK;
     NRC_REQUIRE(A.dim > 0 && A.dim <= 256, NRC_E_LIMIT, "dim %d outside [1, 256]", A.dim);
     const int threads = 256;
-    int64_t blocks = ((int64_t)A.n_rows * 32 + threads - 1) / threads;
     const int64_t cap = (int64_t)sm_count() * 8;
+    if (!g_spmm_exact && (A.dim == 32 || A.dim == 64 || A.dim == 128)) {
+        int64_t blocks = ((int64_t)A.n_rows + 7) / 8;
+        if (blocks > cap) blocks = cap;
+        if (A.dim == 32) spmm_csr_fast_kernel<8><<<(unsigned)blocks, threads, 0, st>>>(A);
+        else if (A.dim == 64) spmm_csr_fast_kernel<16><<<(unsigned)blocks, threads, 0, st>>>(A);
+        else spmm_csr_fast_kernel<32><<<(unsigned)blocks, threads, 0, st>>>(A);
+        NRC_CUDA_CHECK(cudaGetLastError());
+        return NRC_OK;
+    }
+    int64_t blocks = ((int64_t)A.n_rows * 32 + threads - 1) / threads;
     if (blocks > cap) blocks = cap;
     if (A.dim == 32) spmm_csr_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(A);
     else if (A.dim == 64) spmm_csr_kernel<2><<<(unsigned)blocks, threads, 0, st>>>(A);
@@ -217,6 +341,13 @@ lightgcn_grad_kernel(const float* __restrict__ E, const float* __restrict__ E0, 
 }  // namespace nrc
 
 using namespace nrc;
+
+// 1: every SpMM of this process uses the sequential, separately-rounded accumulation that is
+// bit-identical to scipy / TF's CPU kernel (parity tests); 0 (default): the fast order.
+extern "C" int nrc_spmm_set_exact(int32_t on) {
+    g_spmm_exact = on != 0;
+    return NRC_OK;
+}
 
 extern "C" int nrc_spmm_csr(const int64_t* indptr, const int32_t* indices, const float* values,
                             const int32_t* row_order, int32_t n_rows, const float* x, int32_t dim,

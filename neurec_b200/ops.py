@@ -376,6 +376,12 @@ def opt_apply_multi(opt, variables, stamp, hyper):
     _count()
 
 
+def spmm_set_exact(on):
+    """True: sequential, separately rounded accumulation (bit-identical to scipy / TF's CPU kernel);
+    False (default): the fast order (nrc_spmm_set_exact)."""
+    check(_lib.load().nrc_spmm_set_exact(1 if on else 0))
+
+
 def spmm_csr(indptr, indices, values, x, row_order=None, bias=None, y=None, sum_=None, div=0.0,
              want_y=True):
     """y = A.x in CSR order (LightGCN.py:140); optional fused epilogue, see nrc_spmm_csr."""

@@ -21,9 +21,18 @@ def degree_order(A):
     return dev(np.argsort(-np.diff(A.indptr), kind="stable").astype(np.int32))
 
 
+@pytest.fixture
+def exact_spmm():
+    """Sequential accumulation order (bit-identical to scipy / TF's CPU kernel) for the test's duration."""
+    from neurec_b200 import ops
+    ops.spmm_set_exact(True)
+    yield
+    ops.spmm_set_exact(False)
+
+
 @pytest.mark.parametrize("dim", [64, 32, 128, 16, 50])
 @pytest.mark.parametrize("adj_type", ["pre", "norm"])
-def test_spmm_bit_exact_vs_scipy(ml100k, dim, adj_type):
+def test_spmm_bit_exact_vs_scipy(ml100k, dim, adj_type, exact_spmm):
     from neurec_b200 import ops
     d = ml100k
     A = tf_math.lightgcn_adj(d["train_indptr"], d["train_indices"], d["num_users"], d["num_items"], adj_type)
@@ -45,7 +54,7 @@ def test_spmm_bit_exact_vs_scipy(ml100k, dim, adj_type):
     assert np.array_equal(dS.cpu().numpy(), ((S + wy).astype(np.float32) / np.float32(4)).astype(np.float32))
 
 
-def test_spmm_empty_rows_and_long_rows():
+def test_spmm_empty_rows_and_long_rows(exact_spmm):
     import scipy.sparse as sp
     from neurec_b200 import ops
     rs = np.random.RandomState(0)
@@ -59,7 +68,7 @@ def test_spmm_empty_rows_and_long_rows():
 
 
 @pytest.mark.parametrize("n_layers", [1, 3])
-def test_lightgcn_propagate_bit_exact(ml100k, n_layers):
+def test_lightgcn_propagate_bit_exact(ml100k, n_layers, exact_spmm):
     from neurec_b200 import ops
     d = ml100k
     A = tf_math.lightgcn_adj(d["train_indptr"], d["train_indices"], d["num_users"], d["num_items"], "pre")
@@ -108,3 +117,48 @@ def test_lightgcn_train_epoch_vs_oracle(ml100k):
                              dev(neg), bs, 1e-3, tf_math.adam_lr_t(0.01, steps), [0.01, 0.9, 0.999, 1e-8],
                              ef, gf, ge, (wa, wb), sl)
     assert np.abs(de0b.cpu().numpy() - tr.e0).max() < 5e-5
+
+
+@pytest.mark.parametrize("dim", [32, 64, 128])
+@pytest.mark.parametrize("adj_type", ["pre", "norm"])
+def test_fast_spmm_matches_scipy_within_reassociation(ml100k, dim, adj_type):
+    """The default accumulation order (several non-zeros per load, FFMA partial sums, long rows split
+    over the CTA): deterministic and within fp32 re-association of the exact product -- also with the
+    fused epilogue, with and without the degree order, and on rows far beyond the long-row threshold."""
+    from neurec_b200 import ops
+    d = ml100k
+    A = tf_math.lightgcn_adj(d["train_indptr"], d["train_indices"], d["num_users"], d["num_items"], adj_type)
+    assert np.diff(A.indptr).max() > 500                 # ml-100k has rows of 580+ non-zeros: the CTA path runs
+    n = A.shape[0]
+    X = (np.random.RandomState(dim).randn(n, dim)).astype(np.float32)
+    want = (A.astype(np.float64) @ X.astype(np.float64))
+    scale = np.abs(A).astype(np.float64) @ np.abs(X).astype(np.float64) + 1e-30
+    ip, ix, va = csr_dev(A)
+    got = ops.spmm_csr(ip, ix, va, dev(X), row_order=degree_order(A)).cpu().numpy()
+    assert (np.abs(got - want) / scale).max() < 4e-7
+    got2 = ops.spmm_csr(ip, ix, va, dev(X), row_order=degree_order(A)).cpu().numpy()
+    assert np.array_equal(got, got2)                     # deterministic
+    got3 = ops.spmm_csr(ip, ix, va, dev(X)).cpu().numpy()    # natural row order: same sums per row
+    assert np.array_equal(got, got3)
+    B = np.random.RandomState(1).randn(n, dim).astype(np.float32)
+    S = np.random.RandomState(2).randn(n, dim).astype(np.float32)
+    dS = dev(S)
+    y = ops.spmm_csr(ip, ix, va, dev(X), bias=dev(B), sum_=dS, div=4.0).cpu().numpy()
+    assert np.abs(y - (B + want)).max() < 1e-5
+    assert np.abs(dS.cpu().numpy() - (S + B + want) / 4.0).max() < 1e-5
+
+
+def test_fast_spmm_empty_rows_tails_and_one_huge_row():
+    import scipy.sparse as sp
+    from neurec_b200 import ops
+    rs = np.random.RandomState(0)
+    n, dim = 700, 64
+    dense = (rs.rand(n, n) < 0.03) * rs.randn(n, n)
+    dense[5] = 0; dense[17] = rs.randn(n); dense[n - 1] = 0; dense[n - 1, 3] = 2.0
+    A = sp.csr_matrix(dense.astype(np.float32)); A.sort_indices()
+    X = rs.randn(n, dim).astype(np.float32)
+    want = A.astype(np.float64) @ X.astype(np.float64)
+    for order in (None, degree_order(A)):
+        got = ops.spmm_csr(*csr_dev(A), dev(X), row_order=order).cpu().numpy()
+        assert np.abs(got - want).max() < 2e-5
+        assert (got[5] == 0).all() and np.allclose(got[n - 1], 2.0 * X[3])
