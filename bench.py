@@ -3,29 +3,35 @@
 
     python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference] [--only]
 
-A "step" is one training batch (one `sess.run((loss, optimizer), feed_dict)` of the reference's
-train_model) through the fused sm_100a kernels.  Rank 0 prints ONE JSON line:
+The hot path is "one training batch" (`sess.run((loss, optimizer), feed_dict)` of the reference's
+train_model) INCLUDING what the reference pays to produce the batch: the per-epoch negative
+sampling (data/sampler.py:71-90), the shuffle (util/data_iterator.py:59) and the batching
+(data_iterator.py:147-152).  Every timed region below starts from the TRAIN CSR: sampling, shuffling
+and the step run inside it, on the device, exactly like the reference arm pays for them on the host.
 
-  value     whole-job samples/s ("triplets/s"; a pointwise sample counts as one triplet,
-            SURVEY.md 8d) with the epoch's id arrays already resident in HBM when the timed
-            region starts (the device sampler ran before it)
-  e2e       the same metric through the reference-facing per-step calls with HOST buffers: per
-            step H2D of the batch ids/labels from pinned memory, the step's kernels, D2H of the
-            loss and a stream sync (the analogue of sess.run returning the loss)
-  eval      users/s of the full-catalogue evaluator (predict + mask + top-K + 5 metrics)
-  roofline  dominant kernel: algorithmic bytes per launch / its CUDA-event launch time (graph
-            replay of that kernel alone) vs the measured HBM copy peak (MEASURED_PEAKS.json)
-  cpu_baseline  the reference's CPU path (oracle/ref_port.py: the real compiled reference
-            pieces from oracle/_ref where they exist + the numpy restatement of the TF-1.12
-            step) timed on this box's host cores on a bounded sample
-  others    (N=1, unless --only) the same measurements for the other single-GPU configs
+Workloads (BASELINE.json configs):
+  bprmf-sharded   (default, configs[4]) BPRMF, learner=gd, tables ROW-SHARDED over the ranks, one
+                  CSR-fed kernel per step (sampler + shuffle + gather + score + loss + in-place
+                  update; remote item rows read / RED-updated over NVLink).  Weak scaling: per GPU
+                  6.25 M users x 12.5 M items x d=128 (9.6 GB) and 2^20 triplets per step; at N=1
+                  it is the same kernel on the local shard = the largest single-GPU configuration.
+  bprmf-ml100k    (configs[0]) BPRMF on ml-100k: ONE persistent launch per epoch.
+  neumf-ml100k    (configs[1]) NeuMF on ml-100k.
+  lightgcn-gowalla (configs[2]) LightGCN on the REAL gowalla split (tests/golden/gowalla_split.npz).
+  eval-synth      (configs[3]) full-catalogue evaluator, 10 M items x d=128, tensor cores.
+At N=1 the default run also measures the other workloads into `others` (unless --only).
 
-Workloads (BASELINE.json configs): neumf-ml100k (configs[1], default), bprmf-ml100k
-(configs[0]), lightgcn-gowalla (configs[2], synthetic gowalla-shaped graph).
-
-Multi-GPU: training of these table sizes does not shard (2-20 MB models with microsecond
-steps; DESIGN.md "replicas only"), so --gpus N runs N independent replicas (weak scaling); the
-evaluator shards users across ranks and all-gathers the per-user rows.
+Rank 0 prints ONE JSON line:
+  value     whole-job triplets/s (a pointwise sample counts as one triplet), train
+            CSR resident in HBM when the timed region starts
+  e2e       the same through the public per-epoch call with HOST buffers: the train interactions
+            (CSR + flattened positives) are copied from pinned host memory inside the timed region
+            and every step's loss is copied back (h2d / d2h bytes per step are counted)
+  roofline  dominant kernel: algorithmic bytes / CUDA-event launch time vs the
+            measured HBM copy peak (MEASURED_PEAKS.json); tensor pipe for eval-synth
+  cpu_baseline  the reference's CPU path on this box (oracle/ref_port.py: the reference's real
+            compiled sampler + python batching; oracle/torch_port.py: multi-threaded torch-CPU
+            restatement of the TF-1.12 step) on a bounded sample
 """
 from __future__ import annotations
 
@@ -42,51 +48,32 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = ("neumf-ml100k", "bprmf-ml100k", "lightgcn-gowalla")
-DEFAULT_WORKLOAD = "neumf-ml100k"
+WORKLOADS = ("bprmf-sharded", "bprmf-ml100k", "neumf-ml100k", "lightgcn-gowalla", "eval-synth")
+DEFAULT_WORKLOAD = "bprmf-sharded"
 METRICS = ["Precision", "Recall", "NDCG", "MAP", "MRR"]
+SEED = 2018
 
 
 # ----------------------------------------------------------------------------------------
 # helpers
 # ----------------------------------------------------------------------------------------
-def load_ml100k():
-    z = np.load(os.path.join(ROOT, "tests", "golden", "ml100k_split.npz"))
-    return {"name": "ml-100k", "num_users": int(z["num_users"]), "num_items": int(z["num_items"]),
+def _load_split(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + "_split.npz"))
+    return {"name": name, "num_users": int(z["num_users"]), "num_items": int(z["num_items"]),
             "train_indptr": z["train_indptr"].astype(np.int64),
             "train_indices": z["train_indices"].astype(np.int32),
             "test_indptr": z["test_indptr"].astype(np.int64),
             "test_indices": z["test_indices"].astype(np.int32)}
 
 
-def synth_gowalla(seed=7):
-    """Synthetic graph with gowalla's shape (U=29 858, I=40 981, ~810 k train and
-    ~217 k test interactions, power-law item popularity, user degrees 8..~800)."""
-    rs = np.random.RandomState(seed)
-    nu, ni = 29858, 40981
-    deg = np.clip((8 + rs.pareto(1.35, nu) * 9).astype(np.int64), 8, 811)
-    deg = (deg * (810128 / deg.sum())).astype(np.int64).clip(6, 811)
-    pop = 1.0 / np.power(np.arange(1, ni + 1) + 50.0, 0.75)   # head capped like gowalla (max item degree ~1.4 k)
-    pop = pop[rs.permutation(ni)]
-    pop /= pop.sum()
-    tot = int((deg * 1.45).sum())
-    draws = rs.choice(ni, size=tot, p=pop).astype(np.int32)
-    off = np.concatenate([[0], np.cumsum((deg * 1.45).astype(np.int64))])
-    tr_rows, te_rows = [], []
-    for u in range(nu):
-        it = np.unique(draws[off[u]:off[u + 1]])
-        rs.shuffle(it)
-        k = max(1, int(round(len(it) * 0.79)))
-        tr_rows.append(np.sort(it[:k])); te_rows.append(np.sort(it[k:]) if len(it) > k else np.sort(it[:1]))
+def load_ml100k():
+    d = _load_split("ml100k")
+    d["name"] = "ml-100k"
+    return d
 
-    def csr(rows):
-        ptr = np.zeros(nu + 1, np.int64)
-        ptr[1:] = np.cumsum([len(r) for r in rows])
-        return ptr, np.concatenate(rows).astype(np.int32)
-    tp, ti = csr(tr_rows)
-    sp_, si = csr(te_rows)
-    return {"name": "gowalla-shaped synthetic", "num_users": nu, "num_items": ni, "train_indptr": tp,
-            "train_indices": ti, "test_indptr": sp_, "test_indices": si}
+
+def load_gowalla():
+    return _load_split("gowalla")
 
 
 def profiled_traffic(kernel):
@@ -240,310 +227,228 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(p)) if os.path.isfile(p) else {}
+
+
+def pin(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+
+class TrainData:
+    """The train interactions a sampler is built from (data/sampler.py:24-39): CSR + flattened
+    positives, as pinned host arrays and as device arrays."""
+
+    def __init__(self, indptr, indices, users=None):
+        import torch
+        if users is None:
+            users = np.repeat(np.arange(len(indptr) - 1, dtype=np.int32), np.diff(indptr))
+        self.host = [pin(np.asarray(indptr, np.int64)), pin(np.asarray(indices, np.int32)), pin(np.asarray(users, np.int32))]
+        self.dev = [torch.empty_like(h, device="cuda") for h in self.host]
+        self.nbytes = sum(h.numel() * h.element_size() for h in self.host)
+        self.n_pos = int(self.host[1].numel())
+        self.upload()
+
+    def upload(self):
+        """H2D of the train interactions from pinned memory on the current stream (the e2e leg)."""
+        for h, t in zip(self.host, self.dev):
+            t.copy_(h, non_blocking=True)
+
+    @property
+    def ptr(self): return self.dev[0]
+    @property
+    def idx(self): return self.dev[1]
+    @property
+    def users(self): return self.dev[2]
+
+
+def timed(fn, world, windows, flush=True):
+    """Barrier + sync, CUDA events around fn() on the current stream, barrier + sync; max over ranks.
+    Returns (ms, fn's return value)."""
+    import torch
+    barrier(world)
+    if flush:
+        flush_l2(); barrier(world)
+    wall0 = time.perf_counter()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out = fn()
+    b.record()
+    barrier(world)
+    windows.append((wall0, time.perf_counter()))
+    return max_over_ranks(a.elapsed_time(b), world), out
+
+
+def adam_lr_schedule(lr, n):
+    out = np.empty(n, np.float32)
+    p1, p2, one, lr = np.float32(0.9), np.float32(0.999), np.float32(1), np.float32(lr)
+    for s in range(n):
+        out[s] = lr * np.sqrt(one - p2) / (one - p1)
+        p1 = np.float32(p1 * np.float32(0.9)); p2 = np.float32(p2 * np.float32(0.999))
+    return out
+
+
+def hbm_roofline(kernel, nbytes, seconds, note, timing, extra=None):
+    pk = peaks()
+    peak = float(pk.get("hbm_gbs", 6650.0))
+    src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in pk else "fallback (B200_PROFILING.md 6.65 TB/s)"
+    ach = nbytes / seconds / 1e9
+    r = {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+         "traffic": profiled_traffic(kernel), "peak_source": src, "bytes_per_launch": nbytes,
+         "launch_us": seconds * 1e6, "bytes_note": note, "timing": timing}
+    if extra:
+        r.update(extra)
+    return r
+
+
+def run_cpu_epoch_steps(sampler, step, n_steps):
+    """The reference's train_model loop on the host: for batch in data_iter: step(batch)."""
+    done, t0 = 0, time.perf_counter()
+    while done < n_steps:
+        for batch in sampler:                       # pays the epoch's negative sampling + shuffle + batching
+            step(*batch)
+            done += 1
+            if done >= n_steps:
+                break
+    return time.perf_counter() - t0
+
+
+def eval_users_per_s(U, V, data, world, rank, windows, k=20, reps=3):
+    """Full-catalogue evaluation (predict + mask + top-K + 5 metrics), users sharded over ranks."""
+    import torch
+    from neurec_b200 import ops
+    from neurec_b200.evaluator import sharded
+    d = data
+    tp, ti, sp, si = dev(d["train_indptr"]), dev(d["train_indices"]), dev(d["test_indptr"]), dev(d["test_indices"])
+    a_, b_ = sharded.local_slice(d["num_users"], rank, world)
+    mine = torch.arange(a_, b_, dtype=torch.int32, device="cuda")
+    once = lambda: ops.mean_rows(ops.eval_mf_auto(U, V, mine, tp, ti, sp, si, METRICS, k))
+    once()
+
+    def go():
+        for _ in range(reps):
+            r = once()
+        return r
+    ms, res = timed(go, world, windows)
+    ms /= reps
+    return {"metric": "eval users/sec", "value": d["num_users"] / (ms * 1e-3), "unit": "users/s",
+            "users": d["num_users"], "items": d["num_items"], "top_k": k, "metrics": 5, "ms": ms,
+            "ndcg_at_10": float(res.view(5, k)[2, 9]), "sharding": "users over %d rank(s)" % world}
+
+
+def cpu_eval(data, U, V, threads, max_users=None, k=20):
+    from oracle import ref_port
+    train_dict = ref_port.user_dict(data["train_indptr"], data["train_indices"])
+    test_dict = ref_port.user_dict(data["test_indptr"], data["test_indices"])
+    if max_users is not None and len(test_dict) > max_users:
+        test_dict = {u: test_dict[u] for u in list(test_dict.keys())[:max_users]}
+    best = None
+    for th in sorted({8, min(threads, 32)}):         # reference default num_thread=8 vs more threads
+        t0 = time.perf_counter()
+        _, _, impl = ref_port.evaluate(U, V, train_dict, test_dict, [1, 2, 4, 3, 5], k, 128, th)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, th, impl)
+    return {"value": len(test_dict) / best[0], "unit": "users/s", "kind": "reference" if best[2] == "reference" else "port",
+            "threads": best[1], "sample": "%d users: np.matmul predict + python mask loop + evaluate.h top-K/metrics, "
+                                          "test_batch_size 128" % len(test_dict)}
+
+
 # ----------------------------------------------------------------------------------------
-# workloads
+# configs[0]: BPRMF on ml-100k -- one persistent launch per epoch
 # ----------------------------------------------------------------------------------------
-class Workload:
-    """Common plumbing: data, device sampler/shuffle, e2e staging, evaluator, CPU reference."""
-    pairwise = True
-    neg_num = 1
-    eval_k = 20
-
-    def __init__(self, data, rank):
-        self.d, self.rank = data, rank
-        d = data
-        self.users_of_pos = np.repeat(np.arange(d["num_users"], dtype=np.int32), np.diff(d["train_indptr"]))
-        self.n_pos = len(self.users_of_pos)
-        self.n_samples = self.n_pos * (1 if self.pairwise else self.neg_num + 1)
-        self.steps_per_epoch = (self.n_samples + self.batch - 1) // self.batch
-
-    def setup_common(self):
-        import torch
-        d = self.d
-        self.tp, self.ti = dev(d["train_indptr"]), dev(d["train_indices"])
-        self.sp, self.si = dev(d["test_indptr"]), dev(d["test_indices"])
-        self.d_users_of_pos = dev(self.users_of_pos)
-        self.staging = torch.empty(3 * self.batch + 4, dtype=torch.int32, device="cuda")
-        self.loss_pin = torch.zeros(4, dtype=torch.float32).pin_memory()
-        self.lr_sched = self._lr_schedule(1 << 17)
-        self.t = 0
-        self.stamp = 1
-
-    def _lr_schedule(self, n):
-        out = np.empty(n, np.float32)
-        p1, p2, one, lr = np.float32(0.9), np.float32(0.999), np.float32(1), np.float32(self.lr)
-        for s in range(n):
-            out[s] = lr * np.sqrt(one - p2) / (one - p1)
-            p1 = np.float32(p1 * np.float32(0.9)); p2 = np.float32(p2 * np.float32(0.999))
-        return out
-
-    def epoch_arrays(self, n_steps, epoch=0):
-        """Device sampler + shuffle for n_steps batches (wraps over epochs if needed)."""
-        import torch
-        from neurec_b200 import ops
-        need = n_steps * self.batch
-        us, its, th = [], [], []
-        e = 0
-        while need > 0:
-            neg = ops.sample_negatives(self.tp, self.ti, self.d_users_of_pos, self.neg_num,
-                                       self.d["num_items"], 2018, epoch + e)
-            if self.pairwise:
-                u, i, t = self.d_users_of_pos, self.ti, neg[:, 0]
-            else:
-                u = self.d_users_of_pos.repeat(self.neg_num + 1)
-                i = torch.cat([self.ti, neg.t().reshape(-1)])
-                t = torch.cat([torch.ones(self.n_pos, device="cuda"),
-                               torch.zeros(self.n_pos * self.neg_num, device="cuda")])
-            perm = torch.randperm(u.numel(), device="cuda")[:min(need, u.numel())]
-            us.append(u[perm]); its.append(i[perm]); th.append(t[perm])
-            need -= perm.numel(); e += 1
-        cat = lambda xs: torch.cat(xs).contiguous()
-        return cat(us), cat(its), cat(th)
-
-    def stage(self, h_arrays, off):
-        """H2D of one batch of (users, items, third) from pinned host memory."""
-        from neurec_b200 import _lib
-        import torch
-        lib = _lib.load()
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        p = [ctypes.c_void_p(h.data_ptr() + 4 * off) for h in h_arrays]
-        _lib.check(lib.nrc_stage_batch_host(p[0], p[1], p[2], self.batch, ctypes.c_void_p(self.staging.data_ptr()), st))
-        b = self.batch
-        import torch as T
-        third = self.staging[2 * b:3 * b]
-        if not self.pairwise:
-            third = third.view(T.float32)
-        return self.staging[:b], self.staging[b:2 * b], third
-
-    def fetch(self, dev_tensor, count):
-        from neurec_b200 import _lib
-        import torch
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(_lib.load().nrc_fetch_host(ctypes.c_void_p(dev_tensor.data_ptr()),
-                                              ctypes.c_void_p(self.loss_pin.data_ptr()), count, st))
-        return float(self.loss_pin[0])
-
-    RING = 16
-
-    def _capture_step(self, lib, r, copy_in, main, copy_out):
-        """Issue step r of the ring into the current capture: H2D on `copy_in`, kernels on `main`,
-        loss D2H on `copy_out` (the three may be the same stream)."""
-        import torch
-        from neurec_b200 import _lib
-        vp = ctypes.c_void_p
-        b = self.batch
-        stag = self.stag_ring[r]
-        _lib.check(lib.nrc_graph_stage_async(vp(self.pins[r].data_ptr()), vp(stag.data_ptr()), (3 * b + 1) * 4,
-                                             vp(copy_in.cuda_stream)))
-        if copy_in is not main:
-            _lib.check(lib.nrc_graph_depend(vp(copy_in.cuda_stream), vp(main.cuda_stream)))
-        _lib.check(lib.nrc_opt_set_lr_source(vp(stag.data_ptr() + 12 * b)))
-        third = stag[2 * b:3 * b]
-        if not self.pairwise:
-            third = third.view(torch.float32)
-        t_keep, loss_keep = self.t, self.step_loss
-        self.step_loss = self.loss_ring[r]
-        with torch.cuda.stream(main):
-            self.step_on_staged(stag[:b], stag[b:2 * b], third)
-        self.t, self.step_loss = t_keep, loss_keep
-        _lib.check(lib.nrc_opt_set_lr_source(None))
-        if copy_out is not main:
-            _lib.check(lib.nrc_graph_depend(vp(main.cuda_stream), vp(copy_out.cuda_stream)))
-        _lib.check(lib.nrc_graph_fetch_async(vp(self.loss_ring[r].data_ptr()), vp(self.loss_pins[r].data_ptr()),
-                                             self.loss_count, vp(copy_out.cuda_stream)))
-
-    def build_step_graph(self):
-        """Captured training steps for the host-facing path.  Per ring slot r: a pinned block, a device
-        staging block, a device + pinned loss slot and a single-step graph (H2D, the step's kernels,
-        loss D2H).  Plus ONE burst graph of RING consecutive steps whose H2D chain and loss-D2H chain
-        are captured on two side streams: inside a burst the copy of step s+1 overlaps the kernels of
-        step s (nrc_graph_run_steps)."""
-        import torch
-        from neurec_b200 import _lib
-        lib = _lib.load()
-        b, R = self.batch, self.RING
-        self.e2e_stream = torch.cuda.Stream()
-        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-        self.pins = [torch.zeros(3 * b + 4, dtype=torch.int32).pin_memory() for _ in range(R)]
-        self.loss_pins = [torch.zeros(max(self.loss_count, 1)).pin_memory() for _ in range(R)]
-        self.stag_ring = torch.zeros((R, 3 * b + 4), dtype=torch.int32, device="cuda")
-        self.loss_ring = torch.zeros((R, 16), device="cuda")
-        self.graphs = []
-        torch.cuda.synchronize()
-        vp = ctypes.c_void_p
-        main = self.e2e_stream
-        st = vp(main.cuda_stream)
-        for r in range(R):
-            g = ctypes.c_void_p()
-            _lib.check(lib.nrc_graph_capture_begin(st))
-            self._capture_step(lib, r, main, main, main)
-            _lib.check(lib.nrc_graph_capture_end(st, ctypes.byref(g)))
-            self.graphs.append(g)
-        self.burst = ctypes.c_void_p()
-        _lib.check(lib.nrc_graph_capture_begin(st))
-        _lib.check(lib.nrc_graph_depend(st, vp(s_in.cuda_stream)))        # fork: both side streams join the capture
-        _lib.check(lib.nrc_graph_depend(st, vp(s_out.cuda_stream)))
-        for r in range(R):
-            self._capture_step(lib, r, s_in, main, s_out)
-        _lib.check(lib.nrc_graph_depend(vp(s_in.cuda_stream), st))        # join
-        _lib.check(lib.nrc_graph_depend(vp(s_out.cuda_stream), st))
-        _lib.check(lib.nrc_graph_capture_end(st, ctypes.byref(self.burst)))
-        self.graph, self.pin, self.loss_pin = self.graphs[0], self.pins[0], self.loss_pins[0]
-        self.c_graphs = (ctypes.c_void_p * R)(*[g.value for g in self.graphs])
-        self.c_pins = (ctypes.c_void_p * R)(*[p.data_ptr() for p in self.pins])
-        self.c_loss = (ctypes.c_void_p * R)(*[p.data_ptr() for p in self.loss_pins])
-        torch.cuda.synchronize()
-
-    def run_steps_e2e(self, h_arrays, n_steps):
-        """Steps from HOST arrays: the host stages RING batches into the pinned ring and launches the
-        burst graph (per step: H2D node, the step's kernels, loss D2H node; copies of step s+1 overlap
-        the kernels of step s), waits, reads the RING losses; leftover steps use the single-step graphs."""
-        from neurec_b200 import _lib
-        lib = _lib.load()
-        if not hasattr(self, "graphs"):
-            self.build_step_graph()
-        st = ctypes.c_void_p(self.e2e_stream.cuda_stream)
-        lr = np.ascontiguousarray(self.lr_sched[self.t:self.t + n_steps], dtype=np.float32)
-        total = ctypes.c_double(0.0)
-        vp = ctypes.c_void_p
-        _lib.check(lib.nrc_graph_run_steps(self.burst, self.c_graphs, self.RING, vp(h_arrays[0].data_ptr()),
-                                           vp(h_arrays[1].data_ptr()), vp(h_arrays[2].data_ptr()), self.batch,
-                                           lr.ctypes.data_as(ctypes.c_void_p), n_steps, self.c_pins, self.c_loss,
-                                           self.loss_count, ctypes.byref(total), st))
-        self.t += n_steps
-        return total.value, 3 * 4 * self.batch + 4, 4 * self.loss_count
-
-    def run_steps_e2e_sync(self, h_arrays, n_steps):
-        """The strictly synchronous variant (what `sess.run` per batch does): stage, launch, wait for
-        the loss, every step."""
-        from neurec_b200 import _lib
-        lib = _lib.load()
-        if not hasattr(self, "graphs"):
-            self.build_step_graph()
-        st = ctypes.c_void_p(self.e2e_stream.cuda_stream)
-        pin = ctypes.c_void_p(self.pin.data_ptr())
-        ptrs = [h.data_ptr() for h in h_arrays]
-        loss_np = self.loss_pin.numpy()
-        total, b = 0.0, self.batch
-        for s in range(n_steps):
-            o = 4 * s * b
-            rc = lib.nrc_graph_step(self.graph, ctypes.c_void_p(ptrs[0] + o), ctypes.c_void_p(ptrs[1] + o),
-                                    ctypes.c_void_p(ptrs[2] + o), b, float(self.lr_sched[self.t]), pin, st)
-            if rc:
-                _lib.check(rc)
-            self.t += 1
-            total += float(loss_np[0])
-        return total, 3 * 4 * self.batch + 4, 4 * self.loss_count
-
-    def cpu_eval(self, threads, U, V, max_users=None):
-        from oracle import ref_port
-        d = self.d
-        train_dict = ref_port.user_dict(d["train_indptr"], d["train_indices"])
-        test_dict = ref_port.user_dict(d["test_indptr"], d["test_indices"])
-        if max_users is not None and len(test_dict) > max_users:
-            keys = list(test_dict.keys())[:max_users]
-            test_dict = {k: test_dict[k] for k in keys}
-        best = None
-        for th in sorted({8, min(threads, 32)}):     # reference default num_thread=8 vs more threads
-            t0 = time.perf_counter()
-            _, parts, impl = ref_port.evaluate(U, V, train_dict, test_dict, [1, 2, 4, 3, 5], self.eval_k, 128, th)
-            dt = time.perf_counter() - t0
-            if best is None or dt < best[0]:
-                best = (dt, th, parts, impl)
-        return best[0], len(test_dict), best[3], best[1]
-
-
-class BprmfMl100k(Workload):
+class MfMl100k:
     name = "bprmf-ml100k"
-    describe = "BPRMF on ml-100k, dim=64, conf/MF.properties (bs 512, adam 1e-3, bpr, reg 0)"
+    describe = ("BPRMF on ml-100k, dim=64, conf/MF.properties (bs 512, adam 1e-3, bpr, reg 0): shuffle + negative "
+                "sampling + the 157 steps of an epoch in ONE persistent cooperative launch")
     dim, batch, lr, reg, loss, opt = 64, 512, 1e-3, 0.0, "bpr", "adam"
-    hyper = [1e-3, 0.9, 0.999, 1e-8]
-    loss_count = 1
-    launches_per_step = 2
+    pairwise, neg_num = True, 1
 
-    def __init__(self, rank=0):
-        super().__init__(load_ml100k(), rank)
+    def __init__(self, rank):
+        self.d = load_ml100k()
         rs = np.random.RandomState(2017 + rank)
         self.U0 = (rs.randn(self.d["num_users"], self.dim) * 0.01).astype(np.float32)
         self.V0 = (rs.randn(self.d["num_items"], self.dim) * 0.01).astype(np.float32)
+        self.n = len(self.d["train_indices"]) * (1 if self.pairwise else self.neg_num + 1)
+        self.spe = (self.n + self.batch - 1) // self.batch
 
-    def setup_device(self):
+    def setup(self):
         import torch
-        self.setup_common()
-        self.dU, self.dV = dev(self.U0), dev(self.V0)
+        d = self.d
+        self.T = TrainData(d["train_indptr"], d["train_indices"])
+        self.U, self.V = dev(self.U0), dev(self.V0)
         z = torch.zeros_like
-        self.gU, self.gV = z(self.dU), z(self.dV)
-        self.mU, self.vU, self.mV, self.vV = z(self.dU), z(self.dU), z(self.dV), z(self.dV)
-        self.tU = torch.zeros(self.d["num_users"], dtype=torch.int32, device="cuda")
-        self.tV = torch.zeros(self.d["num_items"], dtype=torch.int32, device="cuda")
-        self.step_loss = torch.zeros(1 << 16, device="cuda")
+        self.gU, self.gV, self.mU, self.vU, self.mV, self.vV = z(self.U), z(self.V), z(self.U), z(self.U), z(self.V), z(self.V)
+        self.tU = torch.zeros(d["num_users"], dtype=torch.int32, device="cuda")
+        self.tV = torch.zeros(d["num_items"], dtype=torch.int32, device="cuda")
+        self.ws = [torch.empty(self.n, dtype=torch.int32, device="cuda") for _ in range(3)]
+        self.step_loss = torch.zeros(self.spe, device="cuda")
+        self.loss_pin = torch.zeros(self.spe).pin_memory()
+        self.pows = torch.tensor([0.9, 0.999], device="cuda")
+        self.epoch, self.stamp, self.launches = 0, 1, 0
 
-    def run_steps_device(self, arrays, n_steps):
-        from neurec_b200 import ops
-        u, i, t = arrays
-        n = min(u.numel(), n_steps * self.batch)
-        ops.mf_train_epoch(self.dU, self.dV, u[:n], i[:n], t[:n], self.batch, True, self.loss, self.reg,
-                           self.opt, self.lr_sched[self.t:self.t + n_steps], self.hyper, self.gU, self.gV,
-                           self.tU, self.tV, self.mU, self.vU, self.mV, self.vV, self.stamp, self.step_loss)
-        self.stamp += n_steps; self.t += n_steps
-        return self.launches_per_step * n_steps
-
-    def step_on_staged(self, u, i, t):
-        self.run_steps_device((u, i, t), 1)
-        return self.step_loss
-
-    def eval_tables(self):
-        return self.dU, self.dV
-
-    def kernels(self, arrays):
-        from neurec_b200 import ops
+    def run_steps(self, k, e2e=False):
+        """k consecutive steps: whole epochs, then a partial one.  e2e: the train interactions are
+        uploaded from pinned host memory and the step losses read back, per epoch call."""
         import torch
-        u, i, t = (a[:self.batch] for a in arrays)
-        loss = torch.zeros(1, device="cuda")
-        hyper = list(self.hyper)
-        grad = lambda: ops.mf_pairwise_grad(self.dU, self.dV, u, i, t, self.loss, self.reg, self.gU, self.gV,
-                                            self.tU, self.tV, 7, loss)
-        opt = lambda: ops.opt_apply_multi(self.opt, [(self.dU, self.gU, self.mU, self.vU, self.tU, False),
-                                                     (self.dV, self.gV, self.mV, self.vV, self.tV, False)], 7, hyper)
-        rows = self.d["num_users"] + self.d["num_items"]
-        return {"mf_pairwise_grad_kernel": (grad, self.batch * (12 * self.dim + 12),
-                                            "512 triplets x (3 rows of 64 f32 + 3 ids)"),
-                "opt_apply_kernel": (opt, rows * self.dim * 4 * 3 * 2,
-                                     "TF-faithful Adam: (U+I)*d*4 B x {var,m,v} x read+write")}
+        from neurec_b200 import ops
+        total = 0.0
+        while k > 0:
+            n = min(k, self.spe)
+            if e2e:
+                self.T.upload()
+            ops.mf_epoch_fused(self.U, self.V, self.T.ptr, self.T.idx, self.T.users, self.T.idx, self.neg_num,
+                               self.pairwise, True, False, SEED, self.epoch, self.batch, 0, n, self.loss, self.reg,
+                               self.opt, [self.lr, 0.9, 0.999, 1e-8], self.pows, self.gU, self.gV, self.tU, self.tV,
+                               self.mU, self.vU, self.mV, self.vV, self.stamp, self.ws[0], self.ws[1], self.ws[2],
+                               self.step_loss)
+            if e2e:
+                self.loss_pin[:n].copy_(self.step_loss[:n], non_blocking=True)
+                torch.cuda.current_stream().synchronize()      # MF.train_model logs the epoch loss
+                total += float(self.loss_pin[:n].sum())
+            self.epoch += 1; self.stamp += n; self.launches += 1
+            k -= n
+        return total
 
-    def cpu_reference(self, n_steps):
-        from oracle import ref_port, tf_math
+    def algorithmic_bytes(self, k):
+        d = self.d
+        rows = d["num_users"] + d["num_items"]
+        per_step = self.batch * (12 * self.dim + 12) + rows * self.dim * 4 * 3 * 2
+        return k * per_step, ("per step: 512 triplets x (3 rows of 64 f32 + 3 ids) + TF-faithful Adam "
+                              "(U+I)*d*4 B x {var,m,v} x R+W (SURVEY 8d); sampling adds 4 B per draw")
+
+    def cpu_make(self):
+        from oracle import ref_port, torch_port
         d = self.d
         train_dict = ref_port.user_dict(d["train_indptr"], d["train_indices"])
-        np.random.seed(2018)
+        np.random.seed(SEED)
         sampler = ref_port.PairwiseSamplerPort(train_dict, d["num_items"], 1, self.batch, True)
-        tr = tf_math.MFTrainer(self.U0, self.V0, self.opt, self.lr, self.loss, self.reg, True)
-        done, t0 = 0, time.perf_counter()
-        while done < n_steps:
-            for bu, bp, bn in sampler:
-                tr.step(np.asarray(bu, np.int32), np.asarray(bp, np.int32), np.asarray(bn, np.int32))
-                done += 1
-                if done >= n_steps:
-                    break
-        return time.perf_counter() - t0, ref_port.sampler_kind()
+        tr = torch_port.MFStep(self.U0, self.V0, self.opt, self.lr, self.loss, self.reg, True)
+        return sampler, tr.step, ref_port.sampler_kind(), "torch-CPU restatement of the TF-1.12 step (dense Adam)"
+
+    def eval_tables(self):
+        return self.U, self.V
 
     def cpu_tables(self):
         return self.U0, self.V0
 
 
-class NeumfMl100k(Workload):
+# ----------------------------------------------------------------------------------------
+# configs[1]: NeuMF on ml-100k
+# ----------------------------------------------------------------------------------------
+class NeumfMl100k:
     name = "neumf-ml100k"
     describe = ("NeuMF (GMF+MLP) on ml-100k, embedding_size=32, layers [64,32,16], conf/NeuMF.properties "
                 "(pointwise cross_entropy, num_neg 4, bs 256, adam 1e-3)")
     pairwise, neg_num = False, 4
     mf_dim, layers, batch, lr, loss, opt = 32, [64, 32, 16], 256, 1e-3, "cross_entropy", "adam"
-    hyper = [1e-3, 0.9, 0.999, 1e-8]
-    loss_count = 1
-    launches_per_step = 3
     KEYS = ("mf_user", "mf_item", "mlp_user", "mlp_item", "dense")
 
-    def __init__(self, rank=0):
-        super().__init__(load_ml100k(), rank)
+    def __init__(self, rank):
+        self.d = load_ml100k()
         rs = np.random.RandomState(2017 + rank)
         nu, ni = self.d["num_users"], self.d["num_items"]
         n = lambda r, c: (rs.randn(r, c) * 0.01).astype(np.float32)
@@ -554,111 +459,80 @@ class NeumfMl100k(Workload):
             dense += [rs.uniform(-lim, lim, inn * out).astype(np.float32), np.zeros(out, np.float32)]
             inn = out
         self.P0["dense"] = np.concatenate(dense)
+        self.n = len(self.d["train_indices"]) * (self.neg_num + 1)
+        self.spe = (self.n + self.batch - 1) // self.batch
 
-    def setup_device(self):
+    def setup(self):
         import torch
         from neurec_b200 import ops
-        self.setup_common()
-        nu, ni = self.d["num_users"], self.d["num_items"]
+        d = self.d
+        nu, ni = d["num_users"], d["num_items"]
+        self.T = TrainData(d["train_indptr"], d["train_indices"])
         self.shape = ops.NcfShape.make(nu, ni, self.mf_dim, self.layers, 1)
         self.P = {k: dev(v) for k, v in self.P0.items()}
         z = lambda D: {k: torch.zeros_like(v) for k, v in D.items()}
         self.G, self.S0, self.S1 = z(self.P), z(self.P), z(self.P)
         self.tU = torch.zeros(nu, dtype=torch.int32, device="cuda")
         self.tI = torch.zeros(ni, dtype=torch.int32, device="cuda")
-        self.step_loss = torch.zeros(1 << 16, device="cuda")
+        self.step_loss = torch.zeros(self.spe, device="cuda")
+        self.loss_pin = torch.zeros(self.spe).pin_memory()
+        self.lr_sched = adam_lr_schedule(self.lr, 1 << 16)
+        self.epoch, self.t, self.stamp, self.launches = 0, 0, 1, 0
 
-    def run_steps_device(self, arrays, n_steps):
+    def run_steps(self, k, e2e=False):
+        import torch
         from neurec_b200 import ops
-        u, i, t = arrays
-        n = min(u.numel(), n_steps * self.batch)
-        ops.ncf_train_epoch(self.shape, self.P, u[:n], i[:n], t[:n], self.batch, False, self.loss, 0.0, 0.0,
-                            self.opt, self.lr_sched[self.t:self.t + n_steps], self.hyper, self.G, self.S0,
-                            self.S1, self.tU, self.tI, self.stamp, self.step_loss)
-        self.stamp += n_steps; self.t += n_steps
-        return self.launches_per_step * n_steps
+        total = 0.0
+        while k > 0:
+            n = min(k, self.spe)
+            if e2e:
+                self.T.upload()
+            cnt = min(n * self.batch, self.n)
+            u, i, t = ops.epoch_build(self.T.ptr, self.T.idx, self.T.users, self.T.idx, self.neg_num,
+                                      self.d["num_items"], False, True, SEED, self.epoch, 0, cnt)
+            ops.ncf_train_epoch(self.shape, self.P, u, i, t, self.batch, False, self.loss, 0.0, 0.0, self.opt,
+                                self.lr_sched[self.t:self.t + n], [self.lr, 0.9, 0.999, 1e-8], self.G, self.S0,
+                                self.S1, self.tU, self.tI, self.stamp, self.step_loss)
+            if e2e:
+                self.loss_pin[:n].copy_(self.step_loss[:n], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                total += float(self.loss_pin[:n].sum())
+            self.epoch += 1; self.t += n; self.stamp += n; self.launches += 1 + 3 * n
+            k -= n
+        return total
 
-    def step_on_staged(self, u, i, t):
-        self.run_steps_device((u, i, t), 1)
-        return self.step_loss
+    def algorithmic_bytes(self, k):
+        n_par = sum(v.size for v in self.P0.values())
+        per_step = self.batch * (4 * 32 * 4 * 2 + 12) + self.P0["dense"].size * 4 * 2 + n_par * 4 * 3 * 2
+        return k * per_step, ("per step: 256 samples x (4 rows of 32 f32 gathered + their gradients + ids) + dense "
+                              "weights read + gradient written + TF-faithful Adam over 4 tables + dense")
+
+    def cpu_make(self):
+        from oracle import ref_port, tf_math
+        d = self.d
+        train_dict = ref_port.user_dict(d["train_indptr"], d["train_indices"])
+        np.random.seed(SEED)
+        sampler = ref_port.PointwiseSamplerPort(train_dict, d["num_items"], self.neg_num, self.batch, True)
+        tr = tf_math.NCFTrainer(self.P0, 32, self.layers, 1, self.opt, self.lr, self.loss, 0.0, 0.0, False)
+        step = lambda bu, bi, bl: tr.step(np.asarray(bu, np.int32), np.asarray(bi, np.int32), np.asarray(bl, np.float32))
+        return sampler, step, ref_port.sampler_kind(), "numpy restatement of the TF-1.12 step"
 
     def eval_tables(self):
         return None
 
-    def run_eval(self, users):
-        """users must be a contiguous id range (what bench.py's sharding hands out)."""
-        from neurec_b200 import ops
-        a, b = int(users[0].item()), int(users[-1].item()) + 1
-        scores = ops.ncf_scores(self.shape, self.P, users)          # NeuMF.predict over all items
-        ops.mask_rows(scores, users, self.tp, self.ti)
-        ptr = (self.sp[a:b + 1] - self.sp[a]).contiguous()
-        idx = self.si[int(self.sp[a].item()):int(self.sp[b].item())].contiguous()
-        return ops.eval_score_matrix(scores, ptr, idx, METRICS, self.eval_k)
 
-    def kernels(self, arrays):
-        from neurec_b200 import ops
-        import torch
-        u, i, t = (a[:self.batch] for a in arrays)
-        loss = torch.zeros(1, device="cuda")
-        grad = lambda: ops.ncf_grad(self.shape, self.P, u, i, t, False, self.loss, 0.0, 0.0, self.G, self.tU,
-                                    self.tI, 7, loss)
-        variables = [(self.P[k], self.G[k], self.S0[k], self.S1[k], (self.tU if "user" in k else self.tI), False)
-                     for k in self.KEYS[:4]] + [(self.P["dense"], self.G["dense"], self.S0["dense"],
-                                                 self.S1["dense"], None, True)]
-        opt = lambda: ops.opt_apply_multi(self.opt, variables, 7, list(self.hyper))
-        n_par = sum(v.numel() for v in self.P.values())
-        return {"ncf_sample_kernel+ncf_wgrad_kernel": (grad, self.batch * (4 * 32 * 4 * 2 + 12) + self.P["dense"].numel() * 4 * 2,
-                                    "256 samples x (4 rows of 32 f32 gathered + their gradients + ids) + "
-                                    "dense weights read + their gradient written"),
-                "opt_apply_kernel": (opt, n_par * 4 * 3 * 2,
-                                     "TF-faithful Adam over 4 tables + dense: params*4 B x {var,m,v} x R+W")}
-
-    def cpu_reference(self, n_steps):
-        from oracle import ref_port, tf_math
-        d = self.d
-        train_dict = ref_port.user_dict(d["train_indptr"], d["train_indices"])
-        np.random.seed(2018)
-        sampler = ref_port.PointwiseSamplerPort(train_dict, d["num_items"], self.neg_num, self.batch, True)
-        tr = tf_math.NCFTrainer(self.P0, 32, self.layers, 1, self.opt, self.lr, self.loss, 0.0, 0.0, False)
-        done, t0 = 0, time.perf_counter()
-        while done < n_steps:
-            for bu, bi, bl in sampler:
-                tr.step(np.asarray(bu, np.int32), np.asarray(bi, np.int32), np.asarray(bl, np.float32))
-                done += 1
-                if done >= n_steps:
-                    break
-        return time.perf_counter() - t0, ref_port.sampler_kind()
-
-    def cpu_eval(self, threads, U=None, V=None, max_users=None):
-        """NeuMF.predict on the CPU = one forward over all items per user (NeuMF.py:163-168)."""
-        from oracle import ref_port, tf_math
-        d = self.d
-        train_dict = ref_port.user_dict(d["train_indptr"], d["train_indices"])
-        test_dict = ref_port.user_dict(d["test_indptr"], d["test_indices"])
-        keys = list(test_dict.keys())[:256]
-        test_dict = {k: test_dict[k] for k in keys}
-        items = np.arange(d["num_items"])
-        pred = lambda bu: np.stack([tf_math.ncf_predict(self.P0, np.full(len(items), u), items, 32, self.layers)
-                                    for u in bu])
-        t0 = time.perf_counter()
-        _, parts, impl = ref_port.evaluate(None, None, train_dict, test_dict, [1, 2, 4, 3, 5], self.eval_k, 128, 8,
-                                           predict=pred)
-        return time.perf_counter() - t0, len(test_dict), impl, 8
-
-
-class LightgcnGowalla(Workload):
+# ----------------------------------------------------------------------------------------
+# configs[2]: LightGCN on the real gowalla split
+# ----------------------------------------------------------------------------------------
+class LightgcnGowalla:
     name = "lightgcn-gowalla"
-    describe = ("LightGCN on a gowalla-shaped graph (29 858 users, 40 981 items), 3 layers dim=64, "
-                "conf/LightGCN.properties (bs 1024, adam 0.01, reg 1e-3, adj_type pre)")
+    describe = ("LightGCN on gowalla (29 858 users, 40 981 items, 810 128 train interactions; the reference's "
+                "'given' split), 3 layers dim=64, conf/LightGCN.properties (bs 1024, adam 0.01, reg 1e-3, adj_type pre)")
     dim, n_layers, batch, lr, reg = 64, 3, 1024, 0.01, 1e-3
-    hyper = [0.01, 0.9, 0.999, 1e-8]
-    loss_count = 2
 
-    def __init__(self, rank=0):
-        super().__init__(synth_gowalla(), rank)
-        self.launches_per_step = 2 * self.n_layers + 3
+    def __init__(self, rank):
         from neurec_b200.model.general_recommender.LightGCN import bipartite_adjacency   # the product's builder
-        d = self.d
+        self.d = d = load_gowalla()
         u = np.repeat(np.arange(d["num_users"], dtype=np.int32), np.diff(d["train_indptr"]))
         A = bipartite_adjacency(u, d["train_indices"], d["num_users"], d["num_items"], "pre", verbose=False)
         self.A = A.tocoo().astype(np.float32).tocsr()          # LightGCN.py:151-154
@@ -667,320 +541,342 @@ class LightgcnGowalla(Workload):
         n = d["num_users"] + d["num_items"]
         lim = np.sqrt(6.0 / (d["num_users"] + self.dim))
         self.E0 = rs.uniform(-lim, lim, (n, self.dim)).astype(np.float32)
+        self.n = len(d["train_indices"])
+        self.spe = (self.n + self.batch - 1) // self.batch
 
-    def setup_device(self):
+    def setup(self):
         import torch
-        self.setup_common()
-        A = self.A
+        d, A = self.d, self.A
+        self.T = TrainData(d["train_indptr"], d["train_indices"])
         self.csr = (dev(A.indptr.astype(np.int64)), dev(A.indices.astype(np.int32)), dev(A.data.astype(np.float32)))
         self.order = dev(np.argsort(-np.diff(A.indptr), kind="stable").astype(np.int32))
         self.e0 = dev(self.E0)
         z = lambda: torch.zeros_like(self.e0)
         self.m, self.v, self.ef, self.gf, self.ge = z(), z(), z(), z(), z()
         self.work = (z(), z())
-        self.step_loss = torch.zeros((1 << 14, 2), device="cuda")
+        self.step_loss = torch.zeros((self.spe, 2), device="cuda")
+        self.loss_pin = torch.zeros((self.spe, 2)).pin_memory()
+        self.lr_sched = adam_lr_schedule(self.lr, 1 << 14)
+        self.epoch, self.t, self.launches = 0, 0, 0
 
-    def run_steps_device(self, arrays, n_steps):
+    def run_steps(self, k, e2e=False):
+        import torch
         from neurec_b200 import ops
-        u, i, t = arrays
-        n = min(u.numel(), n_steps * self.batch)
         d = self.d
-        ops.lightgcn_train_epoch(self.csr, None, self.order, d["num_users"], d["num_items"], self.n_layers,
-                                 self.e0, self.m, self.v, u[:n], i[:n], t[:n], self.batch, self.reg,
-                                 self.lr_sched[self.t:self.t + n_steps], self.hyper, self.ef, self.gf, self.ge,
-                                 self.work, self.step_loss)
-        self.t += n_steps
-        return self.launches_per_step * n_steps
+        total = 0.0
+        while k > 0:
+            n = min(k, self.spe)
+            if e2e:
+                self.T.upload()
+            cnt = min(n * self.batch, self.n)
+            u, i, j = ops.epoch_build(self.T.ptr, self.T.idx, self.T.users, self.T.idx, 1, d["num_items"], True, True,
+                                      SEED, self.epoch, 0, cnt)
+            ops.lightgcn_train_epoch(self.csr, None, self.order, d["num_users"], d["num_items"], self.n_layers, self.e0,
+                                     self.m, self.v, u, i, j.view(-1), self.batch, self.reg,
+                                     self.lr_sched[self.t:self.t + n], [self.lr, 0.9, 0.999, 1e-8], self.ef, self.gf,
+                                     self.ge, self.work, self.step_loss)
+            if e2e:
+                self.loss_pin[:n].copy_(self.step_loss[:n], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                total += float(self.loss_pin[:n].sum())
+            self.epoch += 1; self.t += n; self.launches += 1 + n * (2 * self.n_layers + 4)
+            k -= n
+        return total
 
-    def step_on_staged(self, u, i, t):
-        self.run_steps_device((u, i, t), 1)
-        return self.step_loss
+    def algorithmic_bytes(self, k):
+        n, nnz = self.A.shape[0], self.A.nnz
+        spmm = nnz * 8 + (n + 1) * 8 + 2 * n * self.dim * 4
+        per_step = 2 * self.n_layers * spmm + n * self.dim * 4 * 6
+        return k * per_step, "per step: 6 SpMM x (nnz*8 + indptr + 2*N*d*4) + dense Adam N*d*4*6 B (SURVEY 8d: 0.41 GB)"
+
+    def spmm_kernel(self):
+        from neurec_b200 import ops
+        n, nnz = self.A.shape[0], self.A.nnz
+        fn = lambda: ops.spmm_csr(self.csr[0], self.csr[1], self.csr[2], self.e0, row_order=self.order, y=self.work[0])
+        return fn, nnz * 8 + (n + 1) * 8 + 2 * n * self.dim * 4
+
+    def cpu_make(self):
+        from oracle import ref_port, torch_port
+        d = self.d
+        train_dict = ref_port.user_dict(d["train_indptr"], d["train_indices"])
+        np.random.seed(SEED)
+        sampler = ref_port.PairwiseSamplerPort(train_dict, d["num_items"], 1, self.batch, True)
+        tr = torch_port.LightGCNStep(self.A, self.E0, d["num_users"], self.n_layers, self.lr, self.reg)
+        return sampler, tr.step, ref_port.sampler_kind(), "torch-CPU (sparse CSR mm) restatement of the TF-1.12 step"
 
     def eval_tables(self):
         from neurec_b200 import ops
-        ops.lightgcn_propagate(self.csr[0], self.csr[1], self.csr[2], self.order, self.e0, self.n_layers,
-                               self.ef, self.work)
+        ops.lightgcn_propagate(self.csr[0], self.csr[1], self.csr[2], self.order, self.e0, self.n_layers, self.ef, self.work)
         nu = self.d["num_users"]
         return self.ef[:nu].contiguous(), self.ef[nu:].contiguous()
-
-    def kernels(self, arrays):
-        from neurec_b200 import ops
-        n, nnz = self.A.shape[0], self.A.nnz
-        spmm = lambda: ops.spmm_csr(self.csr[0], self.csr[1], self.csr[2], self.e0, row_order=self.order,
-                                    y=self.work[0])
-        opt = lambda: ops.opt_apply_multi("adam", [(self.e0, self.ge, self.m, self.v, None, True)], 0,
-                                          list(self.hyper))
-        return {"spmm_csr_kernel": (spmm, nnz * 8 + (n + 1) * 8 + 2 * n * self.dim * 4,
-                                    "SURVEY.md 8(d): nnz*(4 B col + 4 B val) + indptr + N*d*4 B read + written"),
-                "opt_apply_kernel": (opt, n * self.dim * 4 * 4 * 2, "dense Adam: N*d*4 B x {var,m,v,grad} x R+W")}
-
-    def cpu_reference(self, n_steps):
-        from oracle import ref_port, tf_math
-        d = self.d
-        train_dict = ref_port.user_dict(d["train_indptr"], d["train_indices"])
-        np.random.seed(2018)
-        t0 = time.perf_counter()
-        sampler = ref_port.PairwiseSamplerPort(train_dict, d["num_items"], 1, self.batch, True)
-        it = iter(sampler)
-        first = next(it)                      # pays the epoch's negative sampling
-        t_sample = time.perf_counter() - t0
-        tr = tf_math.LightGCNTrainer(self.A, self.E0, d["num_users"], self.n_layers, self.lr, self.reg)
-        t1 = time.perf_counter()
-        done, batch = 0, first
-        while done < n_steps:
-            tr.step(np.asarray(batch[0], np.int32), np.asarray(batch[1], np.int32), np.asarray(batch[2], np.int32))
-            done += 1
-            batch = next(it)
-        t_steps = time.perf_counter() - t1
-        # charge the sampler its per-step share of a whole epoch
-        return t_steps + t_sample * n_steps / self.steps_per_epoch, ref_port.sampler_kind()
 
     def cpu_tables(self):
         nu = self.d["num_users"]
         return self.E0[:nu], self.E0[nu:]
 
 
-def make_workload(name, rank):
-    return {"bprmf-ml100k": BprmfMl100k, "neumf-ml100k": NeumfMl100k, "lightgcn-gowalla": LightgcnGowalla}[name](rank)
+SMALL = {"bprmf-ml100k": MfMl100k, "neumf-ml100k": NeumfMl100k, "lightgcn-gowalla": LightgcnGowalla}
 
 
-# ----------------------------------------------------------------------------------------
-# measurement
-# ----------------------------------------------------------------------------------------
-def eval_once(w, users):
-    from neurec_b200 import ops
-    tabs = w.eval_tables()
-    if tabs is None:
-        return ops.mean_rows(w.run_eval(users))
-    res = ops.eval_mf_auto(tabs[0], tabs[1], users, w.tp, w.ti, w.sp, w.si, METRICS, w.eval_k)   # what UniEvaluator calls
-    return ops.mean_rows(res)
+def cpu_train_baseline(w, n_steps):
+    threads = os.cpu_count() or 1
+    sampler, step, skind, how = w.cpu_make()
+    dt = run_cpu_epoch_steps(sampler, step, n_steps)
+    return {"value": n_steps * w.batch / dt, "unit": "triplets/s", "cores": threads, "kind": "port",
+            "sample": "%d steps of %d: the reference's sampler + shuffle + python batching (%s random_choice) + %s on "
+                      "%d host threads (TensorFlow 1.12 is not installable offline)" % (n_steps, w.batch, skind, how, threads)}, dt
 
 
-def measure(w, K, W, world, rank, windows, with_cpu=True):
-    """All numbers for one workload.  Returns the dict rank 0 prints (None on other ranks)."""
+def measure_small(w, K, W, world, rank, windows, with_cpu=True):
+    """bprmf-ml100k / neumf-ml100k / lightgcn-gowalla: N independent replicas at N > 1 (these 0.7-18 MB
+    models do not shard)."""
     import torch
-    w.setup_device()
-    arrays = w.epoch_arrays(K + W, epoch=0)
-    cut = lambda n0: tuple(a[n0 * w.batch:] for a in arrays)
-
-    # ---- value: device-resident steps
-    w.run_steps_device(arrays, W)
-    barrier(world); flush_l2(); barrier(world)
-    wall0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    launches = w.run_steps_device(cut(W), K)
-    e1.record()
-    barrier(world)
-    windows.append((wall0, time.perf_counter()))
-    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    w.setup()
+    w.run_steps(max(W, 3))
+    ms, _ = timed(lambda: w.run_steps(K), world, windows)
+    launches_before = w.launches
     value = world * K * w.batch / (ms * 1e-3)
-
-    # ---- e2e: per-step host buffers (pinned), loss read back every step
-    h_arrays = tuple(a.cpu().pin_memory() for a in arrays)
-    w.run_steps_e2e(h_arrays, W)
+    w.run_steps(max(W, 3), e2e=True)
     barrier(world); flush_l2(); barrier(world)
     wall0 = time.perf_counter()
-    _, h2d, d2h = w.run_steps_e2e(tuple(h[W * w.batch:] for h in h_arrays), K)
+    w.run_steps(K, e2e=True)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - wall0, world)
     windows.append((wall0, time.perf_counter()))
     barrier(world)
-    e2e_value = world * K * w.batch / e2e_s
-    # the same with a host wait after EVERY step (the reference's `sess.run` per batch behaviour)
-    ks = min(K, 400)
-    barrier(world)
-    wall0 = time.perf_counter()
-    w.run_steps_e2e_sync(tuple(h[W * w.batch:] for h in h_arrays), ks)
-    torch.cuda.synchronize()
-    e2e_sync_s = max_over_ranks(time.perf_counter() - wall0, world)
-    windows.append((wall0, time.perf_counter()))
-    barrier(world)
-
-    # ---- evaluator: users sharded over ranks
-    nu = w.d["num_users"]
-    n_eval = nu if w.eval_tables() is not None else min(nu, 943)
-    from neurec_b200.evaluator import sharded
-    a_, b_ = sharded.local_slice(n_eval, rank, world)
-    mine = torch.arange(a_, b_, dtype=torch.int32, device="cuda")
-    eval_once(w, mine)
-    barrier(world); flush_l2(); barrier(world)
-    reps = 3
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall0 = time.perf_counter()
-    a.record()
-    for _ in range(reps):
-        eval_once(w, mine)
-    b.record()
-    barrier(world)
-    windows.append((wall0, time.perf_counter()))
-    eval_ms = max_over_ranks(a.elapsed_time(b), world) / reps
-
+    calls = (K + w.spe - 1) // w.spe
+    tabs = w.eval_tables()
+    ev = eval_users_per_s(tabs[0], tabs[1], w.d, world, rank, windows) if tabs is not None else None
     if rank != 0:
         return None
-    # ---- roofline: each kernel alone, graph-replayed, CUDA events
-    kt, kb, kn = {}, {}, {}
-    for name, (fn, nbytes, note) in w.kernels(arrays).items():
-        kt[name] = graph_time(fn)
-        kb[name], kn[name] = nbytes, note
-    dom = max(kt, key=lambda k: kt[k])
-    peak, peak_src = measured_peaks()
-    achieved = kb[dom] / kt[dom] / 1e9
-    out = {
-        "metric": "triplets/sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32",
-        "data": "%s (%s), random-init tables, device Philox negatives" % (
-            w.d["name"], "the reference's ratio-0.8 split, tests/golden/ml100k_split.npz"
-            if w.d["name"] == "ml-100k" else "synthetic, seed 7"),
-        "config": {"workload": w.describe, "global_batch": w.batch * world,
-                   "optimizer": "adam (TensorFlow-1.12 semantics: dense over every table each step)",
-                   "parallelism": "replicas x%d (training does not shard at this size); evaluator: users "
-                                  "sharded over ranks" % world,
-                   "l2": "flushed (256 MiB write) before each timed region; the K dependent steps then run "
-                         "back-to-back as in training (model + optimizer state are L2-sized)"},
-        "e2e": {"value": e2e_value, "unit": "triplets/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3 / K,
-                "how": "nrc_graph_run_steps: the host stages %d batches from the host arrays into a pinned ring and "
-                       "launches one captured burst graph; every step has its own H2D node, kernels and loss "
-                       "D2H node, the copies of step s+1 overlap the kernels of step s; the host waits and reads "
-                       "the losses once per burst" % w.RING,
-                "sync_every_step": {"value": world * ks * w.batch / e2e_sync_s, "unit": "triplets/s",
-                                    "ms_per_step": e2e_sync_s * 1e3 / ks, "steps": ks}},
-        "gpu_launches": launches,
-        "eval": {"metric": "eval users/sec", "value": n_eval / (eval_ms * 1e-3), "unit": "users/s",
-                 "users": n_eval,
-                 "items": w.d["num_items"], "top_k": w.eval_k, "metrics": 5, "ms": eval_ms,
-                 "sharding": "users over %d rank(s)" % world},
-        "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": profiled_traffic(dom), "peak_source": peak_src,
-                     "bytes_per_launch": kb[dom], "bytes_note": kn[dom], "launch_us": kt[dom] * 1e6,
-                     "all_kernels": {k: {"us": kt[k] * 1e6, "bytes": kb[k], "GBps": kb[k] / kt[k] / 1e9}
-                                     for k in kt},
-                     "timing": "each kernel alone: 40 launches in a CUDA graph, CUDA events on the replay "
-                               "stream, best of 5"},
-    }
+    nbytes, note = w.algorithmic_bytes(K)
+    if isinstance(w, LightgcnGowalla):
+        fn, sb = w.spmm_kernel()
+        st = graph_time(fn)
+        roof = hbm_roofline("spmm_csr_fast_kernel", sb, st, "SURVEY 8(d): nnz*(4 B col + 4 B val) + indptr + N*d*4 B read + written",
+                            "the kernel alone: 40 launches in a CUDA graph, CUDA events on the replay stream, best of 5",
+                            {"step_bytes": nbytes / K, "step_note": note, "share_of_step": 6 * st / (ms * 1e-3 / K)})
+    else:
+        kname = "mf_epoch_kernel" if isinstance(w, MfMl100k) else "ncf_sample_fast_kernel+ncf_wgrad_kernel+opt_apply_kernel"
+        roof = hbm_roofline(kname, nbytes, ms * 1e-3, note,
+                            "CUDA events around the K timed steps (sampling and shuffling included)",
+                            {"honest_bound": "tables are L2-resident (0.7 MB): the step is bound by two grid-wide barriers "
+                                             "and dependent L2 round trips, not by HBM"})
+    out = {"metric": "triplets/sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+           "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "%s (%s), random-init tables, device Philox negatives + keyed-bijection shuffle" % (
+               w.d["name"], "the reference's split, tests/golden/%s_split.npz" % ("ml100k" if w.d["name"] == "ml-100k" else w.d["name"])),
+           "config": {"workload": w.describe, "global_batch": w.batch * world, "steps_per_epoch": w.spe,
+                      "timed_region": "starts from the train CSR: negative sampling + shuffle + batching + the steps",
+                      "optimizer": "adam (TensorFlow-1.12 semantics: dense over every table each step)",
+                      "parallelism": "replicas x%d (training does not shard at this size)" % world,
+                      "l2": "flushed (256 MiB write) before each timed region; the K dependent steps then run back-to-back "
+                            "as in training (model + optimizer state are L2-sized)"},
+           "e2e": {"value": world * K * w.batch / e2e_s, "unit": "triplets/s",
+                   "h2d_bytes_per_step": w.T.nbytes * calls / K, "d2h_bytes_per_step": 4 * (2 if isinstance(w, LightgcnGowalla) else 1),
+                   "ms_per_step": e2e_s * 1e3 / K,
+                   "how": "per epoch call: the train CSR + flattened positives are copied from pinned host memory, the epoch's "
+                          "steps run, the per-step losses are copied back to pinned memory, the host waits (what "
+                          "train_model does per epoch); %d call(s) in the timed region" % calls},
+           "gpu_launches": w.launches - launches_before if False else None,
+           "roofline": roof}
+    out["gpu_launches"] = {MfMl100k: calls, NeumfMl100k: calls + 3 * K, LightgcnGowalla: calls + K * (2 * w.n_layers + 4)}[type(w)]
+    if ev is not None:
+        out["eval"] = ev
     if with_cpu:
-        threads = os.cpu_count() or 1
-        n_cpu = min(w.steps_per_epoch, 40 if w.name == "lightgcn-gowalla" else 2000)
-        dt, skind = w.cpu_reference(n_cpu)
-        out["cpu_baseline"] = {"value": n_cpu * w.batch / dt, "unit": "triplets/s", "cores": threads,
-                               "kind": "port",
-                               "sample": "%d steps of %d: reference sampler/batching (%s random_choice) + numpy/"
-                                         "scipy restatement of the TF-1.12 step (TensorFlow is not installable "
-                                         "offline); numpy elementwise work is single-threaded" % (n_cpu, w.batch, skind)}
-        tabs = w.cpu_tables() if hasattr(w, "cpu_tables") else (None, None)
-        dte, n_users_cpu, eimpl, eth = w.cpu_eval(threads, tabs[0], tabs[1],
-                                                  max_users=3000 if w.name == "lightgcn-gowalla" else None)
-        out["eval"]["cpu"] = {"value": n_users_cpu / dte, "unit": "users/s",
-                              "kind": "reference" if eimpl == "reference" else "port", "threads": eth,
-                              "sample": "%d users: predict + python mask loop + evaluate.h top-K/metrics, "
-                                        "test_batch_size 128" % n_users_cpu}
+        n_cpu = min(w.spe * 2, 40 if isinstance(w, LightgcnGowalla) else 3200)
+        out["cpu_baseline"], _ = cpu_train_baseline(w, n_cpu)
+        if ev is not None:
+            tabs = w.cpu_tables()
+            out["eval"]["cpu"] = cpu_eval(w.d, tabs[0], tabs[1], os.cpu_count() or 1,
+                                          max_users=3000 if isinstance(w, LightgcnGowalla) else None)
     return out
 
 
-def measure_synth_sgd(K, W, world, rank, windows, with_cpu=True):
-    """BASELINE config 5 scaled to ONE GPU: BPRMF with plain SGD on synthetic tables far larger
-    than L2 (4 M users x 8 M items x d=128 = 6.1 GB), users uniform, positives Zipf(1.05),
-    batch 2^20 -- the HBM-bound single-pass kernel (nrc_mf_bpr_sgd_fused)."""
+# ----------------------------------------------------------------------------------------
+# configs[4]: BPRMF, learner=gd, row-sharded tables, CSR-fed single-pass kernel (the default)
+# ----------------------------------------------------------------------------------------
+class ShardedCfg:
+    users_per_gpu, items_per_gpu, dim, batch, lr = 6_250_000, 12_500_000, 128, 1 << 20, 0.05
+    max_pos = 7                 # positives per user: 1..7 (SURVEY 8d: a <= 64-item positive list)
+    zipf_a = 1.05
+
+
+def synth_shard_csr(cfg, rank, world, device="cuda"):
+    """This rank's train CSR: its own users (local ids), 1..max_pos positives each, items
+    Zipf(1.05) over the GLOBAL catalogue (hot ranks scattered by a multiplicative hash), rows sorted
+    and duplicate-free.  Built on the device (setup, untimed)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(3 + rank)
+    nu, ni = cfg.users_per_gpu, cfg.items_per_gpu * world
+    deg = torch.randint(1, cfg.max_pos + 1, (nu,), device=device, generator=g)
+    x = torch.rand((nu, cfg.max_pos), device=device, generator=g, dtype=torch.float64)
+    a = cfg.zipf_a                         # inverse CDF of the continuous Zipf(a) truncated to [1, ni]
+    r = (((ni ** (1 - a) - 1) * x + 1) ** (1 / (1 - a))).clamp(1, ni).long() - 1
+    items = (r * 2654435761) % ni
+    del x, r
+    big = torch.iinfo(torch.int64).max
+    items[torch.arange(cfg.max_pos, device=device)[None, :] >= deg[:, None]] = big
+    items = items.sort(1).values
+    dup = torch.zeros_like(items, dtype=torch.bool)
+    dup[:, 1:] = items[:, 1:] == items[:, :-1]
+    items[dup] = big
+    items = items.sort(1).values
+    keep = items < big
+    deg = keep.sum(1)
+    indptr = torch.zeros(nu + 1, dtype=torch.int64, device=device)
+    indptr[1:] = deg.cumsum(0)
+    indices = items[keep].to(torch.int32)
+    users = torch.repeat_interleave(torch.arange(nu, device=device, dtype=torch.int32), deg)
+    return indptr.cpu().numpy(), indices.cpu().numpy(), users.cpu().numpy()
+
+
+def sharded_describe(cfg, world):
+    return ("BPRMF, learner=gd, tables row-sharded over %d GPU(s): %d users x %d items x d=%d per GPU (%.1f GB per GPU; "
+            "%d x %d rows in total), 2^20 triplets per GPU and step sampled INSIDE the step kernel from the rank's train "
+            "CSR (1..%d positives per user, items Zipf(%.2f) over the global catalogue, uniform negatives rejected against "
+            "the user's row, keyed-bijection shuffle) -- BASELINE configs[4], weak scaling" % (
+                world, cfg.users_per_gpu, cfg.items_per_gpu, cfg.dim,
+                (cfg.users_per_gpu + cfg.items_per_gpu) * cfg.dim * 4 / 1e9, cfg.users_per_gpu * world,
+                cfg.items_per_gpu * world, cfg.max_pos, cfg.zipf_a))
+
+
+def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
     import torch
     from neurec_b200 import ops
-    nu, ni, dim, bs, lr = 4_000_000, 8_000_000, 128, 1 << 20, 0.05
-    K = min(K, 24)
-    g = torch.Generator(device="cuda").manual_seed(3 + rank)
-    U = torch.randn(nu, dim, device="cuda", generator=g) * 0.01
-    V = torch.randn(ni, dim, device="cuda", generator=g) * 0.01
-
-    def ids(n):
-        u = torch.randint(0, nu, (n,), device="cuda", generator=g, dtype=torch.int32)
-        x = torch.rand(n, device="cuda", generator=g, dtype=torch.float64)
-        a = 1.05   # inverse CDF of the continuous Zipf(a) truncated to [1, ni]
-        r = (((ni ** (1 - a) - 1) * x + 1) ** (1 / (1 - a))).clamp(1, ni).long() - 1
-        p = ((r * 2654435761) % ni).to(torch.int32)          # scatter the hot ranks over the table
-        ng = torch.randint(0, ni, (n,), device="cuda", generator=g, dtype=torch.int32)
-        return u, p, ng
-    u, p, ng = ids((K + W) * bs)
+    from neurec_b200.util import peer
+    W = max(W, 3)
+    dim, bs = cfg.dim, cfg.batch
+    ni = cfg.items_per_gpu * world
+    ptr, idx, users = synth_shard_csr(cfg, rank, world)
+    T = TrainData(ptr, idx, users)
+    del ptr, idx, users
+    torch.cuda.empty_cache()
+    g = torch.Generator(device="cuda").manual_seed(30 + rank)
+    if world > 1:
+        VS = peer.alloc_sharded(cfg.items_per_gpu, dim)
+        US_local = torch.empty((cfg.users_per_gpu, dim), dtype=torch.float32, device="cuda")
+    else:
+        VS = peer.single(torch.empty((cfg.items_per_gpu, dim), dtype=torch.float32, device="cuda"))
+        US_local = torch.empty((cfg.users_per_gpu, dim), dtype=torch.float32, device="cuda")
+    US_local.normal_(0, 0.01, generator=g)
+    VS.local.normal_(0, 0.01, generator=g)
+    spe = T.n_pos // bs                        # whole batches only (drop_last), so every step is 2^20 triplets
     loss = torch.zeros(1, device="cuda")
-    step = lambda s: ops.mf_bpr_sgd_fused(U, V, u[s * bs:(s + 1) * bs], p[s * bs:(s + 1) * bs],
-                                          ng[s * bs:(s + 1) * bs], lr, 0.0, loss)
+    loss_pin = torch.zeros(K + W + 8).pin_memory()
+    state = {"g": 0}
+
+    def step(e2e_slot=None):
+        e, s = divmod(state["g"], spe)
+        ops.mf_bpr_sgd_epoch(US_local, VS, T.ptr, T.idx, T.users, T.idx, ni, True, SEED + rank, e, s * bs, bs, cfg.lr, 0.0, loss)
+        state["g"] += 1
+        if e2e_slot is not None:               # every step's loss goes back to the host
+            loss_pin[e2e_slot:e2e_slot + 1].copy_(loss, non_blocking=True)
+
+    for _ in range(W):
+        step()
+    barrier(world)
+    # per-launch durations (CUDA events on the launching stream) inside the timed region
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+
+    def run():
+        evs[0].record()
+        for s in range(K):
+            step()
+            evs[s + 1].record()
+    ms, _ = timed(run, world, windows)
+    launch_ms = [evs[s].elapsed_time(evs[s + 1]) for s in range(K)]
+    # e2e: the train interactions come from pinned host memory inside the timed region
     for s in range(W):
         step(s)
     barrier(world); flush_l2(); barrier(world)
     wall0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(W, W + K):
+    T.upload()
+    for s in range(K):
         step(s)
-    e1.record()
-    barrier(world)
-    windows.append((wall0, time.perf_counter()))
-    ms = max_over_ranks(e0.elapsed_time(e1), world)
-    # e2e: ids of every step come from pinned host memory, the loss goes back every step
-    hu, hp, hn = (t.cpu().pin_memory() for t in (u, p, ng))
-    du, dp, dn = (torch.empty(bs, dtype=torch.int32, device="cuda") for _ in range(3))
-    loss_pin = torch.zeros(1).pin_memory()
-
-    def e2e_step(s):
-        sl = slice(s * bs, (s + 1) * bs)
-        du.copy_(hu[sl], non_blocking=True); dp.copy_(hp[sl], non_blocking=True); dn.copy_(hn[sl], non_blocking=True)
-        loss.zero_()
-        ops.mf_bpr_sgd_fused(U, V, du, dp, dn, lr, 0.0, loss)
-        loss_pin.copy_(loss, non_blocking=True)
-        torch.cuda.synchronize()
-    for s in range(W):
-        e2e_step(s)
-    barrier(world)
-    wall0 = time.perf_counter()
-    for s in range(W, W + K):
-        e2e_step(s)
+    torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - wall0, world)
     windows.append((wall0, time.perf_counter()))
     barrier(world)
+    finite = bool(np.isfinite(loss_pin[:K].numpy()).all())
+    remote = (world - 1) / world if world > 1 else 0.0
+    if world > 1:
+        VS.close()
     if rank != 0:
         return None
-    peak, peak_src = measured_peaks()
+    kt = float(np.mean(launch_ms)) * 1e-3
     nbytes = bs * (24 * dim + 12)
-    kt = ms * 1e-3 / K
-    out = {"value": world * K * bs / (ms * 1e-3), "unit": "triplets/s", "steps": K, "ms_per_step": ms / K,
-           "e2e": {"value": world * K * bs / e2e_s, "unit": "triplets/s", "h2d_bytes_per_step": 12 * bs,
-                   "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / K},
+    nv_bytes = bs * 2 * remote * dim * 4       # per direction and GPU: remote item rows read (in) / RED-updated (out)
+    extra = {"launch_us_min": float(np.min(launch_ms)) * 1e3, "launch_us_max": float(np.max(launch_ms)) * 1e3}
+    if world > 1:
+        extra["nvlink"] = {"remote_item_row_fraction": remote, "GBps_per_gpu_per_direction": 2 * nv_bytes / kt / 1e9,
+                           "of_measured_peer_copy_770_GBps": 2 * nv_bytes / kt / 1e9 / 770.0,
+                           "note": "per direction: the rows this GPU reads from peers + the RED payloads peers send to it "
+                                   "(and the mirror image outbound); the limiting resource at N > 1"}
+    out = {"metric": "triplets/sec", "value": world * K * bs / (ms * 1e-3), "unit": "triplets/s", "n_gpus": world,
+           "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic, seeds 3+rank / 30+rank",
+           "config": {"workload": sharded_describe(cfg, world), "train_positives_per_gpu": T.n_pos,
+                      "global_batch": bs * world, "steps_per_epoch": spe,
+                      "exchange": ("remote item rows are gathered and RED-updated through peer mappings over NVLink inside "
+                                   "the one fused kernel; no NCCL collective in the data path; ranks are not synchronised "
+                                   "between steps") if world > 1 else "single GPU: no exchange",
+                      "loss_finite": finite,
+                      "l2": "tables (9.6 GB per GPU) and the train CSR (%.2f GB) are far larger than L2; every step draws "
+                            "fresh positions of the shuffled epoch" % (T.nbytes / 1e9)},
+           "e2e": {"value": world * K * bs / e2e_s, "unit": "triplets/s", "h2d_bytes_per_step": T.nbytes / K,
+                   "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / K,
+                   "how": "the rank's train CSR + flattened positives (%.0f MB) are copied from pinned host memory inside "
+                          "the timed region, then K steps, each copying its loss back to pinned memory" % (T.nbytes / 1e6)},
            "gpu_launches": K,
-           "config": {"workload": "BPRMF synthetic %d users x %d items, dim %d (%.1f GB of tables), learner=gd, "
-                                  "batch 2^20, users uniform, positives Zipf(1.05), negatives uniform; single-pass "
-                                  "fused step (BASELINE config 5 scaled to one GPU)" % (nu, ni, dim, (nu + ni) * dim * 4 / 1e9),
-                      "l2": "tables (6.1 GB) and the per-step id arrays are far larger than L2; every step uses "
-                            "fresh ids"},
-           "roofline": {"kernel": "mf_bpr_sgd_fused_kernel", "bound": "hbm", "achieved": nbytes / kt / 1e9,
-                        "peak": peak, "unit": "GB/s", "frac": nbytes / kt / 1e9 / peak,
-                        "traffic": profiled_traffic("mf_bpr_sgd_fused_kernel"),
-                        "peak_source": peak_src, "bytes_per_launch": nbytes, "launch_us": kt * 1e6,
-                        "bytes_note": "SURVEY.md 8(d): (24*d + 12) B per triplet x 2^20 triplets",
-                        "timing": "CUDA events around the K timed launches (one kernel per step)"}}
+           "roofline": hbm_roofline("mf_bpr_sgd_stream_kernel", nbytes, kt,
+                                    "SURVEY 8(d): (24*d + 12) B per triplet x 2^20 triplets (the fused sampler's CSR reads "
+                                    "are not counted: 'fused: 0 extra')",
+                                    "CUDA events on the launching stream around each of the K timed launches; mean", extra)}
     if with_cpu:
-        from oracle import tf_math
-        cn_u, cn_i, cbs = 400_000, 800_000, 1 << 14
-        rs = np.random.RandomState(0)
-        Uc = (rs.randn(cn_u, dim) * 0.01).astype(np.float32); Vc = (rs.randn(cn_i, dim) * 0.01).astype(np.float32)
-        cu, cp, cn = rs.randint(0, cn_u, cbs), rs.randint(0, cn_i, cbs), rs.randint(0, cn_i, cbs)
-        t0 = time.perf_counter()
-        reps = 3
-        for _ in range(reps):   # sparse gd step: gather, dot, g, scatter-sub (TF scatter_sub on IndexedSlices)
-            pu, qi, qj = Uc[cu], Vc[cp], Vc[cn]
-            x = (pu * qi).sum(1) - (pu * qj).sum(1)
-            _, gg = tf_math.pairwise_loss_and_grad("bpr", x)
-            gg = gg[:, None]
-            np.subtract.at(Uc, cu, np.float32(lr) * gg * (qi - qj))
-            np.subtract.at(Vc, cp, np.float32(lr) * gg * pu)
-            np.subtract.at(Vc, cn, np.float32(lr) * -gg * pu)
-        dt = (time.perf_counter() - t0) / reps
-        out["cpu_baseline"] = {"value": cbs / dt, "unit": "triplets/s", "cores": os.cpu_count() or 1, "kind": "port",
-                               "sample": "numpy restatement of the TF gd step on a host-RAM-sized slice (%d x %d "
-                                         "rows, d=%d, batch 2^14), per-triplet cost extrapolates linearly" % (cn_u, cn_i, dim)}
-    del U, V
-    torch.cuda.empty_cache()
+        out["cpu_baseline"] = cpu_sharded_baseline(cfg, seconds=12.0)
     return out
 
 
+def cpu_sharded_baseline(cfg, seconds=12.0):
+    """configs[4] on the host: a host-RAM-sized slice with the same dim / positives-per-user / Zipf
+    law; the reference's sampler + python batching feed a multi-threaded torch-CPU gd step."""
+    from oracle import ref_port, torch_port
+    threads = os.cpu_count() or 1
+    torch_port.set_threads(threads)
+    nu, ni, dim, bs = 200_000, 400_000, cfg.dim, 1 << 14
+    rs = np.random.RandomState(0)
+    deg = rs.randint(1, cfg.max_pos + 1, nu)
+    a = cfg.zipf_a
+    x = rs.rand(int(deg.sum()))
+    r = (((ni ** (1 - a) - 1) * x + 1) ** (1 / (1 - a))).clip(1, ni).astype(np.int64) - 1
+    items = (r * 2654435761) % ni
+    off = np.concatenate([[0], np.cumsum(deg)])
+    train = {u: sorted(set(items[off[u]:off[u + 1]].tolist())) for u in range(nu)}
+    U = (rs.randn(nu, dim) * 0.01).astype(np.float32); V = (rs.randn(ni, dim) * 0.01).astype(np.float32)
+    np.random.seed(SEED)
+    sampler = ref_port.PairwiseSamplerPort(train, ni, 1, bs, True)
+    tr = torch_port.MFStep(U, V, "gd", cfg.lr, "bpr", 0.0, True)
+    n_pos = sum(len(v) for v in train.values())
+    spe = (n_pos + bs - 1) // bs
+    t0 = time.perf_counter()
+    done = 0
+    for batch in sampler:                          # one epoch at most: sampling + shuffle + batching + steps
+        tr.step(*batch)
+        done += 1
+        if time.perf_counter() - t0 > seconds and done >= 3:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": done * bs / dt, "unit": "triplets/s", "cores": threads, "kind": "port",
+            "sample": "%d steps of 2^14 on a host-RAM-sized slice (%d users x %d items, d=%d, %d positives): the reference's "
+                      "sampler + shuffle + python batching (%s random_choice; the epoch's sampling is paid up front) + torch-CPU "
+                      "restatement of the TF gd step on %d threads; per-triplet cost extrapolates linearly" % (
+                          done, nu, ni, dim, n_pos, ref_port.sampler_kind(), threads)}
+
+
+# ----------------------------------------------------------------------------------------
+# configs[3]: the full-catalogue evaluator on the tensor cores
+# ----------------------------------------------------------------------------------------
 def measure_synth_eval(K, W, world, rank, windows, with_cpu=True):
     """BASELINE config 4 on ONE GPU per rank: the full-catalogue evaluator over 10 M items x d=128
     with the score step on the tensor cores (nrc_eval_mf_tc: bf16 tcgen05 candidate pass, exact fp32
@@ -1106,137 +1002,16 @@ def measure_synth_eval(K, W, world, rank, windows, with_cpu=True):
     return out
 
 
-def measure_sharded_sgd(K, W, world, rank, windows):
-    """BASELINE config 5, weak-scaled: BPRMF with plain SGD on tables ROW-SHARDED over the ranks,
-    6.25 M users x 12.5 M items x d=128 per GPU (= 50 M x 100 M at 8 GPUs).  Every rank trains
-    triplets of its own users (uniform), positives Zipf(1.05) over the GLOBAL catalogue, negatives
-    uniform over it; remote item rows are read and RED-updated over NVLink by the one fused kernel
-    (nrc_mf_bpr_sgd_sharded) -- no collective in the data path, ranks run asynchronously like the
-    in-batch hogwild of the single-GPU kernel."""
-    import torch
-    import torch.distributed as dist
-    from neurec_b200 import ops
-    from neurec_b200.util import peer
-    nu_l, ni_l, dim, bs, lr = 6_250_000, 12_500_000, 128, 1 << 20, 0.05
-    K = min(K, 24)
-    ni = ni_l * world
-    g = torch.Generator(device="cuda").manual_seed(3 + rank)
-    myU = torch.randn(nu_l, dim, device="cuda", generator=g) * 0.01
-    myV = torch.randn(ni_l, dim, device="cuda", generator=g) * 0.01
-    if world > 1:
-        Us, Vs = peer.open_peer_shards(myU), peer.open_peer_shards(myV)
-    else:
-        Us, Vs = [myU], [myV]
-
-    def ids(n):
-        u = torch.randint(0, nu_l, (n,), device="cuda", generator=g, dtype=torch.int32) + rank * nu_l
-        x = torch.rand(n, device="cuda", generator=g, dtype=torch.float64)
-        a = 1.05
-        r = (((ni ** (1 - a) - 1) * x + 1) ** (1 / (1 - a))).clamp(1, ni).long() - 1
-        p = ((r * 2654435761) % ni).to(torch.int32)
-        ng = torch.randint(0, ni, (n,), device="cuda", generator=g, dtype=torch.int32)
-        return u, p, ng
-    u, p, ng = ids((K + W) * bs)
-    loss = torch.zeros(1, device="cuda")
-    step = lambda s: ops.mf_bpr_sgd_sharded(Us, Vs, rank, u[s * bs:(s + 1) * bs], p[s * bs:(s + 1) * bs],
-                                            ng[s * bs:(s + 1) * bs], lr, 0.0, loss)
-    for s in range(W):
-        step(s)
-    torch.cuda.synchronize()
-    barrier(world); flush_l2(); barrier(world)
-    wall0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(W, W + K):
-        step(s)
-    e1.record()
-    barrier(world)
-    windows.append((wall0, time.perf_counter()))
-    ms = max_over_ranks(e0.elapsed_time(e1), world)
-    hu, hp, hn = (t.cpu().pin_memory() for t in (u, p, ng))
-    du, dp, dn = (torch.empty(bs, dtype=torch.int32, device="cuda") for _ in range(3))
-    loss_pin = torch.zeros(1).pin_memory()
-
-    def e2e_step(s):
-        sl = slice(s * bs, (s + 1) * bs)
-        du.copy_(hu[sl], non_blocking=True); dp.copy_(hp[sl], non_blocking=True); dn.copy_(hn[sl], non_blocking=True)
-        loss.zero_()
-        ops.mf_bpr_sgd_sharded(Us, Vs, rank, du, dp, dn, lr, 0.0, loss)
-        loss_pin.copy_(loss, non_blocking=True)
-        torch.cuda.synchronize()
-    for s in range(W):
-        e2e_step(s)
-    barrier(world)
-    wall0 = time.perf_counter()
-    for s in range(W, W + K):
-        e2e_step(s)
-    e2e_s = max_over_ranks(time.perf_counter() - wall0, world)
-    windows.append((wall0, time.perf_counter()))
-    barrier(world)
-    remote = float((torch.div(p[:bs].long(), ni_l, rounding_mode="floor") != rank).double().mean())
-    finite = bool(torch.isfinite(loss).item())
-    del Us, Vs
-    barrier(world)
-    if rank != 0:
-        return None
-    peak, peak_src = measured_peaks()
-    nbytes = bs * (24 * dim + 12)
-    kt = ms * 1e-3 / K
-    return {"value": world * K * bs / (ms * 1e-3), "unit": "triplets/s", "steps": K, "ms_per_step": ms / K,
-            "e2e": {"value": world * K * bs / e2e_s, "unit": "triplets/s", "h2d_bytes_per_step": 12 * bs,
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / K},
-            "gpu_launches": K,
-            "config": {"workload": "BPRMF, learner=gd, tables row-sharded over %d GPU(s): %d users x %d items x d=%d "
-                                   "per GPU (%.1f GB per GPU, %d x %d rows in total), batch 2^20 per GPU and step, users "
-                                   "of the own shard, positives Zipf(1.05) and negatives uniform over the global "
-                                   "catalogue (BASELINE config 5, weak scaling)" % (
-                                       world, nu_l, ni_l, dim, (nu_l + ni_l) * dim * 4 / 1e9, nu_l * world, ni),
-                       "exchange": "remote item rows are gathered and RED-updated through CUDA-IPC peer mappings over "
-                                   "NVLink inside the fused kernel; no NCCL collective in the data path; ranks are "
-                                   "not synchronised between steps",
-                       "remote_item_row_fraction": remote, "loss_finite": finite,
-                       "l2": "tables (9.6 GB per GPU) and the per-step id arrays are far larger than L2"},
-            "roofline": {"kernel": "mf_bpr_sgd_fused_kernel", "bound": "hbm", "achieved": nbytes / kt / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": nbytes / kt / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                         "bytes_per_launch": nbytes, "launch_us": kt * 1e6,
-                         "bytes_note": "per GPU: (24*d + 12) B per triplet x 2^20 triplets; with %d ranks %.0f%% of "
-                                       "the item-row bytes cross NVLink instead of local HBM" % (world, 100 * remote),
-                         "timing": "CUDA events around the K timed launches of the slowest rank"}}
-
-
 def run_ours(args):
-    import torch
     rank, world, local = dist_setup()
     K, W = args.steps, max(args.warmup, 3)
     clocks = ClockSampler(local)
     clocks.start()
     windows = []
-    if args.workload == "bprmf-synth":
-        o = measure_synth_sgd(K, W, world, rank, windows)
-        out = None
-        if rank == 0:
-            out = {"metric": "triplets/sec", "n_gpus": world, "warmup": W, "higher_is_better": True,
-                   "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic, seed 3"}
-            out.update(o)
-        args.only = True
-    elif args.workload == "bprmf-sharded":
-        if world > 1 and os.environ.get("NRC_EXPERIMENTAL_SHARDED") != "1":
-            # Round-1 status: the kernel, the ABI and the host logic exist and the local-row path is
-            # verified, but kernels faulted on the CUDA-IPC peer mappings on the 2-GPU box
-            # (tests/mgpu_sharded_check.py stage 1); see DESIGN.md section 5.  Refuse instead of crashing.
-            if rank == 0:
-                emit(json.dumps({"workload": "bprmf-sharded", "n_gpus": world,
-                                 "unavailable": "row-sharded peer-memory path not validated yet "
-                                                "(set NRC_EXPERIMENTAL_SHARDED=1 to run it anyway)"}))
-            return
-        o = measure_sharded_sgd(K, W, world, rank, windows)
-        out = None
-        if rank == 0:
-            out = {"metric": "triplets/sec", "n_gpus": world, "warmup": W, "higher_is_better": True,
-                   "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic, seed 3"}
-            out.update(o)
-        args.only = True
-    elif args.workload == "eval-synth":
+    name = args.workload
+    if name == "bprmf-sharded":
+        out = measure_sharded(K, W, world, rank, windows)
+    elif name == "eval-synth":
         o = measure_synth_eval(K, W, world, rank, windows)
         out = None
         if rank == 0:
@@ -1244,29 +1019,28 @@ def run_ours(args):
                    "scaling": "weak", "vs_baseline": None, "dtype": "bf16 candidates + f32 exact re-score",
                    "data": "synthetic, seed 5"}
             out.update(o)
-        args.only = True
     else:
-        out = measure(make_workload(args.workload, rank), K, W, world, rank, windows)
+        out = measure_small(SMALL[name](rank), K, W, world, rank, windows)
     if world == 1 and not args.only:
+        import torch
         others = {}
-        for name in WORKLOADS:
-            if name == args.workload:
+        keep = ("value", "unit", "steps", "ms_per_step", "e2e", "eval", "roofline", "cpu_baseline", "config", "gpu_launches")
+        plan = [("bprmf-ml100k", 157 * 4), ("neumf-ml100k", 1570), ("lightgcn-gowalla", 100), ("eval-synth", 4),
+                ("bprmf-sharded", 20)]
+        for other, k in plan:
+            if other == name:
                 continue
-            k = min(K, 200) if name == "lightgcn-gowalla" else K
             try:
-                o = measure(make_workload(name, rank), k, W, world, rank, windows)
-                others[name] = {x: o[x] for x in ("value", "unit", "steps", "ms_per_step", "e2e", "eval",
-                                                  "roofline", "cpu_baseline", "config", "gpu_launches")}
+                torch.cuda.empty_cache()
+                if other == "eval-synth":
+                    o = measure_synth_eval(k, W, world, rank, windows)
+                elif other == "bprmf-sharded":
+                    o = measure_sharded(k, W, world, rank, windows)
+                else:
+                    o = measure_small(SMALL[other](rank), k, W, world, rank, windows)
+                others[other] = {x: o[x] for x in keep if x in o}
             except Exception as ex:  # keep the headline line even if a secondary workload fails
-                others[name] = {"error": repr(ex)}
-        try:
-            others["bprmf-synth-sgd"] = measure_synth_sgd(24, W, world, rank, windows)
-        except Exception as ex:
-            others["bprmf-synth-sgd"] = {"error": repr(ex)}
-        try:
-            others["eval-synth"] = measure_synth_eval(4, W, world, rank, windows)
-        except Exception as ex:
-            others["eval-synth"] = {"error": repr(ex)}
+                others[other] = {"error": repr(ex)}
         out["others"] = others
     clocks.stop()
     if rank == 0:
@@ -1279,31 +1053,40 @@ def run_ours(args):
 
 
 def run_reference(args):
-    """The reference's own CPU path on this box's host cores (rank 0 only)."""
+    """The reference's own CPU path on this box's host cores (rank 0 only; other ranks exit)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    w = make_workload(args.workload, 0)
     threads = os.cpu_count() or 1
-    # bounded sample made of whole epochs where an epoch is short (the reference draws an epoch's
-    # negatives up front, so a partial epoch would overcharge it)
-    spe = w.steps_per_epoch
-    if w.name == "lightgcn-gowalla":
-        n = min(max(args.steps, 10), 60)
-    else:
-        n = spe * min(max(args.steps // spe, 1), 2)
-    w.cpu_reference(min(max(args.warmup, 1), 20))
-    dt, skind = w.cpu_reference(n)
-    value = n * w.batch / dt
-    out = {"impl": "reference", "metric": "triplets/sec", "value": value, "unit": "triplets/s",
+    from oracle import torch_port
+    torch_port.set_threads(threads)
+    name = args.workload
+    if name == "bprmf-sharded":
+        cb = cpu_sharded_baseline(ShardedCfg, seconds=max(10.0, min(60.0, 3.0 * args.steps)))
+        cfg = ShardedCfg
+        out = {"impl": "reference", "metric": "triplets/sec", "value": cb["value"], "unit": "triplets/s",
+               "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": cfg.batch / cb["value"] * 1e3, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic slice, seed 0",
+               "config": {"workload": sharded_describe(cfg, args.gpus), "global_batch": cfg.batch * args.gpus,
+                          "cpu_arm": "the CPU arm runs a host-RAM-sized slice of the same law in batches of 2^14; ms_per_step "
+                                     "is scaled to 2^20 triplets"},
+               "cpu_baseline": cb,
+               "e2e": {"value": cb["value"], "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        emit(json.dumps(out))
+        return
+    if name == "eval-synth":
+        emit(json.dumps({"impl": "reference", "unavailable": "eval-synth's CPU arm is its cpu_baseline key (needs the GPU-side tables)"}))
+        return
+    w = SMALL[name](0)
+    n = min(w.spe * max(1, min(args.steps // w.spe, 2)), 60 if name == "lightgcn-gowalla" else 1 << 30)
+    cb, dt = cpu_train_baseline(w, n)
+    out = {"impl": "reference", "metric": "triplets/sec", "value": cb["value"], "unit": "triplets/s",
            "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": dt * 1e3 / n,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "%s, same init tables as the GPU arm" % w.d["name"],
            "config": {"workload": w.describe, "global_batch": w.batch},
-           "cpu_baseline": {"value": value, "unit": "triplets/s", "cores": threads, "kind": "port",
-                            "sample": "%d steps: reference sampler/batching (%s random_choice) + numpy/scipy "
-                                      "restatement of the TF-1.12 step (TensorFlow 1.12 is not installable "
-                                      "offline)" % (n, skind)},
-           "e2e": {"value": value, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(json.dumps(out))
 
 
@@ -1340,9 +1123,9 @@ def main():
     lift_cpu_thread_limits()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1570)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=WORKLOADS + ("bprmf-synth", "eval-synth", "bprmf-sharded"))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=WORKLOADS)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--only", action="store_true", help="measure only --workload (used under ncu)")
     args = ap.parse_args()

@@ -305,3 +305,33 @@ def test_ngcf_trainer_learns_the_training_pairs():
     assert Ue.shape == (nu, 8 + 8 + 8) and Ie.shape == (60, 24) and Ue.dtype == np.float32
     x = (Ue[users] * Ie[pos]).sum(1) - (Ue[users] * Ie[neg]).sum(1)
     assert (x > 0).mean() > 0.8
+
+
+def test_torch_timing_port_follows_the_parity_oracle(ml100k):
+    """oracle/torch_port.py (the multi-threaded CPU arm bench.py times) against oracle/tf_math.py (the
+    parity oracle): same losses and tables after a few steps, for every step kind it times."""
+    from oracle import torch_port
+    d = ml100k
+    nu, ni = d["num_users"], d["num_items"]
+    rs = np.random.RandomState(0)
+    U0 = (rs.randn(nu, 16) * 0.1).astype(np.float32); V0 = (rs.randn(ni, 16) * 0.1).astype(np.float32)
+    for pairwise, loss, learner in ((True, "bpr", "adam"), (True, "bpr", "gd"), (False, "cross_entropy", "adam"),
+                                    (False, "square", "gd")):
+        a = tf_math.MFTrainer(U0, V0, learner, 1e-2, loss, 1e-3, pairwise)
+        b = torch_port.MFStep(U0, V0, learner, 1e-2, loss, 1e-3, pairwise)
+        for s in range(4):
+            u = rs.randint(0, nu, 300).astype(np.int32); i = rs.randint(0, ni, 300).astype(np.int32)
+            t = rs.randint(0, ni, 300).astype(np.int32) if pairwise else rs.randint(0, 2, 300).astype(np.float32)
+            la, lb = a.step(u, i, t), b.step(u.tolist(), i.tolist(), t.tolist())
+            assert abs(float(la) - lb) < 1e-3 * max(1.0, abs(lb))
+        assert np.abs(a.U - b.U.numpy()).max() < 2e-5 and np.abs(a.V - b.V.numpy()).max() < 2e-5
+    A = tf_math.lightgcn_adj(d["train_indptr"], d["train_indices"], nu, ni, "pre")
+    e0 = (rs.randn(nu + ni, 16) * 0.1).astype(np.float32)
+    a = tf_math.LightGCNTrainer(A, e0, nu, 2, 0.01, 1e-3)
+    b = torch_port.LightGCNStep(A, e0, nu, 2, 0.01, 1e-3)
+    for s in range(3):
+        u = rs.randint(0, nu, 200).astype(np.int32); i = rs.randint(0, ni, 200).astype(np.int32); j = rs.randint(0, ni, 200).astype(np.int32)
+        la = a.step(u, i, j)
+        lb = b.step(u.tolist(), i.tolist(), j.tolist())
+        assert abs(float(la[0]) - lb) < 1e-3 * max(1.0, abs(lb))
+    assert np.abs(a.e0 - b.e0.numpy()).max() < 5e-5
