@@ -442,7 +442,8 @@ class MfMl100k:
 class NeumfMl100k:
     name = "neumf-ml100k"
     describe = ("NeuMF (GMF+MLP) on ml-100k, embedding_size=32, layers [64,32,16], conf/NeuMF.properties "
-                "(pointwise cross_entropy, num_neg 4, bs 256, adam 1e-3)")
+                "(pointwise cross_entropy, num_neg 4, bs 256, adam 1e-3): shuffle + negative sampling + the 1570 steps of an "
+                "epoch in ONE persistent cooperative launch")
     pairwise, neg_num = False, 4
     mf_dim, layers, batch, lr, loss, opt = 32, [64, 32, 16], 256, 1e-3, "cross_entropy", "adam"
     KEYS = ("mf_user", "mf_item", "mlp_user", "mlp_item", "dense")
@@ -476,7 +477,8 @@ class NeumfMl100k:
         self.tI = torch.zeros(ni, dtype=torch.int32, device="cuda")
         self.step_loss = torch.zeros(self.spe, device="cuda")
         self.loss_pin = torch.zeros(self.spe).pin_memory()
-        self.lr_sched = adam_lr_schedule(self.lr, 1 << 16)
+        self.ws = [torch.empty(self.n, dtype=torch.int32, device="cuda") for _ in range(3)]
+        self.pows = torch.tensor([0.9, 0.999], device="cuda")
         self.epoch, self.t, self.stamp, self.launches = 0, 0, 1, 0
 
     def run_steps(self, k, e2e=False):
@@ -487,17 +489,15 @@ class NeumfMl100k:
             n = min(k, self.spe)
             if e2e:
                 self.T.upload()
-            cnt = min(n * self.batch, self.n)
-            u, i, t = ops.epoch_build(self.T.ptr, self.T.idx, self.T.users, self.T.idx, self.neg_num,
-                                      self.d["num_items"], False, True, SEED, self.epoch, 0, cnt)
-            ops.ncf_train_epoch(self.shape, self.P, u, i, t, self.batch, False, self.loss, 0.0, 0.0, self.opt,
-                                self.lr_sched[self.t:self.t + n], [self.lr, 0.9, 0.999, 1e-8], self.G, self.S0,
-                                self.S1, self.tU, self.tI, self.stamp, self.step_loss)
+            ops.ncf_epoch_fused(self.shape, self.P, self.T.ptr, self.T.idx, self.T.users, self.T.idx, self.neg_num, False,
+                                True, False, SEED, self.epoch, self.batch, 0, n, self.loss, 0.0, 0.0, self.opt,
+                                [self.lr, 0.9, 0.999, 1e-8], self.pows, self.G, self.S0, self.S1, self.tU, self.tI,
+                                self.stamp, self.ws[0], self.ws[1], self.ws[2], self.step_loss)
             if e2e:
                 self.loss_pin[:n].copy_(self.step_loss[:n], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
                 total += float(self.loss_pin[:n].sum())
-            self.epoch += 1; self.t += n; self.stamp += n; self.launches += 1 + 3 * n
+            self.epoch += 1; self.t += n; self.stamp += n; self.launches += 1
             k -= n
         return total
 
@@ -657,7 +657,7 @@ def measure_small(w, K, W, world, rank, windows, with_cpu=True):
                             "the kernel alone: 40 launches in a CUDA graph, CUDA events on the replay stream, best of 5",
                             {"step_bytes": nbytes / K, "step_note": note, "share_of_step": 6 * st / (ms * 1e-3 / K)})
     else:
-        kname = "mf_epoch_kernel" if isinstance(w, MfMl100k) else "ncf_sample_fast_kernel+ncf_wgrad_kernel+opt_apply_kernel"
+        kname = "mf_epoch_kernel" if isinstance(w, MfMl100k) else "ncf_epoch_kernel"
         roof = hbm_roofline(kname, nbytes, ms * 1e-3, note,
                             "CUDA events around the K timed steps (sampling and shuffling included)",
                             {"honest_bound": "tables are L2-resident (0.7 MB): the step is bound by two grid-wide barriers "
@@ -680,7 +680,7 @@ def measure_small(w, K, W, world, rank, windows, with_cpu=True):
                           "train_model does per epoch); %d call(s) in the timed region" % calls},
            "gpu_launches": w.launches - launches_before if False else None,
            "roofline": roof}
-    out["gpu_launches"] = {MfMl100k: calls, NeumfMl100k: calls + 3 * K, LightgcnGowalla: calls + K * (2 * w.n_layers + 4)}[type(w)]
+    out["gpu_launches"] = {MfMl100k: calls, NeumfMl100k: calls, LightgcnGowalla: calls + K * (2 * w.n_layers + 4)}[type(w)]
     if ev is not None:
         out["eval"] = ev
     if with_cpu:

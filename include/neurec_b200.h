@@ -467,6 +467,26 @@ int nrc_ncf_train_epoch(const nrc_ncf_shape* shape, float* mf_user, float* mf_it
                         int32_t* touched_user, int32_t* touched_item, int32_t first_stamp,
                         float* step_loss, void* stream);
 
+/* Steps [first_step, first_step + num_steps) of one epoch of NeuMF.train_model / MLP.train_model
+ * (NeuMF.py:126-151, MLP.py:100-120) in ONE persistent cooperative launch: the epoch arrays of
+ * nrc_epoch_build (built in the same launch when first_step == 0), then per step the per-sample
+ * tower forward / backward out of shared memory, the weight gradients in fixed summation order and
+ * the TensorFlow-1.12 optimizer over the four tables and the packed dense parameters, with grid-wide
+ * barriers in between.  Arguments as nrc_ncf_train_epoch + the epoch description of
+ * nrc_mf_epoch_fused (adam_pows, workspace arrays i32 [n_samples], step_loss zeroed at first_step 0).
+ * grads[0..3] are the table accumulators (grads[4] is not used: dW never leaves the chip). */
+int nrc_ncf_epoch_fused(const nrc_ncf_shape* shape, float* mf_user, float* mf_item, float* mlp_user,
+                        float* mlp_item, float* dense, const int64_t* train_indptr,
+                        const int32_t* train_indices, const int32_t* pos_users,
+                        const int32_t* pos_items, int64_t n_pos, int32_t neg_num, int32_t pairwise,
+                        int32_t shuffle, int32_t drop_last, uint64_t seed, uint64_t epoch,
+                        int32_t batch_size, int64_t first_step, int64_t num_steps, int32_t loss_kind,
+                        float reg_mf, float reg_mlp, int32_t opt_kind, const float* hyper_host,
+                        float* adam_pows, float* const* grads, float* const* slot0,
+                        float* const* slot1, int32_t* touched_user, int32_t* touched_item,
+                        int32_t first_stamp, int32_t* ws_users, int32_t* ws_items, void* ws_third,
+                        float* step_loss, void* stream);
+
 /* ======================================================================================
  * Graph propagation: CSR SpMM and the LightGCN step
  * ==================================================================================== */

@@ -87,14 +87,22 @@ class _NCFBase(AbstractRecommender):
                                 shuffle=True)
 
     def _train_epoch(self, data_iter):
-        users, items, third = data_iter.device_epoch()
+        """One epoch = ONE persistent launch (nrc_ncf_epoch_fused): shuffle + negative sampling + every
+        batch of NeuMF.py:131-147 / MLP.py:104-120; only the per-step losses come back."""
         steps = len(data_iter)
-        step_loss = torch.empty(max(steps, 1), dtype=torch.float32, device="cuda")
-        ops.ncf_train_epoch(self.shape, self.params, users, items, third, self.batch_size,
-                            self.is_pairwise is True, self._loss, self._reg_mf, self._reg_mlp,
-                            self.opt.kind, self.opt.lr_t(steps), self.opt.hyper, self._G, self._S0,
-                            self._S1, self._tU, self._tI, self.opt.take_stamps(steps), step_loss)
-        return float(step_loss[:steps].sum().item())
+        d, a = data_iter.epoch_args()
+        n = data_iter._n_samples()
+        if getattr(self, "_ws", None) is None or self._ws[0].numel() < n:
+            self._ws = tuple(torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(3))
+        if getattr(self, "_step_loss", None) is None or self._step_loss.numel() < steps:
+            self._step_loss = torch.empty(max(steps, 1), dtype=torch.float32, device="cuda")
+        ops.ncf_epoch_fused(self.shape, self.params, d["ptr"], d["idx"], d["users"], d["pos"], a["neg_num"],
+                            self.is_pairwise is True, a["shuffle"], a["drop_last"], a["seed"], a["epoch"],
+                            self.batch_size, 0, steps, self._loss, self._reg_mf, self._reg_mlp, self.opt.kind,
+                            self.opt.hyper, self.opt.device_pows(), self._G, self._S0, self._S1, self._tU, self._tI,
+                            self.opt.take_stamps(steps), self._ws[0], self._ws[1], self._ws[2], self._step_loss)
+        self.opt.lr_t(steps)              # keep the host mirror of the beta powers in step
+        return float(self._step_loss[:steps].sum().item())
 
     def predict(self, user_ids, candidate_items_user_ids=None):
         # NeuMF.py:158-168: one forward over all items per user (tower 0 = self.output)

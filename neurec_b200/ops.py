@@ -504,6 +504,26 @@ def ncf_train_epoch(shape, P, users, items, third, batch_size, pairwise, loss, r
     return steps
 
 
+def ncf_epoch_fused(shape, P, train_indptr, train_indices, pos_users, pos_items, neg_num, pairwise, shuffle,
+                    drop_last, seed, epoch, batch_size, first_step, num_steps, loss, reg_mf, reg_mlp, opt, hyper,
+                    adam_pows, G, S0, S1, tU, tI, first_stamp, ws_users, ws_items, ws_third, step_loss):
+    """Steps [first_step, first_step + num_steps) of one NeuMF / MLP epoch -- shuffle, negative
+    sampling and every step -- in one persistent cooperative launch (nrc_ncf_epoch_fused)."""
+    k = ("mf_user", "mf_item", "mlp_user", "mlp_item", "dense")
+    h = np.zeros(4, dtype=np.float32)
+    h[:len(hyper)] = hyper
+    PA = ctypes.c_void_p * 5
+    arr = lambda D: ctypes.cast(PA(*[(D[x].data_ptr() if D.get(x) is not None else None) for x in k]),
+                                ctypes.c_void_p)
+    check(_lib.load().nrc_ncf_epoch_fused(
+        ctypes.byref(shape), *[_p(P[x]) for x in k], _p(train_indptr), _p(train_indices), _p(pos_users),
+        _p(pos_items), pos_users.numel(), int(neg_num), 1 if pairwise else 0, 1 if shuffle else 0,
+        1 if drop_last else 0, int(seed), int(epoch), int(batch_size), int(first_step), int(num_steps),
+        LOSS_IDS[loss], float(reg_mf), float(reg_mlp), OPT_IDS[opt], h.ctypes.data, _p(adam_pows), arr(G), arr(S0),
+        arr(S1), _p(tU), _p(tI), int(first_stamp), _p(ws_users), _p(ws_items), _p(ws_third), _p(step_loss), _stream()))
+    _count()
+
+
 def mf_train_epoch(U, V, users, items, third, batch_size, pairwise, loss, reg, opt, lr_t, hyper,
                    gU, gV, tU, tV, s0U, s1U, s0V, s1V, first_stamp, step_loss):
     n = users.numel()

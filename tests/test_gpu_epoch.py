@@ -241,3 +241,57 @@ def test_csr_fed_sgd_kernel_with_repeated_rows_sums_every_contribution():
     assert abs(float(loss) - float(g_all[0])) < 1e-3 * float(g_all[0])
     assert np.abs(dU.cpu().numpy() - (U0 - np.float32(lr) * g_all[1])).max() < 5e-6
     assert np.abs(dV.cpu().numpy() - (V0 - np.float32(lr) * g_all[2])).max() < 5e-6
+
+
+@pytest.mark.parametrize("pairwise,loss,opt,mf_dim,layers,steps", [
+    (False, "cross_entropy", "adam", 32, [64, 32, 16], 40),     # BASELINE configs[1] (conf/NeuMF.properties + embedding 32)
+    (True, "bpr", "adam", 16, [64, 32, 16], 12),                # pairwise NeuMF: two differently-initialised towers
+    (True, "bpr", "adam", 0, [64, 32, 16], 10),                 # MLP pairwise: shared tower, both passes feed dW
+    (False, "square", "rmsprop", 8, [32, 16], 8),               # another tower shape, touched-row optimizer
+    (False, "cross_entropy", "gd", 4, [48, 24], 6),             # widths that take the generic layer paths
+])
+def test_fused_ncf_epoch_matches_the_oracle_trainer(ml100k, pairwise, loss, opt, mf_dim, layers, steps):
+    """nrc_ncf_epoch_fused (sampler + shuffle + every NeuMF / MLP step in one persistent launch) vs
+    tf_math.NCFTrainer on the epoch arrays of oracle.epoch_build."""
+    from neurec_b200 import ops
+    from test_gpu_ncf import make_params, KEYS
+    d = ml100k
+    nu, ni, bs = d["num_users"], d["num_items"], 256
+    nt = 2 if (pairwise and mf_dim == 16) else 1
+    neg_num = 1 if pairwise else 4
+    P, mlp_dim = make_params(nu, ni, mf_dim, layers, nt, 7, scale=0.01)
+    pu, pi = _flat(d)
+    wu, wi, wt = oracle.epoch_build(d["train_indptr"], d["train_indices"], pu, pi, neg_num, ni, pairwise, True, 77, 5)
+    if pairwise:
+        wt = wt[:, 0]
+    n = len(wu)
+    lr = 1e-3 if opt == "adam" else 1e-2
+    tr = tf_math.NCFTrainer(P, mlp_dim, layers, nt, opt, lr, loss, 1e-4, 1e-4, pairwise)
+    want = tr.epoch(wu[:steps * bs], wi[:steps * bs], wt[:steps * bs], bs)
+    shape = ops.NcfShape.make(nu, ni, mf_dim, layers, nt)
+    dP = {k: (dev(v) if v is not None else None) for k, v in P.items()}
+    i0, i1 = tf_math.SLOT_INIT[opt]
+    mk = lambda val: {k: (None if v is None or val is None else torch.full_like(v, val)) for k, v in dP.items()}
+    G, S0, S1 = mk(0.0), mk(i0), mk(i1)
+    tU = torch.zeros(nu, dtype=torch.int32, device="cuda"); tI = torch.zeros(ni, dtype=torch.int32, device="cuda")
+    total_steps = (n + bs - 1) // bs
+    step_loss = torch.full((total_steps,), 3.0, device="cuda")
+    ws = tuple(torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(3))
+    pows = torch.tensor([0.9, 0.999], device="cuda") if opt == "adam" else None
+    args = (shape, dP, dev(d["train_indptr"]), dev(d["train_indices"]), dev(pu), dev(pi), neg_num, pairwise, True, False,
+            77, 5, bs)
+    tail = (loss, 1e-4, 1e-4, opt, tf_math.DEFAULT_HYPER[opt](lr), pows, G, S0, S1, tU, tI)
+    cut = steps // 2                                                 # the epoch cut into two calls
+    ops.ncf_epoch_fused(*args, 0, cut, *tail, 1, ws[0], ws[1], ws[2], step_loss)
+    ops.ncf_epoch_fused(*args, cut, steps - cut, *tail, 1 + cut, ws[0], ws[1], ws[2], step_loss)
+    got = step_loss.cpu().numpy()
+    assert np.array_equal(ws[0].cpu().numpy(), wu) and np.array_equal(ws[1].cpu().numpy(), wi)
+    assert np.allclose(got[:steps], want, rtol=2e-4, atol=1e-6), np.abs(got[:steps] - want).max()
+    assert (got[steps:] == 0).all()
+    for k in KEYS:
+        if P[k] is not None:
+            assert np.abs(dP[k].cpu().numpy() - tr.P[k]).max() < 3e-5, k
+    assert np.abs(tr.P["dense"] - P["dense"]).max() > 1e-5          # the towers really moved
+    for k in KEYS[:4]:
+        if G[k] is not None:
+            assert float(G[k].abs().max()) == 0.0                    # accumulators left clean
