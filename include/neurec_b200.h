@@ -197,6 +197,25 @@ int nrc_mf_scores(const float* user_table, const float* item_table, int32_t dim,
 int nrc_mask_rows(float* scores, int32_t rating_len, int32_t num_rows, const int32_t* users,
                   const int64_t* train_indptr, const int32_t* train_indices, void* stream);
 
+/* Item-sharded evaluation (catalogues that exceed one GPU): the pieces around the
+ * per-shard nrc_eval_mf call.  Replaces MF.predict + cpp_evaluate_matrix (MF.py:120-122,
+ * evaluate.h:23-72) when the item table is cut into row blocks over ranks.
+ *   nrc_mf_score_pairs        exact fp32 scores (the evaluators' FMA chain) of C candidate items per
+ *                             row; user_rows f32 [num_rows, dim] are the batch's gathered user rows,
+ *                             items i32 [num_rows, C] index item_table (-1 = none), the train CSR is
+ *                             indexed by ROW in the same id space; masked / missing -> -inf
+ *   nrc_eval_merge_candidates per row the K best of C (score, GLOBAL id) candidates in (score desc,
+ *                             id asc) order + the metrics of metric.h on them; *tie_count += rows
+ *                             with equal scores inside their top K+1 (there the reference's order
+ *                             depends on its heap and only the score sequence is guaranteed equal) */
+int nrc_mf_score_pairs(const float* user_rows, const float* item_table, int32_t dim,
+                       const int32_t* items, int32_t num_rows, int32_t C, const int64_t* train_indptr,
+                       const int32_t* train_indices, float* out, void* stream);
+int nrc_eval_merge_candidates(const int32_t* cand_ids, const float* cand_scores, int32_t C,
+                              int32_t num_rows, const int64_t* test_indptr, const int32_t* test_indices,
+                              const int32_t* metric_host, int32_t metric_num, int32_t top_k,
+                              float* results, int32_t* ranks, int32_t* tie_count, void* stream);
+
 /* np.mean(all_user_result, axis=0) in fp32, evaluator/backend/cpp/uni_evaluator.py:150:
  * out[c] = (sequential fp32 sum over rows of results[:, c]) / num_rows, bit-identical to
  * numpy's axis-0 reduction order. */

@@ -1399,6 +1399,144 @@ extern "C" int nrc_eval_mf_tc(const float* user_table, const float* item_table, 
     return NRC_OK;
 }
 
+// ----------------------------------------------------------------------------------------
+// Item-sharded evaluation (tables that exceed one GPU).  Every rank scores its own item
+// shard (nrc_eval_mf on the shard, top_k + 1 ranks only), re-scores those few candidates exactly
+// (nrc_mf_score_pairs), the [B, K+1] (score, global id) lists of all ranks are all-gathered and the
+// user's home rank merges them (nrc_eval_merge_candidates).  For a user without exact score ties
+// inside its global top K+1 the merged ranking IS the reference's (evaluate.h:23-50: the K largest
+// scores in descending order -- each of them is among the K+1 best of its own shard); users with
+// such ties are counted (*tie_count) and ranked score-descending, id-ascending (the
+// reference's own order among equal scores is an artefact of its heap).
+// ----------------------------------------------------------------------------------------
+namespace nrc {
+
+__global__ void mf_score_pairs_kernel(const float* __restrict__ Urows, const float* __restrict__ V, int D,
+                                      const int32_t* __restrict__ items, int C, int64_t total,
+                                      const int64_t* __restrict__ train_ptr, const int32_t* __restrict__ train_idx,
+                                      float* __restrict__ out) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = e / C;
+        const int item = items[e];
+        float s = -INFINITY;
+        if (item >= 0) {
+            const int64_t t0 = train_ptr[b];
+            if (!sorted_contains(train_idx + t0, train_ptr[b + 1] - t0, item))
+                s = tc_exact_score(reinterpret_cast<const float4*>(Urows + (size_t)b * D), V, item, D);
+        }
+        out[e] = s;
+    }
+}
+
+// (score desc, id asc) order on pairs
+__device__ __forceinline__ bool pair_before(float sa, int ia, float sb, int ib) {
+    return sa > sb || (sa == sb && ia < ib);
+}
+
+constexpr int kMergePerLane = 16;   // candidates per lane: C <= 512
+
+__global__ void __launch_bounds__(256)
+eval_merge_kernel(const int32_t* __restrict__ cand_ids, const float* __restrict__ cand_scores, int C, int num_rows,
+                  const int64_t* __restrict__ test_ptr, const int32_t* __restrict__ test_idx, int K, int M,
+                  float* __restrict__ results, int32_t* __restrict__ ranks, int32_t* __restrict__ tie_count) {
+    extern __shared__ int smem_i[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int row = blockIdx.x * wpb + warp;
+    if (row >= num_rows) return;
+    int* rank = smem_i + warp * 4 * K;
+    float sc[kMergePerLane];
+    int id[kMergePerLane];
+#pragma unroll
+    for (int q = 0; q < kMergePerLane; ++q) {
+        const int c = q * 32 + lane;
+        const bool ok = c < C;
+        sc[q] = ok ? cand_scores[(size_t)row * C + c] : -INFINITY;
+        id[q] = ok ? cand_ids[(size_t)row * C + c] : INT32_MAX;
+        if (sc[q] == -INFINITY) id[q] = INT32_MAX;        // masked / padding entries never win a tie
+    }
+    bool tie = false;
+    float prev = INFINITY;
+    for (int r = 0; r <= K; ++r) {                        // K picks + one more to see a tie at the cut
+        float bs = -INFINITY; int bi = INT32_MAX, bq = -1;
+#pragma unroll
+        for (int q = 0; q < kMergePerLane; ++q)
+            if (pair_before(sc[q], id[q], bs, bi)) { bs = sc[q]; bi = id[q]; bq = q; }
+        float ws = bs; int wi = bi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float os = __shfl_xor_sync(kFull, ws, o);
+            const int oi = __shfl_xor_sync(kFull, wi, o);
+            if (pair_before(os, oi, ws, wi)) { ws = os; wi = oi; }
+        }
+        if (ws == prev || ws == -INFINITY) tie = true;    // equal scores inside the top K+1, or too few items
+        prev = ws;
+        if (r < K) {
+            if (lane == 0) rank[r] = (wi == INT32_MAX) ? -1 : wi;
+            if (bq >= 0 && bs == ws && bi == wi) {        // the owner retires its entry
+#pragma unroll
+                for (int q = 0; q < kMergePerLane; ++q)
+                    if (q == bq) { sc[q] = -INFINITY; id[q] = INT32_MAX; }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0 && tie && tie_count) atomicAdd(tie_count, 1);
+    if (ranks) for (int i = lane; i < K; i += kWarp) ranks[(size_t)row * K + i] = rank[i];
+    if (results) {
+        const int64_t t0 = test_ptr[row];
+        const int T = (int)(test_ptr[row + 1] - t0);
+        int* s_cnt = rank + K;
+        float* s_sum_pre = reinterpret_cast<float*>(s_cnt + K);
+        float* s_dcg = s_sum_pre + K;
+        metrics_for_user(rank, K, test_idx + t0, T, s_cnt, s_sum_pre, s_dcg, M, results + (size_t)row * M * K, lane);
+    }
+}
+
+}  // namespace nrc
+
+// Exact fp32 scores (the FMA chain every evaluator kernel uses) of C candidate items per row:
+// user_rows f32 [num_rows, dim] (already gathered), items i32 [num_rows, C] ids INTO item_table
+// (-1 = none), train CSR indexed by ROW (not by user id) in the same id space as `items`; a masked or
+// missing candidate scores -inf.  out f32 [num_rows, C].
+extern "C" int nrc_mf_score_pairs(const float* user_rows, const float* item_table, int32_t dim, const int32_t* items,
+                                  int32_t num_rows, int32_t C, const int64_t* train_indptr,
+                                  const int32_t* train_indices, float* out, void* stream) {
+    NRC_REQUIRE(dim > 0 && dim % 4 == 0, NRC_E_LIMIT, "dim %d must be a positive multiple of 4", dim);
+    NRC_REQUIRE(num_rows >= 0 && C > 0, NRC_E_VALUE, "bad shape");
+    if (num_rows == 0) return NRC_OK;
+    const int64_t total = (int64_t)num_rows * C;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    mf_score_pairs_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(user_rows, item_table, dim, items, C, total,
+                                                                           train_indptr, train_indices, out);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+// Merge of per-shard candidate lists + metrics: cand_ids i32 / cand_scores f32 [num_rows, C] (GLOBAL
+// item ids; -inf scores are ignored), test CSR indexed by ROW with global item ids.  results f32
+// [num_rows, metric_num * top_k] (metric-major, as nrc_eval_score_matrix), ranks i32 [num_rows, top_k]
+// (optional), *tie_count += rows whose top K+1 held equal scores or fewer than K+1 items (optional).
+extern "C" int nrc_eval_merge_candidates(const int32_t* cand_ids, const float* cand_scores, int32_t C,
+                                         int32_t num_rows, const int64_t* test_indptr, const int32_t* test_indices,
+                                         const int32_t* metric_host, int32_t metric_num, int32_t top_k,
+                                         float* results, int32_t* ranks, int32_t* tie_count, void* stream) {
+    NRC_REQUIRE(top_k > 0 && top_k <= kMaxTopK, NRC_E_LIMIT, "top_k %d outside [1, %d]", top_k, kMaxTopK);
+    NRC_REQUIRE(C > top_k && C <= 32 * kMergePerLane, NRC_E_LIMIT, "C = %d candidates per row outside (top_k, %d]", C,
+                32 * kMergePerLane);
+    int rc = check_metrics(metric_host, metric_num);
+    if (rc) return rc;
+    if (num_rows <= 0) return NRC_OK;
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * 4 * top_k * 4 > 96 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * 4 * top_k * 4;
+    eval_merge_kernel<<<(num_rows + warps - 1) / warps, warps * 32, smem, as_stream(stream)>>>(
+        cand_ids, cand_scores, C, num_rows, test_indptr, test_indices, top_k, metric_num, results, ranks, tie_count);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
 extern "C" int nrc_mean_rows(const float* results, int64_t num_rows, int32_t num_cols,
                              float* out, void* stream) {
     NRC_REQUIRE(num_cols >= 0 && num_rows >= 0, NRC_E_VALUE, "negative shape");

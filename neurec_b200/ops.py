@@ -135,6 +135,35 @@ def eval_mf_tc(user_table, item_table, users, train_indptr, train_indices, test_
     return (res, ranks) if return_ranks else res
 
 
+def mf_score_pairs(user_rows, item_table, items, train_indptr, train_indices):
+    """Exact fp32 scores of `items` [B, C] (ids into item_table, -1 = none) for the gathered user rows
+    [B, dim]; masked (train CSR indexed by ROW) or missing candidates score -inf (nrc_mf_score_pairs)."""
+    _req(user_rows, torch.float32, "user_rows"); _req(item_table, torch.float32, "item_table")
+    _req(items, torch.int32, "items")
+    B, C = items.shape
+    out = torch.empty((B, C), dtype=torch.float32, device=items.device)
+    check(_lib.load().nrc_mf_score_pairs(_p(user_rows), _p(item_table), item_table.shape[1], _p(items), B, C,
+                                         _p(train_indptr), _p(train_indices), _p(out), _stream()))
+    _count()
+    return out
+
+
+def eval_merge_candidates(cand_ids, cand_scores, test_indptr, test_indices, metric, top_k, return_ranks=False):
+    """Per row the top_k of C (score, global id) candidates + metrics (nrc_eval_merge_candidates).
+    Returns (results, [ranks,] tie_count tensor)."""
+    _req(cand_ids, torch.int32, "cand_ids"); _req(cand_scores, torch.float32, "cand_scores")
+    B, C = cand_ids.shape
+    m = _metric_arr(metric)
+    res = torch.empty((B, len(m) * top_k), dtype=torch.float32, device=cand_ids.device)
+    ranks = torch.empty((B, top_k), dtype=torch.int32, device=cand_ids.device) if return_ranks else None
+    ties = torch.zeros(1, dtype=torch.int32, device=cand_ids.device)
+    check(_lib.load().nrc_eval_merge_candidates(_p(cand_ids), _p(cand_scores), C, B, _p(test_indptr), _p(test_indices),
+                                                m.ctypes.data, len(m), int(top_k), _p(res), _p(ranks), _p(ties),
+                                                _stream()))
+    _count()
+    return (res, ranks, ties) if return_ranks else (res, ties)
+
+
 TC_MIN_ITEMS = 16384     # measured crossover on B200: 8 192 users x 16 384 items, d=64 -> 1.8x; see profiles/dbg_tc_crossover.py
 
 

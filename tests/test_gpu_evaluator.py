@@ -222,3 +222,61 @@ def test_full_size_properties_gowalla_shape():
     for row, u in enumerate(us[:128]):
         sc = Sh[row][ranks_h[u]]
         assert np.all(sc[:-1] >= sc[1:] - 1e-4)
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+def test_item_sharded_evaluation_is_bit_identical_for_any_shard_count(G):
+    """the item table cut into G row blocks; per shard the K+1 best unmasked items of every
+    user (nrc_eval_mf on the shard + exact re-score), merged on the home rank -> the SAME ranks and
+    metric rows as the unsharded evaluator and the C oracle, for G = 1, 2, 4, 8 (the shards are run one
+    after the other here; tests/mgpu_eval_sharded_check.py runs them on real ranks with NCCL)."""
+    from neurec_b200 import ops
+    from neurec_b200.evaluator import sharded
+    nu, ni, dim, K = 300, 5003, 64, 20
+    rs = np.random.RandomState(G)
+    U = (rs.randn(nu, dim) * 0.1).astype(np.float32); V = (rs.randn(ni, dim) * 0.1).astype(np.float32)
+    tp, ti = random_csr(rs, nu, ni, rs.randint(1, 120, nu))
+    sp, si = random_csr(rs, nu, ni, rs.randint(1, 12, nu))
+    users = np.arange(nu, dtype=np.int32)
+    want, wranks = oracle.eval_mf(U, V, users, tp, ti, sp, si, ALL, K, thread_num=4, return_ranks=True)
+    per = (ni + G - 1) // G
+    shards = []
+    for g in range(G):
+        lo, hi = g * per, min(ni, (g + 1) * per)
+        lp, li = sharded.ItemShard.restrict_csr(tp, ti, lo, hi)
+        shards.append(sharded.ItemShard(dev(V[lo:hi]), lo, dev(lp), dev(li)))
+    user_lo, B = 37, 200                                       # a batch of consecutive users
+    rows = dev(U[user_lo:user_lo + B])
+    ids, scs = zip(*[sharded.shard_candidates(rows, sh, user_lo, K) for sh in shards])
+    res, ranks, ties = sharded.merge_and_score(list(ids), list(scs), dev(sp), dev(si), user_lo, ALL, K, return_ranks=True)
+    assert int(ties.item()) == 0                               # random fp32 scores: no exact ties
+    assert np.array_equal(ranks.cpu().numpy(), wranks[user_lo:user_lo + B])
+    assert np.array_equal(res.cpu().numpy(), want[user_lo:user_lo + B])
+
+
+def test_item_sharded_evaluation_flags_ties_and_tiny_shards():
+    from neurec_b200 import ops
+    from neurec_b200.evaluator import sharded
+    nu, ni, dim, K = 40, 64, 64, 5
+    rs = np.random.RandomState(3)
+    U = rs.randint(-1, 2, (nu, dim)).astype(np.float32); V = rs.randint(-1, 2, (ni, dim)).astype(np.float32)   # ties everywhere
+    tp, ti = random_csr(rs, nu, ni, rs.randint(0, 30, nu))
+    sp, si = random_csr(rs, nu, ni, rs.randint(1, 6, nu))
+    shards = []
+    for g in range(16):                                        # 4 items per shard < K + 1
+        lo, hi = g * 4, (g + 1) * 4
+        lp, li = sharded.ItemShard.restrict_csr(tp, ti, lo, hi)
+        shards.append(sharded.ItemShard(dev(V[lo:hi]), lo, dev(lp), dev(li)))
+    rows = dev(U)
+    ids, scs = zip(*[sharded.shard_candidates(rows, sh, 0, K) for sh in shards])
+    res, ranks, ties = sharded.merge_and_score(list(ids), list(scs), dev(sp), dev(si), 0, ALL, K, return_ranks=True)
+    assert int(ties.item()) > 0
+    # whatever the order among equal scores, the SCORE sequence of the top K equals the oracle's
+    s = oracle.mf_scores(U, V, np.arange(nu, dtype=np.int32))
+    oracle.mask_train(s, np.arange(nu, dtype=np.int32), tp, ti)
+    got = ranks.cpu().numpy()
+    for b in range(nu):
+        want_scores = np.sort(s[b])[::-1][:K]
+        mine = np.array([s[b, i] if i >= 0 else -np.inf for i in got[b]])
+        assert np.array_equal(mine, want_scores), b
+        assert not set(got[b][got[b] >= 0].tolist()) & set(ti[tp[b]:tp[b + 1]].tolist())
