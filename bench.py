@@ -899,9 +899,17 @@ def measure_synth_eval(K, W, world, rank, windows, with_cpu=True):
         return (torch.arange(nu + 1, device="cuda", dtype=torch.int64) * deg), idx.reshape(-1).contiguous()
     tp, ti = csr(50, 6)
     sp, si = csr(10, 7)
+    # trained-looking user rows: noise + a multiple of the mean of 3 of the user's held-out items, so that
+    # the truth items really sit among the top-K and the metric epilogue is exercised with hits
+    for a in range(0, nu, 1 << 18):
+        b = min(nu, a + (1 << 18))
+        held = si.view(nu, 10)[a:b, :3].long()
+        U[a:b] += V[held.reshape(-1)].view(b - a, 3, dim).mean(1) * 4.0
+    del held
     batch = lambda s: (torch.arange(ub, device="cuda", dtype=torch.int64)
                        + (rank * (K + W) + s) * ub).remainder(nu).to(torch.int32)
     step = lambda users: ops.eval_mf_tc(U, V, users, tp, ti, sp, si, METRICS, topk)
+    ops.eval_tc_items_version(1)     # ONE evaluation in user batches: the bf16 item table is converted once, not per step
     for s in range(W):
         step(batch(s))
     torch.cuda.synchronize()
@@ -997,6 +1005,7 @@ def measure_synth_eval(K, W, world, rank, windows, with_cpu=True):
                                          "restatement of MF.predict + the reference's C++ evaluator (OpenMP/AVX2, %d "
                                          "threads)" % (n_cpu, threads),
                                "bit_identical_to_gpu": bool(np.array_equal(got, want))}
+    ops.eval_tc_items_version(0)
     del U, V
     torch.cuda.empty_cache()
     return out

@@ -173,6 +173,12 @@ int nrc_eval_mf_tc(const float* user_table, const float* item_table, int32_t dim
                    const int64_t* test_indptr, const int32_t* test_indices,
                    const int32_t* metric_host, int32_t metric_num, int32_t top_k, int32_t cand_cap,
                    float* results, int32_t* ranks, void* stream);
+/* nrc_eval_mf_tc keeps a bf16 copy of the item table (and its largest row norm).  By default it is
+ * rebuilt on every call; a caller that evaluates ONE fixed model in several calls (user batches) sets
+ * a non-zero version first: the copy is then reused while (item_table pointer, shape, version) stay
+ * the same.  Change the version (or pass 0) whenever the table's contents change. */
+int nrc_eval_tc_items_version(uint64_t version);
+
 /* Measurement hook: CUDA-event duration (ms, on the launching stream) and algorithmic flops
  * (2 * users * items * dim) of the last tcgen05 candidate-kernel launch made by nrc_eval_mf_tc;
  * waits for that launch.  bench.py derives the tensor-pipe roofline fraction from it. */

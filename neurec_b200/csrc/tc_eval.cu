@@ -619,9 +619,18 @@ static double g_last_flops = 0.0;
 
 static size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// The bf16 copy + max row norm are reused across calls while the caller vouches that the table has
+// not changed: nrc_eval_tc_items_version(v != 0) keys the cache on (pointer, shape, v); version 0
+// (default) converts on every call.
+static uint64_t g_items_version = 0, g_cached_version = 0;
+static const float* g_cached_ptr = nullptr;
+
 int prepare_items(const float* V, int D, int N, cudaStream_t st) {
     NRC_REQUIRE(D % 64 == 0 && D >= 64 && D <= 256, NRC_E_LIMIT,
                 "the tensor-core pass needs dim in {64, 128, 192, 256} (got %d)", D);
+    if (g_items_version != 0 && g_cached_version == g_items_version && g_cached_ptr == V && g_items_n == N &&
+        g_items_d == D && g_vb != nullptr)
+        return NRC_OK;
     const size_t o_vmax = up256((size_t)N * D * 2);
     int rc = g_items.reserve(o_vmax + 256);
     if (rc) return rc;
@@ -632,6 +641,7 @@ int prepare_items(const float* V, int D, int N, cudaStream_t st) {
     tc_prepare_items_kernel<<<sm_count() * 8, 256, 0, st>>>(V, N, D, Vb, g_vmax);
     NRC_CUDA_CHECK(cudaGetLastError());
     g_vb = Vb; g_items_n = N; g_items_d = D;
+    g_cached_ptr = V; g_cached_version = g_items_version;
     return NRC_OK;
 }
 
@@ -755,6 +765,14 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
 
 }  // namespace tc
 }  // namespace nrc
+
+// Evaluations of one fixed model in several calls (user batches) share the bf16 item table: set a
+// non-zero version before the first call and keep it while the table is unchanged; any other value
+// (or 0 = never cache) makes the next call convert again.
+extern "C" int nrc_eval_tc_items_version(uint64_t version) {
+    nrc::tc::g_items_version = version;
+    return NRC_OK;
+}
 
 // Duration (CUDA events on the launching stream) and algorithmic flops (2 * users * items * dim)
 // of the last tcgen05 candidate-kernel launch; waits for that launch to finish.

@@ -187,6 +187,12 @@ def eval_mf_auto(user_table, item_table, users, train_indptr, train_indices, tes
                    metric, top_k, return_ranks)
 
 
+def eval_tc_items_version(version):
+    """Non-zero: eval_mf_tc reuses its bf16 item-table copy while (table pointer, shape, version) are
+    unchanged (one fixed model evaluated in several user batches); 0: convert on every call."""
+    check(_lib.load().nrc_eval_tc_items_version(int(version)))
+
+
 def eval_tc_last_launch():
     """(kernel_ms, flops) of the last tcgen05 candidate-kernel launch made by eval_mf_tc."""
     import ctypes
