@@ -565,6 +565,51 @@ int nrc_lightgcn_train_epoch(const int64_t* indptr, const int32_t* indices, cons
                              float* grad_e0, float* work_a, float* work_b, float* step_loss2,
                              void* stream);
 
+/* ======================================================================================
+ * NGCF: dense part of the propagation layer
+ * ==================================================================================== */
+
+/* NGCF.__init__ / _init_weights, NGCF.py:14-44, 262-284 (alg_type 'ngcf').  Weights are one packed
+ * f32 buffer: per layer W_gc [d_k, d_k+1] row-major, b_gc [d_k+1], W_bi [d_k, d_k+1], b_bi [d_k+1]
+ * (nrc_ngcf_weights_size floats).  Widths up to 64, up to 4 layers. */
+typedef struct nrc_ngcf_shape {
+    int32_t num_users, num_items;
+    int32_t emb_dim;
+    int32_t n_layers;
+    int32_t layers[4];
+} nrc_ngcf_shape;
+
+int nrc_ngcf_weights_size(const nrc_ngcf_shape* shape);
+int64_t nrc_ngcf_work_floats(const nrc_ngcf_shape* shape);   /* size of the `work` buffer below */
+
+/* tf.nn.dropout's keep mask (NGCF.py:193, always on): out[e] = 1.0 with probability keep, else 0.0;
+ * counter-based Philox4x32-10 keyed by (seed, stream_id).  out f32 [n]. */
+int nrc_dropout_mask(int64_t n, float keep, uint64_t seed, uint64_t stream_id, float* out, void* stream);
+
+/* _create_ngcf_embed, NGCF.py:160-202: per layer side = A_hat.ego (the CSR of get_adj_mat, NGCF.py:
+ * 299-332; the n_fold slabs of :174-179 are one product), leaky_relu(side W_gc + b_gc) +
+ * leaky_relu((ego*side) W_bi + b_bi), dropout with the given masks (f32 0/1, layer k's [N, d_k+1]
+ * block after the previous ones; NULL = keep everything), l2_normalize, concatenation.
+ * all_emb f32 [N, emb_dim + sum(layers)], users first. */
+int nrc_ngcf_forward(const nrc_ngcf_shape* shape, const int64_t* indptr, const int32_t* indices,
+                     const float* values, const int32_t* row_order, const float* e0,
+                     const float* weights, const float* masks, float keep, float* all_emb,
+                     float* work, void* stream);
+
+/* Loss and gradients of one batch, NGCF.py:94-110 + the backward of :160-202: forward as above, then
+ * sum softplus(-(pos - neg)) + reg * l2_loss(u, i, j) on the concatenated rows, back through
+ * normalise / dropout / leaky-relu / both GEMMs / SpMM (t_* = CSR of A_hat^T, NULL when symmetric).
+ * grad_all f32 [N, d_total] must be zero on entry and is zero on return; grad_e0 f32 [N, emb_dim]
+ * and grad_weights f32 [weights_size] are overwritten; loss2 f32 [2] += {mf_loss, emb_loss}.
+ * Apply them with nrc_opt_apply_multi (dense-gradient formulas, like every variable of NGCF). */
+int nrc_ngcf_grad(const nrc_ngcf_shape* shape, const int64_t* indptr, const int32_t* indices,
+                  const float* values, const int32_t* row_order, const int64_t* t_indptr,
+                  const int32_t* t_indices, const float* t_values, const int32_t* t_row_order,
+                  const float* e0, const float* weights, const float* masks, float keep,
+                  const int32_t* users, const int32_t* pos_items, const int32_t* neg_items,
+                  int64_t batch, float reg, float* all_emb, float* grad_all, float* grad_e0,
+                  float* grad_weights, float* work, float* loss2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ def resolve_model(recommender):
     name = "neurec_b200.model.general_recommender." + recommender
     if importlib.util.find_spec(name) is None:
         raise ImportError("recommender '%s' is outside the accelerated hot path "
-                          "(available: MF, MLP, NeuMF, LightGCN)" % recommender)
+                          "(available: MF, MLP, NeuMF, LightGCN, NGCF)" % recommender)
     return getattr(importlib.import_module(name), recommender)
 
 

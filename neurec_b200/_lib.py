@@ -35,7 +35,7 @@ def declared_functions(header: str = HEADER):
     text = open(header).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     out = {}
-    for m in re.finditer(r"(const char\*|int)\s+(nrc_\w+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"(const char\*|int64_t|int)\s+(nrc_\w+)\s*\(([^)]*)\)\s*;", text):
         ret, name, args = m.group(1), m.group(2), m.group(3)
         argtypes = []
         args = args.strip()
@@ -47,7 +47,7 @@ def declared_functions(header: str = HEADER):
                 else:
                     ty = a.replace("const", "").split()[0]
                     argtypes.append(_CT[ty])
-        out[name] = (ctypes.c_char_p if ret.startswith("const char") else ctypes.c_int, argtypes)
+        out[name] = ({"const char*": ctypes.c_char_p, "int64_t": ctypes.c_int64}.get(ret, ctypes.c_int), argtypes)
     return out
 
 

@@ -574,3 +574,74 @@ def mf_train_epoch(U, V, users, items, third, batch_size, pairwise, loss, reg, o
         _p(s0V), _p(s1V), int(first_stamp), _p(step_loss), _stream()))
     _count(2 * steps)
     return steps
+
+
+# ------------------------------------------------------------------------------------ NGCF
+class NgcfShape(ctypes.Structure):
+    """ctypes mirror of nrc_ngcf_shape (include/neurec_b200.h)."""
+    _fields_ = [("num_users", ctypes.c_int32), ("num_items", ctypes.c_int32), ("emb_dim", ctypes.c_int32),
+                ("n_layers", ctypes.c_int32), ("layers", ctypes.c_int32 * 4)]
+
+    @classmethod
+    def make(cls, num_users, num_items, emb_dim, layers):
+        layers = list(layers)
+        if not 1 <= len(layers) <= 4:
+            raise ValueError("NGCF supports 1 to 4 propagation layers")
+        s = cls()
+        s.num_users, s.num_items, s.emb_dim, s.n_layers = int(num_users), int(num_items), int(emb_dim), len(layers)
+        for i, v in enumerate(layers):
+            s.layers[i] = int(v)
+        return s
+
+    @property
+    def n_nodes(self):
+        return self.num_users + self.num_items
+
+    @property
+    def d_total(self):
+        return self.emb_dim + sum(self.layers[i] for i in range(self.n_layers))
+
+    def weights_size(self):
+        n = _lib.load().nrc_ngcf_weights_size(ctypes.byref(self))
+        check(n if n < 0 else 0)
+        return n
+
+    def work_floats(self):
+        n = _lib.load().nrc_ngcf_work_floats(ctypes.byref(self))
+        check(int(n) if n < 0 else 0)
+        return int(n)
+
+    def mask_floats(self):
+        return self.n_nodes * sum(self.layers[i] for i in range(self.n_layers))
+
+
+def dropout_mask(n, keep, seed, stream_id, out=None, device="cuda"):
+    """tf.nn.dropout's keep mask (1.0 with probability keep) from the counter-based generator."""
+    if out is None:
+        out = torch.empty((int(n),), dtype=torch.float32, device=device)
+    check(_lib.load().nrc_dropout_mask(int(n), float(keep), int(seed), int(stream_id), _p(out), _stream()))
+    _count()
+    return out
+
+
+def ngcf_forward(shape, csr, row_order, e0, weights, masks, keep, all_emb=None, work=None):
+    """_create_ngcf_embed (NGCF.py:160-202): the concatenated embeddings [N, d_total]."""
+    if all_emb is None:
+        all_emb = torch.empty((shape.n_nodes, shape.d_total), dtype=torch.float32, device=e0.device)
+    if work is None:
+        work = torch.empty(shape.work_floats(), dtype=torch.float32, device=e0.device)
+    check(_lib.load().nrc_ngcf_forward(ctypes.byref(shape), _p(csr[0]), _p(csr[1]), _p(csr[2]), _p(row_order), _p(e0),
+                                       _p(weights), _p(masks), float(keep), _p(all_emb), _p(work), _stream()))
+    _count(2 * shape.n_layers + 1)
+    return all_emb
+
+
+def ngcf_grad(shape, csr, row_order, t_csr, t_row_order, e0, weights, masks, keep, users, pos, neg, reg, all_emb,
+              grad_all, grad_e0, grad_weights, work, loss2):
+    """Loss + gradients of one NGCF batch (nrc_ngcf_grad)."""
+    t = t_csr if t_csr is not None else (None, None, None)
+    check(_lib.load().nrc_ngcf_grad(ctypes.byref(shape), _p(csr[0]), _p(csr[1]), _p(csr[2]), _p(row_order), _p(t[0]),
+                                    _p(t[1]), _p(t[2]), _p(t_row_order), _p(e0), _p(weights), _p(masks), float(keep),
+                                    _p(users), _p(pos), _p(neg), users.numel(), float(reg), _p(all_emb), _p(grad_all),
+                                    _p(grad_e0), _p(grad_weights), _p(work), _p(loss2), _stream()))
+    _count(4 * shape.n_layers + 4)
