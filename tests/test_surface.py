@@ -264,6 +264,7 @@ def _write_synthetic_dataset(path, nu=120, ni=200, seed=0):
     ["--recommender=NeuMF", "--epochs=3", "--embedding_size=32"],
     ["--recommender=MLP", "--epochs=2"],
     ["--recommender=LightGCN", "--epochs=3", "--n_layers=3"],
+    ["--recommender=NGCF", "--epochs=3", "--learning_rate=0.01"],
 ])
 def test_main_end_to_end(tmp_path, args):
     """main.py + NeuRec.properties + conf/*.properties drive the kernels; the log lines keep the
