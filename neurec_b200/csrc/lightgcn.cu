@@ -193,9 +193,11 @@ __device__ __forceinline__ void spmm_accumulate(const SpmmArgs& A, int64_t beg, 
             }
 #pragma unroll
             for (int j = 0; j < UN; ++j) {
-                float4& a = (j & 1) ? a1 : a0;
-                a.x = fmaf(v[j], x[j].x, a.x); a.y = fmaf(v[j], x[j].y, a.y);
-                a.z = fmaf(v[j], x[j].z, a.z); a.w = fmaf(v[j], x[j].w, a.w);
+                if ((j0 + j) * NPI + grp < cnt) {          // padding slots gathered row 0: never accumulate them
+                    float4& a = (j & 1) ? a1 : a0;
+                    a.x = fmaf(v[j], x[j].x, a.x); a.y = fmaf(v[j], x[j].y, a.y);
+                    a.z = fmaf(v[j], x[j].z, a.z); a.w = fmaf(v[j], x[j].w, a.w);
+                }
             }
         }
     }
