@@ -384,6 +384,20 @@ int nrc_mf_bpr_sgd_epoch(float* user_table, float* const* item_shards, int32_t w
                          int64_t first, int64_t count, float lr, float reg, float* loss,
                          void* stream);
 
+/* The explicitly-named LAZY-Adam variant of nrc_mf_bpr_sgd_epoch (BASELINE configs[4]:
+ * "learner=gd for the roofline run plus an explicitly-named lazy-Adam run"; the reference's own
+ * learner=adam, util/learner.py:6, is TF's DENSE Adam and is what nrc_opt_apply_* implement).
+ * tf.contrib.opt.LazyAdamOptimizer semantics on the rows of each triplet, applied per triplet in one
+ * pass without batch-wide de-duplication (rows that repeat inside a batch are updated per occurrence
+ * and may overwrite each other).  Single GPU; user / item slots m, v shaped like the tables. */
+int nrc_mf_bpr_lazy_adam_epoch(float* user_table, float* user_m, float* user_v, float* item_table,
+                               float* item_m, float* item_v, int32_t dim, const int64_t* train_indptr,
+                               const int32_t* train_indices, const int32_t* pos_users,
+                               const int32_t* pos_items, int64_t n_pos, int32_t num_items,
+                               int32_t shuffle, uint64_t seed, uint64_t epoch, int64_t first,
+                               int64_t count, float lr_t, float beta1, float beta2, float eps,
+                               float reg, float* loss, void* stream);
+
 /* A device allocation of its own (cudaMalloc, never a slice of a caching allocator's block) for a
  * table shard that other ranks map: *dev_ptr_out and its 64-byte CUDA IPC handle.  Peers open the
  * handle with nrc_ipc_open(handle, 0, &ptr) -- one handle per shard, so a mapping is never opened

@@ -380,6 +380,88 @@ static int launch_bpr_sgd_stream(float* U_local, const RowShards& SV, int dim, c
     return NRC_OK;
 }
 
+// ----------------------------------------------------------------------------------------
+// The explicitly-named LAZY-Adam variant for tables too large for TF's dense Adam (SURVEY 8d,
+// configs[4] "plus an explicitly-named lazy-Adam run"): tf.contrib.opt.LazyAdamOptimizer semantics
+// -- only the rows of the batch move:  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;
+// var -= lr_t * m / (sqrt(v) + eps) -- applied per TRIPLET in one pass (no batch-wide de-duplication:
+// a row that repeats inside the batch is updated once per occurrence by plain loads / stores, so
+// concurrent occurrences may overwrite each other; identical to LazyAdam when no row repeats).
+// NOT what the reference's learner=adam does (that is dense, optim.cu); never used for parity claims.
+// Algorithmic traffic: rows of (var, m, v) read + written for 3 rows = 72*dim + 12 B per triplet.
+// ----------------------------------------------------------------------------------------
+template <int VEC>
+__device__ __forceinline__ void st_vec(float* p, const float (&v)[VEC]) {
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else if constexpr (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    else *p = v[0];
+}
+
+template <int VEC>
+__device__ __forceinline__ void lazy_adam_row(float* var, float* m, float* v, const float (&x)[VEC], const float (&g)[VEC],
+                                              float lr_t, float b1, float b2, float eps) {
+    float mm[VEC], vv[VEC], out[VEC];
+    ld_vec<VEC>(m, mm); ld_vec<VEC>(v, vv);
+#pragma unroll
+    for (int t = 0; t < VEC; ++t) {
+        mm[t] = b1 * mm[t] + (1.0f - b1) * g[t];
+        vv[t] = b2 * vv[t] + (1.0f - b2) * g[t] * g[t];
+        out[t] = x[t] - lr_t * mm[t] / (sqrtf(vv[t]) + eps);
+    }
+    st_vec<VEC>(m, mm); st_vec<VEC>(v, vv); st_vec<VEC>(var, out);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+mf_bpr_lazy_adam_stream_kernel(float* __restrict__ U, float* __restrict__ mU, float* __restrict__ vU, float* __restrict__ V,
+                               float* __restrict__ mV, float* __restrict__ vV, const EpochSpec E, int64_t first, int64_t count,
+                               float lr_t, float b1, float b2, float eps, float reg, float* __restrict__ loss) {
+    constexpr int D = 32 * VEC;
+    constexpr int CH = 256;
+    __shared__ int32_t s_u[CH], s_i[CH], s_j[CH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float loss_acc = 0.0f;
+    for (int64_t c0 = (int64_t)blockIdx.x * CH; c0 < count; c0 += (int64_t)gridDim.x * CH) {
+        const int n = (count - c0 < CH) ? (int)(count - c0) : CH;
+        if ((int)threadIdx.x < n) {
+            int32_t u, i, j;
+            epoch_sample(E, first + c0 + threadIdx.x, 0, u, i, j);
+            s_u[threadIdx.x] = u; s_i[threadIdx.x] = i; s_j[threadIdx.x] = j;
+        }
+        __syncthreads();
+        for (int t = warp; t < n; t += 8) {
+            const size_t ou = (size_t)s_u[t] * D + lane * VEC, oi = (size_t)s_i[t] * D + lane * VEC,
+                         oj = (size_t)s_j[t] * D + lane * VEC;
+            float a[VEC], bi[VEC], bj[VEC];
+            ld_vec<VEC>(U + ou, a); ld_vec<VEC>(V + oi, bi); ld_vec<VEC>(V + oj, bj);
+            float di = 0.f, dj = 0.f, sq = 0.f;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+                di = fmaf(a[c], bi[c], di); dj = fmaf(a[c], bj[c], dj);
+                sq += a[c] * a[c] + bi[c] * bi[c] + bj[c] * bj[c];
+            }
+            di = warp_sum(di); dj = warp_sum(dj);
+            const float x = di - dj;
+            float l = (x >= 0.f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
+            if (reg != 0.0f) l += reg * 0.5f * warp_sum(sq);
+            loss_acc += l;
+            const float g = -1.0f / (1.0f + expf(x));
+            float gu[VEC], gi[VEC], gj[VEC];
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) {
+                gu[c] = g * (bi[c] - bj[c]) + reg * a[c];
+                gi[c] = g * a[c] + reg * bi[c];
+                gj[c] = -g * a[c] + reg * bj[c];
+            }
+            lazy_adam_row<VEC>(U + ou, mU + ou, vU + ou, a, gu, lr_t, b1, b2, eps);
+            lazy_adam_row<VEC>(V + oi, mV + oi, vV + oi, bi, gi, lr_t, b1, b2, eps);
+            lazy_adam_row<VEC>(V + oj, mV + oj, vV + oj, bj, gj, lr_t, b1, b2, eps);
+        }
+        __syncthreads();
+    }
+    if (lane == 0 && loss) atomicAdd(loss, loss_acc);
+}
+
 static int grad_grid(int64_t batch) {
     const int wpb = 8;
     int64_t blocks = (batch + wpb - 1) / wpb;
@@ -506,6 +588,37 @@ extern "C" int nrc_mf_bpr_sgd_epoch(float* user_table, float* const* item_shards
     SV.rows_per_shard = world > 1 ? (int32_t)items_per_shard : 0;
     SV.self = self_rank;
     return launch_bpr_sgd_stream(user_table, SV, dim, E, first, count, lr, reg, loss, as_stream(stream));
+}
+
+// BPR with LAZY Adam straight from the train CSR (single GPU): the explicitly-named lazy variant of
+// nrc_mf_bpr_sgd_epoch for tables where TF's dense Adam pass is out of reach.  lr_t = Adam's
+// lr * sqrt(1 - b2^t) / (1 - b1^t) of this step (one value per call = per batch).
+extern "C" int nrc_mf_bpr_lazy_adam_epoch(float* user_table, float* user_m, float* user_v, float* item_table, float* item_m,
+                                          float* item_v, int32_t dim, const int64_t* train_indptr,
+                                          const int32_t* train_indices, const int32_t* pos_users, const int32_t* pos_items,
+                                          int64_t n_pos, int32_t num_items, int32_t shuffle, uint64_t seed, uint64_t epoch,
+                                          int64_t first, int64_t count, float lr_t, float beta1, float beta2, float eps,
+                                          float reg, float* loss, void* stream) {
+    NRC_REQUIRE(dim == 32 || dim == 64 || dim == 128, NRC_E_LIMIT, "lazy Adam supports dim 32, 64, 128 (got %d)", dim);
+    NRC_REQUIRE(user_table && user_m && user_v && item_table && item_m && item_v, NRC_E_VALUE, "table / slot pointers are NULL");
+    EpochSpec E;
+    int rc = epoch_spec_init(E, train_indptr, train_indices, pos_users, pos_items, n_pos, 1, num_items, 1, shuffle, seed,
+                             epoch);
+    if (rc) return rc;
+    NRC_REQUIRE(first >= 0 && count >= 0 && first + count <= n_pos, NRC_E_VALUE,
+                "[first, first + count) = [%lld, %lld) outside the epoch's %lld triplets", (long long)first,
+                (long long)(first + count), (long long)n_pos);
+    if (count == 0) return NRC_OK;
+    int64_t blocks = (count + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = as_stream(stream);
+#define NRC_LAZY(VEC) mf_bpr_lazy_adam_stream_kernel<VEC><<<(unsigned)blocks, 256, 0, st>>>( \
+        user_table, user_m, user_v, item_table, item_m, item_v, E, first, count, lr_t, beta1, beta2, eps, reg, loss)
+    if (dim == 128) NRC_LAZY(4); else if (dim == 64) NRC_LAZY(2); else NRC_LAZY(1);
+#undef NRC_LAZY
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
 }
 
 // Peer mappings are only usable by kernels of this device after peer access is enabled.

@@ -376,6 +376,17 @@ def mf_bpr_sgd_epoch(user_table, item_shards, train_indptr, train_indices, pos_u
     _count()
 
 
+def mf_bpr_lazy_adam_epoch(U, mU, vU, V, mV, vV, train_indptr, train_indices, pos_users, pos_items, num_items, shuffle,
+                           seed, epoch, first, count, lr_t, reg, loss_out, beta1=0.9, beta2=0.999, eps=1e-8):
+    """The explicitly-named lazy-Adam variant of mf_bpr_sgd_epoch (nrc_mf_bpr_lazy_adam_epoch)."""
+    check(_lib.load().nrc_mf_bpr_lazy_adam_epoch(_p(U), _p(mU), _p(vU), _p(V), _p(mV), _p(vV), U.shape[1],
+                                                 _p(train_indptr), _p(train_indices), _p(pos_users), _p(pos_items),
+                                                 pos_users.numel(), int(num_items), 1 if shuffle else 0, int(seed),
+                                                 int(epoch), int(first), int(count), float(lr_t), float(beta1),
+                                                 float(beta2), float(eps), float(reg), _p(loss_out), _stream()))
+    _count()
+
+
 def opt_apply_rows(opt, var, grad, slot0, slot1, touched, stamp, hyper):
     h = np.zeros(4, dtype=np.float32)
     h[:len(hyper)] = hyper

@@ -295,3 +295,49 @@ def test_fused_ncf_epoch_matches_the_oracle_trainer(ml100k, pairwise, loss, opt,
     for k in KEYS[:4]:
         if G[k] is not None:
             assert float(G[k].abs().max()) == 0.0                    # accumulators left clean
+
+
+@pytest.mark.parametrize("dim", [128, 64])
+def test_lazy_adam_variant_on_a_duplicate_free_epoch(dim):
+    """nrc_mf_bpr_lazy_adam_epoch (the explicitly-named lazy variant for huge tables): on an
+    epoch without repeated rows it is exactly LazyAdam -- only the batch's rows move, by the Adam
+    formulas with this step's lr_t; untouched rows and their slots stay bit-identical."""
+    from neurec_b200 import ops
+    nu, ni, n = 2000, 300_000, 2000
+    rs = np.random.RandomState(dim + 1)
+    tp = np.arange(nu + 1, dtype=np.int64)
+    pos_items = rs.permutation(ni)[:nu].astype(np.int32)
+    pos_users = np.arange(nu, dtype=np.int32)
+    for seed in range(50):
+        wu, wi, wj = oracle.epoch_build(tp, pos_items, pos_users, pos_items, 1, ni, True, True, seed, 0)
+        if len(np.unique(np.concatenate([wi, wj[:, 0]]))) == 2 * n:
+            break
+    else:
+        pytest.skip("no duplicate-free epoch found")
+    wj = wj[:, 0]
+    U0 = (rs.randn(nu, dim) * 0.1).astype(np.float32); V0 = (rs.randn(ni, dim) * 0.1).astype(np.float32)
+    mU0 = (rs.randn(nu, dim) * 0.01).astype(np.float32); vU0 = (rs.rand(nu, dim) * 0.01).astype(np.float32)
+    mV0 = (rs.randn(ni, dim) * 0.01).astype(np.float32); vV0 = (rs.rand(ni, dim) * 0.01).astype(np.float32)
+    lr_t, b1, b2, eps, reg = np.float32(3e-3), np.float32(0.9), np.float32(0.999), np.float32(1e-8), np.float32(1e-3)
+    pu, qi, qj = U0[wu], V0[wi], V0[wj]
+    x = (pu * qi).sum(1) - (pu * qj).sum(1)
+    wl, g = tf_math.pairwise_loss_and_grad("bpr", x)
+    g = g[:, None].astype(np.float32)
+
+    def lazy(var, m, v, rows, grad):
+        m[rows] = b1 * m[rows] + (np.float32(1) - b1) * grad
+        v[rows] = b2 * v[rows] + (np.float32(1) - b2) * grad * grad
+        var[rows] = var[rows] - lr_t * m[rows] / (np.sqrt(v[rows]) + eps)
+    Uw, mUw, vUw, Vw, mVw, vVw = (a.copy() for a in (U0, mU0, vU0, V0, mV0, vV0))
+    lazy(Uw, mUw, vUw, wu, g * (qi - qj) + reg * pu)
+    lazy(Vw, mVw, vVw, wi, g * pu + reg * qi)
+    lazy(Vw, mVw, vVw, wj, -g * pu + reg * qj)
+    d = [dev(a) for a in (U0, mU0, vU0, V0, mV0, vV0)]
+    loss = torch.zeros(1, device="cuda")
+    ops.mf_bpr_lazy_adam_epoch(*d, dev(tp), dev(pos_items), dev(pos_users), dev(pos_items), ni, True, seed, 0, 0, n,
+                               float(lr_t), float(reg), loss)
+    for got, want, name in zip(d, (Uw, mUw, vUw, Vw, mVw, vVw), "U mU vU V mV vV".split()):
+        assert np.abs(got.cpu().numpy() - want).max() < 2e-6, name
+    untouched = np.setdiff1d(np.arange(ni), np.concatenate([wi, wj]))
+    assert np.array_equal(d[3].cpu().numpy()[untouched], V0[untouched])
+    assert np.array_equal(d[4].cpu().numpy()[untouched], mV0[untouched])
