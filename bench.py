@@ -800,6 +800,23 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
     barrier(world)
     finite = bool(np.isfinite(loss_pin[:K].numpy()).all())
     remote = (world - 1) / world if world > 1 else 0.0
+    lazy = None
+    if world == 1:          # the explicitly-named lazy-Adam run SURVEY 8(d) asks for (single GPU: rows of var, m, v)
+        z = torch.zeros_like
+        mU, vU, mV, vV = z(US_local), z(US_local), z(VS.local), z(VS.local)
+        lr_sched = adam_lr_schedule(1e-3, K + W)
+        lstate = {"g": 0}
+
+        def lazy_step():
+            e, s = divmod(lstate["g"], spe)
+            ops.mf_bpr_lazy_adam_epoch(US_local, mU, vU, VS.local, mV, vV, T.ptr, T.idx, T.users, T.idx, ni, True, SEED + 7,
+                                       e, s * bs, bs, float(lr_sched[lstate["g"]]), 0.0, loss)
+            lstate["g"] += 1
+        for _ in range(W):
+            lazy_step()
+        lms, _ = timed(lambda: [lazy_step() for _ in range(K)], world, windows)
+        lazy = {"ms": lms / K, "finite": bool(torch.isfinite(loss).item())}
+        del mU, vU, mV, vV
     if world > 1:
         VS.close()
     if rank != 0:
@@ -833,6 +850,16 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
                                     "SURVEY 8(d): (24*d + 12) B per triplet x 2^20 triplets (the fused sampler's CSR reads "
                                     "are not counted: 'fused: 0 extra')",
                                     "CUDA events on the launching stream around each of the K timed launches; mean", extra)}
+    if lazy is not None:
+        lb = bs * (72 * dim + 12)
+        out["lazy_adam"] = {"value": bs / (lazy["ms"] * 1e-3), "unit": "triplets/s", "ms_per_step": lazy["ms"],
+                            "loss_finite": lazy["finite"],
+                            "what": "the explicitly-named lazy-Adam run of SURVEY 8(d): nrc_mf_bpr_lazy_adam_epoch, rows of "
+                                    "(var, m, v) read + written per triplet, no batch-wide de-duplication -- NOT the reference's "
+                                    "dense TF Adam",
+                            "roofline": hbm_roofline("mf_bpr_lazy_adam_stream_kernel", lb, lazy["ms"] * 1e-3,
+                                                     "SURVEY 8(d): (72*d + 12) B per triplet x 2^20 triplets",
+                                                     "CUDA events around the K timed launches")}
     if with_cpu:
         out["cpu_baseline"] = cpu_sharded_baseline(cfg, seconds=12.0)
     return out
