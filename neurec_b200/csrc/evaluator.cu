@@ -37,8 +37,16 @@ __constant__ int c_metric[kMaxMetrics];
 static bool g_tables_ready = false;
 static bool g_force_exact = false;   // nrc_eval_force_exact: skip the tie-free fast passes
 
+// __constant__ tables live per device: remember which device holds them and upload again when the
+// calling thread has switched devices (one process per GPU is the supported model; this keeps a
+// process that touches a second device correct instead of silently reading zeros).
+static int g_tables_dev = -1;
+
 static int upload_tables() {
-    if (g_tables_ready) return NRC_OK;
+    int dev = 0;
+    NRC_CUDA_CHECK(cudaGetDevice(&dev));
+    if (g_tables_ready && dev == g_tables_dev) return NRC_OK;
+    g_tables_dev = dev;
     static double inv[kMaxTopK];
     static float idcg[kMaxTopK];
     float acc = 0.0f;
@@ -737,7 +745,11 @@ static int check_metrics(const int32_t* metric_host, int metric_num) {
         ids[i] = metric_host[i];
     }
     static int cached[kMaxMetrics] = {-1, -1, -1, -1, -1, -1, -1, -1};
-    if (memcmp(cached, ids, sizeof(ids)) != 0) {
+    static int cached_dev = -1;
+    int dev = 0;
+    NRC_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev != cached_dev || memcmp(cached, ids, sizeof(ids)) != 0) {
+        cached_dev = dev;
         // a previous launch may still be reading the old ids on another stream
         NRC_CUDA_CHECK(cudaDeviceSynchronize());
         NRC_CUDA_CHECK(cudaMemcpyToSymbol(c_metric, ids, sizeof(ids)));
