@@ -120,13 +120,12 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        __threadfence();
-        atomicAdd(counter, 1u);
+        // release-arrive (orders everything the CTA wrote before its bar.sync), acquire-poll
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
         unsigned int seen;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
         } while (seen < target);
-        __threadfence();
     }
     __syncthreads();
 }

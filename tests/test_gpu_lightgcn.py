@@ -138,8 +138,8 @@ def test_fast_spmm_matches_scipy_within_reassociation(ml100k, dim, adj_type):
     assert (np.abs(got - want) / scale).max() < 4e-7
     got2 = ops.spmm_csr(ip, ix, va, dev(X), row_order=degree_order(A)).cpu().numpy()
     assert np.array_equal(got, got2)                     # deterministic
-    got3 = ops.spmm_csr(ip, ix, va, dev(X)).cpu().numpy()    # natural row order: same sums per row
-    assert np.array_equal(got, got3)
+    got3 = ops.spmm_csr(ip, ix, va, dev(X)).cpu().numpy()    # natural row order: a long row may share its unit with other rows -> other split
+    assert (np.abs(got3 - want) / scale).max() < 4e-7
     B = np.random.RandomState(1).randn(n, dim).astype(np.float32)
     S = np.random.RandomState(2).randn(n, dim).astype(np.float32)
     dS = dev(S)
