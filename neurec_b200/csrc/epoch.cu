@@ -24,6 +24,7 @@
 #include "optim.cuh"
 
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace nrc {
 
@@ -104,6 +105,7 @@ struct MfEpochParams {
     int64_t first_step, num_steps, steps_total;
     int32_t num_users, num_items, D, batch_size;
     int32_t loss_kind, opt_kind, first_stamp, build;
+    int32_t dbg;                // NRC_EPOCH_DBG experiment bits (0 in normal use): 1 skip the gradient phase, 2 skip the optimizer phase
     float reg, h0, h1, h2, h3;
 };
 
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(512, 1) mf_epoch_kernel(const MfEpochParams P)
         // ---- phase 1: gradients of the batch
         const float inv_b = 1.0f / (float)cnt;
         float loss_acc = 0.0f;
-        for (int64_t b = warp_g; b < cnt; b += warps) {
+        for (int64_t b = warp_g; b < cnt && !(P.dbg & 1); b += warps) {
             const int32_t u = __ldcg(P.ws_u + off + b), i = __ldcg(P.ws_i + off + b), t = __ldcg(P.ws_t + off + b);
             loss_acc += mf_sample_grad<PAIRWISE, VEC>(P, lane, u, i, t, inv_b, stamp);
         }
@@ -292,7 +294,8 @@ __global__ void __launch_bounds__(512, 1) mf_epoch_kernel(const MfEpochParams P)
             p1 = __fmul_rn(p1, P.h1);
             p2 = __fmul_rn(p2, P.h2);
         }
-        if ((D & 3) == 0) {
+        if (P.dbg & 2) {
+        } else if ((D & 3) == 0) {
             for (int64_t e = tid * 4; e < eAll; e += nthr * 4) {
                 const bool isU = e < eU;
                 const int64_t i = isU ? e : e - eU;
@@ -436,6 +439,11 @@ extern "C" int nrc_mf_epoch_fused(float* user_table, float* item_table, int32_t 
     P.num_users = num_users; P.num_items = num_items; P.D = dim; P.batch_size = batch_size;
     P.loss_kind = loss_kind; P.opt_kind = opt_kind; P.first_stamp = first_stamp;
     P.build = first_step == 0 ? 1 : 0;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("NRC_EPOCH_DBG"); dbg = e ? atoi(e) : 0; }
+        P.dbg = dbg;
+    }
     P.reg = reg;
     P.h0 = hyper_host ? hyper_host[0] : 0.0f; P.h1 = hyper_host ? hyper_host[1] : 0.0f;
     P.h2 = hyper_host ? hyper_host[2] : 0.0f; P.h3 = hyper_host ? hyper_host[3] : 0.0f;

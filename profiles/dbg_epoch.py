@@ -44,6 +44,14 @@ def run(pairwise, dim, bs, neg_num, loss, reps=20):
 
 
 run(True, 64, 512, 1, "bpr")
-run(True, 128, 512, 1, "bpr")
-run(False, 32, 256, 4, "cross_entropy")
-run(True, 64, 4096, 1, "bpr")
+if os.environ.get("NRC_EPOCH_ONLY") is None:
+    run(True, 128, 512, 1, "bpr")
+    run(False, 32, 256, 4, "cross_entropy")
+    run(True, 64, 4096, 1, "bpr")
+
+if os.environ.get("NRC_EPOCH_DBG") is None:
+    import subprocess
+    for bits, what in ((3, "barriers only (both phases skipped)"), (1, "optimizer phase + barriers"), (2, "gradient phase + barriers")):
+        env = dict(os.environ, NRC_EPOCH_DBG=str(bits), NRC_EPOCH_ONLY="1")
+        out = subprocess.run([sys.executable, __file__], env=env, capture_output=True, text=True).stdout.strip().splitlines()
+        print("  NRC_EPOCH_DBG=%d (%s): %s" % (bits, what, out[0] if out else "?"), flush=True)
