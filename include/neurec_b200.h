@@ -179,6 +179,11 @@ int nrc_eval_mf_tc(const float* user_table, const float* item_table, int32_t dim
  * the same.  Change the version (or pass 0) whenever the table's contents change. */
 int nrc_eval_tc_items_version(uint64_t version);
 
+/* Epilogue layout of the tensor-core candidate kernel (main pass): 8 warps (one thread per user and
+ * item tile) or 16 warps (two threads per user, one per half tile, each with its own threshold and
+ * candidate list).  Results are identical; a tuning knob (env NRC_TC_CH=2 selects 16 as well). */
+int nrc_eval_tc_epilogue_warps(int32_t warps);
+
 /* Measurement hook: CUDA-event duration (ms, on the launching stream) and algorithmic flops
  * (2 * users * items * dim) of the last tcgen05 candidate-kernel launch made by nrc_eval_mf_tc;
  * waits for that launch.  bench.py derives the tensor-pipe roofline fraction from it. */

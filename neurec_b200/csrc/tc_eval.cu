@@ -299,7 +299,7 @@ namespace tc {
 constexpr int kMaxList = 64;           // threshold rank <= 64 (2*top_k for the tie-replay pass)
 constexpr int kMU = 256;               // users per CTA
 constexpr int kMaxStages = 3;
-constexpr int kCandThreads = 320;
+constexpr int kCandThreads = 320;          // CH = 1: 8 epilogue warps + MMA + TMA; CH = 2: 16 epilogue warps (576 threads)
 
 struct CandArgs {
     const __nv_bfloat16* Ub;   // [num_eval, D] bf16 rows of the users being evaluated (gathered)
@@ -313,17 +313,22 @@ struct CandArgs {
     int lstride;               // shared-memory words per list (odd: conflict-free whatever entry a lane touches)
     int nst;                   // shared-memory item stages (2 or 3)
     int seg_tiles;             // item tiles per grid.y segment
-    int nslots;                // candidate lists per user = gridDim.y
+    int nslots;                // candidate lists per user = gridDim.y * CH
     int cap;                   // entries per list
     int32_t* cand;             // [num_eval, nslots, cap] candidate item ids, ascending inside a list
     float* cand_val;           // same shape: the approximate (bf16 tensor-core) score of each candidate
     int32_t* cand_cnt;         // [num_eval, nslots] candidates seen (> cap => overflow)
 };
 
-template <int NT>   // items per tile (UMMA N): 128 (default) or 256
-__global__ void __launch_bounds__(kCandThreads, 1)
+// CH = column halves per tile with their own epilogue warps: 1 -> 8 epilogue warps, one user per
+// thread over all NT columns; 2 -> 16 epilogue warps, a user is served by two threads (columns
+// [0, NT/2) and [NT/2, NT)), each with its OWN threshold list and candidate list (slot), like two
+// item segments interleaved -- twice the warps to hide the tcgen05.ld -> filter dependency chains.
+template <int NT, int CH>   // items per tile (UMMA N): 128 (default) or 256
+__global__ void __launch_bounds__((8 * CH + 2) * 32, 1)
 tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV) {
-    constexpr int kMmaWarp = 8, kTmaWarp = 9;
+    constexpr int kMmaWarp = 8 * CH, kTmaWarp = 8 * CH + 1;
+    constexpr int kThreads = (8 * CH + 2) * 32;
     constexpr int kAccStages = 256 / NT;   // TMEM stages per user half: 512 columns = 2 halves x kAccStages x NT
     extern __shared__ __align__(1024) uint8_t smem[];
     const int D = P.D;
@@ -341,8 +346,8 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
 
     for (int h = 0; h < 2; ++h)
         load_tile_sw128(sA + (size_t)h * half_bytes, P.Ub + (size_t)(row0 + h * kM) * D, kM,
-                        max(0, min(kM, P.num_eval - row0 - h * kM)), D, tid, kCandThreads);
-    for (int i = tid; i < kMU * P.lstride; i += kCandThreads) sList[i] = -INFINITY;
+                        max(0, min(kM, P.num_eval - row0 - h * kM)), D, tid, kThreads);
+    for (int i = tid; i < CH * kMU * P.lstride; i += kThreads) sList[i] = -INFINITY;
     fence_async_smem();
     if (tid == 0) {
         for (int i = 0; i < kMaxStages; ++i) {
@@ -351,7 +356,7 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 128);   // the four epilogue warps of one user half
+            mbar_init(&acc_empty[i], 128 * CH);   // the four (eight) epilogue warps of one user half
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -422,12 +427,14 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
         }
     } else {
         // ---------------- epilogue: one user per thread ----------------
-        const int h = warp >> 2, wq = warp & 3;      // user half and TMEM lane quarter
+        const int h = (warp >> 2) & 1, wq = warp & 3;      // user half and TMEM lane quarter
+        const int ch = warp >> 3;                          // column half served by this warp (0 when CH == 1)
+        constexpr int CW = NT / CH;                        // columns per epilogue thread and tile
         const int r = h * kM + wq * 32 + lane;       // user row inside the CTA
         const int row = row0 + r;
         const bool live = row < P.num_eval;
-        float* lst = sList + r * P.lstride;
-        const int slot = blockIdx.y;
+        float* lst = sList + (ch * kMU + r) * P.lstride;
+        const int slot = blockIdx.y * CH + ch;
         const float margin = live ? P.margin[row] : 0.0f;
         const int u = live ? P.users[row] : 0;
         const int64_t tb = live ? P.train_ptr[u] : 0;
@@ -520,15 +527,16 @@ tc_candidate_kernel(const CandArgs P, const __grid_constant__ CUtensorMap tmapV)
             const uint32_t tbase = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((a * 2 + h) * NT);
             uint32_t ra[32], rb[32];
             __syncwarp();   // the candidate branch diverges; tcgen05.ld needs the whole warp
-            tmem_ld32_issue(tbase, ra);
+            const int c_beg = ch * CW, c_end = c_beg + CW;
+            tmem_ld32_issue(tbase + (uint32_t)c_beg, ra);
 #pragma unroll 1
-            for (int c = 0; c < NT; c += 64) {
+            for (int c = c_beg; c < c_end; c += 64) {
                 tmem_ld_wait(ra);
                 tmem_ld32_issue(tbase + (uint32_t)(c + 32), rb);
                 filter_chunk(ra, c);
                 __syncwarp();
                 tmem_ld_wait(rb);
-                if (c + 64 < NT) tmem_ld32_issue(tbase + (uint32_t)(c + 64), ra);
+                if (c + 64 < c_end) tmem_ld32_issue(tbase + (uint32_t)(c + 64), ra);
                 filter_chunk(rb, c + 32);
                 __syncwarp();
             }
@@ -622,6 +630,7 @@ static size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 // The bf16 copy + max row norm are reused across calls while the caller vouches that the table has
 // not changed: nrc_eval_tc_items_version(v != 0) keys the cache on (pointer, shape, v); version 0
 // (default) converts on every call.
+static int g_ch_pref = -1;      // epilogue layout: 1 = 8 warps, 2 = 16 warps (nrc_eval_tc_epilogue_warps / NRC_TC_CH)
 static uint64_t g_items_version = 0, g_cached_version = 0;
 static const float* g_cached_ptr = nullptr;
 
@@ -658,7 +667,11 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
     // candidates better; NRC_TC_NT=256 selects the 256-item tile (fewer shared-memory reads per
     // MMA, single-buffered accumulators) when two such stages fit.
     const int lstride = (LQ <= 32) ? 33 : 65;
-    const size_t list_bytes = (size_t)kMU * lstride * 4;
+    // 16 epilogue warps (two column halves per user, NRC_TC_CH=2) when their lists fit beside >= 2 stages
+    if (g_ch_pref < 0) { const char* e = getenv("NRC_TC_CH"); g_ch_pref = e ? atoi(e) : 1; }
+    const int CH = (g_ch_pref == 2 && pass == 0 &&
+              (size_t)2 * kM * D * 2 + (size_t)2 * kMU * lstride * 4 + 2048 + (size_t)2 * 128 * D * 2 <= 227 * 1024) ? 2 : 1;
+    const size_t list_bytes = (size_t)kMU * CH * lstride * 4;
     const size_t fixed = (size_t)2 * kM * D * 2 + list_bytes + 2048;
     const size_t budget = 227 * 1024 - fixed;
     const char* nt_env = getenv("NRC_TC_NT");
@@ -685,7 +698,7 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
     }
     const int seg_tiles = (T + G - 1) / G;
     G = (T + seg_tiles - 1) / seg_tiles;           // no empty segment
-    const int nslots = G;
+    const int nslots = G * CH;
     int nst = (int)(budget / ((size_t)kNT * D * 2));
     if (nst > kMaxStages) nst = kMaxStages;
     NRC_REQUIRE(nst >= 2, NRC_E_LIMIT, "dim %d with threshold rank %d does not fit the tensor-core pass", D, LQ);
@@ -733,9 +746,13 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
     if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
     static bool attr_done = false;
     if (!attr_done) {
-        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             226 * 1024));
-        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            226 * 1024));
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            226 * 1024));
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(tc_candidate_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             226 * 1024));
         attr_done = true;
     }
@@ -747,8 +764,13 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
         }
         NRC_CUDA_CHECK(cudaEventRecord(g_ev[0], st));
     }
-    if (kNT == 256) tc_candidate_kernel<256><<<grid, kCandThreads, smem, st>>>(P, tmapV);
-    else tc_candidate_kernel<128><<<grid, kCandThreads, smem, st>>>(P, tmapV);
+    if (CH == 2) {
+        if (kNT == 256) tc_candidate_kernel<256, 2><<<grid, 576, smem, st>>>(P, tmapV);
+        else tc_candidate_kernel<128, 2><<<grid, 576, smem, st>>>(P, tmapV);
+    } else {
+        if (kNT == 256) tc_candidate_kernel<256, 1><<<grid, kCandThreads, smem, st>>>(P, tmapV);
+        else tc_candidate_kernel<128, 1><<<grid, kCandThreads, smem, st>>>(P, tmapV);
+    }
     NRC_CUDA_CHECK(cudaGetLastError());
     if (pass == 0) {
         NRC_CUDA_CHECK(cudaEventRecord(g_ev[1], st));
@@ -771,6 +793,14 @@ int run_pass(int pass, const float* U, const int32_t* users, int num_rows, const
 // (or 0 = never cache) makes the next call convert again.
 extern "C" int nrc_eval_tc_items_version(uint64_t version) {
     nrc::tc::g_items_version = version;
+    return NRC_OK;
+}
+
+// 8 (default) or 16 epilogue warps in the candidate kernel of the main pass (16: every user is served by
+// two threads, one per half of each item tile, each with its own threshold and candidate list).
+extern "C" int nrc_eval_tc_epilogue_warps(int32_t warps) {
+    NRC_REQUIRE(warps == 8 || warps == 16, NRC_E_VALUE, "epilogue warps must be 8 or 16 (got %d)", warps);
+    nrc::tc::g_ch_pref = warps / 8;
     return NRC_OK;
 }
 

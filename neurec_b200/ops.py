@@ -193,6 +193,11 @@ def eval_tc_items_version(version):
     check(_lib.load().nrc_eval_tc_items_version(int(version)))
 
 
+def eval_tc_epilogue_warps(warps):
+    """8 or 16 epilogue warps in the tensor-core candidate kernel (same results; tuning knob)."""
+    check(_lib.load().nrc_eval_tc_epilogue_warps(int(warps)))
+
+
 def eval_tc_last_launch():
     """(kernel_ms, flops) of the last tcgen05 candidate-kernel launch made by eval_mf_tc."""
     import ctypes

@@ -179,3 +179,23 @@ def test_tc_eval_adversarial_bf16_rounding_keeps_the_exact_top1(K):
                                 return_ranks=True)
     assert np.array_equal(ranks.cpu().numpy(), wranks)
     assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_tc_eval_sixteen_epilogue_warps_give_the_same_bits():
+    """The 16-warp epilogue (two threads per user, one per half item tile, own threshold + candidate list
+    each) must select exactly what the 8-warp layout selects: ranks and metric rows bit-identical to the
+    oracle, also with masks, ties (integer tables) and a catalogue that is not a multiple of the tile."""
+    from neurec_b200 import ops
+    try:
+        ops.eval_tc_epilogue_warps(16)
+        for (nu, ni, dim, K, ints) in ((300, 5000, 64, 20, False), (129, 20049, 128, 10, False), (140, 900, 64, 20, True),
+                                       (500, 12345, 128, 31, False)):
+            U, V, tp, ti, sp, si = _problem(nu, ni, dim, nu + ni + 1, int_tables=ints)
+            users = np.arange(nu, dtype=np.int32)
+            want, wranks = oracle.eval_mf(U, V, users, tp, ti, sp, si, ALL, K, thread_num=4, return_ranks=True)
+            got, ranks = ops.eval_mf_tc(dev(U), dev(V), dev(users), dev(tp), dev(ti), dev(sp), dev(si), ALL, K,
+                                        return_ranks=True)
+            assert np.array_equal(ranks.cpu().numpy(), wranks), (nu, ni, dim, K)
+            assert np.array_equal(got.cpu().numpy(), want)
+    finally:
+        ops.eval_tc_epilogue_warps(8)
