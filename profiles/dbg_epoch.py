@@ -51,7 +51,11 @@ if os.environ.get("NRC_EPOCH_ONLY") is None:
 
 if os.environ.get("NRC_EPOCH_DBG") is None:
     import subprocess
-    for bits, what in ((3, "barriers only (both phases skipped)"), (1, "optimizer phase + barriers"), (2, "gradient phase + barriers")):
+    env = dict(os.environ, NRC_EPOCH_TWO_BARRIER="1", NRC_EPOCH_ONLY="1", NRC_EPOCH_DBG="0")
+    out = subprocess.run([sys.executable, __file__], env=env, capture_output=True, text=True).stdout.strip().splitlines()
+    print("  two-barrier kernel (NRC_EPOCH_TWO_BARRIER=1): %s" % (out[0] if out else "?"), flush=True)
+    for bits, what in ((3, "two-barrier kernel, barriers only (both phases skipped)"), (1, "two-barrier kernel, optimizer phase + barriers"),
+                       (2, "two-barrier kernel, gradient phase + barriers")):
         env = dict(os.environ, NRC_EPOCH_DBG=str(bits), NRC_EPOCH_ONLY="1")
         out = subprocess.run([sys.executable, __file__], env=env, capture_output=True, text=True).stdout.strip().splitlines()
         print("  NRC_EPOCH_DBG=%d (%s): %s" % (bits, what, out[0] if out else "?"), flush=True)
