@@ -620,6 +620,8 @@ SMALL = {"bprmf-ml100k": MfMl100k, "neumf-ml100k": NeumfMl100k, "lightgcn-gowall
 
 def cpu_train_baseline(w, n_steps):
     threads = os.cpu_count() or 1
+    from oracle import torch_port
+    torch_port.set_threads(threads)
     sampler, step, skind, how = w.cpu_make()
     dt = run_cpu_epoch_steps(sampler, step, n_steps)
     return {"value": n_steps * w.batch / dt, "unit": "triplets/s", "cores": threads, "kind": "port",
