@@ -16,6 +16,8 @@
 //            row gradients added with RED.ADD into dense accumulators (duplicates sum)
 //   phase 2  element-wise optimizer over every table of the model in ONE launch; zeroes the
 //            accumulators for the next step.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "epoch.cuh"
 #include "optim.cuh"
@@ -163,6 +165,7 @@ struct RowShards {
     float* base[8];
     int32_t rows_per_shard;   // 0: a single local table at base[0]
     int32_t self;             // this rank's shard (rows of other shards live in peer memory)
+    int32_t vec_remote;       // 1: vector REDs on peer rows too (NRC_PEER_VEC_RED=1; default scalar REDs)
     // SHARDED is a compile-time switch and the shard base is picked with constant indices only, so
     // the struct stays in the kernel-parameter constant bank (a dynamic index would spill it to
     // local memory and cost the single-GPU kernel ~15 % of its bandwidth).
@@ -186,7 +189,7 @@ struct RowShards {
 // (32-bit float atomics are the form every NVLink generation forwards to the owner's L2).
 template <int VEC>
 __device__ __forceinline__ void red_row(float* p, const float (&d)[VEC], bool remote) {
-    if (remote) {
+    if (remote) {   // scalar form
 #pragma unroll
         for (int t = 0; t < VEC; ++t) atomicAdd(p + t, d[t]);
         return;
@@ -345,7 +348,7 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
                 dvi[t] = -lr * (g0 * a0[t] + reg * b0[t]);
                 dvj[t] = -lr * (-g0 * a0[t] + reg * c0v[t]);
             }
-            red_row<VEC>(pu0, du, false); red_row<VEC>(qi0, dvi, ri0); red_row<VEC>(qj0, dvj, rj0);
+            red_row<VEC>(pu0, du, false); red_row<VEC>(qi0, dvi, ri0 && !V.vec_remote); red_row<VEC>(qj0, dvj, rj0 && !V.vec_remote);
             loss_acc += l0;
             if (two) {
 #pragma unroll
@@ -354,7 +357,7 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
                     dvi[t] = -lr * (g1 * a1[t] + reg * b1[t]);
                     dvj[t] = -lr * (-g1 * a1[t] + reg * c1v[t]);
                 }
-                red_row<VEC>(pu1, du, false); red_row<VEC>(qi1, dvi, ri1); red_row<VEC>(qj1, dvj, rj1);
+                red_row<VEC>(pu1, du, false); red_row<VEC>(qi1, dvi, ri1 && !V.vec_remote); red_row<VEC>(qj1, dvj, rj1 && !V.vec_remote);
                 loss_acc += l1;
             }
         }
@@ -587,6 +590,11 @@ extern "C" int nrc_mf_bpr_sgd_epoch(float* user_table, float* const* item_shards
     }
     SV.rows_per_shard = world > 1 ? (int32_t)items_per_shard : 0;
     SV.self = self_rank;
+    {
+        static int vec = -1;
+        if (vec < 0) { const char* e = getenv("NRC_PEER_VEC_RED"); vec = e ? atoi(e) : 0; }
+        SV.vec_remote = vec;
+    }
     return launch_bpr_sgd_stream(user_table, SV, dim, E, first, count, lr, reg, loss, as_stream(stream));
 }
 
