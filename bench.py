@@ -48,7 +48,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = ("bprmf-sharded", "bprmf-ml100k", "neumf-ml100k", "lightgcn-gowalla", "eval-synth")
+WORKLOADS = ("bprmf-sharded", "bprmf-ml100k", "neumf-ml100k", "lightgcn-gowalla", "eval-synth", "eval-sharded")
 DEFAULT_WORKLOAD = "bprmf-sharded"
 METRICS = ["Precision", "Recall", "NDCG", "MAP", "MRR"]
 SEED = 2018
@@ -1040,6 +1040,76 @@ def measure_synth_eval(K, W, world, rank, windows, with_cpu=True):
     return out
 
 
+def measure_eval_sharded(K, W, world, rank, windows):
+    """The item-sharded evaluator, weak-scaled in catalogue size: every rank holds
+    5 M items x d=128 of the item table (and its slice of the train CSR) and 1/N of the user table; a step
+    evaluates one batch of 37 888 consecutive users against the WHOLE catalogue (N x 5 M items): one
+    all-gather of the batch's user rows, the tensor-core candidate pass + exact re-score per shard, one
+    all-gather of the [B, 21] (id, score) lists, merge + 5 metrics."""
+    import torch
+    from neurec_b200 import ops
+    from neurec_b200.evaluator import sharded
+    ni_l, dim, topk, B = 5_000_000, 128, 20, 37_888
+    K = max(1, min(K, 8)); W = 3
+    nu = B * (K + W)
+    ni = ni_l * world
+    g = torch.Generator(device="cuda").manual_seed(50 + rank)
+    V = torch.randn(ni_l, dim, device="cuda", generator=g) * 0.1
+    a_, b_ = sharded.local_slice(B, rank, world)
+    gu = torch.Generator(device="cuda").manual_seed(7)                 # same user table on every rank; each keeps its slice
+    U_all = torch.randn(nu, dim, device="cuda", generator=gu) * 0.1
+
+    def csr_local(deg, seed):                                           # this shard's rows of the (global) train CSR
+        gg = torch.Generator(device="cuda").manual_seed(seed + rank)
+        per = max(1, deg // world)
+        idx = torch.randint(0, ni_l - per, (nu, per), device="cuda", generator=gg, dtype=torch.int32).sort(1).values
+        idx += torch.arange(per, device="cuda", dtype=torch.int32)
+        return torch.arange(nu + 1, device="cuda", dtype=torch.int64) * per, idx.reshape(-1).contiguous()
+    tp, ti = csr_local(48, 60)
+    gt = torch.Generator(device="cuda").manual_seed(70)                 # test CSR: global ids, same on every rank
+    si = torch.randint(0, ni - 10, (nu, 10), device="cuda", generator=gt, dtype=torch.int32).sort(1).values
+    si += torch.arange(10, device="cuda", dtype=torch.int32)
+    sp = torch.arange(nu + 1, device="cuda", dtype=torch.int64) * 10
+    si = si.reshape(-1).contiguous()
+    shard = sharded.ItemShard(V, rank * ni_l, tp, ti)
+    ops.eval_tc_items_version(1)
+
+    def step(s):
+        lo = s * B
+        mine = U_all[lo + a_:lo + b_].contiguous()
+        return sharded.evaluate_item_sharded(mine, shard, sp, si, lo, B, METRICS, topk)
+    for s in range(W):
+        step(s)
+    ties = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def run():
+        for s in range(W, W + K):
+            res, t = step(s)
+            ties.add_(t)
+        return res
+    ms, res = timed(run, world, windows, flush=False)
+    ops.eval_tc_items_version(0)
+    if rank != 0:
+        return None
+    pk = peaks()
+    tpeak = pk.get("bf16_tflops_sustained") or pk.get("bf16_tflops") or 2250.0
+    flops = 2.0 * B * ni_l * dim                                       # per rank and step
+    return {"metric": "eval users/sec", "value": K * B / (ms * 1e-3), "unit": "users/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 candidates + f32 exact re-score", "data": "synthetic, seeds 50+rank / 7 / 70",
+            "gpu_launches": K * 8,
+            "config": {"workload": "item-sharded full-catalogue evaluator: %d GPU(s) x %d items x d=%d (catalogue of %d items), "
+                                   "%d users per step, top-%d, 5 metrics" % (world, ni_l, dim, ni, B, topk),
+                       "collectives": "per step: all-gather of the batch's user rows (%.1f MB) + all-gather of the [B, %d] id and "
+                                      "score lists (%.1f MB per rank)" % (B * dim * 4 / 1e6, topk + 1, B * (topk + 1) * 8 / 1e6),
+                       "tie_rows": int(ties.item()), "user_item_pairs_per_s": K * B * float(ni) / (ms * 1e-3)},
+            "e2e": {"value": K * B / (ms * 1e-3), "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "device-resident only (the N=1 e2e of the evaluator is eval-synth's)"},
+            "roofline": {"kernel": "tc_candidate_kernel", "bound": "tensor", "achieved": flops / (ms * 1e-3 / K) / 1e12,
+                         "peak": tpeak, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3 / K) / 1e12 / tpeak, "traffic": None,
+                         "note": "whole step (collectives, re-score and merge included) against the tensor peak, per GPU"}}
+
+
 def run_ours(args):
     rank, world, local = dist_setup()
     K, W = args.steps, max(args.warmup, 3)
@@ -1049,6 +1119,9 @@ def run_ours(args):
     name = args.workload
     if name == "bprmf-sharded":
         out = measure_sharded(K, W, world, rank, windows)
+    elif name == "eval-sharded":
+        out = measure_eval_sharded(K, W, world, rank, windows)
+        args.only = True
     elif name == "eval-synth":
         o = measure_synth_eval(K, W, world, rank, windows)
         out = None

@@ -87,8 +87,12 @@ def shard_candidates(user_rows, shard, user_lo, top_k):
     tp = shard.train_ptr[user_lo:user_lo + B + 1]                      # a view: CSR rows of the batch
     k1 = min(top_k + 1, shard.V.shape[0])
     nothing = torch.zeros(B + 1, dtype=torch.int64, device=dev)       # no truth needed for ranks only
-    _, local = ops.eval_mf(user_rows, shard.V, rows, tp, shard.train_idx, nothing, shard.train_idx,
-                           ["Precision"], k1, return_ranks=True, want_results=False)
+    if ops.use_tensor_core_eval(shard.V.shape[0], shard.V.shape[1], k1, B):      # large shard: tcgen05 candidate pass
+        _, local = ops.eval_mf_tc(user_rows, shard.V, rows, tp, shard.train_idx, nothing, shard.train_idx,
+                                  ["Precision"], k1, return_ranks=True)
+    else:
+        _, local = ops.eval_mf(user_rows, shard.V, rows, tp, shard.train_idx, nothing, shard.train_idx,
+                               ["Precision"], k1, return_ranks=True, want_results=False)
     if k1 < top_k + 1:
         local = torch.cat([local, torch.full((B, top_k + 1 - k1), -1, dtype=torch.int32, device=dev)], 1).contiguous()
     scores = ops.mf_score_pairs(user_rows, shard.V, local, tp, shard.train_idx)
