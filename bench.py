@@ -77,10 +77,13 @@ def load_gowalla():
 
 
 def profiled_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture, or None."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.isfile(p):
-        return json.load(open(p)).get(kernel)
+    """DRAM bytes per launch of `kernel` from the committed ncu captures (latest round first), or None."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.isfile(p):
+            v = json.load(open(p)).get(kernel)
+            if v is not None:
+                return v
     return None
 
 
