@@ -105,6 +105,7 @@ struct MfEpochParams {
     int64_t first_step, num_steps, steps_total;
     int32_t num_users, num_items, D, batch_size;
     int32_t loss_kind, opt_kind, first_stamp, build;
+    int32_t bar_mode;           // grid_barrier flavour (NRC_BAR_MODE)
     int32_t dbg;                // NRC_EPOCH_DBG experiment bits (0 in normal use): 1 skip the gradient phase, 2 skip the optimizer phase
     float reg, h0, h1, h2, h3;
 };
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(512, 1) mf_epoch_kernel(const MfEpochParams P)
             P.ws_u[p] = u; P.ws_i[p] = it; P.ws_t[p] = th;
         }
         for (int64_t s = tid; s < P.steps_total; s += nthr) P.step_loss[s] = 0.0f;
-        grid_barrier(P.barrier, target);
+        grid_barrier(P.barrier, target, P.bar_mode);
     }
 
     // TF keeps beta1^t / beta2^t as fp32 variables multiplied once per step (adam.py::_finish)
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(512, 1) mf_epoch_kernel(const MfEpochParams P)
             loss_acc += mf_sample_grad<PAIRWISE, VEC>(P, lane, u, i, t, inv_b, stamp);
         }
         if (lane == 0 && warp_g < cnt) atomicAdd(P.step_loss + s, loss_acc);
-        grid_barrier(P.barrier, target);
+        grid_barrier(P.barrier, target, P.bar_mode);
         // ---- phase 2: optimizer over both tables
         float h0 = P.h0;
         if (adam) {   // lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), fp32 (adam.py::_prepare)
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(512, 1) mf_epoch_kernel(const MfEpochParams P)
                 *grd = 0.0f;
             }
         }
-        grid_barrier(P.barrier, target);
+        grid_barrier(P.barrier, target, P.bar_mode);
     }
     if (adam && tid == 0) { P.adam_pows[0] = p1; P.adam_pows[1] = p2; }
 }
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(512, 1) mf_epoch1_kernel(const MfEpoch1Params 
             P.ws_u[p] = u; P.ws_i[p] = it; P.ws_t[p] = th;
         }
         for (int64_t s = tid; s < P.steps_total; s += nthr) P.step_loss[s] = 0.0f;
-        grid_barrier(P.barrier, target);
+        grid_barrier(P.barrier, target, P.bar_mode);
     }
     const bool adam = P.opt_kind == NRC_OPT_ADAM;
     const bool stamped = !(adam || P.opt_kind == NRC_OPT_GD);
@@ -432,8 +433,25 @@ __global__ void __launch_bounds__(512, 1) mf_epoch1_kernel(const MfEpoch1Params 
         const MfStateSet dst = last ? home : alt;               // the last pass lands in the caller's buffers (in place if it must)
         const int32_t stamp_prev = P.first_stamp + t - 1, stamp_cur = P.first_stamp + t;
         // ---- dense optimizer pass of step t-1: cur -> dst; zero the accumulator of step t+1 (all of them in the last pass)
-        if (pending) {
-            for (int64_t e = tid * 4; e < eAll; e += nthr * 4) {
+        // Roles.  When the batch needs at most half of the grid's warps, every `gstride`-th warp takes one
+        // triplet of step t (so the gradient warps are spread over all SMs) and ALL OTHER warps run the dense
+        // pass of step t-1 at the same time; otherwise every warp does the dense pass and then its triplets.
+        int64_t cnt_t = 0;
+        if (!last) {
+            const int64_t off_t = (P.first_step + t) * P.batch_size;
+            cnt_t = (P.n_used - off_t < P.batch_size) ? (P.n_used - off_t) : P.batch_size;
+        }
+        const bool split = pending && !last && cnt_t * 2 <= warps;
+        const int64_t gstride = split ? warps / cnt_t : 1;
+        const bool grad_warp = split ? (warp_g % gstride == 0 && warp_g / gstride < cnt_t) : true;
+        int64_t d_tid = tid, d_nthr = nthr;                    // dense-pass worker id / count
+        if (split) {
+            const int64_t before = (warp_g / gstride + 1 < cnt_t) ? (warp_g / gstride + 1) : cnt_t;   // gradient warps with index <= mine
+            d_tid = (warp_g - before) * 32 + lane;
+            d_nthr = (warps - cnt_t) * 32;
+        }
+        if (pending && !(split && grad_warp)) {
+            for (int64_t e = d_tid * 4; e < eAll; e += d_nthr * 4) {
                 const bool isU = e < eU;
                 const int64_t i = isU ? e : e - eU;
                 const float4 g = __ldcg(reinterpret_cast<const float4*>((isU ? gU_pend : gV_pend) + i));
@@ -457,10 +475,12 @@ __global__ void __launch_bounds__(512, 1) mf_epoch1_kernel(const MfEpoch1Params 
         // ---- gradients of step t on rows with the pending update pulled in
         const int64_t s = P.first_step + t;
         const int64_t off = s * P.batch_size;
-        const int64_t cnt = (P.n_used - off < P.batch_size) ? (P.n_used - off) : P.batch_size;
+        const int64_t cnt = cnt_t;
         const float inv_b = 1.0f / (float)cnt;
         float loss_acc = 0.0f;
-        for (int64_t b = warp_g; b < cnt; b += warps) {
+        const int64_t b0 = split ? (grad_warp ? warp_g / gstride : cnt) : warp_g;
+        const int64_t bstep = split ? cnt : warps;
+        for (int64_t b = b0; b < cnt; b += bstep) {
             const int32_t u = __ldcg(P.ws_u + off + b), i = __ldcg(P.ws_i + off + b), th = __ldcg(P.ws_t + off + b);
             const size_t ou = (size_t)u * D + lane * VEC, oi = (size_t)i * D + lane * VEC;
             const size_t oj = PAIRWISE ? (size_t)th * D + lane * VEC : 0;
@@ -506,8 +526,8 @@ __global__ void __launch_bounds__(512, 1) mf_epoch1_kernel(const MfEpoch1Params 
                 if constexpr (PAIRWISE) tVc[th] = stamp_cur;
             }
         }
-        if (lane == 0 && warp_g < cnt) atomicAdd(P.step_loss + s, loss_acc);
-        grid_barrier(P.barrier, target);
+        if (lane == 0 && b0 < cnt) atomicAdd(P.step_loss + s, loss_acc);
+        grid_barrier(P.barrier, target, P.bar_mode);
         // rotate the roles
         if (pending) { const MfStateSet x = cur; cur = alt; alt = x; }
         { float* x = gU_pend; gU_pend = gU_cur; gU_cur = gU_zero; gU_zero = x; }
@@ -521,6 +541,12 @@ __global__ void __launch_bounds__(512, 1) mf_epoch1_kernel(const MfEpoch1Params 
 // scratch of the one-barrier kernel: state set 1, two gradient accumulators, one stamp set
 static float* g_e1_buf = nullptr;
 static size_t g_e1_floats = 0;
+
+int epoch_bar_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("NRC_BAR_MODE"); mode = e ? atoi(e) : 2; }
+    return mode;
+}
 
 // per-device barrier word of the persistent kernels
 static unsigned int* g_barrier[16] = {nullptr};
@@ -625,6 +651,7 @@ extern "C" int nrc_mf_epoch_fused(float* user_table, float* item_table, int32_t 
         if (dbg < 0) { const char* e = getenv("NRC_EPOCH_DBG"); dbg = e ? atoi(e) : 0; }
         P.dbg = dbg;
     }
+    P.bar_mode = epoch_bar_mode();
     P.reg = reg;
     P.h0 = hyper_host ? hyper_host[0] : 0.0f; P.h1 = hyper_host ? hyper_host[1] : 0.0f;
     P.h2 = hyper_host ? hyper_host[2] : 0.0f; P.h3 = hyper_host ? hyper_host[3] : 0.0f;

@@ -50,7 +50,8 @@ struct NcfEpochParams {
     float* adam_pows;
     unsigned int* barrier;
     int64_t n_used, first_step, num_steps, steps_total;
-    int32_t batch_size, pairwise, loss_kind, opt_kind, first_stamp, build;
+    int32_t batch_size, pairwise, loss_kind, opt_kind, first_stamp, build, bar_mode;
+    int32_t wblocked, wblocks, sred_off;   // blocked weight-gradient path: 4 x 4 blocks per tower; smem offset (floats) of its reduction slots
     float reg_mf, reg_mlp, h0, h1, h2, h3;
 };
 
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
             Q.ws_u[p] = u; Q.ws_i[p] = it; Q.ws_t[p] = th;
         }
         for (int64_t s = gtid; s < Q.steps_total; s += nthr) Q.step_loss[s] = 0.0f;
-        grid_barrier(Q.barrier, target);
+        grid_barrier(Q.barrier, target, Q.bar_mode);
     }
     const bool adam = Q.opt_kind == NRC_OPT_ADAM;
     float p1 = 0.0f, p2 = 0.0f;
@@ -250,8 +251,14 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
                 const int in = S.in_dim[l], out = S.out_dim[l];
                 const float* src = Q.dense + (size_t)t * S.tower_size;
                 float* dst = sW + (size_t)t * S.s_tower_size;
-                for (int e = tid_cta; e < in * out; e += kEpThreads)
-                    dst[S.sw_off[l] + (e / out) * (out + 1) + (e % out)] = __ldcg(src + S.w_off[l] + e);
+                if (out <= kEpThreads && kEpThreads % out == 0) {          // no integer divisions in the loop
+                    const int j = tid_cta % out, kstep = kEpThreads / out;
+                    for (int k = tid_cta / out; k < in; k += kstep)
+                        dst[S.sw_off[l] + k * (out + 1) + j] = __ldcg(src + S.w_off[l] + k * out + j);
+                } else {
+                    for (int e = tid_cta; e < in * out; e += kEpThreads)
+                        dst[S.sw_off[l] + (e / out) * (out + 1) + (e % out)] = __ldcg(src + S.w_off[l] + e);
+                }
                 for (int e = tid_cta; e < out; e += kEpThreads) dst[S.sb_off[l] + e] = __ldcg(src + S.b_off[l] + e);
             }
         __syncthreads();
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
             loss_acc += l;
         }
         if (tid == 0 && loss_acc != 0.0f) atomicAdd(Q.step_loss + s, loss_acc);
-        grid_barrier(Q.barrier, target);
+        grid_barrier(Q.barrier, target, Q.bar_mode);
         // ---- phase 2
         float h0 = Q.h0;
         if (adam) {
@@ -271,7 +278,75 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
             p1 = __fmul_rn(p1, Q.h1);
             p2 = __fmul_rn(p2, Q.h2);
         }
-        // (a) dense weights: lane quartet per entry, batch in kWSlices fixed slices
+        // (a) dense weights.  Blocked path (every layer width a multiple of 4): a 64-thread group owns a 4 x 4
+        // block of one layer's weight matrix (or 4 bias entries); each thread takes the samples s = lane64,
+        // lane64 + 64, ... with ONE float4 of activations and ONE float4 of deltas per sample (all loads of a
+        // thread are independent: one L2 round trip), 16 FMAs per sample; the 64 partial blocks are summed by
+        // warp shuffles + one shared-memory hop in fixed order; 16 lanes apply the dense optimizer formula.
+        if (Q.wblocked) {
+            const int grp64 = tid_cta >> 6, l64 = tid_cta & 63, wl = tid_cta & 31;
+            float* sred = sm + Q.sred_off + grp64 * 16;
+            for (int bi = blockIdx.x * (kEpThreads / 64) + grp64; bi < Q.wblocks * S.n_towers; bi += gridDim.x * (kEpThreads / 64)) {
+                const int tower = bi / Q.wblocks;
+                int bb = bi - tower * Q.wblocks, l = 0;
+                bool is_bias = false;
+                for (;; ++l) {
+                    const int nw = (S.in_dim[l] >> 2) * (S.out_dim[l] >> 2), nb = S.out_dim[l] >> 2;
+                    if (bb < nw) break;
+                    bb -= nw;
+                    if (bb < nb) { is_bias = true; break; }
+                    bb -= nb;
+                }
+                const int ob = S.out_dim[l] >> 2;
+                const int k0 = is_bias ? 0 : (bb / ob) * 4, j0 = (is_bias ? bb : bb % ob) * 4;
+                float acc[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+                for (int p = 0; p < passes; ++p) {
+                    if (S.n_towers == 2 && p != tower) continue;     // shared tower (MLP.py:53-54): both passes feed dW
+                    const float* ap = Q.scratch + p * S.act_size + S.a_off[l] + k0;
+                    const float* dp = Q.scratch + (passes + p) * S.act_size + S.a_off[l + 1] + j0;
+#pragma unroll 4
+                    for (int64_t ss = l64; ss < cnt; ss += 64) {
+                        const float4 d4 = __ldcg(reinterpret_cast<const float4*>(dp + ss * stride));
+                        const float4 a4 = is_bias ? make_float4(1.f, 0.f, 0.f, 0.f)
+                                                  : __ldcg(reinterpret_cast<const float4*>(ap + ss * stride));
+                        const float av[4] = {a4.x, a4.y, a4.z, a4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) acc[r * 4 + c] = fmaf(av[r], dv[c], acc[r * 4 + c]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(kFull, acc[i], o);
+                }
+                float mine = 0.0f;                                   // lane i keeps entry i of the block
+#pragma unroll
+                for (int i = 0; i < 16; ++i) mine = (wl == i) ? acc[i] : mine;
+                if ((l64 >> 5) == 1 && wl < 16) sred[wl] = mine;     // second warp of the group -> shared memory
+                asm volatile("bar.sync %0, 64;" ::"r"(3 + grp64) : "memory");
+                if ((l64 >> 5) == 0 && wl < 16) {
+                    const float g = mine + sred[wl];
+                    const int r = wl >> 2, c = wl & 3;
+                    if (!is_bias || r == 0) {
+                        const int e = is_bias ? (S.b_off[l] + j0 + c) : (S.w_off[l] + (k0 + r) * S.out_dim[l] + j0 + c);
+                        const int e_all = tower * S.tower_size + e;
+                        float var = __ldcg(Q.dense + e_all);
+                        float a0 = has0 ? __ldcg(Q.d_s0 + e_all) : 0.0f;
+                        float a1 = has1 ? __ldcg(Q.d_s1 + e_all) : 0.0f;
+                        opt_update(Q.opt_kind, 1, true, h0, Q.h1, Q.h2, Q.h3, var, g, a0, a1);
+                        Q.dense[e_all] = var;
+                        if (has0) Q.d_s0[e_all] = a0;
+                        if (has1) Q.d_s1[e_all] = a1;
+                    }
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(3 + grp64) : "memory");
+            }
+        } else {
+        // generic path: lane quartet per entry, batch in kWSlices fixed slices
         const int64_t quartets = (int64_t)dense_total * kWSlices;
         for (int64_t q0 = gtid; q0 < ((quartets + 31) & ~(int64_t)31); q0 += nthr) {   // warp-uniform trip count
             const bool live = q0 < quartets;
@@ -309,6 +384,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
                 if (has1) Q.d_s1[e_all] = a1;
             }
         }
+        }
         // (b) embedding tables
 #pragma unroll 1
         for (int t = 0; t < 4; ++t) {
@@ -344,7 +420,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
                 }
             }
         }
-        grid_barrier(Q.barrier, target);
+        grid_barrier(Q.barrier, target, Q.bar_mode);
     }
     if (adam && gtid == 0) { Q.adam_pows[0] = p1; Q.adam_pows[1] = p2; }
 }
@@ -395,7 +471,15 @@ extern "C" int nrc_ncf_epoch_fused(const nrc_ncf_shape* shape, float* mf_user, f
     if (num_steps == 0) return NRC_OK;
     const NcfDev& S = Q.S;
     const int passes = pairwise ? 2 : 1;
-    const size_t smem = ((size_t)S.n_towers * S.s_tower_size + (size_t)kGroups * (2 * passes * S.act_size + kNcfThreads + 8)) * 4;
+    const size_t smem_floats = (size_t)S.n_towers * S.s_tower_size + (size_t)kGroups * (2 * passes * S.act_size + kNcfThreads + 8);
+    const size_t smem = (smem_floats + (kEpThreads / 64) * 16) * 4;
+    Q.sred_off = (int32_t)smem_floats;
+    Q.wblocked = 1; Q.wblocks = 0;
+    for (int l = 0; l < S.n_layers; ++l) {
+        if ((S.in_dim[l] & 3) || (S.out_dim[l] & 3)) Q.wblocked = 0;
+        Q.wblocks += (S.in_dim[l] >> 2) * (S.out_dim[l] >> 2) + (S.out_dim[l] >> 2);
+    }
+    if ((S.act_size & 3) || S.n_layers == 0) Q.wblocked = 0;
     NRC_REQUIRE(smem <= 200 * 1024, NRC_E_LIMIT, "NCF tower needs %zu B of shared memory", smem);
     const size_t need = (size_t)2 * passes * S.act_size * (size_t)batch_size;
     if (need > g_ep_scratch_floats) {
@@ -420,7 +504,7 @@ extern "C" int nrc_ncf_epoch_fused(const nrc_ncf_shape* shape, float* mf_user, f
     Q.scratch = g_ep_scratch; Q.step_loss = step_loss; Q.adam_pows = adam_pows;
     Q.first_step = first_step; Q.num_steps = num_steps;
     Q.batch_size = batch_size; Q.pairwise = pairwise ? 1 : 0; Q.loss_kind = loss_kind; Q.opt_kind = opt_kind;
-    Q.first_stamp = first_stamp; Q.build = first_step == 0 ? 1 : 0;
+    Q.first_stamp = first_stamp; Q.build = first_step == 0 ? 1 : 0; Q.bar_mode = epoch_bar_mode();
     Q.reg_mf = reg_mf; Q.reg_mlp = reg_mlp;
     Q.h0 = hyper_host ? hyper_host[0] : 0.0f; Q.h1 = hyper_host ? hyper_host[1] : 0.0f;
     Q.h2 = hyper_host ? hyper_host[2] : 0.0f; Q.h3 = hyper_host ? hyper_host[3] : 0.0f;

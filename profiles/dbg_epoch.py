@@ -49,13 +49,17 @@ if os.environ.get("NRC_EPOCH_ONLY") is None:
     run(False, 32, 256, 4, "cross_entropy")
     run(True, 64, 4096, 1, "bpr")
 
-if os.environ.get("NRC_EPOCH_DBG") is None:
+if os.environ.get("NRC_EPOCH_ONLY") is None:
     import subprocess
-    env = dict(os.environ, NRC_EPOCH_TWO_BARRIER="1", NRC_EPOCH_ONLY="1", NRC_EPOCH_DBG="0")
-    out = subprocess.run([sys.executable, __file__], env=env, capture_output=True, text=True).stdout.strip().splitlines()
-    print("  two-barrier kernel (NRC_EPOCH_TWO_BARRIER=1): %s" % (out[0] if out else "?"), flush=True)
-    for bits, what in ((3, "two-barrier kernel, barriers only (both phases skipped)"), (1, "two-barrier kernel, optimizer phase + barriers"),
-                       (2, "two-barrier kernel, gradient phase + barriers")):
-        env = dict(os.environ, NRC_EPOCH_DBG=str(bits), NRC_EPOCH_ONLY="1")
-        out = subprocess.run([sys.executable, __file__], env=env, capture_output=True, text=True).stdout.strip().splitlines()
-        print("  NRC_EPOCH_DBG=%d (%s): %s" % (bits, what, out[0] if out else "?"), flush=True)
+
+    def sub(label, **env):
+        e = dict(os.environ, NRC_EPOCH_ONLY="1", **{k: str(v) for k, v in env.items()})
+        out = subprocess.run([sys.executable, __file__], env=e, capture_output=True, text=True).stdout.strip().splitlines()
+        print("  %-70s %s" % (label, out[0] if out else "?"), flush=True)
+    for mode in (0, 1, 2):
+        sub("one-barrier kernel, NRC_BAR_MODE=%d" % mode, NRC_BAR_MODE=mode)
+    for mode in (0, 1, 2):
+        sub("two-barrier kernel, NRC_BAR_MODE=%d" % mode, NRC_BAR_MODE=mode, NRC_EPOCH_TWO_BARRIER=1)
+    sub("two-barrier kernel, barriers only (both phases skipped)", NRC_EPOCH_DBG=3)
+    sub("two-barrier kernel, optimizer phase + barriers", NRC_EPOCH_DBG=1)
+    sub("two-barrier kernel, gradient phase + barriers", NRC_EPOCH_DBG=2)
