@@ -230,41 +230,57 @@ __global__ void __launch_bounds__(256) spmm_csr_fast_kernel(const SpmmArgs A) {
     __shared__ float4 s_part[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int units = (A.n_rows + 7) >> 3;
-    for (int w = blockIdx.x; w < units; w += gridDim.x) {
+    // this warp's row of the NEXT unit is fetched while the current one is processed (the
+    // row_order -> indptr -> indices -> X chain is four dependent L2 round trips otherwise)
+    auto fetch = [&](int w, int& r, int64_t& beg, int64_t& end, bool& lng) {
         const int rr = w * 8 + warp;
-        const bool live = rr < A.n_rows;
-        const int r = live ? (A.row_order ? __ldg(A.row_order + rr) : rr) : 0;
-        const int64_t beg = live ? __ldg(A.indptr + r) : 0, end = live ? __ldg(A.indptr + r + 1) : 0;
-        const bool any_long = __syncthreads_or(live && (end - beg) > kLongRow);
+        const bool live = w < units && rr < A.n_rows;
+        r = live ? (A.row_order ? __ldg(A.row_order + rr) : rr) : 0;
+        beg = live ? __ldg(A.indptr + r) : 0;
+        end = live ? __ldg(A.indptr + r + 1) : 0;
+        if (A.row_order) {      // degree-descending order: a unit holds a long row iff its FIRST row is long
+            const int r0 = (w < units) ? __ldg(A.row_order + w * 8) : 0;
+            lng = (w < units) && (__ldg(A.indptr + r0 + 1) - __ldg(A.indptr + r0)) > kLongRow;
+        } else {
+            lng = false;        // decided per unit with a CTA vote below
+        }
+    };
+    int r, rn; int64_t beg, end, begn, endn; bool lng, lngn;
+    fetch(blockIdx.x, r, beg, end, lng);
+    for (int w = blockIdx.x; w < units; w += gridDim.x) {
+        fetch(w + gridDim.x, rn, begn, endn, lngn);
+        const bool live = w * 8 + warp < A.n_rows;
+        const bool any_long = A.row_order ? lng : (bool)__syncthreads_or(live && (end - beg) > kLongRow);
         if (!any_long) {
             if (live) {
                 float4 acc;
                 spmm_accumulate<G>(A, beg, end, 32, lane, acc);
                 if (lane < G) spmm_epilogue<G>(A, r, lane, acc);
             }
-            continue;
-        }
-        // a unit with a long row: every row of the unit by the whole CTA, one after the other
-        for (int k = 0; k < 8; ++k) {
-            const int rk = w * 8 + k;
-            if (rk >= A.n_rows) break;
-            const int row = A.row_order ? __ldg(A.row_order + rk) : rk;
-            const int64_t b0 = __ldg(A.indptr + row), e0 = __ldg(A.indptr + row + 1);
-            float4 acc;
-            spmm_accumulate<G>(A, b0 + 32 * warp, e0, 32 * 8, lane, acc);
-            s_part[warp][lane] = acc;
-            __syncthreads();
-            if (warp == 0 && lane < G) {
-                float4 t = s_part[0][lane];
+        } else {
+            // a unit with a long row: every row of the unit by the whole CTA, one after the other
+            for (int k = 0; k < 8; ++k) {
+                const int rk = w * 8 + k;
+                if (rk >= A.n_rows) break;
+                const int row = A.row_order ? __ldg(A.row_order + rk) : rk;
+                const int64_t b0 = __ldg(A.indptr + row), e0 = __ldg(A.indptr + row + 1);
+                float4 acc;
+                spmm_accumulate<G>(A, b0 + 32 * warp, e0, 32 * 8, lane, acc);
+                s_part[warp][lane] = acc;
+                __syncthreads();
+                if (warp == 0 && lane < G) {
+                    float4 t = s_part[0][lane];
 #pragma unroll
-                for (int q = 1; q < 8; ++q) {
-                    const float4 u = s_part[q][lane];
-                    t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                    for (int q = 1; q < 8; ++q) {
+                        const float4 u = s_part[q][lane];
+                        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                    }
+                    spmm_epilogue<G>(A, row, lane, t);
                 }
-                spmm_epilogue<G>(A, row, lane, t);
+                __syncthreads();
             }
-            __syncthreads();
         }
+        r = rn; beg = begn; end = endn; lng = lngn;
     }
 }
 

@@ -86,3 +86,30 @@ def test_route_triplets_to_user_owner_world_size_2_gloo():
     out = mp.Manager().dict()
     mp.spawn(_route_worker, args=(ws, _free_port(), out), nprocs=ws, join=True)
     assert [out[r] for r in range(ws)] == [1, 1]
+
+
+def test_item_shard_csr_restriction_partitions_every_row():
+    """Host side of the item-sharded evaluator (evaluator/sharded.py::ItemShard.restrict_csr): the train CSR
+    cut by item range keeps every (user, item) entry in exactly one shard, with local ids, rows still sorted."""
+    import numpy as np
+    from neurec_b200.evaluator import sharded
+    rs = np.random.RandomState(0)
+    nu, ni, G = 50, 1000, 8
+    rows = [np.unique(rs.randint(0, ni, rs.randint(0, 40))) for _ in range(nu)]
+    ptr = np.zeros(nu + 1, np.int64); ptr[1:] = np.cumsum([len(r) for r in rows])
+    idx = np.concatenate(rows).astype(np.int32)
+    per = (ni + G - 1) // G
+    rebuilt = [[] for _ in range(nu)]
+    for g in range(G):
+        lo, hi = g * per, min(ni, (g + 1) * per)
+        lp, li = sharded.ItemShard.restrict_csr(ptr, idx, lo, hi)
+        assert lp[0] == 0 and len(lp) == nu + 1
+        for u in range(nu):
+            loc = li[lp[u]:lp[u + 1]]
+            assert (np.diff(loc) > 0).all() and (loc >= 0).all() and (loc < hi - lo).all()
+            rebuilt[u].extend((loc + lo).tolist())
+    for u in range(nu):
+        assert rebuilt[u] == rows[u].tolist()
+    # contiguous user blocks used by the all-gather of user rows
+    blocks = [sharded.local_slice(37, r, 4) for r in range(4)]
+    assert blocks[0][0] == 0 and blocks[-1][1] == 37 and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
