@@ -176,7 +176,7 @@ def test_csr_fed_sgd_kernel_equals_build_then_step(dim):
     restatement, on an epoch without repeated rows (where the in-place step is order-free)."""
     from neurec_b200 import ops
     from neurec_b200.util import peer
-    nu, ni, n = 3000, 400_000, 3000
+    nu, ni, n = 300, 400_000, 300
     rs = np.random.RandomState(dim)
     tp = np.arange(nu + 1, dtype=np.int64)                      # one positive per user
     pos_items = rs.permutation(ni)[:nu].astype(np.int32)
@@ -204,8 +204,8 @@ def test_csr_fed_sgd_kernel_equals_build_then_step(dim):
     dU, dV = dev(U0), dev(V0)
     loss = torch.zeros(1, device="cuda")
     a = (dev(tp), dev(pos_items), dev(pos_users), dev(pos_items), ni, True, seed, 2)
-    ops.mf_bpr_sgd_epoch(dU, peer.single(dV), *a, 0, 1111, lr, reg, loss)
-    ops.mf_bpr_sgd_epoch(dU, peer.single(dV), *a, 1111, n - 1111, lr, reg, loss)
+    ops.mf_bpr_sgd_epoch(dU, peer.single(dV), *a, 0, 111, lr, reg, loss)
+    ops.mf_bpr_sgd_epoch(dU, peer.single(dV), *a, 111, n - 111, lr, reg, loss)
     assert np.abs(dU.cpu().numpy() - Uw).max() < 2e-6 and np.abs(dV.cpu().numpy() - Vw).max() < 2e-6
     assert abs(float(loss) - want_loss) < 1e-3 * want_loss
     # (a) build + step
@@ -303,7 +303,7 @@ def test_lazy_adam_variant_on_a_duplicate_free_epoch(dim):
     epoch without repeated rows it is exactly LazyAdam -- only the batch's rows move, by the Adam
     formulas with this step's lr_t; untouched rows and their slots stay bit-identical."""
     from neurec_b200 import ops
-    nu, ni, n = 2000, 300_000, 2000
+    nu, ni, n = 300, 300_000, 300
     rs = np.random.RandomState(dim + 1)
     tp = np.arange(nu + 1, dtype=np.int64)
     pos_items = rs.permutation(ni)[:nu].astype(np.int32)
