@@ -23,6 +23,8 @@
 //   ncf_wgrad_kernel   dW_l = A_l^T . Delta_l and db_l = colsum(Delta_l) over the batch: one
 //                      thread per weight entry and batch slice, coalesced over the output
 //                      column, one RED.ADD per entry and slice.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ncf.cuh"
 #include "optim.cuh"
@@ -450,6 +452,141 @@ ncf_scores_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ u
     }
 }
 
+// ----------------------------------------------------------------------------------------
+// Fast predict for the reference's default tower (layers [64, 32, 16], mlp_dim 32; NeuMF.py:163-168 /
+// MLP.py:136-140 score every item for every test user).  The first layer factorises over the concat:
+//   relu([mu, mi] W0 + b0) = relu(A_u + B_i),  A_u = mu W0[:32] + b0 (per user),  B_i = mi W0[32:] (per item)
+// so the 64x64 layer costs 64 adds per (user, item) pair once B is tabulated (ncf_item_part_kernel).
+// Layers 2 and 3 are [pairs, 64] x [64, 32] x [32, 16] products done as register-tiled SIMT GEMMs:
+// a warp owns 32 pairs; h1 of its pairs sits in shared memory (broadcast float4 reads, 1 LDS per 4
+// FMAs), lane j keeps column j of W1 (64 registers) and 32 accumulators, then lanes (j, half) keep a
+// column of W2 and do 16 pairs each; the GMF dot is added and the 16 outputs summed by shuffles
+// (NeuMF.py:85 reduce_sum(concat(mf, mlp))).  fp32 FMA throughout: same values as the generic
+// kernel up to the association of the first layer's sum.
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ncf_item_part_kernel(const float* __restrict__ mlp_item, const float* __restrict__ dense, int num_items,
+                     float* __restrict__ B) {
+    // B[i][j] = sum_k mlp_item[i][k] * W0[32 + k][j];  thread = (item, j) with j fastest
+    __shared__ float sW[32 * 64];
+    for (int e = threadIdx.x; e < 32 * 64; e += blockDim.x) sW[e] = dense[32 * 64 + e];
+    __syncthreads();
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)num_items * 64; t += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t >> 6), j = (int)(t & 63);
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) acc = fmaf(__ldg(mlp_item + (size_t)i * 32 + k), sW[k * 64 + j], acc);
+        B[t] = acc;
+    }
+}
+
+constexpr int kSfWarps = 8;
+constexpr int kSfH1Stride = 68;   // floats per pair row of h1 (64 + 4: float4 rows, conflict-free broadcast)
+constexpr int kSfH2Stride = 36;
+
+__global__ void __launch_bounds__(kSfWarps * 32)
+ncf_scores_fast_kernel(const float* __restrict__ mf_user, const float* __restrict__ mf_item, int mf_dim,
+                       const float* __restrict__ mlp_user, const float* __restrict__ dense,
+                       const float* __restrict__ B, const int32_t* __restrict__ users, int num_items,
+                       float* __restrict__ scores) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int W0o = 0, B0o = 64 * 64, W1o = B0o + 64, B1o = W1o + 64 * 32, W2o = B1o + 32, B2o = W2o + 32 * 16;
+    float* sA = sm;                                   // [64]  A_u
+    float* sMf = sA + 64;                             // [mf_dim] GMF user row
+    float* sH1 = sMf + ((mf_dim + 3) & ~3);           // per warp [32][68]
+    float* sH2 = sH1 + kSfWarps * 32 * kSfH1Stride;   // per warp [32][36]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int u = users[blockIdx.x];
+    // A_u = mu . W0[:32] + b0
+    if (threadIdx.x < 64) {
+        float acc = __ldg(dense + B0o + threadIdx.x);
+        for (int k = 0; k < 32; ++k) acc = fmaf(__ldg(mlp_user + (size_t)u * 32 + k), __ldg(dense + W0o + k * 64 + threadIdx.x), acc);
+        sA[threadIdx.x] = acc;
+    }
+    for (int k = threadIdx.x; k < mf_dim; k += blockDim.x) sMf[k] = mf_user[(size_t)u * mf_dim + k];
+    // lane j: column j of W1 (layer 2) and, for layer 3, column (lane & 15) of W2
+    float w1[64], w2[32];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) w1[k] = __ldg(dense + W1o + k * 32 + lane);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) w2[k] = __ldg(dense + W2o + k * 16 + (lane & 15));
+    const float b1 = __ldg(dense + B1o + lane), b2 = __ldg(dense + B2o + (lane & 15));
+    __syncthreads();
+    float* h1 = sH1 + warp * 32 * kSfH1Stride;
+    float* h2 = sH2 + warp * 32 * kSfH2Stride;
+    const int tiles = (num_items + 31) >> 5;
+    for (int tile = blockIdx.y * kSfWarps + warp; tile < tiles; tile += gridDim.y * kSfWarps) {
+        const int i0 = tile * 32;
+        // h1[p][k] = relu(A_u[k] + B[i0 + p][k]): lanes sweep k (coalesced rows of B)
+        for (int p = 0; p < 32; ++p) {
+            const int it = i0 + p;
+            const bool ok = it < num_items;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int k = lane + 32 * t;
+                h1[p * kSfH1Stride + k] = ok ? fmaxf(sA[k] + __ldg(B + (size_t)it * 64 + k), 0.0f) : 0.0f;
+            }
+        }
+        // GMF part of pair p = lane
+        float mf = 0.0f;
+        {
+            const int it = i0 + lane;
+            if (it < num_items)
+                for (int k = 0; k < mf_dim; ++k) mf = fmaf(sMf[k], __ldg(mf_item + (size_t)it * mf_dim + k), mf);
+        }
+        __syncwarp();
+        // layer 2: acc[p] = sum_k h1[p][k] * W1[k][lane]
+        float acc[32];
+#pragma unroll
+        for (int p = 0; p < 32; ++p) acc[p] = 0.0f;
+#pragma unroll
+        for (int k4 = 0; k4 < 16; ++k4) {
+#pragma unroll
+            for (int p = 0; p < 32; ++p) {
+                const float4 h = *reinterpret_cast<const float4*>(h1 + p * kSfH1Stride + k4 * 4);
+                acc[p] = fmaf(h.x, w1[k4 * 4 + 0], acc[p]);
+                acc[p] = fmaf(h.y, w1[k4 * 4 + 1], acc[p]);
+                acc[p] = fmaf(h.z, w1[k4 * 4 + 2], acc[p]);
+                acc[p] = fmaf(h.w, w1[k4 * 4 + 3], acc[p]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 32; ++p) h2[p * kSfH2Stride + lane] = fmaxf(acc[p] + b1, 0.0f);
+        __syncwarp();
+        // layer 3: lane (j = lane & 15, half = lane >> 4) does pairs p = half, half + 2, ...
+        const int half = lane >> 4;
+        float out[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int p = 2 * q + half;
+            float a = 0.0f;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+                const float4 h = *reinterpret_cast<const float4*>(h2 + p * kSfH2Stride + k4 * 4);
+                a = fmaf(h.x, w2[k4 * 4 + 0], a); a = fmaf(h.y, w2[k4 * 4 + 1], a);
+                a = fmaf(h.z, w2[k4 * 4 + 2], a); a = fmaf(h.w, w2[k4 * 4 + 3], a);
+            }
+            a = fmaxf(a + b2, 0.0f);
+            // sum over the 16 outputs (lanes of this half)
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(kFull, a, o);
+            out[q] = a;
+        }
+        // pair p = lane: its MLP sum sits in out[lane >> 1] of the lanes of half (lane & 1)
+        float mine = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float v = __shfl_sync(kFull, out[q], (lane & 1) * 16);   // any lane of that half holds the sum
+            mine = ((lane >> 1) == q) ? v : mine;
+        }
+        if (i0 + lane < num_items) scores[(size_t)blockIdx.x * num_items + i0 + lane] = mf + mine;
+        __syncwarp();
+    }
+}
+
+static float* g_item_part = nullptr;
+static size_t g_item_part_floats = 0;
+
 // library-owned scratch for activations / deltas, grown on demand (never inside a capture:
 // callers warm up once before capturing a step graph)
 static float* g_scratch = nullptr;
@@ -539,6 +676,36 @@ extern "C" int nrc_ncf_scores(const nrc_ncf_shape* shape, const float* mf_user, 
     S.n_towers = 1;
     NcfPtrs P{mf_user, mf_item, mlp_user, mlp_item, dense, nullptr, nullptr, nullptr, nullptr,
               nullptr, nullptr, nullptr};
+    const bool fast = S.n_layers == 3 && S.mlp_dim == 32 && S.out_dim[0] == 64 && S.out_dim[1] == 32 && S.out_dim[2] == 16 &&
+                      S.mf_dim <= 256 && !getenv("NRC_NCF_SCORES_GENERIC");
+    if (fast) {
+        const size_t need = (size_t)num_items * 64;
+        if (need > g_item_part_floats) {
+            if (g_item_part) NRC_CUDA_CHECK(cudaFree(g_item_part));
+            g_item_part = nullptr; g_item_part_floats = 0;
+            NRC_CUDA_CHECK(cudaMalloc(&g_item_part, need * sizeof(float)));
+            g_item_part_floats = need;
+        }
+        cudaStream_t st = as_stream(stream);
+        int64_t pb = ((int64_t)num_items * 64 + 255) / 256;
+        if (pb > (int64_t)sm_count() * 8) pb = (int64_t)sm_count() * 8;
+        ncf_item_part_kernel<<<(unsigned)pb, 256, 0, st>>>(mlp_item, dense, num_items, g_item_part);
+        NRC_CUDA_CHECK(cudaGetLastError());
+        const size_t fsmem = (64 + ((S.mf_dim + 3) & ~3) + (size_t)kSfWarps * 32 * (kSfH1Stride + kSfH2Stride)) * 4;
+        static bool fattr = false;
+        if (!fattr) {
+            NRC_CUDA_CHECK(cudaFuncSetAttribute(ncf_scores_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            fattr = true;
+        }
+        const int tiles = (num_items + 31) / 32;
+        int gy = (n_users >= sm_count() * 2) ? 1 : (sm_count() * 2 + n_users - 1) / n_users;
+        if (gy > (tiles + kSfWarps - 1) / kSfWarps) gy = (tiles + kSfWarps - 1) / kSfWarps;
+        if (gy < 1) gy = 1;
+        ncf_scores_fast_kernel<<<dim3(n_users, gy), kSfWarps * 32, fsmem, st>>>(mf_user, mf_item, S.mf_dim, mlp_user, dense,
+                                                                                  g_item_part, users, num_items, scores);
+        NRC_CUDA_CHECK(cudaGetLastError());
+        return NRC_OK;
+    }
     const size_t smem = ((size_t)S.s_tower_size + (size_t)kNcfWarps * S.act_size) * 4;
     NRC_REQUIRE(smem <= 200 * 1024, NRC_E_LIMIT, "NCF tower needs %zu B of shared memory", smem);
     static bool attr_done = false;
