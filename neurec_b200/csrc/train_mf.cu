@@ -165,18 +165,20 @@ struct RowShards {
     float* base[8];
     int32_t rows_per_shard;   // 0: a single local table at base[0]
     int32_t self;             // this rank's shard (rows of other shards live in peer memory)
-    int32_t vec_remote;       // 1: vector REDs on peer rows too (NRC_PEER_VEC_RED=1; default scalar REDs)
+    int32_t vec_remote;       // how rows of OTHER ranks are updated: 0 scalar REDs (default), 1 vector REDs,
+                              // 2 one bulk reduce-add of the whole row (cp.reduce.async.bulk from shared memory) -- NRC_PEER_VEC_RED
+    int32_t force_remote;     // debug (NRC_FORCE_REMOTE_PATH=1): take the remote update path for local item rows too
     // SHARDED is a compile-time switch and the shard base is picked with constant indices only, so
     // the struct stays in the kernel-parameter constant bank (a dynamic index would spill it to
     // local memory and cost the single-GPU kernel ~15 % of its bandwidth).
     template <bool SHARDED>
     __device__ __forceinline__ float* row(int32_t id, int D, bool& remote) const {
         if constexpr (!SHARDED) {
-            remote = false;
+            remote = force_remote != 0;
             return base[0] + (size_t)id * D;
         } else {
             const int32_t owner = id / rows_per_shard;
-            remote = owner != self;
+            remote = owner != self || force_remote;
             float* b = base[0];
 #pragma unroll
             for (int r = 1; r < 8; ++r) b = (owner == r) ? base[r] : b;
@@ -297,6 +299,28 @@ __device__ __forceinline__ void ld_vec(const float* p, float (&v)[VEC]) {
     }
 }
 
+// Update of a row that lives on another rank, by mode (RowShards::vec_remote).  Mode 2 stages the warp's
+// delta row in shared memory and issues ONE bulk reduce-add of the whole row through the copy engine
+// (cp.reduce.async.bulk ... .add.f32): a single transaction per row over NVLink instead of 32 x VEC REDs.
+template <int VEC>
+__device__ __forceinline__ void remote_row_update(float* p_row_lane, const float (&d)[VEC], int mode, float* stage, int lane) {
+    if (mode == 2) {
+#pragma unroll
+        for (int t = 0; t < VEC; ++t) stage[lane * VEC + t] = d[t];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            float* row = p_row_lane;     // lane 0 points at the start of the row
+            const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stage);
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                         ::"l"(row), "r"(saddr), "r"((uint32_t)(32 * VEC * 4)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    } else {
+        red_row<VEC>(p_row_lane, d, mode == 0);
+    }
+}
+
 template <int VEC, bool SHARDED>
 __global__ void __launch_bounds__(256)
 mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const EpochSpec E, int64_t first,
@@ -304,7 +328,9 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
     constexpr int D = 32 * VEC;
     constexpr int CH = 256;
     __shared__ int32_t s_u[CH], s_i[CH], s_j[CH];
+    __shared__ __align__(16) float s_stage[8][4][D];      // bulk-reduce staging: 4 rows per warp (2 triplets x 2 item rows)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rmode = V.vec_remote;
     float loss_acc = 0.0f;
     for (int64_t c0 = (int64_t)blockIdx.x * CH; c0 < count; c0 += (int64_t)gridDim.x * CH) {
         const int n = (count - c0 < CH) ? (int)(count - c0) : CH;
@@ -315,6 +341,10 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
         }
         __syncthreads();
         for (int t0 = warp * 2; t0 < n; t0 += 16) {
+            if (rmode == 2) {   // the staging rows of the previous pair must have been read by the copy engine
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
             const bool two = t0 + 1 < n;
             const int t1 = two ? t0 + 1 : t0;
             bool ri0, rj0, ri1, rj1;
@@ -348,7 +378,9 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
                 dvi[t] = -lr * (g0 * a0[t] + reg * b0[t]);
                 dvj[t] = -lr * (-g0 * a0[t] + reg * c0v[t]);
             }
-            red_row<VEC>(pu0, du, false); red_row<VEC>(qi0, dvi, ri0 && !V.vec_remote); red_row<VEC>(qj0, dvj, rj0 && !V.vec_remote);
+            red_row<VEC>(pu0, du, false);
+            if (ri0) remote_row_update<VEC>(qi0, dvi, rmode, s_stage[warp][0], lane); else red_row<VEC>(qi0, dvi, false);
+            if (rj0) remote_row_update<VEC>(qj0, dvj, rmode, s_stage[warp][1], lane); else red_row<VEC>(qj0, dvj, false);
             loss_acc += l0;
             if (two) {
 #pragma unroll
@@ -357,12 +389,15 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
                     dvi[t] = -lr * (g1 * a1[t] + reg * b1[t]);
                     dvj[t] = -lr * (-g1 * a1[t] + reg * c1v[t]);
                 }
-                red_row<VEC>(pu1, du, false); red_row<VEC>(qi1, dvi, ri1 && !V.vec_remote); red_row<VEC>(qj1, dvj, rj1 && !V.vec_remote);
+                red_row<VEC>(pu1, du, false);
+                if (ri1) remote_row_update<VEC>(qi1, dvi, rmode, s_stage[warp][2], lane); else red_row<VEC>(qi1, dvi, false);
+                if (rj1) remote_row_update<VEC>(qj1, dvj, rmode, s_stage[warp][3], lane); else red_row<VEC>(qj1, dvj, false);
                 loss_acc += l1;
             }
         }
         __syncthreads();
     }
+    if (rmode == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk reduces performed
     if (lane == 0 && loss) atomicAdd(loss, loss_acc);
 }
 
@@ -591,9 +626,11 @@ extern "C" int nrc_mf_bpr_sgd_epoch(float* user_table, float* const* item_shards
     SV.rows_per_shard = world > 1 ? (int32_t)items_per_shard : 0;
     SV.self = self_rank;
     {
-        static int vec = -1;
+        static int vec = -1, force = -1;
         if (vec < 0) { const char* e = getenv("NRC_PEER_VEC_RED"); vec = e ? atoi(e) : 0; }
+        if (force < 0) { const char* e = getenv("NRC_FORCE_REMOTE_PATH"); force = e ? atoi(e) : 0; }
         SV.vec_remote = vec;
+        SV.force_remote = force;
     }
     return launch_bpr_sgd_stream(user_table, SV, dim, E, first, count, lr, reg, loss, as_stream(stream));
 }
