@@ -544,7 +544,7 @@ static size_t g_e1_floats = 0;
 
 int epoch_bar_mode() {
     static int mode = -1;
-    if (mode < 0) { const char* e = getenv("NRC_BAR_MODE"); mode = e ? atoi(e) : 2; }
+    if (mode < 0) { const char* e = getenv("NRC_BAR_MODE"); mode = e ? atoi(e) : 0; }   // 0 measured fastest (profiles/r2_dbg_epoch.txt)
     return mode;
 }
 
@@ -660,8 +660,12 @@ extern "C" int nrc_mf_epoch_fused(float* user_table, float* item_table, int32_t 
     cudaStream_t st = as_stream(stream);
     NRC_CUDA_CHECK(cudaMemsetAsync(P.barrier, 0, sizeof(unsigned int), st));
 
+    // Default: the two-barrier kernel.  The one-barrier (pull-based) kernel is correct and tested
+    // (NRC_EPOCH_TWO_BARRIER=0) but measured slower on B200: 5.9 vs 5.7 us per step -- a grid barrier costs
+    // ~1.7 us either way and the pull (12 row loads + the optimizer math on three rows per triplet, in the
+    // critical path of every gradient warp) costs more than the barrier it removes.
     static int two_barrier = -1;
-    if (two_barrier < 0) { const char* e = getenv("NRC_EPOCH_TWO_BARRIER"); two_barrier = e ? atoi(e) : 0; }
+    if (two_barrier < 0) { const char* e = getenv("NRC_EPOCH_TWO_BARRIER"); two_barrier = e ? atoi(e) : 1; }
     if (!two_barrier && !P.dbg && (dim == 32 || dim == 64 || dim == 128)) {
         // one barrier per step: scratch = state set 1 (var + slots of both tables), G[1], G[2], stamps set 1
         const size_t eAll = (size_t)(num_users + num_items) * dim;

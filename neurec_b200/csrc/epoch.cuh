@@ -118,7 +118,7 @@ int epoch_spec_init(EpochSpec& E, const int64_t* tptr, const int32_t* tidx, cons
 // (fence cumulativity), thread 0's acquire fence orders them before every later read of the CTA.
 // mode (NRC_BAR_MODE, measurement knob): 0 release-RED + acquire-load polling; 1 fence + relaxed atomic +
 // volatile polling + fence (cooperative-groups style); 2 release-RED + relaxed polling + one acquire fence.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target, int mode = 2) {
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target, int mode = 0) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
@@ -146,6 +146,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     __syncthreads();
 }
 
-int epoch_bar_mode();   // epoch.cu: NRC_BAR_MODE, default 2
+int epoch_bar_mode();   // epoch.cu: NRC_BAR_MODE, default 0
 
 }  // namespace nrc

@@ -19,6 +19,8 @@
 // order; lane owns dim/32 consecutive columns so every gathered E row is one coalesced
 // 128/256/512 B request; (col, val) pairs are fetched 32 at a time and shuffled out.  The graph
 // and E (18 MB for gowalla) are L2-resident; the bound is L2 gather bandwidth.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "optim.cuh"
 
@@ -168,12 +170,12 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs A) {
 // ----------------------------------------------------------------------------------------
 constexpr int kLongRow = 192;
 
-template <int G>   // lanes per gathered row: dim == 4 * G, G in {8, 16, 32}
+template <int G, int UNMAX>   // lanes per gathered row: dim == 4 * G, G in {8, 16, 32}; load instructions in flight
 __device__ __forceinline__ void spmm_accumulate(const SpmmArgs& A, int64_t beg, int64_t end, int64_t seg_stride,
                                                 int lane, float4& acc) {
     constexpr int NPI = 32 / G;            // non-zeros per load instruction
     constexpr int STEPS = 32 / NPI;        // load instructions per 32-nnz segment
-    constexpr int UN = (STEPS < 8) ? STEPS : 8;
+    constexpr int UN = (STEPS < UNMAX) ? STEPS : UNMAX;
     const int grp = lane / G, sub = lane % G;
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
     for (int64_t p = beg; p < end; p += seg_stride) {
@@ -225,8 +227,9 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& A, int r, int sub,
     }
 }
 
-template <int G>
-__global__ void __launch_bounds__(256) spmm_csr_fast_kernel(const SpmmArgs A) {
+// UNMAX = 4: 4 loads in flight per warp, 64 registers, 4 CTAs per SM (default); UNMAX = 8: 8 in flight, 3 CTAs per SM
+template <int G, int UNMAX>
+__global__ void __launch_bounds__(256, UNMAX == 4 ? 4 : 3) spmm_csr_fast_kernel(const SpmmArgs A) {
     __shared__ float4 s_part[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int units = (A.n_rows + 7) >> 3;
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(256) spmm_csr_fast_kernel(const SpmmArgs A) {
         if (!any_long) {
             if (live) {
                 float4 acc;
-                spmm_accumulate<G>(A, beg, end, 32, lane, acc);
+                spmm_accumulate<G, UNMAX>(A, beg, end, 32, lane, acc);
                 if (lane < G) spmm_epilogue<G>(A, r, lane, acc);
             }
         } else {
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(256) spmm_csr_fast_kernel(const SpmmArgs A) {
                 const int row = A.row_order ? __ldg(A.row_order + rk) : rk;
                 const int64_t b0 = __ldg(A.indptr + row), e0 = __ldg(A.indptr + row + 1);
                 float4 acc;
-                spmm_accumulate<G>(A, b0 + 32 * warp, e0, 32 * 8, lane, acc);
+                spmm_accumulate<G, UNMAX>(A, b0 + 32 * warp, e0, 32 * 8, lane, acc);
                 s_part[warp][lane] = acc;
                 __syncthreads();
                 if (warp == 0 && lane < G) {
@@ -294,9 +297,17 @@ static int spmm_launch(const SpmmArgs& A, cudaStream_t st) {
     if (!g_spmm_exact && (A.dim == 32 || A.dim == 64 || A.dim == 128)) {
         int64_t blocks = ((int64_t)A.n_rows + 7) / 8;
         if (blocks > cap) blocks = cap;
-        if (A.dim == 32) spmm_csr_fast_kernel<8><<<(unsigned)blocks, threads, 0, st>>>(A);
-        else if (A.dim == 64) spmm_csr_fast_kernel<16><<<(unsigned)blocks, threads, 0, st>>>(A);
-        else spmm_csr_fast_kernel<32><<<(unsigned)blocks, threads, 0, st>>>(A);
+        static int un = -1;
+        if (un < 0) { const char* e = getenv("NRC_SPMM_UN"); un = (e && atoi(e) == 8) ? 8 : 4; }
+        if (un == 8) {
+            if (A.dim == 32) spmm_csr_fast_kernel<8, 8><<<(unsigned)blocks, threads, 0, st>>>(A);
+            else if (A.dim == 64) spmm_csr_fast_kernel<16, 8><<<(unsigned)blocks, threads, 0, st>>>(A);
+            else spmm_csr_fast_kernel<32, 8><<<(unsigned)blocks, threads, 0, st>>>(A);
+        } else {
+            if (A.dim == 32) spmm_csr_fast_kernel<8, 4><<<(unsigned)blocks, threads, 0, st>>>(A);
+            else if (A.dim == 64) spmm_csr_fast_kernel<16, 4><<<(unsigned)blocks, threads, 0, st>>>(A);
+            else spmm_csr_fast_kernel<32, 4><<<(unsigned)blocks, threads, 0, st>>>(A);
+        }
         NRC_CUDA_CHECK(cudaGetLastError());
         return NRC_OK;
     }

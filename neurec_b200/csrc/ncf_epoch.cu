@@ -51,6 +51,7 @@ struct NcfEpochParams {
     unsigned int* barrier;
     int64_t n_used, first_step, num_steps, steps_total;
     int32_t batch_size, pairwise, loss_kind, opt_kind, first_stamp, build, bar_mode;
+    int32_t sw_floats;                     // shared-memory floats of the weight copy (towers, rounded up to 4)
     int32_t wblocked, wblocks, sred_off;   // blocked weight-gradient path: 4 x 4 blocks per tower; smem offset (floats) of its reduction slots
     float reg_mf, reg_mlp, h0, h1, h2, h3;
 };
@@ -68,14 +69,14 @@ __device__ __forceinline__ float group_sum(float v, float* red, int tid, int grp
     return r;
 }
 
-// a_out = relu(a_in . W + b); W in shared memory with row stride out + 1
+// a_out = relu(a_in . W + b); W in shared memory exactly as in global memory (row stride out)
 __device__ __forceinline__ void fwd_layer(const float* __restrict__ W, const float* __restrict__ B, int in, int out,
                                           const float* a_in, float* a_out, float* part, int tid, int grp) {
     if (out <= kNcfThreads && kNcfThreads % out == 0 && in % (kNcfThreads / out) == 0) {
         const int G = kNcfThreads / out, kpg = in / G, j = tid % out, g = tid / out;
         float acc = 0.0f;
 #pragma unroll 8
-        for (int kk = 0; kk < kpg; ++kk) acc = fmaf(a_in[g * kpg + kk], W[(g * kpg + kk) * (out + 1) + j], acc);
+        for (int kk = 0; kk < kpg; ++kk) acc = fmaf(a_in[g * kpg + kk], W[(g * kpg + kk) * out + j], acc);
         part[tid] = acc;
         group_sync(grp);
         if (tid < out) {
@@ -86,28 +87,34 @@ __device__ __forceinline__ void fwd_layer(const float* __restrict__ W, const flo
     } else {
         for (int j = tid; j < out; j += kNcfThreads) {
             float acc = B[j];
-            for (int k = 0; k < in; ++k) acc = fmaf(a_in[k], W[k * (out + 1) + j], acc);
+            for (int k = 0; k < in; ++k) acc = fmaf(a_in[k], W[k * out + j], acc);
             a_out[j] = fmaxf(acc, 0.0f);
         }
     }
     group_sync(grp);
 }
 
-// d_in[k] = (mask ? a_in[k] > 0 : 1) * sum_j W[k][j] d_out[j]
+// d_in[k] = (mask ? a_in[k] > 0 : 1) * sum_j W[k][j] d_out[j].  Threads (k, jq) walk their jpt columns
+// starting at a k-dependent rotation so that the lanes of a warp (16 or 8 different k) hit different
+// banks of the unpadded row-major W.
 __device__ __forceinline__ void bwd_layer(const float* __restrict__ W, int in, int out, const float* d_out,
                                           const float* a_in, float* d_in, bool mask, int tid, int grp) {
     if (in <= kNcfThreads && kNcfThreads % in == 0 && (kNcfThreads / in) <= 32 && out % (kNcfThreads / in) == 0) {
         const int tpr = kNcfThreads / in, jpt = out / tpr, k = tid / tpr, jq = tid % tpr;
         float s = 0.0f;
+        int jj = k % jpt;
 #pragma unroll 8
-        for (int jj = 0; jj < jpt; ++jj) s = fmaf(W[k * (out + 1) + jq * jpt + jj], d_out[jq * jpt + jj], s);
+        for (int c = 0; c < jpt; ++c) {
+            s = fmaf(W[k * out + jq * jpt + jj], d_out[jq * jpt + jj], s);
+            jj = (jj + 1 == jpt) ? 0 : jj + 1;
+        }
         for (int o = tpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
         if (jq == 0) d_in[k] = mask ? ((a_in[k] > 0.0f) ? s : 0.0f) : s;
     } else {
         const int lane = tid & 31, wrp = tid >> 5;
         for (int k = wrp; k < in; k += kNcfThreads / 32) {
             float s = 0.0f;
-            for (int j = lane; j < out; j += kWarp) s = fmaf(W[k * (out + 1) + j], d_out[j], s);
+            for (int j = lane; j < out; j += kWarp) s = fmaf(W[k * out + j], d_out[j], s);
             s = warp_sum(s);
             if (lane == 0) d_in[k] = mask ? ((a_in[k] > 0.0f) ? s : 0.0f) : s;
         }
@@ -132,9 +139,9 @@ __device__ __forceinline__ void ncf_sample(const NcfEpochParams& Q, const float*
         for (int k = tid; k < 2 * MD; k += kNcfThreads)
             act[k] = (k < MD) ? __ldcg(P.mlp_user + (size_t)u * MD + k) : __ldcg(P.mlp_item + (size_t)it[p] * MD + (k - MD));
         group_sync(grp);
-        const float* tw = sW + (size_t)((p == 1 && S.n_towers == 2) ? 1 : 0) * S.s_tower_size;
+        const float* tw = sW + (size_t)((p == 1 && S.n_towers == 2) ? 1 : 0) * S.tower_size;
         for (int l = 0; l < L; ++l)
-            fwd_layer(tw + S.sw_off[l], tw + S.sb_off[l], S.in_dim[l], S.out_dim[l], act + S.a_off[l], act + S.a_off[l + 1],
+            fwd_layer(tw + S.w_off[l], tw + S.b_off[l], S.in_dim[l], S.out_dim[l], act + S.a_off[l], act + S.a_off[l + 1],
                       part, tid, grp);
         float s = 0.0f;
         if (L > 0)
@@ -167,7 +174,7 @@ __device__ __forceinline__ void ncf_sample(const NcfEpochParams& Q, const float*
     float sq_mf = 0.f, sq_mlp = 0.f;
     for (int p = 0; p < passes; ++p) {
         const float gp = (p == 0) ? g : -g;
-        const float* tw = sW + (size_t)((p == 1 && S.n_towers == 2) ? 1 : 0) * S.s_tower_size;
+        const float* tw = sW + (size_t)((p == 1 && S.n_towers == 2) ? 1 : 0) * S.tower_size;
         float* act = sAct + p * S.act_size;
         float* del = sDel + p * S.act_size;
         if (L > 0) {
@@ -175,7 +182,7 @@ __device__ __forceinline__ void ncf_sample(const NcfEpochParams& Q, const float*
                 del[S.a_off[L] + j] = (act[S.a_off[L] + j] > 0.0f) ? gp : 0.0f;     // ReluGrad on the last layer
             group_sync(grp);
             for (int l2 = L - 1; l2 >= 0; --l2)
-                bwd_layer(tw + S.sw_off[l2], S.in_dim[l2], S.out_dim[l2], del + S.a_off[l2 + 1], act + S.a_off[l2],
+                bwd_layer(tw + S.w_off[l2], S.in_dim[l2], S.out_dim[l2], del + S.a_off[l2 + 1], act + S.a_off[l2],
                           del + S.a_off[l2], l2 > 0, tid, grp);
         }
         for (int k = tid; k < S.mf_dim; k += kNcfThreads) {
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
     const int tid_cta = threadIdx.x, grp = tid_cta / kNcfThreads, tid = tid_cta % kNcfThreads;
     const int passes = Q.pairwise ? 2 : 1;
     float* sW = sm;                                                     // n_towers padded towers
-    float* gbase = sW + (size_t)S.n_towers * S.s_tower_size + (size_t)grp * (2 * passes * S.act_size + kNcfThreads + 8);
+    float* gbase = sW + (size_t)Q.sw_floats + (size_t)grp * (2 * passes * S.act_size + kNcfThreads + 8);
     float* sAct = gbase;
     float* sDel = sAct + passes * S.act_size;
     float* part = sDel + passes * S.act_size;
@@ -246,21 +253,34 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
         const int64_t cnt = (Q.n_used - off < Q.batch_size) ? (Q.n_used - off) : Q.batch_size;
         const int32_t stamp = Q.first_stamp + (int32_t)(s - Q.first_step);
         // ---- phase 1: this step's weights -> shared memory (padded rows), then the samples
-        for (int t = 0; t < S.n_towers; ++t)
-            for (int l = 0; l < S.n_layers; ++l) {
-                const int in = S.in_dim[l], out = S.out_dim[l];
-                const float* src = Q.dense + (size_t)t * S.tower_size;
-                float* dst = sW + (size_t)t * S.s_tower_size;
-                if (out <= kEpThreads && kEpThreads % out == 0) {          // no integer divisions in the loop
-                    const int j = tid_cta % out, kstep = kEpThreads / out;
-                    for (int k = tid_cta / out; k < in; k += kstep)
-                        dst[S.sw_off[l] + k * (out + 1) + j] = __ldcg(src + S.w_off[l] + k * out + j);
-                } else {
-                    for (int e = tid_cta; e < in * out; e += kEpThreads)
-                        dst[S.sw_off[l] + (e / out) * (out + 1) + (e % out)] = __ldcg(src + S.w_off[l] + e);
+        {   // straight float4 copy (the packed dense buffer is 16-byte aligned and sw_floats is a multiple of 4):
+            // every thread's loads are independent -> one L2 round trip
+            const int n4 = Q.sw_floats >> 2, total = S.tower_size * S.n_towers;
+            const float4* src4 = reinterpret_cast<const float4*>(Q.dense);
+            float4* dst4 = reinterpret_cast<float4*>(sW);
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = tid_cta + i * kEpThreads;
+                if (e < n4) {
+                    if (e * 4 + 3 < total) v[i] = __ldcg(src4 + e);
+                    else {      // the tail of a buffer whose length is not a multiple of 4
+                        float t4[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int c = 0; c < 4; ++c) if (e * 4 + c < total) t4[c] = __ldcg(Q.dense + e * 4 + c);
+                        v[i] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                    }
                 }
-                for (int e = tid_cta; e < out; e += kEpThreads) dst[S.sb_off[l] + e] = __ldcg(src + S.b_off[l] + e);
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = tid_cta + i * kEpThreads;
+                if (e < n4) dst4[e] = v[i];
+            }
+            for (int e = tid_cta + 8 * kEpThreads; e < n4; e += kEpThreads) {    // towers beyond 8192 floats
+                if (e * 4 + 3 < total) dst4[e] = __ldcg(src4 + e);
+                else for (int c = 0; c < 4; ++c) sW[e * 4 + c] = (e * 4 + c < total) ? __ldcg(Q.dense + e * 4 + c) : 0.0f;
+            }
+        }
         __syncthreads();
         float loss_acc = 0.0f;
         for (int64_t b = (int64_t)blockIdx.x * kGroups + grp; b < cnt; b += (int64_t)gridDim.x * kGroups) {
@@ -471,7 +491,8 @@ extern "C" int nrc_ncf_epoch_fused(const nrc_ncf_shape* shape, float* mf_user, f
     if (num_steps == 0) return NRC_OK;
     const NcfDev& S = Q.S;
     const int passes = pairwise ? 2 : 1;
-    const size_t smem_floats = (size_t)S.n_towers * S.s_tower_size + (size_t)kGroups * (2 * passes * S.act_size + kNcfThreads + 8);
+    Q.sw_floats = (S.n_towers * S.tower_size + 3) & ~3;
+    const size_t smem_floats = (size_t)Q.sw_floats + (size_t)kGroups * (2 * passes * S.act_size + kNcfThreads + 8);
     const size_t smem = (smem_floats + (kEpThreads / 64) * 16) * 4;
     Q.sred_off = (int32_t)smem_floats;
     Q.wblocked = 1; Q.wblocks = 0;
