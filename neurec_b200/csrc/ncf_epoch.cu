@@ -22,6 +22,8 @@
 //   grid barrier.
 // Arithmetic identical to nrc_ncf_train_epoch except for the summation order of dW (fixed slices
 // instead of atomics) -- tests compare both with oracle/tf_math.NCFTrainer.
+#include <stdlib.h>
+
 #include "epoch.cuh"
 #include "ncf.cuh"
 #include "optim.cuh"
@@ -51,6 +53,7 @@ struct NcfEpochParams {
     unsigned int* barrier;
     int64_t n_used, first_step, num_steps, steps_total;
     int32_t batch_size, pairwise, loss_kind, opt_kind, first_stamp, build, bar_mode;
+    int32_t dbg;                           // NRC_EPOCH_DBG bits (0 in normal use): 1 skip samples, 2 skip weight gradients, 4 skip tables, 8 skip weight staging
     int32_t sw_floats;                     // shared-memory floats of the weight copy (towers, rounded up to 4)
     int32_t wblocked, wblocks, sred_off;   // blocked weight-gradient path: 4 x 4 blocks per tower; smem offset (floats) of its reduction slots
     float reg_mf, reg_mlp, h0, h1, h2, h3;
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
         const int64_t cnt = (Q.n_used - off < Q.batch_size) ? (Q.n_used - off) : Q.batch_size;
         const int32_t stamp = Q.first_stamp + (int32_t)(s - Q.first_step);
         // ---- phase 1: this step's weights -> shared memory (padded rows), then the samples
-        {   // straight float4 copy (the packed dense buffer is 16-byte aligned and sw_floats is a multiple of 4):
+        if (!(Q.dbg & 8)) {   // straight float4 copy (the packed dense buffer is 16-byte aligned and sw_floats is a multiple of 4):
             // every thread's loads are independent -> one L2 round trip
             const int n4 = Q.sw_floats >> 2, total = S.tower_size * S.n_towers;
             const float4* src4 = reinterpret_cast<const float4*>(Q.dense);
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
         }
         __syncthreads();
         float loss_acc = 0.0f;
-        for (int64_t b = (int64_t)blockIdx.x * kGroups + grp; b < cnt; b += (int64_t)gridDim.x * kGroups) {
+        for (int64_t b = (int64_t)blockIdx.x * kGroups + grp; b < cnt && !(Q.dbg & 1); b += (int64_t)gridDim.x * kGroups) {
             float l = 0.0f;
             ncf_sample(Q, sW, sAct, sDel, part, red, tid, grp, b, cnt, __ldcg(Q.ws_u + off + b), __ldcg(Q.ws_i + off + b),
                        __ldcg(Q.ws_t + off + b), stamp, l);
@@ -303,7 +306,8 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
         // lane64 + 64, ... with ONE float4 of activations and ONE float4 of deltas per sample (all loads of a
         // thread are independent: one L2 round trip), 16 FMAs per sample; the 64 partial blocks are summed by
         // warp shuffles + one shared-memory hop in fixed order; 16 lanes apply the dense optimizer formula.
-        if (Q.wblocked) {
+        if (Q.dbg & 2) {
+        } else if (Q.wblocked) {
             const int grp64 = tid_cta >> 6, l64 = tid_cta & 63, wl = tid_cta & 31;
             float* sred = sm + Q.sred_off + grp64 * 16;
             for (int bi = blockIdx.x * (kEpThreads / 64) + grp64; bi < Q.wblocks * S.n_towers; bi += gridDim.x * (kEpThreads / 64)) {
@@ -405,26 +409,45 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
             }
         }
         }
-        // (b) embedding tables
+        // (b) embedding tables: two float4 groups per thread and iteration, all loads issued before the math
 #pragma unroll 1
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < 4 && !(Q.dbg & 4); ++t) {
             const NcfSeg& G = Q.seg[t];
             if (G.elems == 0) continue;
             if ((G.dim & 3) == 0) {
-                for (int64_t e = gtid * 4; e < G.elems; e += nthr * 4) {
+                for (int64_t e = gtid * 4; e < G.elems; e += nthr * 8) {
+                    const int64_t e2 = e + nthr * 4;
+                    const bool two = e2 < G.elems;
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     const float4 g = __ldcg(reinterpret_cast<const float4*>(G.grad + e));
                     float4 v = __ldcg(reinterpret_cast<const float4*>(G.var + e));
-                    float4 a = has0 ? __ldcg(reinterpret_cast<const float4*>(G.s0 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 c = has1 ? __ldcg(reinterpret_cast<const float4*>(G.s1 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const bool touched = (adam || Q.opt_kind == NRC_OPT_GD) ? true : (__ldcg(G.touched + e / G.dim) == stamp);
-                    opt_update(Q.opt_kind, 0, touched, h0, Q.h1, Q.h2, Q.h3, v.x, g.x, a.x, c.x);
-                    opt_update(Q.opt_kind, 0, touched, h0, Q.h1, Q.h2, Q.h3, v.y, g.y, a.y, c.y);
-                    opt_update(Q.opt_kind, 0, touched, h0, Q.h1, Q.h2, Q.h3, v.z, g.z, a.z, c.z);
-                    opt_update(Q.opt_kind, 0, touched, h0, Q.h1, Q.h2, Q.h3, v.w, g.w, a.w, c.w);
+                    float4 a = has0 ? __ldcg(reinterpret_cast<const float4*>(G.s0 + e)) : z4;
+                    float4 c = has1 ? __ldcg(reinterpret_cast<const float4*>(G.s1 + e)) : z4;
+                    const float4 g2 = two ? __ldcg(reinterpret_cast<const float4*>(G.grad + e2)) : z4;
+                    float4 v2 = two ? __ldcg(reinterpret_cast<const float4*>(G.var + e2)) : z4;
+                    float4 a2 = (two && has0) ? __ldcg(reinterpret_cast<const float4*>(G.s0 + e2)) : z4;
+                    float4 c2 = (two && has1) ? __ldcg(reinterpret_cast<const float4*>(G.s1 + e2)) : z4;
+                    const bool stamped = !(adam || Q.opt_kind == NRC_OPT_GD);
+                    const bool t1 = stamped ? (__ldcg(G.touched + e / G.dim) == stamp) : true;
+                    const bool t2 = (stamped && two) ? (__ldcg(G.touched + e2 / G.dim) == stamp) : true;
+                    opt_update(Q.opt_kind, 0, t1, h0, Q.h1, Q.h2, Q.h3, v.x, g.x, a.x, c.x);
+                    opt_update(Q.opt_kind, 0, t1, h0, Q.h1, Q.h2, Q.h3, v.y, g.y, a.y, c.y);
+                    opt_update(Q.opt_kind, 0, t1, h0, Q.h1, Q.h2, Q.h3, v.z, g.z, a.z, c.z);
+                    opt_update(Q.opt_kind, 0, t1, h0, Q.h1, Q.h2, Q.h3, v.w, g.w, a.w, c.w);
                     *reinterpret_cast<float4*>(G.var + e) = v;
                     if (has0) *reinterpret_cast<float4*>(G.s0 + e) = a;
                     if (has1) *reinterpret_cast<float4*>(G.s1 + e) = c;
-                    *reinterpret_cast<float4*>(G.grad + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(G.grad + e) = z4;
+                    if (two) {
+                        opt_update(Q.opt_kind, 0, t2, h0, Q.h1, Q.h2, Q.h3, v2.x, g2.x, a2.x, c2.x);
+                        opt_update(Q.opt_kind, 0, t2, h0, Q.h1, Q.h2, Q.h3, v2.y, g2.y, a2.y, c2.y);
+                        opt_update(Q.opt_kind, 0, t2, h0, Q.h1, Q.h2, Q.h3, v2.z, g2.z, a2.z, c2.z);
+                        opt_update(Q.opt_kind, 0, t2, h0, Q.h1, Q.h2, Q.h3, v2.w, g2.w, a2.w, c2.w);
+                        *reinterpret_cast<float4*>(G.var + e2) = v2;
+                        if (has0) *reinterpret_cast<float4*>(G.s0 + e2) = a2;
+                        if (has1) *reinterpret_cast<float4*>(G.s1 + e2) = c2;
+                        *reinterpret_cast<float4*>(G.grad + e2) = z4;
+                    }
                 }
             } else {
                 for (int64_t e = gtid; e < G.elems; e += nthr) {
@@ -526,6 +549,11 @@ extern "C" int nrc_ncf_epoch_fused(const nrc_ncf_shape* shape, float* mf_user, f
     Q.first_step = first_step; Q.num_steps = num_steps;
     Q.batch_size = batch_size; Q.pairwise = pairwise ? 1 : 0; Q.loss_kind = loss_kind; Q.opt_kind = opt_kind;
     Q.first_stamp = first_stamp; Q.build = first_step == 0 ? 1 : 0; Q.bar_mode = epoch_bar_mode();
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("NRC_EPOCH_DBG"); dbg = e ? atoi(e) : 0; }
+        Q.dbg = dbg;
+    }
     Q.reg_mf = reg_mf; Q.reg_mlp = reg_mlp;
     Q.h0 = hyper_host ? hyper_host[0] : 0.0f; Q.h1 = hyper_host ? hyper_host[1] : 0.0f;
     Q.h2 = hyper_host ? hyper_host[2] : 0.0f; Q.h3 = hyper_host ? hyper_host[3] : 0.0f;

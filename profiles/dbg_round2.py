@@ -20,8 +20,31 @@ def ev(fn, reps):
 
 w = bench.NeumfMl100k(0); w.setup()
 ms = ev(lambda: w.run_steps(w.spe), 5)
-print("NeuMF ml-100k persistent epoch: %.3f ms / %d steps = %.2f us/step, %.1f M samples/s" %
-      (ms, w.spe, 1e3 * ms / w.spe, w.spe * w.batch / ms / 1e3), flush=True)
+print("NeuMF ml-100k persistent epoch%s: %.3f ms / %d steps = %.2f us/step, %.1f M samples/s" %
+      (" [NRC_EPOCH_DBG=%s]" % os.environ["NRC_EPOCH_DBG"] if os.environ.get("NRC_EPOCH_DBG") else "", ms, w.spe,
+       1e3 * ms / w.spe, w.spe * w.batch / ms / 1e3), flush=True)
+if os.environ.get("NRC_NCF_ONLY"):
+    sys.exit(0)
+import subprocess
+for bits, what in ((15, "barriers only"), (14, "samples + barriers"), (13, "weight gradients + barriers"), (11, "tables + barriers"),
+                   (7, "weight staging + barriers")):
+    e = dict(os.environ, NRC_EPOCH_DBG=str(bits), NRC_NCF_ONLY="1")
+    out = subprocess.run([sys.executable, __file__], env=e, capture_output=True, text=True).stdout.strip().splitlines()
+    print("   %-32s %s" % (what, out[0] if out else "?"), flush=True)
+# NeuMF evaluation (predict over all items + mask + top-K + metrics): the fast scoring kernel vs the generic one
+import time
+users = torch.arange(w.d["num_users"], dtype=torch.int32, device="cuda")
+tp, ti, sp, si = (bench.dev(w.d[k]) for k in ("train_indptr", "train_indices", "test_indptr", "test_indices"))
+
+
+def neumf_eval():
+    sc = ops.ncf_scores(w.shape, w.P, users)
+    ops.mask_rows(sc, users, tp, ti)
+    return ops.eval_score_matrix(sc, sp, si, bench.METRICS, 20)
+
+
+ms = ev(neumf_eval, 5)
+print("NeuMF ml-100k evaluation (943 users x 1682 items): %.3f ms = %.2f M users/s" % (ms, 943 / ms / 1e3), flush=True)
 del w
 g = bench.LightgcnGowalla(0); g.setup()
 fn, nbytes = g.spmm_kernel()
