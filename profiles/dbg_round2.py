@@ -27,8 +27,10 @@ if os.environ.get("NRC_NCF_ONLY"):
     sys.exit(0)
 import subprocess
 for bits, what in ((15, "barriers only"), (14, "samples + barriers"), (13, "weight gradients + barriers"), (11, "tables + barriers"),
-                   (7, "weight staging + barriers")):
-    e = dict(os.environ, NRC_EPOCH_DBG=str(bits), NRC_NCF_ONLY="1")
+                   (7, "weight staging + barriers"), (-1, "128-thread group per sample (old)")):
+    e = dict(os.environ, NRC_EPOCH_DBG=str(max(bits, 0)), NRC_NCF_ONLY="1")
+    if bits < 0:
+        e["NRC_NCF_GROUP"] = "1"
     out = subprocess.run([sys.executable, __file__], env=e, capture_output=True, text=True).stdout.strip().splitlines()
     print("   %-32s %s" % (what, out[0] if out else "?"), flush=True)
 # NeuMF evaluation (predict over all items + mask + top-K + metrics): the fast scoring kernel vs the generic one
@@ -45,6 +47,17 @@ def neumf_eval():
 
 ms = ev(neumf_eval, 5)
 print("NeuMF ml-100k evaluation (943 users x 1682 items): %.3f ms = %.2f M users/s" % (ms, 943 / ms / 1e3), flush=True)
+sc = ops.ncf_scores(w.shape, w.P, users)
+for name, fn in (("ncf_scores", lambda: ops.ncf_scores(w.shape, w.P, users)), ("mask_rows", lambda: ops.mask_rows(sc, users, tp, ti)),
+                 ("eval_score_matrix", lambda: ops.eval_score_matrix(sc, sp, si, bench.METRICS, 20))):
+    print("   %-20s %.1f us (stream time incl. host launch gaps)" % (name, 1e3 * ev(fn, 20)), flush=True)
+try:
+    g_ = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_):
+        neumf_eval()
+    print("   whole evaluation as a CUDA graph: %.1f us" % (1e3 * ev(g_.replay, 20)), flush=True)
+except Exception as ex:          # measurement aid only
+    print("   graph capture of the evaluation failed: %r" % (ex,), flush=True)
 del w
 g = bench.LightgcnGowalla(0); g.setup()
 fn, nbytes = g.spmm_kernel()

@@ -41,7 +41,7 @@ def main():
     lp, li = sharded.ItemShard.restrict_csr(tp, ti, lo, hi)
     shard = sharded.ItemShard(d(V[lo:hi]), lo, d(lp), d(li))
     dsp, dsi = d(sp), d(si)
-    ok, ties_total = True, 0
+    ok, ties_total, diff_rows = True, 0, 0
     full = None
     if True:                                             # reference result: the unsharded evaluator
         full = ops.eval_mf(d(U), d(V), d(np.arange(nu, dtype=np.int32)), d(tp), d(ti), dsp, dsi, metric, K, return_ranks=True)
@@ -51,16 +51,33 @@ def main():
         a, b = sharded.local_slice(B, rank, ws)          # the rows of the batch this rank owns
         mine = d(U[user_lo + a:user_lo + b])
         res, ranks, ties = sharded.evaluate_item_sharded(mine, shard, dsp, dsi, user_lo, B, metric, K, return_ranks=True)
-        ok &= bool(torch.equal(ranks, full[1][user_lo:user_lo + B])) and bool(torch.equal(res, full[0][user_lo:user_lo + B]))
-        ties_total += int(ties.item())
+        # Rows with an exact fp32 score tie inside the global top K+1 are counted by the merge and ranked
+        # score-descending / id-ascending; the unsharded evaluator's order among EQUAL scores is an artefact of
+        # the reference's heap (evaluate.h:23-50), so such a row may legitimately differ -- but only by a
+        # permutation / swap of items whose scores are equal.  Every other row must be bit-identical.
+        want_r, want_m = full[1][user_lo:user_lo + B], full[0][user_lo:user_lo + B]
+        bad = ((ranks != want_r).any(dim=1) | (res != want_m).any(dim=1)).nonzero().flatten()
+        n_ties = int(ties.item())
+        ties_total += n_ties
+        diff_rows += int(bad.numel())
+        if bad.numel() > n_ties:
+            ok = False
+        for b in bad.tolist():
+            urow = torch.from_numpy(U[user_lo + b]).cuda().double()
+            sa = (torch.from_numpy(V[ranks[b].cpu().numpy()]).cuda().double() @ urow)
+            sb = (torch.from_numpy(V[want_r[b].cpu().numpy()]).cuda().double() @ urow)
+            if float((sa - sb).abs().max()) > 1e-6:        # the two rankings carry the same score sequence
+                ok = False
     torch.cuda.synchronize(); dist.barrier()
     dt = time.perf_counter() - t0
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("item-sharded evaluator, world %d: %d users x %d items (d=%d) in batches of %d: rows %s the unsharded "
-              "evaluator's on every rank, %d tie rows, %.0f users/s (incl. per-batch checks)" % (
-                  ws, nu, ni, dim, B, "bit-identical to" if int(flag) else "DIFFER from", ties_total, nu / dt), flush=True)
+        print("item-sharded evaluator, world %d: %d users x %d items (d=%d) in batches of %d: %s, %d tie rows "
+              "(flagged by the merge), %d rows differ from the unsharded evaluator's (all of them equal-score "
+              "permutations: %s), %.0f users/s (incl. per-batch checks)" % (
+                  ws, nu, ni, dim, B, "OK" if int(flag) else "FAILED", ties_total, diff_rows, bool(int(flag)), nu / dt),
+              flush=True)
     assert int(flag) == 1
     dist.barrier()
     dist.destroy_process_group()
