@@ -730,12 +730,14 @@ class ShardedCfg:
     users_per_gpu, items_per_gpu, dim, batch, lr = 6_250_000, 12_500_000, 128, 1 << 20, 0.05
     max_pos = 7                 # positives per user: 1..7 (a <= 64-item positive list)
     zipf_a = 1.05
+    n_hot = 16384               # replicated head of the item table: ~2/3 of all positives at Zipf(1.05) (NRC_BENCH_N_HOT)
 
 
 def synth_shard_csr(cfg, rank, world, device="cuda"):
     """This rank's train CSR: its own users (local ids), 1..max_pos positives each, items
-    Zipf(1.05) over the GLOBAL catalogue (hot ranks scattered by a multiplicative hash), rows sorted
-    and duplicate-free.  Built on the device (setup, untimed)."""
+    Zipf(1.05) over the GLOBAL catalogue with item id = popularity rank (what the loader's
+    relabel_by_degree produces: ids in descending train degree), rows sorted and duplicate-free.
+    Built on the device (setup, untimed)."""
     import torch
     g = torch.Generator(device=device).manual_seed(3 + rank)
     nu, ni = cfg.users_per_gpu, cfg.items_per_gpu * world
@@ -743,8 +745,8 @@ def synth_shard_csr(cfg, rank, world, device="cuda"):
     x = torch.rand((nu, cfg.max_pos), device=device, generator=g, dtype=torch.float64)
     a = cfg.zipf_a                         # inverse CDF of the continuous Zipf(a) truncated to [1, ni]
     r = (((ni ** (1 - a) - 1) * x + 1) ** (1 / (1 - a))).clamp(1, ni).long() - 1
-    items = (r * 2654435761) % ni
-    del x, r
+    items = r
+    del x
     big = torch.iinfo(torch.int64).max
     items[torch.arange(cfg.max_pos, device=device)[None, :] >= deg[:, None]] = big
     items = items.sort(1).values
@@ -761,14 +763,20 @@ def synth_shard_csr(cfg, rank, world, device="cuda"):
     return indptr.cpu().numpy(), indices.cpu().numpy(), users.cpu().numpy()
 
 
+def n_hot_of(cfg):
+    return int(os.environ.get("NRC_BENCH_N_HOT", cfg.n_hot))
+
+
 def sharded_describe(cfg, world):
     return ("BPRMF, learner=gd, tables row-sharded over %d GPU(s): %d users x %d items x d=%d per GPU (%.1f GB per GPU; "
             "%d x %d rows in total), 2^20 triplets per GPU and step sampled INSIDE the step kernel from the rank's train "
-            "CSR (1..%d positives per user, items Zipf(%.2f) over the global catalogue, uniform negatives rejected against "
-            "the user's row, keyed-bijection shuffle) -- BASELINE configs[4], weak scaling" % (
+            "CSR (1..%d positives per user, items Zipf(%.2f) over the global catalogue with ids in descending popularity "
+            "(the loader's relabelling), uniform negatives rejected against the user's row, keyed-bijection shuffle); the "
+            "%d most popular item rows are replicated on every GPU, their deltas summed by one all-reduce per step "
+            "-- BASELINE configs[4], weak scaling" % (
                 world, cfg.users_per_gpu, cfg.items_per_gpu, cfg.dim,
                 (cfg.users_per_gpu + cfg.items_per_gpu) * cfg.dim * 4 / 1e9, cfg.users_per_gpu * world,
-                cfg.items_per_gpu * world, cfg.max_pos, cfg.zipf_a))
+                cfg.items_per_gpu * world, cfg.max_pos, cfg.zipf_a, n_hot_of(cfg)))
 
 
 def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
@@ -791,15 +799,19 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
         US_local = torch.empty((cfg.users_per_gpu, dim), dtype=torch.float32, device="cuda")
     US_local.normal_(0, 0.01, generator=g)
     VS.local.normal_(0, 0.01, generator=g)
+    VS.enable_hot(n_hot_of(cfg))
     spe = T.n_pos // bs                        # whole batches only (drop_last), so every step is 2^20 triplets
     loss = torch.zeros(1, device="cuda")
     loss_pin = torch.zeros(K + W + 8).pin_memory()
     state = {"g": 0}
 
-    def step(e2e_slot=None):
+    def step(e2e_slot=None, after_kernel=None):
         e, s = divmod(state["g"], spe)
         ops.mf_bpr_sgd_epoch(US_local, VS, T.ptr, T.idx, T.users, T.idx, ni, True, SEED + rank, e, s * bs, bs, cfg.lr, 0.0, loss)
         state["g"] += 1
+        if after_kernel is not None:
+            after_kernel.record()
+        VS.sync_hot()                          # the replicated head: one all-reduce of n_hot x d floats + apply
         if e2e_slot is not None:               # every step's loss goes back to the host
             loss_pin[e2e_slot:e2e_slot + 1].copy_(loss, non_blocking=True)
 
@@ -808,14 +820,16 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
     barrier(world)
     # per-launch durations (CUDA events on the launching stream) inside the timed region
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    kevs = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
 
     def run():
         evs[0].record()
         for s in range(K):
-            step()
+            step(after_kernel=kevs[s])
             evs[s + 1].record()
     ms, _ = timed(run, world, windows)
-    launch_ms = [evs[s].elapsed_time(evs[s + 1]) for s in range(K)]
+    launch_ms = [evs[s].elapsed_time(kevs[s]) for s in range(K)]          # the step kernel alone
+    sync_ms = [kevs[s].elapsed_time(evs[s + 1]) for s in range(K)]        # all-reduce + apply of the replicated head
     # e2e: the train interactions come from pinned host memory inside the timed region
     for s in range(W):
         step(s)
@@ -830,6 +844,7 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
     barrier(world)
     finite = bool(np.isfinite(loss_pin[:K].numpy()).all())
     remote = (world - 1) / world if world > 1 else 0.0
+    cold_pos = float((T.idx >= n_hot_of(cfg)).float().mean().item()) if n_hot_of(cfg) else 1.0
     lazy = None
     if world == 1:          # the explicitly-named lazy-Adam run SURVEY 8(d) asks for (single GPU: rows of var, m, v)
         z = torch.zeros_like
@@ -853,10 +868,15 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
         return None
     kt = float(np.mean(launch_ms)) * 1e-3
     nbytes = bs * (24 * dim + 12)
-    nv_bytes = bs * 2 * remote * dim * 4       # per direction and GPU: remote item rows read (in) / RED-updated (out)
-    extra = {"launch_us_min": float(np.min(launch_ms)) * 1e3, "launch_us_max": float(np.max(launch_ms)) * 1e3}
+    # per direction and GPU: remote item rows read (in) / reduce-added (out).  Negatives are uniform (all outside the
+    # replicated head, to first order), positives only when their id is outside it
+    nv_bytes = bs * (1.0 + cold_pos) * remote * dim * 4
+    extra = {"launch_us_min": float(np.min(launch_ms)) * 1e3, "launch_us_max": float(np.max(launch_ms)) * 1e3,
+             "replicated_head": {"rows": n_hot_of(cfg), "sync_us_mean": float(np.mean(sync_ms)) * 1e3,
+                                 "what": "per step after the kernel: all-reduce (NCCL, N > 1) of the head's deltas + apply"}}
     if world > 1:
-        extra["nvlink"] = {"remote_item_row_fraction": remote, "GBps_per_gpu_per_direction": 2 * nv_bytes / kt / 1e9,
+        extra["nvlink"] = {"remote_item_row_fraction": remote, "positives_outside_the_replicated_head": cold_pos,
+                           "GBps_per_gpu_per_direction": 2 * nv_bytes / kt / 1e9,
                            "of_measured_peer_copy_770_GBps": 2 * nv_bytes / kt / 1e9 / 770.0,
                            "note": "per direction: the rows this GPU reads from peers + the RED payloads peers send to it "
                                    "(and the mirror image outbound); the limiting resource at N > 1"}
@@ -865,9 +885,10 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
            "vs_baseline": None, "dtype": "f32", "data": "synthetic, seeds 3+rank / 30+rank",
            "config": {"workload": sharded_describe(cfg, world), "train_positives_per_gpu": T.n_pos,
                       "global_batch": bs * world, "steps_per_epoch": spe,
-                      "exchange": ("remote item rows are gathered and RED-updated through peer mappings over NVLink inside "
-                                   "the one fused kernel; no NCCL collective in the data path; ranks are not synchronised "
-                                   "between steps") if world > 1 else "single GPU: no exchange",
+                      "exchange": ("remote item rows are bulk-copied in and reduce-added back through peer mappings over "
+                                   "NVLink inside the one fused kernel; the replicated head's deltas (%d rows) take one NCCL "
+                                   "all-reduce per step, which also keeps the ranks in step" % n_hot_of(cfg)) if world > 1
+                                  else "single GPU: no exchange",
                       "loss_finite": finite,
                       "l2": "tables (9.6 GB per GPU) and the train CSR (%.2f GB) are far larger than L2; every step draws "
                             "fresh positions of the shuffled epoch" % (T.nbytes / 1e9)},
@@ -875,8 +896,8 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / K,
                    "how": "the rank's train CSR + flattened positives (%.0f MB) are copied from pinned host memory inside "
                           "the timed region, then K steps, each copying its loss back to pinned memory" % (T.nbytes / 1e6)},
-           "gpu_launches": K,
-           "roofline": hbm_roofline("mf_bpr_sgd_stream_kernel", nbytes, kt,
+           "gpu_launches": K * (2 if n_hot_of(cfg) else 1),
+           "roofline": hbm_roofline("mf_bpr_sgd_pipe_kernel" if os.environ.get("NRC_SGD_PIPE", "1") != "0" else "mf_bpr_sgd_stream_kernel", nbytes, kt,
                                     "SURVEY 8(d): (24*d + 12) B per triplet x 2^20 triplets (the fused sampler's CSR reads "
                                     "are not counted: 'fused: 0 extra')",
                                     "CUDA events on the launching stream around each of the K timed launches; mean", extra)}

@@ -389,6 +389,31 @@ int nrc_mf_bpr_sgd_epoch(float* user_table, float* const* item_shards, int32_t w
                          int64_t first, int64_t count, float lr, float reg, float* loss,
                          void* stream);
 
+/* nrc_mf_bpr_sgd_epoch with a REPLICATED HEAD of the item table (n_hot = 0: identical to it).  Item ids
+ * [0, n_hot) -- the loader relabels items by descending train degree (neurec_b200.util.peer.relabel_by_degree),
+ * so these are the most popular ones, the rows thousands of triplets of every step land on -- are read from this
+ * rank's replica `hot` [n_hot, dim] and their deltas accumulate in this rank's `hot_delta` [n_hot, dim] instead of
+ * crossing NVLink as same-address atomics on the owner.  Between steps the caller sums hot_delta over the ranks
+ * (one all-reduce of n_hot * dim floats) and calls nrc_mf_hot_apply.  Within a step the replicated rows keep their
+ * pre-step values, which is what TF computes for every row (MF.py:54-76: all gradients of a batch are taken at the
+ * pre-step variables); the other rows are updated in place. */
+int nrc_mf_bpr_sgd_epoch_hot(float* user_table, float* const* item_shards, int32_t world,
+                             int32_t self_rank, int64_t items_per_shard, int32_t dim,
+                             const int64_t* train_indptr, const int32_t* train_indices,
+                             const int32_t* pos_users, const int32_t* pos_items, int64_t n_pos,
+                             int32_t num_items, int32_t shuffle, uint64_t seed, uint64_t epoch,
+                             int64_t first, int64_t count, float lr, float reg, float* loss,
+                             float* hot, float* hot_delta, int32_t n_hot, void* stream);
+/* hot[e] += hot_delta[e]; hot_delta[e] = 0 for e < n_floats (a multiple of 4; both 16-byte aligned). */
+int nrc_mf_hot_apply(float* hot, float* hot_delta, int64_t n_floats, void* stream);
+/* Which kernel nrc_mf_bpr_sgd_epoch launches for dim 64 / 128.  1 (default): the pipelined form -- producer
+ * threads sample and issue bulk copies (cp.async.bulk) of the three rows into a 128-slot shared-memory ring,
+ * consumer warps compute and return the deltas as bulk reduce-adds (cp.reduce.async.bulk .add.f32), local and
+ * peer rows alike.  0: the register form (two triplets per warp, LDG + RED).  Same arithmetic per triplet.
+ * Returns the previous setting.  (NRC_SGD_PIPE=0/1 sets the initial value.) */
+int nrc_mf_sgd_set_pipelined(int32_t on);
+
+
 /* The explicitly-named LAZY-Adam variant of nrc_mf_bpr_sgd_epoch (BASELINE configs[4]:
  * "learner=gd for the roofline run plus an explicitly-named lazy-Adam run"; the reference's own
  * learner=adam, util/learner.py:6, is TF's DENSE Adam and is what nrc_opt_apply_* implement).

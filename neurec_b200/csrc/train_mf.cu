@@ -168,9 +168,29 @@ struct RowShards {
     int32_t vec_remote;       // how rows of OTHER ranks are updated: 0 scalar REDs (default), 1 vector REDs,
                               // 2 one bulk reduce-add of the whole row (cp.reduce.async.bulk from shared memory) -- NRC_PEER_VEC_RED
     int32_t force_remote;     // debug (NRC_FORCE_REMOTE_PATH=1): take the remote update path for local item rows too
+    // Replicated head (n_hot > 0): rows [0, n_hot) -- the loader relabels items by descending train degree, so these
+    // are the most popular ones -- are READ from this rank's replica `hot` (L2-resident) and their deltas are
+    // accumulated into this rank's `hot_delta`; the caller all-reduces hot_delta between steps and applies it
+    // (nrc_mf_hot_apply).  Thousands of triplets per step hit the same few rows: without the replica every one of
+    // them is a same-address atomic that crosses NVLink to the owner.
+    float* hot;
+    float* hot_delta;
+    int32_t n_hot;
     // SHARDED is a compile-time switch and the shard base is picked with constant indices only, so
     // the struct stays in the kernel-parameter constant bank (a dynamic index would spill it to
     // local memory and cost the single-GPU kernel ~15 % of its bandwidth).
+    // row to READ; `upd` receives the address the row's delta is added to (the same row unless it is replicated)
+    template <bool SHARDED>
+    __device__ __forceinline__ float* row(int32_t id, int D, bool& remote, float*& upd) const {
+        if (id < n_hot) {
+            remote = false;
+            upd = hot_delta + (size_t)id * D;
+            return hot + (size_t)id * D;
+        }
+        float* p = row<SHARDED>(id, D, remote);
+        upd = p;
+        return p;
+    }
     template <bool SHARDED>
     __device__ __forceinline__ float* row(int32_t id, int D, bool& remote) const {
         if constexpr (!SHARDED) {
@@ -299,6 +319,13 @@ __device__ __forceinline__ void ld_vec(const float* p, float (&v)[VEC]) {
     }
 }
 
+template <int VEC>
+__device__ __forceinline__ void st_vec(float* p, const float (&v)[VEC]) {
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else if constexpr (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    else *p = v[0];
+}
+
 // Update of a row that lives on another rank, by mode (RowShards::vec_remote).  Mode 2 stages the warp's
 // delta row in shared memory and issues ONE bulk reduce-add of the whole row through the copy engine
 // (cp.reduce.async.bulk ... .add.f32): a single transaction per row over NVLink instead of 32 x VEC REDs.
@@ -350,10 +377,12 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
             bool ri0, rj0, ri1, rj1;
             float* pu0 = U_local + (size_t)s_u[t0] * D + lane * VEC;
             float* pu1 = U_local + (size_t)s_u[t1] * D + lane * VEC;
-            float* qi0 = V.row<SHARDED>(s_i[t0], D, ri0) + lane * VEC;
-            float* qj0 = V.row<SHARDED>(s_j[t0], D, rj0) + lane * VEC;
-            float* qi1 = V.row<SHARDED>(s_i[t1], D, ri1) + lane * VEC;
-            float* qj1 = V.row<SHARDED>(s_j[t1], D, rj1) + lane * VEC;
+            float *wi0, *wj0, *wi1, *wj1;      // where the deltas go (the row itself unless it is replicated)
+            float* qi0 = V.row<SHARDED>(s_i[t0], D, ri0, wi0) + lane * VEC;
+            float* qj0 = V.row<SHARDED>(s_j[t0], D, rj0, wj0) + lane * VEC;
+            float* qi1 = V.row<SHARDED>(s_i[t1], D, ri1, wi1) + lane * VEC;
+            float* qj1 = V.row<SHARDED>(s_j[t1], D, rj1, wj1) + lane * VEC;
+            wi0 += lane * VEC; wj0 += lane * VEC; wi1 += lane * VEC; wj1 += lane * VEC;
             float a0[VEC], b0[VEC], c0v[VEC], a1[VEC], b1[VEC], c1v[VEC];
             ld_vec<VEC>(pu0, a0); ld_vec<VEC>(qi0, b0); ld_vec<VEC>(qj0, c0v);
             ld_vec<VEC>(pu1, a1); ld_vec<VEC>(qi1, b1); ld_vec<VEC>(qj1, c1v);
@@ -379,8 +408,8 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
                 dvj[t] = -lr * (-g0 * a0[t] + reg * c0v[t]);
             }
             red_row<VEC>(pu0, du, false);
-            if (ri0) remote_row_update<VEC>(qi0, dvi, rmode, s_stage[warp][0], lane); else red_row<VEC>(qi0, dvi, false);
-            if (rj0) remote_row_update<VEC>(qj0, dvj, rmode, s_stage[warp][1], lane); else red_row<VEC>(qj0, dvj, false);
+            if (ri0) remote_row_update<VEC>(wi0, dvi, rmode, s_stage[warp][0], lane); else red_row<VEC>(wi0, dvi, false);
+            if (rj0) remote_row_update<VEC>(wj0, dvj, rmode, s_stage[warp][1], lane); else red_row<VEC>(wj0, dvj, false);
             loss_acc += l0;
             if (two) {
 #pragma unroll
@@ -390,8 +419,8 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
                     dvj[t] = -lr * (-g1 * a1[t] + reg * c1v[t]);
                 }
                 red_row<VEC>(pu1, du, false);
-                if (ri1) remote_row_update<VEC>(qi1, dvi, rmode, s_stage[warp][2], lane); else red_row<VEC>(qi1, dvi, false);
-                if (rj1) remote_row_update<VEC>(qj1, dvj, rmode, s_stage[warp][3], lane); else red_row<VEC>(qj1, dvj, false);
+                if (ri1) remote_row_update<VEC>(wi1, dvi, rmode, s_stage[warp][2], lane); else red_row<VEC>(wi1, dvi, false);
+                if (rj1) remote_row_update<VEC>(wj1, dvj, rmode, s_stage[warp][3], lane); else red_row<VEC>(wj1, dvj, false);
                 loss_acc += l1;
             }
         }
@@ -399,6 +428,165 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
     }
     if (rmode == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk reduces performed
     if (lane == 0 && loss) atomicAdd(loss, loss_acc);
+}
+
+// ----------------------------------------------------------------------------------------
+// Pipelined form of the CSR-fed step (default for dim >= 64; NRC_SGD_PIPE=0 selects the register form above).
+// The register form keeps 2 triplets per warp in flight and alternates a sampling phase with an update phase;
+// ncu shows it latency-bound (long-scoreboard stalls, DRAM at ~3/4 of the copy peak).  Here the rows never
+// pass through registers on their way in or out:
+//   producers (4 warps, one THREAD per ring slot): bijection -> (user, positive) -> rejection draw, then three
+//       bulk copies (cp.async.bulk, row bytes each) of the triplet's rows into the slot, completion counted on
+//       the slot's `full` mbarrier.  The next triplet is sampled while the slot is still in use.
+//   consumers (8 warps, 16 slots each): wait `full`, read the three rows from shared memory, the same arithmetic
+//       as above, write the three delta rows IN PLACE, and hand them to the copy engine as three bulk
+//       reduce-adds (cp.reduce.async.bulk .add.f32 -- the update of a local or a peer row alike); the slot's
+//       `empty` mbarrier is released once the engine has read the deltas (wait_group.read).
+// 128 slots x 3 rows in flight per SM (192 KB at d = 128) independent of register pressure, sampling chains,
+// row gathers and updates all overlapped.  One CTA per SM.
+// ----------------------------------------------------------------------------------------
+constexpr int kPipeSlots = 128, kPipeProdWarps = 4, kPipeConsWarps = 8;
+constexpr int kPipeThreads = (kPipeProdWarps + kPipeConsWarps) * 32;
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+template <int VEC, bool SHARDED>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+mf_bpr_sgd_pipe_kernel(float* __restrict__ U_local, const RowShards V, const EpochSpec E, int64_t first,
+                       int64_t count, float lr, float reg, float* __restrict__ loss) {
+    constexpr int D = 32 * VEC;
+    constexpr uint32_t kRowBytes = D * 4;
+    extern __shared__ __align__(128) unsigned char pipe_smem[];
+    float* ring = reinterpret_cast<float*>(pipe_smem);                              // [slots][3][D]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pipe_smem + (size_t)kPipeSlots * 3 * kRowBytes);   // full[], empty[]
+    float** dsts = reinterpret_cast<float**>(bars + 2 * kPipeSlots);                // [slots][3] global row addresses
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < kPipeSlots) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bars + tid)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bars + kPipeSlots + tid)));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * kPipeSlots;
+    if (warp < kPipeProdWarps) {
+        const int s = tid;
+        const uint32_t full = (uint32_t)__cvta_generic_to_shared(bars + s);
+        const uint32_t empty = (uint32_t)__cvta_generic_to_shared(bars + kPipeSlots + s);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (size_t)s * 3 * D);
+        uint32_t r = 0;
+        for (int64_t q = (int64_t)blockIdx.x * kPipeSlots + s; q < count; q += stride, ++r) {
+            int32_t u, i, j;
+            epoch_sample(E, first + q, 0, u, i, j);
+            bool ri, rj;
+            float* pu = U_local + (size_t)u * D;
+            float *wi, *wj;
+            float* qi = V.row<SHARDED>(i, D, ri, wi);
+            float* qj = V.row<SHARDED>(j, D, rj, wj);
+            if (r > 0) mbar_wait(empty, (r - 1) & 1);       // the slot's previous deltas have left shared memory
+            dsts[s * 3 + 0] = pu; dsts[s * 3 + 1] = wi; dsts[s * 3 + 2] = wj;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(3 * kRowBytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(pu), "r"(kRowBytes), "r"(full) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + kRowBytes), "l"(qi), "r"(kRowBytes), "r"(full) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + 2 * kRowBytes), "l"(qj), "r"(kRowBytes), "r"(full) : "memory");
+        }
+    } else {
+        const int cw = warp - kPipeProdWarps;
+        float loss_acc = 0.0f;
+        int prev = -1;
+        for (uint32_t r = 0;; ++r) {
+            bool any = false;
+            for (int s = cw; s < kPipeSlots; s += kPipeConsWarps) {
+                const int64_t q = (int64_t)blockIdx.x * kPipeSlots + s + (int64_t)r * stride;
+                if (q >= count) continue;
+                any = true;
+                mbar_wait((uint32_t)__cvta_generic_to_shared(bars + s), r & 1);
+                float* slot = ring + (size_t)s * 3 * D + lane * VEC;
+                float a[VEC], bi[VEC], bj[VEC];
+                ld_vec<VEC>(slot, a); ld_vec<VEC>(slot + D, bi); ld_vec<VEC>(slot + 2 * D, bj);
+                float di = 0.f, dj = 0.f, sq = 0.f;
+#pragma unroll
+                for (int t = 0; t < VEC; ++t) {
+                    di = fmaf(a[t], bi[t], di); dj = fmaf(a[t], bj[t], dj);
+                    sq += a[t] * a[t] + bi[t] * bi[t] + bj[t] * bj[t];
+                }
+                di = warp_sum(di); dj = warp_sum(dj);
+                const float x = di - dj;
+                float l = (x >= 0.f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
+                if (reg != 0.0f) l += reg * 0.5f * warp_sum(sq);
+                loss_acc += l;
+                const float g = -1.0f / (1.0f + expf(x));
+                float du[VEC], dvi[VEC], dvj[VEC];
+#pragma unroll
+                for (int t = 0; t < VEC; ++t) {
+                    du[t] = -lr * (g * (bi[t] - bj[t]) + reg * a[t]);
+                    dvi[t] = -lr * (g * a[t] + reg * bi[t]);
+                    dvj[t] = -lr * (-g * a[t] + reg * bj[t]);
+                }
+                st_vec<VEC>(slot, du); st_vec<VEC>(slot + D, dvi); st_vec<VEC>(slot + 2 * D, dvj);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(ring + (size_t)s * 3 * D);
+                    float* const p0 = dsts[s * 3 + 0];
+                    float* const p1 = dsts[s * 3 + 1];
+                    float* const p2 = dsts[s * 3 + 2];
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                 ::"l"(p0), "r"(src), "r"(kRowBytes) : "memory");
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                 ::"l"(p1), "r"(src + kRowBytes), "r"(kRowBytes) : "memory");
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                 ::"l"(p2), "r"(src + 2 * kRowBytes), "r"(kRowBytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if (prev >= 0) {        // the previous slot's deltas have been read by the engine: hand the slot back
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
+                                     ::"r"((uint32_t)__cvta_generic_to_shared(bars + kPipeSlots + prev)) : "memory");
+                    }
+                }
+                prev = s;
+                __syncwarp();
+            }
+            if (!any) break;
+        }
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (prev >= 0)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
+                             ::"r"((uint32_t)__cvta_generic_to_shared(bars + kPipeSlots + prev)) : "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every reduce-add performed before the kernel ends
+            if (loss) atomicAdd(loss, loss_acc);
+        }
+    }
+}
+
+template <int VEC, bool SH>
+static int launch_pipe(float* U_local, const RowShards& SV, const EpochSpec& E, int64_t first, int64_t count, float lr,
+                       float reg, float* loss, cudaStream_t st) {
+    constexpr size_t smem = (size_t)kPipeSlots * 3 * (32 * VEC * 4) + (size_t)kPipeSlots * 2 * 8 + (size_t)kPipeSlots * 3 * 8;
+    static bool attr = false;
+    if (!attr) {
+        NRC_CUDA_CHECK(cudaFuncSetAttribute(mf_bpr_sgd_pipe_kernel<VEC, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    int64_t blocks = (count + kPipeSlots - 1) / kPipeSlots;
+    if (blocks > sm_count()) blocks = sm_count();
+    mf_bpr_sgd_pipe_kernel<VEC, SH><<<(unsigned)blocks, kPipeThreads, smem, st>>>(U_local, SV, E, first, count, lr, reg, loss);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+static int g_sgd_pipe = -1;
+static int sgd_pipe_enabled() {
+    if (g_sgd_pipe < 0) { const char* e = getenv("NRC_SGD_PIPE"); g_sgd_pipe = e ? (atoi(e) != 0) : 1; }
+    return g_sgd_pipe;
 }
 
 static int launch_bpr_sgd_stream(float* U_local, const RowShards& SV, int dim, const EpochSpec& E, int64_t first,
@@ -410,6 +598,12 @@ static int launch_bpr_sgd_stream(float* U_local, const RowShards& SV, int dim, c
 #define NRC_LAUNCH_STREAM(VEC, SH) \
     mf_bpr_sgd_stream_kernel<VEC, SH><<<gb, 256, 0, st>>>(U_local, SV, E, first, count, lr, reg, loss)
     const bool sharded = SV.rows_per_shard != 0;
+    if (sgd_pipe_enabled() && !SV.force_remote && (dim == 128 || dim == 64)) {
+        if (dim == 128) return sharded ? launch_pipe<4, true>(U_local, SV, E, first, count, lr, reg, loss, st)
+                                       : launch_pipe<4, false>(U_local, SV, E, first, count, lr, reg, loss, st);
+        return sharded ? launch_pipe<2, true>(U_local, SV, E, first, count, lr, reg, loss, st)
+                       : launch_pipe<2, false>(U_local, SV, E, first, count, lr, reg, loss, st);
+    }
     if (dim == 128) { if (sharded) NRC_LAUNCH_STREAM(4, true); else NRC_LAUNCH_STREAM(4, false); }
     else if (dim == 64) { if (sharded) NRC_LAUNCH_STREAM(2, true); else NRC_LAUNCH_STREAM(2, false); }
     else { if (sharded) NRC_LAUNCH_STREAM(1, true); else NRC_LAUNCH_STREAM(1, false); }
@@ -428,13 +622,6 @@ static int launch_bpr_sgd_stream(float* U_local, const RowShards& SV, int dim, c
 // NOT what the reference's learner=adam does (that is dense, optim.cu); never used for parity claims.
 // Algorithmic traffic: rows of (var, m, v) read + written for 3 rows = 72*dim + 12 B per triplet.
 // ----------------------------------------------------------------------------------------
-template <int VEC>
-__device__ __forceinline__ void st_vec(float* p, const float (&v)[VEC]) {
-    if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    else if constexpr (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
-    else *p = v[0];
-}
-
 template <int VEC>
 __device__ __forceinline__ void lazy_adam_row(float* var, float* m, float* v, const float (&x)[VEC], const float (&g)[VEC],
                                               float lr_t, float b1, float b2, float eps) {
@@ -597,11 +784,12 @@ extern "C" int nrc_mf_bpr_sgd_sharded(float* const* user_shards, float* const* i
 // nrc_mf_bpr_sgd_fused / _sharded without the id arrays in between).  user_table is THIS rank's
 // row block (pos_users are local row ids: the train CSR is partitioned by user owner); items are
 // global ids, item_shards[r] the row block of rank r (world = 1: the whole table).
-extern "C" int nrc_mf_bpr_sgd_epoch(float* user_table, float* const* item_shards, int32_t world, int32_t self_rank,
+extern "C" int nrc_mf_bpr_sgd_epoch_hot(float* user_table, float* const* item_shards, int32_t world, int32_t self_rank,
                                     int64_t items_per_shard, int32_t dim, const int64_t* train_indptr,
                                     const int32_t* train_indices, const int32_t* pos_users, const int32_t* pos_items,
                                     int64_t n_pos, int32_t num_items, int32_t shuffle, uint64_t seed, uint64_t epoch,
-                                    int64_t first, int64_t count, float lr, float reg, float* loss, void* stream) {
+                                    int64_t first, int64_t count, float lr, float reg, float* loss, float* hot, float* hot_delta,
+                                    int32_t n_hot, void* stream) {
     NRC_REQUIRE(world >= 1 && world <= 8, NRC_E_LIMIT, "world %d outside [1, 8]", world);
     NRC_REQUIRE(self_rank >= 0 && self_rank < world, NRC_E_VALUE, "self_rank %d outside [0, %d)", self_rank, world);
     NRC_REQUIRE(user_table != nullptr && item_shards != nullptr, NRC_E_VALUE, "table pointers are NULL");
@@ -625,6 +813,9 @@ extern "C" int nrc_mf_bpr_sgd_epoch(float* user_table, float* const* item_shards
     }
     SV.rows_per_shard = world > 1 ? (int32_t)items_per_shard : 0;
     SV.self = self_rank;
+    NRC_REQUIRE(n_hot >= 0 && n_hot <= num_items && (n_hot == 0 || (hot != nullptr && hot_delta != nullptr)), NRC_E_VALUE,
+                "n_hot %d needs 0 <= n_hot <= num_items and the replica / delta buffers", n_hot);
+    SV.hot = hot; SV.hot_delta = hot_delta; SV.n_hot = n_hot;
     {
         static int vec = -1, force = -1;
         if (vec < 0) { const char* e = getenv("NRC_PEER_VEC_RED"); vec = e ? atoi(e) : 0; }
@@ -635,9 +826,50 @@ extern "C" int nrc_mf_bpr_sgd_epoch(float* user_table, float* const* item_shards
     return launch_bpr_sgd_stream(user_table, SV, dim, E, first, count, lr, reg, loss, as_stream(stream));
 }
 
+extern "C" int nrc_mf_bpr_sgd_epoch(float* user_table, float* const* item_shards, int32_t world, int32_t self_rank,
+                                    int64_t items_per_shard, int32_t dim, const int64_t* train_indptr,
+                                    const int32_t* train_indices, const int32_t* pos_users, const int32_t* pos_items,
+                                    int64_t n_pos, int32_t num_items, int32_t shuffle, uint64_t seed, uint64_t epoch,
+                                    int64_t first, int64_t count, float lr, float reg, float* loss, void* stream) {
+    return nrc_mf_bpr_sgd_epoch_hot(user_table, item_shards, world, self_rank, items_per_shard, dim, train_indptr,
+                                    train_indices, pos_users, pos_items, n_pos, num_items, shuffle, seed, epoch, first,
+                                    count, lr, reg, loss, nullptr, nullptr, 0, stream);
+}
+
+namespace nrc {
+__global__ void __launch_bounds__(256) hot_apply_kernel(float4* __restrict__ hot, float4* __restrict__ delta, int64_t n4) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
+        float4 h = hot[e];
+        const float4 d = delta[e];
+        h.x += d.x; h.y += d.y; h.z += d.z; h.w += d.w;
+        hot[e] = h;
+        delta[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+}  // namespace nrc
+
+extern "C" int nrc_mf_hot_apply(float* hot, float* hot_delta, int64_t n_floats, void* stream) {
+    NRC_REQUIRE(n_floats >= 0 && (n_floats & 3) == 0, NRC_E_VALUE, "n_floats %lld must be a multiple of 4", (long long)n_floats);
+    if (n_floats == 0) return NRC_OK;
+    NRC_REQUIRE(hot && hot_delta, NRC_E_VALUE, "replica / delta pointers are NULL");
+    int64_t blocks = (n_floats / 4 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    hot_apply_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(hot),
+                                                                      reinterpret_cast<float4*>(hot_delta), n_floats / 4);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
 // BPR with LAZY Adam straight from the train CSR (single GPU): the explicitly-named lazy variant of
 // nrc_mf_bpr_sgd_epoch for tables where TF's dense Adam pass is out of reach.  lr_t = Adam's
 // lr * sqrt(1 - b2^t) / (1 - b1^t) of this step (one value per call = per batch).
+extern "C" int nrc_mf_sgd_set_pipelined(int32_t on) {
+    const int before = sgd_pipe_enabled();
+    g_sgd_pipe = on ? 1 : 0;
+    return before;
+}
+
 extern "C" int nrc_mf_bpr_lazy_adam_epoch(float* user_table, float* user_m, float* user_v, float* item_table, float* item_m,
                                           float* item_v, int32_t dim, const int64_t* train_indptr,
                                           const int32_t* train_indices, const int32_t* pos_users, const int32_t* pos_items,

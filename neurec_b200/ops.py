@@ -368,16 +368,19 @@ def mf_bpr_sgd_epoch(user_table, item_shards, train_indptr, train_indices, pos_u
                      seed, epoch, first, count, lr, reg, loss_out):
     """Triplets [first, first + count) of a shuffled BPR + SGD epoch straight from the train CSR
     (nrc_mf_bpr_sgd_epoch): sampling, shuffling, scoring and the in-place update in ONE kernel.
-    `user_table` is this rank's row block (pos_users are local ids), `item_shards` a ShardSet."""
+    `user_table` is this rank's row block (pos_users are local ids), `item_shards` a ShardSet; with a
+    replicated head (ShardSet.enable_hot) call item_shards.sync_hot() after every step."""
     _req(user_table, torch.float32, "user_table")
     _req(train_indptr, torch.int64, "train_indptr"); _req(train_indices, torch.int32, "train_indices")
     _req(pos_users, torch.int32, "pos_users"); _req(pos_items, torch.int32, "pos_items")
-    check(_lib.load().nrc_mf_bpr_sgd_epoch(_p(user_table), item_shards.ptr_array(), item_shards.world,
-                                           item_shards.rank, item_shards.shape[0], user_table.shape[1],
-                                           _p(train_indptr), _p(train_indices), _p(pos_users), _p(pos_items),
-                                           pos_users.numel(), int(num_items), 1 if shuffle else 0, int(seed),
-                                           int(epoch), int(first), int(count), float(lr), float(reg), _p(loss_out),
-                                           _stream()))
+    n_hot = getattr(item_shards, "n_hot", 0)
+    check(_lib.load().nrc_mf_bpr_sgd_epoch_hot(_p(user_table), item_shards.ptr_array(), item_shards.world,
+                                               item_shards.rank, item_shards.shape[0], user_table.shape[1],
+                                               _p(train_indptr), _p(train_indices), _p(pos_users), _p(pos_items),
+                                               pos_users.numel(), int(num_items), 1 if shuffle else 0, int(seed),
+                                               int(epoch), int(first), int(count), float(lr), float(reg), _p(loss_out),
+                                               _p(item_shards.hot) if n_hot else None,
+                                               _p(item_shards.hot_delta) if n_hot else None, int(n_hot), _stream()))
     _count()
 
 
@@ -425,6 +428,12 @@ def opt_apply_multi(opt, variables, stamp, hyper):
                                           cast(tch), cast(rows), cast(dims), cast(dense), int(stamp),
                                           h.ctypes.data, _stream()))
     _count()
+
+
+def mf_sgd_set_pipelined(on):
+    """Kernel behind mf_bpr_sgd_epoch / mf_bpr_sgd_sharded for dim 64 / 128: True (default) the bulk-copy
+    pipeline, False the register form (nrc_mf_sgd_set_pipelined).  Returns the previous setting."""
+    return bool(_lib.load().nrc_mf_sgd_set_pipelined(1 if on else 0))
 
 
 def spmm_set_exact(on):

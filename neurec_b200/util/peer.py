@@ -52,6 +52,54 @@ class ShardSet:
     def __init__(self, local, ptrs, rank, backend, keep):
         self.local, self.ptrs, self.rank, self.backend, self._keep = local, list(ptrs), rank, backend, keep
         self.shape = tuple(local.shape)
+        self.hot = self.hot_delta = None          # replicated head (enable_hot)
+        self.n_hot = 0
+
+    # ---- replicated head: rows [0, n_hot) of the GLOBAL table, the most popular items after relabel_by_degree ----
+    def enable_hot(self, n_hot):
+        """Replicate global rows [0, n_hot) on every rank (collective).  From here on the sharded step reads these
+        rows from the replica and accumulates their deltas locally; call sync_hot() after every step and
+        writeback_hot() before anything reads the owners' blocks (evaluation, checkpoint)."""
+        rows, dim = self.shape
+        n_hot = int(n_hot)
+        if not 0 <= n_hot <= rows * self.world:
+            raise ValueError("n_hot %d outside the table" % n_hot)
+        if (n_hot * dim) % 4:
+            raise ValueError("n_hot * dim must be a multiple of 4")
+        self.n_hot = n_hot
+        dev = self.local.device
+        self.hot = torch.zeros((n_hot, dim), dtype=torch.float32, device=dev)
+        self.hot_delta = torch.zeros((n_hot, dim), dtype=torch.float32, device=dev)
+        lo, hi = self._own_hot_range()
+        if hi > lo:
+            self.hot[lo:hi] = self.local[lo - self.rank * rows:hi - self.rank * rows]
+        if self.world > 1:
+            dist.all_reduce(self.hot)                 # every row has exactly one owner: the sum IS the gather
+        return self
+
+    def _own_hot_range(self):
+        rows = self.shape[0]
+        lo = min(self.n_hot, self.rank * rows)
+        return lo, min(self.n_hot, (self.rank + 1) * rows)
+
+    def sync_hot(self):
+        """End of a step: sum the ranks' deltas of the replicated rows (ONE all-reduce of n_hot * dim floats) and
+        apply them to every replica (nrc_mf_hot_apply: hot += delta, delta = 0)."""
+        if not self.n_hot:
+            return
+        if self.world > 1:
+            dist.all_reduce(self.hot_delta)
+        _lib.check(_lib.load().nrc_mf_hot_apply(ctypes.c_void_p(self.hot.data_ptr()), ctypes.c_void_p(self.hot_delta.data_ptr()),
+                                                self.hot.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def writeback_hot(self):
+        """Owners copy their replicated rows back into their blocks (the blocks' copies are stale in between)."""
+        if not self.n_hot:
+            return
+        rows = self.shape[0]
+        lo, hi = self._own_hot_range()
+        if hi > lo:
+            self.local[lo - self.rank * rows:hi - self.rank * rows] = self.hot[lo:hi]
 
     @property
     def world(self):
@@ -121,6 +169,19 @@ def alloc_sharded(rows, dim, backend=None):
 def single(local):
     """world = 1: the ShardSet of an ordinary tensor (no mapping)."""
     return ShardSet(local, [local.data_ptr()], 0, "local", None)
+
+
+def relabel_by_degree(indices, num_items):
+    """Load-time item relabelling for the replicated head: new id = rank of the item by descending train degree
+    (ties by old id).  `indices` are the train CSR's item ids; returns (new_id_of_old int32 [num_items], degree of
+    every NEW id int64 [num_items]).  The reference remaps raw ids to dense ones at load time as well
+    (data/dataset.py:88-110); this only fixes the order of that remap."""
+    indices = np.asarray(indices)
+    deg = np.bincount(indices, minlength=int(num_items)).astype(np.int64)
+    order = np.argsort(-deg, kind="stable")
+    new_of_old = np.empty(int(num_items), np.int32)
+    new_of_old[order] = np.arange(int(num_items), dtype=np.int32)
+    return new_of_old, deg[order]
 
 
 def route_triplets_to_user_owner(users, pos, neg, users_per_shard):

@@ -19,14 +19,15 @@ def ev(fn, reps):
 
 
 w = bench.NeumfMl100k(0); w.setup()
-ms = ev(lambda: w.run_steps(w.spe), 5)
+EVAL_ONLY = bool(os.environ.get("NRC_EVAL_ONLY"))
+ms = ev(lambda: w.run_steps(w.spe), 1 if EVAL_ONLY else 5)
 print("NeuMF ml-100k persistent epoch%s: %.3f ms / %d steps = %.2f us/step, %.1f M samples/s" %
       (" [NRC_EPOCH_DBG=%s]" % os.environ["NRC_EPOCH_DBG"] if os.environ.get("NRC_EPOCH_DBG") else "", ms, w.spe,
        1e3 * ms / w.spe, w.spe * w.batch / ms / 1e3), flush=True)
 if os.environ.get("NRC_NCF_ONLY"):
     sys.exit(0)
 import subprocess
-for bits, what in ((15, "barriers only"), (14, "samples + barriers"), (13, "weight gradients + barriers"), (11, "tables + barriers"),
+for bits, what in () if EVAL_ONLY else ((15, "barriers only"), (14, "samples + barriers"), (13, "weight gradients + barriers"), (11, "tables + barriers"),
                    (7, "weight staging + barriers"), (-1, "128-thread group per sample (old)")):
     e = dict(os.environ, NRC_EPOCH_DBG=str(max(bits, 0)), NRC_NCF_ONLY="1")
     if bits < 0:
@@ -58,6 +59,8 @@ try:
     print("   whole evaluation as a CUDA graph: %.1f us" % (1e3 * ev(g_.replay, 20)), flush=True)
 except Exception as ex:          # measurement aid only
     print("   graph capture of the evaluation failed: %r" % (ex,), flush=True)
+if EVAL_ONLY:
+    sys.exit(0)
 del w
 g = bench.LightgcnGowalla(0); g.setup()
 fn, nbytes = g.spmm_kernel()

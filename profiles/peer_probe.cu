@@ -18,7 +18,13 @@ __device__ __forceinline__ uint32_t mix(uint32_t x) {
     return x;
 }
 __device__ __forceinline__ int64_t row_of(int64_t k, int64_t rows, int sequential) {
-    if (sequential) return k % rows;
+    if (sequential == 1) return k % rows;
+    if (sequential == 2) return 12345 % rows;                  // one hot row
+    if (sequential == 3) {                                     // p(rank) ~ 1/rank (Zipf exponent 1): rank = rows^u
+        const float u = (mix((uint32_t)k * 2654435761u + 17u) >> 8) * (1.0f / 16777216.0f);
+        const int64_t rank = (int64_t)exp2f(u * log2f((float)rows));
+        return (rank < rows ? rank : rows - 1);
+    }
     const uint64_t r = ((uint64_t)mix((uint32_t)k) << 20) ^ mix((uint32_t)(k >> 3) + 0x9e3779b9u);
     return (int64_t)(r % (uint64_t)rows);
 }
@@ -36,7 +42,7 @@ __global__ void __launch_bounds__(256) read_ldg(const float* __restrict__ T, int
 #pragma unroll
         for (int r = 0; r < R; ++r) acc += v[r].x + v[r].y + v[r].z + v[r].w;
     }
-    if (acc == 12345.678f) *sink = acc;
+    if (acc == 12345.678f && sink) *sink = acc;
 }
 
 // mode 1: warp per row, RED.v4.f32 (no read)
@@ -46,6 +52,16 @@ __global__ void __launch_bounds__(256) red_v4(float* T, int64_t rows, int64_t n,
     for (int64_t k = warp; k < n; k += nw) {
         float* p = T + row_of(k, rows, seq) * D + lane * 4;
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(1e-9f), "f"(1e-9f), "f"(1e-9f), "f"(1e-9f) : "memory");
+    }
+}
+
+// scalar REDs (4 per lane)
+__global__ void __launch_bounds__(256) red_s(float* T, int64_t rows, int64_t n, int seq) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t k = warp; k < n; k += nw) {
+        float* p = T + row_of(k, rows, seq) * D + lane * 4;
+        atomicAdd(p, 1e-9f); atomicAdd(p + 1, 1e-9f); atomicAdd(p + 2, 1e-9f); atomicAdd(p + 3, 1e-9f);
     }
 }
 
@@ -116,6 +132,7 @@ int main(int argc, char** argv) {
     printf("devices: %d\n", ndev);
     const int64_t rows = (argc > 1) ? atoll(argv[1]) : 12500000;      // 6.4 GB
     const int64_t n = (argc > 2) ? atoll(argv[2]) : (1 << 21);
+    const int quick = (argc > 3) ? atoi(argv[3]) : 0;
     float *local = nullptr, *peer = nullptr, *sink = nullptr;
     CK(cudaSetDevice(0));
     CK(cudaMalloc(&local, (size_t)rows * D * 4));
@@ -147,11 +164,14 @@ int main(int argc, char** argv) {
     if (peer) places.push_back({"peer ", peer});
     const double gb = (double)n * D * 4 / 1e9;
     for (const Where& w : places) {
-        for (int range = 0; range < 3; ++range) {
-            // range 0: random over the whole table; 1: random inside the first 64 MB; 2: sequential rows
+        for (int range = 0; range < 5; ++range) {
+            // range 0: random over the whole table; 1: random inside the first 64 MB; 2: sequential rows;
+            // 3: every access to ONE row; 4: Zipf(1) popularity over the whole table
+            if (quick && (range == 1 || range == 2)) continue;
             const int64_t r = (range == 1) ? (64ll << 20) / (D * 4) : rows;
-            const int seq = range == 2;
-            const char* rn = range == 0 ? "random rows, whole table" : range == 1 ? "random rows, 64 MB window" : "sequential rows";
+            const int seq = range == 2 ? 1 : range == 3 ? 2 : range == 4 ? 3 : 0;
+            const char* rn = range == 0 ? "random rows, whole table" : range == 1 ? "random rows, 64 MB window"
+                           : range == 2 ? "sequential rows" : range == 3 ? "ONE row" : "Zipf(1) rows";
             auto run = [&](const char* what, auto launch) {
                 launch(); CK(cudaDeviceSynchronize());
                 CK(cudaEventRecord(a));
@@ -162,14 +182,46 @@ int main(int argc, char** argv) {
                 printf("%s | %-26s | %-44s %8.3f ms  %7.1f GB/s  %6.1f M rows/s\n", w.name, rn, what, ms, gb / ms * 1e3, n / ms / 1e3);
                 fflush(stdout);
             };
-            run("LDG.128, 2 rows in flight/warp, 32 warps/SM", [&] { read_ldg<2><<<sms * 4, 256>>>(w.T, r, n, seq, sink); });
+            if (!quick) {
+                run("LDG.128, 2 rows in flight/warp, 32 warps/SM", [&] { read_ldg<2><<<sms * 4, 256>>>(w.T, r, n, seq, sink); });
+                run("LDG.128, 8 rows in flight/warp, 64 warps/SM", [&] { read_ldg<8><<<sms * 8, 256>>>(w.T, r, n, seq, sink); });
+                run("bulk copy 512 B, 32 rows in flight/CTA x4", [&] { read_bulk<32><<<sms * 4, 128, 32 * D * 4 + 32 * 8>>>(w.T, r, n, seq, sink); });
+            }
             run("LDG.128, 8 rows in flight/warp, 32 warps/SM", [&] { read_ldg<8><<<sms * 4, 256>>>(w.T, r, n, seq, sink); });
-            run("LDG.128, 8 rows in flight/warp, 64 warps/SM", [&] { read_ldg<8><<<sms * 8, 256>>>(w.T, r, n, seq, sink); });
-            run("bulk copy 512 B, 32 rows in flight/CTA x4", [&] { read_bulk<32><<<sms * 4, 128, 32 * D * 4 + 32 * 8>>>(w.T, r, n, seq, sink); });
             run("bulk copy 512 B, 128 rows in flight/CTA x2", [&] { read_bulk<128><<<sms * 2, 128, 128 * D * 4 + 128 * 8>>>(w.T, r, n, seq, sink); });
             run("RED.v4.f32 rows", [&] { red_v4<<<sms * 8, 256>>>(w.T, r, n, seq); });
-            run("ST.128 rows", [&] { st_v4<<<sms * 8, 256>>>(w.T, r, n, seq); });
+            run("scalar RED.f32 rows", [&] { red_s<<<sms * 8, 256>>>(w.T, r, n, seq); });
+            if (!quick) run("ST.128 rows", [&] { st_v4<<<sms * 8, 256>>>(w.T, r, n, seq); });
             run("bulk reduce-add 512 B", [&] { red_bulk<<<sms * 8, 128>>>(w.T, r, n, seq); });
+        }
+    }
+    if (peer) {
+        // both directions at once: device 0 works on device 1's table while device 1 works on device 0's
+        CK(cudaSetDevice(1));
+        CK(cudaDeviceEnablePeerAccess(0, 0));
+        cudaEvent_t a1, b1;
+        CK(cudaEventCreate(&a1)); CK(cudaEventCreate(&b1));
+        for (int seq : {0, 3}) {
+            for (int what = 0; what < 3; ++what) {
+                auto go = [&](int dev, float* T) {
+                    CK(cudaSetDevice(dev));
+                    if (what == 0) read_ldg<8><<<sms * 4, 256>>>(T, rows, n, seq, nullptr);
+                    else if (what == 1) red_v4<<<sms * 8, 256>>>(T, rows, n, seq);
+                    else { read_ldg<8><<<sms * 4, 256>>>(T, rows, n, seq, nullptr); red_v4<<<sms * 8, 256>>>(T, rows, n, seq); }
+                };
+                go(0, peer); go(1, local);
+                CK(cudaSetDevice(0)); CK(cudaDeviceSynchronize()); CK(cudaSetDevice(1)); CK(cudaDeviceSynchronize());
+                CK(cudaSetDevice(0)); CK(cudaEventRecord(a)); CK(cudaSetDevice(1)); CK(cudaEventRecord(a1));
+                for (int i = 0; i < 3; ++i) { go(0, peer); go(1, local); }
+                CK(cudaSetDevice(0)); CK(cudaEventRecord(b)); CK(cudaSetDevice(1)); CK(cudaEventRecord(b1));
+                CK(cudaSetDevice(0)); CK(cudaEventSynchronize(b)); CK(cudaSetDevice(1)); CK(cudaEventSynchronize(b1));
+                float m1; CK(cudaEventElapsedTime(&m1, a1, b1));
+                CK(cudaSetDevice(0));
+                printf("both directions at once | %-12s | %-28s dev0 %8.3f ms  dev1 %8.3f ms per launch set\n",
+                       seq ? "Zipf(1) rows" : "random rows", what == 0 ? "LDG.128 x8" : what == 1 ? "RED.v4" : "LDG.128 x8 then RED.v4",
+                       time_ms(a, b) / 3, m1 / 3);
+                fflush(stdout);
+            }
         }
     }
     return 0;

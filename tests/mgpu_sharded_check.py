@@ -11,6 +11,7 @@ RED-updated over NVLink by the same kernel.
   stage 1  local rows through the sharded entry point
   stage 2  remote rows only (peer loads + peer REDs)
   stage 3  no-duplicate batches: the gathered tables equal the numpy restatement on the FULL tables
+  stage 5  stage 4 again with a replicated head (ShardSet.enable_hot / sync_hot / writeback_hot)
   stage 4  the CSR-fed kernel (sampler + shuffle fused in) on sharded tables equals the same kernel
            run by ONE rank on the full item table with every rank's epoch applied in rank order
            (only checked on duplicate-free epochs where the order does not matter)
@@ -165,6 +166,24 @@ def main():
         say(rank, "stage 4 dim %d (sampler + shuffle fused, CSR-fed, sharded): dup-free %s, max|dU| %.2e max|dV| %.2e -> %s"
             % (dim, dup_free, okU, okV, "OK" if ok else "MISMATCH"))
         assert ok
+        # ---- stage 5: the same epoch with a REPLICATED HEAD (half of the item table): reads from the replica,
+        # deltas summed over the ranks by sync_hot's all-reduce, owners write back -> the same tables
+        US.local.copy_(d(U2[rank * nu_l:(rank + 1) * nu_l])); VS.local.copy_(d(V2[rank * ni_l:(rank + 1) * ni_l]))
+        torch.cuda.synchronize(); dist.barrier()
+        VS.enable_hot(ni // 2)
+        loss = torch.zeros(1, device="cuda")
+        ops.mf_bpr_sgd_epoch(US.local, VS, d(tp), d(tis[rank]), d(pus), d(tis[rank]), ni, True, seed0 + rank, 3, 0, n_loc,
+                             lr, reg, loss)
+        VS.sync_hot(); VS.writeback_hot()
+        torch.cuda.synchronize(); dist.barrier()
+        dist.all_gather(gU, US.local.contiguous()); dist.all_gather(gV, VS.local.contiguous())
+        gotU, gotV = torch.cat(gU).cpu().numpy(), torch.cat(gV).cpu().numpy()
+        okU = float(np.abs(gotU - Uw).max()); okV = float(np.abs(gotV - Vw).max())
+        ok = (okU < 2e-6 and okV < 2e-6) or not dup_free
+        say(rank, "stage 5 dim %d (replicated head of %d rows, all-reduced deltas): max|dU| %.2e max|dV| %.2e -> %s"
+            % (dim, ni // 2, okU, okV, "OK" if ok else "MISMATCH"))
+        assert ok
+        VS.n_hot = 0
         US.close(); VS.close()
         dist.barrier()
     say(rank, "ALL STAGES OK (%s, world %d)" % (backend, ws))

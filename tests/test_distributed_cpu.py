@@ -113,3 +113,15 @@ def test_item_shard_csr_restriction_partitions_every_row():
     # contiguous user blocks used by the all-gather of user rows
     blocks = [sharded.local_slice(37, r, 4) for r in range(4)]
     assert blocks[0][0] == 0 and blocks[-1][1] == 37 and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+
+
+def test_relabel_by_degree_orders_items_by_popularity():
+    """Load-time relabelling behind the replicated head: descending train degree, ties by old id."""
+    from neurec_b200.util import peer
+    idx = np.array([5, 5, 5, 2, 2, 7, 0, 0, 9], np.int32)
+    new_of_old, deg = peer.relabel_by_degree(idx, 10)
+    assert new_of_old[5] == 0 and new_of_old[0] == 1 and new_of_old[2] == 2          # 3, 2 (id 0 first), 2
+    assert new_of_old[7] == 3 and new_of_old[9] == 4
+    assert sorted(new_of_old.tolist()) == list(range(10))
+    assert deg.tolist() == [3, 2, 2, 1, 1, 0, 0, 0, 0, 0]
+    assert np.all(np.diff(np.bincount(new_of_old[idx], minlength=10)) <= 0)

@@ -169,8 +169,17 @@ def test_fused_epoch_equals_the_two_kernel_epoch(ml100k):
     assert np.abs(a["V"].cpu().numpy() - b["V"].cpu().numpy()).max() < 2e-6
 
 
+@pytest.fixture(params=["pipelined", "register"])
+def sgd_kernel(request):
+    """Both kernels behind nrc_mf_bpr_sgd_epoch: the bulk-copy pipeline (default) and the register form."""
+    from neurec_b200 import ops
+    before = ops.mf_sgd_set_pipelined(request.param == "pipelined")
+    yield request.param
+    ops.mf_sgd_set_pipelined(before)
+
+
 @pytest.mark.parametrize("dim", [128, 64, 32])
-def test_csr_fed_sgd_kernel_equals_build_then_step(dim):
+def test_csr_fed_sgd_kernel_equals_build_then_step(dim, sgd_kernel):
     """nrc_mf_bpr_sgd_epoch (sampler + shuffle + in-place BPR/SGD in one kernel, BASELINE config 5)
     against (a) nrc_epoch_build + nrc_mf_bpr_sgd_fused on the same positions and (b) the numpy
     restatement, on an epoch without repeated rows (where the in-place step is order-free)."""
@@ -219,7 +228,7 @@ def test_csr_fed_sgd_kernel_equals_build_then_step(dim):
         ops.mf_bpr_sgd_epoch(dU, peer.single(dV), *a, 10, n, lr, reg, loss)
 
 
-def test_csr_fed_sgd_kernel_with_repeated_rows_sums_every_contribution():
+def test_csr_fed_sgd_kernel_with_repeated_rows_sums_every_contribution(sgd_kernel):
     """Hot rows (Zipf items, few users): in-place REDs must not lose updates -- with lr so small that
     reads of already-updated rows change the gradient only in second order, the result must match
     the sum of all per-triplet updates computed on the pre-step tables."""
@@ -238,6 +247,80 @@ def test_csr_fed_sgd_kernel_with_repeated_rows_sums_every_contribution():
     dU, dV = dev(U0), dev(V0)
     loss = torch.zeros(1, device="cuda")
     ops.mf_bpr_sgd_epoch(dU, peer.single(dV), dev(tp), dev(ti), dev(pos_users), dev(ti), ni, True, 9, 0, 0, n, lr, 0.0, loss)
+    assert abs(float(loss) - float(g_all[0])) < 1e-3 * float(g_all[0])
+    assert np.abs(dU.cpu().numpy() - (U0 - np.float32(lr) * g_all[1])).max() < 5e-6
+    assert np.abs(dV.cpu().numpy() - (V0 - np.float32(lr) * g_all[2])).max() < 5e-6
+
+
+@pytest.mark.parametrize("dim", [128, 32])
+def test_replicated_head_gives_the_same_tables(dim, sgd_kernel):
+    """ShardSet.enable_hot: rows [0, n_hot) are read from the replica and their deltas accumulated next to it;
+    after sync_hot + writeback_hot a duplicate-free epoch leaves bit-identical tables (row + (0 + delta) = row +
+    delta), and with repeated rows every contribution is summed (first-order check)."""
+    from neurec_b200 import ops
+    from neurec_b200.util import peer
+    nu, ni, n = 300, 400_000, 300
+    rs = np.random.RandomState(dim + 7)
+    tp = np.arange(nu + 1, dtype=np.int64)
+    pos_items = rs.permutation(ni)[:nu].astype(np.int32)
+    pos_users = np.arange(nu, dtype=np.int32)
+    for seed in range(50):
+        wu, wi, wj = oracle.epoch_build(tp, pos_items, pos_users, pos_items, 1, ni, True, True, seed, 2)
+        if len(np.unique(np.concatenate([wi, wj[:, 0]]))) == 2 * n:
+            break
+    else:
+        pytest.skip("no duplicate-free epoch found")
+    n_hot = ni // 2
+    assert (wi < n_hot).any() and (wi >= n_hot).any() and (wj < n_hot).any() and (wj >= n_hot).any()
+    U0 = (rs.randn(nu, dim) * 0.1).astype(np.float32); V0 = (rs.randn(ni, dim) * 0.1).astype(np.float32)
+    a = (dev(tp), dev(pos_items), dev(pos_users), dev(pos_items), ni, True, seed, 2)
+    dU, dV, l0 = dev(U0), dev(V0), torch.zeros(1, device="cuda")
+    ops.mf_bpr_sgd_epoch(dU, peer.single(dV), *a, 0, n, 0.05, 0.01, l0)
+    eU, eV, l1 = dev(U0), dev(V0), torch.zeros(1, device="cuda")
+    sh = peer.single(eV).enable_hot(n_hot)
+    ops.mf_bpr_sgd_epoch(eU, sh, *a, 0, n, 0.05, 0.01, l1)
+    assert torch.equal(eV[:n_hot], dev(V0[:n_hot]))             # the owners' copies of replicated rows are untouched ...
+    assert float(sh.hot_delta.abs().max()) > 0                  # ... their deltas wait in the accumulator
+    sh.sync_hot(); sh.writeback_hot()
+    assert float(sh.hot_delta.abs().max()) == 0
+    assert torch.equal(eU, dU) and torch.equal(eV, dV)
+    assert abs(float(l0) - float(l1)) < 1e-4 * abs(float(l0))
+    # repeated rows, everything replicated
+    nu, ni = 64, 512
+    rows = [np.unique(rs.zipf(1.3, 40) % ni).astype(np.int32) for _ in range(nu)]
+    tp, ti = oracle.lists_to_csr(rows)
+    pos_users = np.repeat(np.arange(nu, dtype=np.int32), np.diff(tp))
+    U0 = (rs.randn(nu, dim) * 0.1).astype(np.float32); V0 = (rs.randn(ni, dim) * 0.1).astype(np.float32)
+    wu, wi, wj = oracle.epoch_build(tp, ti, pos_users, ti, 1, ni, True, True, 9, 0)
+    g_all = tf_math.mf_pairwise_grad(U0, V0, wu, wi, wj[:, 0], "bpr", 0.0)
+    dU, dV = dev(U0), dev(V0)
+    sh = peer.single(dV).enable_hot(ni)
+    ops.mf_bpr_sgd_epoch(dU, sh, dev(tp), dev(ti), dev(pos_users), dev(ti), ni, True, 9, 0, 0, len(ti), 1e-4, 0.0,
+                         torch.zeros(1, device="cuda"))
+    sh.sync_hot(); sh.writeback_hot()
+    assert np.abs(dV.cpu().numpy() - (V0 - np.float32(1e-4) * g_all[2])).max() < 5e-6
+
+
+@pytest.mark.parametrize("dim", [128, 64])
+def test_csr_fed_sgd_kernel_many_rounds_per_ring_slot(dim, sgd_kernel):
+    """~60 k triplets in one launch: every ring slot of the pipelined kernel is reused several times (148 CTAs x
+    128 slots per round), with a ragged last round; same first-order check as above plus the loss."""
+    from neurec_b200 import ops
+    from neurec_b200.util import peer
+    nu, ni = 3000, 20000
+    rs = np.random.RandomState(dim)
+    rows = [np.unique(rs.randint(0, ni, 21)).astype(np.int32) for _ in range(nu)]
+    tp, ti = oracle.lists_to_csr(rows)
+    pos_users = np.repeat(np.arange(nu, dtype=np.int32), np.diff(tp))
+    n = len(ti)
+    assert n > 3 * 148 * 128
+    U0 = (rs.randn(nu, dim) * 0.1).astype(np.float32); V0 = (rs.randn(ni, dim) * 0.1).astype(np.float32)
+    lr, reg = 1e-4, 0.01
+    wu, wi, wj = oracle.epoch_build(tp, ti, pos_users, ti, 1, ni, True, True, 5, 1)
+    g_all = tf_math.mf_pairwise_grad(U0, V0, wu, wi, wj[:, 0], "bpr", reg)
+    dU, dV = dev(U0), dev(V0)
+    loss = torch.zeros(1, device="cuda")
+    ops.mf_bpr_sgd_epoch(dU, peer.single(dV), dev(tp), dev(ti), dev(pos_users), dev(ti), ni, True, 5, 1, 0, n, lr, reg, loss)
     assert abs(float(loss) - float(g_all[0])) < 1e-3 * float(g_all[0])
     assert np.abs(dU.cpu().numpy() - (U0 - np.float32(lr) * g_all[1])).max() < 5e-6
     assert np.abs(dV.cpu().numpy() - (V0 - np.float32(lr) * g_all[2])).max() < 5e-6
