@@ -172,7 +172,8 @@ constexpr int kLongRow = 192;
 
 template <int G, int UNMAX>   // lanes per gathered row: dim == 4 * G, G in {8, 16, 32}; load instructions in flight
 __device__ __forceinline__ void spmm_accumulate(const SpmmArgs& A, int64_t beg, int64_t end, int64_t seg_stride,
-                                                int lane, float4& acc) {
+                                                int lane, float4& acc, bool have_first = false, int first_c = 0,
+                                                float first_v = 0.0f) {
     constexpr int NPI = 32 / G;            // non-zeros per load instruction
     constexpr int STEPS = 32 / NPI;        // load instructions per 32-nnz segment
     constexpr int UN = (STEPS < UNMAX) ? STEPS : UNMAX;
@@ -180,8 +181,10 @@ __device__ __forceinline__ void spmm_accumulate(const SpmmArgs& A, int64_t beg, 
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
     for (int64_t p = beg; p < end; p += seg_stride) {
         const int cnt = (int)((end - p < 32) ? (end - p) : 32);
-        const int my_c = (lane < cnt) ? __ldg(A.indices + p + lane) : 0;
-        const float my_v = (lane < cnt) ? __ldg(A.values + p + lane) : 0.0f;   // padding: 0 * row 0
+        // the first segment's (column, value) pairs may have been fetched one row ahead by the caller
+        const bool pre = have_first && p == beg;
+        const int my_c = pre ? first_c : ((lane < cnt) ? __ldg(A.indices + p + lane) : 0);
+        const float my_v = pre ? first_v : ((lane < cnt) ? __ldg(A.values + p + lane) : 0.0f);   // padding: 0 * row 0
 #pragma unroll 1
         for (int j0 = 0; j0 * NPI < cnt; j0 += UN) {
             float4 x[UN];
@@ -191,11 +194,13 @@ __device__ __forceinline__ void spmm_accumulate(const SpmmArgs& A, int64_t beg, 
                 const int src = (j0 + j) * NPI + grp;
                 const int c = __shfl_sync(kFull, my_c, src & 31);
                 v[j] = __shfl_sync(kFull, my_v, src & 31);
-                x[j] = __ldg(reinterpret_cast<const float4*>(A.X + (size_t)c * A.dim) + sub);
+                // padding slots of the last batch issue no load at all (predicated off)
+                x[j] = (src < cnt) ? __ldg(reinterpret_cast<const float4*>(A.X + (size_t)c * A.dim) + sub)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int j = 0; j < UN; ++j) {
-                if ((j0 + j) * NPI + grp < cnt) {          // padding slots gathered row 0: never accumulate them
+                if ((j0 + j) * NPI + grp < cnt) {          // padding slots: never accumulated
                     float4& a = (j & 1) ? a1 : a0;
                     a.x = fmaf(v[j], x[j].x, a.x); a.y = fmaf(v[j], x[j].y, a.y);
                     a.z = fmaf(v[j], x[j].z, a.z); a.w = fmaf(v[j], x[j].w, a.w);
@@ -248,16 +253,26 @@ __global__ void __launch_bounds__(256, UNMAX == 4 ? 4 : 3) spmm_csr_fast_kernel(
             lng = false;        // decided per unit with a CTA vote below
         }
     };
-    int r, rn; int64_t beg, end, begn, endn; bool lng, lngn;
+    // the row's first 32 (column, value) pairs: issued one row ahead, consumed by spmm_accumulate
+    auto first_seg = [&](int64_t b, int64_t e, int& c, float& v) {
+        const bool in = b + lane < e;
+        c = in ? __ldg(A.indices + b + lane) : 0;
+        v = in ? __ldg(A.values + b + lane) : 0.0f;
+    };
+    int r, rn, rnn; int64_t beg, end, begn, endn, begnn, endnn; bool lng, lngn, lngnn;
+    int fc, fcn; float fv, fvn;
     fetch(blockIdx.x, r, beg, end, lng);
+    fetch(blockIdx.x + gridDim.x, rn, begn, endn, lngn);
+    first_seg(beg, end, fc, fv);
     for (int w = blockIdx.x; w < units; w += gridDim.x) {
-        fetch(w + gridDim.x, rn, begn, endn, lngn);
+        fetch(w + 2 * gridDim.x, rnn, begnn, endnn, lngnn);      // two units ahead: row id + extent
+        first_seg(begn, endn, fcn, fvn);                          // one unit ahead: its first segment
         const bool live = w * 8 + warp < A.n_rows;
         const bool any_long = A.row_order ? lng : (bool)__syncthreads_or(live && (end - beg) > kLongRow);
         if (!any_long) {
             if (live) {
                 float4 acc;
-                spmm_accumulate<G, UNMAX>(A, beg, end, 32, lane, acc);
+                spmm_accumulate<G, UNMAX>(A, beg, end, 32, lane, acc, true, fc, fv);
                 if (lane < G) spmm_epilogue<G>(A, r, lane, acc);
             }
         } else {
@@ -283,7 +298,8 @@ __global__ void __launch_bounds__(256, UNMAX == 4 ? 4 : 3) spmm_csr_fast_kernel(
                 __syncthreads();
             }
         }
-        r = rn; beg = begn; end = endn; lng = lngn;
+        r = rn; beg = begn; end = endn; lng = lngn; fc = fcn; fv = fvn;
+        rn = rnn; begn = begnn; endn = endnn; lngn = lngnn;
     }
 }
 
@@ -300,6 +316,20 @@ static int spmm_launch(const SpmmArgs& A, cudaStream_t st) {
         static int un = -1;
         // 8 loads in flight measured faster than 4 on gowalla (60.9 vs 70.3 us)
         if (un < 0) { const char* e = getenv("NRC_SPMM_UN"); un = (e && atoi(e) == 4) ? 4 : 8; }
+        {   // one wave: exactly the CTAs that are resident at once (a CTA strides over its units, prefetching ahead;
+            // the old 8-per-SM grid ran 2.67 waves with a third of the machine idle in the last one)
+            static int occ8 = 0, occ4 = 0;
+            if (!occ8) {
+                NRC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ8, spmm_csr_fast_kernel<16, 8>, threads, 0));
+                NRC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, spmm_csr_fast_kernel<16, 4>, threads, 0));
+                if (occ8 < 1) occ8 = 1;
+                if (occ4 < 1) occ4 = 1;
+            }
+            static int waves = -1;
+            if (waves < 0) { const char* e = getenv("NRC_SPMM_WAVES"); waves = e ? atoi(e) : 1; }
+            const int64_t resident = (int64_t)sm_count() * (un == 8 ? occ8 : occ4) * (waves > 0 ? waves : 1);
+            if (waves > 0 && blocks > resident) blocks = resident;
+        }
         if (un == 8) {
             if (A.dim == 32) spmm_csr_fast_kernel<8, 8><<<(unsigned)blocks, threads, 0, st>>>(A);
             else if (A.dim == 64) spmm_csr_fast_kernel<16, 8><<<(unsigned)blocks, threads, 0, st>>>(A);

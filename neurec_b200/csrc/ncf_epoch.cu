@@ -55,7 +55,6 @@ struct NcfEpochParams {
     int32_t batch_size, pairwise, loss_kind, opt_kind, first_stamp, build, bar_mode;
     int64_t seg_end[4];                    // running float4-group counts of seg[0..3] (tables_vec4)
     int32_t tables_vec4;                   // every table width a multiple of 4 (and 16-byte aligned rows)
-    int32_t warp_mode;                     // 1: one warp per sample (default); 0: 128-thread group per sample (NRC_NCF_GROUP=1)
     int32_t dbg;                           // NRC_EPOCH_DBG bits (0 in normal use): 1 skip samples, 2 skip weight gradients, 4 skip tables, 8 skip weight staging
     int32_t sw_floats;                     // shared-memory floats of the weight copy (towers, rounded up to 4)
     int32_t wblocked, wblocks, sred_off;   // blocked weight-gradient path: 4 x 4 blocks per tower; smem offset (floats) of its reduction slots
@@ -222,133 +221,6 @@ __device__ __forceinline__ void ncf_sample(const NcfEpochParams& Q, const float*
     group_sync(grp);
 }
 
-// ----------------------------------------------------------------------------------------
-// One sample by ONE WARP (default): no block-level barriers in the tower, only __syncwarp.  Forward: lane j
-// owns output column j (and j + 32, ...): acc = b[j] + sum_k a[k] W[k][j] with a[k] broadcast from shared
-// memory and W rows read conflict-free.  Backward: lane k owns input k; it walks its row W[k][.] starting
-// at column `lane` (rotation) so that the 32 lanes hit 32 different banks of the unpadded row-major W.
-// A batch of 256 samples occupies 256 of the grid's 1184 warps at once: the phase is one latency chain
-// (ids -> rows -> ~1.3k instructions -> REDs) instead of ~20 block barriers per sample.
-// ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void ncf_sample_warp(const NcfEpochParams& Q, const float* sW, float* sAct, float* sDel, int lane,
-                                                int64_t b, int64_t cnt, int32_t u, int32_t it0, int32_t third, int32_t stamp,
-                                                float& loss_out) {
-    const NcfDev& S = Q.S;
-    const NcfPtrs& P = Q.P;
-    const int passes = Q.pairwise ? 2 : 1;
-    const int it[2] = {it0, Q.pairwise ? third : 0};
-    const int MD = S.mlp_dim, L = S.n_layers;
-    float yhat[2] = {0.0f, 0.0f};
-    for (int p = 0; p < passes; ++p) {
-        float* act = sAct + p * S.act_size;
-        float mf = 0.0f;
-        for (int k = lane; k < S.mf_dim; k += kWarp)
-            mf = fmaf(__ldcg(P.mf_user + (size_t)u * S.mf_dim + k), __ldcg(P.mf_item + (size_t)it[p] * S.mf_dim + k), mf);
-        for (int k = lane; k < 2 * MD; k += kWarp)
-            act[k] = (k < MD) ? __ldcg(P.mlp_user + (size_t)u * MD + k) : __ldcg(P.mlp_item + (size_t)it[p] * MD + (k - MD));
-        __syncwarp();
-        const float* tw = sW + (size_t)((p == 1 && S.n_towers == 2) ? 1 : 0) * S.tower_size;
-        for (int l = 0; l < L; ++l) {
-            const int in = S.in_dim[l], out = S.out_dim[l];
-            const float* W = tw + S.w_off[l];
-            const float* a_in = act + S.a_off[l];
-            float* a_out = act + S.a_off[l + 1];
-            for (int j = lane; j < out; j += kWarp) {
-                float acc = tw[S.b_off[l] + j];
-#pragma unroll 8
-                for (int k = 0; k < in; ++k) acc = fmaf(a_in[k], W[k * out + j], acc);
-                a_out[j] = fmaxf(acc, 0.0f);          // tf.nn.relu
-            }
-            __syncwarp();
-        }
-        float s = 0.0f;
-        if (L > 0)
-            for (int j = lane; j < S.out_dim[L - 1]; j += kWarp) s += act[S.a_off[L] + j];
-        yhat[p] = warp_sum(mf + s);                    // NeuMF.py:85 reduce_sum(concat(mf, mlp))
-    }
-    float l, g;
-    if (Q.pairwise) {
-        const float x = yhat[0] - yhat[1];             // NeuMF.py:92
-        if (Q.loss_kind == NRC_LOSS_BPR) {
-            l = (x >= 0.f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
-            g = -1.0f / (1.0f + expf(x));
-        } else if (Q.loss_kind == NRC_LOSS_HINGE) {
-            const float t = x + 1.0f; l = fmaxf(t, 0.f); g = (t > 0.f) ? 1.f : 0.f;
-        } else {
-            const float t = 1.0f - x; l = t * t; g = -2.0f * t;
-        }
-    } else {
-        const float x = yhat[0], z = __int_as_float(third);
-        if (Q.loss_kind == NRC_LOSS_CROSS_ENTROPY) {
-            const float inv_b = 1.0f / (float)cnt;
-            const float e = expf(-fabsf(x));
-            l = (fmaxf(x, 0.f) - x * z + log1pf(e)) * inv_b;
-            const float sg = (x >= 0.f) ? 1.f / (1.f + e) : e / (1.f + e);
-            g = (sg - z) * inv_b;
-        } else {
-            const float t = z - x; l = t * t; g = -2.0f * t;
-        }
-    }
-    float sq_mf = 0.f, sq_mlp = 0.f;
-    for (int p = 0; p < passes; ++p) {
-        const float gp = (p == 0) ? g : -g;
-        const float* tw = sW + (size_t)((p == 1 && S.n_towers == 2) ? 1 : 0) * S.tower_size;
-        float* act = sAct + p * S.act_size;
-        float* del = sDel + p * S.act_size;
-        if (L > 0) {
-            for (int j = lane; j < S.out_dim[L - 1]; j += kWarp)
-                del[S.a_off[L] + j] = (act[S.a_off[L] + j] > 0.0f) ? gp : 0.0f;     // ReluGrad on the last layer
-            __syncwarp();
-            for (int l2 = L - 1; l2 >= 0; --l2) {
-                const int in = S.in_dim[l2], out = S.out_dim[l2];
-                const float* W = tw + S.w_off[l2];
-                const float* d_out = del + S.a_off[l2 + 1];
-                const float* a_in = act + S.a_off[l2];
-                float* d_in = del + S.a_off[l2];
-                for (int k = lane; k < in; k += kWarp) {
-                    float sacc = 0.0f;
-                    int j = lane % out;                 // rotated start: conflict-free rows
-#pragma unroll 8
-                    for (int c = 0; c < out; ++c) {
-                        sacc = fmaf(W[k * out + j], d_out[j], sacc);
-                        j = (j + 1 == out) ? 0 : j + 1;
-                    }
-                    d_in[k] = (l2 > 0) ? ((a_in[k] > 0.0f) ? sacc : 0.0f) : sacc;
-                }
-                __syncwarp();
-            }
-        }
-        for (int k = lane; k < S.mf_dim; k += kWarp) {
-            const float pu = __ldcg(P.mf_user + (size_t)u * S.mf_dim + k);
-            const float qi = __ldcg(P.mf_item + (size_t)it[p] * S.mf_dim + k);
-            atomicAdd(P.g_mf_user + (size_t)u * S.mf_dim + k, gp * qi + (p == 0 ? Q.reg_mf * pu : 0.f));
-            atomicAdd(P.g_mf_item + (size_t)it[p] * S.mf_dim + k, gp * pu + Q.reg_mf * qi);
-            sq_mf += qi * qi + (p == 0 ? pu * pu : 0.f);
-        }
-        for (int k = lane; k < 2 * MD; k += kWarp) {
-            const float a = act[k];
-            if (k < MD) {
-                atomicAdd(P.g_mlp_user + (size_t)u * MD + k, del[k] + (p == 0 ? Q.reg_mlp * a : 0.f));
-                if (p == 0) sq_mlp += a * a;
-            } else {
-                atomicAdd(P.g_mlp_item + (size_t)it[p] * MD + (k - MD), del[k] + Q.reg_mlp * a);
-                sq_mlp += a * a;
-            }
-        }
-        if (lane == 0) P.t_item[it[p]] = stamp;
-    }
-    if (lane == 0) P.t_user[u] = stamp;
-    if (Q.reg_mf != 0.f || Q.reg_mlp != 0.f)              // NeuMF.py:94-100
-        l += warp_sum(Q.reg_mf * 0.5f * sq_mf + Q.reg_mlp * 0.5f * sq_mlp);
-    loss_out = l;
-    float* out_s = Q.scratch + (size_t)b * (2 * passes * S.act_size);
-    for (int e = lane; e < passes * S.act_size; e += kWarp) {
-        out_s[e] = sAct[e];
-        out_s[passes * S.act_size + e] = sDel[e];
-    }
-    __syncwarp();
-}
-
 __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpochParams Q) {
     extern __shared__ __align__(16) float sm[];
     const NcfDev& S = Q.S;
@@ -360,10 +232,6 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
     float* sDel = sAct + passes * S.act_size;
     float* part = sDel + passes * S.act_size;
     float* red = part + kNcfThreads;
-    // warp-per-sample buffers (Q.warp_mode): [warp][2 * passes * act_size] right after the weights
-    const int lane = tid_cta & 31, warp = tid_cta >> 5;
-    float* wAct = sW + (size_t)Q.sw_floats + (size_t)warp * (2 * passes * S.act_size);
-    float* wDel = wAct + passes * S.act_size;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
     unsigned int target = 0;
@@ -420,17 +288,6 @@ __global__ void __launch_bounds__(kEpThreads, 1) ncf_epoch_kernel(const NcfEpoch
         }
         __syncthreads();
         float loss_acc = 0.0f;
-        if (Q.warp_mode) {
-            constexpr int wpb = kEpThreads / 32;
-            for (int64_t b = (int64_t)blockIdx.x * wpb + warp; b < cnt && !(Q.dbg & 1); b += (int64_t)gridDim.x * wpb) {
-                float l = 0.0f;
-                ncf_sample_warp(Q, sW, wAct, wDel, lane, b, cnt, __ldcg(Q.ws_u + off + b), __ldcg(Q.ws_i + off + b),
-                                __ldcg(Q.ws_t + off + b), stamp, l);
-                loss_acc += l;
-            }
-            if (lane == 0 && loss_acc != 0.0f) atomicAdd(Q.step_loss + s, loss_acc);
-            loss_acc = 0.0f;
-        } else
         for (int64_t b = (int64_t)blockIdx.x * kGroups + grp; b < cnt && !(Q.dbg & 1); b += (int64_t)gridDim.x * kGroups) {
             float l = 0.0f;
             ncf_sample(Q, sW, sAct, sDel, part, red, tid, grp, b, cnt, __ldcg(Q.ws_u + off + b), __ldcg(Q.ws_i + off + b),
@@ -647,14 +504,7 @@ extern "C" int nrc_ncf_epoch_fused(const nrc_ncf_shape* shape, float* mf_user, f
     const NcfDev& S = Q.S;
     const int passes = pairwise ? 2 : 1;
     Q.sw_floats = (S.n_towers * S.tower_size + 3) & ~3;
-    size_t smem_floats = (size_t)Q.sw_floats + (size_t)kGroups * (2 * passes * S.act_size + kNcfThreads + 8);
-    {
-        const size_t warp_layout = (size_t)Q.sw_floats + (size_t)(kEpThreads / 32) * (2 * passes * S.act_size);
-        if (warp_layout > smem_floats) smem_floats = warp_layout;
-        static int grp_mode = -1;
-        if (grp_mode < 0) { const char* e = getenv("NRC_NCF_GROUP"); grp_mode = e ? atoi(e) : 0; }
-        Q.warp_mode = grp_mode ? 0 : 1;
-    }
+    const size_t smem_floats = (size_t)Q.sw_floats + (size_t)kGroups * (2 * passes * S.act_size + kNcfThreads + 8);
     const size_t smem = (smem_floats + (kEpThreads / 64) * 16) * 4;
     Q.sred_off = (int32_t)smem_floats;
     Q.wblocked = 1; Q.wblocks = 0;

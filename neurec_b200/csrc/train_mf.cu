@@ -431,22 +431,25 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
 }
 
 // ----------------------------------------------------------------------------------------
-// Pipelined form of the CSR-fed step (default for dim >= 64; NRC_SGD_PIPE=0 selects the register form above).
+// Pipelined form of the CSR-fed step (NRC_SGD_PIPE / nrc_mf_sgd_set_pipelined).
 // The register form keeps 2 triplets per warp in flight and alternates a sampling phase with an update phase;
 // ncu shows it latency-bound (long-scoreboard stalls, DRAM at ~3/4 of the copy peak).  Here the rows never
-// pass through registers on their way in or out:
-//   producers (4 warps, one THREAD per ring slot): bijection -> (user, positive) -> rejection draw, then three
-//       bulk copies (cp.async.bulk, row bytes each) of the triplet's rows into the slot, completion counted on
-//       the slot's `full` mbarrier.  The next triplet is sampled while the slot is still in use.
-//   consumers (8 warps, 16 slots each): wait `full`, read the three rows from shared memory, the same arithmetic
-//       as above, write the three delta rows IN PLACE, and hand them to the copy engine as three bulk
-//       reduce-adds (cp.reduce.async.bulk .add.f32 -- the update of a local or a peer row alike); the slot's
-//       `empty` mbarrier is released once the engine has read the deltas (wait_group.read).
-// 128 slots x 3 rows in flight per SM (192 KB at d = 128) independent of register pressure, sampling chains,
-// row gathers and updates all overlapped.  One CTA per SM.
+// pass through registers on their way in or out, and sampling runs ahead of the row traffic:
+//   samplers (16 warps, 512 threads): bijection -> (user, positive) -> rejection draw; the ids go into a
+//       512-entry shared-memory queue (sequence-numbered entries, one per sampler thread).  A sampling chain is
+//       4-5 DEPENDENT DRAM round trips, so throughput = chains in flight / chain latency: 512 per SM.
+//   consumers (8 warps, 16 ring slots each): lane 0 takes the next ids from the queue and issues three bulk copies
+//       (cp.async.bulk, one row each) into the slot, completion counted on the slot's mbarrier; when the rows
+//       have landed the warp computes the triplet from shared memory, writes the three delta rows IN PLACE and
+//       hands them to the copy engine as bulk reduce-adds (cp.reduce.async.bulk .add.f32 -- local and peer
+//       rows alike).  A slot is refilled as soon as the engine has read its deltas (wait_group.read), i.e. one
+//       slot later in the warp's round-robin.
+// 128 slots x 3 rows in flight per SM (192 KB at d = 128) whatever the register pressure.  One CTA per SM.
+// CTA-local sequence number n <-> ring slot n % 128, round n / 128, position first + blockIdx*128 + slot + round*stride.
 // ----------------------------------------------------------------------------------------
-constexpr int kPipeSlots = 128, kPipeProdWarps = 4, kPipeConsWarps = 8;
-constexpr int kPipeThreads = (kPipeProdWarps + kPipeConsWarps) * 32;
+constexpr int kPipeSlots = 128, kPipeSamplerWarps = 16, kPipeConsWarps = 8;
+constexpr int kPipeSamplers = kPipeSamplerWarps * 32;          // = id-queue entries (one per sampler thread)
+constexpr int kPipeThreads = (kPipeSamplerWarps + kPipeConsWarps) * 32;
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -454,6 +457,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
+
+struct PipeIds { int32_t u, i, j, pad; };
 
 template <int VEC, bool SHARDED>
 __global__ void __launch_bounds__(kPipeThreads, 1)
@@ -463,51 +468,82 @@ mf_bpr_sgd_pipe_kernel(float* __restrict__ U_local, const RowShards V, const Epo
     constexpr uint32_t kRowBytes = D * 4;
     extern __shared__ __align__(128) unsigned char pipe_smem[];
     float* ring = reinterpret_cast<float*>(pipe_smem);                              // [slots][3][D]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(pipe_smem + (size_t)kPipeSlots * 3 * kRowBytes);   // full[], empty[]
-    float** dsts = reinterpret_cast<float**>(bars + 2 * kPipeSlots);                // [slots][3] global row addresses
+    uint64_t* full = reinterpret_cast<uint64_t*>(pipe_smem + (size_t)kPipeSlots * 3 * kRowBytes);   // [slots]
+    PipeIds* idq = reinterpret_cast<PipeIds*>(full + kPipeSlots);                   // [samplers]
+    volatile int32_t* seq_ready = reinterpret_cast<volatile int32_t*>(idq + kPipeSamplers);   // n + 1 once entry n % Q is filled
+    volatile int32_t* seq_done = seq_ready + kPipeSamplers;                         // n + 1 once it has been taken
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < kPipeSlots) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bars + tid)));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bars + kPipeSlots + tid)));
-    }
+    if (tid < kPipeSlots) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(full + tid)));
+    for (int e = tid; e < kPipeSamplers; e += kPipeThreads) { seq_ready[e] = 0; seq_done[e] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * kPipeSlots;
-    if (warp < kPipeProdWarps) {
-        const int s = tid;
-        const uint32_t full = (uint32_t)__cvta_generic_to_shared(bars + s);
-        const uint32_t empty = (uint32_t)__cvta_generic_to_shared(bars + kPipeSlots + s);
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (size_t)s * 3 * D);
-        uint32_t r = 0;
-        for (int64_t q = (int64_t)blockIdx.x * kPipeSlots + s; q < count; q += stride, ++r) {
+    const int64_t base = (int64_t)blockIdx.x * kPipeSlots;
+    // rounds this CTA takes part in, and its sequence numbers [0, n_end); entries whose position is past `count`
+    // (the ragged last round) are skipped by samplers and consumers alike
+    const int64_t rounds = (count > base) ? (count - base + stride - 1) / stride : 0;
+    const int32_t n_end = (int32_t)(rounds * kPipeSlots);
+    auto pos_of = [&](int32_t n) { return base + (n % kPipeSlots) + (int64_t)(n / kPipeSlots) * stride; };
+    if (warp < kPipeSamplerWarps) {
+        for (int32_t n = tid; n < n_end; n += kPipeSamplers) {
+            const int64_t q = pos_of(n);
+            if (q >= count) continue;
             int32_t u, i, j;
             epoch_sample(E, first + q, 0, u, i, j);
-            bool ri, rj;
-            float* pu = U_local + (size_t)u * D;
-            float *wi, *wj;
-            float* qi = V.row<SHARDED>(i, D, ri, wi);
-            float* qj = V.row<SHARDED>(j, D, rj, wj);
-            if (r > 0) mbar_wait(empty, (r - 1) & 1);       // the slot's previous deltas have left shared memory
-            dsts[s * 3 + 0] = pu; dsts[s * 3 + 1] = wi; dsts[s * 3 + 2] = wj;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(3 * kRowBytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(pu), "r"(kRowBytes), "r"(full) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst + kRowBytes), "l"(qi), "r"(kRowBytes), "r"(full) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst + 2 * kRowBytes), "l"(qj), "r"(kRowBytes), "r"(full) : "memory");
+            if (n >= kPipeSamplers) {                       // this thread's previous entry must have been taken
+                const int32_t want = n - kPipeSamplers + 1;
+                while (seq_done[tid] != want) { }
+            }
+            idq[tid] = PipeIds{u, i, j, 0};
+            __threadfence_block();
+            seq_ready[tid] = n + 1;
         }
     } else {
-        const int cw = warp - kPipeProdWarps;
+        const int cw = warp - kPipeSamplerWarps;
         float loss_acc = 0.0f;
-        int prev = -1;
-        for (uint32_t r = 0;; ++r) {
-            bool any = false;
-            for (int s = cw; s < kPipeSlots; s += kPipeConsWarps) {
-                const int64_t q = (int64_t)blockIdx.x * kPipeSlots + s + (int64_t)r * stride;
-                if (q >= count) continue;
-                any = true;
-                mbar_wait((uint32_t)__cvta_generic_to_shared(bars + s), r & 1);
+        // the update addresses of the triplet in each of this warp's 16 slots (lane k keeps slot cw + 8k)
+        float *upd_u = nullptr, *upd_i = nullptr, *upd_j = nullptr;
+        auto load_slot = [&](int32_t n) {                  // whole warp; lane 0 works, lane (slot index) remembers
+            const int s = n % kPipeSlots, e = n % kPipeSamplers, k = s / kPipeConsWarps;
+            float *pu = nullptr, *wi = nullptr, *wj = nullptr;
+            if (lane == 0) {
+                while (seq_ready[e] != n + 1) { }
+                __threadfence_block();
+                const PipeIds t = idq[e];
+                __threadfence_block();
+                seq_done[e] = n + 1;
+                bool ri, rj;
+                pu = U_local + (size_t)t.u * D;
+                float* qi = V.row<SHARDED>(t.i, D, ri, wi);
+                float* qj = V.row<SHARDED>(t.j, D, rj, wj);
+                const uint32_t bar = (uint32_t)__cvta_generic_to_shared(full + s);
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (size_t)s * 3 * D);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(3 * kRowBytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(pu), "r"(kRowBytes), "r"(bar) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + kRowBytes), "l"(qi), "r"(kRowBytes), "r"(bar) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + 2 * kRowBytes), "l"(qj), "r"(kRowBytes), "r"(bar) : "memory");
+            }
+            pu = reinterpret_cast<float*>(__shfl_sync(kFull, (unsigned long long)pu, 0));
+            wi = reinterpret_cast<float*>(__shfl_sync(kFull, (unsigned long long)wi, 0));
+            wj = reinterpret_cast<float*>(__shfl_sync(kFull, (unsigned long long)wj, 0));
+            if (lane == k) { upd_u = pu; upd_i = wi; upd_j = wj; }
+        };
+        constexpr int kMine = kPipeSlots / kPipeConsWarps;         // 16 slots per consumer warp
+        // prologue: round 0 of every slot of this warp
+        for (int k = 0; k < kMine; ++k) {
+            const int32_t n = cw + k * kPipeConsWarps;
+            if (n < n_end && pos_of(n) < count) load_slot(n);
+        }
+        int32_t prev_n = -1;                                        // sequence number whose deltas were handed over last
+        for (int32_t r = 0; r < (int32_t)rounds; ++r) {
+            for (int k = 0; k < kMine; ++k) {
+                const int s = cw + k * kPipeConsWarps;
+                const int32_t n = r * kPipeSlots + s;
+                if (pos_of(n) >= count) continue;
+                mbar_wait((uint32_t)__cvta_generic_to_shared(full + s), r & 1);
                 float* slot = ring + (size_t)s * 3 * D + lane * VEC;
                 float a[VEC], bi[VEC], bj[VEC];
                 ld_vec<VEC>(slot, a); ld_vec<VEC>(slot + D, bi); ld_vec<VEC>(slot + 2 * D, bj);
@@ -532,12 +568,11 @@ mf_bpr_sgd_pipe_kernel(float* __restrict__ U_local, const RowShards V, const Epo
                 }
                 st_vec<VEC>(slot, du); st_vec<VEC>(slot + D, dvi); st_vec<VEC>(slot + 2 * D, dvj);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
+                float* const p0 = reinterpret_cast<float*>(__shfl_sync(kFull, (unsigned long long)upd_u, k));
+                float* const p1 = reinterpret_cast<float*>(__shfl_sync(kFull, (unsigned long long)upd_i, k));
+                float* const p2 = reinterpret_cast<float*>(__shfl_sync(kFull, (unsigned long long)upd_j, k));
                 if (lane == 0) {
                     const uint32_t src = (uint32_t)__cvta_generic_to_shared(ring + (size_t)s * 3 * D);
-                    float* const p0 = dsts[s * 3 + 0];
-                    float* const p1 = dsts[s * 3 + 1];
-                    float* const p2 = dsts[s * 3 + 2];
                     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                                  ::"l"(p0), "r"(src), "r"(kRowBytes) : "memory");
                     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
@@ -545,22 +580,18 @@ mf_bpr_sgd_pipe_kernel(float* __restrict__ U_local, const RowShards V, const Epo
                     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                                  ::"l"(p2), "r"(src + 2 * kRowBytes), "r"(kRowBytes) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    if (prev >= 0) {        // the previous slot's deltas have been read by the engine: hand the slot back
-                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
-                                     ::"r"((uint32_t)__cvta_generic_to_shared(bars + kPipeSlots + prev)) : "memory");
-                    }
+                    // the deltas handed over one slot ago have left shared memory: that slot can be refilled
+                    if (prev_n >= 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 }
-                prev = s;
                 __syncwarp();
+                if (prev_n >= 0) {
+                    const int32_t nn = prev_n + kPipeSlots;             // same slot, next round
+                    if (nn < n_end && pos_of(nn) < count) load_slot(nn);
+                }
+                prev_n = n;
             }
-            if (!any) break;
         }
         if (lane == 0) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            if (prev >= 0)
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
-                             ::"r"((uint32_t)__cvta_generic_to_shared(bars + kPipeSlots + prev)) : "memory");
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every reduce-add performed before the kernel ends
             if (loss) atomicAdd(loss, loss_acc);
         }
@@ -570,7 +601,7 @@ mf_bpr_sgd_pipe_kernel(float* __restrict__ U_local, const RowShards V, const Epo
 template <int VEC, bool SH>
 static int launch_pipe(float* U_local, const RowShards& SV, const EpochSpec& E, int64_t first, int64_t count, float lr,
                        float reg, float* loss, cudaStream_t st) {
-    constexpr size_t smem = (size_t)kPipeSlots * 3 * (32 * VEC * 4) + (size_t)kPipeSlots * 2 * 8 + (size_t)kPipeSlots * 3 * 8;
+    constexpr size_t smem = (size_t)kPipeSlots * 3 * (32 * VEC * 4) + (size_t)kPipeSlots * 8 + (size_t)kPipeSamplers * (16 + 8);
     static bool attr = false;
     if (!attr) {
         NRC_CUDA_CHECK(cudaFuncSetAttribute(mf_bpr_sgd_pipe_kernel<VEC, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

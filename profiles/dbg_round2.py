@@ -28,10 +28,8 @@ if os.environ.get("NRC_NCF_ONLY"):
     sys.exit(0)
 import subprocess
 for bits, what in () if EVAL_ONLY else ((15, "barriers only"), (14, "samples + barriers"), (13, "weight gradients + barriers"), (11, "tables + barriers"),
-                   (7, "weight staging + barriers"), (-1, "128-thread group per sample (old)")):
+                   (7, "weight staging + barriers")):
     e = dict(os.environ, NRC_EPOCH_DBG=str(max(bits, 0)), NRC_NCF_ONLY="1")
-    if bits < 0:
-        e["NRC_NCF_GROUP"] = "1"
     out = subprocess.run([sys.executable, __file__], env=e, capture_output=True, text=True).stdout.strip().splitlines()
     print("   %-32s %s" % (what, out[0] if out else "?"), flush=True)
 # NeuMF evaluation (predict over all items + mask + top-K + metrics): the fast scoring kernel vs the generic one
