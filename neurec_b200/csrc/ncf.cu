@@ -456,131 +456,146 @@ ncf_scores_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ u
 // Fast predict for the reference's default tower (layers [64, 32, 16], mlp_dim 32; NeuMF.py:163-168 /
 // MLP.py:136-140 score every item for every test user).  The first layer factorises over the concat:
 //   relu([mu, mi] W0 + b0) = relu(A_u + B_i),  A_u = mu W0[:32] + b0 (per user),  B_i = mi W0[32:] (per item)
-// so the 64x64 layer costs 64 adds per (user, item) pair once B is tabulated (ncf_item_part_kernel).
-// Layers 2 and 3 are [pairs, 64] x [64, 32] x [32, 16] products done as register-tiled SIMT GEMMs:
-// a warp owns 32 pairs; h1 of its pairs sits in shared memory (broadcast float4 reads, 1 LDS per 4
-// FMAs), lane j keeps column j of W1 (64 registers) and 32 accumulators, then lanes (j, half) keep a
-// column of W2 and do 16 pairs each; the GMF dot is added and the 16 outputs summed by shuffles
-// (NeuMF.py:85 reduce_sum(concat(mf, mlp))).  fp32 FMA throughout: same values as the generic
-// kernel up to the association of the first layer's sum.
+// so the 64x64 layer costs 64 adds per (user, item) pair once B is tabulated (ncf_item_part_kernel, stored
+// TRANSPOSED [64][ldb] so that an item tile is 64 contiguous runs).  Layers 2 and 3 are
+// [pairs, 64] x [64, 32] x [32, 16] products done as register-blocked SIMT GEMMs by a 256-thread CTA on
+// tiles of 128 items:
+//   work unit = (group of 4 users, item tile); the tile of B^T is staged in shared memory ONCE per unit and
+//   reused by the 4 users;
+//   layer 2: thread (ti, tj) owns a 4-item x 4-column block: per k one float4 of h1^T (conflict-free) and one
+//   float4 of W1 (warp-uniform -> broadcast) feed 16 FMAs (the earlier warp-per-32-pairs kernel fed 4 FMAs per
+//   shared-memory load and sat on the LDS pipe at 1/6 of the fp32 peak);
+//   layer 3: thread (item, column half): 8 FMAs per 3 loads; relu, the 16 outputs and the GMF dot are summed
+//   (NeuMF.py:85 reduce_sum(concat(mf, mlp))).
+// fp32 FMA throughout: same values as the generic kernel up to the association of the sums.
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-ncf_item_part_kernel(const float* __restrict__ mlp_item, const float* __restrict__ dense, int num_items,
-                     float* __restrict__ B) {
-    // B[i][j] = sum_k mlp_item[i][k] * W0[32 + k][j];  thread = (item, j) with j fastest
+ncf_item_part_kernel(const float* __restrict__ mlp_item, const float* __restrict__ dense, int num_items, int ldb,
+                     float* __restrict__ Bt) {
+    // Bt[j][i] = sum_k mlp_item[i][k] * W0[32 + k][j];  thread = (j, item) with the item fastest
     __shared__ float sW[32 * 64];
     for (int e = threadIdx.x; e < 32 * 64; e += blockDim.x) sW[e] = dense[32 * 64 + e];
     __syncthreads();
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)num_items * 64; t += (int64_t)gridDim.x * blockDim.x) {
-        const int i = (int)(t >> 6), j = (int)(t & 63);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)ldb * 64; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t / ldb), i = (int)(t - (int64_t)j * ldb);
         float acc = 0.0f;
+        if (i < num_items) {
 #pragma unroll 8
-        for (int k = 0; k < 32; ++k) acc = fmaf(__ldg(mlp_item + (size_t)i * 32 + k), sW[k * 64 + j], acc);
-        B[t] = acc;
+            for (int k = 0; k < 32; ++k) acc = fmaf(__ldg(mlp_item + (size_t)i * 32 + k), sW[k * 64 + j], acc);
+        }
+        Bt[t] = acc;
     }
 }
 
-constexpr int kSfWarps = 8;
-constexpr int kSfH1Stride = 68;   // floats per pair row of h1 (64 + 4: float4 rows, conflict-free broadcast)
-constexpr int kSfH2Stride = 36;
+constexpr int kTileItems = 128, kTileUsers = 4;
+constexpr int kTS = kTileItems + 4;       // row stride (floats) of the [k][item] tiles: rows stay 16-byte aligned
 
-__global__ void __launch_bounds__(kSfWarps * 32)
-ncf_scores_fast_kernel(const float* __restrict__ mf_user, const float* __restrict__ mf_item, int mf_dim,
+__global__ void __launch_bounds__(256, 2)
+ncf_scores_tile_kernel(const float* __restrict__ mf_user, const float* __restrict__ mf_item, int mf_dim,
                        const float* __restrict__ mlp_user, const float* __restrict__ dense,
-                       const float* __restrict__ B, const int32_t* __restrict__ users, int num_items,
-                       float* __restrict__ scores) {
+                       const float* __restrict__ Bt, int ldb, const int32_t* __restrict__ users, int n_users,
+                       int num_items, float* __restrict__ scores) {
     extern __shared__ __align__(16) float sm[];
     constexpr int W0o = 0, B0o = 64 * 64, W1o = B0o + 64, B1o = W1o + 64 * 32, W2o = B1o + 32, B2o = W2o + 32 * 16;
-    float* sA = sm;                                   // [64]  A_u
-    float* sMf = sA + 64;                             // [mf_dim] GMF user row
-    float* sH1 = sMf + ((mf_dim + 3) & ~3);           // per warp [32][68]
-    float* sH2 = sH1 + kSfWarps * 32 * kSfH1Stride;   // per warp [32][36]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int u = users[blockIdx.x];
-    // A_u = mu . W0[:32] + b0
-    if (threadIdx.x < 64) {
-        float acc = __ldg(dense + B0o + threadIdx.x);
-        for (int k = 0; k < 32; ++k) acc = fmaf(__ldg(mlp_user + (size_t)u * 32 + k), __ldg(dense + W0o + k * 64 + threadIdx.x), acc);
-        sA[threadIdx.x] = acc;
-    }
-    for (int k = threadIdx.x; k < mf_dim; k += blockDim.x) sMf[k] = mf_user[(size_t)u * mf_dim + k];
-    // lane j: column j of W1 (layer 2) and, for layer 3, column (lane & 15) of W2
-    float w1[64], w2[32];
-#pragma unroll
-    for (int k = 0; k < 64; ++k) w1[k] = __ldg(dense + W1o + k * 32 + lane);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) w2[k] = __ldg(dense + W2o + k * 16 + (lane & 15));
-    const float b1 = __ldg(dense + B1o + lane), b2 = __ldg(dense + B2o + (lane & 15));
-    __syncthreads();
-    float* h1 = sH1 + warp * 32 * kSfH1Stride;
-    float* h2 = sH2 + warp * 32 * kSfH2Stride;
-    const int tiles = (num_items + 31) >> 5;
-    for (int tile = blockIdx.y * kSfWarps + warp; tile < tiles; tile += gridDim.y * kSfWarps) {
-        const int i0 = tile * 32;
-        // h1[p][k] = relu(A_u[k] + B[i0 + p][k]): lanes sweep k (coalesced rows of B)
-        for (int p = 0; p < 32; ++p) {
-            const int it = i0 + p;
-            const bool ok = it < num_items;
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int k = lane + 32 * t;
-                h1[p * kSfH1Stride + k] = ok ? fmaxf(sA[k] + __ldg(B + (size_t)it * 64 + k), 0.0f) : 0.0f;
-            }
+    float* sW1 = sm;                                  // [64][32]
+    float* sW2 = sW1 + 64 * 32;                       // [32][16]
+    float* sb1 = sW2 + 32 * 16;                       // [32]
+    float* sb2 = sb1 + 32;                            // [16]
+    float* sA = sb2 + 16;                             // [4][64]   A_u of the unit's users
+    float* sBt = sA + kTileUsers * 64;                // [64][kTS] B^T tile
+    float* h1t = sBt + 64 * kTS;                      // [64][kTS] relu(A_u + B_i), transposed
+    float* h2t = h1t + 64 * kTS;                      // [32][kTS]
+    float* part = h2t + 32 * kTS;                     // [2][128]
+    float* sMfU = part + 2 * kTileItems;              // [4][mf_dim]
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 64 * 32; e += 256) sW1[e] = __ldg(dense + W1o + e);
+    for (int e = tid; e < 32 * 16; e += 256) sW2[e] = __ldg(dense + W2o + e);
+    if (tid < 32) sb1[tid] = __ldg(dense + B1o + tid);
+    if (tid < 16) sb2[tid] = __ldg(dense + B2o + tid);
+    const int n_tiles = (num_items + kTileItems - 1) / kTileItems;
+    const int n_groups = (n_users + kTileUsers - 1) / kTileUsers;
+    const int ti = tid & 31, tj = tid >> 5;           // layer 2: items 4ti.., columns 4tj..
+    const int it3 = tid & 127, jh = tid >> 7;         // layer 3: item, column half
+    for (int unit = blockIdx.x; unit < n_groups * n_tiles; unit += gridDim.x) {
+        const int ug = unit / n_tiles, tile = unit - ug * n_tiles;
+        const int i0 = tile * kTileItems, u0 = ug * kTileUsers;
+        __syncthreads();                              // the previous unit's last reads of sMfU, sBt, sA
+        // ---- stage the unit: B^T tile, GMF item rows, A_u and GMF rows of the 4 users
+        for (int e = tid; e < 64 * (kTileItems / 4); e += 256) {
+            const int k = e / (kTileItems / 4), c4 = (e % (kTileItems / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i0 + c4 < ldb) v = __ldg(reinterpret_cast<const float4*>(Bt + (size_t)k * ldb + i0 + c4));   // ldb % 4 == 0, zero padded
+            *reinterpret_cast<float4*>(sBt + k * kTS + c4) = v;
         }
-        // GMF part of pair p = lane
-        float mf = 0.0f;
         {
-            const int it = i0 + lane;
-            if (it < num_items)
-                for (int k = 0; k < mf_dim; ++k) mf = fmaf(sMf[k], __ldg(mf_item + (size_t)it * mf_dim + k), mf);
+            const int uu = tid >> 6, k = tid & 63;
+            const bool live = u0 + uu < n_users;
+            const int u = live ? __ldg(users + u0 + uu) : 0;
+            float acc = __ldg(dense + B0o + k);
+#pragma unroll 8
+            for (int m = 0; m < 32; ++m) acc = fmaf(__ldg(mlp_user + (size_t)u * 32 + m), __ldg(dense + W0o + m * 64 + k), acc);
+            sA[uu * 64 + k] = acc;
+            for (int m = k; m < mf_dim; m += 64) sMfU[uu * mf_dim + m] = live ? __ldg(mf_user + (size_t)u * mf_dim + m) : 0.0f;
         }
-        __syncwarp();
-        // layer 2: acc[p] = sum_k h1[p][k] * W1[k][lane]
-        float acc[32];
+        __syncthreads();
+        for (int uu = 0; uu < kTileUsers && u0 + uu < n_users; ++uu) {
+            // h1^T = relu(A_u + B^T)
+            for (int e = tid; e < 64 * (kTileItems / 4); e += 256) {
+                const int k = e / (kTileItems / 4), c4 = (e % (kTileItems / 4)) * 4;
+                const float a = sA[uu * 64 + k];
+                float4 v = *reinterpret_cast<const float4*>(sBt + k * kTS + c4);
+                v.x = fmaxf(v.x + a, 0.f); v.y = fmaxf(v.y + a, 0.f); v.z = fmaxf(v.z + a, 0.f); v.w = fmaxf(v.w + a, 0.f);
+                *reinterpret_cast<float4*>(h1t + k * kTS + c4) = v;
+            }
+            __syncthreads();
+            // layer 2: acc[i][c] = sum_k h1[4ti + i][k] * W1[k][4tj + c]
+            float acc[4][4];
 #pragma unroll
-        for (int p = 0; p < 32; ++p) acc[p] = 0.0f;
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int k4 = 0; k4 < 16; ++k4) {
+                for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+#pragma unroll 8
+            for (int k = 0; k < 64; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(h1t + k * kTS + 4 * ti);
+                const float4 w = *reinterpret_cast<const float4*>(sW1 + k * 32 + 4 * tj);
+                const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-            for (int p = 0; p < 32; ++p) {
-                const float4 h = *reinterpret_cast<const float4*>(h1 + p * kSfH1Stride + k4 * 4);
-                acc[p] = fmaf(h.x, w1[k4 * 4 + 0], acc[p]);
-                acc[p] = fmaf(h.y, w1[k4 * 4 + 1], acc[p]);
-                acc[p] = fmaf(h.z, w1[k4 * 4 + 2], acc[p]);
-                acc[p] = fmaf(h.w, w1[k4 * 4 + 3], acc[p]);
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(av[i], wv[c], acc[i][c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float b = sb1[4 * tj + c];
+                *reinterpret_cast<float4*>(h2t + (4 * tj + c) * kTS + 4 * ti) =
+                    make_float4(fmaxf(acc[0][c] + b, 0.f), fmaxf(acc[1][c] + b, 0.f), fmaxf(acc[2][c] + b, 0.f), fmaxf(acc[3][c] + b, 0.f));
+            }
+            __syncthreads();
+            // layer 3 + relu + sum over this thread's 8 columns
+            float o[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c] = sb2[8 * jh + c];
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const float a = h2t[k * kTS + it3];
+                const float4 w0 = *reinterpret_cast<const float4*>(sW2 + k * 16 + 8 * jh);
+                const float4 w1 = *reinterpret_cast<const float4*>(sW2 + k * 16 + 8 * jh + 4);
+                o[0] = fmaf(a, w0.x, o[0]); o[1] = fmaf(a, w0.y, o[1]); o[2] = fmaf(a, w0.z, o[2]); o[3] = fmaf(a, w0.w, o[3]);
+                o[4] = fmaf(a, w1.x, o[4]); o[5] = fmaf(a, w1.y, o[5]); o[6] = fmaf(a, w1.z, o[6]); o[7] = fmaf(a, w1.w, o[7]);
+            }
+            float sacc = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sacc += fmaxf(o[c], 0.0f);
+            part[jh * kTileItems + it3] = sacc;
+            __syncthreads();
+            if (tid < kTileItems && i0 + tid < num_items) {
+                float mf = 0.0f;                              // GMF dot: the item row is one or two L1-resident lines
+                const float* q = mf_item + (size_t)(i0 + tid) * mf_dim;
+#pragma unroll 4
+                for (int k = 0; k < mf_dim; ++k) mf = fmaf(sMfU[uu * mf_dim + k], __ldg(q + k), mf);
+                scores[(size_t)(u0 + uu) * num_items + i0 + tid] = mf + part[tid] + part[kTileItems + tid];
             }
         }
-#pragma unroll
-        for (int p = 0; p < 32; ++p) h2[p * kSfH2Stride + lane] = fmaxf(acc[p] + b1, 0.0f);
-        __syncwarp();
-        // layer 3: lane (j = lane & 15, half = lane >> 4) does pairs p = half, half + 2, ...
-        const int half = lane >> 4;
-        float out[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int p = 2 * q + half;
-            float a = 0.0f;
-#pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4) {
-                const float4 h = *reinterpret_cast<const float4*>(h2 + p * kSfH2Stride + k4 * 4);
-                a = fmaf(h.x, w2[k4 * 4 + 0], a); a = fmaf(h.y, w2[k4 * 4 + 1], a);
-                a = fmaf(h.z, w2[k4 * 4 + 2], a); a = fmaf(h.w, w2[k4 * 4 + 3], a);
-            }
-            a = fmaxf(a + b2, 0.0f);
-            // sum over the 16 outputs (lanes of this half)
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(kFull, a, o);
-            out[q] = a;
-        }
-        // pair p = lane: its MLP sum sits in out[lane >> 1] of the lanes of half (lane & 1)
-        float mine = 0.0f;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const float v = __shfl_sync(kFull, out[q], (lane & 1) * 16);   // any lane of that half holds the sum
-            mine = ((lane >> 1) == q) ? v : mine;
-        }
-        if (i0 + lane < num_items) scores[(size_t)blockIdx.x * num_items + i0 + lane] = mf + mine;
-        __syncwarp();
     }
 }
 
@@ -677,9 +692,10 @@ extern "C" int nrc_ncf_scores(const nrc_ncf_shape* shape, const float* mf_user, 
     NcfPtrs P{mf_user, mf_item, mlp_user, mlp_item, dense, nullptr, nullptr, nullptr, nullptr,
               nullptr, nullptr, nullptr};
     const bool fast = S.n_layers == 3 && S.mlp_dim == 32 && S.out_dim[0] == 64 && S.out_dim[1] == 32 && S.out_dim[2] == 16 &&
-                      S.mf_dim <= 256 && !getenv("NRC_NCF_SCORES_GENERIC");
+                      S.mf_dim <= 64 && !getenv("NRC_NCF_SCORES_GENERIC");
     if (fast) {
-        const size_t need = (size_t)num_items * 64;
+        const int ldb = (num_items + 3) & ~3;
+        const size_t need = (size_t)ldb * 64;
         if (need > g_item_part_floats) {
             if (g_item_part) NRC_CUDA_CHECK(cudaFree(g_item_part));
             g_item_part = nullptr; g_item_part_floats = 0;
@@ -687,22 +703,22 @@ extern "C" int nrc_ncf_scores(const nrc_ncf_shape* shape, const float* mf_user, 
             g_item_part_floats = need;
         }
         cudaStream_t st = as_stream(stream);
-        int64_t pb = ((int64_t)num_items * 64 + 255) / 256;
+        int64_t pb = ((int64_t)ldb * 64 + 255) / 256;
         if (pb > (int64_t)sm_count() * 8) pb = (int64_t)sm_count() * 8;
-        ncf_item_part_kernel<<<(unsigned)pb, 256, 0, st>>>(mlp_item, dense, num_items, g_item_part);
+        ncf_item_part_kernel<<<(unsigned)pb, 256, 0, st>>>(mlp_item, dense, num_items, ldb, g_item_part);
         NRC_CUDA_CHECK(cudaGetLastError());
-        const size_t fsmem = (64 + ((S.mf_dim + 3) & ~3) + (size_t)kSfWarps * 32 * (kSfH1Stride + kSfH2Stride)) * 4;
+        const size_t fsmem = ((size_t)64 * 32 + 32 * 16 + 32 + 16 + kTileUsers * 64 + 2 * 64 * kTS + 32 * kTS + 2 * kTileItems +
+                              (size_t)kTileUsers * S.mf_dim) * 4;
         static bool fattr = false;
         if (!fattr) {
-            NRC_CUDA_CHECK(cudaFuncSetAttribute(ncf_scores_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            NRC_CUDA_CHECK(cudaFuncSetAttribute(ncf_scores_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
             fattr = true;
         }
-        const int tiles = (num_items + 31) / 32;
-        int gy = (n_users >= sm_count() * 2) ? 1 : (sm_count() * 2 + n_users - 1) / n_users;
-        if (gy > (tiles + kSfWarps - 1) / kSfWarps) gy = (tiles + kSfWarps - 1) / kSfWarps;
-        if (gy < 1) gy = 1;
-        ncf_scores_fast_kernel<<<dim3(n_users, gy), kSfWarps * 32, fsmem, st>>>(mf_user, mf_item, S.mf_dim, mlp_user, dense,
-                                                                                  g_item_part, users, num_items, scores);
+        const int64_t units = (int64_t)((n_users + kTileUsers - 1) / kTileUsers) * ((num_items + kTileItems - 1) / kTileItems);
+        int64_t grid = (int64_t)sm_count() * 2;
+        if (grid > units) grid = units;
+        ncf_scores_tile_kernel<<<(unsigned)grid, 256, fsmem, st>>>(mf_user, mf_item, S.mf_dim, mlp_user, dense, g_item_part, ldb,
+                                                                   users, n_users, num_items, scores);
         NRC_CUDA_CHECK(cudaGetLastError());
         return NRC_OK;
     }

@@ -78,6 +78,22 @@ def test_ncf_scores_vs_oracle():
     assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("mf_dim,nu,ni", [(8, 943, 1682), (32, 130, 257), (64, 9, 128), (0, 37, 500)])
+def test_ncf_scores_tile_kernel_equals_the_generic_kernel(mf_dim, nu, ni, monkeypatch):
+    """The register-blocked predict kernel of the default tower (units of 4 users x 128 items, ragged last
+    group / tile, GMF widths 0..64) against the generic warp-per-pair kernel on the same parameters."""
+    from neurec_b200 import ops
+    P, mlp_dim = make_params(nu, ni, mf_dim, [64, 32, 16], 1, 11 + mf_dim, scale=0.3)
+    shape = ops.NcfShape.make(nu, ni, mf_dim, [64, 32, 16], 1)
+    dP = {k: (dev(v) if v is not None else None) for k, v in P.items()}
+    users = dev(np.random.RandomState(3).permutation(nu).astype(np.int32))
+    fast = ops.ncf_scores(shape, dP, users).cpu().numpy()
+    monkeypatch.setenv("NRC_NCF_SCORES_GENERIC", "1")
+    slow = ops.ncf_scores(shape, dP, users).cpu().numpy()
+    assert np.allclose(fast, slow, rtol=1e-5, atol=1e-6)
+    assert np.abs(fast).max() > 1e-3
+
+
 @pytest.mark.parametrize("pairwise,loss,opt", [(False, "cross_entropy", "adam"), (True, "bpr", "adam"),
                                                (False, "square", "rmsprop")])
 def test_ncf_train_epoch_vs_oracle(ml100k, pairwise, loss, opt):
