@@ -735,8 +735,8 @@ class ShardedCfg:
 
 def synth_shard_csr(cfg, rank, world, device="cuda"):
     """This rank's train CSR: its own users (local ids), 1..max_pos positives each, items
-    Zipf(1.05) over the GLOBAL catalogue with item id = popularity rank (what the loader's
-    relabel_by_degree produces: ids in descending train degree), rows sorted and duplicate-free.
+    Zipf(1.05) over the GLOBAL catalogue, ids as the loader's relabel_by_degree leaves them (the
+    n_hot most popular items first, the rest in arbitrary order), rows sorted and duplicate-free.
     Built on the device (setup, untimed)."""
     import torch
     g = torch.Generator(device=device).manual_seed(3 + rank)
@@ -745,8 +745,12 @@ def synth_shard_csr(cfg, rank, world, device="cuda"):
     x = torch.rand((nu, cfg.max_pos), device=device, generator=g, dtype=torch.float64)
     a = cfg.zipf_a                         # inverse CDF of the continuous Zipf(a) truncated to [1, ni]
     r = (((ni ** (1 - a) - 1) * x + 1) ** (1 / (1 - a))).clamp(1, ni).long() - 1
-    items = r
-    del x
+    # the loader's relabelling (peer.relabel_by_degree): the n_hot most popular items get ids [0, n_hot) in rank
+    # order, the order of the rest is arbitrary -- here a multiplicative hash, so that warm rows are spread over the
+    # whole table (and both dies' memory) instead of sitting next to each other
+    nh = n_hot_of(cfg)
+    items = torch.where(r < nh, r, nh + ((r - nh) * 2654435761) % (ni - nh))
+    del x, r
     big = torch.iinfo(torch.int64).max
     items[torch.arange(cfg.max_pos, device=device)[None, :] >= deg[:, None]] = big
     items = items.sort(1).values
@@ -770,7 +774,7 @@ def n_hot_of(cfg):
 def sharded_describe(cfg, world):
     return ("BPRMF, learner=gd, tables row-sharded over %d GPU(s): %d users x %d items x d=%d per GPU (%.1f GB per GPU; "
             "%d x %d rows in total), 2^20 triplets per GPU and step sampled INSIDE the step kernel from the rank's train "
-            "CSR (1..%d positives per user, items Zipf(%.2f) over the global catalogue with ids in descending popularity "
+            "CSR (1..%d positives per user, items Zipf(%.2f) over the global catalogue with the most popular ids first "
             "(the loader's relabelling), uniform negatives rejected against the user's row, keyed-bijection shuffle); the "
             "%d most popular item rows are replicated on every GPU, their deltas summed by one all-reduce per step "
             "-- BASELINE configs[4], weak scaling" % (

@@ -61,6 +61,8 @@ struct SpmmArgs {
     float* Y;            // optional output
     float* sum;          // optional running layer sum: sum = (sum + y) [/ div]
     float div;           // 0 = no division; LightGCN.py:147 reduce_mean divides by n_layers+1
+    const float* sum_in; // optional: the running sum is READ from here instead of `sum` (first layer: sum = E0 + y
+                         // without a copy of E0 into the accumulator first)
 };
 
 // V = columns per lane (dim == 32*V).  V == 0: generic dim (lane strides over columns).
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs A) {
             if (A.Y) vstore(A.Y + o, a);
             if (A.sum) {
                 float s[V];
-                vload_rw(s, A.sum + o);
+                vload_rw(s, const_cast<float*>(A.sum_in ? A.sum_in : A.sum) + o);
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     s[j] = __fadd_rn(s[j], a[j]);
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmArgs A) {
                     if (A.bias) y = __fadd_rn(A.bias[o], y);
                     if (A.Y) A.Y[o] = y;
                     if (A.sum) {
-                        float s = __fadd_rn(A.sum[o], y);
+                        float s = __fadd_rn((A.sum_in ? A.sum_in : A.sum)[o], y);
                         if (A.div != 0.0f) s = __fdiv_rn(s, A.div);
                         A.sum[o] = s;
                     }
@@ -172,8 +174,7 @@ constexpr int kLongRow = 192;
 
 template <int G, int UNMAX>   // lanes per gathered row: dim == 4 * G, G in {8, 16, 32}; load instructions in flight
 __device__ __forceinline__ void spmm_accumulate(const SpmmArgs& A, int64_t beg, int64_t end, int64_t seg_stride,
-                                                int lane, float4& acc, bool have_first = false, int first_c = 0,
-                                                float first_v = 0.0f) {
+                                                int lane, float4& acc) {
     constexpr int NPI = 32 / G;            // non-zeros per load instruction
     constexpr int STEPS = 32 / NPI;        // load instructions per 32-nnz segment
     constexpr int UN = (STEPS < UNMAX) ? STEPS : UNMAX;
@@ -181,10 +182,8 @@ __device__ __forceinline__ void spmm_accumulate(const SpmmArgs& A, int64_t beg, 
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
     for (int64_t p = beg; p < end; p += seg_stride) {
         const int cnt = (int)((end - p < 32) ? (end - p) : 32);
-        // the first segment's (column, value) pairs may have been fetched one row ahead by the caller
-        const bool pre = have_first && p == beg;
-        const int my_c = pre ? first_c : ((lane < cnt) ? __ldg(A.indices + p + lane) : 0);
-        const float my_v = pre ? first_v : ((lane < cnt) ? __ldg(A.values + p + lane) : 0.0f);   // padding: 0 * row 0
+        const int my_c = (lane < cnt) ? __ldg(A.indices + p + lane) : 0;
+        const float my_v = (lane < cnt) ? __ldg(A.values + p + lane) : 0.0f;   // padding: 0 * row 0
 #pragma unroll 1
         for (int j0 = 0; j0 * NPI < cnt; j0 += UN) {
             float4 x[UN];
@@ -194,13 +193,11 @@ __device__ __forceinline__ void spmm_accumulate(const SpmmArgs& A, int64_t beg, 
                 const int src = (j0 + j) * NPI + grp;
                 const int c = __shfl_sync(kFull, my_c, src & 31);
                 v[j] = __shfl_sync(kFull, my_v, src & 31);
-                // padding slots of the last batch issue no load at all (predicated off)
-                x[j] = (src < cnt) ? __ldg(reinterpret_cast<const float4*>(A.X + (size_t)c * A.dim) + sub)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                x[j] = __ldg(reinterpret_cast<const float4*>(A.X + (size_t)c * A.dim) + sub);
             }
 #pragma unroll
             for (int j = 0; j < UN; ++j) {
-                if ((j0 + j) * NPI + grp < cnt) {          // padding slots: never accumulated
+                if ((j0 + j) * NPI + grp < cnt) {          // padding slots gathered row 0: never accumulate them
                     float4& a = (j & 1) ? a1 : a0;
                     a.x = fmaf(v[j], x[j].x, a.x); a.y = fmaf(v[j], x[j].y, a.y);
                     a.z = fmaf(v[j], x[j].z, a.z); a.w = fmaf(v[j], x[j].w, a.w);
@@ -225,7 +222,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmArgs& A, int r, int sub,
     }
     if (A.Y) *reinterpret_cast<float4*>(A.Y + o) = a;
     if (A.sum) {
-        float4 s = *reinterpret_cast<const float4*>(A.sum + o);
+        float4 s = *reinterpret_cast<const float4*>((A.sum_in ? A.sum_in : A.sum) + o);
         s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
         if (A.div != 0.0f) { s.x = __fdiv_rn(s.x, A.div); s.y = __fdiv_rn(s.y, A.div); s.z = __fdiv_rn(s.z, A.div); s.w = __fdiv_rn(s.w, A.div); }
         *reinterpret_cast<float4*>(A.sum + o) = s;
@@ -253,26 +250,16 @@ __global__ void __launch_bounds__(256, UNMAX == 4 ? 4 : 3) spmm_csr_fast_kernel(
             lng = false;        // decided per unit with a CTA vote below
         }
     };
-    // the row's first 32 (column, value) pairs: issued one row ahead, consumed by spmm_accumulate
-    auto first_seg = [&](int64_t b, int64_t e, int& c, float& v) {
-        const bool in = b + lane < e;
-        c = in ? __ldg(A.indices + b + lane) : 0;
-        v = in ? __ldg(A.values + b + lane) : 0.0f;
-    };
-    int r, rn, rnn; int64_t beg, end, begn, endn, begnn, endnn; bool lng, lngn, lngnn;
-    int fc, fcn; float fv, fvn;
+    int r, rn; int64_t beg, end, begn, endn; bool lng, lngn;
     fetch(blockIdx.x, r, beg, end, lng);
-    fetch(blockIdx.x + gridDim.x, rn, begn, endn, lngn);
-    first_seg(beg, end, fc, fv);
     for (int w = blockIdx.x; w < units; w += gridDim.x) {
-        fetch(w + 2 * gridDim.x, rnn, begnn, endnn, lngnn);      // two units ahead: row id + extent
-        first_seg(begn, endn, fcn, fvn);                          // one unit ahead: its first segment
+        fetch(w + gridDim.x, rn, begn, endn, lngn);
         const bool live = w * 8 + warp < A.n_rows;
         const bool any_long = A.row_order ? lng : (bool)__syncthreads_or(live && (end - beg) > kLongRow);
         if (!any_long) {
             if (live) {
                 float4 acc;
-                spmm_accumulate<G, UNMAX>(A, beg, end, 32, lane, acc, true, fc, fv);
+                spmm_accumulate<G, UNMAX>(A, beg, end, 32, lane, acc);
                 if (lane < G) spmm_epilogue<G>(A, r, lane, acc);
             }
         } else {
@@ -298,8 +285,7 @@ __global__ void __launch_bounds__(256, UNMAX == 4 ? 4 : 3) spmm_csr_fast_kernel(
                 __syncthreads();
             }
         }
-        r = rn; beg = begn; end = endn; lng = lngn; fc = fcn; fv = fvn;
-        rn = rnn; begn = begnn; endn = endnn; lngn = lngnn;
+        r = rn; beg = begn; end = endn; lng = lngn;
     }
 }
 
@@ -316,20 +302,6 @@ static int spmm_launch(const SpmmArgs& A, cudaStream_t st) {
         static int un = -1;
         // 8 loads in flight measured faster than 4 on gowalla (60.9 vs 70.3 us)
         if (un < 0) { const char* e = getenv("NRC_SPMM_UN"); un = (e && atoi(e) == 4) ? 4 : 8; }
-        {   // one wave: exactly the CTAs that are resident at once (a CTA strides over its units, prefetching ahead;
-            // the old 8-per-SM grid ran 2.67 waves with a third of the machine idle in the last one)
-            static int occ8 = 0, occ4 = 0;
-            if (!occ8) {
-                NRC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ8, spmm_csr_fast_kernel<16, 8>, threads, 0));
-                NRC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ4, spmm_csr_fast_kernel<16, 4>, threads, 0));
-                if (occ8 < 1) occ8 = 1;
-                if (occ4 < 1) occ4 = 1;
-            }
-            static int waves = -1;
-            if (waves < 0) { const char* e = getenv("NRC_SPMM_WAVES"); waves = e ? atoi(e) : 1; }
-            const int64_t resident = (int64_t)sm_count() * (un == 8 ? occ8 : occ4) * (waves > 0 ? waves : 1);
-            if (waves > 0 && blocks > resident) blocks = resident;
-        }
         if (un == 8) {
             if (A.dim == 32) spmm_csr_fast_kernel<8, 8><<<(unsigned)blocks, threads, 0, st>>>(A);
             else if (A.dim == 64) spmm_csr_fast_kernel<16, 8><<<(unsigned)blocks, threads, 0, st>>>(A);
@@ -424,7 +396,7 @@ extern "C" int nrc_lightgcn_propagate(const int64_t* indptr, const int32_t* indi
     NRC_REQUIRE(n_layers >= 0, NRC_E_VALUE, "n_layers must be >= 0");
     cudaStream_t st = as_stream(stream);
     const size_t bytes = (size_t)n_nodes * dim * sizeof(float);
-    NRC_CUDA_CHECK(cudaMemcpyAsync(e_final, e0, bytes, cudaMemcpyDeviceToDevice, st));
+    if (n_layers == 0) NRC_CUDA_CHECK(cudaMemcpyAsync(e_final, e0, bytes, cudaMemcpyDeviceToDevice, st));
     const float* x = e0;
     float* bufs[2] = {work_a, work_b};
     for (int k = 0; k < n_layers; ++k) {
@@ -432,7 +404,7 @@ extern "C" int nrc_lightgcn_propagate(const int64_t* indptr, const int32_t* indi
         const bool last = (k == n_layers - 1);
         // LightGCN.py:139-147: running sum of the stacked layers, mean at the end
         SpmmArgs A{indptr, indices, values, row_order, n_nodes, dim, x, nullptr, last ? nullptr : y,
-                   e_final, last ? (float)(n_layers + 1) : 0.0f};
+                   e_final, last ? (float)(n_layers + 1) : 0.0f, k == 0 ? e0 : nullptr};   // layer 0: e_final = E0 + y
         int rc = spmm_launch(A, st);
         if (rc) return rc;
         x = y;

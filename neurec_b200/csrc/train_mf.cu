@@ -442,13 +442,14 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
 //       (cp.async.bulk, one row each) into the slot, completion counted on the slot's mbarrier; when the rows
 //       have landed the warp computes the triplet from shared memory, writes the three delta rows IN PLACE and
 //       hands them to the copy engine as bulk reduce-adds (cp.reduce.async.bulk .add.f32 -- local and peer
-//       rows alike).  A slot is refilled as soon as the engine has read its deltas (wait_group.read), i.e. one
-//       slot later in the warp's round-robin.
+//       rows alike).  A slot is refilled once the engine has read its deltas (wait_group.read), kPipeLag
+//       triplets later in the warp's round-robin, so the warp never waits for a reduce it has just issued.
 // 128 slots x 3 rows in flight per SM (192 KB at d = 128) whatever the register pressure.  One CTA per SM.
 // CTA-local sequence number n <-> ring slot n % 128, round n / 128, position first + blockIdx*128 + slot + round*stride.
 // ----------------------------------------------------------------------------------------
 constexpr int kPipeSlots = 128, kPipeSamplerWarps = 16, kPipeConsWarps = 8;
 constexpr int kPipeSamplers = kPipeSamplerWarps * 32;          // = id-queue entries (one per sampler thread)
+constexpr int kPipeLag = 6;                                    // a slot is refilled this many triplets after its deltas were handed over (< 16 - 1)
 constexpr int kPipeThreads = (kPipeSamplerWarps + kPipeConsWarps) * 32;
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -537,7 +538,9 @@ mf_bpr_sgd_pipe_kernel(float* __restrict__ U_local, const RowShards V, const Epo
             const int32_t n = cw + k * kPipeConsWarps;
             if (n < n_end && pos_of(n) < count) load_slot(n);
         }
-        int32_t prev_n = -1;                                        // sequence number whose deltas were handed over last
+        int32_t hist[kPipeLag];                                     // the last kPipeLag sequence numbers handed to the engine
+#pragma unroll
+        for (int h = 0; h < kPipeLag; ++h) hist[h] = -1;
         for (int32_t r = 0; r < (int32_t)rounds; ++r) {
             for (int k = 0; k < kMine; ++k) {
                 const int s = cw + k * kPipeConsWarps;
@@ -580,15 +583,18 @@ mf_bpr_sgd_pipe_kernel(float* __restrict__ U_local, const RowShards V, const Epo
                     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                                  ::"l"(p2), "r"(src + 2 * kRowBytes), "r"(kRowBytes) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    // the deltas handed over one slot ago have left shared memory: that slot can be refilled
-                    if (prev_n >= 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    // the deltas handed over kPipeLag slots ago have left shared memory by now (waiting for the
+                    // group just committed would stall the warp for a full engine round trip per triplet)
+                    if (hist[kPipeLag - 1] >= 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPipeLag) : "memory");
                 }
                 __syncwarp();
-                if (prev_n >= 0) {
-                    const int32_t nn = prev_n + kPipeSlots;             // same slot, next round
+                if (hist[kPipeLag - 1] >= 0) {
+                    const int32_t nn = hist[kPipeLag - 1] + kPipeSlots;   // same slot, next round
                     if (nn < n_end && pos_of(nn) < count) load_slot(nn);
                 }
-                prev_n = n;
+#pragma unroll
+                for (int h = kPipeLag - 1; h > 0; --h) hist[h] = hist[h - 1];
+                hist[0] = n;
             }
         }
         if (lane == 0) {

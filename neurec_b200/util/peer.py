@@ -171,16 +171,24 @@ def single(local):
     return ShardSet(local, [local.data_ptr()], 0, "local", None)
 
 
-def relabel_by_degree(indices, num_items):
-    """Load-time item relabelling for the replicated head: new id = rank of the item by descending train degree
-    (ties by old id).  `indices` are the train CSR's item ids; returns (new_id_of_old int32 [num_items], degree of
-    every NEW id int64 [num_items]).  The reference remaps raw ids to dense ones at load time as well
-    (data/dataset.py:88-110); this only fixes the order of that remap."""
+def relabel_by_degree(indices, num_items, n_hot=None):
+    """Load-time item relabelling for the replicated head: the `n_hot` items of highest train degree get the new
+    ids [0, n_hot) in descending degree (ties by old id); the others keep their relative order behind them (their
+    order is irrelevant to the head -- and a popularity-sorted tail would put all warm rows next to each other in
+    memory).  n_hot=None sorts the whole catalogue.  `indices` are the train CSR's item ids; returns
+    (new_id_of_old int32 [num_items], degree of every NEW id int64 [num_items]).  The reference remaps raw ids to
+    dense ones at load time as well (data/dataset.py:88-110); this only fixes the order of that remap."""
     indices = np.asarray(indices)
-    deg = np.bincount(indices, minlength=int(num_items)).astype(np.int64)
+    num_items = int(num_items)
+    deg = np.bincount(indices, minlength=num_items).astype(np.int64)
     order = np.argsort(-deg, kind="stable")
-    new_of_old = np.empty(int(num_items), np.int32)
-    new_of_old[order] = np.arange(int(num_items), dtype=np.int32)
+    if n_hot is not None and n_hot < num_items:
+        head = order[:int(n_hot)]
+        rest = np.ones(num_items, bool)
+        rest[head] = False
+        order = np.concatenate([head, np.nonzero(rest)[0]])
+    new_of_old = np.empty(num_items, np.int32)
+    new_of_old[order] = np.arange(num_items, dtype=np.int32)
     return new_of_old, deg[order]
 
 

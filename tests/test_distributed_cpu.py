@@ -125,3 +125,7 @@ def test_relabel_by_degree_orders_items_by_popularity():
     assert sorted(new_of_old.tolist()) == list(range(10))
     assert deg.tolist() == [3, 2, 2, 1, 1, 0, 0, 0, 0, 0]
     assert np.all(np.diff(np.bincount(new_of_old[idx], minlength=10)) <= 0)
+    head, deg2 = peer.relabel_by_degree(idx, 10, n_hot=2)           # only the head is sorted, the tail keeps its order
+    assert head[5] == 0 and head[0] == 1
+    assert [int(np.nonzero(head == k)[0][0]) for k in range(2, 10)] == [1, 2, 3, 4, 6, 7, 8, 9]
+    assert deg2[:2].tolist() == [3, 2]
