@@ -461,12 +461,13 @@ ncf_scores_kernel(const NcfDev S, const NcfPtrs P, const int32_t* __restrict__ u
 // [pairs, 64] x [64, 32] x [32, 16] products done as register-blocked SIMT GEMMs by a 256-thread CTA on
 // tiles of 128 items:
 //   work unit = (group of 4 users, item tile); the tile of B^T is staged in shared memory ONCE per unit and
-//   reused by the 4 users;
-//   layer 2: thread (ti, tj) owns a 4-item x 4-column block: per k one float4 of h1^T (conflict-free) and one
-//   float4 of W1 (warp-uniform -> broadcast) feed 16 FMAs (the earlier warp-per-32-pairs kernel fed 4 FMAs per
-//   shared-memory load and sat on the LDS pipe at 1/6 of the fp32 peak);
-//   layer 3: thread (item, column half): 8 FMAs per 3 loads; relu, the 16 outputs and the GMF dot are summed
-//   (NeuMF.py:85 reduce_sum(concat(mf, mlp))).
+//   reused by the 4 users, two at a time (one per 128-thread half of the CTA);
+//   layer 2: thread (ti, tj) owns a 4-item x 8-column block: per k one float4 of h1^T (conflict-free) and two
+//   float4 of W1 (warp-uniform -> broadcast) feed 32 FMAs.  (The first warp-per-32-pairs kernel fed 4 FMAs per
+//   shared-memory load and ran at 1/6 of the fp32 peak; a 4 x 4 block sits exactly on the 128 B/clk
+//   shared-memory limit.)
+//   layer 3: thread = item with all 16 columns: 16 FMAs per 5 loads; relu, the 16 outputs and the GMF dot are
+//   summed (NeuMF.py:85 reduce_sum(concat(mf, mlp))).
 // fp32 FMA throughout: same values as the generic kernel up to the association of the sums.
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -487,26 +488,46 @@ ncf_item_part_kernel(const float* __restrict__ mlp_item, const float* __restrict
     }
 }
 
+// A[r][j] = b0[j] + sum_k mlp_user[users[r]][k] * W0[k][j] for the evaluated users (one thread per entry, j fastest)
+__global__ void __launch_bounds__(256)
+ncf_user_part_kernel(const float* __restrict__ mlp_user, const float* __restrict__ dense, const int32_t* __restrict__ users,
+                     int n_users, float* __restrict__ A) {
+    __shared__ float sW[32 * 64];
+    for (int e = threadIdx.x; e < 32 * 64; e += blockDim.x) sW[e] = dense[e];
+    __syncthreads();
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)n_users * 64; t += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(t >> 6), j = (int)(t & 63);
+        const int u = __ldg(users + r);
+        float acc = __ldg(dense + 64 * 64 + j);
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) acc = fmaf(__ldg(mlp_user + (size_t)u * 32 + k), sW[k * 64 + j], acc);
+        A[t] = acc;
+    }
+}
+
 constexpr int kTileItems = 128, kTileUsers = 4;
 constexpr int kTS = kTileItems + 4;       // row stride (floats) of the [k][item] tiles: rows stay 16-byte aligned
 
-__global__ void __launch_bounds__(256, 2)
+// 256 threads = two halves of 128; a half works on ONE user of the current pair: thread (ti, tj) of a half owns
+// items 4ti..4ti+3 and columns 8tj..8tj+7 of layer 2 (32 accumulators; per k one float4 of h1^T and two
+// warp-uniform float4 of W1 feed 32 FMAs: 6 shared-memory wavefronts per 32 FMA instructions, under the
+// 128 B/clk shared-memory limit that a 4 x 4 block sits on), then item `t` with all 16 columns of layer 3.
+__global__ void __launch_bounds__(256, 1)
 ncf_scores_tile_kernel(const float* __restrict__ mf_user, const float* __restrict__ mf_item, int mf_dim,
-                       const float* __restrict__ mlp_user, const float* __restrict__ dense,
+                       const float* __restrict__ Au, const float* __restrict__ dense,
                        const float* __restrict__ Bt, int ldb, const int32_t* __restrict__ users, int n_users,
                        int num_items, float* __restrict__ scores) {
     extern __shared__ __align__(16) float sm[];
-    constexpr int W0o = 0, B0o = 64 * 64, W1o = B0o + 64, B1o = W1o + 64 * 32, W2o = B1o + 32, B2o = W2o + 32 * 16;
+    constexpr int B0o = 64 * 64, W1o = B0o + 64, B1o = W1o + 64 * 32, W2o = B1o + 32, B2o = W2o + 32 * 16;
     float* sW1 = sm;                                  // [64][32]
     float* sW2 = sW1 + 64 * 32;                       // [32][16]
     float* sb1 = sW2 + 32 * 16;                       // [32]
     float* sb2 = sb1 + 32;                            // [16]
     float* sA = sb2 + 16;                             // [4][64]   A_u of the unit's users
     float* sBt = sA + kTileUsers * 64;                // [64][kTS] B^T tile
-    float* h1t = sBt + 64 * kTS;                      // [64][kTS] relu(A_u + B_i), transposed
-    float* h2t = h1t + 64 * kTS;                      // [32][kTS]
-    float* part = h2t + 32 * kTS;                     // [2][128]
-    float* sMfU = part + 2 * kTileItems;              // [4][mf_dim]
+    float* h1t = sBt + 64 * kTS;                      // [2][64][kTS] relu(A_u + B_i), transposed, per half
+    float* h2t = h1t + 2 * 64 * kTS;                  // [2][32][kTS]
+    float* sMfU = h2t + 2 * 32 * kTS;                 // [4][mf_dim]
     const int tid = threadIdx.x;
     for (int e = tid; e < 64 * 32; e += 256) sW1[e] = __ldg(dense + W1o + e);
     for (int e = tid; e < 32 * 16; e += 256) sW2[e] = __ldg(dense + W2o + e);
@@ -514,13 +535,15 @@ ncf_scores_tile_kernel(const float* __restrict__ mf_user, const float* __restric
     if (tid < 16) sb2[tid] = __ldg(dense + B2o + tid);
     const int n_tiles = (num_items + kTileItems - 1) / kTileItems;
     const int n_groups = (n_users + kTileUsers - 1) / kTileUsers;
-    const int ti = tid & 31, tj = tid >> 5;           // layer 2: items 4ti.., columns 4tj..
-    const int it3 = tid & 127, jh = tid >> 7;         // layer 3: item, column half
+    const int half = tid >> 7, t = tid & 127;
+    const int ti = t & 31, tj = t >> 5;               // layer 2: items 4ti.., columns 8tj..
+    float* h1 = h1t + half * 64 * kTS;
+    float* h2 = h2t + half * 32 * kTS;
     for (int unit = blockIdx.x; unit < n_groups * n_tiles; unit += gridDim.x) {
         const int ug = unit / n_tiles, tile = unit - ug * n_tiles;
         const int i0 = tile * kTileItems, u0 = ug * kTileUsers;
         __syncthreads();                              // the previous unit's last reads of sMfU, sBt, sA
-        // ---- stage the unit: B^T tile, GMF item rows, A_u and GMF rows of the 4 users
+        // ---- stage the unit: B^T tile, A_u and GMF rows of the 4 users
         for (int e = tid; e < 64 * (kTileItems / 4); e += 256) {
             const int k = e / (kTileItems / 4), c4 = (e % (kTileItems / 4)) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -531,74 +554,76 @@ ncf_scores_tile_kernel(const float* __restrict__ mf_user, const float* __restric
             const int uu = tid >> 6, k = tid & 63;
             const bool live = u0 + uu < n_users;
             const int u = live ? __ldg(users + u0 + uu) : 0;
-            float acc = __ldg(dense + B0o + k);
-#pragma unroll 8
-            for (int m = 0; m < 32; ++m) acc = fmaf(__ldg(mlp_user + (size_t)u * 32 + m), __ldg(dense + W0o + m * 64 + k), acc);
-            sA[uu * 64 + k] = acc;
+            sA[uu * 64 + k] = live ? __ldg(Au + (size_t)(u0 + uu) * 64 + k) : 0.0f;
             for (int m = k; m < mf_dim; m += 64) sMfU[uu * mf_dim + m] = live ? __ldg(mf_user + (size_t)u * mf_dim + m) : 0.0f;
         }
         __syncthreads();
-        for (int uu = 0; uu < kTileUsers && u0 + uu < n_users; ++uu) {
-            // h1^T = relu(A_u + B^T)
-            for (int e = tid; e < 64 * (kTileItems / 4); e += 256) {
+        for (int pass = 0; pass < kTileUsers / 2 && u0 + 2 * pass < n_users; ++pass) {
+            const int uu = 2 * pass + half;           // this half's user slot (may be past the end: computed, not stored)
+            // h1^T = relu(A_u + B^T), this half's user
+            for (int e = t; e < 64 * (kTileItems / 4); e += 128) {
                 const int k = e / (kTileItems / 4), c4 = (e % (kTileItems / 4)) * 4;
                 const float a = sA[uu * 64 + k];
                 float4 v = *reinterpret_cast<const float4*>(sBt + k * kTS + c4);
                 v.x = fmaxf(v.x + a, 0.f); v.y = fmaxf(v.y + a, 0.f); v.z = fmaxf(v.z + a, 0.f); v.w = fmaxf(v.w + a, 0.f);
-                *reinterpret_cast<float4*>(h1t + k * kTS + c4) = v;
+                *reinterpret_cast<float4*>(h1 + k * kTS + c4) = v;
             }
             __syncthreads();
-            // layer 2: acc[i][c] = sum_k h1[4ti + i][k] * W1[k][4tj + c]
-            float acc[4][4];
+            // layer 2: acc[i][c] = sum_k h1[4ti + i][k] * W1[k][8tj + c]
+            float acc[4][8];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
-#pragma unroll 8
+                for (int c = 0; c < 8; ++c) acc[i][c] = 0.0f;
+#pragma unroll 4
             for (int k = 0; k < 64; ++k) {
-                const float4 a = *reinterpret_cast<const float4*>(h1t + k * kTS + 4 * ti);
-                const float4 w = *reinterpret_cast<const float4*>(sW1 + k * 32 + 4 * tj);
-                const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+                const float4 a = *reinterpret_cast<const float4*>(h1 + k * kTS + 4 * ti);
+                const float4 w0 = *reinterpret_cast<const float4*>(sW1 + k * 32 + 8 * tj);
+                const float4 w1 = *reinterpret_cast<const float4*>(sW1 + k * 32 + 8 * tj + 4);
+                const float av[4] = {a.x, a.y, a.z, a.w};
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(av[i], wv[c], acc[i][c]);
+                    for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(av[i], wv[c], acc[i][c]);
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float b = sb1[4 * tj + c];
-                *reinterpret_cast<float4*>(h2t + (4 * tj + c) * kTS + 4 * ti) =
+            for (int c = 0; c < 8; ++c) {
+                const float b = sb1[8 * tj + c];
+                *reinterpret_cast<float4*>(h2 + (8 * tj + c) * kTS + 4 * ti) =
                     make_float4(fmaxf(acc[0][c] + b, 0.f), fmaxf(acc[1][c] + b, 0.f), fmaxf(acc[2][c] + b, 0.f), fmaxf(acc[3][c] + b, 0.f));
             }
             __syncthreads();
-            // layer 3 + relu + sum over this thread's 8 columns
-            float o[8];
+            // layer 3 (item t, all 16 columns) + relu + sum + GMF dot
+            float o[16];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) o[c] = sb2[8 * jh + c];
-#pragma unroll 8
+            for (int c = 0; c < 16; ++c) o[c] = sb2[c];
+#pragma unroll 4
             for (int k = 0; k < 32; ++k) {
-                const float a = h2t[k * kTS + it3];
-                const float4 w0 = *reinterpret_cast<const float4*>(sW2 + k * 16 + 8 * jh);
-                const float4 w1 = *reinterpret_cast<const float4*>(sW2 + k * 16 + 8 * jh + 4);
-                o[0] = fmaf(a, w0.x, o[0]); o[1] = fmaf(a, w0.y, o[1]); o[2] = fmaf(a, w0.z, o[2]); o[3] = fmaf(a, w0.w, o[3]);
-                o[4] = fmaf(a, w1.x, o[4]); o[5] = fmaf(a, w1.y, o[5]); o[6] = fmaf(a, w1.z, o[6]); o[7] = fmaf(a, w1.w, o[7]);
+                const float a = h2[k * kTS + t];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 w = *reinterpret_cast<const float4*>(sW2 + k * 16 + 4 * q);
+                    o[4 * q + 0] = fmaf(a, w.x, o[4 * q + 0]); o[4 * q + 1] = fmaf(a, w.y, o[4 * q + 1]);
+                    o[4 * q + 2] = fmaf(a, w.z, o[4 * q + 2]); o[4 * q + 3] = fmaf(a, w.w, o[4 * q + 3]);
+                }
             }
             float sacc = 0.0f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) sacc += fmaxf(o[c], 0.0f);
-            part[jh * kTileItems + it3] = sacc;
-            __syncthreads();
-            if (tid < kTileItems && i0 + tid < num_items) {
+            for (int c = 0; c < 16; ++c) sacc += fmaxf(o[c], 0.0f);
+            if (u0 + uu < n_users && i0 + t < num_items) {
                 float mf = 0.0f;                              // GMF dot: the item row is one or two L1-resident lines
-                const float* q = mf_item + (size_t)(i0 + tid) * mf_dim;
+                const float* q = mf_item + (size_t)(i0 + t) * mf_dim;
 #pragma unroll 4
                 for (int k = 0; k < mf_dim; ++k) mf = fmaf(sMfU[uu * mf_dim + k], __ldg(q + k), mf);
-                scores[(size_t)(u0 + uu) * num_items + i0 + tid] = mf + part[tid] + part[kTileItems + tid];
+                scores[(size_t)(u0 + uu) * num_items + i0 + t] = mf + sacc;
             }
         }
     }
 }
 
+static float* g_user_part = nullptr;
+static size_t g_user_part_floats = 0;
 static float* g_item_part = nullptr;
 static size_t g_item_part_floats = 0;
 
@@ -707,17 +732,28 @@ extern "C" int nrc_ncf_scores(const nrc_ncf_shape* shape, const float* mf_user, 
         if (pb > (int64_t)sm_count() * 8) pb = (int64_t)sm_count() * 8;
         ncf_item_part_kernel<<<(unsigned)pb, 256, 0, st>>>(mlp_item, dense, num_items, ldb, g_item_part);
         NRC_CUDA_CHECK(cudaGetLastError());
-        const size_t fsmem = ((size_t)64 * 32 + 32 * 16 + 32 + 16 + kTileUsers * 64 + 2 * 64 * kTS + 32 * kTS + 2 * kTileItems +
+        const size_t fsmem = ((size_t)64 * 32 + 32 * 16 + 32 + 16 + kTileUsers * 64 + 64 * kTS + 2 * 64 * kTS + 2 * 32 * kTS +
                               (size_t)kTileUsers * S.mf_dim) * 4;
         static bool fattr = false;
         if (!fattr) {
-            NRC_CUDA_CHECK(cudaFuncSetAttribute(ncf_scores_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+            NRC_CUDA_CHECK(cudaFuncSetAttribute(ncf_scores_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
             fattr = true;
         }
         const int64_t units = (int64_t)((n_users + kTileUsers - 1) / kTileUsers) * ((num_items + kTileItems - 1) / kTileItems);
-        int64_t grid = (int64_t)sm_count() * 2;
+        int64_t grid = (int64_t)sm_count();
         if (grid > units) grid = units;
-        ncf_scores_tile_kernel<<<(unsigned)grid, 256, fsmem, st>>>(mf_user, mf_item, S.mf_dim, mlp_user, dense, g_item_part, ldb,
+        const size_t need_u = (size_t)n_users * 64;
+        if (need_u > g_user_part_floats) {
+            if (g_user_part) NRC_CUDA_CHECK(cudaFree(g_user_part));
+            g_user_part = nullptr; g_user_part_floats = 0;
+            NRC_CUDA_CHECK(cudaMalloc(&g_user_part, need_u * sizeof(float)));
+            g_user_part_floats = need_u;
+        }
+        int64_t ub = ((int64_t)n_users * 64 + 255) / 256;
+        if (ub > (int64_t)sm_count() * 8) ub = (int64_t)sm_count() * 8;
+        ncf_user_part_kernel<<<(unsigned)ub, 256, 0, st>>>(mlp_user, dense, users, n_users, g_user_part);
+        NRC_CUDA_CHECK(cudaGetLastError());
+        ncf_scores_tile_kernel<<<(unsigned)grid, 256, fsmem, st>>>(mf_user, mf_item, S.mf_dim, g_user_part, dense, g_item_part, ldb,
                                                                    users, n_users, num_items, scores);
         NRC_CUDA_CHECK(cudaGetLastError());
         return NRC_OK;

@@ -493,7 +493,7 @@ mf_bpr_sgd_pipe_kernel(float* __restrict__ U_local, const RowShards V, const Epo
             epoch_sample(E, first + q, 0, u, i, j);
             if (n >= kPipeSamplers) {                       // this thread's previous entry must have been taken
                 const int32_t want = n - kPipeSamplers + 1;
-                while (seq_done[tid] != want) { }
+                while (seq_done[tid] != want) __nanosleep(256);     // samplers run ahead: sleep, do not steal issue slots from the consumers
             }
             idq[tid] = PipeIds{u, i, j, 0};
             __threadfence_block();
@@ -508,7 +508,7 @@ mf_bpr_sgd_pipe_kernel(float* __restrict__ U_local, const RowShards V, const Epo
             const int s = n % kPipeSlots, e = n % kPipeSamplers, k = s / kPipeConsWarps;
             float *pu = nullptr, *wi = nullptr, *wj = nullptr;
             if (lane == 0) {
-                while (seq_ready[e] != n + 1) { }
+                while (seq_ready[e] != n + 1) __nanosleep(64);
                 __threadfence_block();
                 const PipeIds t = idq[e];
                 __threadfence_block();
