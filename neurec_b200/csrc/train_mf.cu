@@ -165,8 +165,9 @@ struct RowShards {
     float* base[8];
     int32_t rows_per_shard;   // 0: a single local table at base[0]
     int32_t self;             // this rank's shard (rows of other shards live in peer memory)
-    int32_t vec_remote;       // how rows of OTHER ranks are updated: 0 scalar REDs (default), 1 vector REDs,
-                              // 2 one bulk reduce-add of the whole row (cp.reduce.async.bulk from shared memory) -- NRC_PEER_VEC_RED
+    int32_t vec_remote;       // how rows of OTHER ranks are updated: 0 scalar REDs, 1 vector REDs (default), 2 one bulk
+                              // reduce-add of the whole row (cp.reduce.async.bulk from shared memory) -- NRC_PEER_VEC_RED.
+                              // Measured over NVLink on B200 (profiles/r2_peer_probe_v2.txt): 0.29 / 1.33 / 1.34 G rows/s
     int32_t force_remote;     // debug (NRC_FORCE_REMOTE_PATH=1): take the remote update path for local item rows too
     // Replicated head (n_hot > 0): rows [0, n_hot) -- the loader relabels items by descending train degree, so these
     // are the most popular ones -- are READ from this rank's replica `hot` (L2-resident) and their deltas are
@@ -269,11 +270,17 @@ mf_bpr_sgd_fused_kernel(const RowShards U, const RowShards V, const int32_t* __r
             dvi[t] = -lr * (g * a[t] + reg * bi[t]);
             dvj[t] = -lr * (-g * a[t] + reg * bj[t]);
         }
-        red_row<VEC>(pu, du, ru);
-        red_row<VEC>(qi, dvi, ri);
-        red_row<VEC>(qj, dvj, rj);
+        red_row<VEC>(pu, du, ru && U.vec_remote == 0);
+        red_row<VEC>(qi, dvi, ri && V.vec_remote == 0);
+        red_row<VEC>(qj, dvj, rj && V.vec_remote == 0);
     }
     if (lane == 0 && loss) atomicAdd(loss, loss_acc);
+}
+
+static int peer_red_mode() {
+    static int vec = -1;
+    if (vec < 0) { const char* e = getenv("NRC_PEER_VEC_RED"); vec = e ? atoi(e) : 1; }
+    return vec;
 }
 
 static int launch_bpr_sgd(const RowShards& SU, const RowShards& SV, int dim, const int32_t* users,
@@ -813,6 +820,7 @@ extern "C" int nrc_mf_bpr_sgd_sharded(float* const* user_shards, float* const* i
     SU.rows_per_shard = (int32_t)users_per_shard;
     SV.rows_per_shard = (int32_t)items_per_shard;
     SU.self = SV.self = self_rank;
+    SU.vec_remote = SV.vec_remote = peer_red_mode();
     return launch_bpr_sgd(SU, SV, dim, users, pos_items, neg_items, batch, lr, reg, loss, as_stream(stream));
 }
 
@@ -855,7 +863,7 @@ extern "C" int nrc_mf_bpr_sgd_epoch_hot(float* user_table, float* const* item_sh
     SV.hot = hot; SV.hot_delta = hot_delta; SV.n_hot = n_hot;
     {
         static int vec = -1, force = -1;
-        if (vec < 0) { const char* e = getenv("NRC_PEER_VEC_RED"); vec = e ? atoi(e) : 0; }
+        if (vec < 0) vec = peer_red_mode();
         if (force < 0) { const char* e = getenv("NRC_FORCE_REMOTE_PATH"); force = e ? atoi(e) : 0; }
         SV.vec_remote = vec;
         SV.force_remote = force;

@@ -133,7 +133,10 @@ class ShardSet:
 def alloc_sharded(rows, dim, backend=None):
     """Allocate this rank's [rows, dim] fp32 block (same shape on every rank) and map everyone
     else's.  Collective over the default process group."""
-    backend = backend or os.environ.get("NRC_PEER_BACKEND", "ipc")
+    # Default: symmetric memory (CUDA VMM allocations shared as file descriptors).  Measured on 2 x B200 with uniform ids
+    # (tests/mgpu_peer_rate.py): random 512-byte rows of a peer block mapped that way run at NVLink rates, the same
+    # block imported through legacy CUDA IPC (cudaIpcOpenMemHandle) at ~1/3 of that.
+    backend = backend or os.environ.get("NRC_PEER_BACKEND", "symm")
     ws, rank = dist.get_world_size(), dist.get_rank()
     device = torch.device("cuda", torch.cuda.current_device())
     lib = _lib.load()
