@@ -447,16 +447,15 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
 //       4-5 DEPENDENT DRAM round trips, so throughput = chains in flight / chain latency: 512 per SM.
 //   consumers (8 warps, 16 ring slots each): lane 0 takes the next ids from the queue and issues three bulk copies
 //       (cp.async.bulk, one row each) into the slot, completion counted on the slot's mbarrier; when the rows
-//       have landed the warp computes the triplet from shared memory, writes the three delta rows IN PLACE and
-//       hands them to the copy engine as bulk reduce-adds (cp.reduce.async.bulk .add.f32 -- local and peer
-//       rows alike).  A slot is refilled once the engine has read its deltas (wait_group.read), kPipeLag
-//       triplets later in the warp's round-robin, so the warp never waits for a reduce it has just issued.
+//       have landed the warp reads them into registers, REFILLS THE SLOT AT ONCE with its next triplet, and
+//       finishes the current one out of registers: dots by shuffle, deltas by vector RED.ADD (local and peer
+//       rows alike).  (Returning the deltas through the copy engine as bulk reduce-adds -- the first version --
+//       keeps a slot busy until the engine has read them back: measured slower)
 // 128 slots x 3 rows in flight per SM (192 KB at d = 128) whatever the register pressure.  One CTA per SM.
 // CTA-local sequence number n <-> ring slot n % 128, round n / 128, position first + blockIdx*128 + slot + round*stride.
 // ----------------------------------------------------------------------------------------
 constexpr int kPipeSlots = 128, kPipeSamplerWarps = 16, kPipeConsWarps = 8;
 constexpr int kPipeSamplers = kPipeSamplerWarps * 32;          // = id-queue entries (one per sampler thread)
-constexpr int kPipeLag = 6;                                    // a slot is refilled this many triplets after its deltas were handed over (< 16 - 1)
 constexpr int kPipeThreads = (kPipeSamplerWarps + kPipeConsWarps) * 32;
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -545,9 +544,6 @@ mf_bpr_sgd_pipe_kernel(float* __restrict__ U_local, const RowShards V, const Epo
             const int32_t n = cw + k * kPipeConsWarps;
             if (n < n_end && pos_of(n) < count) load_slot(n);
         }
-        int32_t hist[kPipeLag];                                     // the last kPipeLag sequence numbers handed to the engine
-#pragma unroll
-        for (int h = 0; h < kPipeLag; ++h) hist[h] = -1;
         for (int32_t r = 0; r < (int32_t)rounds; ++r) {
             for (int k = 0; k < kMine; ++k) {
                 const int s = cw + k * kPipeConsWarps;
@@ -563,7 +559,15 @@ mf_bpr_sgd_pipe_kernel(float* __restrict__ U_local, const RowShards V, const Epo
                     di = fmaf(a[t], bi[t], di); dj = fmaf(a[t], bj[t], dj);
                     sq += a[t] * a[t] + bi[t] * bi[t] + bj[t] * bj[t];
                 }
-                di = warp_sum(di); dj = warp_sum(dj);
+                di = warp_sum(di); dj = warp_sum(dj);      // every lane's row reads have completed (the sums depend on them)
+                // where this triplet's deltas go, then refill the slot at once: the rows are in registers now
+                float* const p0 = reinterpret_cast<float*>(__shfl_sync(kFull, (unsigned long long)upd_u, k)) + lane * VEC;
+                float* const p1 = reinterpret_cast<float*>(__shfl_sync(kFull, (unsigned long long)upd_i, k)) + lane * VEC;
+                float* const p2 = reinterpret_cast<float*>(__shfl_sync(kFull, (unsigned long long)upd_j, k)) + lane * VEC;
+                {
+                    const int32_t nn = n + kPipeSlots;                   // same slot, next round
+                    if (nn < n_end && pos_of(nn) < count) load_slot(nn);
+                }
                 const float x = di - dj;
                 float l = (x >= 0.f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
                 if (reg != 0.0f) l += reg * 0.5f * warp_sum(sq);
@@ -576,38 +580,12 @@ mf_bpr_sgd_pipe_kernel(float* __restrict__ U_local, const RowShards V, const Epo
                     dvi[t] = -lr * (g * a[t] + reg * bi[t]);
                     dvj[t] = -lr * (-g * a[t] + reg * bj[t]);
                 }
-                st_vec<VEC>(slot, du); st_vec<VEC>(slot + D, dvi); st_vec<VEC>(slot + 2 * D, dvj);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                float* const p0 = reinterpret_cast<float*>(__shfl_sync(kFull, (unsigned long long)upd_u, k));
-                float* const p1 = reinterpret_cast<float*>(__shfl_sync(kFull, (unsigned long long)upd_i, k));
-                float* const p2 = reinterpret_cast<float*>(__shfl_sync(kFull, (unsigned long long)upd_j, k));
-                if (lane == 0) {
-                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(ring + (size_t)s * 3 * D);
-                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
-                                 ::"l"(p0), "r"(src), "r"(kRowBytes) : "memory");
-                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
-                                 ::"l"(p1), "r"(src + kRowBytes), "r"(kRowBytes) : "memory");
-                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
-                                 ::"l"(p2), "r"(src + 2 * kRowBytes), "r"(kRowBytes) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    // the deltas handed over kPipeLag slots ago have left shared memory by now (waiting for the
-                    // group just committed would stall the warp for a full engine round trip per triplet)
-                    if (hist[kPipeLag - 1] >= 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPipeLag) : "memory");
-                }
-                __syncwarp();
-                if (hist[kPipeLag - 1] >= 0) {
-                    const int32_t nn = hist[kPipeLag - 1] + kPipeSlots;   // same slot, next round
-                    if (nn < n_end && pos_of(nn) < count) load_slot(nn);
-                }
-#pragma unroll
-                for (int h = kPipeLag - 1; h > 0; --h) hist[h] = hist[h - 1];
-                hist[0] = n;
+                red_row<VEC>(p0, du, false);       // vector REDs, local and peer rows alike
+                red_row<VEC>(p1, dvi, false);
+                red_row<VEC>(p2, dvj, false);
             }
         }
-        if (lane == 0) {
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every reduce-add performed before the kernel ends
-            if (loss) atomicAdd(loss, loss_acc);
-        }
+        if (lane == 0 && loss) atomicAdd(loss, loss_acc);
     }
 }
 
