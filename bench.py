@@ -730,7 +730,7 @@ class ShardedCfg:
     users_per_gpu, items_per_gpu, dim, batch, lr = 6_250_000, 12_500_000, 128, 1 << 20, 0.05
     max_pos = 7                 # positives per user: 1..7 (a <= 64-item positive list)
     zipf_a = 1.05
-    n_hot = 16384               # replicated head of the item table: ~2/3 of all positives at Zipf(1.05) (NRC_BENCH_N_HOT)
+    n_hot = 16384               # replicated head of the item table (N > 1 only): ~2/3 of all positives at Zipf(1.05) (NRC_BENCH_N_HOT)
 
 
 def synth_shard_csr(cfg, rank, world, device="cuda"):
@@ -748,7 +748,7 @@ def synth_shard_csr(cfg, rank, world, device="cuda"):
     # the loader's relabelling (peer.relabel_by_degree): the n_hot most popular items get ids [0, n_hot) in rank
     # order, the order of the rest is arbitrary -- here a multiplicative hash, so that warm rows are spread over the
     # whole table (and both dies' memory) instead of sitting next to each other
-    nh = n_hot_of(cfg)
+    nh = n_hot_of(cfg, world)
     items = torch.where(r < nh, r, nh + ((r - nh) * 2654435761) % (ni - nh))
     del x, r
     big = torch.iinfo(torch.int64).max
@@ -767,20 +767,29 @@ def synth_shard_csr(cfg, rank, world, device="cuda"):
     return indptr.cpu().numpy(), indices.cpu().numpy(), users.cpu().numpy()
 
 
-def n_hot_of(cfg):
-    return int(os.environ.get("NRC_BENCH_N_HOT", cfg.n_hot))
+def n_hot_of(cfg, world):
+    """Rows of the replicated head.  The head exists to keep thousands of same-address REDs per step off NVLink; on one
+    GPU those rows sit in L2 anyway and the replica only adds a pass (measured, profiles/r2_sgd_forms.txt: 0.646 of the
+    HBM peak with it, 0.720 without), so the default is 0 at N = 1."""
+    return int(os.environ.get("NRC_BENCH_N_HOT", cfg.n_hot if world > 1 else 0))
+
+
+def sgd_form():
+    """The form of the CSR-fed step the library runs: the register form unless NRC_SGD_PIPE=1 (csrc/train_mf.cu)."""
+    return "mf_bpr_sgd_pipe_kernel" if os.environ.get("NRC_SGD_PIPE", "0") != "0" else "mf_bpr_sgd_stream_kernel"
 
 
 def sharded_describe(cfg, world):
     return ("BPRMF, learner=gd, tables row-sharded over %d GPU(s): %d users x %d items x d=%d per GPU (%.1f GB per GPU; "
             "%d x %d rows in total), 2^20 triplets per GPU and step sampled INSIDE the step kernel from the rank's train "
             "CSR (1..%d positives per user, items Zipf(%.2f) over the global catalogue with the most popular ids first "
-            "(the loader's relabelling), uniform negatives rejected against the user's row, keyed-bijection shuffle); the "
-            "%d most popular item rows are replicated on every GPU, their deltas summed by one all-reduce per step "
-            "-- BASELINE configs[4], weak scaling" % (
+            "(the loader's relabelling), uniform negatives rejected against the user's row, keyed-bijection shuffle); %s"
+            " -- BASELINE configs[4], weak scaling" % (
                 world, cfg.users_per_gpu, cfg.items_per_gpu, cfg.dim,
                 (cfg.users_per_gpu + cfg.items_per_gpu) * cfg.dim * 4 / 1e9, cfg.users_per_gpu * world,
-                cfg.items_per_gpu * world, cfg.max_pos, cfg.zipf_a, n_hot_of(cfg)))
+                cfg.items_per_gpu * world, cfg.max_pos, cfg.zipf_a,
+                ("the %d most popular item rows are replicated on every GPU, their deltas summed by one all-reduce per step"
+                 % n_hot_of(cfg, world)) if n_hot_of(cfg, world) else "no replicated head"))
 
 
 def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
@@ -803,7 +812,7 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
         US_local = torch.empty((cfg.users_per_gpu, dim), dtype=torch.float32, device="cuda")
     US_local.normal_(0, 0.01, generator=g)
     VS.local.normal_(0, 0.01, generator=g)
-    VS.enable_hot(n_hot_of(cfg))
+    VS.enable_hot(n_hot_of(cfg, world))
     spe = T.n_pos // bs                        # whole batches only (drop_last), so every step is 2^20 triplets
     loss = torch.zeros(1, device="cuda")
     loss_pin = torch.zeros(K + W + 8).pin_memory()
@@ -848,7 +857,7 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
     barrier(world)
     finite = bool(np.isfinite(loss_pin[:K].numpy()).all())
     remote = (world - 1) / world if world > 1 else 0.0
-    cold_pos = float((T.idx >= n_hot_of(cfg)).float().mean().item()) if n_hot_of(cfg) else 1.0
+    cold_pos = float((T.idx >= n_hot_of(cfg, world)).float().mean().item()) if n_hot_of(cfg, world) else 1.0
     lazy = None
     if world == 1:          # the explicitly-named lazy-Adam run SURVEY 8(d) asks for (single GPU: rows of var, m, v)
         z = torch.zeros_like
@@ -876,7 +885,7 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
     # replicated head, to first order), positives only when their id is outside it
     nv_bytes = bs * (1.0 + cold_pos) * remote * dim * 4
     extra = {"launch_us_min": float(np.min(launch_ms)) * 1e3, "launch_us_max": float(np.max(launch_ms)) * 1e3,
-             "replicated_head": {"rows": n_hot_of(cfg), "sync_us_mean": float(np.mean(sync_ms)) * 1e3,
+             "replicated_head": {"rows": n_hot_of(cfg, world), "sync_us_mean": float(np.mean(sync_ms)) * 1e3,
                                  "what": "per step after the kernel: all-reduce (NCCL, N > 1) of the head's deltas + apply"}}
     if world > 1:
         extra["nvlink"] = {"remote_item_row_fraction": remote, "positives_outside_the_replicated_head": cold_pos,
@@ -891,7 +900,7 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
                       "global_batch": bs * world, "steps_per_epoch": spe,
                       "exchange": ("remote item rows are bulk-copied in and reduce-added back through peer mappings over "
                                    "NVLink inside the one fused kernel; the replicated head's deltas (%d rows) take one NCCL "
-                                   "all-reduce per step, which also keeps the ranks in step" % n_hot_of(cfg)) if world > 1
+                                   "all-reduce per step, which also keeps the ranks in step" % n_hot_of(cfg, world)) if world > 1
                                   else "single GPU: no exchange",
                       "loss_finite": finite,
                       "l2": "tables (9.6 GB per GPU) and the train CSR (%.2f GB) are far larger than L2; every step draws "
@@ -900,8 +909,8 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / K,
                    "how": "the rank's train CSR + flattened positives (%.0f MB) are copied from pinned host memory inside "
                           "the timed region, then K steps, each copying its loss back to pinned memory" % (T.nbytes / 1e6)},
-           "gpu_launches": K * (2 if n_hot_of(cfg) else 1),
-           "roofline": hbm_roofline("mf_bpr_sgd_pipe_kernel" if os.environ.get("NRC_SGD_PIPE", "1") != "0" else "mf_bpr_sgd_stream_kernel", nbytes, kt,
+           "gpu_launches": K * (2 if n_hot_of(cfg, world) else 1),
+           "roofline": hbm_roofline(sgd_form(), nbytes, kt,
                                     "SURVEY 8(d): (24*d + 12) B per triplet x 2^20 triplets (the fused sampler's CSR reads "
                                     "are not counted: 'fused: 0 extra')",
                                     "CUDA events on the launching stream around each of the K timed launches; mean", extra)}

@@ -406,10 +406,11 @@ int nrc_mf_bpr_sgd_epoch_hot(float* user_table, float* const* item_shards, int32
                              float* hot, float* hot_delta, int32_t n_hot, void* stream);
 /* hot[e] += hot_delta[e]; hot_delta[e] = 0 for e < n_floats (a multiple of 4; both 16-byte aligned). */
 int nrc_mf_hot_apply(float* hot, float* hot_delta, int64_t n_floats, void* stream);
-/* Which kernel nrc_mf_bpr_sgd_epoch launches for dim 64 / 128.  1 (default): the pipelined form -- producer
- * threads sample and issue bulk copies (cp.async.bulk) of the three rows into a 128-slot shared-memory ring,
- * consumer warps compute and return the deltas as bulk reduce-adds (cp.reduce.async.bulk .add.f32), local and
- * peer rows alike.  0: the register form (two triplets per warp, LDG + RED).  Same arithmetic per triplet.
+/* Which kernel nrc_mf_bpr_sgd_epoch launches for dim 64 / 128.  0 (default): the register form (a CTA samples 256
+ * positions, then two triplets per warp in flight: LDG.128 row gathers, shuffle dots, vector RED.ADD).  1: the
+ * pipelined form -- sampler warps feed an id queue, consumer warps issue bulk copies (cp.async.bulk) of the three
+ * rows into a 128-slot shared-memory ring and return the deltas as vector REDs.  Same arithmetic per triplet.
+ * Measured on B200 (profiles/r2_sgd_forms.txt): register form 0.72 of the HBM copy peak, pipelined 0.47-0.59.
  * Returns the previous setting.  (NRC_SGD_PIPE=0/1 sets the initial value.) */
 int nrc_mf_sgd_set_pipelined(int32_t on);
 
@@ -653,6 +654,67 @@ int nrc_ngcf_grad(const nrc_ngcf_shape* shape, const int64_t* indptr, const int3
                   const int32_t* users, const int32_t* pos_items, const int32_t* neg_items,
                   int64_t batch, float reg, float* all_emb, float* grad_all, float* grad_e0,
                   float* grad_weights, float* work, float* loss2, void* stream);
+
+/* ======================================================================================
+ * APR, SBPR, time-ordered samplers, interactions -> CSR
+ * ==================================================================================== */
+
+/* APR._create_adversarial, model/general_recommender/APR.py:92-118:
+ * out[r, :] = tf.nn.l2_normalize(x, 1)[r, :] * scale = (x * rsqrt(max(sum(x^2), 1e-12))) * scale.
+ * x, out f32 [rows, dim] (may alias). */
+int nrc_l2_normalize_rows(const float* x, int64_t rows, int32_t dim, float scale, float* out, void* stream);
+
+/* out[p, :] = src[index[p] % src_rows, :]; src i32 [src_rows, width], index i64 [n] (nrc_shuffle_perm), out i32
+ * [n, width].  The recent-items window of TimeOrderPointwiseSampler / TimeOrderPairwiseSampler
+ * (data/sampler.py:216-354) travelling with the shuffled samples (util/data_iterator.py:147-152). */
+int nrc_gather_rows_i32(const int32_t* src, int64_t src_rows, int32_t width, const int64_t* index, int64_t n,
+                        int32_t* out, void* stream);
+
+/* SBPR._get_pairwise_all_data + DataIterator(shuffle=True), model/social_recommender/SBPR.py:103-149:
+ * positions [first, first + count) of the shuffled epoch `epoch`.  For the positive (u, i) at a position:
+ * social item k uniform (with replacement) over social_items(u) (np.random.choice, :139), negative j uniform over
+ * the items outside train(u) + social_items(u) (randint_choice with exclusion, :135-137),
+ * s_uk = 1 + #{f in trust(u): k in train(f)} (:141-145).  CSRs have ascending rows; pos_users / pos_items are the
+ * flattened positives of the users with a non-empty social row (:125-131), n_pos of them; max_excluded = the
+ * largest train(u) + social(u) size (ValueError when >= num_items, random_choice.pyx:32-33).
+ * Outputs i32 [count] x 4 and f32 [count]. */
+int nrc_sbpr_epoch_build(const int64_t* train_indptr, const int32_t* train_indices, const int64_t* social_indptr,
+                         const int32_t* social_indices, const int64_t* trust_indptr, const int32_t* trust_indices,
+                         const int32_t* pos_users, const int32_t* pos_items, int64_t n_pos, int32_t num_items,
+                         int32_t max_excluded, int32_t shuffle, uint64_t seed, uint64_t epoch, int64_t first,
+                         int64_t count, int32_t* out_users, int32_t* out_pos, int32_t* out_social,
+                         int32_t* out_neg, float* out_suk, void* stream);
+
+/* SBPR._create_inference / _create_loss, SBPR.py:66-92: x = <p, q> + b per item; loss =
+ * l((x_i - x_k) / s_uk) + l(x_k - x_j) + reg * l2_loss(p, q_k, q_i, q_j, b_i, b_k, b_j) with l = learner.pairwise_loss
+ * (util/learner.py:17-29), summed over the batch into *loss.  Row gradients are ADDED into the dense accumulators
+ * (grad_bias f32 [num_items]); touched_* get `stamp` (bias shares the items' stamps). */
+int nrc_sbpr_grad(const float* user_table, const float* item_table, const float* item_bias, int32_t dim,
+                  const int32_t* users, const int32_t* pos_items, const int32_t* social_items,
+                  const int32_t* neg_items, const float* suk, int64_t batch, int32_t loss_kind, float reg,
+                  float* grad_user, float* grad_item, float* grad_bias, int32_t* touched_user,
+                  int32_t* touched_item, int32_t stamp, float* loss, void* stream);
+
+/* SBPR.train_model's batch loop, SBPR.py:111-121, over a device-built epoch of n samples: per batch nrc_sbpr_grad +
+ * one TF-1.12 optimizer launch over user table, item table and item bias.  lr_t_host f32 [steps] (adam), hyper_host
+ * as nrc_opt_apply_rows; step_loss f32 [steps] receives every batch's loss. */
+int nrc_sbpr_train_epoch(float* user_table, float* item_table, float* item_bias, int32_t num_users,
+                         int32_t num_items, int32_t dim, const int32_t* users, const int32_t* pos_items,
+                         const int32_t* social_items, const int32_t* neg_items, const float* suk, int64_t n,
+                         int32_t batch_size, int32_t loss_kind, float reg, int32_t opt_kind,
+                         const float* lr_t_host, const float* hyper_host, float* grad_user, float* grad_item,
+                         float* grad_bias, int32_t* touched_user, int32_t* touched_item, float* slot0_user,
+                         float* slot1_user, float* slot0_item, float* slot1_item, float* slot0_bias,
+                         float* slot1_bias, int32_t first_stamp, float* step_loss, void* stream);
+
+/* Interactions (COO, any order, duplicates allowed) -> CSR with ascending duplicate-free rows: what
+ * Dataset.to_csr_matrix + csr_to_user_dict (data/dataset.py:288-296, util/tool.py:56-65) hand to samplers and
+ * evaluator.  rows, cols i32 [nnz]; out_indptr i64 [num_rows + 1]; out_indices i32 [nnz] (the first
+ * out_indptr[num_rows] entries are valid); scratch work_i64 [2 * (num_rows + 1)], work_i32 [2 * nnz];
+ * *bad_flag (device i32) = 1 when an id was out of range (those interactions are dropped). */
+int nrc_csr_from_coo(const int32_t* rows, const int32_t* cols, int64_t nnz, int32_t num_rows, int32_t num_cols,
+                     int64_t* out_indptr, int32_t* out_indices, int64_t* work_i64, int32_t* work_i32,
+                     int32_t* bad_flag, void* stream);
 
 #ifdef __cplusplus
 }

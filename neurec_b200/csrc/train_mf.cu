@@ -438,7 +438,9 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
 }
 
 // ----------------------------------------------------------------------------------------
-// Pipelined form of the CSR-fed step (NRC_SGD_PIPE / nrc_mf_sgd_set_pipelined).
+// Pipelined form of the CSR-fed step (NRC_SGD_PIPE=1 / nrc_mf_sgd_set_pipelined; NOT the default: measured at 0.47-0.59
+// of the HBM copy peak against 0.72 for the register form above -- profiles/r2_sgd_forms.txt.  Kept as the measured
+// alternative north_star names: rows staged through shared memory by the bulk-copy engine).
 // The register form keeps 2 triplets per warp in flight and alternates a sampling phase with an update phase;
 // ncu shows it latency-bound (long-scoreboard stalls, DRAM at ~3/4 of the copy peak).  Here the rows never
 // pass through registers on their way in or out, and sampling runs ahead of the row traffic:
@@ -607,7 +609,7 @@ static int launch_pipe(float* U_local, const RowShards& SV, const EpochSpec& E, 
 
 static int g_sgd_pipe = -1;
 static int sgd_pipe_enabled() {
-    if (g_sgd_pipe < 0) { const char* e = getenv("NRC_SGD_PIPE"); g_sgd_pipe = e ? (atoi(e) != 0) : 1; }
+    if (g_sgd_pipe < 0) { const char* e = getenv("NRC_SGD_PIPE"); g_sgd_pipe = e ? (atoi(e) != 0) : 0; }
     return g_sgd_pipe;
 }
 

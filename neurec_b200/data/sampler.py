@@ -27,6 +27,11 @@ from .. import ops
 _EPOCH_COUNTER = itertools.count()      # process-wide stream position (the reference's global RNG state)
 
 
+def _EPOCH_COUNTER_NEXT():
+    """Next position of the process-wide stream (models that sample outside a Sampler object: SBPR)."""
+    return next(_EPOCH_COUNTER)
+
+
 def reseed(first_epoch=0):
     """Restart the process-wide epoch numbering (tests; the analogue of re-seeding np.random)."""
     global _EPOCH_COUNTER

@@ -1,7 +1,11 @@
-"""AbstractRecommender: the model plug-in base class (reference model/AbstractRecommender.py:9-45).
-Sequential / social bases are outside the hot path."""
+"""AbstractRecommender: the model plug-in base classes (reference model/AbstractRecommender.py:9-80).
+The sequential base is outside the hot path."""
 import os
 import time
+
+import numpy as np
+import pandas as pd
+import scipy.sparse as sp
 
 from ..evaluator import ProxyEvaluator
 from ..util.logger import Logger
@@ -37,3 +41,20 @@ class AbstractRecommender(object):
 
     def predict(self, user_ids, items):
         raise NotImplementedError
+
+
+class SocialAbstractRecommender(AbstractRecommender):
+    """AbstractRecommender.py:54-74: reads conf["social_file"] (user, friend pairs in raw ids), keeps the pairs whose
+    two ends are known users and builds ``social_matrix`` (users x users CSR; duplicate pairs collapse)."""
+
+    def __init__(self, dataset, conf):
+        super(SocialAbstractRecommender, self).__init__(dataset, conf)
+        pairs = pd.read_csv(conf["social_file"], sep=conf["data.convert.separator"], header=None,
+                            names=["user", "friend"])
+        known = np.array(list(dataset.userids.keys()))
+        pairs = pairs[np.isin(pairs["user"], known)]
+        pairs = pairs[np.isin(pairs["friend"], known)]
+        user_id = [dataset.userids[u] for u in pairs["user"]]
+        friend_id = [dataset.userids[u] for u in pairs["friend"]]
+        num_users = dataset.train_matrix.shape[0]
+        self.social_matrix = sp.csr_matrix(([1] * len(user_id), (user_id, friend_id)), shape=(num_users, num_users))

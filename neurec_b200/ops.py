@@ -431,8 +431,8 @@ def opt_apply_multi(opt, variables, stamp, hyper):
 
 
 def mf_sgd_set_pipelined(on):
-    """Kernel behind mf_bpr_sgd_epoch / mf_bpr_sgd_sharded for dim 64 / 128: True (default) the bulk-copy
-    pipeline, False the register form (nrc_mf_sgd_set_pipelined).  Returns the previous setting."""
+    """Kernel behind mf_bpr_sgd_epoch for dim 64 / 128: False (default) the register form, True the bulk-copy
+    pipeline (nrc_mf_sgd_set_pipelined).  Returns the previous setting."""
     return bool(_lib.load().nrc_mf_sgd_set_pipelined(1 if on else 0))
 
 
@@ -670,3 +670,90 @@ def ngcf_grad(shape, csr, row_order, t_csr, t_row_order, e0, weights, masks, kee
                                     _p(users), _p(pos), _p(neg), users.numel(), float(reg), _p(all_emb), _p(grad_all),
                                     _p(grad_e0), _p(grad_weights), _p(work), _p(loss2), _stream()))
     _count(4 * shape.n_layers + 4)
+
+
+# ------------------------------------------------- APR, SBPR, time order, CSR build
+def l2_normalize_rows(x, scale, out=None):
+    """tf.nn.l2_normalize(x, 1) * scale (APR.py:103-104,117-118) on a f32 [rows, dim] table."""
+    _req(x, torch.float32, "x")
+    out = torch.empty_like(x) if out is None else _req(out, torch.float32, "out")
+    check(_lib.load().nrc_l2_normalize_rows(_p(x), x.shape[0], x.shape[1], float(scale), _p(out), _stream()))
+    _count()
+    return out
+
+
+def gather_rows_i32(src, index, out=None):
+    """out[p] = src[index[p] % len(src)] for an int32 [rows, width] (or [rows]) table and an int64 index."""
+    _req(src, torch.int32, "src"); _req(index, torch.int64, "index")
+    width = 1 if src.dim() == 1 else int(src.shape[1])
+    shape = (index.numel(),) if src.dim() == 1 else (index.numel(), width)
+    out = torch.empty(shape, dtype=torch.int32, device=src.device) if out is None else out
+    check(_lib.load().nrc_gather_rows_i32(_p(src), src.shape[0], width, _p(index), index.numel(), _p(out), _stream()))
+    _count()
+    return out
+
+
+def sbpr_epoch_build(train_indptr, train_indices, social_indptr, social_indices, trust_indptr, trust_indices,
+                     pos_users, pos_items, num_items, max_excluded, shuffle, seed, epoch, first=0, count=None):
+    """One epoch of SBPR._get_pairwise_all_data + DataIterator (SBPR.py:103-149) as device arrays:
+    users, pos, social, neg i32 [count] and s_uk f32 [count]."""
+    for t, n in ((train_indptr, "train_indptr"), (social_indptr, "social_indptr"), (trust_indptr, "trust_indptr")):
+        _req(t, torch.int64, n)
+    for t, n in ((train_indices, "train_indices"), (social_indices, "social_indices"), (trust_indices, "trust_indices"),
+                 (pos_users, "pos_users"), (pos_items, "pos_items")):
+        _req(t, torch.int32, n)
+    n_pos = pos_users.numel()
+    count = n_pos - first if count is None else int(count)
+    dev = pos_users.device
+    mk = lambda dt: torch.empty((count,), dtype=dt, device=dev)
+    ou, oi, ok, oj, os_ = mk(torch.int32), mk(torch.int32), mk(torch.int32), mk(torch.int32), mk(torch.float32)
+    check(_lib.load().nrc_sbpr_epoch_build(_p(train_indptr), _p(train_indices), _p(social_indptr), _p(social_indices),
+                                           _p(trust_indptr), _p(trust_indices), _p(pos_users), _p(pos_items), n_pos,
+                                           int(num_items), int(max_excluded), 1 if shuffle else 0, int(seed), int(epoch),
+                                           int(first), count, _p(ou), _p(oi), _p(ok), _p(oj), _p(os_), _stream()))
+    _count()
+    return ou, oi, ok, oj, os_
+
+
+def sbpr_grad(U, V, B, users, pos, social, neg, suk, loss, reg, gU, gV, gB, tU, tV, stamp, loss_out):
+    check(_lib.load().nrc_sbpr_grad(_p(U), _p(V), _p(B), U.shape[1], _p(users), _p(pos), _p(social), _p(neg), _p(suk),
+                                    users.numel(), LOSS_IDS[loss], float(reg), _p(gU), _p(gV), _p(gB), _p(tU), _p(tV),
+                                    int(stamp), _p(loss_out), _stream()))
+    _count()
+
+
+def sbpr_train_epoch(U, V, B, users, pos, social, neg, suk, batch_size, loss, reg, opt, lr_t, hyper, gU, gV, gB, tU, tV,
+                     s0U, s1U, s0V, s1V, s0B, s1B, first_stamp, step_loss):
+    n = users.numel()
+    steps = (n + batch_size - 1) // batch_size
+    lr_t = np.ascontiguousarray(lr_t, dtype=np.float32)
+    assert lr_t.size >= max(steps, 1)
+    h = np.zeros(4, dtype=np.float32)
+    h[:len(hyper)] = hyper
+    check(_lib.load().nrc_sbpr_train_epoch(
+        _p(U), _p(V), _p(B), U.shape[0], V.shape[0], U.shape[1], _p(users), _p(pos), _p(social), _p(neg), _p(suk), n,
+        int(batch_size), LOSS_IDS[loss], float(reg), OPT_IDS[opt], lr_t.ctypes.data, h.ctypes.data, _p(gU), _p(gV),
+        _p(gB), _p(tU), _p(tV), _p(s0U), _p(s1U), _p(s0V), _p(s1V), _p(s0B), _p(s1B), int(first_stamp), _p(step_loss),
+        _stream()))
+    _count(2 * steps)
+    return steps
+
+
+def csr_from_coo(rows, cols, num_rows, num_cols):
+    """Interactions -> (indptr i64 [num_rows + 1], indices i32 [distinct]) with ascending duplicate-free rows
+    (Dataset.to_csr_matrix + csr_to_user_dict, dataset.py:288-296, tool.py:56-65).  ValueError on ids out of range."""
+    _req(rows, torch.int32, "rows"); _req(cols, torch.int32, "cols")
+    if rows.numel() != cols.numel():
+        raise ValueError("rows and cols must have the same length")
+    nnz, dev = rows.numel(), rows.device
+    indptr = torch.empty((num_rows + 1,), dtype=torch.int64, device=dev)
+    indices = torch.empty((max(nnz, 1),), dtype=torch.int32, device=dev)
+    w64 = torch.empty((2 * (num_rows + 1),), dtype=torch.int64, device=dev)
+    w32 = torch.empty((max(2 * nnz, 1),), dtype=torch.int32, device=dev)
+    bad = torch.empty((1,), dtype=torch.int32, device=dev)
+    check(_lib.load().nrc_csr_from_coo(_p(rows), _p(cols), nnz, int(num_rows), int(num_cols), _p(indptr), _p(indices),
+                                       _p(w64), _p(w32), _p(bad), _stream()))
+    _count(6)
+    if int(bad.item()):
+        raise ValueError("interaction ids outside [0, %d) x [0, %d)" % (num_rows, num_cols))
+    return indptr, indices[:int(indptr[-1].item())]

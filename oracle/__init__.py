@@ -265,6 +265,50 @@ def philox_batch_choice(high, out_indptr, replace=True, exclusion_csr=None, seed
     return out
 
 
+def social_items_csr(train_indptr, train_indices, trust_indptr, trust_indices):
+    """SBPR._get_SocialItemsSet (social_recommender/SBPR.py:39-49) as a CSR with ascending rows: for every user
+    the items its trusted users interacted with, minus its own."""
+    tp = np.asarray(train_indptr, np.int64); ti = np.asarray(train_indices, np.int32)
+    fp = np.asarray(trust_indptr, np.int64); fi = np.asarray(trust_indices, np.int32)
+    rows = []
+    for u in range(len(tp) - 1):
+        own = set(ti[tp[u]:tp[u + 1]].tolist())
+        if not own:                        # the reference iterates train_dict: users without train items are skipped
+            rows.append(np.zeros(0, np.int32)); continue
+        items = {int(i) for f in fi[fp[u]:fp[u + 1]] for i in ti[tp[f]:tp[f + 1]] if int(i) not in own}
+        rows.append(np.asarray(sorted(items), np.int32))
+    return lists_to_csr(rows)
+
+
+def sbpr_epoch_build(train_indptr, train_indices, social_indptr, social_indices, trust_indptr, trust_indices,
+                     pos_users, pos_items, num_items, shuffle, seed, epoch):
+    """One epoch of SBPR._get_pairwise_all_data + DataIterator (SBPR.py:103-149) in the product's order and with
+    the product's draws: (users, pos, social, neg, suk)."""
+    tp, tpp = _i64(train_indptr); ti, tip = _i32(train_indices)
+    sp, spp = _i64(social_indptr); si, sip = _i32(social_indices)
+    fp, fpp = _i64(trust_indptr); fi, fip = _i32(trust_indices)
+    us, usp = _i32(pos_users)
+    pos_items = np.ascontiguousarray(pos_items, dtype=np.int32)
+    n = len(us)
+    soc = np.empty(n, np.int32); neg = np.empty(n, np.int32); suk = np.empty(n, np.float32)
+    lib().orc_sbpr_sample(tpp, tip, spp, sip, fpp, fip, usp, ctypes.c_int64(n), ctypes.c_int(int(num_items)),
+                          ctypes.c_uint64(seed), ctypes.c_uint64(epoch), soc.ctypes.data_as(_c_i32p),
+                          neg.ctypes.data_as(_c_i32p), suk.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    perm = shuffle_perm(n, seed, epoch, shuffle)
+    return us[perm], pos_items[perm], soc[perm], neg[perm], suk[perm]
+
+
+def csr_from_coo(rows, cols, num_rows):
+    """Interactions -> CSR with ascending duplicate-free rows (dataset.py:288-296 + tool.py:56-65)."""
+    rows = np.asarray(rows, np.int64); cols = np.asarray(cols, np.int64)
+    key = np.unique(rows * (int(cols.max()) + 1 if len(cols) else 1) + cols)
+    width = int(cols.max()) + 1 if len(cols) else 1
+    r, c = key // width, key % width
+    indptr = np.zeros(num_rows + 1, np.int64)
+    np.add.at(indptr, r + 1, 1)
+    return np.cumsum(indptr), c.astype(np.int32)
+
+
 # ----------------------------------------------------------------------------------------
 # Importing the REAL Python reference (build container only; never on the GPU box)
 # ----------------------------------------------------------------------------------------

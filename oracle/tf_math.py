@@ -215,6 +215,76 @@ class MFTrainer:
 
 
 # ----------------------------------------------------------------------------------------
+# APR (APR.py:92-118) and SBPR (social_recommender/SBPR.py:66-92) -- SURVEY.md 8(f) rank 3
+# ----------------------------------------------------------------------------------------
+def l2_normalize_rows(x, scale):
+    """tf.nn.l2_normalize(x, 1) * scale: x * rsqrt(max(sum(x^2), 1e-12)) * scale (APR.py:103-104,117-118)."""
+    x = np.asarray(x, f32)
+    ss = (x * x).sum(1, dtype=f32, keepdims=True)
+    return ((x * (f32(1.0) / np.sqrt(np.maximum(ss, f32(1e-12))))) * f32(scale)).astype(f32)
+
+
+def sbpr_grad(U, V, B, users, pos, soc, neg, suk, loss="bpr", reg=0.0):
+    """SBPR._create_loss (SBPR.py:79-92) -> (loss, gU, gV, gB, touchedU, touchedV); x = <p, q> + b;
+    loss = l((x_i - x_k) / s) + l(x_k - x_j) + reg * l2_loss(p1, q2, q1, q3, b1, b2, b3)."""
+    U = np.asarray(U, f32); V = np.asarray(V, f32); B = np.asarray(B, f32)
+    s = np.asarray(suk, f32)
+    pu, qi, qk, qj = U[users], V[pos], V[soc], V[neg]
+    bi, bk, bj = B[pos], B[soc], B[neg]
+    xi = (pu * qi).sum(1, dtype=f32) + bi
+    xk = (pu * qk).sum(1, dtype=f32) + bk
+    xj = (pu * qj).sum(1, dtype=f32) + bj
+    l1, g1 = pairwise_loss_and_grad(loss, (xi - xk) / s)
+    l2, g2 = pairwise_loss_and_grad(loss, xk - xj)
+    reg = f32(reg)
+    sq = sum((a * a).sum(dtype=f32) for a in (pu, qk, qi, qj, bi, bk, bj))
+    total = l1.sum(dtype=f32) + l2.sum(dtype=f32) + reg * f32(0.5) * f32(sq)
+    ci = (g1 / s).astype(f32); ck = (g2 - ci).astype(f32); cj = (-g2).astype(f32)
+    gU = np.zeros_like(U); gV = np.zeros_like(V); gB = np.zeros_like(B)
+    np.add.at(gU, users, (ci[:, None] * qi + ck[:, None] * qk + cj[:, None] * qj + reg * pu).astype(f32))
+    np.add.at(gV, pos, (ci[:, None] * pu + reg * qi).astype(f32))
+    np.add.at(gV, soc, (ck[:, None] * pu + reg * qk).astype(f32))
+    np.add.at(gV, neg, (cj[:, None] * pu + reg * qj).astype(f32))
+    np.add.at(gB, pos, (ci + reg * bi).astype(f32))
+    np.add.at(gB, soc, (ck + reg * bk).astype(f32))
+    np.add.at(gB, neg, (cj + reg * bj).astype(f32))
+    tU = np.zeros(U.shape[0], bool); tU[users] = True
+    tV = np.zeros(V.shape[0], bool); tV[pos] = True; tV[soc] = True; tV[neg] = True
+    return f32(total), gU, gV, gB, tU, tV
+
+
+class SBPRTrainer:
+    """CPU stand-in for SBPR.build_graph + the sess.run((loss, optimizer)) loop (SBPR.py:94-121)."""
+
+    def __init__(self, U, V, B, learner="adam", lr=1e-3, loss="bpr", reg=0.01):
+        self.U = np.array(U, dtype=f32); self.V = np.array(V, dtype=f32); self.B = np.array(B, dtype=f32)
+        self.learner, self.lr, self.loss, self.reg = learner, lr, loss, reg
+        i0, i1 = SLOT_INIT[learner]
+        mk = lambda a, v: None if v is None else np.full_like(a, v)
+        self.slots = [(mk(a, i0), mk(a, i1)) for a in (self.U, self.V, self.B)]
+        self.t = 0
+
+    def step(self, users, pos, soc, neg, suk):
+        l, gU, gV, gB, tU, tV = sbpr_grad(self.U, self.V, self.B, users, pos, soc, neg, suk, self.loss, self.reg)
+        hyper = DEFAULT_HYPER[self.learner](self.lr)
+        if self.learner == "adam":
+            hyper[0] = adam_lr_t(self.lr, 1, start_step=self.t)[0]
+        for var, g, (s0, s1), touched in ((self.U, gU, self.slots[0], tU), (self.V, gV, self.slots[1], tV),
+                                          (self.B, gB, self.slots[2], tV)):
+            opt_apply(self.learner, var, g, s0, s1, touched, hyper)
+        self.t += 1
+        return l
+
+    def epoch(self, users, pos, soc, neg, suk, batch_size):
+        n = len(users)
+        losses = []
+        for off in range(0, n, batch_size):
+            sl = slice(off, min(n, off + batch_size))
+            losses.append(self.step(users[sl], pos[sl], soc[sl], neg[sl], suk[sl]))
+        return np.asarray(losses, dtype=f32)
+
+
+# ----------------------------------------------------------------------------------------
 # LightGCN: LightGCN.py:35-78 (adjacency), 132-149 (propagation), 156-166 (loss)
 # ----------------------------------------------------------------------------------------
 def lightgcn_adj(train_indptr, train_indices, num_users, num_items, adj_type="pre"):

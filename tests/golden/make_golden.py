@@ -16,6 +16,9 @@ What is captured (all from the real reference code, imported through oracle.impo
   kat_surface.json    Configurator / DataIterator / sampler / metrics_info surface behaviour.
   gowalla_split.npz   (``python tests/golden/make_golden.py gowalla``) the 'given' split of
                       dataset/gowalla.{train,test} as loaded by data.Dataset (BASELINE config 3).
+  ciao_split.npz / kat_ciao.json   (``python tests/golden/make_golden.py ciao``) dataset/Ciao_u5_s2 as loaded by
+                      data.Dataset + SocialAbstractRecommender (trust CSR), SBPR._get_SocialItemsSet checksums and
+                      4 000 (user, social item, negative, s_uk) samples of one real SBPR._get_pairwise_all_data epoch.
   kat_gowalla.json / kat_gowalla_adj.npz   LightGCN.create_adj_mat('pre') (LightGCN.py:35-78) on that
                       split: nnz, row sums, value checksums; ProxyEvaluator strings for random
                       tables on all 29 858 test users and on a 512-user slice.
@@ -260,8 +263,60 @@ def gowalla():
     print("gowalla fixtures written to", OUT)
 
 
+def ciao():
+    """SBPR on dataset/Ciao_u5_s2 with the reference's own loader, social matrix
+    (SocialAbstractRecommender), social-item sets (SBPR._get_SocialItemsSet) and one real epoch of
+    SBPR._get_pairwise_all_data (glibc rand() + np.random streams: the VALUES are not reproducible by the product,
+    the (user, social item) -> s_uk relation and the membership constraints are)."""
+    import importlib
+    import zlib
+    import oracle
+    cwd = oracle.import_reference()
+    os.chdir(cwd)
+    sys.argv = ["main.py", "--recommender=SBPR", "--data.input.dataset=Ciao_u5_s2"]
+    np.random.seed(2018)
+    from util import Configurator
+    from data.dataset import Dataset
+    conf = Configurator("NeuRec.properties", default_section="hyperparameters")
+    ds = Dataset(conf)
+    m = importlib.import_module("model.social_recommender.SBPR")
+    model = m.SBPR(None, ds, conf)
+    tr, te = ds.train_matrix.tocsr(), ds.test_matrix.tocsr()
+    tr.sort_indices(); te.sort_indices()
+    trust = model.social_matrix.tocsr(); trust.sort_indices()
+    np.savez_compressed(os.path.join(OUT, "ciao_split.npz"), num_users=ds.num_users, num_items=ds.num_items,
+                        train_indptr=tr.indptr.astype(np.int32), train_indices=tr.indices.astype(np.int32),
+                        test_indptr=te.indptr.astype(np.int32), test_indices=te.indices.astype(np.int32),
+                        trust_indptr=trust.indptr.astype(np.int32), trust_indices=trust.indices.astype(np.int32))
+    social = model.userSocialItemsSetList
+    sptr = np.zeros(ds.num_users + 1, np.int64)
+    for u, items in social.items():
+        sptr[u + 1] = len(items)
+    sptr = np.cumsum(sptr)
+    sidx = np.concatenate([np.sort(np.asarray(social[u], np.int32)) for u in sorted(social)]) if social else np.zeros(0, np.int32)
+    users, pos, soc, neg, suk = (np.asarray(a) for a in model._get_pairwise_all_data())
+    pick = np.random.RandomState(0).choice(len(users), 4000, replace=False)
+    res = {"num_users": int(ds.num_users), "num_items": int(ds.num_items), "train_nnz": int(tr.nnz), "test_nnz": int(te.nnz),
+           "trust_nnz": int(trust.nnz), "users_with_social_items": len(social), "social_items_total": int(sptr[-1]),
+           "social_indptr_crc32": int(zlib.crc32(sptr.astype(np.int64).tobytes())),
+           "social_indices_crc32": int(zlib.crc32(sidx.astype(np.int32).tobytes())),
+           "epoch_samples": int(len(users)), "epoch_users_crc32": int(zlib.crc32(users.astype(np.int32).tobytes())),
+           "epoch_pos_crc32": int(zlib.crc32(pos.astype(np.int32).tobytes())),
+           "suk_mean": float(np.mean(suk)), "suk_max": int(np.max(suk)),
+           "suk_hist": np.bincount(suk.astype(np.int64), minlength=8)[:8].tolist(),
+           "sample_user": users[pick].astype(int).tolist(), "sample_social": soc[pick].astype(int).tolist(),
+           "sample_neg": neg[pick].astype(int).tolist(), "sample_suk": suk[pick].astype(int).tolist(),
+           "dataset_str": str(ds), "conf": {k: conf[k] for k in ("learning_rate", "embedding_size", "learner", "loss_function",
+                                                                  "num_epochs", "reg_mf", "batch_size", "init_method", "stddev")}}
+    with open(os.path.join(OUT, "kat_ciao.json"), "w") as fo:
+        json.dump(res, fo, indent=1)
+    print("ciao fixtures written to", OUT)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "gowalla":
         gowalla()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ciao":
+        ciao()
     else:
         main()

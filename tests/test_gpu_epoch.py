@@ -171,7 +171,7 @@ def test_fused_epoch_equals_the_two_kernel_epoch(ml100k):
 
 @pytest.fixture(params=["pipelined", "register"])
 def sgd_kernel(request):
-    """Both kernels behind nrc_mf_bpr_sgd_epoch: the bulk-copy pipeline (default) and the register form."""
+    """Both kernels behind nrc_mf_bpr_sgd_epoch: the register form (default) and the bulk-copy pipeline."""
     from neurec_b200 import ops
     before = ops.mf_sgd_set_pipelined(request.param == "pipelined")
     yield request.param
