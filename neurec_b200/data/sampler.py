@@ -164,3 +164,114 @@ class PointwiseSampler(_NegativeSamplerBase):
         for off in range(0, len(users), self.batch_size):
             sl = slice(off, off + self.batch_size)
             yield users[sl].tolist(), items[sl].tolist(), labels[sl].tolist()
+
+
+# ------------------------------------------------------------------------------------------------
+# Time-ordered samplers (data/sampler.py:42-68, 216-354) -- SURVEY.md 8(f) rank 4
+# ------------------------------------------------------------------------------------------------
+def _generative_time_order_positive_items(user_pos_dict, high_order=1):
+    """data/sampler.py:42-68: for a user's time-ordered items s, instance t is (s[t:t+high_order], s[t+high_order]).
+    -> (user_pos_len int64 [m, 2], users int32 [n], recent int32 [n] or [n, high_order], next items int32 [n])."""
+    if high_order <= 0:
+        raise ValueError("'high_order' must be a positive integer.")
+    if not isinstance(user_pos_dict, dict):
+        raise TypeError("'user_pos_dict' must be a dict.")
+    if not user_pos_dict:
+        raise ValueError("'user_pos_dict' cannot be empty.")
+    lens, users, recent, nxt = [], [], [], []
+    for user, seq in user_pos_dict.items():
+        seq = np.asarray(seq, dtype=np.int32)
+        m = len(seq) - high_order
+        if m <= 0:
+            continue
+        lens.append([user, m])
+        users.append(np.full(m, user, dtype=np.int32))
+        recent.append(seq[:m] if high_order == 1 else np.lib.stride_tricks.sliding_window_view(seq, high_order)[:m])
+        nxt.append(seq[high_order:])
+    if not lens:
+        width = () if high_order == 1 else (high_order,)
+        return (np.zeros((0, 2), np.int64), np.zeros(0, np.int32), np.zeros((0,) + width, np.int32), np.zeros(0, np.int32))
+    return (np.asarray(lens, dtype=np.int64), np.concatenate(users), np.ascontiguousarray(np.concatenate(recent)),
+            np.concatenate(nxt))
+
+
+class _TimeOrderBase(_NegativeSamplerBase):
+    """Shared state of the two time-ordered samplers: the device epoch is the Pairwise / Pointwise one over the
+    (user, next item) instances -- negatives uniform outside ALL of the user's train items (sampler.py:269-270,
+    338-339) -- plus the recent-items window of every instance, gathered on the device through the same keyed
+    bijection (nrc_shuffle_perm + nrc_gather_rows_i32) so that it stays aligned with the shuffled samples."""
+
+    def __init__(self, dataset, high_order, neg_num, batch_size, shuffle, drop_last, seed):
+        Sampler.__init__(self)
+        if high_order < 0:
+            raise ValueError("'high_order' must be a positive integer.")         # sampler.py:251-252,322-323
+        if neg_num <= 0:
+            raise ValueError("'neg_num' must be a positive integer.")            # sampler.py:253-254,324-325
+        self.batch_size, self.shuffle, self.drop_last = batch_size, shuffle, drop_last
+        self.neg_num, self.high_order = neg_num, high_order
+        self.item_num = dataset.num_items
+        self.user_pos_dict = dataset.get_user_train_dict(by_time=True)
+        self.user_pos_len, self._users_np, self._recent_np, self._pos_np = \
+            _generative_time_order_positive_items(self.user_pos_dict, high_order=high_order)
+        if max(len(v) for v in self.user_pos_dict.values()) >= self.item_num:
+            raise ValueError("The number of 'exclusion' is greater than 'high'.")  # pyx:32-33
+        self.seed, self.epoch = int(seed), -1
+        self._dev = None
+        self._recent_dev = None
+
+    def _device_recent(self, pairwise):
+        """The recent-items windows of the epoch just built, in its shuffled order (int32 CUDA tensor)."""
+        if self._recent_dev is None:
+            self._recent_dev = torch.from_numpy(self._recent_np).cuda()
+        perm = ops.shuffle_perm(self._n_samples(), self.seed, self.epoch, self.shuffle)[:self._n_used()]
+        return ops.gather_rows_i32(self._recent_dev, perm.contiguous())
+
+
+class TimeOrderPairwiseSampler(_TimeOrderBase):
+    """(users, recent_items, next_items, neg_items) batches (data/sampler.py:297-354)."""
+
+    def __init__(self, dataset, high_order=1, neg_num=1, batch_size=1024, shuffle=True, drop_last=False, seed=2018):
+        super().__init__(dataset, high_order, neg_num, batch_size, shuffle, drop_last, seed)
+        self.users_list, self.recent_items_list, self.pos_items_list = self._users_np, self._recent_np, self._pos_np
+
+    def _n_samples(self):
+        return len(self._users_np)
+
+    def device_epoch(self):
+        """Shuffled epoch as CUDA tensors: users [n], recent [n] or [n, high_order], next [n], neg [n] or [n, neg_num]."""
+        users, pos, neg = self._device_epoch(True)
+        return users, self._device_recent(True), pos, (neg.view(-1) if self.neg_num == 1 else neg)
+
+    def __iter__(self):
+        users, recent, pos, neg = (t.cpu().numpy() for t in self.device_epoch())
+        for off in range(0, len(users), self.batch_size):
+            sl = slice(off, off + self.batch_size)
+            yield users[sl].tolist(), recent[sl].tolist(), pos[sl].tolist(), neg[sl].tolist()
+
+
+class TimeOrderPointwiseSampler(_TimeOrderBase):
+    """(users, recent_items, items, labels) batches: the positives (label 1.0) then the k-th negatives of all
+    positives, k-major, users and windows repeated neg_num + 1 times (data/sampler.py:216-294)."""
+
+    def __init__(self, dataset, high_order=1, neg_num=1, batch_size=1024, shuffle=True, drop_last=False, seed=2018):
+        super().__init__(dataset, high_order, neg_num, batch_size, shuffle, drop_last, seed)
+        self.pos_items_list = self._pos_np
+        self.users_list = np.tile(self._users_np, self.neg_num + 1)
+        reps = (self.neg_num + 1,) + (1,) * (self._recent_np.ndim - 1)
+        self.recent_items_list = np.tile(self._recent_np, reps)
+        n_pos = len(self._pos_np)
+        self.all_labels = np.concatenate([np.ones(n_pos, np.float32), np.zeros(n_pos * self.neg_num, np.float32)])
+
+    def _n_samples(self):
+        return len(self._users_np) * (self.neg_num + 1)
+
+    def device_epoch(self):
+        """Shuffled epoch as CUDA tensors: users [n] i32, recent [n(, high_order)] i32, items [n] i32, labels [n] f32."""
+        users, items, labels = self._device_epoch(False)
+        return users, self._device_recent(False), items, labels
+
+    def __iter__(self):
+        users, recent, items, labels = (t.cpu().numpy() for t in self.device_epoch())
+        for off in range(0, len(users), self.batch_size):
+            sl = slice(off, off + self.batch_size)
+            yield users[sl].tolist(), recent[sl].tolist(), items[sl].tolist(), labels[sl].tolist()
