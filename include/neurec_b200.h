@@ -716,6 +716,32 @@ int nrc_csr_from_coo(const int32_t* rows, const int32_t* cols, int64_t nnz, int3
                      int64_t* out_indptr, int32_t* out_indices, int64_t* work_i64, int32_t* work_i32,
                      int32_t* bad_flag, void* stream);
 
+/* SpectralCF, model/general_recommender/SpectralCF.py:63-91.  a_hat f32 [N, N] (N = users + items, users first) is
+ * the constant dense operator U U^T + U diag(lamda) U^T the reference builds with numpy at construction (:37-43,
+ * 67-69); filters f32 [num_layers, dim, dim]; activation ids follow util/tool.py:10-33 (softmax is not provided:
+ * NRC_E_NOTIMPL, like an unknown name).  dim <= 128, num_layers <= 8. */
+#define NRC_ACT_IDENTITY 0
+#define NRC_ACT_SIGMOID 1
+#define NRC_ACT_TANH 2
+#define NRC_ACT_RELU 3
+#define NRC_ACT_ELU 4
+#define NRC_ACT_SELU 5
+int64_t nrc_spectralcf_work_floats(int32_t num_nodes, int32_t dim, int32_t num_layers);
+/* _create_inference (:63-83): all_emb f32 [N, dim * (num_layers + 1)] = [E_0 | E_1 | ...], E_k = act((a_hat E_{k-1}) W_k). */
+int nrc_spectralcf_forward(int32_t num_nodes, int32_t dim, int32_t num_layers, const float* a_hat, const float* e0,
+                           const float* filters, int32_t activation, float* all_emb, float* work, void* stream);
+/* One batch of _create_loss (:85-91) and the backward of the whole graph: forward as above, learner.pairwise_loss on
+ * the concatenated rows + reg * l2_loss(u, i, j), then back through concat / activation / both products per layer.
+ * a_hat_t: a_hat transposed, or NULL (the kernel then reads a_hat with transposed indexing).  grad_all f32
+ * [N, dim * (num_layers + 1)] must be zero on entry and is zero on return; touched i32 [N] scratch; grad_e0 f32
+ * [N, dim] and grad_filters f32 [num_layers, dim, dim] are overwritten; *loss += the batch loss.  Apply with
+ * nrc_opt_apply_multi (dense-gradient formulas: every variable's gradient flows through tf.matmul). */
+int nrc_spectralcf_grad(int32_t num_users, int32_t num_items, int32_t dim, int32_t num_layers, const float* a_hat,
+                        const float* a_hat_t, const float* e0, const float* filters, int32_t activation,
+                        const int32_t* users, const int32_t* pos_items, const int32_t* neg_items, int64_t batch,
+                        int32_t loss_kind, float reg, float* all_emb, float* grad_all, int32_t* touched,
+                        float* grad_e0, float* grad_filters, float* work, float* loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,14 +17,24 @@ Like the reference's global ``rand()`` / ``np.random`` state, the stream positio
 every epoch drawn by ANY sampler takes the next epoch number, so a model that builds a new sampler
 per epoch (MLP.py:100) still sees fresh negatives.
 """
-import itertools
-
 import numpy as np
 import torch
 
 from .. import ops
 
-_EPOCH_COUNTER = itertools.count()      # process-wide stream position (the reference's global RNG state)
+class _StreamPosition(object):
+    """Process-wide position of the sampler stream (the analogue of the reference's global rand() / np.random state)."""
+
+    def __init__(self, first=0):
+        self.value = int(first)
+
+    def __next__(self):
+        v = self.value
+        self.value += 1
+        return v
+
+
+_EPOCH_COUNTER = _StreamPosition()
 
 
 def _EPOCH_COUNTER_NEXT():
@@ -35,7 +45,7 @@ def _EPOCH_COUNTER_NEXT():
 def reseed(first_epoch=0):
     """Restart the process-wide epoch numbering (tests; the analogue of re-seeding np.random)."""
     global _EPOCH_COUNTER
-    _EPOCH_COUNTER = itertools.count(int(first_epoch))
+    _EPOCH_COUNTER = _StreamPosition(first_epoch)
 
 
 class Sampler(object):

@@ -757,3 +757,43 @@ def csr_from_coo(rows, cols, num_rows, num_cols):
     if int(bad.item()):
         raise ValueError("interaction ids outside [0, %d) x [0, %d)" % (num_rows, num_cols))
     return indptr, indices[:int(indptr[-1].item())]
+
+
+ACT_IDS = {"identity": 0, "sigmoid": 1, "tanh": 2, "relu": 3, "elu": 4, "selu": 5}
+
+
+def _act_id(name):
+    if name not in ACT_IDS:
+        raise NotImplementedError("ERROR")                      # util/tool.py:32-33
+    return ACT_IDS[name]
+
+
+def spectralcf_work(num_nodes, dim, num_layers, device="cuda"):
+    n = int(_lib.load().nrc_spectralcf_work_floats(int(num_nodes), int(dim), int(num_layers)))
+    return torch.empty((max(n, 1),), dtype=torch.float32, device=device)
+
+
+def spectralcf_forward(a_hat, e0, filters, activation, all_emb=None, work=None):
+    """SpectralCF._create_inference (SpectralCF.py:63-83): [E_0 | act((A_hat E_0) W_1) | ...] f32 [N, d (K + 1)]."""
+    _req(a_hat, torch.float32, "a_hat"); _req(e0, torch.float32, "e0"); _req(filters, torch.float32, "filters")
+    N, d = e0.shape
+    K = filters.shape[0]
+    if all_emb is None:
+        all_emb = torch.empty((N, d * (K + 1)), dtype=torch.float32, device=e0.device)
+    work = spectralcf_work(N, d, K, e0.device) if work is None else work
+    check(_lib.load().nrc_spectralcf_forward(N, d, K, _p(a_hat), _p(e0), _p(filters), _act_id(activation), _p(all_emb),
+                                             _p(work), _stream()))
+    _count(1 + 2 * K)
+    return all_emb
+
+
+def spectralcf_grad(num_users, a_hat, a_hat_t, e0, filters, activation, users, pos, neg, loss, reg, all_emb, grad_all,
+                    touched, grad_e0, grad_filters, work, loss_out):
+    """One batch of SpectralCF's loss + backward (nrc_spectralcf_grad)."""
+    N, d = e0.shape
+    K = filters.shape[0]
+    check(_lib.load().nrc_spectralcf_grad(int(num_users), N - int(num_users), d, K, _p(a_hat), _p(a_hat_t), _p(e0),
+                                          _p(filters), _act_id(activation), _p(users), _p(pos), _p(neg), users.numel(),
+                                          LOSS_IDS[loss.lower()], float(reg), _p(all_emb), _p(grad_all), _p(touched),
+                                          _p(grad_e0), _p(grad_filters), _p(work), _p(loss_out), _stream()))
+    _count(3 + 6 * K)

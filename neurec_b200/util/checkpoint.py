@@ -8,8 +8,6 @@ stamp counter and the position of the process-wide sampler stream (data/sampler.
 of the reference's global rand() / np.random state).  ``save`` writes one ``torch.save`` file (CPU tensors);
 ``load`` copies into the tensors ``build_graph`` allocated, so a resumed run continues bit for bit.
 """
-import itertools
-
 import torch
 
 from ..data import sampler as _sampler
@@ -40,7 +38,7 @@ def _walk(obj, prefix=""):
 
 
 def _stream_position():
-    return _sampler._EPOCH_COUNTER.__reduce__()[1][0]          # next value of the itertools.count
+    return _sampler._EPOCH_COUNTER.value
 
 
 def state_dict(model):
@@ -89,6 +87,6 @@ def load(model, path):
             raise ValueError("'%s': checkpoint %s %s, model %s %s" % (name, tuple(saved.shape), saved.dtype,
                                                                     tuple(live[name].shape), live[name].dtype))
         live[name].copy_(saved)
-    _sampler._EPOCH_COUNTER = itertools.count(int(meta["sampler_stream"]))
+    _sampler.reseed(int(meta["sampler_stream"]))
     torch.cuda.synchronize()
     return meta

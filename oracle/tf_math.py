@@ -285,6 +285,147 @@ class SBPRTrainer:
 
 
 # ----------------------------------------------------------------------------------------
+# SpectralCF (general_recommender/SpectralCF.py:37-43, 63-91, 108-128) -- SURVEY.md 8(f) rank 3
+# ----------------------------------------------------------------------------------------
+def spectralcf_a_hat(train_indptr, train_indices, num_users, num_items):
+    """The dense spectral operator of SpectralCF: A = I + bipartite adjacency (:108-114), D = row sums (:116-119),
+    L = I - D^-1 A (:121-128), (lamda, U) = eig(L) (:41-42), A_hat = U U^T + U diag(lamda) U^T cast to fp32 (:67-69;
+    a complex result of eig loses its imaginary part in that cast, as in the reference)."""
+    nu, ni = int(num_users), int(num_items)
+    n = nu + ni
+    graph = np.zeros((nu, ni), dtype=f32)
+    rows = np.repeat(np.arange(nu), np.diff(np.asarray(train_indptr)))
+    graph[rows, np.asarray(train_indices)] = 1.0
+    A = np.zeros((n, n), dtype=f32)
+    A[:nu, nu:] = graph
+    A[nu:, :nu] = graph.T
+    A = np.identity(n, dtype=f32) + A
+    D = A.sum(axis=1)
+    L = np.identity(n, dtype=f32) - np.dot(np.diag(np.power(D, -1)), A)
+    lamda, U = np.linalg.eig(L)
+    lamda = np.diag(lamda)
+    A_hat = np.dot(U, U.T) + np.dot(np.dot(U, lamda), U.T)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return np.ascontiguousarray(A_hat.astype(f32))
+
+
+_SELU_SCALE, _SELU_ALPHA = 1.0507009873554805, 1.6732632423543772
+
+
+def activation(act, z):
+    """tool.activation_function (util/tool.py:10-33) -> fp value of the same dtype."""
+    z = np.asarray(z)
+    one = z.dtype.type(1)
+    if act == "sigmoid":
+        return one / (one + np.exp(-z))
+    if act == "tanh":
+        return np.tanh(z)
+    if act == "relu":
+        return np.maximum(z, 0)
+    if act == "elu":
+        return np.where(z > 0, z, np.exp(np.minimum(z, 0)) - one)
+    if act == "identity":
+        return z
+    if act == "selu":
+        return (z.dtype.type(_SELU_SCALE) * np.where(z > 0, z, z.dtype.type(_SELU_ALPHA) * (np.exp(np.minimum(z, 0)) - one))).astype(z.dtype)
+    raise NotImplementedError("ERROR")
+
+
+def activation_grad_from_output(act, y):
+    """d act / d z written in terms of the OUTPUT y (what the backward kernel has at hand)."""
+    y = np.asarray(y)
+    one = y.dtype.type(1)
+    if act == "sigmoid":
+        return y * (one - y)
+    if act == "tanh":
+        return one - y * y
+    if act == "relu":
+        return (y > 0).astype(y.dtype)
+    if act == "elu":
+        return np.where(y > 0, one, y + one)
+    if act == "identity":
+        return np.ones_like(y)
+    if act == "selu":
+        return np.where(y > 0, y.dtype.type(_SELU_SCALE), y + y.dtype.type(_SELU_SCALE * _SELU_ALPHA))
+    raise NotImplementedError("ERROR")
+
+
+def spectralcf_forward(A_hat, e0, filters, act="sigmoid"):
+    """SpectralCF._create_inference (:63-83): E_k = act((A_hat E_{k-1}) W_k); returns (all_emb [N, d (K+1)], [S_k])."""
+    emb = np.asarray(e0)
+    all_emb, sides = [emb], []
+    for W in filters:
+        side = A_hat.astype(emb.dtype) @ emb
+        emb = activation(act, side @ W)
+        sides.append(side)
+        all_emb.append(emb)
+    return np.concatenate(all_emb, axis=1), sides
+
+
+def spectralcf_loss_and_grad(A_hat, e0, filters, num_users, users, pos, neg, reg, loss="bpr", act="sigmoid"):
+    """Loss (:85-91: pairwise_loss on the concatenated rows + reg * l2_loss(u, i, j)) and its gradient w.r.t. the
+    embedding table and every filter -- all dense (they flow through tf.matmul with A_hat)."""
+    A = A_hat.astype(np.asarray(e0).dtype)
+    all_emb, sides = spectralcf_forward(A, e0, filters, act)
+    dt = all_emb.dtype.type
+    d = e0.shape[1]
+    ue, ie = all_emb[:num_users], all_emb[num_users:]
+    pu, qi, qj = ue[users], ie[pos], ie[neg]
+    x = (pu * qi).sum(1) - (pu * qj).sum(1)
+    if all_emb.dtype == f32:
+        l, g = pairwise_loss_and_grad(loss.lower(), x)
+    else:
+        l = {"bpr": np.log1p(np.exp(-x)), "hinge": np.maximum(x + 1, 0), "square": (1 - x) ** 2}[loss.lower()]
+        g = {"bpr": -1 / (1 + np.exp(x)), "hinge": (x + 1 > 0).astype(x.dtype), "square": -2 * (1 - x)}[loss.lower()]
+    reg = dt(reg)
+    total = l.sum() + reg * dt(0.5) * ((pu * pu).sum() + (qi * qi).sum() + (qj * qj).sum())
+    G = np.zeros_like(all_emb)
+    g = g[:, None].astype(all_emb.dtype)
+    np.add.at(G, users, g * (qi - qj) + reg * pu)
+    np.add.at(G, num_users + np.asarray(pos), g * pu + reg * qi)
+    np.add.at(G, num_users + np.asarray(neg), -g * pu + reg * qj)
+    K = len(filters)
+    dW = [None] * K
+    carry = np.zeros((all_emb.shape[0], d), dtype=all_emb.dtype)
+    for k in range(K, 0, -1):
+        Ek = all_emb[:, k * d:(k + 1) * d]
+        dZ = (G[:, k * d:(k + 1) * d] + carry) * activation_grad_from_output(act, Ek)
+        dW[k - 1] = sides[k - 1].T @ dZ
+        carry = A.T @ (dZ @ filters[k - 1].T)
+    dE0 = G[:, :d] + carry
+    return total, dE0, dW, all_emb
+
+
+class SpectralCFTrainer:
+    """SpectralCF.train_model's step on the restatement: dense TF-1.12 optimizer over the table and every filter."""
+
+    def __init__(self, A_hat, e0, filters, num_users, learner="adam", lr=1e-3, reg=1e-3, loss="bpr", act="sigmoid"):
+        self.A = np.asarray(A_hat, f32)
+        self.e0 = np.array(e0, f32); self.filters = [np.array(W, f32) for W in filters]
+        self.nu, self.learner, self.lr, self.reg, self.loss, self.act = num_users, learner, lr, reg, loss, act
+        i0, i1 = SLOT_INIT[learner]
+        mk = lambda a, v: None if v is None else np.full_like(a, v)
+        self.slots = [(mk(a, i0), mk(a, i1)) for a in [self.e0] + self.filters]
+        self.t = 0
+
+    def step(self, users, pos, neg):
+        l, dE0, dW, _ = spectralcf_loss_and_grad(self.A, self.e0, self.filters, self.nu, users, pos, neg, self.reg,
+                                                 self.loss, self.act)
+        hyper = DEFAULT_HYPER[self.learner](self.lr)
+        if self.learner == "adam":
+            hyper[0] = adam_lr_t(self.lr, 1, start_step=self.t)[0]
+        for var, g, (s0, s1) in zip([self.e0] + self.filters, [dE0] + dW, self.slots):
+            opt_apply(self.learner, var, np.asarray(g, f32), s0, s1, None, hyper, dense_var=True)
+        self.t += 1
+        return f32(l)
+
+    def embeddings(self):
+        return spectralcf_forward(self.A, self.e0, self.filters, self.act)[0]
+
+
+# ----------------------------------------------------------------------------------------
 # LightGCN: LightGCN.py:35-78 (adjacency), 132-149 (propagation), 156-166 (loss)
 # ----------------------------------------------------------------------------------------
 def lightgcn_adj(train_indptr, train_indices, num_users, num_items, adj_type="pre"):
