@@ -716,6 +716,15 @@ int nrc_csr_from_coo(const int32_t* rows, const int32_t* cols, int64_t nnz, int3
                      int64_t* out_indptr, int32_t* out_indices, int64_t* work_i64, int32_t* work_i32,
                      int32_t* bad_flag, void* stream);
 
+/* split_by_ratio / split_by_loo, data/utils.py:59-106, on the device: every user's interactions ordered by `keys`
+ * (i64 [n] interaction times, by_time=True) or, when keys is NULL (by_time=False), by a counter-based random word
+ * keyed by `seed` (DataFrame.sample(frac=1)); ties by input position; the first ceil(ratio * n_u) (mode 0) or all but
+ * the last when n_u > 3 (mode 1, leave-one-out) go to the train set.  users i32 [n] dense ids; is_train i32 [n] <- 1/0.
+ * Scratch work_i64 [2 * (num_users + 1)], work_i32 [n]; *bad_flag (device i32) = 1 on an out-of-range user id. */
+int nrc_split_interactions(const int32_t* users, const int64_t* keys, int64_t n, int32_t num_users, int32_t mode,
+                           double ratio, uint64_t seed, int32_t* is_train, int64_t* work_i64, int32_t* work_i32,
+                           int32_t* bad_flag, void* stream);
+
 /* SpectralCF, model/general_recommender/SpectralCF.py:63-91.  a_hat f32 [N, N] (N = users + items, users first) is
  * the constant dense operator U U^T + U diag(lamda) U^T the reference builds with numpy at construction (:37-43,
  * 67-69); filters f32 [num_layers, dim, dim]; activation ids follow util/tool.py:10-33 (softmax is not provided:

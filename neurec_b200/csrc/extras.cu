@@ -272,6 +272,59 @@ csr_compact_rows_kernel(const int64_t* __restrict__ ptr, const int64_t* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-user train / test split (data/utils.py:59-106): order every user's interactions by key -- the interaction time
+// (by_time=True) or a counter-based random word (by_time=False: DataFrame.sample(frac=1), a uniformly random order) --
+// ties by position in the input, and send the first cut(n_u) to the train set:
+//   ratio  cut = ceil(ratio * n_u)                        (split_by_ratio, :59-80)
+//   loo    cut = n_u if n_u <= 3 else n_u - 1             (split_by_loo, :83-106)
+// One warp per user, rank by counting (rows are short).
+// ---------------------------------------------------------------------------------------------
+__global__ void index_scatter_kernel(const int32_t* __restrict__ rows, int64_t n, int32_t num_rows, const int64_t* __restrict__ ptr,
+                                     int64_t* __restrict__ cursor, int32_t* __restrict__ out) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t r = rows[e];
+        if (r < 0 || r >= num_rows) continue;
+        const int64_t slot = (int64_t)atomicAdd(reinterpret_cast<unsigned long long*>(cursor + r), 1ull);
+        out[ptr[r] + slot] = (int32_t)e;
+    }
+}
+
+__global__ void coo_count_rows_kernel(const int32_t* __restrict__ rows, int64_t n, int32_t num_rows, int64_t* __restrict__ cnt,
+                                      int32_t* __restrict__ bad) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t r = rows[e];
+        if (r < 0 || r >= num_rows) { *bad = 1; continue; }
+        atomicAdd(reinterpret_cast<unsigned long long*>(cnt + r + 1), 1ull);
+    }
+}
+
+constexpr uint64_t kSplitStream = 0x53504C4954000000ull;    // 'SPLIT'
+
+__global__ void __launch_bounds__(256)
+split_rank_kernel(const int64_t* __restrict__ ptr, int32_t num_users, const int32_t* __restrict__ seg, const int64_t* __restrict__ keys,
+                  int mode, double ratio, uint64_t seed, int32_t* __restrict__ is_train) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wpb = blockDim.x >> 5;
+    for (int64_t u = blockIdx.x * wpb + (threadIdx.x >> 5); u < num_users; u += (int64_t)gridDim.x * wpb) {
+        const int64_t b = ptr[u], n = ptr[u + 1] - b;
+        const int64_t cut = mode == 0 ? (int64_t)ceil(ratio * (double)n) : (n <= 3 ? n : n - 1);
+        for (int64_t e = lane; e < n; e += kWarp) {
+            const int32_t me = seg[b + e];
+            // keys are compared as unsigned 64-bit words: times are shifted by 2^63 to keep their signed order
+            const uint64_t ke = keys ? ((uint64_t)keys[me] ^ 0x8000000000000000ull) : philox_word((uint64_t)me, 0, seed, kSplitStream);
+            int64_t rank = 0;
+            for (int64_t q = 0; q < n; ++q) {
+                const int32_t other = __ldg(seg + b + q);
+                const uint64_t kq = keys ? ((uint64_t)__ldg(keys + other) ^ 0x8000000000000000ull)
+                                         : philox_word((uint64_t)other, 0, seed, kSplitStream);
+                rank += (kq < ke) || (kq == ke && other < me);
+            }
+            is_train[me] = rank < cut ? 1 : 0;
+        }
+    }
+}
+
 static unsigned grid_for(int64_t work_items, int per_block) {
     int64_t blocks = (work_items + per_block - 1) / per_block;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -409,6 +462,31 @@ extern "C" int nrc_csr_from_coo(const int32_t* rows, const int32_t* cols, int64_
     csr_sort_rows_kernel<<<grid_for(num_rows, 8), 256, 0, st>>>(raw_ptr, num_rows, scattered, sorted, out_indptr);
     scan_i64_kernel<<<1, 1024, 0, st>>>(out_indptr, num_rows);
     csr_compact_rows_kernel<<<grid_for(num_rows, 8), 256, 0, st>>>(raw_ptr, out_indptr, num_rows, sorted, out_indices);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+// data/utils.py:59-106 on the device.  users i32 [n] (dense ids); keys i64 [n] = interaction times (by_time=True) or NULL
+// (by_time=False: counter-based random order keyed by `seed`); mode 0 = ratio, 1 = leave-one-out.  is_train i32 [n]
+// receives 1 / 0 per interaction (interactions of out-of-range users are left untouched and *bad_flag is set).
+// Scratch: work_i64 [2 * (num_users + 1)], work_i32 [n].
+extern "C" int nrc_split_interactions(const int32_t* users, const int64_t* keys, int64_t n, int32_t num_users, int32_t mode,
+                                      double ratio, uint64_t seed, int32_t* is_train, int64_t* work_i64, int32_t* work_i32,
+                                      int32_t* bad_flag, void* stream) {
+    NRC_REQUIRE(num_users > 0 && n >= 0, NRC_E_VALUE, "num_users > 0 and n >= 0 required");
+    NRC_REQUIRE(mode == 0 || mode == 1, NRC_E_VALUE, "There is not splitter '%d'", mode);       // dataset.py:160-161
+    NRC_REQUIRE(mode == 1 || (ratio >= 0.0 && ratio <= 1.0), NRC_E_VALUE, "ratio %f outside [0, 1]", ratio);
+    cudaStream_t st = as_stream(stream);
+    int64_t* ptr = work_i64;
+    int64_t* cursor = work_i64 + (num_users + 1);
+    NRC_CUDA_CHECK(cudaMemsetAsync(ptr, 0, (size_t)(num_users + 1) * 8, st));
+    NRC_CUDA_CHECK(cudaMemsetAsync(cursor, 0, (size_t)(num_users + 1) * 8, st));
+    NRC_CUDA_CHECK(cudaMemsetAsync(bad_flag, 0, 4, st));
+    if (n == 0) return NRC_OK;
+    coo_count_rows_kernel<<<grid_for(n, 256), 256, 0, st>>>(users, n, num_users, ptr, bad_flag);
+    scan_i64_kernel<<<1, 1024, 0, st>>>(ptr, num_users);
+    index_scatter_kernel<<<grid_for(n, 256), 256, 0, st>>>(users, n, num_users, ptr, cursor, work_i32);
+    split_rank_kernel<<<grid_for(num_users, 8), 256, 0, st>>>(ptr, num_users, work_i32, keys, mode, ratio, seed, is_train);
     NRC_CUDA_CHECK(cudaGetLastError());
     return NRC_OK;
 }

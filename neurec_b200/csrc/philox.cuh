@@ -22,15 +22,19 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return Philox4{c0, c1, c2, c3};
 }
 
+// k-th 64-bit word of output element `elem`
+__device__ __forceinline__ uint64_t philox_word(uint64_t elem, uint32_t k, uint64_t seed, uint64_t stream_id) {
+    const Philox4 r = philox4x32_10((uint32_t)elem, (uint32_t)(elem >> 32), k >> 1,
+                                    (uint32_t)stream_id, (uint32_t)seed,
+                                    (uint32_t)(seed >> 32) ^ (uint32_t)(stream_id >> 32));
+    return (k & 1u) ? (((uint64_t)r.w << 32) | r.z) : (((uint64_t)r.y << 32) | r.x);
+}
+
 // k-th candidate of output element `elem`: 64 random bits reduced modulo `high`
 // (random_choice.pyx:53 `a = llrand() % c_high`).
 __device__ __forceinline__ int32_t philox_candidate(uint64_t elem, uint32_t k, uint64_t seed,
                                                     uint64_t stream_id, int32_t high) {
-    const Philox4 r = philox4x32_10((uint32_t)elem, (uint32_t)(elem >> 32), k >> 1,
-                                    (uint32_t)stream_id, (uint32_t)seed,
-                                    (uint32_t)(seed >> 32) ^ (uint32_t)(stream_id >> 32));
-    const uint64_t word = (k & 1u) ? (((uint64_t)r.w << 32) | r.z) : (((uint64_t)r.y << 32) | r.x);
-    return (int32_t)(word % (uint64_t)high);
+    return (int32_t)(philox_word(elem, k, seed, stream_id) % (uint64_t)high);
 }
 
 // First candidate not contained in the sorted exclusion row; -1 when the row excludes

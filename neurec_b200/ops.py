@@ -797,3 +797,24 @@ def spectralcf_grad(num_users, a_hat, a_hat_t, e0, filters, activation, users, p
                                           LOSS_IDS[loss.lower()], float(reg), _p(all_emb), _p(grad_all), _p(touched),
                                           _p(grad_e0), _p(grad_filters), _p(work), _p(loss_out), _stream()))
     _count(3 + 6 * K)
+
+
+def split_interactions(users, keys, num_users, mode="ratio", ratio=0.8, seed=0):
+    """Per-user train / test split of an interaction list on the device (data/utils.py:59-106): int32 [n] of 1 (train)
+    / 0 (test).  keys: int64 CUDA tensor of interaction times (by_time=True) or None (by_time=False)."""
+    _req(users, torch.int32, "users")
+    if keys is not None:
+        _req(keys, torch.int64, "keys")
+    if mode not in ("ratio", "loo"):
+        raise ValueError("There is not splitter '%s'" % mode)             # dataset.py:160-161
+    n, dev = users.numel(), users.device
+    out = torch.zeros((n,), dtype=torch.int32, device=dev)
+    w64 = torch.empty((2 * (int(num_users) + 1),), dtype=torch.int64, device=dev)
+    w32 = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+    bad = torch.empty((1,), dtype=torch.int32, device=dev)
+    check(_lib.load().nrc_split_interactions(_p(users), _p(keys), n, int(num_users), 0 if mode == "ratio" else 1,
+                                             float(ratio), int(seed), _p(out), _p(w64), _p(w32), _p(bad), _stream()))
+    _count(4)
+    if int(bad.item()):
+        raise ValueError("user ids outside [0, %d)" % num_users)
+    return out

@@ -309,6 +309,32 @@ def csr_from_coo(rows, cols, num_rows):
     return np.cumsum(indptr), c.astype(np.int32)
 
 
+def split_interactions(users, keys, num_users, mode="ratio", ratio=0.8, seed=0):
+    """split_by_ratio / split_by_loo (data/utils.py:59-106) per interaction: 1 = train, 0 = test.  keys = interaction
+    times (by_time=True) or None (by_time=False: the product's counter-based random order, seed-keyed); ties by input
+    position; cut = ceil(ratio * n_u), or n_u - 1 when n_u > 3 for leave-one-out."""
+    import math
+    users = np.asarray(users, np.int64)
+    n = len(users)
+    if keys is None:
+        k = np.empty(n, np.uint64)
+        lib().orc_philox_words(ctypes.c_int64(n), ctypes.c_uint64(seed), ctypes.c_uint64(0x53504C4954000000),
+                               k.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
+    else:
+        k = (np.asarray(keys, np.int64).view(np.uint64) ^ np.uint64(1 << 63))
+    order = np.lexsort((np.arange(n), k, users))            # by user, then key, then input position
+    out = np.zeros(n, np.int32)
+    counts = np.bincount(users, minlength=num_users)
+    start = 0
+    for u in range(num_users):
+        c = int(counts[u])
+        if c:
+            cut = math.ceil(ratio * c) if mode == "ratio" else (c if c <= 3 else c - 1)
+            out[order[start:start + cut]] = 1
+        start += c
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # Importing the REAL Python reference (build container only; never on the GPU box)
 # ----------------------------------------------------------------------------------------

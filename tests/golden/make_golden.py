@@ -19,6 +19,8 @@ What is captured (all from the real reference code, imported through oracle.impo
   ciao_split.npz / kat_ciao.json   (``python tests/golden/make_golden.py ciao``) dataset/Ciao_u5_s2 as loaded by
                       data.Dataset + SocialAbstractRecommender (trust CSR), SBPR._get_SocialItemsSet checksums and
                       4 000 (user, social item, negative, s_uk) samples of one real SBPR._get_pairwise_all_data epoch.
+  kat_split_ml100k.npz  (``python tests/golden/make_golden.py split``) data/utils.py split_by_ratio(0.8) and split_by_loo with
+                      by_time=True on ml-100k.rating: one train/test bit per interaction in file order.
   kat_gowalla.json / kat_gowalla_adj.npz   LightGCN.create_adj_mat('pre') (LightGCN.py:35-78) on that
                       split: nnz, row sums, value checksums; ProxyEvaluator strings for random
                       tables on all 29 858 test users and on a 512-user slice.
@@ -313,8 +315,37 @@ def ciao():
     print("ciao fixtures written to", OUT)
 
 
+def split():
+    """the reference's own split_by_ratio / split_by_loo (data/utils.py:59-106) with by_time=True
+    on dataset/ml-100k.rating -> one train/test bit per interaction in FILE order (bit-packed)."""
+    import oracle
+    cwd = oracle.import_reference()
+    os.chdir(cwd)
+    import pandas as pd
+    from data.utils import load_data, split_by_loo, split_by_ratio
+    path = os.path.join("/root/reference", "dataset", "ml-100k.rating")
+    cols = ["user", "item", "rating", "time"]
+    out = {}
+    for name, fn in (("ratio", lambda d: split_by_ratio(d, ratio=0.8, by_time=True)), ("loo", lambda d: split_by_loo(d, by_time=True))):
+        data = load_data(path, "\t", cols)
+        key = data["user"].astype(np.int64) * 1000003 + data["item"].astype(np.int64)
+        assert key.is_unique
+        train, test = fn(data.copy())
+        tkey = set((train["user"].astype(np.int64) * 1000003 + train["item"].astype(np.int64)).tolist())
+        flags = np.fromiter((k in tkey for k in key.tolist()), dtype=np.uint8, count=len(key))
+        assert len(train) + len(test) == len(data) and int(flags.sum()) == len(train)
+        out[name] = np.packbits(flags)
+        out[name + "_train"] = np.int64(len(train))
+    data = load_data(path, "\t", cols)                       # the inputs of the split, in file order (raw user ids, times)
+    np.savez_compressed(os.path.join(OUT, "kat_split_ml100k.npz"), n=np.int64(len(data)),
+                        user=data["user"].values.astype(np.uint16), time=data["time"].values.astype(np.int32), **out)
+    print("split fixtures written to", OUT, {k: int(v) for k, v in out.items() if k.endswith("_train")})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "gowalla":
+    if len(sys.argv) > 1 and sys.argv[1] == "split":
+        split()
+    elif len(sys.argv) > 1 and sys.argv[1] == "gowalla":
         gowalla()
     elif len(sys.argv) > 1 and sys.argv[1] == "ciao":
         ciao()

@@ -190,3 +190,103 @@ def test_time_order_instances_follow_the_reference_loop():
         gen([1, 2], 1)
     with pytest.raises(ValueError):
         gen({}, 1)
+
+
+# ------------------------------------------------------------------------------------------------ SpectralCF
+def _spectral_problem(dtype, seed=0, nu=9, ni=13, d=5, K=2):
+    rs = np.random.RandomState(seed)
+    rows = [np.sort(rs.choice(ni, rs.randint(1, 5), replace=False)) for _ in range(nu)]
+    ptr = np.cumsum([0] + [len(r) for r in rows]); idx = np.concatenate(rows)
+    A = tf_math.spectralcf_a_hat(ptr, idx, nu, ni).astype(dtype)
+    e0 = (rs.randn(nu + ni, d) * 0.3).astype(dtype)
+    W = [(rs.randn(d, d) * 0.4).astype(dtype) for _ in range(K)]
+    users = rs.randint(0, nu, 7); pos = rs.randint(0, ni, 7); neg = rs.randint(0, ni, 7)
+    return ptr, idx, A, e0, W, nu, users, pos, neg
+
+
+@pytest.mark.parametrize("act", ["sigmoid", "tanh", "relu", "elu", "identity", "selu"])
+def test_spectralcf_gradients_match_finite_differences(act):
+    """Manual backprop of SpectralCF.py:63-91 (concat, activation, filter product, dense spectral product) against
+    central differences in fp64 -- for every activation of util/tool.py:10-33 the kernels provide."""
+    _, _, A, e0, W, nu, users, pos, neg = _spectral_problem(np.float64)
+    total = lambda e, w: tf_math.spectralcf_loss_and_grad(A, e, w, nu, users, pos, neg, 0.05, "bpr", act)[0]
+    _, dE0, dW, _ = tf_math.spectralcf_loss_and_grad(A, e0, W, nu, users, pos, neg, 0.05, "bpr", act)
+    rs = np.random.RandomState(1)
+    h = 1e-6
+    for _ in range(12):
+        r, c = rs.randint(e0.shape[0]), rs.randint(e0.shape[1])
+        p, m = e0.copy(), e0.copy(); p[r, c] += h; m[r, c] -= h
+        fd = (total(p, W) - total(m, W)) / (2 * h)
+        assert abs(fd - dE0[r, c]) < 1e-6 * max(1.0, abs(fd))
+    for k in range(len(W)):
+        for _ in range(6):
+            r, c = rs.randint(W[k].shape[0]), rs.randint(W[k].shape[1])
+            Wp = [w.copy() for w in W]; Wm = [w.copy() for w in W]; Wp[k][r, c] += h; Wm[k][r, c] -= h
+            fd = (total(e0, Wp) - total(e0, Wm)) / (2 * h)
+            assert abs(fd - dW[k][r, c]) < 1e-6 * max(1.0, abs(fd))
+    with pytest.raises(NotImplementedError):
+        tf_math.activation("softplus", e0)
+
+
+def test_spectral_operator_of_the_product_equals_the_restatement():
+    """SpectralCF.__init__ (:37-43) + A_hat (:67-69): the plug-in's host-side construction and the oracle's, same bits;
+    the operator is symmetric up to rounding and A_hat 1 = (1 + eigen-part) behaves like a smoothing operator."""
+    from neurec_b200.model.general_recommender.SpectralCF import spectral_operator
+    ptr, idx, A, *_ = _spectral_problem(np.float32, nu=14, ni=19)
+    train = sp.csr_matrix((np.ones(len(idx), np.float32), idx, ptr), shape=(14, 19))
+    got = spectral_operator(train)
+    assert got.dtype == np.float32 and got.shape == (33, 33) and np.array_equal(got, A)
+    assert np.abs(got - got.T).max() < 1e-5
+
+
+def test_spectralcf_trainer_learns():
+    ptr, idx, A, e0, W, nu, users, pos, neg = _spectral_problem(np.float32, seed=3, nu=20, ni=30, d=8)
+    rs = np.random.RandomState(0)
+    users = np.repeat(np.arange(nu), np.diff(ptr)); pos = idx
+    tr = tf_math.SpectralCFTrainer(A, e0, W, nu, "adam", 0.01, 1e-3)
+    losses = []
+    for _ in range(40):
+        neg = rs.randint(0, 30, len(users))
+        losses.append(float(tr.step(users, pos, neg)))
+    assert losses[-1] < 0.8 * losses[0]
+    assert tr.embeddings().shape == (50, 24)
+
+
+# ------------------------------------------------------------------------------------------ train / test split
+@pytest.fixture(scope="module")
+def split_golden():
+    z = np.load(os.path.join(GOLDEN, "kat_split_ml100k.npz"))
+    n = int(z["n"])
+    users = np.unique(z["user"], return_inverse=True)[1].astype(np.int32)
+    return {"n": n, "users": users, "num_users": int(users.max()) + 1, "time": z["time"].astype(np.int64),
+            "ratio": np.unpackbits(z["ratio"])[:n], "loo": np.unpackbits(z["loo"])[:n]}
+
+
+@pytest.mark.parametrize("mode", ["ratio", "loo"])
+def test_split_restatement_equals_the_reference_split(split_golden, mode):
+    """data/utils.py split_by_ratio(0.8) / split_by_loo with by_time=True run by the REAL reference on ml-100k.rating
+    (100 000 interactions, many equal timestamps inside a user): the restatement assigns every interaction to the
+    same side."""
+    g = split_golden
+    got = oracle.split_interactions(g["users"], g["time"], g["num_users"], mode, 0.8)
+    assert np.array_equal(got, g[mode])
+
+
+def test_random_split_restatement_contract(split_golden):
+    """by_time=False: a uniformly random ceil(ratio n_u) of every user's interactions, another one for another seed."""
+    g = split_golden
+    a = oracle.split_interactions(g["users"], None, g["num_users"], "ratio", 0.8, seed=1)
+    b = oracle.split_interactions(g["users"], None, g["num_users"], "ratio", 0.8, seed=2)
+    cnt = np.bincount(g["users"], minlength=g["num_users"])
+    want = np.ceil(0.8 * cnt).astype(np.int64)
+    assert np.array_equal(np.bincount(g["users"], weights=a, minlength=g["num_users"]).astype(np.int64), want)
+    assert np.array_equal(np.bincount(g["users"], weights=b, minlength=g["num_users"]).astype(np.int64), want)
+    assert 0.25 < (a != b).mean() < 0.40                       # two independent 80 % subsets differ on ~32 %
+    # position inside the user's time order does not matter: early and late interactions are kept equally often
+    order = np.lexsort((g["time"], g["users"]))
+    first_half = np.zeros(g["n"], bool)
+    start = 0
+    for c in cnt:
+        first_half[order[start:start + c // 2]] = True
+        start += c
+    assert abs(a[first_half].mean() - a[~first_half].mean()) < 0.01

@@ -366,3 +366,133 @@ def test_checkpoint_resume_continues_the_run(ml100k, tmp_path, monkeypatch):
     c = MF(None, ds, conf2); c.build_graph()
     with pytest.raises(ValueError):
         checkpoint.load(c, path)
+
+
+# ------------------------------------------------------------------------------------------------ SpectralCF
+def _spectral_case(nu=120, ni=170, d=24, K=2, seed=0, batch=256):
+    rs = np.random.RandomState(seed)
+    rows = [np.sort(rs.choice(ni, rs.randint(2, 12), replace=False)) for _ in range(nu)]
+    ptr = np.cumsum([0] + [len(r) for r in rows]).astype(np.int64); idx = np.concatenate(rows).astype(np.int32)
+    A = tf_math.spectralcf_a_hat(ptr, idx, nu, ni)
+    e0 = (rs.randn(nu + ni, d) * 0.2).astype(np.float32)
+    W = (rs.randn(K, d, d) * (1.0 / np.sqrt(d))).astype(np.float32)
+    users = rs.randint(0, nu, batch).astype(np.int32)
+    pos = rs.randint(0, ni, batch).astype(np.int32); neg = rs.randint(0, ni, batch).astype(np.int32)
+    return A, e0, W, nu, users, pos, neg
+
+
+@pytest.mark.parametrize("act,d,K", [("sigmoid", 24, 2), ("tanh", 100, 2), ("relu", 33, 1), ("elu", 16, 3), ("identity", 128, 1),
+                                     ("selu", 8, 2)])
+def test_spectralcf_forward_vs_oracle(act, d, K):
+    from neurec_b200 import ops
+    A, e0, W, nu, *_ = _spectral_case(d=d, K=K)
+    want, _ = tf_math.spectralcf_forward(A, e0, list(W), act)
+    got = ops.spectralcf_forward(dev(A), dev(e0), dev(W), act).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 2e-5 * max(1.0, np.abs(want).max())
+    with pytest.raises(NotImplementedError):
+        ops.spectralcf_forward(dev(A), dev(e0), dev(W), "softmax")
+
+
+@pytest.mark.parametrize("act,loss,with_t", [("sigmoid", "bpr", True), ("tanh", "hinge", False), ("relu", "square", True),
+                                             ("selu", "BPR", False)])
+def test_spectralcf_grad_vs_oracle(act, loss, with_t):
+    """Loss, d loss / d E_0 and d loss / d W_k of one batch against the numpy backprop (itself checked by finite
+    differences); tolerance: fp32 re-association of the dense products (fixed-order k-chunks here, BLAS blocking there)."""
+    from neurec_b200 import ops
+    A, e0, W, nu, users, pos, neg = _spectral_case(d=24, K=2, seed=1)
+    N, d, K = e0.shape[0], e0.shape[1], W.shape[0]
+    want_l, dE0, dW, want_all = tf_math.spectralcf_loss_and_grad(A, e0, list(W), nu, users, pos, neg, 0.01, loss, act)
+    dA = dev(A)
+    all_emb = torch.zeros((N, d * (K + 1)), device="cuda"); G = torch.zeros_like(all_emb)
+    touched = torch.zeros(N, dtype=torch.int32, device="cuda")
+    gE = torch.empty((N, d), device="cuda"); gW = torch.empty((K, d, d), device="cuda")
+    out = torch.zeros(1, device="cuda")
+    ops.spectralcf_grad(nu, dA, dA.t().contiguous() if with_t else None, dev(e0), dev(W), act, dev(users), dev(pos), dev(neg),
+                        loss, 0.01, all_emb, G, touched, gE, gW, ops.spectralcf_work(N, d, K), out)
+    assert abs(out.item() - float(want_l)) < 1e-4 * abs(float(want_l))
+    assert np.abs(all_emb.cpu().numpy() - want_all).max() < 2e-5
+    assert np.abs(gE.cpu().numpy() - dE0).max() < 2e-5 * max(1.0, np.abs(dE0).max())
+    for k in range(K):
+        assert np.abs(gW[k].cpu().numpy() - dW[k]).max() < 5e-5 * max(1.0, np.abs(dW[k]).max()), k
+    assert float(G.abs().max().item()) == 0.0                            # the accumulator is handed back clean
+
+
+def test_spectralcf_steps_vs_oracle_trainer():
+    """Five Adam steps through nrc_spectralcf_grad + nrc_opt_apply_multi (dense formulas) against SpectralCFTrainer."""
+    from neurec_b200 import ops
+    A, e0, W, nu, *_ = _spectral_case(d=16, K=2, seed=2)
+    N, d, K = e0.shape[0], 16, 2
+    rs = np.random.RandomState(5)
+    tr = tf_math.SpectralCFTrainer(A, e0, list(W), nu, "adam", 1e-2, 1e-3, "bpr", "sigmoid")
+    dA, dE, dWt = dev(A), dev(e0), dev(W)
+    dAt = dA.t().contiguous()
+    all_emb = torch.zeros((N, d * (K + 1)), device="cuda"); G = torch.zeros_like(all_emb)
+    touched = torch.zeros(N, dtype=torch.int32, device="cuda")
+    gE, gW = torch.zeros_like(dE), torch.zeros_like(dWt)
+    z = torch.zeros_like
+    sE, sW = (z(dE), z(dE)), (z(dWt), z(dWt))
+    work = ops.spectralcf_work(N, d, K)
+    lr_t = tf_math.adam_lr_t(1e-2, 5)
+    for s in range(5):
+        users = rs.randint(0, nu, 200).astype(np.int32); pos = rs.randint(0, 170, 200).astype(np.int32)
+        neg = rs.randint(0, 170, 200).astype(np.int32)
+        want = tr.step(users, pos, neg)
+        out = torch.zeros(1, device="cuda")
+        ops.spectralcf_grad(nu, dA, dAt, dE, dWt, "sigmoid", dev(users), dev(pos), dev(neg), "bpr", 1e-3, all_emb, G, touched, gE, gW,
+                            work, out)
+        ops.opt_apply_multi("adam", [(dE, gE, sE[0], sE[1], None, True), (dWt, gW, sW[0], sW[1], None, True)], s + 1,
+                            [float(lr_t[s]), 0.9, 0.999, 1e-8])
+        assert abs(out.item() - float(want)) < 2e-4 * abs(float(want)), s
+    assert np.abs(dE.cpu().numpy() - tr.e0).max() < 1e-4
+    for k in range(K):
+        assert np.abs(dWt[k].cpu().numpy() - tr.filters[k]).max() < 1e-4
+    assert np.abs(tr.e0 - e0).max() > 1e-2                                # five Adam steps of 1e-2 moved the table
+
+
+def test_main_runs_spectralcf(tmp_path):
+    data = tmp_path / "dataset"
+    _write_social_dataset(str(data))
+    cmd = [sys.executable, os.path.join(ROOT, "main.py"), "--data.input.path=%s" % data, "--data.input.dataset=toy",
+           "--topk=[5,10]", "--test_batch_size=64", "--recommender=SpectralCF", "--epochs=5", "--embedding_size=32",
+           "--learning_rate=0.005"]
+    for name in ("NeuRec.properties", "conf"):
+        os.symlink(os.path.join(ROOT, name), tmp_path / name)
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    epochs = re.findall(r"epoch (\d+):\t([0-9.\t ]+)", r.stdout)
+    assert len(epochs) == 5
+    vals = np.array([[float(x) for x in e[1].split()] for e in epochs])
+    assert vals.shape[1] == 10 and np.isfinite(vals).all() and (vals >= 0).all() and (vals <= 1).all()
+    losses = [float(x) for x in re.findall(r"\[iter \d+ : loss : ([0-9.eE+-]+), time: ", r.stdout)]
+    assert len(losses) == 5 and losses[-1] < losses[0]
+
+
+# ------------------------------------------------------------------------------------------ train / test split
+def test_split_interactions_bit_exact_and_equal_to_the_reference_split():
+    """nrc_split_interactions against the restatement (every mode) and, for by_time=True on ml-100k, against the bits
+    the REAL reference's split_by_ratio / split_by_loo produced (tests/golden/kat_split_ml100k.npz)."""
+    from neurec_b200 import ops
+    z = np.load(os.path.join(GOLDEN, "kat_split_ml100k.npz"))
+    n = int(z["n"])
+    users = np.unique(z["user"], return_inverse=True)[1].astype(np.int32)
+    nu = int(users.max()) + 1
+    times = z["time"].astype(np.int64)
+    for mode in ("ratio", "loo"):
+        got = ops.split_interactions(dev(users), dev(times), nu, mode, 0.8).cpu().numpy()
+        assert np.array_equal(got, np.unpackbits(z[mode])[:n]), mode
+        assert np.array_equal(got, oracle.split_interactions(users, times, nu, mode, 0.8))
+    for seed in (0, 2018):
+        for mode, ratio in (("ratio", 0.8), ("ratio", 0.5), ("loo", 0.0)):
+            got = ops.split_interactions(dev(users), None, nu, mode, ratio, seed).cpu().numpy()
+            assert np.array_equal(got, oracle.split_interactions(users, None, nu, mode, ratio, seed)), (seed, mode, ratio)
+    rs = np.random.RandomState(0)                               # negative times, empty users, tiny users
+    u = rs.randint(0, 40, 300).astype(np.int32); u[u == 7] = 8
+    t = rs.randint(-50, 50, 300).astype(np.int64)
+    for mode in ("ratio", "loo"):
+        assert np.array_equal(ops.split_interactions(dev(u), dev(t), 40, mode, 0.7).cpu().numpy(),
+                              oracle.split_interactions(u, t, 40, mode, 0.7))
+    with pytest.raises(ValueError):
+        ops.split_interactions(dev(u), dev(t), 39, "ratio", 0.8)
+    with pytest.raises(ValueError):
+        ops.split_interactions(dev(u), dev(t), 40, "given", 0.8)
