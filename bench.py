@@ -285,6 +285,24 @@ def timed(fn, world, windows, flush=True):
     return max_over_ranks(a.elapsed_time(b), world), out
 
 
+WARM_SECONDS = 0.3
+
+
+def warm_up(step_fn, min_steps):
+    """At least `min_steps` untimed steps AND at least WARM_SECONDS of them: the small workloads' steps are
+    microseconds, so a fixed handful would be timed while the SM clock is still ramping up after the (host-side)
+    setup.  Returns the number of warm-up steps run."""
+    import torch
+    done, t0 = 0, time.perf_counter()
+    while done < min_steps or time.perf_counter() - t0 < WARM_SECONDS:
+        step_fn()
+        done += 1
+        if done >= min_steps:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    return done
+
+
 def adam_lr_schedule(lr, n):
     out = np.empty(n, np.float32)
     p1, p2, one, lr = np.float32(0.9), np.float32(0.999), np.float32(1), np.float32(lr)
@@ -662,11 +680,12 @@ def measure_small(w, K, W, world, rank, windows, with_cpu=True):
     models do not shard)."""
     import torch
     w.setup()
-    w.run_steps(max(W, 3))
+    chunk = max(W, 3)
+    warmed = chunk * warm_up(lambda: w.run_steps(chunk), 1)
     ms, _ = timed(lambda: w.run_steps(K), world, windows)
     launches_before = w.launches
     value = world * K * w.batch / (ms * 1e-3)
-    w.run_steps(max(W, 3), e2e=True)
+    warm_up(lambda: w.run_steps(chunk, e2e=True), 1)
     barrier(world); flush_l2(); barrier(world)
     wall0 = time.perf_counter()
     w.run_steps(K, e2e=True)
@@ -692,7 +711,7 @@ def measure_small(w, K, W, world, rank, windows, with_cpu=True):
                             "CUDA events around the K timed steps (sampling and shuffling included)",
                             {"honest_bound": "tables are L2-resident (0.7 MB): the step is bound by two grid-wide barriers "
                                              "and dependent L2 round trips, not by HBM"})
-    out = {"metric": "triplets/sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+    out = {"metric": "triplets/sec", "value": value, "unit": "triplets/s", "n_gpus": world, "steps": K, "warmup": warmed,
            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "%s (%s), random-init tables, device Philox negatives + keyed-bijection shuffle" % (
                w.d["name"], "the reference's split, tests/golden/%s_split.npz" % ("ml100k" if w.d["name"] == "ml-100k" else w.d["name"])),
@@ -815,7 +834,7 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
     VS.enable_hot(n_hot_of(cfg, world))
     spe = T.n_pos // bs                        # whole batches only (drop_last), so every step is 2^20 triplets
     loss = torch.zeros(1, device="cuda")
-    loss_pin = torch.zeros(K + W + 8).pin_memory()
+    loss_pin = torch.zeros(K + 8).pin_memory()
     state = {"g": 0}
 
     def step(e2e_slot=None, after_kernel=None):
@@ -828,8 +847,16 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
         if e2e_slot is not None:               # every step's loss goes back to the host
             loss_pin[e2e_slot:e2e_slot + 1].copy_(loss, non_blocking=True)
 
+    # warm-up: W steps, then as many more as fill WARM_SECONDS -- the same number on every rank (a step holds a collective)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(W):
         step()
+    torch.cuda.synchronize()
+    per_step = (time.perf_counter() - t0) / W
+    extra = int(max_over_ranks(max(0.0, WARM_SECONDS - per_step * W) / per_step, world)) + 1
+    for _ in range(extra):
+        step()
+    W += extra
     barrier(world)
     # per-launch durations (CUDA events on the launching stream) inside the timed region
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
@@ -844,8 +871,8 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
     launch_ms = [evs[s].elapsed_time(kevs[s]) for s in range(K)]          # the step kernel alone
     sync_ms = [kevs[s].elapsed_time(evs[s + 1]) for s in range(K)]        # all-reduce + apply of the replicated head
     # e2e: the train interactions come from pinned host memory inside the timed region
-    for s in range(W):
-        step(s)
+    for _ in range(3):
+        step(0)
     barrier(world); flush_l2(); barrier(world)
     wall0 = time.perf_counter()
     T.upload()
@@ -862,7 +889,7 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
     if world == 1:          # the explicitly-named lazy-Adam run SURVEY 8(d) asks for (single GPU: rows of var, m, v)
         z = torch.zeros_like
         mU, vU, mV, vV = z(US_local), z(US_local), z(VS.local), z(VS.local)
-        lr_sched = adam_lr_schedule(1e-3, K + W)
+        lr_sched = adam_lr_schedule(1e-3, K + 4096)
         lstate = {"g": 0}
 
         def lazy_step():
@@ -870,8 +897,7 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
             ops.mf_bpr_lazy_adam_epoch(US_local, mU, vU, VS.local, mV, vV, T.ptr, T.idx, T.users, T.idx, ni, True, SEED + 7,
                                        e, s * bs, bs, float(lr_sched[lstate["g"]]), 0.0, loss)
             lstate["g"] += 1
-        for _ in range(W):
-            lazy_step()
+        warm_up(lazy_step, 3)
         lms, _ = timed(lambda: [lazy_step() for _ in range(K)], world, windows)
         lazy = {"ms": lms / K, "finite": bool(torch.isfinite(loss).item())}
         del mU, vU, mV, vV
