@@ -25,7 +25,7 @@ Rank 0 prints ONE JSON line:
   value     whole-job triplets/s (a pointwise sample counts as one triplet), train
             CSR resident in HBM when the timed region starts
   e2e       the same through the public per-epoch call with HOST buffers: the train interactions
-            (CSR + flattened positives) are copied from pinned host memory inside the timed region
+            (the CSR; the positives' users are expanded from it on the device) are copied from pinned host memory inside the timed region
             and every step's loss is copied back (h2d / d2h bytes per step are counted)
   roofline  dominant kernel: algorithmic bytes / CUDA-event launch time vs the
             measured HBM copy peak (MEASURED_PEAKS.json); tensor pipe for eval-synth
@@ -242,23 +242,25 @@ def pin(a):
 
 
 class TrainData:
-    """The train interactions a sampler is built from (data/sampler.py:24-39): CSR + flattened
-    positives, as pinned host arrays and as device arrays."""
+    """The train interactions a sampler is built from (data/sampler.py:24-39): the CSR as pinned host arrays and as
+    device arrays; the flattened positives' users are expanded from the row pointers ON the device (nrc_csr_row_ids),
+    so an upload moves only (indptr, indices)."""
 
     def __init__(self, indptr, indices, users=None):
         import torch
-        if users is None:
-            users = np.repeat(np.arange(len(indptr) - 1, dtype=np.int32), np.diff(indptr))
-        self.host = [pin(np.asarray(indptr, np.int64)), pin(np.asarray(indices, np.int32)), pin(np.asarray(users, np.int32))]
+        self.host = [pin(np.asarray(indptr, np.int64)), pin(np.asarray(indices, np.int32))]
         self.dev = [torch.empty_like(h, device="cuda") for h in self.host]
+        self.dev.append(torch.empty((self.host[1].numel(),), dtype=torch.int32, device="cuda"))
         self.nbytes = sum(h.numel() * h.element_size() for h in self.host)
         self.n_pos = int(self.host[1].numel())
         self.upload()
 
     def upload(self):
-        """H2D of the train interactions from pinned memory on the current stream (the e2e leg)."""
+        """H2D of the train interactions from pinned memory on the current stream (the e2e leg) + the expansion."""
+        from neurec_b200 import ops
         for h, t in zip(self.host, self.dev):
             t.copy_(h, non_blocking=True)
+        ops.csr_row_ids(self.dev[0], out=self.dev[2])
 
     @property
     def ptr(self): return self.dev[0]
@@ -724,7 +726,7 @@ def measure_small(w, K, W, world, rank, windows, with_cpu=True):
            "e2e": {"value": world * K * w.batch / e2e_s, "unit": "triplets/s",
                    "h2d_bytes_per_step": w.T.nbytes * calls / K, "d2h_bytes_per_step": 4 * (2 if isinstance(w, LightgcnGowalla) else 1),
                    "ms_per_step": e2e_s * 1e3 / K,
-                   "how": "per epoch call: the train CSR + flattened positives are copied from pinned host memory, the epoch's "
+                   "how": "per epoch call: the train CSR is copied from pinned host memory (positives' users expanded on the device), the epoch's "
                           "steps run, the per-step losses are copied back to pinned memory, the host waits (what "
                           "train_model does per epoch); %d call(s) in the timed region" % calls},
            "gpu_launches": w.launches - launches_before if False else None,
@@ -782,8 +784,7 @@ def synth_shard_csr(cfg, rank, world, device="cuda"):
     indptr = torch.zeros(nu + 1, dtype=torch.int64, device=device)
     indptr[1:] = deg.cumsum(0)
     indices = items[keep].to(torch.int32)
-    users = torch.repeat_interleave(torch.arange(nu, device=device, dtype=torch.int32), deg)
-    return indptr.cpu().numpy(), indices.cpu().numpy(), users.cpu().numpy()
+    return indptr.cpu().numpy(), indices.cpu().numpy()
 
 
 def n_hot_of(cfg, world):
@@ -818,9 +819,9 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
     W = max(W, 3)
     dim, bs = cfg.dim, cfg.batch
     ni = cfg.items_per_gpu * world
-    ptr, idx, users = synth_shard_csr(cfg, rank, world)
-    T = TrainData(ptr, idx, users)
-    del ptr, idx, users
+    ptr, idx = synth_shard_csr(cfg, rank, world)
+    T = TrainData(ptr, idx)
+    del ptr, idx
     torch.cuda.empty_cache()
     g = torch.Generator(device="cuda").manual_seed(30 + rank)
     if world > 1:
@@ -933,8 +934,9 @@ def measure_sharded(K, W, world, rank, windows, with_cpu=True, cfg=ShardedCfg):
                             "fresh positions of the shuffled epoch" % (T.nbytes / 1e9)},
            "e2e": {"value": world * K * bs / e2e_s, "unit": "triplets/s", "h2d_bytes_per_step": T.nbytes / K,
                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_s * 1e3 / K,
-                   "how": "the rank's train CSR + flattened positives (%.0f MB) are copied from pinned host memory inside "
-                          "the timed region, then K steps, each copying its loss back to pinned memory" % (T.nbytes / 1e6)},
+                   "how": "the rank's train CSR (%.0f MB; the flattened positives' users are expanded from the row pointers on "
+                          "the device) is copied from pinned host memory inside the timed region, then K steps, each "
+                          "copying its loss back to pinned memory" % (T.nbytes / 1e6)},
            "gpu_launches": K * (2 if n_hot_of(cfg, world) else 1),
            "roofline": hbm_roofline(sgd_form(), nbytes, kt,
                                     "SURVEY 8(d): (24*d + 12) B per triplet x 2^20 triplets (the fused sampler's CSR reads "

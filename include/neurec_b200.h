@@ -716,6 +716,10 @@ int nrc_csr_from_coo(const int32_t* rows, const int32_t* cols, int64_t nnz, int3
                      int64_t* out_indptr, int32_t* out_indices, int64_t* work_i64, int32_t* work_i32,
                      int32_t* bad_flag, void* stream);
 
+/* users_list of _generate_positive_items (data/sampler.py:24-39) expanded on the device: out[e] = row of CSR entry e,
+ * out i32 [indptr[num_rows]] -- only (indptr, indices) of the train interactions have to be uploaded. */
+int nrc_csr_row_ids(const int64_t* indptr, int64_t num_rows, int32_t* out, void* stream);
+
 /* split_by_ratio / split_by_loo, data/utils.py:59-106, on the device: every user's interactions ordered by `keys`
  * (i64 [n] interaction times, by_time=True) or, when keys is NULL (by_time=False), by a counter-based random word
  * keyed by `seed` (DataFrame.sample(frac=1)); ties by input position; the first ceil(ratio * n_u) (mode 0) or all but

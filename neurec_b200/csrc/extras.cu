@@ -325,6 +325,18 @@ split_rank_kernel(const int64_t* __restrict__ ptr, int32_t num_users, const int3
     }
 }
 
+// users_list of _generate_positive_items (data/sampler.py:24-39) from the CSR row pointers: out[e] = row of entry e.
+// One warp per row (rows of a train CSR are short; a 700-entry row is 22 strides).
+__global__ void __launch_bounds__(256)
+csr_row_ids_kernel(const int64_t* __restrict__ ptr, int64_t num_rows, int32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wpb = blockDim.x >> 5;
+    for (int64_t r = blockIdx.x * wpb + (threadIdx.x >> 5); r < num_rows; r += (int64_t)gridDim.x * wpb) {
+        const int64_t b = __ldg(ptr + r), e = __ldg(ptr + r + 1);
+        for (int64_t q = b + lane; q < e; q += kWarp) out[q] = (int32_t)r;
+    }
+}
+
 static unsigned grid_for(int64_t work_items, int per_block) {
     int64_t blocks = (work_items + per_block - 1) / per_block;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -487,6 +499,16 @@ extern "C" int nrc_split_interactions(const int32_t* users, const int64_t* keys,
     scan_i64_kernel<<<1, 1024, 0, st>>>(ptr, num_users);
     index_scatter_kernel<<<grid_for(n, 256), 256, 0, st>>>(users, n, num_users, ptr, cursor, work_i32);
     split_rank_kernel<<<grid_for(num_users, 8), 256, 0, st>>>(ptr, num_users, work_i32, keys, mode, ratio, seed, is_train);
+    NRC_CUDA_CHECK(cudaGetLastError());
+    return NRC_OK;
+}
+
+// The flattened positives' users (data/sampler.py:24-39 `users_list`) expanded on the device from the CSR row pointers,
+// so that only (indptr, indices) have to cross PCIe.  out i32 [indptr[num_rows]].
+extern "C" int nrc_csr_row_ids(const int64_t* indptr, int64_t num_rows, int32_t* out, void* stream) {
+    NRC_REQUIRE(num_rows >= 0, NRC_E_VALUE, "num_rows >= 0 required");
+    if (num_rows == 0) return NRC_OK;
+    csr_row_ids_kernel<<<grid_for(num_rows, 8), 256, 0, as_stream(stream)>>>(indptr, num_rows, out);
     NRC_CUDA_CHECK(cudaGetLastError());
     return NRC_OK;
 }

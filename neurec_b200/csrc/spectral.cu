@@ -58,18 +58,22 @@ struct GemmArgs {
 
 constexpr int kGemmRows = 32, kGemmK = 32, kGemmMaxN = 128;
 
+// Thread (tx, ty): rows 4 ty .. 4 ty + 3 (one LDS.128 of the A tile, broadcast across the warp) x columns
+// 4 tx .. 4 tx + 3 (one LDS.128 of the X tile, conflict-free): 16 FMAs per two vector shared-memory reads.
 __global__ void __launch_bounds__(256) dense_gemm_kernel(const GemmArgs G) {
-    __shared__ float As[kGemmK][kGemmRows + 1];            // [k][row]
-    __shared__ float Xs[kGemmK][kGemmMaxN];                // [k][col]
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps: warp ty owns rows 4 ty .. 4 ty + 3
+    __shared__ __align__(16) float As[kGemmK][kGemmRows + 4];        // [k][row]; row stride 36 floats keeps float4 alignment
+    __shared__ __align__(16) float Xs[kGemmK][kGemmMaxN];            // [k][col]; columns >= n stay zero
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int row0 = blockIdx.x * kGemmRows;
     const int k_begin = blockIdx.y * G.k_per_cta;
     const int k_end = min(G.K, k_begin + G.k_per_cta);
+    for (int e = threadIdx.x; e < kGemmK * kGemmMaxN; e += 256) (&Xs[0][0])[e] = 0.0f;
     float acc[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+    __syncthreads();
     for (int k0 = k_begin; k0 < k_end; k0 += kGemmK) {
         // A tile: 32 rows x 32 k
         for (int e = threadIdx.x; e < kGemmRows * kGemmK; e += 256) {
@@ -90,17 +94,17 @@ __global__ void __launch_bounds__(256) dense_gemm_kernel(const GemmArgs G) {
             Xs[kk][c] = v;
         }
         __syncthreads();
+        if (4 * tx < G.n) {
 #pragma unroll 8
-        for (int kk = 0; kk < kGemmK; ++kk) {
-            float a[4], x[4];
+            for (int kk = 0; kk < kGemmK; ++kk) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+                const float4 x = *reinterpret_cast<const float4*>(&Xs[kk][tx * 4]);
+                const float av[4] = {a.x, a.y, a.z, a.w}, xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-            for (int r = 0; r < 4; ++r) a[r] = As[kk][ty * 4 + r];
+                for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) x[c] = (tx + 32 * c < G.n) ? Xs[kk][tx + 32 * c] : 0.0f;
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], x[c], acc[r][c]);
+                    for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], xv[c], acc[r][c]);
+            }
         }
         __syncthreads();
     }
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(256) dense_gemm_kernel(const GemmArgs G) {
         if (gr >= G.M) continue;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int gc = tx + 32 * c;
+            const int gc = tx * 4 + c;
             if (gc >= G.n) continue;
             float* y = G.Y + (int64_t)gr * G.ldy + gc;
             if (split) atomicAdd(y, acc[r][c]);
@@ -162,11 +166,14 @@ static int gemm(const float* A, int64_t lda, int trans_a, const float* X, int64_
     NRC_REQUIRE(n > 0 && n <= kGemmMaxN, NRC_E_LIMIT, "embedding_size %d outside [1, %d]", n, kGemmMaxN);
     GemmArgs G{A, lda, trans_a, X, ldx, trans_x, Y, ldy, M, K, n, act, K};
     unsigned gy = 1;
+    // few row tiles and a long reduction (A_hat products on small graphs): two K halves per row tile fill the SMs; the
+    // sum of two partials onto zero is exact in either order, so the result stays deterministic
+    if (split_k <= 1 && act == ACT_IDENTITY && K >= 1024 && (M + kGemmRows - 1) / kGemmRows < sm_count()) split_k = 2;
     if (split_k > 1) {
         int per = ((K + split_k - 1) / split_k + kGemmK - 1) / kGemmK * kGemmK;
         G.k_per_cta = per;
         gy = (unsigned)((K + per - 1) / per);
-        NRC_CUDA_CHECK(cudaMemsetAsync(Y, 0, (size_t)M * ldy * sizeof(float), st));      // callers pass ldy == n for split outputs
+        NRC_CUDA_CHECK(cudaMemset2DAsync(Y, (size_t)ldy * sizeof(float), 0, (size_t)n * sizeof(float), (size_t)M, st));
     }
     dim3 grid((unsigned)((M + kGemmRows - 1) / kGemmRows), gy);
     dense_gemm_kernel<<<grid, 256, 0, st>>>(G);

@@ -818,3 +818,13 @@ def split_interactions(users, keys, num_users, mode="ratio", ratio=0.8, seed=0):
     if int(bad.item()):
         raise ValueError("user ids outside [0, %d)" % num_users)
     return out
+
+
+def csr_row_ids(indptr, nnz=None, out=None):
+    """Row id of every CSR entry (the sampler's flattened `users_list`, data/sampler.py:24-39), int32 [nnz]."""
+    _req(indptr, torch.int64, "indptr")
+    if out is None:
+        out = torch.empty((int(indptr[-1].item()) if nnz is None else int(nnz),), dtype=torch.int32, device=indptr.device)
+    check(_lib.load().nrc_csr_row_ids(_p(indptr), indptr.numel() - 1, _p(out), _stream()))
+    _count()
+    return out

@@ -496,3 +496,12 @@ def test_split_interactions_bit_exact_and_equal_to_the_reference_split():
         ops.split_interactions(dev(u), dev(t), 39, "ratio", 0.8)
     with pytest.raises(ValueError):
         ops.split_interactions(dev(u), dev(t), 40, "given", 0.8)
+
+
+def test_csr_row_ids(ml100k):
+    from neurec_b200 import ops
+    d = ml100k
+    want = np.repeat(np.arange(d["num_users"], dtype=np.int32), np.diff(d["train_indptr"]))
+    assert np.array_equal(ops.csr_row_ids(dev(d["train_indptr"])).cpu().numpy(), want)
+    ptr = np.array([0, 0, 3, 3, 3, 1000, 1001], np.int64)                 # empty rows, a long row
+    assert np.array_equal(ops.csr_row_ids(dev(ptr)).cpu().numpy(), np.repeat(np.arange(6, dtype=np.int32), np.diff(ptr)))
