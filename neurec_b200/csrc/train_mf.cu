@@ -646,11 +646,12 @@ static int launch_bpr_sgd_stream(float* U_local, const RowShards& SV, int dim, c
 // NOT what the reference's learner=adam does (that is dense, optim.cu); never used for parity claims.
 // Algorithmic traffic: rows of (var, m, v) read + written for 3 rows = 72*dim + 12 B per triplet.
 // ----------------------------------------------------------------------------------------
+// one row of (var, m, v) with the slots already in registers: all nine row loads of a triplet are issued together
 template <int VEC>
-__device__ __forceinline__ void lazy_adam_row(float* var, float* m, float* v, const float (&x)[VEC], const float (&g)[VEC],
-                                              float lr_t, float b1, float b2, float eps) {
-    float mm[VEC], vv[VEC], out[VEC];
-    ld_vec<VEC>(m, mm); ld_vec<VEC>(v, vv);
+__device__ __forceinline__ void lazy_adam_row(float* var, float* m, float* v, const float (&x)[VEC], float (&mm)[VEC],
+                                              float (&vv)[VEC], const float (&g)[VEC], float lr_t, float b1, float b2,
+                                              float eps) {
+    float out[VEC];
 #pragma unroll
     for (int t = 0; t < VEC; ++t) {
         mm[t] = b1 * mm[t] + (1.0f - b1) * g[t];
@@ -661,7 +662,7 @@ __device__ __forceinline__ void lazy_adam_row(float* var, float* m, float* v, co
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 mf_bpr_lazy_adam_stream_kernel(float* __restrict__ U, float* __restrict__ mU, float* __restrict__ vU, float* __restrict__ V,
                                float* __restrict__ mV, float* __restrict__ vV, const EpochSpec E, int64_t first, int64_t count,
                                float lr_t, float b1, float b2, float eps, float reg, float* __restrict__ loss) {
@@ -681,8 +682,12 @@ mf_bpr_lazy_adam_stream_kernel(float* __restrict__ U, float* __restrict__ mU, fl
         for (int t = warp; t < n; t += 8) {
             const size_t ou = (size_t)s_u[t] * D + lane * VEC, oi = (size_t)s_i[t] * D + lane * VEC,
                          oj = (size_t)s_j[t] * D + lane * VEC;
-            float a[VEC], bi[VEC], bj[VEC];
+            // nine independent row loads in flight per triplet (rows of var, m, v of the three ids)
+            float a[VEC], bi[VEC], bj[VEC], mu[VEC], vu[VEC], mi[VEC], vi[VEC], mj[VEC], vj[VEC];
             ld_vec<VEC>(U + ou, a); ld_vec<VEC>(V + oi, bi); ld_vec<VEC>(V + oj, bj);
+            ld_vec<VEC>(mU + ou, mu); ld_vec<VEC>(vU + ou, vu);
+            ld_vec<VEC>(mV + oi, mi); ld_vec<VEC>(vV + oi, vi);
+            ld_vec<VEC>(mV + oj, mj); ld_vec<VEC>(vV + oj, vj);
             float di = 0.f, dj = 0.f, sq = 0.f;
 #pragma unroll
             for (int c = 0; c < VEC; ++c) {
@@ -702,9 +707,9 @@ mf_bpr_lazy_adam_stream_kernel(float* __restrict__ U, float* __restrict__ mU, fl
                 gi[c] = g * a[c] + reg * bi[c];
                 gj[c] = -g * a[c] + reg * bj[c];
             }
-            lazy_adam_row<VEC>(U + ou, mU + ou, vU + ou, a, gu, lr_t, b1, b2, eps);
-            lazy_adam_row<VEC>(V + oi, mV + oi, vV + oi, bi, gi, lr_t, b1, b2, eps);
-            lazy_adam_row<VEC>(V + oj, mV + oj, vV + oj, bj, gj, lr_t, b1, b2, eps);
+            lazy_adam_row<VEC>(U + ou, mU + ou, vU + ou, a, mu, vu, gu, lr_t, b1, b2, eps);
+            lazy_adam_row<VEC>(V + oi, mV + oi, vV + oi, bi, mi, vi, gi, lr_t, b1, b2, eps);
+            lazy_adam_row<VEC>(V + oj, mV + oj, vV + oj, bj, mj, vj, gj, lr_t, b1, b2, eps);
         }
         __syncthreads();
     }

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def load(name):
-    with open(os.path.join(HERE, name)) as f:
+    with open(name if os.path.isabs(name) or os.path.isfile(name) else os.path.join(HERE, name)) as f:
         return json.loads(f.read().strip().splitlines()[-1])
 
 
@@ -16,7 +16,8 @@ def fmt(v):
 
 
 def main():
-    d = load("r2_bench_n1.json")
+    import sys
+    d = load(sys.argv[1] if len(sys.argv) > 1 else "r2_bench_n1.json")
     ref = load("r2_bench_reference_n1.json")
     rows = [("configs[4] BPRMF gd, 6.25 M x 12.5 M x 128 (headline)", d, ref["value"], ref["cpu_baseline"]["cores"])]
     for k in ("bprmf-ml100k", "neumf-ml100k", "lightgcn-gowalla"):
