@@ -169,6 +169,10 @@ struct RowShards {
                               // reduce-add of the whole row (cp.reduce.async.bulk from shared memory) -- NRC_PEER_VEC_RED.
                               // Measured over NVLink on B200 (profiles/r2_peer_probe_v2.txt): 0.29 / 1.33 / 1.34 G rows/s
     int32_t force_remote;     // debug (NRC_FORCE_REMOTE_PATH=1): take the remote update path for local item rows too
+    int32_t local_bulk;       // CSR-fed kernel: local rows (user rows, own item rows, the head's delta rows) are updated by ONE
+                              // bulk reduce-add of the staged delta row (cp.reduce.async.bulk .add.f32) instead of 32 vector REDs
+                              // -- NRC_SGD_LOCAL_BULK, default 1: measured 0.754 vs 0.683 of the HBM copy peak with the item
+                              // rows taking that path (profiles/r2_sgd_update_modes.txt)
     // Replicated head (n_hot > 0): rows [0, n_hot) -- the loader relabels items by descending train degree, so these
     // are the most popular ones -- are READ from this rank's replica `hot` (L2-resident) and their deltas are
     // accumulated into this rank's `hot_delta`; the caller all-reduces hot_delta between steps and applies it
@@ -333,38 +337,46 @@ __device__ __forceinline__ void st_vec(float* p, const float (&v)[VEC]) {
     else *p = v[0];
 }
 
-// Update of a row that lives on another rank, by mode (RowShards::vec_remote).  Mode 2 stages the warp's
-// delta row in shared memory and issues ONE bulk reduce-add of the whole row through the copy engine
-// (cp.reduce.async.bulk ... .add.f32): a single transaction per row over NVLink instead of 32 x VEC REDs.
+// In-place update of the three rows of one triplet, each by its own mode: 0 scalar REDs, 1 vector REDs, 2 ONE bulk
+// reduce-add of the whole row (cp.reduce.async.bulk ... .add.f32) from the warp's staging rows -- a single transaction
+// per row for the L2 (or over NVLink) instead of 32 x VEC REDs.  The bulk rows of a triplet share one proxy fence,
+// one warp barrier and one bulk group.  p*: lane-offset row pointers (lane 0's is the start of the row).
 template <int VEC>
-__device__ __forceinline__ void remote_row_update(float* p_row_lane, const float (&d)[VEC], int mode, float* stage, int lane) {
-    if (mode == 2) {
-#pragma unroll
-        for (int t = 0; t < VEC; ++t) stage[lane * VEC + t] = d[t];
+__device__ __forceinline__ void update_rows3(float* p0, const float (&d0)[VEC], int m0, float* p1, const float (&d1)[VEC], int m1,
+                                             float* p2, const float (&d2)[VEC], int m2, float* stage, int lane) {
+    constexpr int D = 32 * VEC;
+    if (m0 == 2) st_vec<VEC>(stage + lane * VEC, d0); else red_row<VEC>(p0, d0, m0 == 0);
+    if (m1 == 2) st_vec<VEC>(stage + D + lane * VEC, d1); else red_row<VEC>(p1, d1, m1 == 0);
+    if (m2 == 2) st_vec<VEC>(stage + 2 * D + lane * VEC, d2); else red_row<VEC>(p2, d2, m2 == 0);
+    if (m0 == 2 || m1 == 2 || m2 == 2) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-            float* row = p_row_lane;     // lane 0 points at the start of the row
             const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stage);
-            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
-                         ::"l"(row), "r"(saddr), "r"((uint32_t)(32 * VEC * 4)) : "memory");
+            constexpr uint32_t kBytes = (uint32_t)(D * 4);
+            if (m0 == 2) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                      ::"l"(p0), "r"(saddr), "r"(kBytes) : "memory");
+            if (m1 == 2) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                      ::"l"(p1), "r"(saddr + kBytes), "r"(kBytes) : "memory");
+            if (m2 == 2) asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                      ::"l"(p2), "r"(saddr + 2 * kBytes), "r"(kBytes) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-    } else {
-        red_row<VEC>(p_row_lane, d, mode == 0);
     }
 }
 
 template <int VEC, bool SHARDED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const EpochSpec E, int64_t first,
                          int64_t count, float lr, float reg, float* __restrict__ loss) {
     constexpr int D = 32 * VEC;
     constexpr int CH = 256;
     __shared__ int32_t s_u[CH], s_i[CH], s_j[CH];
-    __shared__ __align__(16) float s_stage[8][4][D];      // bulk-reduce staging: 4 rows per warp (2 triplets x 2 item rows)
+    __shared__ __align__(16) float s_stage[8][6][D];      // bulk-reduce staging: 6 rows per warp (2 triplets x 3 rows)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rmode = V.vec_remote;
+    const int lmode = V.local_bulk ? 2 : 1;              // update mode of LOCAL rows: 2 bulk reduce-add, 1 vector RED
+    const bool any_bulk = (lmode == 2) || (rmode == 2);
     float loss_acc = 0.0f;
     for (int64_t c0 = (int64_t)blockIdx.x * CH; c0 < count; c0 += (int64_t)gridDim.x * CH) {
         const int n = (count - c0 < CH) ? (int)(count - c0) : CH;
@@ -375,10 +387,6 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
         }
         __syncthreads();
         for (int t0 = warp * 2; t0 < n; t0 += 16) {
-            if (rmode == 2) {   // the staging rows of the previous pair must have been read by the copy engine
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
-            }
             const bool two = t0 + 1 < n;
             const int t1 = two ? t0 + 1 : t0;
             bool ri0, rj0, ri1, rj1;
@@ -407,6 +415,11 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
             float l1 = (x1 >= 0.f) ? log1pf(expf(-x1)) : (-x1 + log1pf(expf(x1)));
             if (reg != 0.0f) { l0 += reg * 0.5f * warp_sum(sq0); l1 += reg * 0.5f * warp_sum(sq1); }
             const float g0 = -1.0f / (1.0f + expf(x0)), g1 = -1.0f / (1.0f + expf(x1));
+            if (any_bulk) {     // the staging rows of the previous pair must have been read by the copy engine; waited for
+                                // HERE, behind this pair's loads and arithmetic, not in front of them
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
             float du[VEC], dvi[VEC], dvj[VEC];
 #pragma unroll
             for (int t = 0; t < VEC; ++t) {
@@ -414,9 +427,7 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
                 dvi[t] = -lr * (g0 * a0[t] + reg * b0[t]);
                 dvj[t] = -lr * (-g0 * a0[t] + reg * c0v[t]);
             }
-            red_row<VEC>(pu0, du, false);
-            if (ri0) remote_row_update<VEC>(wi0, dvi, rmode, s_stage[warp][0], lane); else red_row<VEC>(wi0, dvi, false);
-            if (rj0) remote_row_update<VEC>(wj0, dvj, rmode, s_stage[warp][1], lane); else red_row<VEC>(wj0, dvj, false);
+            update_rows3<VEC>(pu0, du, lmode, wi0, dvi, ri0 ? rmode : lmode, wj0, dvj, rj0 ? rmode : lmode, s_stage[warp][0], lane);
             loss_acc += l0;
             if (two) {
 #pragma unroll
@@ -425,15 +436,13 @@ mf_bpr_sgd_stream_kernel(float* __restrict__ U_local, const RowShards V, const E
                     dvi[t] = -lr * (g1 * a1[t] + reg * b1[t]);
                     dvj[t] = -lr * (-g1 * a1[t] + reg * c1v[t]);
                 }
-                red_row<VEC>(pu1, du, false);
-                if (ri1) remote_row_update<VEC>(wi1, dvi, rmode, s_stage[warp][2], lane); else red_row<VEC>(wi1, dvi, false);
-                if (rj1) remote_row_update<VEC>(wj1, dvj, rmode, s_stage[warp][3], lane); else red_row<VEC>(wj1, dvj, false);
+                update_rows3<VEC>(pu1, du, lmode, wi1, dvi, ri1 ? rmode : lmode, wj1, dvj, rj1 ? rmode : lmode, s_stage[warp][3], lane);
                 loss_acc += l1;
             }
         }
         __syncthreads();
     }
-    if (rmode == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk reduces performed
+    if (any_bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk reduces performed
     if (lane == 0 && loss) atomicAdd(loss, loss_acc);
 }
 
@@ -852,6 +861,9 @@ extern "C" int nrc_mf_bpr_sgd_epoch_hot(float* user_table, float* const* item_sh
         if (force < 0) { const char* e = getenv("NRC_FORCE_REMOTE_PATH"); force = e ? atoi(e) : 0; }
         SV.vec_remote = vec;
         SV.force_remote = force;
+        static int bulk = -1;
+        if (bulk < 0) { const char* e = getenv("NRC_SGD_LOCAL_BULK"); bulk = e ? (atoi(e) != 0) : 1; }
+        SV.local_bulk = bulk;
     }
     return launch_bpr_sgd_stream(user_table, SV, dim, E, first, count, lr, reg, loss, as_stream(stream));
 }
