@@ -7,9 +7,14 @@ does; it raises when its CUDA library is missing instead of falling back to anyt
 Three things live here:
 
 * ``neurec_oracle.c``  -- plain-C restatement of the reference's compiled path
-  (evaluator, metrics, libstdc++ partial_sort_copy tie order, libc-rand sampler).
+  (evaluator, metrics, libstdc++ partial_sort_copy tie order, libc-rand sampler) and of the
+  product's counter-based streams (Philox negatives, keyed-bijection order, SBPR draws, split keys).
 * ``tf_math.py``       -- numpy fp32 restatement of the TF-1.12 graphs (MF/BPR, pointwise,
-  MLP/NeuMF, LightGCN, NGCF propagation) and of the TF optimizers.
+  MLP/NeuMF, LightGCN, NGCF, APR, SBPR, SpectralCF) and of the TF optimizers; parity UNPINNED at
+  the TensorFlow boundary (no TF offline), gradients pinned by finite differences.
+* numpy restatements in this file of the data side: SBPR's social-item sets (crc-identical to the
+  real reference's on Ciao), interactions -> CSR, the per-user train/test split (bit-identical to the
+  real reference's split_by_ratio / split_by_loo on ml-100k).
 * ``_ref/``            -- the REAL reference: its C++ headers and .pyx files compiled from
   where they lie under /root/reference by ``oracle/Makefile`` (``make ref``).  Used to pin
   the restatements and, in bench.py, as the ``"kind": "reference"`` CPU baseline.

@@ -14,6 +14,10 @@ Restated call sites (paths relative to /root/reference):
   model/general_recommender/NeuMF.py:69-104    NeuMF graph (see neumf_*)
   model/general_recommender/MLP.py:45-87       MLP graph
   model/general_recommender/LightGCN.py:35-78,132-166   adjacency + propagation + loss
+  model/general_recommender/NGCF.py:94-110,160-202,299-332   NGCF layers, loss, adjacency
+  model/general_recommender/APR.py:92-118       adversarial deltas (l2_normalize * eps)
+  model/social_recommender/SBPR.py:66-92        SBPR quadruple loss with item bias
+  model/general_recommender/SpectralCF.py:37-43,63-91,108-128   spectral operator, layers, loss
 TensorFlow pieces (python/training/{adam,adagrad,rmsprop,momentum,gradient_descent}.py,
 core/kernels/training_ops.cc, python/ops/nn_impl.py, python/ops/losses/losses_impl.py):
   * embedding_lookup gradients are IndexedSlices; several lookups of one variable are
