@@ -1250,6 +1250,15 @@ def run_ours(args):
             except Exception as ex:  # keep the headline line even if a secondary workload fails
                 others[other] = {"error": repr(ex)}
         out["others"] = others
+    if world > 1 and not args.only and name == "bprmf-sharded" and os.environ.get("NRC_BENCH_NO_EVAL", "0") == "0":
+        # BASELINE's metric is "BPR triplets/sec & eval users/sec @1/2/4/8": the evaluator line of the same N (configs[3]:
+        # item table replicated per GPU, users sharded over the ranks -- SURVEY 8e) rides in `others`, as at N = 1
+        import torch
+        torch.cuda.empty_cache()
+        o = measure_synth_eval(4, W, world, rank, windows, with_cpu=False)
+        if rank == 0:
+            keep = ("value", "unit", "steps", "ms_per_step", "e2e", "roofline", "config", "gpu_launches")
+            out["others"] = {"eval-synth": {x: o[x] for x in keep if x in o}}
     clocks.stop()
     if rank == 0:
         out["clocks"] = clocks.summary(windows)
