@@ -48,8 +48,8 @@ def main():
     print()
     print("lazy-Adam run: %s triplets/s, %.3f of the HBM peak (%s)" % (fmt(la["value"]), la["roofline"]["frac"], la["roofline"]["kernel"]))
     print()
-    print("| N | G triplets/s | per GPU | vs N=1 per GPU | kernel us | head sync us | NVLink GB/s per GPU and direction | of 770 | e2e G/s |")
-    print("|---|---|---|---|---|---|---|---|---|")
+    print("| N | G triplets/s | per GPU | vs N=1 per GPU | kernel us | head sync us | NVLink GB/s per GPU and direction | of 770 | e2e G/s | evaluator users/s (configs[3], users sharded) |")
+    print("|---|---|---|---|---|---|---|---|---|---|")
     base = d["value"]
     for n, name in ((1, "r2_bench_n1.json"), (2, "r2_bench_n2.json"), (8, "r2_bench_n8.json")):
         if not os.path.isfile(os.path.join(HERE, name)):
@@ -57,10 +57,11 @@ def main():
         x = load(name)
         r = x["roofline"]
         nv = r.get("nvlink", {})
-        print("| %d | %.3f | %.3f | %.2f | %.0f | %.0f | %s | %s | %.3f |" % (
+        ev = x.get("others", {}).get("eval-synth")
+        print("| %d | %.3f | %.3f | %.2f | %.0f | %.0f | %s | %s | %.3f | %s |" % (
             n, x["value"] / 1e9, x["value"] / 1e9 / n, x["value"] / n / base, r["launch_us"], r["replicated_head"]["sync_us_mean"],
             "%.0f" % nv["GBps_per_gpu_per_direction"] if nv else "-", "%.2f" % nv["of_measured_peer_copy_770_GBps"] if nv else "-",
-            x["e2e"]["value"] / 1e9))
+            x["e2e"]["value"] / 1e9, fmt(ev["value"]) if ev else "(line predates the evaluator entry)"))
 
 
 if __name__ == "__main__":
