@@ -612,6 +612,22 @@ class LightgcnGowalla:
         per_step = 2 * self.n_layers * spmm + n * self.dim * 4 * 6
         return k * per_step, "per step: 6 SpMM x (nnz*8 + indptr + 2*N*d*4) + dense Adam N*d*4*6 B (SURVEY 8d: 0.41 GB)"
 
+    def l2_gather(self, seconds):
+        """The bound that matters for this kernel: the graph and the table are L2-resident (DRAM traffic = the compulsory
+        50 MB), and every non-zero gathers a dim*4-byte row out of L2.  L2 -> SM bytes per product vs the L2 -> SM rate
+        measured on this GPU with TMA loads (DESIGN.md 3a ablation: 12.3 TB/s = ~6 300 B/clk)."""
+        n, nnz = self.A.shape[0], self.A.nnz
+        nbytes = nnz * self.dim * 4 + nnz * 8 + (n + 1) * 8 + n * 4
+        cap = 12.3e12
+        return {"bytes_per_launch": nbytes, "achieved_TBps": nbytes / seconds / 1e12, "cap_TBps": cap / 1e12,
+                "frac": nbytes / seconds / cap,
+                "measured_gather_rates_TBps": {"LDG.128 on L2-resident random 512 B rows": 9.09,
+                                               "cp.async.bulk on the same rows": 6.70},
+                "note": "row gathers nnz*dim*4 B + (col, val) stream + row pointers and order, all served by L2; the cap is the "
+                        "L2->SM rate measured with TMA tile loads in the evaluator ablation (DESIGN.md 3a); the two gather "
+                        "rates are profiles/r2_peer_probe_v2.txt (local, Zipf rows = L2 hits): index-driven row gathers by "
+                        "LDG.128 deliver more than the bulk-copy engine does, which is why this kernel is not bulk-copy fed"}
+
     def spmm_kernel(self):
         from neurec_b200 import ops
         n, nnz = self.A.shape[0], self.A.nnz
@@ -711,7 +727,8 @@ def measure_small(w, K, W, world, rank, windows, with_cpu=True):
         st = graph_time(fn)
         roof = hbm_roofline("spmm_csr_fast_kernel", sb, st, "SURVEY 8(d): nnz*(4 B col + 4 B val) + indptr + N*d*4 B read + written",
                             "the kernel alone: 40 launches in a CUDA graph, CUDA events on the replay stream, best of 5",
-                            {"step_bytes": nbytes / K, "step_note": note, "share_of_step": 6 * st / (ms * 1e-3 / K)})
+                            {"step_bytes": nbytes / K, "step_note": note, "share_of_step": 6 * st / (ms * 1e-3 / K),
+                             "l2_gather": w.l2_gather(st)})
     else:
         kname = "mf_epoch_kernel" if isinstance(w, MfMl100k) else "ncf_epoch_kernel"
         roof = hbm_roofline(kname, nbytes, ms * 1e-3, note,
