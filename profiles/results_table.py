@@ -51,7 +51,7 @@ def main():
     print("| N | G triplets/s | per GPU | vs N=1 per GPU | kernel us | head sync us | NVLink GB/s per GPU and direction | of 770 | e2e G/s | evaluator users/s (configs[3], users sharded) |")
     print("|---|---|---|---|---|---|---|---|---|---|")
     base = d["value"]
-    for n, name in ((1, "r2_bench_n1.json"), (2, "r2_bench_n2.json"), (8, "r2_bench_n8.json")):
+    for n, name in ((1, "r2_bench_n1.json"), (2, "r2_bench_n2.json"), (4, "r2_bench_n4.json"), (8, "r2_bench_n8.json")):
         if not os.path.isfile(os.path.join(HERE, name)):
             continue
         x = load(name)

@@ -73,6 +73,9 @@ def test_multi_gpu_line_communicates():
     nv = d["roofline"]["nvlink"]
     assert abs(nv["remote_item_row_fraction"] - (n - 1) / n) < 1e-9 and nv["GBps_per_gpu_per_direction"] > 0
     assert d["config"]["loss_finite"] is True
+    ev = d.get("others", {}).get("eval-synth")          # BASELINE: "eval users/sec @1/2/4/8" rides in the same line
+    if ev is not None:
+        assert ev["unit"] == "users/s" and ev["value"] > 0 and ev["roofline"]["bound"] == "tensor"
 
 
 def test_argument_parser_accepts_the_drivers_command_lines():
