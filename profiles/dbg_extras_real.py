@@ -37,7 +37,7 @@ def dataset(npz, name):
 
 
 def ndcg10(model):
-    s = model.evaluator.evaluate(model)
+    s = model.evaluate()                # the model's own evaluate(): SpectralCF / NGCF propagate first
     return float(s.split()[4])          # Precision@10 @20 Recall@10 @20 NDCG@10 ...
 
 
@@ -51,6 +51,8 @@ def run(name, model, epoch_fn, epochs):
         if e in (0, epochs // 2, epochs - 1):
             print("%s: epoch %d  %.1f ms  loss %.4f  NDCG@10 %.5f" % (name, e + 1, dt * 1e3, loss, ndcg10(model)), flush=True)
 
+
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
 
 # ---- SBPR on Ciao
 from neurec_b200.model.social_recommender.SBPR import SBPR  # noqa: E402
@@ -69,7 +71,8 @@ AR.SocialAbstractRecommender.__init__ = social_init
 conf = Conf(BASE, recommender="SBPR", learning_rate=0.001, embedding_size=16, learner="adam", loss_function="bpr", num_epochs=1,
             reg_mf=0.01, batch_size=512, init_method="normal", stddev=0.01, verbose=1)
 m = SBPR(None, ds, conf)
-run("SBPR / Ciao (%d samples per epoch, %d steps of 512)" % (m._n, (m._n + 511) // 512), m, lambda: m._train_epoch() / m._n, 12)
+if ONLY in ("", "sbpr"):
+    run("SBPR / Ciao (%d samples per epoch, %d steps of 512)" % (m._n, (m._n + 511) // 512), m, lambda: m._train_epoch() / m._n, 12)
 AR.SocialAbstractRecommender.__init__ = orig
 
 # ---- APR on ml-100k
@@ -79,13 +82,16 @@ conf = Conf(BASE, recommender="APR", learning_rate=0.001, embedding_size=64, lea
             adv_epoch=0, reg=0.0, reg_adv=1.0, batch_size=512, init_method="tnormal", stddev=0.01, verbose=1)
 m = APR(None, ds, conf)
 it = PairwiseSampler(ds, neg_num=1, batch_size=512, shuffle=True)
-run("APR / ml-100k (157 steps of 512)", m, lambda: m._train_epoch(it) / len(it), 30)
+if ONLY in ("", "apr"):
+    run("APR / ml-100k (157 steps of 512)", m, lambda: m._train_epoch(it) / len(it), 30)
 
 # ---- SpectralCF on ml-100k (the operator is a 2 625 x 2 625 eigendecomposition on the host, once)
 from neurec_b200.model.general_recommender.SpectralCF import SpectralCF  # noqa: E402
 conf = Conf(BASE, recommender="SpectralCF", learning_rate=0.001, learner="adam", batch_size=256, num_layers=2, activation="sigmoid",
             embedding_size=100, epochs=1, reg=0.001, loss_function="BPR", dropout=0.0, embed_init_method="xavier_normal",
             weight_init_method="xavier_normal", stddev=0.01, verbose=1)
+if ONLY not in ("", "spectral"):
+    sys.exit(0)
 t0 = time.perf_counter()
 m = SpectralCF(None, ds, conf)
 print("SpectralCF: operator built on the host in %.1f s" % (time.perf_counter() - t0), flush=True)
