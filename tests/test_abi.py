@@ -67,3 +67,20 @@ def test_evaluator_routing_rule():
     assert not ops.use_tensor_core_eval(40981, 32, 20, 29858)        # dim not a multiple of 64
     assert not ops.use_tensor_core_eval(40981, 64, 50, 29858)        # top_k > 31
     assert not ops.use_tensor_core_eval(40981, 64, 20, 128)          # a handful of users
+
+
+def test_documents_name_only_entry_points_that_exist():
+    """Every `nrc_*` identifier DESIGN.md / INTEGRATION.md / README.md mention is declared in include/neurec_b200.h
+    (documentation that drifts from the ABI is caught here)."""
+    import re
+    from neurec_b200 import _lib
+    declared = set(_lib.declared_functions())
+    header = open(_lib.HEADER).read()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for doc in ("DESIGN.md", "INTEGRATION.md", "README.md"):
+        text = open(os.path.join(root, doc)).read()
+        for name in sorted(set(re.findall(r"\bnrc_[a-z0-9_]+\b", text))):
+            if name.endswith("_"):          # a prefix such as `nrc_graph_` / `nrc_ngcf_*` written as a family
+                assert any(d.startswith(name) for d in declared), (doc, name)
+                continue
+            assert name in declared or name in header, (doc, name)
