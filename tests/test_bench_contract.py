@@ -84,3 +84,16 @@ def test_argument_parser_accepts_the_drivers_command_lines():
         assert out.returncode == 0
         for flag in ("--gpus", "--steps", "--warmup", "--impl", "--workload"):
             assert flag in out.stdout + out.stderr
+
+
+def test_documents_cite_profiles_that_exist():
+    """Every profiles/<file> (or bare r2_*.{json,txt} name) DESIGN.md and profiles/README.md cite is committed."""
+    import re
+    have = set(os.listdir(os.path.join(ROOT, "profiles")))
+    missing = []
+    for doc in ("DESIGN.md", os.path.join("profiles", "README.md"), "INTEGRATION.md"):
+        text = open(os.path.join(ROOT, doc)).read()
+        names = set(re.findall(r"profiles/([A-Za-z0-9_.]+\.(?:json|txt|py|sh|cu))", text))
+        names |= set(re.findall(r"`(r[12]_[A-Za-z0-9_.]+\.(?:json|txt|sh))`", text))
+        missing += [(doc, n) for n in sorted(names) if n not in have]
+    assert not missing, missing
