@@ -19,6 +19,8 @@ What is captured (all from the real reference code, imported through oracle.impo
   ciao_split.npz / kat_ciao.json   (``python tests/golden/make_golden.py ciao``) dataset/Ciao_u5_s2 as loaded by
                       data.Dataset + SocialAbstractRecommender (trust CSR), SBPR._get_SocialItemsSet checksums and
                       4 000 (user, social item, negative, s_uk) samples of one real SBPR._get_pairwise_all_data epoch.
+  kat_time_order.json   (same command) _generative_time_order_positive_items (data/sampler.py:42-68) run by the reference on the
+                      by-time train sequences of that split, high_order 1..3: lengths and crc32 of its four outputs.
   kat_split_ml100k.npz  (``python tests/golden/make_golden.py split``) data/utils.py split_by_ratio(0.8) and split_by_loo with
                       by_time=True on ml-100k.rating: one train/test bit per interaction in file order.
   kat_gowalla.json / kat_gowalla_adj.npz   LightGCN.create_adj_mat('pre') (LightGCN.py:35-78) on that
@@ -315,6 +317,33 @@ def ciao():
     print("ciao fixtures written to", OUT)
 
 
+def by_time_dict(users, items, times, train_flags):
+    """{dense user id: train items ordered by (time, file position)} -- shared by make_golden.py and tests/test_extras.py."""
+    uid = np.unique(users, return_inverse=True)[1]
+    keep = np.nonzero(train_flags)[0]
+    order = keep[np.lexsort((keep, times[keep], uid[keep]))]
+    out = {}
+    for e in order:
+        out.setdefault(int(uid[e]), []).append(int(items[e]))
+    return out
+
+
+def time_order(data, train_flags):
+    """data/sampler.py:42-68 run by the REAL reference on the by-time train sequences of the split above."""
+    import zlib
+    from data.sampler import _generative_time_order_positive_items as gen
+    d = by_time_dict(data["user"].values, data["item"].values, data["time"].values, train_flags)
+    res = {}
+    for ho in (1, 2, 3):
+        lens, users, recent, nxt = gen(d, high_order=ho)
+        res[str(ho)] = {"n": len(users), "lens_crc32": int(zlib.crc32(np.asarray(lens, np.int64).tobytes())),
+                        "users_crc32": int(zlib.crc32(np.asarray(users, np.int32).tobytes())),
+                        "recent_crc32": int(zlib.crc32(np.asarray(recent, np.int32).tobytes())),
+                        "next_crc32": int(zlib.crc32(np.asarray(nxt, np.int32).tobytes()))}
+    with open(os.path.join(OUT, "kat_time_order.json"), "w") as fo:
+        json.dump(res, fo, indent=1)
+
+
 def split():
     """the reference's own split_by_ratio / split_by_loo (data/utils.py:59-106) with by_time=True
     on dataset/ml-100k.rating -> one train/test bit per interaction in FILE order (bit-packed)."""
@@ -338,7 +367,9 @@ def split():
         out[name + "_train"] = np.int64(len(train))
     data = load_data(path, "\t", cols)                       # the inputs of the split, in file order (raw user ids, times)
     np.savez_compressed(os.path.join(OUT, "kat_split_ml100k.npz"), n=np.int64(len(data)),
-                        user=data["user"].values.astype(np.uint16), time=data["time"].values.astype(np.int32), **out)
+                        user=data["user"].values.astype(np.uint16), item=data["item"].values.astype(np.uint16),
+                        time=data["time"].values.astype(np.int32), **out)
+    time_order(data, np.unpackbits(out["ratio"])[:len(data)])
     print("split fixtures written to", OUT, {k: int(v) for k, v in out.items() if k.endswith("_train")})
 
 

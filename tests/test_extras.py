@@ -290,3 +290,29 @@ def test_random_split_restatement_contract(split_golden):
         first_half[order[start:start + c // 2]] = True
         start += c
     assert abs(a[first_half].mean() - a[~first_half].mean()) < 0.01
+
+
+def test_time_order_instances_equal_the_reference_on_ml100k(split_golden):
+    """_generative_time_order_positive_items run by the REAL reference (tests/golden/make_golden.py split ->
+    kat_time_order.json) on the by-time train sequences of the ratio-0.8 split of ml-100k: our numpy-window
+    restatement yields the same lengths, users, windows and next items (crc32) for high_order 1, 2, 3."""
+    from neurec_b200.data.sampler import _generative_time_order_positive_items as gen
+    z = np.load(os.path.join(GOLDEN, "kat_split_ml100k.npz"))
+    with open(os.path.join(GOLDEN, "kat_time_order.json")) as f:
+        kat = json.load(f)
+    users, items, times = z["user"].astype(np.int64), z["item"].astype(np.int64), z["time"].astype(np.int64)
+    flags = split_golden["ratio"]
+    uid = np.unique(users, return_inverse=True)[1]                      # same construction as make_golden.by_time_dict
+    keep = np.nonzero(flags)[0]
+    order = keep[np.lexsort((keep, times[keep], uid[keep]))]
+    d = {}
+    for e in order:
+        d.setdefault(int(uid[e]), []).append(int(items[e]))
+    for ho in (1, 2, 3):
+        lens, us, recent, nxt = gen(d, high_order=ho)
+        want = kat[str(ho)]
+        assert len(us) == want["n"]
+        assert zlib.crc32(np.asarray(lens, np.int64).tobytes()) == want["lens_crc32"]
+        assert zlib.crc32(np.asarray(us, np.int32).tobytes()) == want["users_crc32"]
+        assert zlib.crc32(np.ascontiguousarray(recent, dtype=np.int32).tobytes()) == want["recent_crc32"]
+        assert zlib.crc32(np.asarray(nxt, np.int32).tobytes()) == want["next_crc32"]
