@@ -19,6 +19,8 @@ What is captured (all from the real reference code, imported through oracle.impo
   ciao_split.npz / kat_ciao.json   (``python tests/golden/make_golden.py ciao``) dataset/Ciao_u5_s2 as loaded by
                       data.Dataset + SocialAbstractRecommender (trust CSR), SBPR._get_SocialItemsSet checksums and
                       4 000 (user, social item, negative, s_uk) samples of one real SBPR._get_pairwise_all_data epoch.
+  kat_spectral.npz      (``python tests/golden/make_golden.py spectral``) SpectralCF's adjacency / degree / Laplacian methods
+                      (SpectralCF.py:108-128) run by the real class on a 14 x 19 graph + the operator U U^T + U diag(lamda) U^T.
   kat_time_order.json   (same command) _generative_time_order_positive_items (data/sampler.py:42-68) run by the reference on the
                       by-time train sequences of that split, high_order 1..3: lengths and crc32 of its four outputs.
   kat_split_ml100k.npz  (``python tests/golden/make_golden.py split``) data/utils.py split_by_ratio(0.8) and split_by_loo with
@@ -344,6 +346,31 @@ def time_order(data, train_flags):
         json.dump(res, fo, indent=1)
 
 
+def spectral():
+    """SpectralCF.adjacient_matrix / degree_matrix / laplacian_matrix (SpectralCF.py:108-128) run by the REAL reference class
+    on a small bipartite graph (the methods need only self.graph / num_users / num_items), then the operator of :41-42,67-69."""
+    import importlib
+    import types
+    import oracle
+    cwd = oracle.import_reference()
+    os.chdir(cwd)
+    m = importlib.import_module("model.general_recommender.SpectralCF").SpectralCF
+    rs = np.random.RandomState(7)
+    nu, ni = 14, 19
+    graph = (rs.rand(nu, ni) < 0.2).astype(np.float32)
+    graph[np.arange(nu), rs.randint(0, ni, nu)] = 1.0               # no empty user
+    f = types.SimpleNamespace(graph=graph, num_users=nu, num_items=ni)
+    f.A = m.adjacient_matrix(f, self_connection=True)
+    f.D = m.degree_matrix(f)
+    L = m.laplacian_matrix(f, normalized=True)
+    lamda, U = np.linalg.eig(L)
+    lam = np.diag(lamda)
+    A_hat = (np.dot(U, U.T) + np.dot(np.dot(U, lam), U.T)).astype(np.float32)       # SpectralCF.py:67-69
+    np.savez_compressed(os.path.join(OUT, "kat_spectral.npz"), graph=graph.astype(np.uint8), A=f.A.astype(np.float32),
+                        D=f.D.astype(np.float32), L=L.astype(np.float32), A_hat=A_hat)
+    print("spectral fixture written", A_hat.shape, A_hat.dtype)
+
+
 def split():
     """the reference's own split_by_ratio / split_by_loo (data/utils.py:59-106) with by_time=True
     on dataset/ml-100k.rating -> one train/test bit per interaction in FILE order (bit-packed)."""
@@ -376,6 +403,8 @@ def split():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "split":
         split()
+    elif len(sys.argv) > 1 and sys.argv[1] == "spectral":
+        spectral()
     elif len(sys.argv) > 1 and sys.argv[1] == "gowalla":
         gowalla()
     elif len(sys.argv) > 1 and sys.argv[1] == "ciao":

@@ -316,3 +316,25 @@ def test_time_order_instances_equal_the_reference_on_ml100k(split_golden):
         assert zlib.crc32(np.asarray(us, np.int32).tobytes()) == want["users_crc32"]
         assert zlib.crc32(np.ascontiguousarray(recent, dtype=np.int32).tobytes()) == want["recent_crc32"]
         assert zlib.crc32(np.asarray(nxt, np.int32).tobytes()) == want["next_crc32"]
+
+
+def test_spectral_operator_equals_the_reference_methods():
+    """SpectralCF.adjacient_matrix / degree_matrix / laplacian_matrix of the REAL reference class on a 14 x 19 graph
+    (kat_spectral.npz) and the operator built from their eigendecomposition: the oracle's restatement and the plug-in's
+    host-side construction reproduce A, D, L exactly and A_hat to the rounding of numpy's eig (same LAPACK here: equal)."""
+    from neurec_b200.model.general_recommender.SpectralCF import spectral_operator
+    z = np.load(os.path.join(GOLDEN, "kat_spectral.npz"))
+    graph = z["graph"].astype(np.float32)
+    nu, ni = graph.shape
+    train = sp.csr_matrix(graph)
+    got = spectral_operator(train)
+    want = z["A_hat"]
+    assert got.shape == want.shape == (nu + ni, nu + ni)
+    assert np.abs(got - want).max() < 1e-5 * np.abs(want).max()
+    ora = tf_math.spectralcf_a_hat(train.indptr, train.indices, nu, ni)
+    assert np.abs(ora - want).max() < 1e-5 * np.abs(want).max()
+    # the pieces, restated here the way both constructions build them
+    A = np.identity(nu + ni, dtype=np.float32); A[:nu, nu:] += graph; A[nu:, :nu] += graph.T
+    assert np.array_equal(A, z["A"]) and np.array_equal(A.sum(1), z["D"])
+    L = np.identity(nu + ni, dtype=np.float32) - np.dot(np.diag(np.power(A.sum(1), -1)), A)
+    assert np.array_equal(L, z["L"])
