@@ -338,3 +338,42 @@ def test_abstract_recommender_wires_evaluator_and_logger(ml100k, tmp_path, monke
         model.build_graph()
     with pytest.raises(NotImplementedError):
         model.predict([0], None)
+
+
+REF_DATA = "/root/reference/dataset"
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF_DATA, "ml-100k.rating")), reason="the reference's dataset files are not here")
+@pytest.mark.parametrize("name,golden", [("ml-100k", "ml100k_split.npz"), ("Ciao_u5_s2", "ciao_split.npz")])
+def test_dataset_loader_reproduces_the_reference_split(tmp_path, monkeypatch, name, golden):
+    """Our data.Dataset (load -> filter -> per-user ratio split under np.random.seed(2018) -> id remap -> CSR,
+    data/dataset.py:75-210 + data/utils.py:24-80) against the train / test matrices the REAL reference's Dataset built
+    from the same file (tests/golden/*_split.npz); for Ciao also SocialAbstractRecommender's trust matrix
+    (AbstractRecommender.py:54-74).  CPU only; runs where the reference's dataset directory exists."""
+    import shutil
+    from neurec_b200.data import Dataset
+    from neurec_b200.util import Configurator
+    data = tmp_path / "dataset"
+    data.mkdir()
+    shutil.copy(os.path.join(REF_DATA, name + ".rating"), data / (name + ".rating"))
+    for f in ("NeuRec.properties", "conf"):
+        os.symlink(os.path.join(ROOT, f), tmp_path / f)
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(sys, "argv", ["main.py", "--data.input.path=%s" % data, "--data.input.dataset=%s" % name])
+    np.random.seed(2018)                                   # main.py:10, as in make_golden.py
+    conf = Configurator("NeuRec.properties", default_section="hyperparameters")
+    ds = Dataset(conf)
+    z = np.load(os.path.join(GOLDEN, golden))
+    assert (ds.num_users, ds.num_items) == (int(z["num_users"]), int(z["num_items"]))
+    for mat, p, i in ((ds.train_matrix, "train_indptr", "train_indices"), (ds.test_matrix, "test_indptr", "test_indices")):
+        m = mat.tocsr(); m.sort_indices()
+        assert np.array_equal(m.indptr, z[p].astype(m.indptr.dtype)) and np.array_equal(m.indices, z[i].astype(m.indices.dtype)), (name, p)
+    if name == "Ciao_u5_s2":
+        from neurec_b200.model.AbstractRecommender import SocialAbstractRecommender
+        shutil.copy(os.path.join(REF_DATA, name + ".uu"), data / (name + ".uu"))
+        monkeypatch.setattr(sys, "argv", sys.argv + ["--recommender=SBPR", "--social_file=%s" % (data / (name + ".uu"))])
+        conf = Configurator("NeuRec.properties", default_section="hyperparameters")
+        model = SocialAbstractRecommender(ds, conf)
+        t = model.social_matrix.tocsr(); t.sort_indices()
+        assert np.array_equal(t.indptr, z["trust_indptr"].astype(t.indptr.dtype))
+        assert np.array_equal(t.indices, z["trust_indices"].astype(t.indices.dtype))
