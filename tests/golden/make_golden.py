@@ -19,6 +19,8 @@ What is captured (all from the real reference code, imported through oracle.impo
   ciao_split.npz / kat_ciao.json   (``python tests/golden/make_golden.py ciao``) dataset/Ciao_u5_s2 as loaded by
                       data.Dataset + SocialAbstractRecommender (trust CSR), SBPR._get_SocialItemsSet checksums and
                       4 000 (user, social item, negative, s_uk) samples of one real SBPR._get_pairwise_all_data epoch.
+  kat_neg_eval.json     (``python tests/golden/make_golden.py neg``) ProxyEvaluator.evaluate() of the reference with a negative-candidate
+                      dict (rec.evaluate.neg > 0 branch, cpp/uni_evaluator.py:123-131) on the ml-100k split.
   kat_spectral.npz      (``python tests/golden/make_golden.py spectral``) SpectralCF's adjacency / degree / Laplacian methods
                       (SpectralCF.py:108-128) run by the real class on a 14 x 19 graph + the operator U U^T + U diag(lamda) U^T.
   kat_time_order.json   (same command) _generative_time_order_positive_items (data/sampler.py:42-68) run by the reference on the
@@ -346,6 +348,36 @@ def time_order(data, train_flags):
         json.dump(res, fo, indent=1)
 
 
+def neg_eval():
+    """rec.evaluate.neg > 0 (evaluator/backend/cpp/uni_evaluator.py:123-131): the REAL reference's ProxyEvaluator with a
+    negative-candidate dict on the ml-100k split; inputs by the recipe of tests/test_surface.py::test_candidate_ranking_branch."""
+    import oracle
+    cwd = oracle.import_reference()
+    os.chdir(cwd)
+    from evaluator import ProxyEvaluator
+    z = np.load(os.path.join(OUT, "ml100k_split.npz"))
+    nu, ni = int(z["num_users"]), int(z["num_items"])
+    rows = lambda p, i: {u: z[i][z[p][u]:z[p][u + 1]].astype(int).tolist() for u in range(nu) if z[p][u + 1] > z[p][u]}
+    train_d, test_d = rows("train_indptr", "train_indices"), rows("test_indptr", "test_indices")
+    rs = np.random.RandomState(2)
+    neg_d = {}
+    for u in test_d:
+        seen = set(train_d[u]) | set(test_d[u])
+        neg_d[u] = [int(i) for i in rs.choice(ni, 60) if i not in seen][:40]
+    U = (rs.randn(nu, 16)).astype(np.float32); V = (rs.randn(ni, 16)).astype(np.float32)
+
+    class _Model:
+        def predict(self, user_ids, candidate_items=None):           # MF.py:120-134
+            if candidate_items is None:
+                return np.matmul(U[user_ids], V.T)
+            return [np.squeeze(np.matmul(U[u], V[np.asarray(c)].T)) for u, c in zip(user_ids, candidate_items)]
+    ev = ProxyEvaluator(train_d, test_d, neg_d, metric=["Recall", "NDCG"], group_view=None, top_k=10, batch_size=300, num_thread=8)
+    res = {"info": ev.metrics_info(), "eval": ev.evaluate(_Model())}
+    with open(os.path.join(OUT, "kat_neg_eval.json"), "w") as fo:
+        json.dump(res, fo, indent=1)
+    print("neg-eval fixture written:", res["eval"][:60])
+
+
 def spectral():
     """SpectralCF.adjacient_matrix / degree_matrix / laplacian_matrix (SpectralCF.py:108-128) run by the REAL reference class
     on a small bipartite graph (the methods need only self.graph / num_users / num_items), then the operator of :41-42,67-69."""
@@ -405,6 +437,8 @@ if __name__ == "__main__":
         split()
     elif len(sys.argv) > 1 and sys.argv[1] == "spectral":
         spectral()
+    elif len(sys.argv) > 1 and sys.argv[1] == "neg":
+        neg_eval()
     elif len(sys.argv) > 1 and sys.argv[1] == "gowalla":
         gowalla()
     elif len(sys.argv) > 1 and sys.argv[1] == "ciao":

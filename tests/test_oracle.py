@@ -335,3 +335,35 @@ def test_torch_timing_port_follows_the_parity_oracle(ml100k):
         lb = b.step(u.tolist(), i.tolist(), j.tolist())
         assert abs(float(la[0]) - lb) < 1e-3 * max(1.0, abs(lb))
     assert np.abs(a.e0 - b.e0.numpy()).max() < 5e-5
+
+
+def test_candidate_ranking_model_equals_the_reference(ml100k):
+    """rec.evaluate.neg > 0 (evaluator/backend/cpp/uni_evaluator.py:123-131): the padded-matrix model of that branch the
+    GPU test compares the product with (tests/test_surface.py::test_candidate_ranking_branch) reproduces the string the
+    REAL reference's ProxyEvaluator printed for the same inputs (tests/golden/kat_neg_eval.json)."""
+    import json
+    import os
+    d = ml100k
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_neg_eval.json")) as f:
+        kat = json.load(f)
+    nu, ni = d["num_users"], d["num_items"]
+    rows_of = lambda p, i: {u: d[i][d[p][u]:d[p][u + 1]].astype(int).tolist() for u in range(nu) if d[p][u + 1] > d[p][u]}
+    train_d, test_d = rows_of("train_indptr", "train_indices"), rows_of("test_indptr", "test_indices")
+    rs = np.random.RandomState(2)
+    neg_d = {}
+    for u in test_d:
+        seen = set(train_d[u]) | set(test_d[u])
+        neg_d[u] = [int(i) for i in rs.choice(ni, 60) if i not in seen][:40]
+    U = (rs.randn(nu, 16)).astype(np.float32); V = (rs.randn(ni, 16)).astype(np.float32)
+    rows = []
+    for u in test_d:
+        c = list(test_d[u]) + neg_d[u]
+        s = np.matmul(U[u], V[c].T)[None, :].astype(np.float32)
+        pad = np.full((1, max(10, len(c))), -np.inf, np.float32); pad[0, :len(c)] = s
+        ip, ix = oracle.lists_to_csr([range(len(test_d[u]))])
+        rows.append(oracle.evaluate_matrix(pad, ip, ix, [2, 4], 10)[0])
+    got = np.mean(np.stack(rows), axis=0, dtype=np.float32)
+    want = np.array([float(x) for x in kat["eval"].split()], np.float32)
+    assert got.shape == want.shape == (20,)
+    assert np.abs(got - want).max() < 5e-8 + 1e-8          # the string carries 8 decimals
+    assert "\t".join(("%.8f" % x).ljust(12) for x in got) == kat["eval"]
