@@ -19,6 +19,8 @@ What is captured (all from the real reference code, imported through oracle.impo
   ciao_split.npz / kat_ciao.json   (``python tests/golden/make_golden.py ciao``) dataset/Ciao_u5_s2 as loaded by
                       data.Dataset + SocialAbstractRecommender (trust CSR), SBPR._get_SocialItemsSet checksums and
                       4 000 (user, social item, negative, s_uk) samples of one real SBPR._get_pairwise_all_data epoch.
+  kat_adjacency.json    (``python tests/golden/make_golden.py adjacency``) LightGCN.create_adj_mat for all five adj_type values and
+                      NGCF.get_adj_mat('norm') run by the reference classes on the ml-100k split (nnz, crc32, sums).
   kat_neg_eval.json     (``python tests/golden/make_golden.py neg``) ProxyEvaluator.evaluate() of the reference with a negative-candidate
                       dict (rec.evaluate.neg > 0 branch, cpp/uni_evaluator.py:123-131) on the ml-100k split.
   kat_spectral.npz      (``python tests/golden/make_golden.py spectral``) SpectralCF's adjacency / degree / Laplacian methods
@@ -378,6 +380,43 @@ def neg_eval():
     print("neg-eval fixture written:", res["eval"][:60])
 
 
+def adjacency():
+    """LightGCN.create_adj_mat for every adj_type (LightGCN.py:35-78) and NGCF.get_adj_mat('norm') (NGCF.py:288-319) run by
+    the REAL reference classes on the ml-100k split: nnz, crc32 of the sorted-CSR index / fp32 value arrays, fp64 sum."""
+    import importlib
+    import types
+    import zlib
+    import scipy.sparse as sp
+    import oracle
+    cwd = oracle.import_reference()
+    os.chdir(cwd)
+    z = np.load(os.path.join(OUT, "ml100k_split.npz"))
+    nu, ni = int(z["num_users"]), int(z["num_items"])
+    users = np.repeat(np.arange(nu), np.diff(z["train_indptr"])).tolist()
+    items = z["train_indices"].astype(int).tolist()
+
+    def digest(A):
+        A = A.tocoo().astype(np.float32).tocsr()
+        A.sort_indices()
+        return {"nnz": int(A.nnz), "indptr_crc32": int(zlib.crc32(A.indptr.astype(np.int64).tobytes())),
+                "indices_crc32": int(zlib.crc32(A.indices.astype(np.int32).tobytes())),
+                "data_crc32": int(zlib.crc32(A.data.astype(np.float32).tobytes())), "sum_f64": float(A.data.astype(np.float64).sum())}
+    res = {}
+    L = importlib.import_module("model.general_recommender.LightGCN").LightGCN
+    ds = types.SimpleNamespace(get_train_interactions=lambda: (users, items))
+    f = types.SimpleNamespace(dataset=ds, n_users=nu, n_items=ni)
+    for t in ("plain", "norm", "gcmc", "pre", "mean"):
+        res["lightgcn_" + t] = digest(L.create_adj_mat(f, t))
+    N = importlib.import_module("model.general_recommender.NGCF").NGCF
+    graph = sp.csr_matrix((np.ones(len(users), np.float32), (users, items)), shape=(nu, ni)).toarray()
+    g = types.SimpleNamespace(num_users=nu, num_items=ni, graph=graph, adj_type="norm", logger=types.SimpleNamespace(info=lambda *a: None))
+    g.normalized_adj_single = lambda adj: N.normalized_adj_single(g, adj)
+    res["ngcf_norm"] = digest(N.get_adj_mat(g))
+    with open(os.path.join(OUT, "kat_adjacency.json"), "w") as fo:
+        json.dump(res, fo, indent=1)
+    print("adjacency fixture written:", {k: v["nnz"] for k, v in res.items()})
+
+
 def spectral():
     """SpectralCF.adjacient_matrix / degree_matrix / laplacian_matrix (SpectralCF.py:108-128) run by the REAL reference class
     on a small bipartite graph (the methods need only self.graph / num_users / num_items), then the operator of :41-42,67-69."""
@@ -439,6 +478,8 @@ if __name__ == "__main__":
         spectral()
     elif len(sys.argv) > 1 and sys.argv[1] == "neg":
         neg_eval()
+    elif len(sys.argv) > 1 and sys.argv[1] == "adjacency":
+        adjacency()
     elif len(sys.argv) > 1 and sys.argv[1] == "gowalla":
         gowalla()
     elif len(sys.argv) > 1 and sys.argv[1] == "ciao":

@@ -367,3 +367,29 @@ def test_candidate_ranking_model_equals_the_reference(ml100k):
     assert got.shape == want.shape == (20,)
     assert np.abs(got - want).max() < 5e-8 + 1e-8          # the string carries 8 decimals
     assert "\t".join(("%.8f" % x).ljust(12) for x in got) == kat["eval"]
+
+
+def test_adjacency_restatements_equal_the_reference_classes(ml100k):
+    """LightGCN.create_adj_mat for 'plain', 'norm', 'gcmc', 'pre', 'mean' (LightGCN.py:35-78) and NGCF.get_adj_mat('norm')
+    (NGCF.py:288-319) run by the REAL reference classes on the ml-100k split (tests/golden/kat_adjacency.json): the
+    oracle's restatements give the same sparsity pattern and the same fp32 values, crc for crc."""
+    import json
+    import os
+    import zlib
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_adjacency.json")) as f:
+        kat = json.load(f)
+    d = ml100k
+    nu, ni = d["num_users"], d["num_items"]
+
+    def digest(A):
+        A = A.tocoo().astype(np.float32).tocsr()
+        A.sort_indices()
+        return (int(A.nnz), zlib.crc32(A.indptr.astype(np.int64).tobytes()), zlib.crc32(A.indices.astype(np.int32).tobytes()),
+                zlib.crc32(A.data.astype(np.float32).tobytes()))
+    for t in ("plain", "norm", "gcmc", "pre", "mean"):
+        w = kat["lightgcn_" + t]
+        got = digest(tf_math.lightgcn_adj(d["train_indptr"], d["train_indices"], nu, ni, t))
+        assert got == (w["nnz"], w["indptr_crc32"], w["indices_crc32"], w["data_crc32"]), t
+    w = kat["ngcf_norm"]
+    got = digest(tf_math.ngcf_adj(d["train_indptr"], d["train_indices"], nu, ni, "norm"))
+    assert got == (w["nnz"], w["indptr_crc32"], w["indices_crc32"], w["data_crc32"])
