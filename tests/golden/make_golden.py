@@ -19,6 +19,8 @@ What is captured (all from the real reference code, imported through oracle.impo
   ciao_split.npz / kat_ciao.json   (``python tests/golden/make_golden.py ciao``) dataset/Ciao_u5_s2 as loaded by
                       data.Dataset + SocialAbstractRecommender (trust CSR), SBPR._get_SocialItemsSet checksums and
                       4 000 (user, social item, negative, s_uk) samples of one real SBPR._get_pairwise_all_data epoch.
+  kat_sampler_layout.json (``python tests/golden/make_golden.py layout``) one unshuffled epoch of the reference's PointwiseSampler
+                      (neg_num=2) and PairwiseSampler (neg_num=3) on the ml-100k split: crc32 of users / labels / positives, shapes.
   kat_adjacency.json    (``python tests/golden/make_golden.py adjacency``) LightGCN.create_adj_mat for all five adj_type values and
                       NGCF.get_adj_mat('norm') run by the reference classes on the ml-100k split (nnz, crc32, sums).
   kat_neg_eval.json     (``python tests/golden/make_golden.py neg``) ProxyEvaluator.evaluate() of the reference with a negative-candidate
@@ -417,6 +419,37 @@ def adjacency():
     print("adjacency fixture written:", {k: v["nnz"] for k, v in res.items()})
 
 
+def sampler_layout():
+    """One unshuffled epoch of the REAL PointwiseSampler (neg_num=2) and PairwiseSampler (neg_num=3) on the ml-100k split
+    (data/sampler.py:93-213): the layout -- who sits where -- as crc32s; the negatives themselves are glibc rand() draws."""
+    import zlib
+    out = json.loads(fresh(
+        "import numpy as np, random, zlib\n"
+        "np.random.seed(2018); random.seed(2018)\n"
+        "from util import Configurator\n"
+        "from data.dataset import Dataset\n"
+        "from data import PairwiseSampler, PointwiseSampler\n"
+        "conf = Configurator('NeuRec.properties', default_section='hyperparameters')\n"
+        "ds = Dataset(conf)\n"
+        "train = ds.get_user_train_dict()\n"
+        "crc = lambda a, t: int(zlib.crc32(np.asarray(a, dtype=t).tobytes()))\n"
+        "U, I, L = [], [], []\n"
+        "for u, i, l in PointwiseSampler(ds, neg_num=2, batch_size=4096, shuffle=False): U += u; I += i; L += l\n"
+        "n_pos = sum(len(v) for v in train.values())\n"
+        "ok = all(I[e] not in train[U[e]] for e in range(n_pos, len(U)))\n"
+        "res = {'n': len(U), 'n_pos': n_pos, 'users_crc32': crc(U, np.int32), 'labels_crc32': crc(L, np.float32),\n"
+        "       'pos_items_crc32': crc(I[:n_pos], np.int32), 'negatives_outside_train': bool(ok)}\n"
+        "PU, PP, PN = [], [], []\n"
+        "for u, p, n in PairwiseSampler(ds, neg_num=3, batch_size=4096, shuffle=False): PU += u; PP += p; PN += n\n"
+        "res.update({'pair_n': len(PU), 'pair_users_crc32': crc(PU, np.int32), 'pair_pos_crc32': crc(PP, np.int32),\n"
+        "            'pair_neg_shape': list(np.asarray(PN).shape),\n"
+        "            'pair_negatives_outside_train': bool(all(j not in train[u] for u, row in zip(PU, PN) for j in row))})\n"
+        "print(json.dumps(res))").strip().splitlines()[-1])
+    with open(os.path.join(OUT, "kat_sampler_layout.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("sampler layout fixture written:", out)
+
+
 def spectral():
     """SpectralCF.adjacient_matrix / degree_matrix / laplacian_matrix (SpectralCF.py:108-128) run by the REAL reference class
     on a small bipartite graph (the methods need only self.graph / num_users / num_items), then the operator of :41-42,67-69."""
@@ -480,6 +513,8 @@ if __name__ == "__main__":
         neg_eval()
     elif len(sys.argv) > 1 and sys.argv[1] == "adjacency":
         adjacency()
+    elif len(sys.argv) > 1 and sys.argv[1] == "layout":
+        sampler_layout()
     elif len(sys.argv) > 1 and sys.argv[1] == "gowalla":
         gowalla()
     elif len(sys.argv) > 1 and sys.argv[1] == "ciao":

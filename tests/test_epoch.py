@@ -72,3 +72,30 @@ def test_epoch_build_layouts(ml100k):
     n = len(ti)
     assert np.array_equal(i3[:n], ti) and np.array_equal(i3[n:2 * n], neg[:, 0]) and np.array_equal(i3[2 * n:], neg[:, 1])
     assert np.array_equal(u3, np.tile(pos_users, 3))
+
+
+def test_unshuffled_epoch_layout_equals_the_reference_samplers(ml100k):
+    """One unshuffled epoch of the REAL PointwiseSampler (neg_num=2) and PairwiseSampler (neg_num=3) on the ml-100k split
+    (tests/golden/kat_sampler_layout.json): the restated epoch (oracle.epoch_build, which the device kernels match bit for
+    bit) puts the same users, labels and positives in the same places; its negatives (another stream) obey the same rule."""
+    import json
+    import os
+    import zlib
+    import oracle
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_sampler_layout.json")) as f:
+        kat = json.load(f)
+    d = ml100k
+    tp, ti, ni = d["train_indptr"], d["train_indices"], d["num_items"]
+    pos_users = np.repeat(np.arange(d["num_users"], dtype=np.int32), np.diff(tp))
+    crc = lambda a, t: zlib.crc32(np.asarray(a, dtype=t).tobytes())
+    u, i, lab = oracle.epoch_build(tp, ti, pos_users, ti, 2, ni, False, False, 2018, 0)
+    n_pos = len(pos_users)
+    assert len(u) == kat["n"] and n_pos == kat["n_pos"]
+    assert crc(u, np.int32) == kat["users_crc32"] and crc(lab, np.float32) == kat["labels_crc32"]
+    assert crc(i[:n_pos], np.int32) == kat["pos_items_crc32"]
+    rows = [set(ti[tp[x]:tp[x + 1]].tolist()) for x in range(d["num_users"])]
+    assert all(int(i[e]) not in rows[u[e]] for e in range(n_pos, len(u)))
+    pu, pp, pn = oracle.epoch_build(tp, ti, pos_users, ti, 3, ni, True, False, 2018, 0)
+    assert len(pu) == kat["pair_n"] and list(pn.shape) == kat["pair_neg_shape"]
+    assert crc(pu, np.int32) == kat["pair_users_crc32"] and crc(pp, np.int32) == kat["pair_pos_crc32"]
+    assert all(int(j) not in rows[x] for x, r in zip(pu, pn) for j in r)
