@@ -4,8 +4,10 @@ Parity status: UNPINNED at the TensorFlow boundary.  tensorflow==1.12.3 (require
 the reference) is a third-party dependency that is neither vendored in /root/reference nor
 installable here (no network, Python 3.12), and the reference ships no tests or golden values
 for it.  The arithmetic below restates TF's published algorithms; every function cites the
-reference call site it stands in for.  What IS pinned: the formulas agree with closed-form
-gradients checked by finite differences in tests/test_oracle.py.
+reference call site it stands in for.  What IS checked independently: every hand-derived gradient
+agrees with torch.autograd on the same graphs (tests/test_oracle_autograd.py) and with finite
+differences (tests/test_oracle.py, tests/test_extras.py); the momentum / Adam / Adagrad recursions
+agree with torch.optim where both libraries define the same rule.
 
 Restated call sites (paths relative to /root/reference):
   model/general_recommender/MF.py:54-76        BPRMF / pointwise "GMF" graph
